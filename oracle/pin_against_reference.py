@@ -216,7 +216,8 @@ def main():
     np.savez_compressed(
         os.path.join(args.out, "train_step_64.npz"), rgb=rgb.numpy(), nir=nir.numpy(),
         loss_D=float(loss_D), loss_G=float(loss_G), pred=pred1.detach().numpy(), sd_g_seed=21, sd_d_seed=22,
-        **{"gG." + k: gG[k].numpy() for k in keep_g}, **{"gD." + k: gD[k].numpy() for k in keep_d},
+        # big gradients are stored as their first 8 rows (+ every tensor's L2 norm below) to keep fixtures small
+        **{"gG." + k: gG[k][:8].numpy() for k in keep_g}, **{"gD." + k: gD[k][:8].numpy() for k in keep_d},
         **{"gnormG." + k: float(gG[k].norm()) for k in gG}, **{"gnormD." + k: float(gD[k].norm()) for k in gD},
         **{"newD." + k: new_d[k].detach().numpy() for k in ("model.11.weight", "model.0.bias")},
         **{"newG." + k: new_g[k].detach().numpy() for k in ("model.26.weight",)})
