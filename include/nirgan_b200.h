@@ -1,0 +1,152 @@
+/* nirgan_b200 -- C ABI of the B200 (sm_100a) NIR-GAN hot-path library.
+ *
+ * Every entry point takes plain device pointers, explicit sizes and an opaque CUDA stream
+ * (cudaStream_t passed as void*).  No torch / C++ types cross this boundary.  The caller owns
+ * every buffer; the library allocates nothing persistent apart from cached TMA descriptors.
+ *
+ * All compute entry points return 0 on success, a negative NG_E_* code for argument / shape /
+ * alignment errors and a positive value (cudaError_t) for CUDA failures.  ng_last_error()
+ * returns a thread-local human-readable message for the last non-zero status.  There is NO
+ * CPU fallback: on a device that is not sm_100 the compute entry points return NG_E_ARCH.
+ *
+ * Tensor layouts used on the device
+ *   activation  : NHWC, element type `dtype`, optional materialised halo:
+ *                 [B][H + 2*pad][W + 2*pad][C]            ("haloed buffer", pad >= 0)
+ *   pre-norm    : NHWC compact [B][H][W][C] (conv output before InstanceNorm)
+ *   weights     : packed [tap = kh*KW + kw][n][k]  (k contiguous; n = output channel of the op)
+ *   stats       : float [B][C][2] = (mean, rstd)
+ *
+ * Reference interfaces replaced (paths relative to the NIR-GAN repository):
+ *   ng_conv2d          nn.Conv2d / nn.ConvTranspose2d call sites  model/networks.py:342,349,360-363,367,
+ *                      405-427 (ResnetBlock), 559-579 (NLayerDiscriminator) and their autograd dgrad
+ *   ng_conv2d_wgrad    autograd weight gradient of the same call sites (model/pix2pix.py:165-257)
+ *   ng_in_stats / ng_in_stats_finalize / ng_in_apply / ng_in_apply_bwd
+ *                      nn.InstanceNorm2d + ReLU/LeakyReLU + residual add + ReflectionPad2d
+ *                      model/networks.py:29-30,341-344,350-351,405-434,567-576; the SatCLIP
+ *                      injection x*(1+s*e) model/generator_inject.py:113-127
+ *   ng_prep_input      F.pad(..., mode='reflect') model/pix2pix.py:91-93, ReflectionPad2d(3)
+ *                      model/networks.py:341, torch.cat((rgb, pred),1) model/pix2pix.py:197,202,216
+ *   ng_linear          self.fc(embeds) model/generator_inject.py:110
+ *   ng_lsgan_loss      GANLoss('lsgan') model/networks.py:232-233,268-270
+ *   ng_g_pixel_losses  L1Loss model/pix2pix.py:60,222 + RemoteSensingIndices NDVI/NDWI/EVI
+ *                      utils/remote_sensing_indices.py:84-159,277-319
+ *   ng_adam_step       torch.optim.Adam model/pix2pix.py:486-487
+ */
+#ifndef NIRGAN_B200_H_
+#define NIRGAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NG_VERSION 100
+
+/* element types */
+enum { NG_F32 = 0, NG_F16 = 1, NG_BF16 = 2 };
+/* conv implementations */
+enum { NG_IMPL_SIMT = 0,   /* CUDA-core fp32-accumulate implicit GEMM (verification mode, any dtype) */
+       NG_IMPL_TC = 1 };   /* tcgen05 / TMEM / TMA implicit GEMM (f16 or bf16 operands) */
+/* conv forms */
+enum { NG_FORM_GATHER = 0,     /* out[y] = sum_k in[y*stride + sgn*k - sgn*pad] * w[k]   (conv, dgrad of convT / s1 conv) */
+       NG_FORM_PHASED = 1 };   /* out[stride*i + a] = sum_{k == a+pad (mod stride)} in[i + (a+pad-k)/stride] * w[k]
+                                  (ConvTranspose2d, dgrad of a strided conv) */
+/* epilogues */
+enum { NG_EPI_RAW = 0,        /* store pre-norm output (+ per-tile sum / sum-of-squares partials) */
+       NG_EPI_BIAS_ACT = 1,   /* out = act(acc + bias) stored as `dtype` NHWC */
+       NG_EPI_HEAD = 2 };     /* single output channel: out = act(acc + bias) stored fp32 [B][H-2c][W-2c] */
+/* activations */
+enum { NG_ACT_NONE = 0, NG_ACT_RELU = 1, NG_ACT_LRELU = 2, NG_ACT_TANH = 3 };
+/* halo modes */
+enum { NG_HALO_ZERO = 0, NG_HALO_REFLECT = 1 };
+/* injection styles (model/generator_inject.py:122-127) */
+enum { NG_INJECT_NONE = 0, NG_INJECT_ADD = 1, NG_INJECT_MUL_SCALED = 2, NG_INJECT_MUL = 3 };
+
+/* error codes */
+enum { NG_OK = 0, NG_E_ARG = -1, NG_E_SHAPE = -2, NG_E_ALIGN = -3, NG_E_ARCH = -4, NG_E_UNSUPPORTED = -5,
+       NG_E_DRIVER = -6 };
+
+typedef struct ng_conv_args {
+  int32_t dtype;        /* NG_F32 / NG_F16 / NG_BF16: element type of x, w and (for RAW / BIAS_ACT) y */
+  int32_t impl;         /* NG_IMPL_* */
+  int32_t form;         /* NG_FORM_* */
+  int32_t sgn;          /* +1 (correlation) or -1 (flipped taps; dgrad of a stride-1 conv). GATHER only */
+  int32_t B, Hin, Win, Cin;   /* input interior; Cin is the stored (padded) channel count */
+  int32_t in_pad;       /* halo materialised in the input buffer */
+  int32_t Cout;         /* stored output channels (multiple of 8; HEAD: 16, of which channel 0 is real) */
+  int32_t KH, KW, stride, pad;
+  int32_t Hout, Wout;
+  int32_t epilogue;     /* NG_EPI_* */
+  int32_t act;          /* NG_ACT_* (BIAS_ACT / HEAD) */
+  float   slope;        /* LeakyReLU slope */
+  int32_t crop;         /* HEAD: rows/cols cropped from every border of the output */
+  int32_t reserved;
+  const void* x;        /* [B][Hin+2*in_pad][Win+2*in_pad][Cin] */
+  const void* w;        /* packed [KH*KW][Cout][Cin] */
+  const float* bias;    /* [Cout] or NULL */
+  void* y;              /* RAW/BIAS_ACT: [B][Hout][Wout][Cout] dtype; HEAD: float [B][Hout-2c][Wout-2c] */
+  float* stat_partials; /* RAW + TC: [B][ng_conv_stat_slots][Cout][2] (sum, sumsq) or NULL */
+} ng_conv_args;
+
+int         ng_version(void);
+const char* ng_last_error(void);
+/* 0 when `device` is an sm_100 GPU usable by this library */
+int         ng_device_check(int device);
+
+/* number of per-image partial-statistics slots ng_conv2d(TC, RAW) writes for this geometry */
+int ng_conv_stat_slots(const ng_conv_args* a);
+int ng_conv2d(const ng_conv_args* a, void* stream);
+
+/* weight gradient: dw[tap][n][k] (fp32, packed layout) = sum_pixels dy[.., n] * x[.. shifted by tap .., k]
+ * with the geometry of the forward op described by `a` (a->x = forward input, a->y = dY compact). */
+int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void* stream);
+
+/* pack an fp32 weight (4-D, [d0][d1][KH][KW]) into [tap][n][k]; n_axis selects which of d0/d1 is n.
+ * k is zero-padded to k_pad, n to n_pad. */
+int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
+                   int32_t n_pad, int32_t k_pad, int32_t dtype, void* dst, void* stream);
+/* inverse for gradients: packed fp32 [tap][n_pad][k_pad] -> fp32 [d0][d1][KH][KW] (accumulate=0: overwrite) */
+int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
+                          int32_t n_pad, int32_t k_pad, float* dst, void* stream);
+
+/* NCHW fp32 (one or two sources concatenated on C) -> haloed NHWC `dtype` with channels zero-padded to c_pad.
+ * wrap_pad: reflect padding applied first (Px2Px_PL.forward, padding_amount); halo: second reflect (or zero) halo. */
+int ng_prep_input(const float* src_a, int32_t ca, const float* src_b, int32_t cb, int32_t B, int32_t H, int32_t W,
+                  int32_t wrap_pad, int32_t halo, int32_t halo_mode, int32_t c_pad, int32_t dtype, void* dst,
+                  void* stream);
+
+/* per-(n,c) mean / rstd (eps 1e-5, biased variance) of a compact NHWC tensor */
+int ng_in_stats(const void* y, int32_t dtype, int32_t B, int32_t HW, int32_t C, float* mean_rstd, void* stream);
+/* same from the conv epilogue partial sums */
+int ng_in_stats_finalize(const float* partials, int32_t B, int32_t slots, int32_t C, int32_t count,
+                         float* mean_rstd, void* stream);
+
+/* out = act( inject( (y - mean) * rstd ) ) + residual, written with a halo of out_pad.
+ * mean_rstd == NULL skips the normalisation (y is used as is). */
+int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd,
+                int32_t act, float slope, const void* residual, int32_t res_pad, const float* inject_e,
+                int32_t inject_mode, const float* inject_scale, void* out, int32_t out_pad, int32_t halo_mode,
+                void* stream);
+
+/* y[b][n] = sum_k x[b][k] * w[n][k] + bias[n]   (fp32) */
+int ng_linear(const float* x, const float* w, const float* bias, int32_t B, int32_t K, int32_t N, float* y,
+              void* stream);
+
+/* mean((p - target)^2) over n elements -> loss[0] (+= when accumulate); grad (optional) = gscale*2*(p-target)/n */
+int ng_lsgan_loss(const float* p, int64_t n, float target, float* loss, int32_t accumulate, float* grad,
+                  float gscale, void* stream);
+
+/* fused generator pixel losses on NCHW fp32 planes: out[0]=L1, out[1]=NDVI, out[2]=NDWI, out[3]=EVI (means);
+ * dpred (optional) = d( w[0]*L1 + w[1]*NDVI + w[2]*NDWI + w[3]*EVI ) / dpred.  scratch: >= 4*1024 floats. */
+int ng_g_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
+                      const float* weights4, float* out4, float* dpred, float* scratch, void* stream);
+
+/* Adam (torch defaults: eps 1e-8, no weight decay, bias-corrected) on a flat fp32 parameter vector */
+int ng_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, int32_t step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIRGAN_B200_H_ */

@@ -1,0 +1,57 @@
+// extern "C" convolution entry points: validate, build the tap-table geometry, dispatch.
+#include "common.cuh"
+
+namespace ng {
+int conv_simt(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st);
+int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, float* dbias, cudaStream_t st);
+int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st);
+int conv_tc_stat_slots(const ng_conv_args& a, const ConvGeom& g);
+}  // namespace ng
+
+using namespace ng;
+
+static int validate(const ng_conv_args* a) {
+  NG_REQUIRE(a != nullptr, NG_E_ARG, "conv: null argument block");
+  NG_REQUIRE(a->x && a->w && a->y, NG_E_ARG, "conv: null tensor pointer");
+  NG_REQUIRE(a->dtype == NG_F32 || a->dtype == NG_F16 || a->dtype == NG_BF16, NG_E_ARG, "conv: bad dtype %d", a->dtype);
+  NG_REQUIRE(a->epilogue >= NG_EPI_RAW && a->epilogue <= NG_EPI_HEAD, NG_E_ARG, "conv: bad epilogue %d", a->epilogue);
+  NG_REQUIRE(a->Cin % 16 == 0, NG_E_SHAPE, "conv: stored Cin %d must be a multiple of 16", a->Cin);
+  NG_REQUIRE(a->Cout % 8 == 0, NG_E_SHAPE, "conv: stored Cout %d must be a multiple of 8", a->Cout);
+  NG_REQUIRE(a->crop >= 0 && (a->epilogue == NG_EPI_HEAD || a->crop == 0), NG_E_ARG, "conv: crop only with the head epilogue");
+  return NG_OK;
+}
+
+extern "C" int ng_conv_stat_slots(const ng_conv_args* a) {
+  if (!a) return NG_E_ARG;
+  ConvGeom g;
+  int r = build_geometry(*a, g);
+  if (r) return r;
+  if (a->impl != NG_IMPL_TC) return 0;
+  return conv_tc_stat_slots(*a, g);
+}
+
+extern "C" int ng_conv2d(const ng_conv_args* a, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  r = validate(a);
+  if (r) return r;
+  ConvGeom g;
+  r = build_geometry(*a, g);
+  if (r) return r;
+  if (a->impl == NG_IMPL_SIMT) return conv_simt(*a, g, (cudaStream_t)stream);
+  if (a->impl == NG_IMPL_TC) return conv_tc(*a, g, (cudaStream_t)stream);
+  set_error("conv: unknown impl %d", a->impl);
+  return NG_E_ARG;
+}
+
+extern "C" int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  r = validate(a);
+  if (r) return r;
+  NG_REQUIRE(dw_packed != nullptr, NG_E_ARG, "wgrad: null output");
+  ConvGeom g;
+  r = build_geometry(*a, g);
+  if (r) return r;
+  return wgrad_simt(*a, g, dw_packed, dbias, (cudaStream_t)stream);
+}

@@ -1,0 +1,239 @@
+// CUDA-core implicit-GEMM convolution (fp32 accumulate) over the tap-table geometry.
+// This is the fp32 "verification mode" of the hot path (north-star: <=1e-4 vs the reference) and the
+// independent on-device checker for the tcgen05 kernel; it accepts f32 / f16 / bf16 operands.
+#include "common.cuh"
+
+namespace ng {
+
+constexpr int ST_PX = 64;   // virtual pixels per tile (8 x 8 patch)
+constexpr int ST_CO = 64;   // output channels per tile
+constexpr int ST_K = 16;    // channels per smem chunk
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, const T* __restrict__ w,
+                 const float* __restrict__ bias, void* __restrict__ yv, int epilogue, int act, float slope,
+                 int crop, int patches_x, int patches_y, int co_tiles) {
+  __shared__ float As[ST_K][ST_PX + 4];
+  __shared__ float Bs[ST_K][ST_CO + 4];
+
+  int tile = blockIdx.x;
+  const int cot = tile % co_tiles; tile /= co_tiles;
+  const int px_ = tile % patches_x; tile /= patches_x;
+  const int py_ = tile % patches_y; tile /= patches_y;
+  const int n = tile % g.B;
+  const int phase = tile / g.B;
+
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;
+  // loader mapping: 4 threads per row, 4 consecutive channels each
+  const int lrow = t >> 2, lk = (t & 3) * 4;
+  const int li = py_ * 8 + (lrow >> 3), lj = px_ * 8 + (lrow & 7);   // virtual pixel of the A row
+  const int lco = cot * ST_CO + lrow;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int tp = g.phase_tap0[phase]; tp < g.phase_tap0[phase + 1]; ++tp) {
+    const int by = g.S * li + g.taps[tp].dy, bx = g.S * lj + g.taps[tp].dx;
+    const bool a_ok = by >= 0 && by < g.Hb && bx >= 0 && bx < g.Wb;
+    const T* ap = x + (((size_t)n * g.Hb + (a_ok ? by : 0)) * g.Wb + (a_ok ? bx : 0)) * g.Cin;
+    const bool b_ok = lco < g.Cout;
+    const T* bp = w + ((size_t)g.taps[tp].wrow + (b_ok ? lco : 0)) * g.Cin;
+    for (int c0 = 0; c0 < g.Cin; c0 += ST_K) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        As[lk + e][lrow] = a_ok ? to_f32<T>(ap[c0 + lk + e]) : 0.f;
+        Bs[lk + e][lrow] = b_ok ? to_f32<T>(bp[c0 + lk + e]) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < ST_K; ++k) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = ty * 4 + i;
+    const int vi = py_ * 8 + (row >> 3), vj = px_ * 8 + (row & 7);
+    const int oy = g.OS * vi + g.phase_oy[phase], ox = g.OS * vj + g.phase_ox[phase];
+    if (oy >= g.Hout || ox >= g.Wout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = cot * ST_CO + tx * 4 + j;
+      if (co >= g.Cout) continue;
+      float v = acc[i][j];
+      if (epilogue == NG_EPI_RAW) {
+        reinterpret_cast<T*>(yv)[(((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout + co] = from_f32<T>(v);
+      } else if (epilogue == NG_EPI_BIAS_ACT) {
+        v = apply_act(v + (bias ? bias[co] : 0.f), act, slope);
+        reinterpret_cast<T*>(yv)[(((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout + co] = from_f32<T>(v);
+      } else {  // NG_EPI_HEAD
+        if (co != 0) continue;
+        const int hy = oy - crop, hx = ox - crop, HH = g.Hout - 2 * crop, WW = g.Wout - 2 * crop;
+        if (hy < 0 || hx < 0 || hy >= HH || hx >= WW) continue;
+        v = apply_act(v + (bias ? bias[0] : 0.f), act, slope);
+        reinterpret_cast<float*>(yv)[((size_t)n * HH + hy) * WW + hx] = v;
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_simt(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
+  const int patches_y = (g.VH + 7) / 8, patches_x = (g.VW + 7) / 8, co_tiles = (g.Cout + ST_CO - 1) / ST_CO;
+  const long long tiles = (long long)g.nphase * g.B * patches_y * patches_x * co_tiles;
+  NG_REQUIRE(tiles < (1ll << 31), NG_E_SHAPE, "conv_simt: too many tiles");
+  conv_simt_kernel<T><<<(unsigned)tiles, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.w, a.bias, a.y, a.epilogue,
+                                                      a.act, a.slope, a.crop, patches_x, patches_y, co_tiles);
+  NG_LAUNCH_CHECK("conv_simt_kernel");
+  return NG_OK;
+}
+
+int conv_simt(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
+  NG_REQUIRE(a.Cin % ST_K == 0, NG_E_SHAPE, "conv_simt: Cin %d must be a multiple of %d", a.Cin, ST_K);
+  switch (a.dtype) {
+    case NG_F32:  return launch_simt<float>(a, g, st);
+    case NG_F16:  return launch_simt<__half>(a, g, st);
+    case NG_BF16: return launch_simt<__nv_bfloat16>(a, g, st);
+  }
+  set_error("conv_simt: bad dtype %d", a.dtype);
+  return NG_E_ARG;
+}
+
+// ---- weight gradient ------------------------------------------------------------------------------
+// dw[tap][n][k] += sum over virtual pixels of dy[.., n] * x[.. shifted .., k].  Tile: 64 n x 64 k,
+// pixels split across blocks, fp32 atomics into a zero-initialised dw.
+constexpr int WG_PIX = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+wgrad_simt_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, const T* __restrict__ dy,
+                  float* __restrict__ dw, int n_tiles, int k_tiles, int splits, int pix_per_split) {
+  __shared__ float Ys[WG_PIX][64 + 4];
+  __shared__ float Xs[WG_PIX][64 + 4];
+  int id = blockIdx.x;
+  const int sp = id % splits; id /= splits;
+  const int kt = id % k_tiles; id /= k_tiles;
+  const int nt = id % n_tiles; id /= n_tiles;
+  const int tp = id;
+  int phase = 0;
+  while (tp >= g.phase_tap0[phase + 1]) ++phase;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int lp = t >> 4, lc = (t & 15) * 4;   // loader: 16 pixels x 16 threads x 4 channels
+  const long long npix = (long long)g.B * g.VH * g.VW;
+  const long long p0 = (long long)sp * pix_per_split, p1 = min(npix, p0 + pix_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long pb = p0; pb < p1; pb += WG_PIX) {
+    const long long p = pb + lp;
+    bool ok = p < p1;
+    int n = 0, vi = 0, vj = 0;
+    if (ok) { vj = (int)(p % g.VW); long long r = p / g.VW; vi = (int)(r % g.VH); n = (int)(r / g.VH); }
+    const int oy = g.OS * vi + g.phase_oy[phase], ox = g.OS * vj + g.phase_ox[phase];
+    const bool y_ok = ok && oy < g.Hout && ox < g.Wout;
+    const int by = g.S * vi + g.taps[tp].dy, bx = g.S * vj + g.taps[tp].dx;
+    const bool x_ok = y_ok && by >= 0 && by < g.Hb && bx >= 0 && bx < g.Wb;
+    const T* yp = dy + (((size_t)n * g.Hout + (y_ok ? oy : 0)) * g.Wout + (y_ok ? ox : 0)) * g.Cout;
+    const T* xp = x + (((size_t)n * g.Hb + (x_ok ? by : 0)) * g.Wb + (x_ok ? bx : 0)) * g.Cin;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int cn = nt * 64 + lc + e, ck = kt * 64 + lc + e;
+      Ys[lp][lc + e] = (x_ok && cn < g.Cout) ? to_f32<T>(yp[cn]) : 0.f;
+      Xs[lp][lc + e] = (x_ok && ck < g.Cin) ? to_f32<T>(xp[ck]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < WG_PIX; ++q) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = Ys[q][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Xs[q][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int wbase = g.taps[tp].wrow;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cn = nt * 64 + ty * 4 + i;
+    if (cn >= g.Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ck = kt * 64 + tx * 4 + j;
+      if (ck >= g.Cin) continue;
+      atomicAdd(&dw[((size_t)wbase + cn) * g.Cin + ck], acc[i][j]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ dy, long long rows, int C, float* __restrict__ out) {
+  // grid.x blocks stride over rows; thread handles channel threadIdx.x (C <= 1024 handled by loop)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (long long r = blockIdx.x; r < rows; r += gridDim.x) s += to_f32<T>(dy[r * C + c]);
+    atomicAdd(&out[c], s);
+  }
+}
+
+template <typename T>
+static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, float* dbias, cudaStream_t st) {
+  const int n_tiles = (g.Cout + 63) / 64, k_tiles = (g.Cin + 63) / 64;
+  const long long npix = (long long)g.B * g.VH * g.VW;
+  long long sp_ = npix / 2048; if (sp_ < 1) sp_ = 1; if (sp_ > 64) sp_ = 64;
+  int splits = (int)sp_;
+  long long pps = (npix + splits - 1) / splits;
+  pps = (pps + WG_PIX - 1) / WG_PIX * WG_PIX;
+  splits = (int)((npix + pps - 1) / pps);
+  const size_t wbytes = (size_t)a.KH * a.KW * g.Cout * g.Cin * sizeof(float);
+  int e = check_cuda(cudaMemsetAsync(dw, 0, wbytes, st), "wgrad memset");
+  if (e) return e;
+  const long long blocks = (long long)g.ntaps * n_tiles * k_tiles * splits;
+  wgrad_simt_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, n_tiles, k_tiles,
+                                                        splits, (int)pps);
+  NG_LAUNCH_CHECK("wgrad_simt_kernel");
+  if (dbias) {
+    e = check_cuda(cudaMemsetAsync(dbias, 0, (size_t)g.Cout * sizeof(float), st), "dbias memset");
+    if (e) return e;
+    const long long rows = (long long)g.B * g.Hout * g.Wout;
+    const unsigned cs_blocks = (unsigned)(rows < 1024 ? rows : 1024);
+    const unsigned cs_threads = (unsigned)(g.Cout < 256 ? g.Cout : 256);
+    colsum_kernel<T><<<cs_blocks, cs_threads, 0, st>>>((const T*)a.y, rows, g.Cout, dbias);
+    NG_LAUNCH_CHECK("colsum_kernel");
+  }
+  return NG_OK;
+}
+
+int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, float* dbias, cudaStream_t st) {
+  switch (a.dtype) {
+    case NG_F32:  return launch_wgrad<float>(a, g, dw, dbias, st);
+    case NG_F16:  return launch_wgrad<__half>(a, g, dw, dbias, st);
+    case NG_BF16: return launch_wgrad<__nv_bfloat16>(a, g, dw, dbias, st);
+  }
+  set_error("wgrad_simt: bad dtype %d", a.dtype);
+  return NG_E_ARG;
+}
+
+}  // namespace ng

@@ -1,0 +1,514 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// GEMM view: M = 128 "virtual pixels" of one image (a BH x BW patch), N = BN output channels,
+// K = (taps of the phase) x Cin.  For every tap and KC-channel chunk one pipeline stage is filled by
+// two TMA tiled loads:
+//   A: box (KC ch, BW px, BH px, 1 img) of the haloed NHWC activation tensor at the tap's offset
+//      (element stride S along w/h for strided convs; out-of-bounds = zero fill = zero padding),
+//      landing in shared memory as 128 rows x KC in the canonical K-major swizzled UMMA layout;
+//   B: box (KC, BN) of the packed weight matrix [tap*Cout + n][Cin].
+// One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator;
+// four epilogue warps drain TMEM (tcgen05.ld 32x32b), convert to 16-bit, stage the tile in swizzled
+// shared memory, reduce per-channel sum / sum-of-squares for InstanceNorm (deterministic per-tile
+// partials) and write the rows out with 16-byte coalesced stores.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 =
+// epilogue (warp_id % 4 selects the TMEM lane quarter).  Persistent: grid = min(tiles, #SM).
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+
+namespace ng {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Wait for the phase with the given parity.  A wedged pipeline must fault, never hang the GPU: after
+// ~2 s without progress the kernel reports the barrier and traps.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 0xFF) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) {
+        printf("nirgan_b200: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+               (int)threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SW128, 6 = SW32)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                       // LBO: unused for swizzled K-major layouts
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+  ConvGeom g;
+  int BH, BW;                 // patch of virtual pixels (BH*BW <= 128)
+  int patches_y, patches_x, co_tiles;
+  int total_tiles;
+  int epilogue, act, crop;
+  float slope;
+  int bf16;
+  int stat_slots;
+  const float* bias;
+  void* y;
+  float* stat_partials;
+};
+
+template <int BN, int KC>
+struct TcCfg {
+  static constexpr int A_BYTES = 128 * KC * 2;
+  static constexpr int B_BYTES = (BN * KC * 2 + 1023) / 1024 * 1024;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_BYTES = BN >= 64 ? 128 * BN * 2 : 0;
+  static constexpr int RED_BYTES = BN >= 64 ? 2048 : 0;              // cross-group stats combine
+  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int STAGES_RAW = (BUDGET - STAGING_BYTES - RED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns between the two accumulators
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE <= 64 ? 64 : (2 * ACC_STRIDE <= 128 ? 128 : (2 * ACC_STRIDE <= 256 ? 256 : 512));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + RED_BYTES + 1024 /*rowoff*/ + 256 /*barriers*/ +
+                                    1024 /*alignment slack*/;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+};
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BN, KC>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  float* red = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
+  long long* rowoff = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(red) + Cfg::RED_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowoff) + 1024);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int chunks = g.Cin / KC;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int cot = t % p.co_tiles; t /= p.co_tiles;
+        const int ph = t % g.nphase; t /= g.nphase;
+        const int px = t % p.patches_x; t /= p.patches_x;
+        const int py = t % p.patches_y; t /= p.patches_y;
+        const int n = t;
+        const int i0 = py * p.BH, j0 = px * p.BW;
+        for (int tp = g.phase_tap0[ph]; tp < g.phase_tap0[ph + 1]; ++tp) {
+          const int by = g.S * i0 + g.taps[tp].dy, bx = g.S * j0 + g.taps[tp].dx;
+          const int brow = g.taps[tp].wrow + cot * BN;
+          for (int c = 0; c < chunks; ++c) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+            mbar_expect_tx(fb, 128 * KC * 2 + BN * KC * 2);
+            tma_load_4d(&tmA, fb, sa, c * KC, bx, by, n);
+            tma_load_2d(&tmB, fb, sa + Cfg::A_BYTES, c * KC, brow);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bf16 ? 1 : 0) << 7) | ((uint32_t)(p.bf16 ? 1 : 0) << 10) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t SBO = KC == 64 ? 1024 : 256;
+      constexpr uint32_t LAYOUT = KC == 64 ? 2 : 6;
+      uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int ph = (tile / p.co_tiles) % g.nphase;
+        const int kiters = (g.phase_tap0[ph + 1] - g.phase_tap0[ph]) * chunks;
+        mbar_wait(smem_u32(&tempty_bar[as]), as_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_kmajor_desc(sa, SBO, LAYOUT);
+          const uint64_t bdesc = make_kmajor_desc(sa + Cfg::A_BYTES, SBO, LAYOUT);
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k)
+            umma_f16(tmem_c, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kit | k) != 0));
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tfull_bar[as]));
+        if (++as == 2) { as = 0; as_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;          // accumulator row == TMEM lane
+    const int et = threadIdx.x - 64;        // 0..127 epilogue thread index
+    uint32_t as = 0, as_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int cot = t % p.co_tiles; t /= p.co_tiles;
+      const int ph = t % g.nphase; t /= g.nphase;
+      const int px = t % p.patches_x; t /= p.patches_x;
+      const int py = t % p.patches_y; t /= p.patches_y;
+      const int n = t;
+      const int vi = py * p.BH + row / p.BW, vj = px * p.BW + row % p.BW;
+      const int oy = g.OS * vi + g.phase_oy[ph], ox = g.OS * vj + g.phase_ox[ph];
+      const bool valid = row < p.BH * p.BW && oy < g.Hout && ox < g.Wout;
+      const int n0 = cot * BN;
+
+      mbar_wait(smem_u32(&tfull_bar[as]), as_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+
+      if constexpr (BN < 64) {
+        // ---- single real output channel (generator head, PatchGAN last layer) ----
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tempty_bar[as]));
+        if (valid) {
+          const int hy = oy - p.crop, hx = ox - p.crop, HH = g.Hout - 2 * p.crop, WW = g.Wout - 2 * p.crop;
+          if (hy >= 0 && hx >= 0 && hy < HH && hx < WW) {
+            const float v = apply_act(__uint_as_float(r[0]) + (p.bias ? p.bias[0] : 0.f), p.act, p.slope);
+            reinterpret_cast<float*>(p.y)[((size_t)n * HH + hy) * WW + hx] = v;
+          }
+        }
+      } else {
+        rowoff[row] = valid ? ((((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout + n0) : -1ll;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(taddr + ch * 32, r);
+          tmem_ld_wait();
+          uint32_t w[16];
+          if (p.epilogue == NG_EPI_BIAS_ACT) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float b = p.bias ? p.bias[n0 + ch * 32 + k] : 0.f;
+              r[k] = __float_as_uint(apply_act(__uint_as_float(r[k]) + b, p.act, p.slope));
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float a = valid ? __uint_as_float(r[2 * k]) : 0.f, b = valid ? __uint_as_float(r[2 * k + 1]) : 0.f;
+            w[k] = p.bf16 ? pack2<__nv_bfloat16>(a, b) : pack2<__half>(a, b);
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int chunk = (ch * 4 + c4) ^ (row & 7);
+            *reinterpret_cast<uint4*>(staging + (size_t)row * (BN * 2) + chunk * 16) =
+                make_uint4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tempty_bar[as]));     // accumulator drained: the MMA warp may reuse it
+        epi_bar_sync();
+
+        // ---- per-channel partial statistics (deterministic: fixed row order, fixed combine order) ----
+        if (p.epilogue == NG_EPI_RAW && p.stat_partials != nullptr) {
+          constexpr int PAIRS = BN / 2, G = 128 / PAIRS;
+          const int cp = et % PAIRS, rs = et / PAIRS;
+          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+          for (int r2 = rs; r2 < 128; r2 += G) {
+            const uint32_t word = *reinterpret_cast<const uint32_t*>(staging + (size_t)r2 * (BN * 2) +
+                                                                     (((cp >> 2) ^ (r2 & 7)) * 16) + (cp & 3) * 4);
+            const float2 v = p.bf16 ? unpack2<__nv_bfloat16>(word) : unpack2<__half>(word);
+            s0 += v.x; q0 = fmaf(v.x, v.x, q0); s1 += v.y; q1 = fmaf(v.y, v.y, q1);
+          }
+          if constexpr (G > 1) {
+            if (rs > 0) *reinterpret_cast<float4*>(red + ((rs - 1) * PAIRS + cp) * 4) = make_float4(s0, q0, s1, q1);
+            epi_bar_sync();
+            if (rs == 0) {
+              for (int k = 1; k < G; ++k) {
+                const float4 o = *reinterpret_cast<const float4*>(red + ((k - 1) * PAIRS + cp) * 4);
+                s0 += o.x; q0 += o.y; s1 += o.z; q1 += o.w;
+              }
+            }
+          }
+          if (rs == 0) {
+            const int slot = (ph * p.patches_y + py) * p.patches_x + px;
+            float* dst = p.stat_partials + (((size_t)n * p.stat_slots + slot) * g.Cout + n0 + 2 * cp) * 2;
+            *reinterpret_cast<float4*>(dst) = make_float4(s0, q0, s1, q1);
+          }
+        }
+
+        // ---- coalesced row stores: BN/8 lanes x 16 B per row ----
+        {
+          constexpr int LPR = BN / 8, RPI = 32 / LPR;     // lanes per row, rows per warp-instruction
+          const int we = warp - 2;
+          const int chunk = lane % LPR;
+          uint8_t* ybase = reinterpret_cast<uint8_t*>(p.y);
+          for (int r2 = we * RPI + lane / LPR; r2 < 128; r2 += 4 * RPI) {
+            const long long off = rowoff[r2];
+            if (off >= 0) {
+              const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)r2 * (BN * 2) + ((chunk ^ (r2 & 7)) * 16));
+              *reinterpret_cast<uint4*>(ybase + off * 2 + chunk * 16) = v;
+            }
+          }
+        }
+        epi_bar_sync();   // staging / rowoff are reused by the next tile
+      }
+      if (++as == 2) { as = 0; as_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::mutex g_mu;
+
+static int get_encode() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_encode) return NG_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+    return NG_E_DRIVER;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return NG_OK;
+}
+
+static void choose_patch(int VH, int VW, int S, int& BH, int& BW) {
+  long long best = -1;
+  BH = 1; BW = 1;
+  for (int bw = 1; bw <= 128 && bw * S <= 256 && bw <= VW; ++bw) {
+    int bh = 128 / bw;
+    if (bh * S > 256) bh = 256 / S;
+    if (bh > VH) bh = VH;            // taller than the image only wastes rows
+    const long long tiles = (long long)((VH + bh - 1) / bh) * ((VW + bw - 1) / bw);
+    // fewer tiles wins; ties prefer wider rows (longer contiguous stores)
+    const long long score = tiles * 1024 - bw;
+    if (best < 0 || score < best) { best = score; BH = bh; BW = bw; }
+  }
+}
+
+template <int BN, int KC>
+static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
+  using Cfg = TcCfg<BN, KC>;
+  int r = get_encode();
+  if (r) return r;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  choose_patch(g.VH, g.VW, g.S, p.BH, p.BW);
+  p.patches_y = (g.VH + p.BH - 1) / p.BH;
+  p.patches_x = (g.VW + p.BW - 1) / p.BW;
+  p.co_tiles = g.Cout / BN;
+  const long long tiles = (long long)g.B * p.patches_y * p.patches_x * g.nphase * p.co_tiles;
+  NG_REQUIRE(tiles > 0 && tiles < (1ll << 31), NG_E_SHAPE, "conv_tc: tile count out of range");
+  p.total_tiles = (int)tiles;
+  p.epilogue = a.epilogue; p.act = a.act; p.crop = a.crop; p.slope = a.slope;
+  p.bf16 = a.dtype == NG_BF16;
+  p.stat_slots = g.nphase * p.patches_y * p.patches_x;
+  p.bias = a.bias; p.y = a.y; p.stat_partials = a.stat_partials;
+
+  CUtensorMap tmA, tmB;
+  const CUtensorMapDataType dt = a.dtype == NG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wb, (cuuint64_t)g.Hb, (cuuint64_t)g.B};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Wb * g.Cin * 2, (cuuint64_t)g.Hb * g.Wb * g.Cin * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(p.BW * g.S), (cuuint32_t)(p.BH * g.S), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
+    CUresult cr = g_encode(&tmA, dt, 4, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "cuTensorMapEncodeTiled(A) failed: %d (dims %d %d %d %d box %d %d %d)",
+               (int)cr, g.Cin, g.Wb, g.Hb, g.B, KC, p.BW * g.S, p.BH * g.S);
+  }
+  {
+    const int taps_total = a.KH * a.KW;
+    cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)taps_total * g.Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = g_encode(&tmB, dt, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "cuTensorMapEncodeTiled(B) failed: %d", (int)cr);
+  }
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    int e = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg::SMEM_BYTES), "cudaFuncSetAttribute(conv_tc)");
+    if (e) return e;
+    attr_set = true;
+  }
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  conv_tc_kernel<BN, KC><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  NG_LAUNCH_CHECK("conv_tc_kernel");
+  return NG_OK;
+}
+
+static int tc_block_n(const ng_conv_args& a) {
+  if (a.epilogue == NG_EPI_HEAD) return 16;
+  if (a.Cout % 256 == 0) return 256;
+  if (a.Cout % 128 == 0) return 128;
+  if (a.Cout % 64 == 0) return 64;
+  return 0;
+}
+
+int conv_tc_stat_slots(const ng_conv_args& a, const ConvGeom& g) {
+  int BH, BW;
+  choose_patch(g.VH, g.VW, g.S, BH, BW);
+  return g.nphase * ((g.VH + BH - 1) / BH) * ((g.VW + BW - 1) / BW);
+}
+
+int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
+  NG_REQUIRE(a.dtype == NG_F16 || a.dtype == NG_BF16, NG_E_UNSUPPORTED, "conv_tc: operands must be f16 or bf16");
+  NG_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0, NG_E_ALIGN,
+             "conv_tc: tensors must be 16-byte aligned");
+  const int bn = tc_block_n(a);
+  const int kc = a.Cin % 64 == 0 ? 64 : (a.Cin == 16 ? 16 : 0);
+  NG_REQUIRE(bn != 0 && kc != 0, NG_E_UNSUPPORTED, "conv_tc: Cin %d / Cout %d not tileable", a.Cin, a.Cout);
+  NG_REQUIRE(a.epilogue != NG_EPI_HEAD || a.Cout == 16, NG_E_SHAPE, "conv_tc: head epilogue expects Cout stored as 16");
+  if (bn == 16 && kc == 64) return launch_tc<16, 64>(a, g, st);
+  if (bn == 64 && kc == 16) return launch_tc<64, 16>(a, g, st);
+  if (bn == 64 && kc == 64) return launch_tc<64, 64>(a, g, st);
+  if (bn == 128 && kc == 64) return launch_tc<128, 64>(a, g, st);
+  if (bn == 256 && kc == 64) return launch_tc<256, 64>(a, g, st);
+  set_error("conv_tc: no kernel for BN %d KC %d", bn, kc);
+  return NG_E_UNSUPPORTED;
+}
+
+}  // namespace ng

@@ -1,0 +1,504 @@
+// Memory-bound kernels of the hot path: layout / packing, InstanceNorm statistics, the fused
+// normalise + inject + activation + residual + halo "apply", the SatCLIP projection, the fused
+// pixel losses and Adam.  All are vectorised (16-byte accesses on the 16-bit paths) and sized in
+// multiples of the SM count.
+#include "common.cuh"
+
+namespace ng {
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: src fp32 [d0][d1][KH][KW] -> dst [tap][n_pad][k_pad], n = d(n_axis), k = the other
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ src, int d0, int d1, int taps, int n_axis, int n_pad,
+                                   int k_pad, T* __restrict__ dst) {
+  const long long total = (long long)taps * n_pad * k_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % k_pad);
+    const int n = (int)((i / k_pad) % n_pad);
+    const int tp = (int)(i / ((long long)k_pad * n_pad));
+    const int a0 = n_axis == 0 ? n : k, a1 = n_axis == 0 ? k : n;
+    float v = 0.f;
+    if (a0 < d0 && a1 < d1) v = src[((long long)a0 * d1 + a1) * taps + tp];
+    dst[i] = from_f32<T>(v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int d0, int d1, int taps, int n_axis,
+                                    int n_pad, int k_pad, float* __restrict__ dst) {
+  const long long total = (long long)d0 * d1 * taps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tp = (int)(i % taps);
+    const int a1 = (int)((i / taps) % d1);
+    const int a0 = (int)(i / ((long long)taps * d1));
+    const int n = n_axis == 0 ? a0 : a1, k = n_axis == 0 ? a1 : a0;
+    dst[i] = packed[((long long)tp * n_pad + n) * k_pad + k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// input preparation: NCHW fp32 (1 or 2 sources) -> haloed NHWC with channel padding
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void prep_input_kernel(const float* __restrict__ sa, int ca, const float* __restrict__ sb, int cb, int B,
+                                  int H, int W, int wrap, int halo, int halo_mode, int cpad, T* __restrict__ dst) {
+  const int H1 = H + 2 * wrap, W1 = W + 2 * wrap;     // after the wrapper's reflect padding
+  const int Hb = H1 + 2 * halo, Wb = W1 + 2 * halo;
+  const long long total = (long long)B * Hb * Wb;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int xb = (int)(p % Wb);
+    const int yb = (int)((p / Wb) % Hb);
+    const int n = (int)(p / ((long long)Wb * Hb));
+    int y1 = yb - halo, x1 = xb - halo;
+    bool zero = false;
+    if (halo_mode == NG_HALO_REFLECT) { y1 = reflect_idx(y1, H1); x1 = reflect_idx(x1, W1); }
+    else zero = y1 < 0 || y1 >= H1 || x1 < 0 || x1 >= W1;
+    T* o = dst + p * cpad;
+    if (zero) {
+      for (int c = 0; c < cpad; ++c) o[c] = from_f32<T>(0.f);
+      continue;
+    }
+    const int y0 = reflect_idx(y1 - wrap, H), x0 = reflect_idx(x1 - wrap, W);
+    for (int c = 0; c < cpad; ++c) {
+      float v = 0.f;
+      if (c < ca) v = sa[(((long long)n * ca + c) * H + y0) * W + x0];
+      else if (c < ca + cb) v = sb[(((long long)n * cb + (c - ca)) * H + y0) * W + x0];
+      o[c] = from_f32<T>(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// InstanceNorm statistics
+// ---------------------------------------------------------------------------------------------
+// grid (B, C/32): block of 256 threads = 8 row-groups x 32 channels; two-pass (mean, then centred variance).
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_stats_kernel(const T* __restrict__ y, int HW, int C, float* __restrict__ mr) {
+  __shared__ float red[8][33];
+  __shared__ float smean[32];
+  const int n = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), rg = threadIdx.x >> 5;
+  const T* base = y + (size_t)n * HW * C;
+  float s = 0.f;
+  if (c < C) for (int p = rg; p < HW; p += 8) s += to_f32<T>(base[(size_t)p * C + c]);
+  red[rg][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rg == 0) {
+    float tsum = 0.f;
+    for (int i = 0; i < 8; ++i) tsum += red[i][threadIdx.x];
+    smean[threadIdx.x] = tsum / HW;
+  }
+  __syncthreads();
+  const float mean = smean[threadIdx.x & 31];
+  float q = 0.f;
+  if (c < C) for (int p = rg; p < HW; p += 8) { float d = to_f32<T>(base[(size_t)p * C + c]) - mean; q += d * d; }
+  red[rg][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (rg == 0 && c < C) {
+    float tq = 0.f;
+    for (int i = 0; i < 8; ++i) tq += red[i][threadIdx.x];
+    mr[((size_t)n * C + c) * 2 + 0] = mean;
+    mr[((size_t)n * C + c) * 2 + 1] = rsqrtf(tq / HW + 1e-5f);
+  }
+}
+
+// partials: [B][slots][C][2] (sum, sumsq) -> mean / rstd.  fixed summation order => deterministic.
+__global__ void in_stats_finalize_kernel(const float* __restrict__ part, int B, int slots, int C, float inv_count,
+                                         float* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int n = i / C, c = i % C;
+  const float* p = part + ((size_t)n * slots * C + c) * 2;
+  double s = 0.0, q = 0.0;
+  for (int k = 0; k < slots; ++k) { s += p[(size_t)k * C * 2]; q += p[(size_t)k * C * 2 + 1]; }
+  const double mean = s * inv_count;
+  double var = q * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mr[(size_t)i * 2 + 0] = (float)mean;
+  mr[(size_t)i * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+// ---------------------------------------------------------------------------------------------
+// apply: out(haloed) = act( inject( (y-mean)*rstd ) ) + residual
+// one thread = one output buffer position x 8 channels (16 B on the 16-bit paths)
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Vec8 { T v[8]; };
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y), c = unpack2<T>(u.z), d = unpack2<T>(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 u;
+    u.x = pack2<T>(f[0], f[1]); u.y = pack2<T>(f[2], f[3]); u.z = pack2<T>(f[4], f[5]); u.w = pack2<T>(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
+__device__ __forceinline__ float bilerp128(const float* __restrict__ e, int oy, int ox, int H, int W) {
+  // F.interpolate(mode='bilinear', align_corners=False) from a 128x128 grid (model/generator_inject.py:116)
+  const float sy = fmaxf((oy + 0.5f) * (128.f / H) - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * (128.f / W) - 0.5f, 0.f);
+  const int y0 = min((int)sy, 127), x0 = min((int)sx, 127);
+  const int y1 = min(y0 + 1, 127), x1 = min(x0 + 1, 127);
+  const float ly = sy - y0, lx = sx - x0;
+  const float v00 = e[y0 * 128 + x0], v01 = e[y0 * 128 + x1], v10 = e[y1 * 128 + x0], v11 = e[y1 * 128 + x1];
+  return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_apply_kernel(const T* __restrict__ y, int B, int H, int W, int C, const float* __restrict__ mr, int act,
+                float slope, const T* __restrict__ res, int res_pad, const float* __restrict__ inj, int inj_mode,
+                const float* __restrict__ inj_scale, T* __restrict__ out, int op, int halo_mode) {
+  const int Ho = H + 2 * op, Wo = W + 2 * op, C8 = C >> 3;
+  const long long total = (long long)B * Ho * Wo * C8;
+  const float s = (inj_mode != NG_INJECT_NONE && inj_scale) ? *inj_scale : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long p = i / C8;
+    const int xo = (int)(p % Wo); p /= Wo;
+    const int yo = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    int ys = yo - op, xs = xo - op;
+    float f[8];
+    T* o = out + (((size_t)n * Ho + yo) * Wo + xo) * C + c8 * 8;
+    if (halo_mode == NG_HALO_REFLECT) { ys = reflect_idx(ys, H); xs = reflect_idx(xs, W); }
+    else if (ys < 0 || ys >= H || xs < 0 || xs >= W) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = 0.f;
+      store8<T>(o, f);
+      continue;
+    }
+    load8<T>(y + (((size_t)n * H + ys) * W + xs) * C + c8 * 8, f);
+    if (mr) {
+      const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 m = m4[k];
+        f[2 * k] = (f[2 * k] - m.x) * m.y;
+        f[2 * k + 1] = (f[2 * k + 1] - m.z) * m.w;
+      }
+    }
+    if (inj_mode != NG_INJECT_NONE) {
+      const float e = bilerp128(inj + (size_t)n * 128 * 128, ys, xs, H, W);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (inj_mode == NG_INJECT_ADD) f[k] = f[k] + s * e;
+        else if (inj_mode == NG_INJECT_MUL_SCALED) f[k] = f[k] * (1.f + s * e);
+        else f[k] = f[k] * e;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = apply_act(f[k], act, slope);
+    if (res) {
+      float r[8];
+      const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
+      load8<T>(res + (((size_t)n * Hr + ys + res_pad) * Wr + xs + res_pad) * C + c8 * 8, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r[k];
+    }
+    store8<T>(o, f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// linear: y[b][n] = x[b][:] . w[n][:] + bias[n]; one warp per n, lanes split K, loop over b
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B, int K,
+              int N, float* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* wr = w + (size_t)warp * K;
+  const float bv = bias ? bias[warp] : 0.f;
+  for (int b = 0; b < B; ++b) {
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(x[(size_t)b * K + k], wr[k], s);
+    s = warp_sum(s);
+    if (lane == 0) y[(size_t)b * N + warp] = s + bv;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// losses
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lsgan_kernel(const float* __restrict__ p, long long n, float target, float* __restrict__ partial,
+             float* __restrict__ grad, float gcoef) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = p[i] - target;
+    s += d * d;
+    if (grad) grad[i] = gcoef * d;
+  }
+  __shared__ float red[8];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = 0.f;
+    for (int i = 0; i < 8; ++i) tsum += red[i];
+    partial[blockIdx.x] = tsum;
+  }
+}
+
+// deterministic second stage: out[j] (+)= scale * sum_i partial[i*stride + j]
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int stride, float scale,
+                                       float* __restrict__ out, int accumulate) {
+  const int j = threadIdx.x;
+  if (j >= stride) return;
+  double s = 0.0;
+  for (int i = 0; i < nblocks; ++i) s += partial[(size_t)i * stride + j];
+  const float v = (float)(s * scale);
+  out[j] = accumulate ? out[j] + v : v;
+}
+
+// fused L1 + NDVI + NDWI + EVI (loss mode, eps 1e-6, criterion l1) forward and d/dpred.
+// utils/remote_sensing_indices.py:104-110,140-148,296-310; model/pix2pix.py:222.
+__global__ void __launch_bounds__(256)
+g_pixel_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ nir, const float* __restrict__ pred,
+                    int B, int HW, float w0, float w1, float w2, float w3, float inv_n, float* __restrict__ partial,
+                    float* __restrict__ dpred) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), q = (int)(i % HW);
+    const float R = rgb[((size_t)n * 3 + 0) * HW + q], G = rgb[((size_t)n * 3 + 1) * HW + q],
+                Bl = rgb[((size_t)n * 3 + 2) * HW + q];
+    const float t = nir[i], p = pred[i];
+    const float eps = 1e-6f;
+    // L1
+    const float d0 = p - t;
+    s0 += fabsf(d0);
+    float g = w0 * (d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f));
+    // NDVI: (n-R)/(n+R+eps); d/dp = (2R+eps)/(p+R+eps)^2
+    {
+      const float it = (t - R) / (t + R + eps), dp = p + R + eps, ip = (p - R) / dp;
+      const float df = it - ip;
+      s1 += fabsf(df);
+      const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+      g += w1 * (-sg) * ((2.f * R + eps) / (dp * dp));
+    }
+    // NDWI with green
+    {
+      const float it = (t - G) / (t + G + eps), dp = p + G + eps, ip = (p - G) / dp;
+      const float df = it - ip;
+      s2 += fabsf(df);
+      const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+      g += w2 * (-sg) * ((2.f * G + eps) / (dp * dp));
+    }
+    // EVI: 2.5*(n-R)/((n+6)*(R-7.5)*(B+1)+eps);  with k=(R-7.5)(B+1): d/dp = 2.5*(k*(6+R)+eps)/den^2
+    {
+      const float k = (R - 7.5f) * (Bl + 1.f);
+      const float dt = (t + 6.f) * k + eps, dp = (p + 6.f) * k + eps;
+      const float it = 2.5f * ((t - R) / dt), ip = 2.5f * ((p - R) / dp);
+      const float df = it - ip;
+      s3 += fabsf(df);
+      const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
+      g += w3 * (-sg) * (2.5f * (k * (6.f + R) + eps) / (dp * dp));
+    }
+    if (dpred) dpred[i] = g * inv_n;
+  }
+  __shared__ float red[4][8];
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1;
+    red[2][threadIdx.x >> 5] = s2; red[3][threadIdx.x >> 5] = s3;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float tsum = 0.f;
+    for (int i = 0; i < 8; ++i) tsum += red[threadIdx.x][i];
+    partial[(size_t)blockIdx.x * 4 + threadIdx.x] = tsum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    // torch.optim.Adam (single-tensor): denom = sqrt(v)/sqrt(bc2) + eps; p -= lr/bc1 * m/denom
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+static inline unsigned grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 8;   // 8 resident CTAs of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace ng
+
+using namespace ng;
+
+#define DISPATCH_DTYPE(dtype, CALL)                                         \
+  switch (dtype) {                                                          \
+    case NG_F32: { using T = float; CALL; break; }                          \
+    case NG_F16: { using T = __half; CALL; break; }                         \
+    case NG_BF16: { using T = __nv_bfloat16; CALL; break; }                 \
+    default: ng::set_error("bad dtype %d", (int)(dtype)); return NG_E_ARG;  \
+  }
+
+extern "C" int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
+                              int32_t n_pad, int32_t k_pad, int32_t dtype, void* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src && dst && (n_axis == 0 || n_axis == 1), NG_E_ARG, "pack_weight: bad arguments");
+  const int nn = n_axis == 0 ? d0 : d1, kk = n_axis == 0 ? d1 : d0;
+  NG_REQUIRE(n_pad >= nn && k_pad >= kk, NG_E_SHAPE, "pack_weight: padding smaller than the tensor");
+  const long long total = (long long)KH * KW * n_pad * k_pad;
+  DISPATCH_DTYPE(dtype, (pack_weight_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            src, d0, d1, KH * KW, n_axis, n_pad, k_pad, (T*)dst)));
+  NG_LAUNCH_CHECK("pack_weight_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW,
+                                     int32_t n_axis, int32_t n_pad, int32_t k_pad, float* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(packed && dst && (n_axis == 0 || n_axis == 1), NG_E_ARG, "unpack_weight_grad: bad arguments");
+  const long long total = (long long)d0 * d1 * KH * KW;
+  unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, d0, d1, KH * KW, n_axis, n_pad,
+                                                                             k_pad, dst);
+  NG_LAUNCH_CHECK("unpack_wgrad_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_prep_input(const float* src_a, int32_t ca, const float* src_b, int32_t cb, int32_t B, int32_t H,
+                             int32_t W, int32_t wrap_pad, int32_t halo, int32_t halo_mode, int32_t c_pad,
+                             int32_t dtype, void* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src_a && dst && ca > 0 && cb >= 0 && (cb == 0 || src_b), NG_E_ARG, "prep_input: bad arguments");
+  NG_REQUIRE(c_pad >= ca + cb, NG_E_SHAPE, "prep_input: c_pad %d < %d channels", c_pad, ca + cb);
+  NG_REQUIRE(wrap_pad < H && wrap_pad < W, NG_E_SHAPE, "prep_input: reflect pad %d needs a larger tile", wrap_pad);
+  NG_REQUIRE(halo_mode != NG_HALO_REFLECT || (halo < H + 2 * wrap_pad && halo < W + 2 * wrap_pad), NG_E_SHAPE,
+             "prep_input: halo too large");
+  const long long total = (long long)B * (H + 2 * wrap_pad + 2 * halo) * (W + 2 * wrap_pad + 2 * halo);
+  DISPATCH_DTYPE(dtype, (prep_input_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            src_a, ca, src_b, cb, B, H, W, wrap_pad, halo, halo_mode, c_pad, (T*)dst)));
+  NG_LAUNCH_CHECK("prep_input_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_in_stats(const void* y, int32_t dtype, int32_t B, int32_t HW, int32_t C, float* mean_rstd,
+                           void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(y && mean_rstd && B > 0 && HW > 0 && C > 0, NG_E_ARG, "in_stats: bad arguments");
+  dim3 grid(B, (C + 31) / 32);
+  DISPATCH_DTYPE(dtype, (in_stats_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)y, HW, C, mean_rstd)));
+  NG_LAUNCH_CHECK("in_stats_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_in_stats_finalize(const float* partials, int32_t B, int32_t slots, int32_t C, int32_t count,
+                                    float* mean_rstd, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(partials && mean_rstd && B > 0 && slots > 0 && C > 0 && count > 0, NG_E_ARG,
+             "in_stats_finalize: bad arguments");
+  in_stats_finalize_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, B, slots, C,
+                                                                                 1.0f / (float)count, mean_rstd);
+  NG_LAUNCH_CHECK("in_stats_finalize_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C,
+                           const float* mean_rstd, int32_t act, float slope, const void* residual, int32_t res_pad,
+                           const float* inject_e, int32_t inject_mode, const float* inject_scale, void* out,
+                           int32_t out_pad, int32_t halo_mode, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(y && out, NG_E_ARG, "in_apply: null tensor");
+  NG_REQUIRE(C % 8 == 0, NG_E_SHAPE, "in_apply: C %d must be a multiple of 8", C);
+  NG_REQUIRE(inject_mode == NG_INJECT_NONE || inject_e, NG_E_ARG, "in_apply: injection without embedding map");
+  NG_REQUIRE(inject_mode == NG_INJECT_NONE || inject_mode == NG_INJECT_MUL || inject_scale, NG_E_ARG,
+             "in_apply: scaled injection without scale_param");
+  NG_REQUIRE(halo_mode != NG_HALO_REFLECT || (out_pad < H && out_pad < W), NG_E_SHAPE, "in_apply: halo too large");
+  NG_REQUIRE(((uintptr_t)y & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)residual & 15) == 0, NG_E_ALIGN,
+             "in_apply: tensors must be 16-byte aligned");
+  const long long total = (long long)B * (H + 2 * out_pad) * (W + 2 * out_pad) * (C / 8);
+  DISPATCH_DTYPE(dtype, (in_apply_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)y, B, H, W, C, mean_rstd, act, slope, (const T*)residual, res_pad, inject_e,
+                            inject_mode, inject_scale, (T*)out, out_pad, halo_mode)));
+  NG_LAUNCH_CHECK("in_apply_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_linear(const float* x, const float* w, const float* bias, int32_t B, int32_t K, int32_t N,
+                         float* y, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(x && w && y && B > 0 && K > 0 && N > 0, NG_E_ARG, "linear: bad arguments");
+  const int blocks = (N * 32 + 255) / 256;
+  linear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, w, bias, B, K, N, y);
+  NG_LAUNCH_CHECK("linear_kernel");
+  return NG_OK;
+}
+
+// scratch for the two-stage reductions lives in caller memory for ng_g_pixel_losses; lsgan maps are tiny
+// (B*30*30) so a single block suffices and needs no scratch.
+extern "C" int ng_lsgan_loss(const float* p, int64_t n, float target, float* loss, int32_t accumulate, float* grad,
+                             float gscale, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(p && loss && n > 0, NG_E_ARG, "lsgan_loss: bad arguments");
+  // single block: the PatchGAN map is B x 30 x 30; deterministic and scratch-free
+  static_assert(sizeof(float) == 4, "");
+  float* partial = loss + 1;   // loss must have room for 2 floats: [0] = loss, [1] = scratch
+  lsgan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p, (long long)n, target, partial, grad,
+                                                   gscale * 2.0f / (float)n);
+  NG_LAUNCH_CHECK("lsgan_kernel");
+  reduce_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partial, 1, 1, 1.0f / (float)n, loss, accumulate);
+  NG_LAUNCH_CHECK("reduce_partials_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_g_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
+                                 const float* weights4, float* out4, float* dpred, float* scratch, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(rgb && nir && pred && out4 && scratch && weights4, NG_E_ARG, "g_pixel_losses: bad arguments");
+  const long long total = (long long)B * HW;
+  unsigned blocks = grid_for(total, 256);
+  if (blocks > 1024) blocks = 1024;
+  g_pixel_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, nir, pred, B, HW, weights4[0], weights4[1],
+                                                               weights4[2], weights4[3], 1.0f / (float)total, scratch,
+                                                               dpred);
+  NG_LAUNCH_CHECK("g_pixel_loss_kernel");
+  reduce_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, (int)blocks, 4, 1.0f / (float)total, out4, 0);
+  NG_LAUNCH_CHECK("reduce_partials_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                            float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(p && g && m && v && n > 0 && step >= 1, NG_E_ARG, "adam_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (long long)n, lr, beta1, beta2, eps, bc1,
+                                                                 sqrtf(bc2), grad_scale);
+  NG_LAUNCH_CHECK("adam_kernel");
+  return NG_OK;
+}

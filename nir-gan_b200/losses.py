@@ -1,0 +1,80 @@
+"""Fused loss kernels behind autograd (LSGAN, L1 + NDVI/NDWI/EVI)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from .engine import require_cuda
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _LsganFn(torch.autograd.Function):
+    """mean((p - target)^2); backward = 2 (p - target) / n (computed in the same kernel)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        p = pred.contiguous().float()
+        out = torch.empty(2, dtype=torch.float32, device=p.device)     # [0] loss, [1] scratch
+        need_grad = pred.requires_grad
+        grad = torch.empty_like(p) if need_grad else None
+        L.call("ng_lsgan_loss", p.data_ptr(), p.numel(), float(target), out.data_ptr(), 0,
+               grad.data_ptr() if need_grad else None, 1.0, _stream(p))
+        if need_grad:
+            ctx.save_for_backward(grad)
+        ctx.shape = pred.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).view(ctx.shape), None
+
+
+def lsgan(pred: torch.Tensor, target: float) -> torch.Tensor:
+    require_cuda(pred, "lsgan prediction")
+    return _LsganFn.apply(pred, target)
+
+
+class _PixelLossFn(torch.autograd.Function):
+    """One pass over (rgb, nir, pred): returns [L1, NDVI, NDWI, EVI] means and keeps
+    d(sum_i w_i * loss_i)/dpred for the backward (weights fixed at call time)."""
+
+    @staticmethod
+    def forward(ctx, rgb, nir, pred, weights):
+        B, _, H, W = pred.shape
+        rgb, nir, p = rgb.contiguous().float(), nir.contiguous().float(), pred.contiguous().float()
+        out = torch.empty(4, dtype=torch.float32, device=p.device)
+        scratch = torch.empty(4 * 1024, dtype=torch.float32, device=p.device)
+        need_grad = pred.requires_grad
+        dpred = torch.empty_like(p) if need_grad else None
+        w = (L.c_f32 * 4)(*[float(v) for v in weights])
+        L.call("ng_g_pixel_losses", rgb.data_ptr(), nir.data_ptr(), p.data_ptr(), B, H * W, w, out.data_ptr(),
+               dpred.data_ptr() if need_grad else None, scratch.data_ptr(), _stream(p))
+        if need_grad:
+            ctx.save_for_backward(dpred)
+        ctx.weights = [float(v) for v in weights]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        # out_i enters the total loss as w_i * out_i, so gout == weights (up to a common factor c):
+        # dpred was computed for exactly that combination; recover c from the first non-zero weight.
+        (dpred,) = ctx.saved_tensors
+        c = None
+        for i, w in enumerate(ctx.weights):
+            if w != 0.0:
+                c = gout[i] / w
+                break
+        if c is None:
+            return None, None, torch.zeros_like(dpred), None
+        return None, None, dpred * c, None
+
+
+def pixel_losses(rgb, nir, pred, weights4):
+    """weights4 = (w_L1, w_NDVI, w_NDWI, w_EVI) that the caller will apply to the four returned means."""
+    for t, n in ((rgb, "rgb"), (nir, "nir"), (pred, "pred")):
+        require_cuda(t, n)
+    return _PixelLossFn.apply(rgb, nir, pred, tuple(weights4))

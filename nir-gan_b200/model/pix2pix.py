@@ -1,0 +1,99 @@
+"""Lightning-free B200 mirror of the hot-path parts of ``model/pix2pix.py::Px2Px_PL``.
+
+Kept: the constructor's network selection (pix2pix.py:18-86), ``forward(input, embeds=None)`` with the
+reflect-pad / crop wrapper (:88-110), ``predict_step`` (:134-163, with precomputed SatCLIP embeddings
+in place of coordinates -- the location encoder is out of scope),
+``training_step(batch, batch_idx, optimizer_idx)`` loss composition (:165-257) and
+``configure_optimizers`` (:485-492).  Dropped: Lightning hooks, wandb logging, validation plots.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import networks
+from .generator_inject import define_G_inject
+from ..losses import pixel_losses
+
+
+def _get(cfg, name, default=None):
+    return getattr(cfg, name, default) if not isinstance(cfg, dict) else cfg.get(name, default)
+
+
+class Px2Px(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt.base_configs
+        self.config = opt
+        o, sat = self.opt, opt.satclip
+        self.satclip = bool(_get(sat, "use_satclip", False))
+        style = _get(sat, "satclip_style", None)
+        if self.satclip and style == "concat":
+            self.netG = networks.define_G(o.input_nc + 1, o.output_nc, o.ngf, o.netG, o.norm, not o.no_dropout,
+                                          o.init_type, o.init_gain)
+        elif self.satclip and style == "inject":
+            self.netG = define_G_inject(self.config)
+        else:
+            self.netG = networks.define_G(o.input_nc, o.output_nc, o.ngf, o.netG, o.norm, not o.no_dropout,
+                                          o.init_type, o.init_gain)
+        self.netD = networks.define_D(o.input_nc + o.output_nc, o.ndf, o.netD, o.n_layers_D, o.norm, o.init_type,
+                                      o.init_gain)
+        self.criterionGAN = networks.GANLoss(o.gan_mode)
+        self.inject = self.satclip and style == "inject"
+
+    # pix2pix.py:88-110 -- the pad / crop is fused into the first / last kernel (wrap_pad)
+    def forward(self, input, embeds=None, use_padding=True):
+        pad = self.config.Data.padding_amount if self.config.Data.padding else 0
+        if self.inject:
+            return self.netG(input, embeds, wrap_pad=pad)
+        return self.netG(input, wrap_pad=pad)
+
+    @torch.no_grad()
+    def predict_step(self, rgb, embeds=None):
+        assert self.training is False, "Model is in training mode, set to eval mode before predicting"
+        return self.forward(rgb, embeds) if self.inject else self.forward(rgb)
+
+    def extract_batch(self, batch):
+        if self.inject:
+            return batch["rgb"], batch["nir"], batch["embeds"]
+        return batch["rgb"], batch["nir"]
+
+    def training_step(self, batch, batch_idx, optimizer_idx):
+        assert self.training is True, "Model is in eval mode, set to training mode before training"
+        if self.inject:
+            rgb, nir, embeds = self.extract_batch(batch)
+        else:
+            (rgb, nir), embeds = self.extract_batch(batch), None
+        o = self.config.base_configs
+        if optimizer_idx == 0:      # discriminator, pix2pix.py:195-212
+            with torch.no_grad():    # fake_AB.detach(): G needs no graph in the D pass
+                pred = self.forward(rgb, embeds)
+            pred_fake = self.netD(torch.cat((rgb, pred), 1))
+            loss_D_fake = self.criterionGAN(pred_fake, False)
+            pred_real = self.netD(torch.cat((rgb, nir), 1))
+            loss_D_real = self.criterionGAN(pred_real, True)
+            return loss_D_fake + loss_D_real          # no 0.5 factor (pix2pix.py:206)
+        # generator, pix2pix.py:214-257
+        pred = self.forward(rgb, embeds)
+        pred_fake = self.netD(torch.cat((rgb, pred), 1))
+        loss_G = self.criterionGAN(pred_fake, True) * o.lambda_GAN
+        if _get(o, "lambda_ssim", 0.0) > 0.0 or _get(o, "lambda_hist", 0.0) > 0.0:
+            raise NotImplementedError("ssim / hist losses are outside the nirgan_b200 hot path (weight 0 in all configs)")
+        lam_rs = float(_get(o, "lambda_rs_losses", 0.0))
+        w = _get(o, "internal_rs_loss_weights", None)
+        wd = dict(w) if isinstance(w, dict) else (vars(w) if w is not None else {})
+        if lam_rs > 0.0 and _get(o, "rs_losses_criterium", "l1") != "l1":
+            raise NotImplementedError("rs_losses_criterium other than 'l1' is outside the hot path")
+        ws = [float(o.lambda_L1)] + [lam_rs * max(float(wd.get(k, 0.0)), 0.0) if lam_rs > 0.0 else 0.0
+                                     for k in ("lambda_ndvi", "lambda_ndwi", "lambda_evi")]
+        parts = pixel_losses(rgb, nir, pred, ws)    # one fused pass: L1 + NDVI + NDWI + EVI (+ d/dpred)
+        for wi, pi in zip(ws, parts):
+            if wi != 0.0:
+                loss_G = loss_G + wi * pi
+        return loss_G
+
+    def configure_optimizers(self):
+        o = self.opt
+        optim_g = torch.optim.Adam(self.netG.parameters(), lr=o.lr, betas=(o.beta1, 0.999))
+        optim_d = torch.optim.Adam(self.netD.parameters(), lr=o.lr, betas=(o.beta1, 0.999))
+        return [optim_d, optim_g]

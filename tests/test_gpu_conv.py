@@ -1,0 +1,195 @@
+"""GPU parity of the convolution kernels (CUDA-core and tcgen05) through the C ABI.
+
+Checker: the same convolution restated with torch fp32 ops on operands rounded to the kernel's
+operand precision (TF32 disabled), so only accumulation order and the output rounding differ.
+Tolerances (written here, per the parity contract):
+  fp32 CUDA-core path    : max-abs <= 2e-5 * max|y|  (+1e-6)
+  16-bit operand paths   : max-abs <= 3e-3 * max|y|  (one 16-bit output rounding, fp32 accumulate)
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _impls():
+    from nirgan_b200 import _lib as L
+    return [pytest.param(L.IMPL_SIMT, L.F32, id="simt-f32"), pytest.param(L.IMPL_SIMT, L.F16, id="simt-f16"),
+            pytest.param(L.IMPL_TC, L.F16, id="tc-f16"), pytest.param(L.IMPL_TC, L.BF16, id="tc-bf16")]
+
+
+def _tol(dtype, ref):
+    from nirgan_b200 import _lib as L
+    scale = float(ref.abs().max())
+    return (2e-5 if dtype == L.F32 else (3e-3 if dtype == L.F16 else 1.2e-2)) * scale + 1e-6
+
+
+def _gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, generator=g, device="cuda") * scale
+
+
+# name, Cin, Cout, K, stride, pad, halo_mode, H, W, B
+CONV_CASES = [
+    ("stem7x7", 3, 64, 7, 1, 3, "reflect", 32, 32, 2),
+    ("stem7x7_odd", 3, 64, 7, 1, 3, "reflect", 36, 44, 1),
+    ("down1_s2", 64, 128, 3, 2, 1, "zero", 32, 32, 2),
+    ("down2_s2_odd", 128, 256, 3, 2, 1, "zero", 18, 18, 2),
+    ("down2_s2_69", 128, 256, 3, 2, 1, "zero", 138, 138, 1),
+    ("res3x3", 256, 256, 3, 1, 1, "reflect", 16, 16, 2),
+    ("res3x3_64", 256, 256, 3, 1, 1, "reflect", 64, 64, 2),
+    ("res3x3_odd21", 256, 256, 3, 1, 1, "reflect", 21, 21, 3),
+    ("res3x3_69", 256, 256, 3, 1, 1, "reflect", 69, 69, 1),
+    ("d_l1_k4s2", 64, 128, 4, 2, 1, "zero", 32, 32, 2),
+    ("d_l2_k4s2", 128, 256, 4, 2, 1, "zero", 16, 16, 2),
+    ("d_l3_k4s1", 256, 512, 4, 1, 1, "zero", 9, 9, 2),
+]
+
+
+@pytest.mark.parametrize("impl,dtype", _impls())
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_raw_and_stats(case, impl, dtype):
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    name, Cin, Cout, K, s, p, mode, H, W, B = case
+    x = Hh.rnd(_gen(B, Cin, H, W, seed=1), dtype)
+    w = Hh.rnd(_gen(Cout, Cin, K, K, seed=2, scale=0.05), dtype)
+    halo = p if mode == "reflect" else 0          # zero padding comes from out-of-bounds reads
+    xb = Hh.to_actbuf(x, halo, mode, dtype, c_pad=Hh.rup(Cin, 16))
+    wp = Hh.pack_weight(w, 0, Cout, Hh.rup(Cin, 16), dtype)
+    Ho, Wo = (H + 2 * p - K) // s + 1, (W + 2 * p - K) // s + 1
+    y, mr, _ = Hh.conv_call(xb, wp, Cout, K, s, p, Ho, Wo, dtype, impl, want_stats=True)
+    xr = F.pad(x, (p,) * 4, mode="reflect") if mode == "reflect" else F.pad(x, (p,) * 4)
+    ref = F.conv2d(xr, w, stride=s)
+    got = Hh.from_compact(y, B, Ho, Wo, Cout)
+    assert torch.isfinite(got).all(), f"{name}: non-finite output (unwritten rows?)"
+    err = float((got - ref).abs().max())
+    assert err <= _tol(dtype, ref), f"{name}: max-abs {err:.3e} > {_tol(dtype, ref):.3e}"
+    # InstanceNorm statistics describe the *stored* tensor
+    mu, rstd = Hh.stats_ref(got)
+    assert float((mr[..., 0] - mu).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+    assert float((mr[..., 1] / rstd - 1).abs().max()) <= 2e-4
+
+
+CONVT_CASES = [
+    ("up1", 256, 128, 8, 8, 2),
+    ("up1_odd", 256, 128, 9, 9, 1),
+    ("up2", 128, 64, 16, 16, 2),
+    ("up2_138", 128, 64, 69, 69, 1),
+]
+
+
+@pytest.mark.parametrize("impl,dtype", _impls())
+@pytest.mark.parametrize("case", CONVT_CASES, ids=[c[0] for c in CONVT_CASES])
+def test_conv_transpose_phased(case, impl, dtype):
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    name, Cin, Cout, H, W, B = case
+    x = Hh.rnd(_gen(B, Cin, H, W, seed=3), dtype)
+    w = Hh.rnd(_gen(Cin, Cout, 3, 3, seed=4, scale=0.05), dtype)      # ConvTranspose2d layout (Cin, Cout, kh, kw)
+    xb = Hh.to_actbuf(x, 0, "zero", dtype)
+    wp = Hh.pack_weight(w, 1, Cout, Cin, dtype)
+    y, mr, _ = Hh.conv_call(xb, wp, Cout, 3, 2, 1, 2 * H, 2 * W, dtype, impl, form=L.FORM_PHASED, want_stats=True)
+    ref = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=1)
+    got = Hh.from_compact(y, B, 2 * H, 2 * W, Cout)
+    assert torch.isfinite(got).all()
+    err = float((got - ref).abs().max())
+    assert err <= _tol(dtype, ref), f"{name}: max-abs {err:.3e}"
+    mu, rstd = Hh.stats_ref(got)
+    assert float((mr[..., 0] - mu).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+    assert float((mr[..., 1] / rstd - 1).abs().max()) <= 2e-4
+
+
+@pytest.mark.parametrize("impl,dtype", _impls())
+@pytest.mark.parametrize("crop,H", [(0, 32), (10, 44)])
+def test_head_conv_tanh(impl, dtype, crop, H):
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    B, Cin = 2, 64
+    x = Hh.rnd(_gen(B, Cin, H, H, seed=5), dtype)
+    w = Hh.rnd(_gen(1, Cin, 7, 7, seed=6, scale=0.02), dtype)
+    bias = _gen(1, seed=7, scale=0.1)
+    xb = Hh.to_actbuf(x, 3, "reflect", dtype)
+    wp = Hh.pack_weight(w, 0, 16, Cin, dtype)
+    y, _, _ = Hh.conv_call(xb, wp, 16, 7, 1, 3, H, H, dtype, impl, epilogue=L.EPI_HEAD, act=L.ACT_TANH, crop=crop,
+                           bias=bias)
+    ref = torch.tanh(F.conv2d(F.pad(x, (3,) * 4, mode="reflect"), w, bias))
+    if crop:
+        ref = ref[..., crop:-crop, crop:-crop]
+    got = y.view(B, 1, H - 2 * crop, H - 2 * crop)
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= (2e-5 if dtype == L.F32 else 2e-4)
+
+
+@pytest.mark.parametrize("impl,dtype", _impls())
+def test_patchgan_first_and_last_layer(impl, dtype):
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    B, H = 2, 32
+    x = Hh.rnd(_gen(B, 4, H, H, seed=8), dtype)
+    w = Hh.rnd(_gen(64, 4, 4, 4, seed=9, scale=0.05), dtype)
+    bias = _gen(64, seed=10, scale=0.1)
+    xb = Hh.to_actbuf(x, 0, "zero", dtype, c_pad=16)
+    wp = Hh.pack_weight(w, 0, 64, 16, dtype)
+    y, _, _ = Hh.conv_call(xb, wp, 64, 4, 2, 1, H // 2, H // 2, dtype, impl, epilogue=L.EPI_BIAS_ACT, act=L.ACT_LRELU,
+                           slope=0.2, bias=bias)
+    ref = F.leaky_relu(F.conv2d(x, w, bias, stride=2, padding=1), 0.2)
+    got = Hh.from_compact(y, B, H // 2, H // 2, 64)
+    assert float((got - ref).abs().max()) <= _tol(dtype, ref)
+    # last layer: 512 -> 1, k4 s1 p1, bias, no activation, fp32 output
+    x = Hh.rnd(_gen(B, 512, 7, 7, seed=11), dtype)
+    w = Hh.rnd(_gen(1, 512, 4, 4, seed=12, scale=0.02), dtype)
+    bias = _gen(1, seed=13, scale=0.1)
+    xb = Hh.to_actbuf(x, 0, "zero", dtype)
+    wp = Hh.pack_weight(w, 0, 16, 512, dtype)
+    y, _, _ = Hh.conv_call(xb, wp, 16, 4, 1, 1, 6, 6, dtype, impl, epilogue=L.EPI_HEAD, act=L.ACT_NONE, bias=bias)
+    ref = F.conv2d(x, w, bias, stride=1, padding=1)
+    assert float((y.view(B, 1, 6, 6) - ref).abs().max()) <= (5e-5 if dtype == L.F32 else 2e-3)
+
+
+@pytest.mark.parametrize("impl,dtype", _impls())
+def test_dgrad_forms(impl, dtype):
+    """The three data-gradient shapes of the training step, all served by the forward kernels."""
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    B = 2
+    # (1) dgrad of a stride-1 3x3 conv on a reflect-haloed input = full correlation with flipped taps
+    dy = Hh.rnd(_gen(B, 256, 12, 12, seed=14), dtype)
+    w = Hh.rnd(_gen(256, 256, 3, 3, seed=15, scale=0.05), dtype)             # (Cout, Cin, kh, kw)
+    xb = Hh.to_actbuf(dy, 0, "zero", dtype)
+    wp = Hh.pack_weight(w, 1, 256, 256, dtype)                                 # n = Cin of the forward conv
+    y, _, _ = Hh.conv_call(xb, wp, 256, 3, 1, 0, 14, 14, dtype, impl, sgn=-1)
+    ref = F.conv_transpose2d(dy, w, stride=1, padding=0)
+    assert float((Hh.from_compact(y, B, 14, 14, 256) - ref).abs().max()) <= _tol(dtype, ref)
+    # (2) dgrad of a 4x4 stride-2 pad-1 conv (PatchGAN) = phased transposed conv
+    dy = Hh.rnd(_gen(B, 128, 8, 8, seed=16), dtype)
+    w = Hh.rnd(_gen(128, 64, 4, 4, seed=17, scale=0.05), dtype)
+    xb = Hh.to_actbuf(dy, 0, "zero", dtype)
+    wp = Hh.pack_weight(w, 1, 64, 128, dtype)
+    y, _, _ = Hh.conv_call(xb, wp, 64, 4, 2, 1, 16, 16, dtype, impl, form=L.FORM_PHASED)
+    ref = F.conv_transpose2d(dy, w, stride=2, padding=1)
+    assert float((Hh.from_compact(y, B, 16, 16, 64) - ref).abs().max()) <= _tol(dtype, ref)
+    # (3) dgrad of ConvTranspose2d(k3,s2,p1,op1) = stride-2 3x3 conv of dy with pad 1
+    dy = Hh.rnd(_gen(B, 128, 16, 16, seed=18), dtype)
+    w = Hh.rnd(_gen(256, 128, 3, 3, seed=19, scale=0.05), dtype)             # ConvT weight (Cin=256, Cout=128)
+    xb = Hh.to_actbuf(dy, 0, "zero", dtype)
+    wp = Hh.pack_weight(w, 0, 256, 128, dtype)
+    y, _, _ = Hh.conv_call(xb, wp, 256, 3, 2, 1, 8, 8, dtype, impl)
+    ref = F.conv2d(dy, w, stride=2, padding=1)
+    assert float((Hh.from_compact(y, B, 8, 8, 256) - ref).abs().max()) <= _tol(dtype, ref)
+
+
+def test_argument_errors_are_reported():
+    """Error behaviour of the C ABI: negative status + message, never a crash."""
+    import ctypes as C
+    from nirgan_b200 import _lib as L
+    a = L.ConvArgs()
+    assert L.load().ng_conv2d(C.byref(a), None) < 0
+    assert "conv" in L.last_error()
+    assert L.load().ng_conv2d(None, None) < 0
+    with pytest.raises(RuntimeError):
+        L.call("ng_in_apply", None, L.F16, 1, 4, 4, 8, None, 0, 0.0, None, 0, None, 0, None, None, 0, 0, None)
