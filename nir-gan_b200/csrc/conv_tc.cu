@@ -227,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
             const uint32_t fb = smem_u32(&full_bar[stage]);
             const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
-            mbar_expect_tx(fb, 128 * KC * 2 + BN * KC * 2);
+            mbar_expect_tx(fb, (uint32_t)(p.BH * p.BW * KC * 2 + BN * KC * 2));   // the A box holds BH*BW (<=128) rows
             tma_load_4d(&tmA, fb, sa, c * KC, bx, by, n);
             tma_load_2d(&tmB, fb, sa + Cfg::A_BYTES, c * KC, brow);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -158,7 +158,7 @@ def test_adam_matches_torch():
         opt.step()
         L.call("ng_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 2e-4, 0.5, 0.999, 1e-8,
                step, 1.0, Hh.stream())
-        assert float((p - ref_p.detach()).abs().max()) <= 2e-7
+        assert float((p - ref_p.detach()).abs().max()) <= 5e-7      # 2 ulp at |p| ~ 2
 
 
 @pytest.mark.parametrize("kind", ["res", "down", "convT", "dk4s2", "head"])
