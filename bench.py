@@ -279,6 +279,10 @@ def main():
         "model_frac_of_sustained_peak": value * gflop_tile / 1e3 / pk["tf_sustained"],
         "op_ms": {k: round(sum(v), 4) for k, v in by_name.items()},
     }
+    if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
+        with open(os.path.join(ROOT, "gpurun_out", "op_times.json"), "w") as f:
+            json.dump([{"op": name, "label": plan.labels[i], "ms": round(op_ms[i], 5)}
+                       for i, (fn, a, name) in enumerate(plan.ops)], f, indent=0)
     if not args.no_cpu_baseline:
         v, cores, sample = cpu_oracle_tiles_per_sec()
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

@@ -73,9 +73,12 @@ typedef struct ng_conv_args {
   int32_t form;         /* NG_FORM_* */
   int32_t sgn;          /* +1 (correlation) or -1 (flipped taps; dgrad of a stride-1 conv). GATHER only */
   int32_t B, Hin, Win, Cin;   /* input interior; Cin is the stored (padded) channel count */
-  int32_t in_pad;       /* halo materialised in the input buffer */
+  int32_t in_pad;       /* halo rows materialised above/below the input interior */
+  int32_t in_pad_w;     /* halo columns materialised left/right (usually == in_pad) */
   int32_t Cout;         /* stored output channels (multiple of 8; HEAD: 16, of which channel 0 is real) */
-  int32_t KH, KW, stride, pad;
+  int32_t KH, KW, stride;
+  int32_t pad;          /* logical padding along H */
+  int32_t pad_w;        /* logical padding along W (usually == pad) */
   int32_t Hout, Wout;
   int32_t epilogue;     /* NG_EPI_* */
   int32_t act;          /* NG_ACT_* (BIAS_ACT / HEAD) */
@@ -110,6 +113,27 @@ int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t KH, int32_t
 int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
                           int32_t n_pad, int32_t k_pad, float* dst, void* stream);
 
+/* Generator stem input in "row-merged" form: NCHW fp32 -> [B][H+2*wrap+2*halo][W+2*wrap][64] `dtype`, where element
+ * (kw*8 + c) of output pixel (y, x) is channel c of the reflect-padded image at (y, x + kw)  (kw < KW <= 8, c < cin <= 8,
+ * zero elsewhere).  A KHxKW convolution over cin channels then becomes a KHx1 convolution over 64 "channels" whose
+ * GEMM-K rows are 128 contiguous bytes (one TMA / UMMA swizzle row).  Replaces ReflectionPad2d(3) + the im2col half of
+ * Conv2d(3->64, k7) (model/networks.py:341-342) and Px2Px_PL.forward's F.pad (model/pix2pix.py:91-93). */
+int ng_prep_stem(const float* src, int32_t cin, int32_t B, int32_t H, int32_t W, int32_t wrap_pad, int32_t halo,
+                 int32_t KW, int32_t dtype, void* dst, void* stream);
+/* weights for the row-merged stem: fp32 [O][I][KH][KW] -> [kh][O][kw*8 + c] (zero padded to 64) */
+int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH, int32_t KW, int32_t dtype, void* dst,
+                             void* stream);
+/* inverse for gradients: fp32 [kh][O][64] -> fp32 [O][I][KH][KW] */
+int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW, float* dst,
+                                    void* stream);
+
+/* Single-output-channel KHxKW convolution as "tap GEMM + gather": z = [B][Hz][Wz][zc] holds, per input pixel, the
+ * dot product of its channels with each of the KH*KW taps (a 1x1 ng_conv2d with Cout = zc >= KH*KW);
+ * out[n][y][x] = act(bias + sum_{kh,kw} z[n][y+kh][x+kw][kh*KW+kw]) for the (Hz-KH+1-2*crop) x (Wz-KW+1-2*crop)
+ * cropped output.  Replaces Conv2d(64->1, k7) + Tanh (model/networks.py:366-368) without the 49x im2col re-read. */
+int ng_tap_gather(const void* z, int32_t dtype, int32_t B, int32_t Hz, int32_t Wz, int32_t zc, int32_t KH, int32_t KW,
+                  const float* bias, int32_t act, int32_t crop, float* out, void* stream);
+
 /* NCHW fp32 (one or two sources concatenated on C) -> haloed NHWC `dtype` with channels zero-padded to c_pad.
  * wrap_pad: reflect padding applied first (Px2Px_PL.forward, padding_amount); halo: second reflect (or zero) halo. */
 int ng_prep_input(const float* src_a, int32_t ca, const float* src_b, int32_t cb, int32_t B, int32_t H, int32_t W,
@@ -133,7 +157,8 @@ int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, int32_t W, i
 int ng_linear(const float* x, const float* w, const float* bias, int32_t B, int32_t K, int32_t N, float* y,
               void* stream);
 
-/* mean((p - target)^2) over n elements -> loss[0] (+= when accumulate); grad (optional) = gscale*2*(p-target)/n */
+/* mean((p - target)^2) over n elements -> loss[0] (+= when accumulate); loss must have room for 2 floats
+ * (loss[1] is scratch); grad (optional) = gscale*2*(p-target)/n */
 int ng_lsgan_loss(const float* p, int64_t n, float target, float* loss, int32_t accumulate, float* grad,
                   float gscale, void* stream);
 

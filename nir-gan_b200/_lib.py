@@ -26,8 +26,8 @@ c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 class ConvArgs(C.Structure):
     """Mirror of ``struct ng_conv_args``."""
     _fields_ = [(n, c_i32) for n in (
-        "dtype", "impl", "form", "sgn", "B", "Hin", "Win", "Cin", "in_pad", "Cout", "KH", "KW", "stride", "pad",
-        "Hout", "Wout", "epilogue", "act")] + [
+        "dtype", "impl", "form", "sgn", "B", "Hin", "Win", "Cin", "in_pad", "in_pad_w", "Cout", "KH", "KW", "stride",
+        "pad", "pad_w", "Hout", "Wout", "epilogue", "act")] + [
         ("slope", c_f32), ("crop", c_i32), ("reserved", c_i32),
         ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("y", c_vp), ("stat_partials", c_vp)]
 
@@ -41,6 +41,10 @@ _SIGNATURES = {
     "ng_conv2d_wgrad": (c_i32, [C.POINTER(ConvArgs), c_vp, c_vp, c_vp]),
     "ng_pack_weight": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_unpack_weight_grad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ng_prep_stem": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ng_pack_weight_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ng_unpack_weight_grad_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ng_tap_gather": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ng_prep_input": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_vp, c_vp]),
     "ng_in_stats": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),

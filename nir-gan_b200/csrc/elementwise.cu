@@ -105,20 +105,28 @@ in_stats_kernel(const T* __restrict__ y, int HW, int C, float* __restrict__ mr) 
   }
 }
 
-// partials: [B][slots][C][2] (sum, sumsq) -> mean / rstd.  fixed summation order => deterministic.
-__global__ void in_stats_finalize_kernel(const float* __restrict__ part, int B, int slots, int C, float inv_count,
-                                         float* __restrict__ mr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * C) return;
-  const int n = i / C, c = i % C;
-  const float* p = part + ((size_t)n * slots * C + c) * 2;
-  double s = 0.0, q = 0.0;
-  for (int k = 0; k < slots; ++k) { s += p[(size_t)k * C * 2]; q += p[(size_t)k * C * 2 + 1]; }
-  const double mean = s * inv_count;
-  double var = q * inv_count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  mr[(size_t)i * 2 + 0] = (float)mean;
-  mr[(size_t)i * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+// partials: [B][slots][C][2] (sum, sumsq) -> mean / rstd.  One thread per (n, c) pair of channels walks the
+// slots in fixed order (deterministic); consecutive threads read consecutive 16-byte words.
+__global__ void __launch_bounds__(128)
+in_stats_finalize_kernel(const float* __restrict__ part, int B, int slots, int C, float inv_count,
+                         float* __restrict__ mr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // index over B * C/2
+  const int C2 = C >> 1;
+  if (i >= B * C2) return;
+  const int n = i / C2, c2 = i % C2;
+  const float4* p = reinterpret_cast<const float4*>(part + ((size_t)n * slots * C + 2 * c2) * 2);
+  double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
+  const size_t stride = (size_t)C * 2 / 4;
+#pragma unroll 4
+  for (int k = 0; k < slots; ++k) {
+    const float4 v = p[(size_t)k * stride];
+    s0 += v.x; q0 += v.y; s1 += v.z; q1 += v.w;
+  }
+  const double m0 = s0 * inv_count, m1 = s1 * inv_count;
+  double v0 = q0 * inv_count - m0 * m0, v1 = q1 * inv_count - m1 * m1;
+  v0 = v0 < 0.0 ? 0.0 : v0; v1 = v1 < 0.0 ? 0.0 : v1;
+  *reinterpret_cast<float4*>(mr + ((size_t)n * C + 2 * c2) * 2) =
+      make_float4((float)m0, (float)(1.0 / sqrt(v0 + 1e-5)), (float)m1, (float)(1.0 / sqrt(v1 + 1e-5)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -162,58 +170,69 @@ __device__ __forceinline__ float bilerp128(const float* __restrict__ e, int oy, 
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-in_apply_kernel(const T* __restrict__ y, int B, int H, int W, int C, const float* __restrict__ mr, int act,
+in_apply_kernel(const T* __restrict__ y, int B, int H, int W, int C, int c8_shift, const float* __restrict__ mr, int act,
                 float slope, const T* __restrict__ res, int res_pad, const float* __restrict__ inj, int inj_mode,
-                const float* __restrict__ inj_scale, T* __restrict__ out, int op, int halo_mode) {
+                const float* __restrict__ inj_scale, T* __restrict__ out, int op, int halo_mode, int rows_per_block) {
+  // blocks own whole output rows (n, yo): no per-element division by H/W, loads of one row are independent
   const int Ho = H + 2 * op, Wo = W + 2 * op, C8 = C >> 3;
-  const long long total = (long long)B * Ho * Wo * C8;
   const float s = (inj_mode != NG_INJECT_NONE && inj_scale) ? *inj_scale : 1.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    long long p = i / C8;
-    const int xo = (int)(p % Wo); p /= Wo;
-    const int yo = (int)(p % Ho);
-    const int n = (int)(p / Ho);
-    int ys = yo - op, xs = xo - op;
-    float f[8];
-    T* o = out + (((size_t)n * Ho + yo) * Wo + xo) * C + c8 * 8;
-    if (halo_mode == NG_HALO_REFLECT) { ys = reflect_idx(ys, H); xs = reflect_idx(xs, W); }
-    else if (ys < 0 || ys >= H || xs < 0 || xs >= W) {
+  const int row_elems = Wo * C8;
+  for (int r = 0; r < rows_per_block; ++r) {
+    const long long grow = (long long)blockIdx.x * rows_per_block + r;
+    if (grow >= (long long)B * Ho) return;
+    const int yo = (int)(grow % Ho), n = (int)(grow / Ho);
+    int ys = yo - op;
+    const bool row_zero = halo_mode != NG_HALO_REFLECT && (ys < 0 || ys >= H);
+    if (halo_mode == NG_HALO_REFLECT) ys = reflect_idx(ys, H);
+    T* orow = out + ((size_t)n * Ho + yo) * Wo * C;
+    const T* yrow = y + ((size_t)n * H + (row_zero ? 0 : ys)) * W * C;
+    const float* mrn = mr ? mr + (size_t)n * C * 2 : nullptr;
+    const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
+    const T* rrow = res ? res + (((size_t)n * Hr + ys + res_pad) * Wr + res_pad) * C : nullptr;
+    const float* injn = inj ? inj + (size_t)n * 128 * 128 : nullptr;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < row_elems; e += 256) {
+      const int xo = e >> c8_shift, c8 = e & (C8 - 1);
+      int xs = xo - op;
+      float f[8];
+      bool zero = row_zero;
+      if (halo_mode == NG_HALO_REFLECT) xs = reflect_idx(xs, W);
+      else zero = zero || xs < 0 || xs >= W;
+      if (zero) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = 0.f;
-      store8<T>(o, f);
-      continue;
-    }
-    load8<T>(y + (((size_t)n * H + ys) * W + xs) * C + c8 * 8, f);
-    if (mr) {
-      const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 m = m4[k];
-        f[2 * k] = (f[2 * k] - m.x) * m.y;
-        f[2 * k + 1] = (f[2 * k + 1] - m.z) * m.w;
+        for (int k = 0; k < 8; ++k) f[k] = 0.f;
+        store8<T>(orow + (size_t)e * 8, f);
+        continue;
       }
-    }
-    if (inj_mode != NG_INJECT_NONE) {
-      const float e = bilerp128(inj + (size_t)n * 128 * 128, ys, xs, H, W);
+      load8<T>(yrow + ((size_t)xs * C8 + c8) * 8, f);
+      if (mrn) {
+        const float4* m4 = reinterpret_cast<const float4*>(mrn + c8 * 16);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (inj_mode == NG_INJECT_ADD) f[k] = f[k] + s * e;
-        else if (inj_mode == NG_INJECT_MUL_SCALED) f[k] = f[k] * (1.f + s * e);
-        else f[k] = f[k] * e;
+        for (int k = 0; k < 4; ++k) {
+          const float4 m = m4[k];
+          f[2 * k] = (f[2 * k] - m.x) * m.y;
+          f[2 * k + 1] = (f[2 * k + 1] - m.z) * m.w;
+        }
       }
-    }
+      if (inj_mode != NG_INJECT_NONE) {
+        const float ev = bilerp128(injn, ys, xs, H, W);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = apply_act(f[k], act, slope);
-    if (res) {
-      float r[8];
-      const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
-      load8<T>(res + (((size_t)n * Hr + ys + res_pad) * Wr + xs + res_pad) * C + c8 * 8, r);
+        for (int k = 0; k < 8; ++k) {
+          if (inj_mode == NG_INJECT_ADD) f[k] = f[k] + s * ev;
+          else if (inj_mode == NG_INJECT_MUL_SCALED) f[k] = f[k] * (1.f + s * ev);
+          else f[k] = f[k] * ev;
+        }
+      }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] += r[k];
+      for (int k = 0; k < 8; ++k) f[k] = apply_act(f[k], act, slope);
+      if (rrow) {
+        float rv[8];
+        load8<T>(rrow + ((size_t)xs * C8 + c8) * 8, rv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += rv[k];
+      }
+      store8<T>(orow + (size_t)e * 8, f);
     }
-    store8<T>(o, f);
   }
 }
 
@@ -347,6 +366,93 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// generator stem in row-merged form (see ng_prep_stem in the header): one thread = one 16-byte
+// (kw, 8-channel) group of one output pixel.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+prep_stem_kernel(const float* __restrict__ src, int cin, int B, int H, int W, int wrap, int halo, int KW,
+                 T* __restrict__ dst) {
+  const int H1 = H + 2 * wrap, W1 = W + 2 * wrap, Hb = H1 + 2 * halo;
+  const long long total = (long long)B * Hb * W1 * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int kw = (int)(i & 7);
+    long long p = i >> 3;
+    const int x = (int)(p % W1); p /= W1;
+    const int yb = (int)(p % Hb);
+    const int n = (int)(p / Hb);
+    float f[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = 0.f;
+    if (kw < KW) {
+      // column x + kw of the (halo-padded) image = column (x + kw - halo) of the wrapper-padded image
+      const int y1 = reflect_idx(yb - halo, H1), x1 = reflect_idx(x + kw - halo, W1);
+      const int y0 = reflect_idx(y1 - wrap, H), x0 = reflect_idx(x1 - wrap, W);
+      for (int c = 0; c < cin; ++c) f[c] = src[(((long long)n * cin + c) * H + y0) * W + x0];
+    }
+    T* o = dst + i * 8;
+    if constexpr (sizeof(T) == 2) {
+      uint4 u;
+      u.x = pack2<T>(f[0], f[1]); u.y = pack2<T>(f[2], f[3]); u.z = pack2<T>(f[4], f[5]); u.w = pack2<T>(f[6], f[7]);
+      *reinterpret_cast<uint4*>(o) = u;
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void pack_rowmerged_kernel(const float* __restrict__ src, int O, int I, int KH, int KW, T* __restrict__ dst) {
+  const int total = KH * O * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i & 63, o = (i >> 6) % O, kh = (i >> 6) / O;
+    const int kw = e >> 3, c = e & 7;
+    float v = 0.f;
+    if (kw < KW && c < I) v = src[(((long long)o * I + c) * KH + kh) * KW + kw];
+    dst[i] = from_f32<T>(v);
+  }
+}
+
+__global__ void unpack_rowmerged_kernel(const float* __restrict__ packed, int O, int I, int KH, int KW,
+                                        float* __restrict__ dst) {
+  const int total = O * I * KH * KW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kw = i % KW, kh = (i / KW) % KH, c = (i / (KW * KH)) % I, o = i / (KW * KH * I);
+    dst[i] = packed[((long long)kh * O + o) * 64 + kw * 8 + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tap gather: out[n][y][x] = act(bias + sum_t z[n][y+kh][x+kw][t])   (see ng_tap_gather)
+// one warp = 32 consecutive output columns of one row; lanes walk the taps.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+tap_gather_kernel(const T* __restrict__ z, int B, int Hz, int Wz, int zc, int KH, int KW,
+                  const float* __restrict__ bias, int act, int crop, float* __restrict__ out) {
+  const int Ho = Hz - KH + 1 - 2 * crop, Wo = Wz - KW + 1 - 2 * crop;
+  const long long total = (long long)B * Ho * Wo;
+  const float b0 = bias ? bias[0] : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wo);
+    const int y = (int)((i / Wo) % Ho);
+    const int n = (int)(i / ((long long)Wo * Ho));
+    const T* base = z + (((long long)n * Hz + y + crop) * Wz + x + crop) * zc;
+    float s = 0.f;
+    for (int kh = 0; kh < KH; ++kh) {
+      const T* row = base + (long long)kh * Wz * zc + kh * KW;
+#pragma unroll 7
+      for (int kw = 0; kw < KW; ++kw) s += to_f32<T>(row[(long long)kw * zc + kw]);
+    }
+    out[i] = apply_act(s + b0, act, 0.f);
+  }
+}
+
 static inline unsigned grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 8;   // 8 resident CTAs of 256 threads per SM
@@ -422,8 +528,9 @@ extern "C" int ng_in_stats_finalize(const float* partials, int32_t B, int32_t sl
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(partials && mean_rstd && B > 0 && slots > 0 && C > 0 && count > 0, NG_E_ARG,
              "in_stats_finalize: bad arguments");
-  in_stats_finalize_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, B, slots, C,
-                                                                                 1.0f / (float)count, mean_rstd);
+  NG_REQUIRE(C % 2 == 0, NG_E_SHAPE, "in_stats_finalize: C must be even");
+  in_stats_finalize_kernel<<<(B * C / 2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, B, slots, C,
+                                                                                     1.0f / (float)count, mean_rstd);
   NG_LAUNCH_CHECK("in_stats_finalize_kernel");
   return NG_OK;
 }
@@ -441,10 +548,18 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   NG_REQUIRE(halo_mode != NG_HALO_REFLECT || (out_pad < H && out_pad < W), NG_E_SHAPE, "in_apply: halo too large");
   NG_REQUIRE(((uintptr_t)y & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)residual & 15) == 0, NG_E_ALIGN,
              "in_apply: tensors must be 16-byte aligned");
-  const long long total = (long long)B * (H + 2 * out_pad) * (W + 2 * out_pad) * (C / 8);
-  DISPATCH_DTYPE(dtype, (in_apply_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                            (const T*)y, B, H, W, C, mean_rstd, act, slope, (const T*)residual, res_pad, inject_e,
-                            inject_mode, inject_scale, (T*)out, out_pad, halo_mode)));
+  const int C8 = C / 8;
+  NG_REQUIRE((C8 & (C8 - 1)) == 0, NG_E_SHAPE, "in_apply: C/8 must be a power of two (C = %d)", C);
+  int c8_shift = 0;
+  while ((1 << c8_shift) < C8) ++c8_shift;
+  const long long rows = (long long)B * (H + 2 * out_pad);
+  const int row_elems = (W + 2 * out_pad) * C8;
+  int rpb = 1;                                   // give every block >= ~2048 16-byte items
+  while ((long long)rpb * row_elems < 2048 && rpb < 16) rpb *= 2;
+  const long long blocks = (rows + rpb - 1) / rpb;
+  DISPATCH_DTYPE(dtype, (in_apply_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)y, B, H, W, C, c8_shift, mean_rstd, act, slope, (const T*)residual, res_pad,
+                            inject_e, inject_mode, inject_scale, (T*)out, out_pad, halo_mode, rpb)));
   NG_LAUNCH_CHECK("in_apply_kernel");
   return NG_OK;
 }
@@ -500,5 +615,50 @@ extern "C" int ng_adam_step(float* p, const float* g, float* m, float* v, int64_
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (long long)n, lr, beta1, beta2, eps, bc1,
                                                                  sqrtf(bc2), grad_scale);
   NG_LAUNCH_CHECK("adam_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_prep_stem(const float* src, int32_t cin, int32_t B, int32_t H, int32_t W, int32_t wrap_pad,
+                            int32_t halo, int32_t KW, int32_t dtype, void* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src && dst && cin > 0 && cin <= 8 && KW > 0 && KW <= 8, NG_E_ARG, "prep_stem: cin and KW must be in 1..8");
+  NG_REQUIRE(wrap_pad < H && wrap_pad < W && halo < H + 2 * wrap_pad && halo < W + 2 * wrap_pad, NG_E_SHAPE,
+             "prep_stem: reflect padding needs a larger tile");
+  const long long total = (long long)B * (H + 2 * wrap_pad + 2 * halo) * (W + 2 * wrap_pad) * 8;
+  DISPATCH_DTYPE(dtype, (prep_stem_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            src, cin, B, H, W, wrap_pad, halo, KW, (T*)dst)));
+  NG_LAUNCH_CHECK("prep_stem_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH, int32_t KW, int32_t dtype,
+                                        void* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src && dst && I > 0 && I <= 8 && KW > 0 && KW <= 8, NG_E_ARG, "pack_weight_rowmerged: I and KW must be in 1..8");
+  DISPATCH_DTYPE(dtype, (pack_rowmerged_kernel<T><<<grid_for((long long)KH * O * 64, 256), 256, 0, (cudaStream_t)stream>>>(
+                            src, O, I, KH, KW, (T*)dst)));
+  NG_LAUNCH_CHECK("pack_rowmerged_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW,
+                                               float* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(packed && dst && I > 0 && I <= 8 && KW > 0 && KW <= 8, NG_E_ARG, "unpack_weight_grad_rowmerged: bad arguments");
+  unpack_rowmerged_kernel<<<grid_for((long long)O * I * KH * KW, 256), 256, 0, (cudaStream_t)stream>>>(packed, O, I, KH,
+                                                                                                      KW, dst);
+  NG_LAUNCH_CHECK("unpack_rowmerged_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_tap_gather(const void* z, int32_t dtype, int32_t B, int32_t Hz, int32_t Wz, int32_t zc, int32_t KH,
+                             int32_t KW, const float* bias, int32_t act, int32_t crop, float* out, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(z && out && KH * KW <= zc, NG_E_ARG, "tap_gather: need KH*KW <= zc");
+  NG_REQUIRE(Hz - KH + 1 - 2 * crop > 0 && Wz - KW + 1 - 2 * crop > 0, NG_E_SHAPE, "tap_gather: empty output");
+  const long long total = (long long)B * (Hz - KH + 1 - 2 * crop) * (Wz - KW + 1 - 2 * crop);
+  DISPATCH_DTYPE(dtype, (tap_gather_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)z, B, Hz, Wz, zc, KH, KW, bias, act, crop, out)));
+  NG_LAUNCH_CHECK("tap_gather_kernel");
   return NG_OK;
 }

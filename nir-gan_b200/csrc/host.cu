@@ -69,11 +69,11 @@ int build_geometry(const ng_conv_args& a, ConvGeom& g) {
   NG_REQUIRE(a.B > 0 && a.Hin > 0 && a.Win > 0 && a.Cin > 0 && a.Cout > 0, NG_E_SHAPE, "conv: empty shape");
   NG_REQUIRE(a.KH > 0 && a.KW > 0 && a.KH * a.KW <= 64, NG_E_SHAPE, "conv: kernel %dx%d unsupported", a.KH, a.KW);
   NG_REQUIRE(a.stride == 1 || a.stride == 2, NG_E_UNSUPPORTED, "conv: stride %d unsupported", a.stride);
-  NG_REQUIRE(a.in_pad >= 0 && a.pad >= 0, NG_E_ARG, "conv: negative padding");
+  NG_REQUIRE(a.in_pad >= 0 && a.pad >= 0 && a.in_pad_w >= 0 && a.pad_w >= 0, NG_E_ARG, "conv: negative padding");
   memset(&g, 0, sizeof(g));
   g.B = a.B;
   g.Hb = a.Hin + 2 * a.in_pad;
-  g.Wb = a.Win + 2 * a.in_pad;
+  g.Wb = a.Win + 2 * a.in_pad_w;
   g.Cin = a.Cin;
   g.Cout = a.Cout;
   g.Hout = a.Hout;
@@ -82,7 +82,7 @@ int build_geometry(const ng_conv_args& a, ConvGeom& g) {
     NG_REQUIRE(a.sgn == 1 || a.sgn == -1, NG_E_ARG, "conv: sgn must be +-1");
     NG_REQUIRE(a.sgn == 1 || a.stride == 1, NG_E_UNSUPPORTED, "conv: flipped taps need stride 1");
     int eh = a.sgn == 1 ? (a.Hin + 2 * a.pad - a.KH) / a.stride + 1 : a.Hin + a.KH - 1 - 2 * a.pad;
-    int ew = a.sgn == 1 ? (a.Win + 2 * a.pad - a.KW) / a.stride + 1 : a.Win + a.KW - 1 - 2 * a.pad;
+    int ew = a.sgn == 1 ? (a.Win + 2 * a.pad_w - a.KW) / a.stride + 1 : a.Win + a.KW - 1 - 2 * a.pad_w;
     NG_REQUIRE(a.Hout == eh && a.Wout == ew, NG_E_SHAPE, "conv: Hout/Wout %dx%d, expected %dx%d", a.Hout, a.Wout,
                eh, ew);
     g.VH = a.Hout; g.VW = a.Wout; g.S = a.stride; g.OS = 1; g.nphase = 1;
@@ -91,13 +91,15 @@ int build_geometry(const ng_conv_args& a, ConvGeom& g) {
     for (int kh = 0; kh < a.KH; ++kh)
       for (int kw = 0; kw < a.KW; ++kw, ++t) {
         g.taps[t].dy = (int16_t)(a.sgn * (kh - a.pad) + a.in_pad);
-        g.taps[t].dx = (int16_t)(a.sgn * (kw - a.pad) + a.in_pad);
+        g.taps[t].dx = (int16_t)(a.sgn * (kw - a.pad_w) + a.in_pad_w);
         g.taps[t].wrow = (kh * a.KW + kw) * a.Cout;
       }
     g.ntaps = t;
     g.phase_tap0[1] = t;
   } else if (a.form == NG_FORM_PHASED) {
     NG_REQUIRE(a.stride == 2, NG_E_UNSUPPORTED, "phased conv: stride must be 2");
+    NG_REQUIRE(a.pad == a.pad_w && a.in_pad == a.in_pad_w && a.KH == a.KW, NG_E_UNSUPPORTED,
+               "phased conv: symmetric kernels / padding only");
     int s = a.stride;
     g.VH = (a.Hout + s - 1) / s; g.VW = (a.Wout + s - 1) / s; g.S = 1; g.OS = s; g.nphase = s * s;
     int t = 0;

@@ -112,10 +112,12 @@ class Plan:
         self.keepalive: list = []
         self.launches = 0          # kernel launches per run (for bench.py's gpu_launches)
         self.records: dict = {}
+        self.labels: List[str] = []
 
-    def add(self, fn_name: str, *args, launches: int = 1):
+    def add(self, fn_name: str, *args, launches: int = 1, label: str = ""):
         fn = getattr(L.load(), fn_name)
         self.ops.append((fn, args, fn_name))
+        self.labels.append(label or fn_name)
         self.launches += launches
 
     def run(self, stream_ptr: int):
@@ -139,20 +141,30 @@ class Engine:
 
     # ---- weights -----------------------------------------------------------------------------
     def packed_weight(self, w: torch.Tensor, n_axis: int, n_pad: int, k_pad: int, stream: int) -> torch.Tensor:
-        """fp32 master (4-D) -> packed [tap][n_pad][k_pad] shadow, refreshed when the master changes."""
+        """fp32 master (4-D) -> packed shadow, refreshed when the master changes.
+        n_axis 0/1: [tap][n_pad][k_pad];  n_axis 'rowmerged': [kh][O][kw*8+c] (stem);
+        n_axis 'taps': [n = tap (padded to n_pad)][k_pad] for the tap-GEMM form of a 1-output-channel conv."""
         key = (w.data_ptr(), n_axis, n_pad, k_pad, self.dt_enum)
         ver = w._version
         hit = self._packed.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
         d0, d1, kh, kw = w.shape
-        dst = hit[1] if hit is not None else torch.empty(kh * kw * n_pad * k_pad, dtype=self.dt_torch,
-                                                         device=self.device)
         src = w.detach()
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.float().contiguous()
-        L.call("ng_pack_weight", src.data_ptr(), d0, d1, kh, kw, n_axis, n_pad, k_pad, self.dt_enum,
-               dst.data_ptr(), stream)
+        if n_axis == "rowmerged":
+            dst = hit[1] if hit is not None else torch.empty(kh * d0 * 64, dtype=self.dt_torch, device=self.device)
+            L.call("ng_pack_weight_rowmerged", src.data_ptr(), d0, d1, kh, kw, self.dt_enum, dst.data_ptr(), stream)
+        elif n_axis == "taps":
+            assert d0 == 1 and kh * kw <= n_pad
+            dst = hit[1] if hit is not None else torch.zeros(n_pad * k_pad, dtype=self.dt_torch, device=self.device)
+            L.call("ng_pack_weight", src.data_ptr(), d0, d1, kh, kw, 0, 1, k_pad, self.dt_enum, dst.data_ptr(), stream)
+        else:
+            dst = hit[1] if hit is not None else torch.empty(kh * kw * n_pad * k_pad, dtype=self.dt_torch,
+                                                             device=self.device)
+            L.call("ng_pack_weight", src.data_ptr(), d0, d1, kh, kw, n_axis, n_pad, k_pad, self.dt_enum,
+                   dst.data_ptr(), stream)
         self._packed[key] = (ver, dst)
         return dst
 
@@ -165,11 +177,14 @@ class Engine:
     def conv_args(self, x: ActBuf, w: torch.Tensor, y: torch.Tensor, Cout: int, K: int, stride: int, pad: int,
                   Hout: int, Wout: int, form=L.FORM_GATHER, sgn=1, epilogue=L.EPI_RAW, act=L.ACT_NONE, slope=0.0,
                   crop=0, bias: Optional[torch.Tensor] = None, partials: Optional[torch.Tensor] = None,
-                  impl: Optional[int] = None) -> L.ConvArgs:
+                  impl: Optional[int] = None, KW: Optional[int] = None, pad_w: Optional[int] = None,
+                  in_pad_w: Optional[int] = None) -> L.ConvArgs:
         a = L.ConvArgs()
         a.dtype, a.impl, a.form, a.sgn = self.dt_enum, self.impl if impl is None else impl, form, sgn
         a.B, a.Hin, a.Win, a.Cin, a.in_pad = x.B, x.H, x.W, x.C, x.pad
-        a.Cout, a.KH, a.KW, a.stride, a.pad = Cout, K, K, stride, pad
+        a.in_pad_w = x.pad if in_pad_w is None else in_pad_w
+        a.Cout, a.KH, a.KW, a.stride, a.pad = Cout, K, (K if KW is None else KW), stride, pad
+        a.pad_w = pad if pad_w is None else pad_w
         a.Hout, a.Wout = Hout, Wout
         a.epilogue, a.act, a.slope, a.crop = epilogue, act, slope, crop
         a.x, a.w, a.bias, a.y = x.t.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr()
@@ -177,11 +192,11 @@ class Engine:
         return a
 
     def add_conv_norm(self, plan: Plan, name: str, x: ActBuf, w_packed: torch.Tensor, Cout: int, K: int, stride: int,
-                      pad: int, Hout: int, Wout: int, form=L.FORM_GATHER, sgn=1):
+                      pad: int, Hout: int, Wout: int, form=L.FORM_GATHER, sgn=1, **geom):
         """conv -> compact pre-norm Y + (mean, rstd).  Returns (Y ActBuf, mean_rstd tensor)."""
         y = self.act(name + ".y", x.B, Hout, Wout, Cout, 0)
         mr = self.buffers.get(name + ".mr", x.B * Cout * 2, torch.float32)
-        a = self.conv_args(x, w_packed, y.t, Cout, K, stride, pad, Hout, Wout, form, sgn)
+        a = self.conv_args(x, w_packed, y.t, Cout, K, stride, pad, Hout, Wout, form, sgn, **geom)
         if self.impl == L.IMPL_TC:
             slots = L.load().ng_conv_stat_slots(C.byref(a))
             if slots <= 0:
@@ -189,12 +204,14 @@ class Engine:
             part = self.buffers.get(name + ".part", x.B * slots * Cout * 2, torch.float32)
             a.stat_partials = part.data_ptr()
             plan.keepalive.append(a)
-            plan.add("ng_conv2d", C.byref(a))
-            plan.add("ng_in_stats_finalize", part.data_ptr(), x.B, slots, Cout, Hout * Wout, mr.data_ptr())
+            plan.add("ng_conv2d", C.byref(a), label=name)
+            plan.add("ng_in_stats_finalize", part.data_ptr(), x.B, slots, Cout, Hout * Wout, mr.data_ptr(),
+                     label=name + ".fin")
         else:
             plan.keepalive.append(a)
-            plan.add("ng_conv2d", C.byref(a))
-            plan.add("ng_in_stats", y.t.data_ptr(), self.dt_enum, x.B, Hout * Wout, Cout, mr.data_ptr())
+            plan.add("ng_conv2d", C.byref(a), label=name)
+            plan.add("ng_in_stats", y.t.data_ptr(), self.dt_enum, x.B, Hout * Wout, Cout, mr.data_ptr(),
+                     label=name + ".stats")
         return y, mr
 
     def add_apply(self, plan: Plan, name: str, y: ActBuf, mr: Optional[torch.Tensor], act: int, out_pad: int,
@@ -204,7 +221,7 @@ class Engine:
         out = self.act(name, y.B, y.H, y.W, y.C, out_pad)
         plan.add("ng_in_apply", y.t.data_ptr(), self.dt_enum, y.B, y.H, y.W, y.C, _ptr(mr), act, slope,
                  _ptr(residual.t) if residual else None, residual.pad if residual else 0, _ptr(inject_e),
-                 inject_mode, _ptr(inject_scale), out.t.data_ptr(), out_pad, halo_mode)
+                 inject_mode, _ptr(inject_scale), out.t.data_ptr(), out_pad, halo_mode, label=name)
         return out
 
 
@@ -221,6 +238,7 @@ class GeneratorRunner:
         self.cfg = cfg or EngineConfig.from_env()
         self._engine: Optional[Engine] = None
         self._plans: Dict[Tuple, Plan] = {}
+        self.head_mode = os.environ.get("NIRGAN_B200_HEAD", "tapgemm")     # 'tapgemm' | 'direct'
 
     # lazily bound to the device of the first input
     def engine(self, device) -> Engine:
@@ -254,14 +272,18 @@ class GeneratorRunner:
             wrec.append((conv, n_axis, n_pad, k_pad))
             return pw(conv, n_axis, n_pad, k_pad)
 
-        # input: NCHW fp32 -> NHWC, wrapper reflect pad + stem reflect halo 3, channels padded to 16
+        # input: NCHW fp32 -> row-merged NHWC [B][H1+6][W1][kw*8+c] (wrapper reflect pad + stem reflect halo fused):
+        # the 7x7x3 stem becomes a 7x1 conv over 64 "channels" = 7 K-steps of 128-byte rows instead of 49 thin taps
         src = eng.buffers.get("g.in", B * cin * H * W, torch.float32)
         plan.records["src"] = src
-        x0 = eng.act("g.x0", B, H1, W1, 16, 3)
-        plan.add("ng_prep_input", src.data_ptr(), cin, None, 0, B, H, W, wrap, 3, L.HALO_REFLECT, 16, eng.dt_enum,
-                 x0.t.data_ptr())
-        # stem 7x7 (bias cancelled by InstanceNorm -> skipped)
-        y, mr = eng.add_conv_norm(plan, "g.stem", x0, W_(stem, 0, ngf, 16), ngf, 7, 1, 3, H1, W1)
+        if cin > 8:
+            raise NotImplementedError("nirgan_b200 stem kernel: input_nc <= 8")
+        x0 = ActBuf(eng.buffers.get("g.x0", B * (H1 + 6) * W1 * 64, eng.dt_torch), B, H1, W1, 64, 3)
+        plan.add("ng_prep_stem", src.data_ptr(), cin, B, H, W, wrap, 3, 7, eng.dt_enum, x0.t.data_ptr(),
+                 label="g.prep")
+        # stem (bias cancelled by InstanceNorm -> skipped)
+        y, mr = eng.add_conv_norm(plan, "g.stem", x0, W_(stem, "rowmerged", ngf, 64), ngf, 7, 1, 3, H1, W1,
+                                  KW=1, pad_w=0, in_pad_w=0)
         x = eng.add_apply(plan, "g.x1", y, mr, L.ACT_RELU, 0)
         # down 1 (+ SatCLIP injection between IN and ReLU)
         H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
@@ -312,12 +334,23 @@ class GeneratorRunner:
         y, mr = eng.add_conv_norm(plan, "g.u2", x, W_(u2, 1, ngf, 2 * ngf), ngf, 3, 2, 1, 4 * H3, 4 * W3,
                                   form=L.FORM_PHASED)
         x = eng.add_apply(plan, "g.x6", y, mr, L.ACT_RELU, 3)
-        # head 7x7 -> 1 channel (+bias, tanh), fp32 NCHW, wrapper crop fused
+        # head 7x7 -> 1 channel (+bias, tanh), fp32 NCHW, wrapper crop fused.
         out = eng.buffers.get("g.out", B * H * W, torch.float32)
-        a = eng.conv_args(x, W_(head, 0, 16, ngf), out, 16, 7, 1, 3, H1, W1, epilogue=L.EPI_HEAD, act=L.ACT_TANH,
-                          crop=wrap, bias=head.bias.data)
-        plan.keepalive.append(a)
-        plan.add("ng_conv2d", C.byref(a))
+        if self.head_mode == "tapgemm" and ngf == 64:
+            # tap GEMM + gather: z[pixel][tap] = <x[pixel,:], w[tap,:]> over the haloed buffer (each input pixel
+            # read once, no 49x im2col re-read), then out = tanh(b + sum_t z[(y+kh, x+kw), t])
+            xz = ActBuf(x.t, B, H1 + 6, W1 + 6, ngf, 0)
+            z = eng.act("g.z", B, H1 + 6, W1 + 6, 64, 0)
+            a = eng.conv_args(xz, W_(head, "taps", 64, ngf), z.t, 64, 1, 1, 0, H1 + 6, W1 + 6)
+            plan.keepalive.append(a)
+            plan.add("ng_conv2d", C.byref(a), label="g.head.gemm")
+            plan.add("ng_tap_gather", z.t.data_ptr(), eng.dt_enum, B, H1 + 6, W1 + 6, 64, 7, 7, head.bias.data_ptr(),
+                     L.ACT_TANH, wrap, out.data_ptr(), label="g.head.gather")
+        else:
+            a = eng.conv_args(x, W_(head, 0, 16, ngf), out, 16, 7, 1, 3, H1, W1, epilogue=L.EPI_HEAD,
+                              act=L.ACT_TANH, crop=wrap, bias=head.bias.data)
+            plan.keepalive.append(a)
+            plan.add("ng_conv2d", C.byref(a), label="g.head")
         plan.records["out"] = out
         plan.records["post"] = getattr(mod, "post_correction", False)
         return plan

@@ -57,8 +57,8 @@ def conv_call(x: ActBuf, wp: torch.Tensor, Cout: int, K: int, stride: int, pad: 
         y = torch.full((x.B * Hout * Wout * Cout,), float("nan"), dtype=torch.float32, device=dev).to(TORCH_DT[dtype])
     a = L.ConvArgs()
     a.dtype, a.impl, a.form, a.sgn = dtype, impl, form, sgn
-    a.B, a.Hin, a.Win, a.Cin, a.in_pad = x.B, x.H, x.W, x.C, x.pad
-    a.Cout, a.KH, a.KW, a.stride, a.pad = Cout, K, K, stride, pad
+    a.B, a.Hin, a.Win, a.Cin, a.in_pad, a.in_pad_w = x.B, x.H, x.W, x.C, x.pad, x.pad
+    a.Cout, a.KH, a.KW, a.stride, a.pad, a.pad_w = Cout, K, K, stride, pad, pad
     a.Hout, a.Wout = Hout, Wout
     a.epilogue, a.act, a.slope, a.crop = epilogue, act, slope, crop
     a.x, a.w, a.y = x.t.data_ptr(), wp.data_ptr(), y.data_ptr()

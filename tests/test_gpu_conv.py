@@ -193,3 +193,68 @@ def test_argument_errors_are_reported():
     assert L.load().ng_conv2d(None, None) < 0
     with pytest.raises(RuntimeError):
         L.call("ng_in_apply", None, L.F16, 1, 4, 4, 8, None, 0, 0.0, None, 0, None, 0, None, None, 0, 0, None)
+
+
+@pytest.mark.parametrize("impl,dtype", _impls())
+@pytest.mark.parametrize("wrap,H,W", [(0, 32, 32), (10, 24, 36)])
+def test_stem_rowmerged(impl, dtype, wrap, H, W):
+    """ng_prep_stem + 7x1 conv over 64 merged (kw, c) channels == ReflectionPad2d(3) + Conv2d(3->64, k7)
+    on the (optionally wrapper-padded) tile."""
+    import ctypes as C
+    from nirgan_b200 import _lib as L
+    from nirgan_b200.engine import ActBuf
+    import helpers as Hh
+    B = 2
+    x = _gen(B, 3, H, W, seed=21)
+    w = Hh.rnd(_gen(64, 3, 7, 7, seed=22, scale=0.05), dtype)
+    H1, W1 = H + 2 * wrap, W + 2 * wrap
+    x0 = torch.empty(B * (H1 + 6) * W1 * 64, dtype=Hh.TORCH_DT[dtype], device="cuda")
+    L.call("ng_prep_stem", x.data_ptr(), 3, B, H, W, wrap, 3, 7, dtype, x0.data_ptr(), Hh.stream())
+    wp = torch.empty(7 * 64 * 64, dtype=Hh.TORCH_DT[dtype], device="cuda")
+    L.call("ng_pack_weight_rowmerged", w.data_ptr(), 64, 3, 7, 7, dtype, wp.data_ptr(), Hh.stream())
+    y = torch.full((B * H1 * W1 * 64,), float("nan"), device="cuda").to(Hh.TORCH_DT[dtype])
+    a = L.ConvArgs()
+    a.dtype, a.impl, a.form, a.sgn = dtype, impl, L.FORM_GATHER, 1
+    a.B, a.Hin, a.Win, a.Cin, a.in_pad, a.in_pad_w = B, H1, W1, 64, 3, 0
+    a.Cout, a.KH, a.KW, a.stride, a.pad, a.pad_w, a.Hout, a.Wout = 64, 7, 1, 1, 3, 0, H1, W1
+    a.x, a.w, a.y = x0.data_ptr(), wp.data_ptr(), y.data_ptr()
+    L.call("ng_conv2d", C.byref(a), Hh.stream())
+    xr = Hh.rnd(x, dtype)
+    if wrap:
+        xr = F.pad(xr, (wrap,) * 4, mode="reflect")
+    ref = F.conv2d(F.pad(xr, (3,) * 4, mode="reflect"), w)
+    got = Hh.from_compact(y, B, H1, W1, 64)
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= _tol(dtype, ref)
+    # weight-gradient unpack is the exact inverse of the row-merged pack
+    back = torch.empty_like(w)
+    L.call("ng_unpack_weight_grad_rowmerged", wp.float().contiguous().data_ptr(), 64, 3, 7, 7, back.data_ptr(),
+           Hh.stream())
+    assert torch.equal(back, w)
+
+
+@pytest.mark.parametrize("impl,dtype", _impls())
+@pytest.mark.parametrize("crop,H", [(0, 32), (10, 44)])
+def test_head_tap_gemm_and_gather(impl, dtype, crop, H):
+    """1x1 'tap GEMM' (Cout = 49 taps -> 64) over the haloed buffer + ng_tap_gather == Conv2d(64->1, k7) + Tanh."""
+    from nirgan_b200 import _lib as L
+    from nirgan_b200.engine import ActBuf
+    import helpers as Hh
+    B, Cin = 2, 64
+    x = Hh.rnd(_gen(B, Cin, H, H, seed=5), dtype)
+    w = Hh.rnd(_gen(1, Cin, 7, 7, seed=6, scale=0.02), dtype)
+    bias = _gen(1, seed=7, scale=0.1)
+    xb = Hh.to_actbuf(x, 3, "reflect", dtype)
+    xz = ActBuf(xb.t, B, H + 6, H + 6, Cin, 0)
+    wt = torch.zeros(64 * 64, dtype=Hh.TORCH_DT[dtype], device="cuda")
+    L.call("ng_pack_weight", w.data_ptr(), 1, Cin, 7, 7, 0, 1, 64, dtype, wt.data_ptr(), Hh.stream())
+    z, _, _ = Hh.conv_call(xz, wt, 64, 1, 1, 0, H + 6, H + 6, dtype, impl)
+    out = torch.full((B * (H - 2 * crop) ** 2,), float("nan"), device="cuda")
+    L.call("ng_tap_gather", z.data_ptr(), dtype, B, H + 6, H + 6, 64, 7, 7, bias.data_ptr(), L.ACT_TANH, crop,
+           out.data_ptr(), Hh.stream())
+    ref = torch.tanh(F.conv2d(F.pad(x, (3,) * 4, mode="reflect"), w, bias))
+    if crop:
+        ref = ref[..., crop:-crop, crop:-crop]
+    got = out.view(B, 1, H - 2 * crop, H - 2 * crop)
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= (2e-5 if dtype == L.F32 else (1e-3 if dtype == L.F16 else 6e-3))

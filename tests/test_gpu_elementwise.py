@@ -195,8 +195,8 @@ def test_wgrad_matches_autograd(kind):
     dyb = Hh.to_actbuf(dy, 0, "zero", dtype, c_pad=co_pad)
     a = L.ConvArgs()
     a.dtype, a.impl, a.form, a.sgn = dtype, L.IMPL_SIMT, form, 1
-    a.B, a.Hin, a.Win, a.Cin, a.in_pad = B, H, H, Cin, xb.pad
-    a.Cout, a.KH, a.KW, a.stride, a.pad, a.Hout, a.Wout = co_pad, K, K, s, p, Ho, Ho
+    a.B, a.Hin, a.Win, a.Cin, a.in_pad, a.in_pad_w = B, H, H, Cin, xb.pad, xb.pad
+    a.Cout, a.KH, a.KW, a.stride, a.pad, a.pad_w, a.Hout, a.Wout = co_pad, K, K, s, p, p, Ho, Ho
     a.x, a.w, a.y = xb.t.data_ptr(), xb.t.data_ptr(), dyb.t.data_ptr()
     dwp = torch.empty(K * K * co_pad * Cin, device="cuda")
     db = torch.empty(co_pad, device="cuda")
