@@ -87,8 +87,10 @@ def build_model(dev):
     import nirgan_b200  # noqa: F401
     from nirgan_b200.model.generator_inject import define_G_inject
     from test_gpu_models import inject_config
+    import contextlib
     torch.manual_seed(0)
-    net = define_G_inject(inject_config())       # random-init, N(0, 0.02) like the reference
+    with contextlib.redirect_stdout(sys.stderr):   # the reference prints its scale-param init; stdout is JSON only
+        net = define_G_inject(inject_config())     # random-init, N(0, 0.02) like the reference
     return net.to(dev).eval()
 
 

@@ -109,9 +109,9 @@ int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void*
  * k is zero-padded to k_pad, n to n_pad. */
 int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
                    int32_t n_pad, int32_t k_pad, int32_t dtype, void* dst, void* stream);
-/* inverse for gradients: packed fp32 [tap][n_pad][k_pad] -> fp32 [d0][d1][KH][KW] (accumulate=0: overwrite) */
+/* inverse for gradients: dst[d0][d1][KH][KW] = scale * packed[tap][n_pad][k_pad]  (fp32; scale undoes loss scaling) */
 int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
-                          int32_t n_pad, int32_t k_pad, float* dst, void* stream);
+                          int32_t n_pad, int32_t k_pad, float scale, float* dst, void* stream);
 
 /* Generator stem input in "row-merged" form: NCHW fp32 -> [B][H+2*wrap+2*halo][W+2*wrap][64] `dtype`, where element
  * (kw*8 + c) of output pixel (y, x) is channel c of the reflect-padded image at (y, x + kw)  (kw < KW <= 8, c < cin <= 8,
@@ -123,9 +123,9 @@ int ng_prep_stem(const float* src, int32_t cin, int32_t B, int32_t H, int32_t W,
 /* weights for the row-merged stem: fp32 [O][I][KH][KW] -> [kh][O][kw*8 + c] (zero padded to 64) */
 int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH, int32_t KW, int32_t dtype, void* dst,
                              void* stream);
-/* inverse for gradients: fp32 [kh][O][64] -> fp32 [O][I][KH][KW] */
-int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW, float* dst,
-                                    void* stream);
+/* inverse for gradients: fp32 [kh][O][64] -> fp32 [O][I][KH][KW], times scale */
+int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW, float scale,
+                                    float* dst, void* stream);
 
 /* Single-output-channel KHxKW convolution as "tap GEMM + gather": z = [B][Hz][Wz][zc] holds, per input pixel, the
  * dot product of its channels with each of the KH*KW taps (a 1x1 ng_conv2d with Cout = zc >= KH*KW);
@@ -152,6 +152,30 @@ int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, int32_t W, i
                 int32_t act, float slope, const void* residual, int32_t res_pad, const float* inject_e,
                 int32_t inject_mode, const float* inject_scale, void* out, int32_t out_pad, int32_t halo_mode,
                 void* stream);
+
+/* Backward of the unit computed by ng_in_apply (autograd of InstanceNorm2d / ReLU / LeakyReLU / residual add /
+ * ReflectionPad2d / the SatCLIP injection; model/pix2pix.py:165-257 runs it through torch autograd):
+ *   g_halo : dL/d(haloed output buffer) [B][H+2*g_pad][W+2*g_pad][C] or NULL (halo folded back per halo_mode)
+ *   g_skip : dL/d(output interior) from a skip connection, compact [B][H][W][C], or NULL
+ *   y, mean_rstd : the forward's pre-norm tensor and statistics (mean_rstd NULL = unit without normalisation)
+ *   dy     : dL/dy compact [B][H][W][C];  do_out (optional): dL/d(output interior) for the residual path
+ *   dscale / de_map (optional): accumulated dL/d(scale_param) (1 float, caller zero-initialised) and
+ *   dL/d(bilinear embedding map) [B][H][W] for the injection.   sums_scratch: [B][C][2] floats. */
+int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y, int32_t dtype,
+              int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd, int32_t act, float slope,
+              const float* inject_e, int32_t inject_mode, const float* inject_scale, float* sums_scratch, void* dy,
+              void* do_out, float* dscale, float* de_map, void* stream);
+/* dst[B][H][W][c_pad] (dtype): channel 0 = scale * dout * act'(out) inside the crop window, zero elsewhere.
+ * dout/out: fp32 [B][H-2*crop][W-2*crop] (the fp32 single-channel head output and its gradient). */
+int ng_head_bwd_prep(const float* dout, const float* out, int32_t B, int32_t H, int32_t W, int32_t crop, int32_t act,
+                     float scale, int32_t c_pad, int32_t dtype, void* dst, void* stream);
+/* gradient export: NHWC [B][H][W][c_pad] (dtype) -> NCHW fp32 [B][c][H][W], times scale */
+int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c,
+                    float scale, float* dst, void* stream);
+/* SatCLIP injection backward: adjoint of the bilinear resize (128x128 -> HxW) then of fc:
+ * dfc_w[16384][256] = (scale * A^T de_map)^T embeds, dfc_b[16384].  de128_scratch: [B][16384] floats. */
+int ng_inject_bwd(const float* de_map, int32_t B, int32_t H, int32_t W, float scale, const float* embeds,
+                  float* de128_scratch, float* dfc_w, float* dfc_b, void* stream);
 
 /* y[b][n] = sum_k x[b][k] * w[n][k] + bias[n]   (fp32) */
 int ng_linear(const float* x, const float* w, const float* bias, int32_t B, int32_t K, int32_t N, float* y,

@@ -1,0 +1,394 @@
+// Backward of the fused "InstanceNorm -> inject -> activation (+ residual) -> halo" unit, plus the small
+// gradient plumbing kernels of the training step (tanh' / channel padding, NHWC->NCHW gradient export,
+// SatCLIP injection gradients).  All memory-bound; 16-byte vector accesses over 8 channels.
+//
+// Forward unit (ng_in_apply):   xh = (y - mean) * rstd ; u = inject(xh) ; o = act(u) [+ residual] ; buffer = halo(o)
+// Backward, given g = dL/d(buffer) (haloed) and/or g_skip = dL/do from a skip connection:
+//   do  = fold_halo(g) + g_skip
+//   du  = do * act'(u)
+//   dxh = du * d inject / d xh
+//   dy  = rstd * (dxh - mean_hw(dxh) - xh * mean_hw(dxh * xh))          (InstanceNorm backward)
+// Pass 1 (ng_in_bwd_reduce) accumulates the two per-(n,c) means (+ injection gradients), pass 2
+// (ng_in_bwd_apply) recomputes dxh and writes dy (and, for residual blocks, do for the skip path).
+#include "common.cuh"
+
+namespace ng {
+
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&f)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y), c = unpack2<T>(u.z), d = unpack2<T>(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&f)[8]) {
+  if constexpr (sizeof(T) == 2) {
+    uint4 u;
+    u.x = pack2<T>(f[0], f[1]); u.y = pack2<T>(f[2], f[3]); u.z = pack2<T>(f[4], f[5]); u.w = pack2<T>(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  } else {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
+__device__ __forceinline__ float bilerp128_b(const float* __restrict__ e, int oy, int ox, int H, int W) {
+  const float sy = fmaxf((oy + 0.5f) * (128.f / H) - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * (128.f / W) - 0.5f, 0.f);
+  const int y0 = min((int)sy, 127), x0 = min((int)sx, 127);
+  const int y1 = min(y0 + 1, 127), x1 = min(x0 + 1, 127);
+  const float ly = sy - y0, lx = sx - x0;
+  return (1.f - ly) * ((1.f - lx) * e[y0 * 128 + x0] + lx * e[y0 * 128 + x1]) +
+         ly * ((1.f - lx) * e[y1 * 128 + x0] + lx * e[y1 * 128 + x1]);
+}
+
+struct BwdArgs {
+  int B, H, W, C;
+  int act; float slope;
+  int gp, halo_mode;           // halo of the incoming gradient buffer
+  int inj_mode;
+  float inv_hw;
+};
+
+// dL/do for 8 channels of interior pixel (n, y, x): fold the haloed gradient + skip gradient
+template <typename T>
+__device__ __forceinline__ void gather_do(const BwdArgs& a, const T* __restrict__ g, const T* __restrict__ gskip, int n,
+                                          int y, int x, int c8, float (&d)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) d[k] = 0.f;
+  if (g) {
+    const int p = a.gp, Hb = a.H + 2 * p, Wb = a.W + 2 * p;
+    int ys[3], xs[3];
+    ys[0] = y + p; xs[0] = x + p;
+    ys[1] = ys[2] = xs[1] = xs[2] = -1;
+    if (a.halo_mode == NG_HALO_REFLECT && p > 0) {
+      if (y >= 1 && y <= p) ys[1] = p - y;
+      if (y >= a.H - 1 - p && y <= a.H - 2) ys[2] = p + 2 * (a.H - 1) - y;
+      if (x >= 1 && x <= p) xs[1] = p - x;
+      if (x >= a.W - 1 - p && x <= a.W - 2) xs[2] = p + 2 * (a.W - 1) - x;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (ys[i] < 0) continue;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (xs[j] < 0) continue;
+        float f[8];
+        ld8<T>(g + (((size_t)n * Hb + ys[i]) * Wb + xs[j]) * a.C + c8 * 8, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] += f[k];
+      }
+    }
+  }
+  if (gskip) {
+    float f[8];
+    ld8<T>(gskip + (((size_t)n * a.H + y) * a.W + x) * a.C + c8 * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] += f[k];
+  }
+}
+
+// Computes xh, dxh (and du) for 8 channels.  Returns the bilinear embedding value used (0 if none).
+template <typename T>
+__device__ __forceinline__ float unit_backward(const BwdArgs& a, const T* __restrict__ yv, const float* __restrict__ mrn,
+                                               const float* __restrict__ injn, float s, int n, int y, int x, int c8,
+                                               const float (&d_o)[8], float (&xh)[8], float (&du)[8], float (&dxh)[8]) {
+  ld8<T>(yv + (((size_t)n * a.H + y) * a.W + x) * a.C + c8 * 8, xh);
+  if (mrn) {
+    const float4* m4 = reinterpret_cast<const float4*>(mrn + c8 * 16);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 m = m4[k];
+      xh[2 * k] = (xh[2 * k] - m.x) * m.y;
+      xh[2 * k + 1] = (xh[2 * k + 1] - m.z) * m.w;
+    }
+  }
+  float ev = 0.f, fac = 1.f, add = 0.f;
+  if (a.inj_mode != NG_INJECT_NONE) {
+    ev = bilerp128_b(injn, y, x, a.H, a.W);
+    if (a.inj_mode == NG_INJECT_ADD) { add = s * ev; }
+    else if (a.inj_mode == NG_INJECT_MUL_SCALED) fac = 1.f + s * ev;
+    else fac = ev;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float u = xh[k] * fac + add;
+    float dact = 1.f;
+    if (a.act == NG_ACT_RELU) dact = u > 0.f ? 1.f : 0.f;
+    else if (a.act == NG_ACT_LRELU) dact = u > 0.f ? 1.f : a.slope;
+    du[k] = d_o[k] * dact;
+    dxh[k] = du[k] * fac;
+  }
+  return ev;
+}
+
+// ---- pass 1: per-(n,c) sums of dxh and dxh*xh (+ injection gradients) --------------------------------
+// grid = (row chunks, B); block 256 threads; a block walks `rows_per_block` rows of image n.
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_bwd_reduce_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const T* __restrict__ gskip,
+                     const T* __restrict__ yv, const float* __restrict__ mr, const float* __restrict__ inj,
+                     const float* __restrict__ inj_scale, float* __restrict__ sums, float* __restrict__ dscale,
+                     float* __restrict__ de_map, int rows_per_block) {
+  extern __shared__ float sm[];            // [C][2] block accumulators
+  const int n = blockIdx.y, C8 = a.C >> 3;
+  for (int i = threadIdx.x; i < a.C * 2; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const float s = (a.inj_mode != NG_INJECT_NONE && inj_scale) ? *inj_scale : 1.f;
+  const float* mrn = mr ? mr + (size_t)n * a.C * 2 : nullptr;
+  const float* injn = inj ? inj + (size_t)n * 128 * 128 : nullptr;
+  const int y0 = blockIdx.x * rows_per_block, y1 = min(a.H, y0 + rows_per_block);
+  const int items = (y1 - y0) * a.W * C8;
+  // a thread keeps one channel group (c8) when 256 % C8 == 0, so it can accumulate in registers
+  float acc1[8], acc2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc1[k] = acc2[k] = 0.f;
+  float ds_acc = 0.f;
+  const int c8 = threadIdx.x % C8;         // C8 is a power of two <= 64 -> divides 256
+  for (int e = threadIdx.x; e < items; e += 256) {
+    const int pix = e / C8;
+    const int y = y0 + pix / a.W, x = pix % a.W;
+    float d_o[8], xh[8], du[8], dxh[8];
+    gather_do<T>(a, g, gskip, n, y, x, c8, d_o);
+    const float ev = unit_backward<T>(a, yv, mrn, injn, s, n, y, x, c8, d_o, xh, du, dxh);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc1[k] += dxh[k]; acc2[k] = fmaf(dxh[k], xh[k], acc2[k]); }
+    if (a.inj_mode != NG_INJECT_NONE) {
+      float t = 0.f;     // sum over these 8 channels of du * d u / d(s*e)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += (a.inj_mode == NG_INJECT_ADD) ? du[k] : du[k] * xh[k];
+      // u = xh*(1+s*e) | xh + s*e | xh*e
+      if (a.inj_mode == NG_INJECT_MUL) { if (de_map) atomicAdd(&de_map[((size_t)n * a.H + y) * a.W + x], t); }
+      else {
+        ds_acc += t * ev;
+        if (de_map) atomicAdd(&de_map[((size_t)n * a.H + y) * a.W + x], t * s);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    atomicAdd(&sm[(c8 * 8 + k) * 2 + 0], acc1[k]);
+    atomicAdd(&sm[(c8 * 8 + k) * 2 + 1], acc2[k]);
+  }
+  if (a.inj_mode != NG_INJECT_NONE && dscale) {
+    ds_acc = warp_sum(ds_acc);
+    if ((threadIdx.x & 31) == 0 && ds_acc != 0.f) atomicAdd(dscale, ds_acc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.C * 2; i += 256) atomicAdd(&sums[(size_t)n * a.C * 2 + i], sm[i]);
+}
+
+// ---- pass 2: dy = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh)); optional do export for the skip path -----
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_bwd_apply_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const T* __restrict__ gskip,
+                    const T* __restrict__ yv, const float* __restrict__ mr, const float* __restrict__ inj,
+                    const float* __restrict__ inj_scale, const float* __restrict__ sums, T* __restrict__ dy,
+                    T* __restrict__ do_out) {
+  const int C8 = a.C >> 3;
+  const long long total = (long long)a.B * a.H * a.W * C8;
+  const float s = (a.inj_mode != NG_INJECT_NONE && inj_scale) ? *inj_scale : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    long long p = i / C8;
+    const int x = (int)(p % a.W); p /= a.W;
+    const int y = (int)(p % a.H);
+    const int n = (int)(p / a.H);
+    const float* mrn = mr ? mr + (size_t)n * a.C * 2 : nullptr;
+    const float* injn = inj ? inj + (size_t)n * 128 * 128 : nullptr;
+    float d_o[8], xh[8], du[8], dxh[8];
+    gather_do<T>(a, g, gskip, n, y, x, c8, d_o);
+    unit_backward<T>(a, yv, mrn, injn, s, n, y, x, c8, d_o, xh, du, dxh);
+    float out[8];
+    if (mrn) {
+      const float4* s4 = reinterpret_cast<const float4*>(sums + ((size_t)n * a.C + c8 * 8) * 2);
+      const float4* m4 = reinterpret_cast<const float4*>(mrn + c8 * 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 sv = s4[k], m = m4[k];
+        out[2 * k] = m.y * (dxh[2 * k] - sv.x * a.inv_hw - xh[2 * k] * sv.y * a.inv_hw);
+        out[2 * k + 1] = m.w * (dxh[2 * k + 1] - sv.z * a.inv_hw - xh[2 * k + 1] * sv.w * a.inv_hw);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[k] = dxh[k];
+    }
+    const size_t off = (((size_t)n * a.H + y) * a.W + x) * a.C + c8 * 8;
+    st8<T>(dy + off, out);
+    if (do_out) st8<T>(do_out + off, d_o);
+  }
+}
+
+// ---- gradient plumbing ------------------------------------------------------------------------------
+// dst[n][y][x][0] = scale * dout[n][y-crop][x-crop] * act'(out)  (zero outside the crop, channels 1.. zero)
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_bwd_prep_kernel(const float* __restrict__ dout, const float* __restrict__ out, int B, int H, int W, int crop,
+                     int act, float scale, int cpad, T* __restrict__ dst) {
+  const long long total = (long long)B * H * W;
+  const int Hc = H - 2 * crop, Wc = W - 2 * crop;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), n = (int)(i / ((long long)W * H));
+    float v = 0.f;
+    const int yc = y - crop, xc = x - crop;
+    if (yc >= 0 && yc < Hc && xc >= 0 && xc < Wc) {
+      const size_t o = ((size_t)n * Hc + yc) * Wc + xc;
+      v = dout[o] * scale;
+      if (act == NG_ACT_TANH) { const float t = out[o]; v *= (1.f - t * t); }
+    }
+    T* d = dst + i * cpad;
+    d[0] = from_f32<T>(v);
+    for (int c = 1; c < cpad; ++c) d[c] = from_f32<T>(0.f);
+  }
+}
+
+// NHWC (cpad channels, T, scaled) -> NCHW fp32 (c channels), dst = src * scale
+template <typename T>
+__global__ void __launch_bounds__(256)
+grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, int c, float scale, float* __restrict__ dst) {
+  const long long total = (long long)B * c * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int ch = (int)((i / ((long long)W * H)) % c), n = (int)(i / ((long long)W * H * c));
+    dst[i] = to_f32<T>(src[(((size_t)n * H + y) * W + x) * cpad + ch]) * scale;
+  }
+}
+
+// adjoint of F.interpolate(bilinear, align_corners=False) 128x128 -> HxW:  de128 += A^T de_map
+__global__ void __launch_bounds__(256)
+bilerp128_bwd_kernel(const float* __restrict__ de_map, int B, int H, int W, float scale, float* __restrict__ de128) {
+  const long long total = (long long)B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % W), oy = (int)((i / W) % H), n = (int)(i / ((long long)W * H));
+    const float v = de_map[i] * scale;
+    const float sy = fmaxf((oy + 0.5f) * (128.f / H) - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * (128.f / W) - 0.5f, 0.f);
+    const int y0 = min((int)sy, 127), x0 = min((int)sx, 127);
+    const int y1 = min(y0 + 1, 127), x1 = min(x0 + 1, 127);
+    const float ly = sy - y0, lx = sx - x0;
+    float* e = de128 + (size_t)n * 128 * 128;
+    atomicAdd(&e[y0 * 128 + x0], v * (1.f - ly) * (1.f - lx));
+    atomicAdd(&e[y0 * 128 + x1], v * (1.f - ly) * lx);
+    atomicAdd(&e[y1 * 128 + x0], v * ly * (1.f - lx));
+    atomicAdd(&e[y1 * 128 + x1], v * ly * lx);
+  }
+}
+
+// fc backward: dW[n][k] = sum_b dy[b][n] * x[b][k];  db[n] = sum_b dy[b][n]   (fp32)
+__global__ void __launch_bounds__(256)
+linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int B, int K, int N, float* __restrict__ dw,
+                  float* __restrict__ db) {
+  const int n = blockIdx.x;
+  for (int k = threadIdx.x; k < K; k += 256) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s = fmaf(dy[(size_t)b * N + n], x[(size_t)b * K + k], s);
+    dw[(size_t)n * K + k] = s;
+  }
+  if (threadIdx.x == 0 && db) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dy[(size_t)b * N + n];
+    db[n] = s;
+  }
+}
+
+static inline unsigned grid_cap(long long items) {
+  long long blocks = (items + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace ng
+
+using namespace ng;
+
+#define DISPATCH_T(dtype, CALL)                                             \
+  switch (dtype) {                                                          \
+    case NG_F32: { using T = float; CALL; break; }                          \
+    case NG_F16: { using T = __half; CALL; break; }                         \
+    case NG_BF16: { using T = __nv_bfloat16; CALL; break; }                 \
+    default: ng::set_error("bad dtype %d", (int)(dtype)); return NG_E_ARG;  \
+  }
+
+extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y,
+                         int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd, int32_t act,
+                         float slope, const float* inject_e, int32_t inject_mode, const float* inject_scale,
+                         float* sums_scratch, void* dy, void* do_out, float* dscale, float* de_map, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE((g_halo || g_skip) && y && dy, NG_E_ARG, "in_bwd: null tensor");
+  NG_REQUIRE(C % 8 == 0 && ((C / 8) & (C / 8 - 1)) == 0 && C <= 512, NG_E_SHAPE, "in_bwd: C = %d unsupported", C);
+  NG_REQUIRE(mean_rstd == nullptr || sums_scratch != nullptr, NG_E_ARG, "in_bwd: normalised unit needs a [B][C][2] scratch");
+  NG_REQUIRE(inject_mode == NG_INJECT_NONE || inject_e, NG_E_ARG, "in_bwd: injection without embedding map");
+  NG_REQUIRE(halo_mode != NG_HALO_REFLECT || (2 * g_pad + 1 < H && 2 * g_pad + 1 < W), NG_E_SHAPE, "in_bwd: halo too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdArgs a;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.act = act; a.slope = slope; a.gp = g_pad; a.halo_mode = halo_mode;
+  a.inj_mode = inject_mode; a.inv_hw = 1.0f / ((float)H * (float)W);
+  if (mean_rstd || inject_mode != NG_INJECT_NONE) {
+    float* sums = sums_scratch;
+    if (sums) {
+      int e = check_cuda(cudaMemsetAsync(sums, 0, (size_t)B * C * 2 * sizeof(float), st), "in_bwd memset");
+      if (e) return e;
+    }
+    if (de_map) {
+      int e = check_cuda(cudaMemsetAsync(de_map, 0, (size_t)B * H * W * sizeof(float), st), "in_bwd memset de");
+      if (e) return e;
+    }
+    if (mean_rstd || dscale || de_map) {
+      NG_REQUIRE(sums != nullptr, NG_E_ARG, "in_bwd: scratch required");
+      int rpb = (4096 + W * (C / 8) - 1) / (W * (C / 8));
+      if (rpb < 1) rpb = 1;
+      dim3 grid((H + rpb - 1) / rpb, B);
+      DISPATCH_T(dtype, (in_bwd_reduce_kernel<T><<<grid, 256, C * 2 * sizeof(float), st>>>(
+                            a, (const T*)g_halo, (const T*)g_skip, (const T*)y, mean_rstd, inject_e, inject_scale, sums,
+                            dscale, de_map, rpb)));
+      NG_LAUNCH_CHECK("in_bwd_reduce_kernel");
+    }
+  }
+  const long long total = (long long)B * H * W * (C / 8);
+  DISPATCH_T(dtype, (in_bwd_apply_kernel<T><<<grid_cap(total), 256, 0, st>>>(
+                        a, (const T*)g_halo, (const T*)g_skip, (const T*)y, mean_rstd, inject_e, inject_scale,
+                        sums_scratch, (T*)dy, (T*)do_out)));
+  NG_LAUNCH_CHECK("in_bwd_apply_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_head_bwd_prep(const float* dout, const float* out, int32_t B, int32_t H, int32_t W, int32_t crop,
+                                int32_t act, float scale, int32_t c_pad, int32_t dtype, void* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(dout && dst && (act != NG_ACT_TANH || out), NG_E_ARG, "head_bwd_prep: null tensor");
+  DISPATCH_T(dtype, (head_bwd_prep_kernel<T><<<grid_cap((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(
+                        dout, out, B, H, W, crop, act, scale, c_pad, (T*)dst)));
+  NG_LAUNCH_CHECK("head_bwd_prep_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c,
+                               float scale, float* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src && dst && c <= c_pad, NG_E_ARG, "grad_to_nchw: bad arguments");
+  DISPATCH_T(dtype, (grad_to_nchw_kernel<T><<<grid_cap((long long)B * c * H * W), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)src, B, H, W, c_pad, c, scale, dst)));
+  NG_LAUNCH_CHECK("grad_to_nchw_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_inject_bwd(const float* de_map, int32_t B, int32_t H, int32_t W, float scale, const float* embeds,
+                             float* de128_scratch, float* dfc_w, float* dfc_b, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(de_map && embeds && de128_scratch && dfc_w, NG_E_ARG, "inject_bwd: null tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  int e = check_cuda(cudaMemsetAsync(de128_scratch, 0, (size_t)B * 128 * 128 * sizeof(float), st), "inject_bwd memset");
+  if (e) return e;
+  bilerp128_bwd_kernel<<<grid_cap((long long)B * H * W), 256, 0, st>>>(de_map, B, H, W, scale, de128_scratch);
+  NG_LAUNCH_CHECK("bilerp128_bwd_kernel");
+  linear_bwd_kernel<<<128 * 128, 256, 0, st>>>(de128_scratch, embeds, B, 256, 128 * 128, dfc_w, dfc_b);
+  NG_LAUNCH_CHECK("linear_bwd_kernel");
+  return NG_OK;
+}

@@ -504,6 +504,8 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   NG_REQUIRE(a.epilogue != NG_EPI_HEAD || a.Cout == 16, NG_E_SHAPE, "conv_tc: head epilogue expects Cout stored as 16");
   if (bn == 16 && kc == 64) return launch_tc<16, 64>(a, g, st);
   if (bn == 64 && kc == 16) return launch_tc<64, 16>(a, g, st);
+  if (bn == 128 && kc == 16) return launch_tc<128, 16>(a, g, st);
+  if (bn == 256 && kc == 16) return launch_tc<256, 16>(a, g, st);
   if (bn == 64 && kc == 64) return launch_tc<64, 64>(a, g, st);
   if (bn == 128 && kc == 64) return launch_tc<128, 64>(a, g, st);
   if (bn == 256 && kc == 64) return launch_tc<256, 64>(a, g, st);

@@ -26,7 +26,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int d0, int d1
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int d0, int d1, int taps, int n_axis,
-                                    int n_pad, int k_pad, float* __restrict__ dst) {
+                                    int n_pad, int k_pad, float scale, float* __restrict__ dst) {
   const long long total = (long long)d0 * d1 * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -34,7 +34,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int d0, in
     const int a1 = (int)((i / taps) % d1);
     const int a0 = (int)(i / ((long long)taps * d1));
     const int n = n_axis == 0 ? a0 : a1, k = n_axis == 0 ? a1 : a0;
-    dst[i] = packed[((long long)tp * n_pad + n) * k_pad + k];
+    dst[i] = scale * packed[((long long)tp * n_pad + n) * k_pad + k];
   }
 }
 
@@ -417,12 +417,12 @@ __global__ void pack_rowmerged_kernel(const float* __restrict__ src, int O, int 
   }
 }
 
-__global__ void unpack_rowmerged_kernel(const float* __restrict__ packed, int O, int I, int KH, int KW,
+__global__ void unpack_rowmerged_kernel(const float* __restrict__ packed, int O, int I, int KH, int KW, float scale,
                                         float* __restrict__ dst) {
   const int total = O * I * KH * KW;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int kw = i % KW, kh = (i / KW) % KH, c = (i / (KW * KH)) % I, o = i / (KW * KH * I);
-    dst[i] = packed[((long long)kh * O + o) * 64 + kw * 8 + c];
+    dst[i] = scale * packed[((long long)kh * O + o) * 64 + kw * 8 + c];
   }
 }
 
@@ -487,12 +487,13 @@ extern "C" int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t 
 }
 
 extern "C" int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW,
-                                     int32_t n_axis, int32_t n_pad, int32_t k_pad, float* dst, void* stream) {
+                                     int32_t n_axis, int32_t n_pad, int32_t k_pad, float scale, float* dst,
+                                     void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(packed && dst && (n_axis == 0 || n_axis == 1), NG_E_ARG, "unpack_weight_grad: bad arguments");
   const long long total = (long long)d0 * d1 * KH * KW;
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, d0, d1, KH * KW, n_axis, n_pad,
-                                                                             k_pad, dst);
+                                                                             k_pad, scale, dst);
   NG_LAUNCH_CHECK("unpack_wgrad_kernel");
   return NG_OK;
 }
@@ -642,11 +643,11 @@ extern "C" int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, 
 }
 
 extern "C" int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW,
-                                               float* dst, void* stream) {
+                                               float scale, float* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(packed && dst && I > 0 && I <= 8 && KW > 0 && KW <= 8, NG_E_ARG, "unpack_weight_grad_rowmerged: bad arguments");
   unpack_rowmerged_kernel<<<grid_for((long long)O * I * KH * KW, 256), 256, 0, (cudaStream_t)stream>>>(packed, O, I, KH,
-                                                                                                      KW, dst);
+                                                                                                      KW, scale, dst);
   NG_LAUNCH_CHECK("unpack_rowmerged_kernel");
   return NG_OK;
 }

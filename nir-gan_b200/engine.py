@@ -23,6 +23,9 @@ import torch
 
 from . import _lib as L
 
+# bumped by B200Adam.step(): parameter storage is updated in place by ng_adam_step (no torch version bump)
+WEIGHT_EPOCH = [0]
+
 _PRECISIONS = {
     "fp16": (L.F16, torch.float16),
     "bf16": (L.BF16, torch.bfloat16),
@@ -145,7 +148,7 @@ class Engine:
         n_axis 0/1: [tap][n_pad][k_pad];  n_axis 'rowmerged': [kh][O][kw*8+c] (stem);
         n_axis 'taps': [n = tap (padded to n_pad)][k_pad] for the tap-GEMM form of a 1-output-channel conv."""
         key = (w.data_ptr(), n_axis, n_pad, k_pad, self.dt_enum)
-        ver = w._version
+        ver = (w._version, WEIGHT_EPOCH[0])
         hit = self._packed.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
@@ -227,169 +230,3 @@ class Engine:
 
 def conv_out(h: int, k: int, s: int, p: int) -> int:
     return (h + 2 * p - k) // s + 1
-
-
-class GeneratorRunner:
-    """Executes ResnetGenerator / ResnetGenerator_inject forward (model/networks.py:341-374,
-    model/generator_inject.py:105-135) for a module that keeps the reference state_dict layout."""
-
-    def __init__(self, module: torch.nn.Module, cfg: Optional[EngineConfig] = None):
-        self.module = module
-        self.cfg = cfg or EngineConfig.from_env()
-        self._engine: Optional[Engine] = None
-        self._plans: Dict[Tuple, Plan] = {}
-        self.head_mode = os.environ.get("NIRGAN_B200_HEAD", "tapgemm")     # 'tapgemm' | 'direct'
-
-    # lazily bound to the device of the first input
-    def engine(self, device) -> Engine:
-        if self._engine is None or self._engine.device != device:
-            self._engine = Engine(self.cfg, device)
-            self._plans.clear()
-        return self._engine
-
-    def _convs(self):
-        m = self.module.model
-        nb = self.module.n_blocks
-        blocks = [m[10 + b] for b in range(nb)]
-        return m[1], m[4], m[7], blocks, m[10 + nb], m[13 + nb], m[17 + nb]
-
-    def _build(self, eng: Engine, B: int, H: int, W: int, wrap: int, inject: bool, stream: int) -> Plan:
-        mod = self.module
-        stem, d1, d2, blocks, u1, u2, head = self._convs()
-        ngf = stem.weight.shape[0]
-        cin = stem.weight.shape[1]
-        assert ngf % 64 == 0, "nirgan_b200 kernels are tiled for ngf multiples of 64"
-        plan = Plan()
-        H1, W1 = H + 2 * wrap, W + 2 * wrap
-        if H1 % 4 or W1 % 4:
-            raise RuntimeError(f"nirgan_b200: padded tile {H1}x{W1} must be divisible by 4 "
-                               f"(two stride-2 stages, as in the reference)")
-        pw = lambda conv, n_axis, n_pad, k_pad: eng.packed_weight(conv.weight, n_axis, n_pad, k_pad, stream)
-        plan.records["weights"] = []   # (conv module, n_axis, n_pad, k_pad) to re-pack when masters change
-        wrec = plan.records["weights"]
-
-        def W_(conv, n_axis, n_pad, k_pad):
-            wrec.append((conv, n_axis, n_pad, k_pad))
-            return pw(conv, n_axis, n_pad, k_pad)
-
-        # input: NCHW fp32 -> row-merged NHWC [B][H1+6][W1][kw*8+c] (wrapper reflect pad + stem reflect halo fused):
-        # the 7x7x3 stem becomes a 7x1 conv over 64 "channels" = 7 K-steps of 128-byte rows instead of 49 thin taps
-        src = eng.buffers.get("g.in", B * cin * H * W, torch.float32)
-        plan.records["src"] = src
-        if cin > 8:
-            raise NotImplementedError("nirgan_b200 stem kernel: input_nc <= 8")
-        x0 = ActBuf(eng.buffers.get("g.x0", B * (H1 + 6) * W1 * 64, eng.dt_torch), B, H1, W1, 64, 3)
-        plan.add("ng_prep_stem", src.data_ptr(), cin, B, H, W, wrap, 3, 7, eng.dt_enum, x0.t.data_ptr(),
-                 label="g.prep")
-        # stem (bias cancelled by InstanceNorm -> skipped)
-        y, mr = eng.add_conv_norm(plan, "g.stem", x0, W_(stem, "rowmerged", ngf, 64), ngf, 7, 1, 3, H1, W1,
-                                  KW=1, pad_w=0, in_pad_w=0)
-        x = eng.add_apply(plan, "g.x1", y, mr, L.ACT_RELU, 0)
-        # down 1 (+ SatCLIP injection between IN and ReLU)
-        H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
-        y, mr = eng.add_conv_norm(plan, "g.d1", x, W_(d1, 0, 2 * ngf, ngf), 2 * ngf, 3, 2, 1, H2, W2)
-        if inject:
-            if H2 != W2:
-                raise RuntimeError("nirgan_b200: SatCLIP injection is defined for square tiles only "
-                                   "(generator_inject.py:116 passes size=(W,H))")
-            emb = eng.buffers.get("g.emb", B * 256, torch.float32)
-            e = eng.buffers.get("g.e", B * 128 * 128, torch.float32)
-            plan.records["emb"] = emb
-            plan.add("ng_linear", emb.data_ptr(), mod.fc.weight.data_ptr(), mod.fc.bias.data_ptr(), B, 256,
-                     128 * 128, e.data_ptr())
-            style = mod.inject_style
-            # `elif inject_style == "multiply" and self.scale_param` truthiness quirk (generator_inject.py:124)
-            # is resolved on the host at plan time.
-            if style == "add":
-                mode = L.INJECT_ADD
-            elif style == "multiply":
-                mode = L.INJECT_MUL_SCALED if bool(mod.scale_param) else L.INJECT_MUL   # one-time host read
-            else:
-                raise NotImplementedError(f"inject style [{style}] is not recognized")
-            x = eng.add_apply(plan, "g.x2", y, mr, L.ACT_RELU, 0, inject_e=e, inject_mode=mode,
-                              inject_scale=mod.scale_param.data)
-            plan.records["inject_mode"] = mode
-        else:
-            x = eng.add_apply(plan, "g.x2", y, mr, L.ACT_RELU, 0)
-        # down 2 -> first haloed (reflect 1) residual-trunk buffer
-        H3, W3 = conv_out(H2, 3, 2, 1), conv_out(W2, 3, 2, 1)
-        C4 = 4 * ngf
-        y, mr = eng.add_conv_norm(plan, "g.d2", x, W_(d2, 0, C4, 2 * ngf), C4, 3, 2, 1, H3, W3)
-        nb = len(blocks)
-        x = eng.add_apply(plan, "g.t0", y, mr, L.ACT_RELU, 1 if nb else 0)
-        for b, blk in enumerate(blocks):
-            c1, c2 = blk.conv_block[1], blk.conv_block[5]
-            y, mr = eng.add_conv_norm(plan, "g.ra", x, W_(c1, 0, C4, C4), C4, 3, 1, 1, H3, W3)
-            a = eng.add_apply(plan, "g.ta", y, mr, L.ACT_RELU, 1)
-            y, mr = eng.add_conv_norm(plan, "g.rb", a, W_(c2, 0, C4, C4), C4, 3, 1, 1, H3, W3)
-            last = b == nb - 1
-            # out = x + IN(conv2(...)); no ReLU after the add (networks.py:433)
-            nxt = eng.add_apply(plan, f"g.t{(b + 1) % 2}" if not last else "g.tl", y, mr, L.ACT_NONE,
-                                0 if last else 1, residual=x)
-            x = nxt
-        # up 1, up 2 (ConvTranspose k3 s2 p1 op1 as 4 output-parity phases)
-        y, mr = eng.add_conv_norm(plan, "g.u1", x, W_(u1, 1, 2 * ngf, C4), 2 * ngf, 3, 2, 1, 2 * H3, 2 * W3,
-                                  form=L.FORM_PHASED)
-        x = eng.add_apply(plan, "g.x5", y, mr, L.ACT_RELU, 0)
-        y, mr = eng.add_conv_norm(plan, "g.u2", x, W_(u2, 1, ngf, 2 * ngf), ngf, 3, 2, 1, 4 * H3, 4 * W3,
-                                  form=L.FORM_PHASED)
-        x = eng.add_apply(plan, "g.x6", y, mr, L.ACT_RELU, 3)
-        # head 7x7 -> 1 channel (+bias, tanh), fp32 NCHW, wrapper crop fused.
-        out = eng.buffers.get("g.out", B * H * W, torch.float32)
-        if self.head_mode == "tapgemm" and ngf == 64:
-            # tap GEMM + gather: z[pixel][tap] = <x[pixel,:], w[tap,:]> over the haloed buffer (each input pixel
-            # read once, no 49x im2col re-read), then out = tanh(b + sum_t z[(y+kh, x+kw), t])
-            xz = ActBuf(x.t, B, H1 + 6, W1 + 6, ngf, 0)
-            z = eng.act("g.z", B, H1 + 6, W1 + 6, 64, 0)
-            a = eng.conv_args(xz, W_(head, "taps", 64, ngf), z.t, 64, 1, 1, 0, H1 + 6, W1 + 6)
-            plan.keepalive.append(a)
-            plan.add("ng_conv2d", C.byref(a), label="g.head.gemm")
-            plan.add("ng_tap_gather", z.t.data_ptr(), eng.dt_enum, B, H1 + 6, W1 + 6, 64, 7, 7, head.bias.data_ptr(),
-                     L.ACT_TANH, wrap, out.data_ptr(), label="g.head.gather")
-        else:
-            a = eng.conv_args(x, W_(head, 0, 16, ngf), out, 16, 7, 1, 3, H1, W1, epilogue=L.EPI_HEAD,
-                              act=L.ACT_TANH, crop=wrap, bias=head.bias.data)
-            plan.keepalive.append(a)
-            plan.add("ng_conv2d", C.byref(a), label="g.head")
-        plan.records["out"] = out
-        plan.records["post"] = getattr(mod, "post_correction", False)
-        return plan
-
-    def _refresh_weights(self, eng: Engine, plan: Plan, stream: int):
-        for conv, n_axis, n_pad, k_pad in plan.records["weights"]:
-            eng.packed_weight(conv.weight, n_axis, n_pad, k_pad, stream)
-
-    @torch.no_grad()
-    def forward(self, x: torch.Tensor, embeds: Optional[torch.Tensor] = None, wrap_pad: int = 0) -> torch.Tensor:
-        require_cuda(x, "generator input")
-        if x.dim() != 4:
-            raise RuntimeError("generator input must be (B, C, H, W)")
-        eng = self.engine(x.device)
-        Btot, Cin, H, W = x.shape
-        inject = embeds is not None
-        chunk = eng.cfg.chunk if eng.cfg.chunk > 0 else Btot
-        out = torch.empty(Btot, 1, H, W, dtype=torch.float32, device=x.device)
-        stream = torch.cuda.current_stream(x.device).cuda_stream
-        x = x.contiguous().float()
-        if inject:
-            require_cuda(embeds, "embeds")
-            embeds = embeds.contiguous().float()
-        for b0 in range(0, Btot, chunk):
-            B = min(chunk, Btot - b0)
-            key = (B, Cin, H, W, wrap_pad, inject)
-            plan = self._plans.get(key)
-            if plan is None:
-                plan = self._build(eng, B, H, W, wrap_pad, inject, stream)
-                self._plans[key] = plan
-            else:
-                self._refresh_weights(eng, plan, stream)
-            plan.records["src"].view(B, Cin, H, W).copy_(x[b0:b0 + B])
-            if inject:
-                plan.records["emb"].view(B, 256).copy_(embeds[b0:b0 + B])
-            plan.run(stream)
-            o = plan.records["out"].view(B, 1, H, W)
-            if plan.records["post"]:
-                o = o * self.module.post_correction_param
-            out[b0:b0 + B].copy_(o)
-        self.last_plan = plan
-        return out

@@ -1,0 +1,234 @@
+"""Unit graph: the hot path as a chain of fused units, compiled to forward and backward plans.
+
+A *unit* is   conv -> [InstanceNorm -> inject -> activation (+ residual)] -> haloed output buffer
+(or conv + bias + activation fused in the conv epilogue for the layers without a norm).  The same
+description drives
+  * the forward plan      (ng_conv2d, ng_in_stats[_finalize], ng_in_apply),
+  * the backward plan     (ng_in_bwd, ng_conv2d_wgrad, ng_unpack_weight_grad, ng_conv2d as dgrad)
+so the training step of model/pix2pix.py:165-257 runs entirely on the C-ABI kernels.  Data gradients
+reuse the forward convolution kernels with re-packed weights:
+  stride-1 conv            -> flipped-tap full correlation          (GATHER, sgn=-1)
+  stride-2 conv            -> phase-decomposed transposed conv      (PHASED)
+  ConvTranspose2d(s2)      -> stride-2 conv                         (GATHER, stride 2)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _lib as L
+from .engine import ActBuf, Engine, Plan, _ptr
+
+
+@dataclass
+class Unit:
+    name: str
+    conv: torch.nn.Module                 # parameter holder (Conv2d / ConvTranspose2d)
+    x: ActBuf                             # input buffer (haloed)
+    cout: int                             # stored output channels
+    K: int
+    stride: int
+    pad: int
+    Hout: int
+    Wout: int
+    form: int = L.FORM_GATHER
+    pack: object = 0                      # n_axis (0 / 1) or 'rowmerged'
+    KW: Optional[int] = None
+    pad_w: Optional[int] = None
+    in_pad_w: Optional[int] = None
+    kind: str = "norm"                    # 'norm' | 'biasact' | 'head'
+    act: int = L.ACT_NONE
+    slope: float = 0.0
+    out_pad: int = 0
+    halo_mode: int = L.HALO_REFLECT
+    residual: Optional[int] = None        # index of the unit whose output buffer is added
+    inject: Optional[dict] = None         # {'e': tensor, 'mode': int, 'scale': tensor}
+    crop: int = 0
+    # filled by the builder
+    y: Optional[ActBuf] = None
+    mr: Optional[torch.Tensor] = None
+    out: Optional[ActBuf] = None
+    out_f32: Optional[torch.Tensor] = None
+    wkey: tuple = ()
+
+
+class UnitGraph:
+    def __init__(self, eng: Engine, tag: str, stream: int):
+        self.eng, self.tag, self.stream = eng, tag, stream
+        self.units: List[Unit] = []
+        self.pre_ops = []                   # (fn_name, args, label) executed before the units (input prep, fc)
+        self.records: dict = {}
+
+    # ---- construction -----------------------------------------------------------------------------
+    def weight(self, u: Unit) -> torch.Tensor:
+        cin = u.x.C
+        if u.pack == "rowmerged":
+            return self.eng.packed_weight(u.conv.weight, "rowmerged", u.cout, 64, self.stream)
+        return self.eng.packed_weight(u.conv.weight, u.pack, u.cout, cin, self.stream)
+
+    def add(self, u: Unit) -> Unit:
+        eng, B = self.eng, u.x.B
+        pre = f"{self.tag}.{u.name}"
+        if u.kind == "head":
+            u.out_f32 = eng.buffers.get(pre + ".out", B * (u.Hout - 2 * u.crop) * (u.Wout - 2 * u.crop), torch.float32)
+        else:
+            u.y = eng.act(pre + ".y", B, u.Hout, u.Wout, u.cout, 0)
+            if u.kind == "norm":
+                u.mr = eng.buffers.get(pre + ".mr", B * u.cout * 2, torch.float32)
+                u.out = eng.act(pre + ".o", B, u.Hout, u.Wout, u.cout, u.out_pad)
+            else:
+                u.out = u.y                  # conv epilogue already produced the activation (pad 0)
+        self.units.append(u)
+        return u
+
+    def _args(self, u: Unit, x: ActBuf, w: torch.Tensor, y: torch.Tensor, **over) -> L.ConvArgs:
+        kw = dict(form=u.form, sgn=1, KW=u.KW, pad_w=u.pad_w, in_pad_w=u.in_pad_w)
+        kw.update(over)
+        return self.eng.conv_args(x, w, y, u.cout, u.K, u.stride, u.pad, u.Hout, u.Wout, **kw)
+
+    # ---- forward ------------------------------------------------------------------------------------
+    def compile_forward(self) -> Plan:
+        eng = self.eng
+        plan = Plan()
+        plan.records.update(self.records)
+        plan.records["weights"] = [u for u in self.units]
+        for name, args, label in self.pre_ops:
+            plan.add(name, *args, label=label)
+        for u in self.units:
+            w = self.weight(u)
+            pre = f"{self.tag}.{u.name}"
+            if u.kind == "head":
+                a = self._args(u, u.x, w, u.out_f32, epilogue=L.EPI_HEAD, act=u.act, crop=u.crop, bias=u.conv.bias.data)
+                plan.keepalive.append(a)
+                plan.add("ng_conv2d", C.byref(a), label=pre)
+                continue
+            if u.kind == "biasact":
+                a = self._args(u, u.x, w, u.y.t, epilogue=L.EPI_BIAS_ACT, act=u.act, slope=u.slope,
+                               bias=u.conv.bias.data)
+                plan.keepalive.append(a)
+                plan.add("ng_conv2d", C.byref(a), label=pre)
+                continue
+            a = self._args(u, u.x, w, u.y.t)
+            B = u.x.B
+            if eng.impl == L.IMPL_TC:
+                slots = L.load().ng_conv_stat_slots(C.byref(a))
+                if slots <= 0:
+                    L.check(slots if slots < 0 else -1, "ng_conv_stat_slots")
+                part = eng.buffers.get(pre + ".part", B * slots * u.cout * 2, torch.float32)
+                a.stat_partials = part.data_ptr()
+                plan.keepalive.append(a)
+                plan.add("ng_conv2d", C.byref(a), label=pre)
+                plan.add("ng_in_stats_finalize", part.data_ptr(), B, slots, u.cout, u.Hout * u.Wout, u.mr.data_ptr(),
+                         label=pre + ".fin")
+            else:
+                plan.keepalive.append(a)
+                plan.add("ng_conv2d", C.byref(a), label=pre)
+                plan.add("ng_in_stats", u.y.t.data_ptr(), eng.dt_enum, B, u.Hout * u.Wout, u.cout, u.mr.data_ptr(),
+                         label=pre + ".stats")
+            res = self.units[u.residual].out if u.residual is not None else None
+            inj = u.inject or {}
+            plan.add("ng_in_apply", u.y.t.data_ptr(), eng.dt_enum, B, u.Hout, u.Wout, u.cout, u.mr.data_ptr(), u.act,
+                     u.slope, _ptr(res.t) if res else None, res.pad if res else 0, _ptr(inj.get("e")),
+                     inj.get("mode", L.INJECT_NONE), _ptr(inj.get("scale")), u.out.t.data_ptr(), u.out_pad, u.halo_mode,
+                     label=pre + ".apply")
+        return plan
+
+    def refresh_weights(self):
+        for u in self.units:
+            self.weight(u)
+
+    # ---- backward -------------------------------------------------------------------------------------
+    def _dgrad_weight(self, u: Unit) -> torch.Tensor:
+        """Weights re-packed for the data gradient: roles of Cin / Cout swapped."""
+        w = u.conv.weight
+        cin = u.x.C
+        if u.form == L.FORM_PHASED:                 # ConvTranspose2d (Cin, Cout, k, k): n = Cin, k = Cout
+            return self.eng.packed_weight(w, 0, cin, u.cout, self.stream)
+        return self.eng.packed_weight(w, 1, cin, u.cout, self.stream)       # Conv2d (Cout, Cin, k, k): n = Cin
+
+    def compile_backward(self, dout_f32: torch.Tensor, loss_scale: float, need_dw: bool, need_dx: bool,
+                         want_inject_grads: bool = False) -> Plan:
+        """dout_f32: gradient of the fp32 single-channel output of the last (head) unit.  Returns a plan whose
+        records hold 'dw' {unit index: packed fp32 grad}, 'db' {unit index: bias grad}, 'dx' (ActBuf-shaped grad of the
+        first unit's input buffer, when need_dx)."""
+        eng, tag = self.eng, self.tag
+        plan = Plan()
+        S = float(loss_scale)
+        units = self.units
+        n = len(units)
+        g_halo = [None] * n         # gradient w.r.t. each unit's haloed output buffer (from the next unit's dgrad)
+        g_skip = [None] * n         # gradient w.r.t. each unit's output interior from a residual consumer
+        dw, db = {}, {}
+        dY = None
+        for i in range(n - 1, -1, -1):
+            u = units[i]
+            pre = f"{tag}.{u.name}"
+            B = u.x.B
+            # ---- gradient of the conv output ----
+            if u.kind == "head":
+                dY = eng.act(pre + ".dy", B, u.Hout, u.Wout, u.cout, 0)
+                plan.add("ng_head_bwd_prep", dout_f32.data_ptr(), _ptr(u.out_f32), B, u.Hout, u.Wout, u.crop, u.act, S,
+                         u.cout, eng.dt_enum, dY.t.data_ptr(), label=pre + ".dprep")
+            else:
+                dY = eng.act(pre + ".dy", B, u.Hout, u.Wout, u.cout, 0)
+                gh, gs = g_halo[i], g_skip[i]
+                assert gh is not None or gs is not None, f"unit {u.name} receives no gradient"
+                do_out = None
+                if u.residual is not None:
+                    do_out = eng.act(pre + ".do", B, u.Hout, u.Wout, u.cout, 0)
+                    g_skip[u.residual] = do_out
+                inj = u.inject or {}
+                sums = eng.buffers.get(pre + ".bsum", B * u.cout * 2, torch.float32) if u.kind == "norm" else None
+                dscale = de_map = None
+                if inj and want_inject_grads:
+                    dscale = eng.buffers.get(pre + ".dscale", 1, torch.float32)
+                    de_map = eng.buffers.get(pre + ".demap", B * u.Hout * u.Wout, torch.float32)
+                    plan.records["inject"] = {"dscale": dscale, "de_map": de_map, "H": u.Hout, "W": u.Wout, "unit": i}
+                # for 'biasact' units y holds the activated output: its sign is the activation mask
+                plan.add("ng_in_bwd", _ptr(gh.t) if gh else None, u.out_pad if gh else 0, u.halo_mode,
+                         _ptr(gs.t) if gs else None, u.y.t.data_ptr(), eng.dt_enum, B, u.Hout, u.Wout, u.cout,
+                         _ptr(u.mr) if u.kind == "norm" else None, u.act, u.slope, _ptr(inj.get("e")),
+                         inj.get("mode", L.INJECT_NONE), _ptr(inj.get("scale")), _ptr(sums), dY.t.data_ptr(),
+                         _ptr(do_out.t) if do_out else None, _ptr(dscale), _ptr(de_map), launches=2, label=pre + ".bwd")
+            # ---- weight gradient ----
+            if need_dw:
+                taps = u.K * (u.KW if u.KW is not None else u.K)
+                kdim = 64 if u.pack == "rowmerged" else u.x.C
+                dwp = eng.buffers.get(pre + ".dwp", taps * u.cout * kdim, torch.float32)
+                has_bias_grad = u.kind in ("head", "biasact")
+                dbb = eng.buffers.get(pre + ".db", u.cout, torch.float32) if has_bias_grad else None
+                a = self._args(u, u.x, dwp, dY.t)         # a.w is unused by wgrad; a.y = dY
+                plan.keepalive.append(a)
+                plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), _ptr(dbb), launches=2, label=pre + ".wgrad")
+                dw[i], db[i] = dwp, dbb
+            # ---- data gradient ----
+            if i == 0 and not need_dx:
+                continue
+            xin = u.x
+            g = eng.act(pre + ".dx", xin.B, xin.H, xin.W, xin.C, xin.pad)
+            wd = self._dgrad_weight(u)
+            dyb = ActBuf(dY.t, B, u.Hout, u.Wout, u.cout, 0)
+            Kw = u.KW if u.KW is not None else u.K
+            assert Kw == u.K, "data gradient of asymmetric kernels is not needed on this path"
+            Hg, Wg = xin.H + 2 * xin.pad, xin.W + 2 * xin.pad
+            if u.form == L.FORM_PHASED:            # ConvTranspose -> stride-2 conv of dY
+                a = eng.conv_args(dyb, wd, g.t, xin.C, u.K, 2, u.pad, Hg, Wg)
+            elif u.stride == 2:                     # strided conv -> phased transposed conv
+                a = eng.conv_args(dyb, wd, g.t, xin.C, u.K, 2, u.pad, Hg, Wg, form=L.FORM_PHASED)
+            else:                                   # stride-1 conv -> flipped full correlation
+                # haloed input (in_pad == pad): gradient of the haloed buffer, pad 0;  zero-padded input: pad = pad
+                eff_pad = 0 if xin.pad == u.pad else u.pad
+                a = eng.conv_args(dyb, wd, g.t, xin.C, u.K, 1, eff_pad, Hg, Wg, sgn=-1)
+            if xin.C < 64:
+                a.impl = L.IMPL_SIMT          # thin data gradients (PatchGAN input, 16 stored channels): CUDA-core kernel
+            plan.keepalive.append(a)
+            plan.add("ng_conv2d", C.byref(a), label=pre + ".dgrad")
+            if i > 0:
+                g_halo[i - 1] = g
+            else:
+                plan.records["dx"] = g
+        plan.records["dw"], plan.records["db"] = dw, db
+        return plan

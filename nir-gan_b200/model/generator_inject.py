@@ -13,7 +13,8 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from ..engine import EngineConfig, GeneratorRunner, require_cuda
+from ..engine import EngineConfig, require_cuda
+from ..runners import GeneratorRunner
 from .networks import _B200Module, _generator_trunk, _instance_bias, get_norm_layer, init_net
 
 

@@ -21,7 +21,8 @@ import torch
 import torch.nn as nn
 from torch.nn import init
 
-from ..engine import EngineConfig, GeneratorRunner, require_cuda
+from ..engine import EngineConfig, require_cuda
+from ..runners import GeneratorRunner, PatchGANRunner
 
 
 # ---------------------------------------------------------------------------------------------
@@ -118,6 +119,11 @@ class _B200Module(nn.Module):
         self._runner = None
         return self
 
+    def reset_training_slots(self):
+        """Forget activations of training forwards whose backward will never run."""
+        if getattr(self, "_runner", None) is not None:
+            self._runner._live = 0
+
     def _get_runner(self, factory):
         if getattr(self, "_runner", None) is None:
             object.__setattr__(self, "_runner", factory(self, self.b200_config))
@@ -191,7 +197,6 @@ class NLayerDiscriminator(_B200Module):
     def forward(self, input):
         require_cuda(input, "NLayerDiscriminator input")
         from ..autograd import discriminator_apply
-        from ..engine_d import PatchGANRunner
         return discriminator_apply(self, self._get_runner(PatchGANRunner), input)
 
 

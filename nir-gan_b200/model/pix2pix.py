@@ -58,14 +58,30 @@ class Px2Px(nn.Module):
             return batch["rgb"], batch["nir"], batch["embeds"]
         return batch["rgb"], batch["nir"]
 
+    def _toggle(self, active: nn.Module, frozen: nn.Module):
+        """PL-1.9 ``toggle_optimizer``: parameters of the optimizer that is not stepping do not require grad."""
+        saved = [(p, p.requires_grad) for p in frozen.parameters()]
+        for p, _ in saved:
+            p.requires_grad_(False)
+        return saved
+
     def training_step(self, batch, batch_idx, optimizer_idx):
         assert self.training is True, "Model is in eval mode, set to training mode before training"
+        frozen = self._toggle(self.netD, self.netG) if optimizer_idx == 0 else self._toggle(self.netG, self.netD)
+        try:
+            return self._training_step(batch, batch_idx, optimizer_idx)
+        finally:
+            for p, rg in frozen:
+                p.requires_grad_(rg)
+
+    def _training_step(self, batch, batch_idx, optimizer_idx):
         if self.inject:
             rgb, nir, embeds = self.extract_batch(batch)
         else:
             (rgb, nir), embeds = self.extract_batch(batch), None
         o = self.config.base_configs
         if optimizer_idx == 0:      # discriminator, pix2pix.py:195-212
+            self.netD.reset_training_slots()
             with torch.no_grad():    # fake_AB.detach(): G needs no graph in the D pass
                 pred = self.forward(rgb, embeds)
             pred_fake = self.netD(torch.cat((rgb, pred), 1))
@@ -74,6 +90,7 @@ class Px2Px(nn.Module):
             loss_D_real = self.criterionGAN(pred_real, True)
             return loss_D_fake + loss_D_real          # no 0.5 factor (pix2pix.py:206)
         # generator, pix2pix.py:214-257
+        self.netD.reset_training_slots()
         pred = self.forward(rgb, embeds)
         pred_fake = self.netD(torch.cat((rgb, pred), 1))
         loss_G = self.criterionGAN(pred_fake, True) * o.lambda_GAN
@@ -93,7 +110,9 @@ class Px2Px(nn.Module):
         return loss_G
 
     def configure_optimizers(self):
+        """pix2pix.py:485-492: [optim_d, optim_g], Adam(lr, betas=(beta1, 0.999)); the update runs in ng_adam_step."""
+        from ..optim import B200Adam
         o = self.opt
-        optim_g = torch.optim.Adam(self.netG.parameters(), lr=o.lr, betas=(o.beta1, 0.999))
-        optim_d = torch.optim.Adam(self.netD.parameters(), lr=o.lr, betas=(o.beta1, 0.999))
+        optim_g = B200Adam(self.netG.parameters(), lr=o.lr, betas=(o.beta1, 0.999))
+        optim_d = B200Adam(self.netD.parameters(), lr=o.lr, betas=(o.beta1, 0.999))
         return [optim_d, optim_g]

@@ -1,0 +1,270 @@
+"""Runners: build the unit graphs of the generator (plain / SatCLIP-injected) and the PatchGAN
+discriminator from reference-layout ``nn.Module``s and execute them (inference and training)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .engine import ActBuf, Engine, EngineConfig, Plan, conv_out, require_cuda, _ptr
+from .graph import Unit, UnitGraph
+
+
+class _RunnerBase:
+    def __init__(self, module: torch.nn.Module, cfg: Optional[EngineConfig] = None):
+        self.module = module
+        self.cfg = cfg or EngineConfig.from_env()
+        self._engine: Optional[Engine] = None
+        self._fwd: Dict[Tuple, Tuple[UnitGraph, Plan]] = {}
+        self._train: Dict[Tuple, dict] = {}
+        self._live = 0                    # training contexts holding un-backwarded activations
+        self.last_plan: Optional[Plan] = None
+
+    def engine(self, device) -> Engine:
+        if self._engine is None or self._engine.device != device:
+            self._engine = Engine(self.cfg, device)
+            self._fwd.clear()
+            self._train.clear()
+        return self._engine
+
+    def loss_scale(self) -> float:
+        # fp16 gradients are carried with a power-of-two loss scale (exactly undone when exporting gradients)
+        return float(os.environ.get("NIRGAN_B200_LOSS_SCALE", "4096")) if self.cfg.precision == "fp16" else 1.0
+
+
+# =================================================================================================
+class GeneratorRunner(_RunnerBase):
+    """ResnetGenerator / ResnetGenerator_inject (model/networks.py:341-374, model/generator_inject.py:105-135)."""
+
+    def __init__(self, module, cfg=None):
+        super().__init__(module, cfg)
+        self.head_mode = os.environ.get("NIRGAN_B200_HEAD", "tapgemm")     # inference head: 'tapgemm' | 'direct'
+
+    def _convs(self):
+        m = self.module.model
+        nb = self.module.n_blocks
+        return m[1], m[4], m[7], [m[10 + b] for b in range(nb)], m[10 + nb], m[13 + nb], m[17 + nb]
+
+    def build_graph(self, eng: Engine, B: int, H: int, W: int, wrap: int, inject: bool, stream: int, tag: str,
+                    direct_head: bool) -> UnitGraph:
+        mod = self.module
+        stem, d1, d2, blocks, u1, u2, head = self._convs()
+        ngf, cin = stem.weight.shape[0], stem.weight.shape[1]
+        if ngf % 64:
+            raise NotImplementedError("nirgan_b200 kernels are tiled for ngf multiples of 64")
+        if cin > 8:
+            raise NotImplementedError("nirgan_b200 stem kernel: input_nc <= 8")
+        H1, W1 = H + 2 * wrap, W + 2 * wrap
+        if H1 % 4 or W1 % 4:
+            raise RuntimeError(f"nirgan_b200: padded tile {H1}x{W1} must be divisible by 4 (two stride-2 stages)")
+        g = UnitGraph(eng, tag, stream)
+        # input: NCHW fp32 -> row-merged NHWC [B][H1+6][W1][kw*8+c] (wrapper reflect pad + stem reflect halo fused):
+        # the 7x7x3 stem becomes a 7x1 conv over 64 "channels" = 7 K-steps of 128-byte rows instead of 49 thin taps
+        src = eng.buffers.get(tag + ".in", B * cin * H * W, torch.float32)
+        g.records["src"] = src
+        x0 = ActBuf(eng.buffers.get(tag + ".x0", B * (H1 + 6) * W1 * 64, eng.dt_torch), B, H1, W1, 64, 3)
+        g.pre_ops.append(("ng_prep_stem", (src.data_ptr(), cin, B, H, W, wrap, 3, 7, eng.dt_enum, x0.t.data_ptr()),
+                          tag + ".prep"))
+        C2, C4 = 2 * ngf, 4 * ngf
+        H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
+        H3, W3 = conv_out(H2, 3, 2, 1), conv_out(W2, 3, 2, 1)
+        u = g.add(Unit("stem", stem, x0, ngf, 7, 1, 3, H1, W1, pack="rowmerged", KW=1, pad_w=0, in_pad_w=0,
+                       act=L.ACT_RELU, out_pad=0))
+        inj = None
+        if inject:
+            if H2 != W2:
+                raise RuntimeError("nirgan_b200: SatCLIP injection is defined for square tiles only "
+                                   "(generator_inject.py:116 passes size=(W,H))")
+            emb = eng.buffers.get(tag + ".emb", B * 256, torch.float32)
+            e = eng.buffers.get(tag + ".e", B * 128 * 128, torch.float32)
+            g.records["emb"] = emb
+            g.pre_ops.append(("ng_linear", (emb.data_ptr(), mod.fc.weight.data_ptr(), mod.fc.bias.data_ptr(), B, 256,
+                                            128 * 128, e.data_ptr()), tag + ".fc"))
+            style = mod.inject_style
+            if style == "add":
+                mode = L.INJECT_ADD
+            elif style == "multiply":
+                # `and self.scale_param` truthiness quirk (generator_inject.py:124): one host read at plan time
+                mode = L.INJECT_MUL_SCALED if bool(mod.scale_param) else L.INJECT_MUL
+            else:
+                raise NotImplementedError(f"inject style [{style}] is not recognized")
+            inj = {"e": e, "mode": mode, "scale": mod.scale_param.data}
+        u = g.add(Unit("d1", d1, u.out, C2, 3, 2, 1, H2, W2, act=L.ACT_RELU, out_pad=0, inject=inj))
+        nb = len(blocks)
+        u = g.add(Unit("d2", d2, u.out, C4, 3, 2, 1, H3, W3, act=L.ACT_RELU, out_pad=1 if nb else 0))
+        for b, blk in enumerate(blocks):
+            src_idx = len(g.units) - 1
+            a = g.add(Unit(f"r{b}a", blk.conv_block[1], u.out, C4, 3, 1, 1, H3, W3, act=L.ACT_RELU, out_pad=1))
+            # out = x + IN(conv2(...)); no ReLU after the add (networks.py:433)
+            u = g.add(Unit(f"r{b}b", blk.conv_block[5], a.out, C4, 3, 1, 1, H3, W3, act=L.ACT_NONE,
+                           out_pad=0 if b == nb - 1 else 1, residual=src_idx))
+        # ConvTranspose k3 s2 p1 op1 as 4 output-parity phases
+        u = g.add(Unit("u1", u1, u.out, C2, 3, 2, 1, 2 * H3, 2 * W3, form=L.FORM_PHASED, pack=1, act=L.ACT_RELU))
+        u = g.add(Unit("u2", u2, u.out, ngf, 3, 2, 1, 4 * H3, 4 * W3, form=L.FORM_PHASED, pack=1, act=L.ACT_RELU,
+                       out_pad=3))
+        g.records["head_in"] = u.out
+        if direct_head:
+            g.add(Unit("head", head, u.out, 16, 7, 1, 3, H1, W1, kind="head", act=L.ACT_TANH, crop=wrap))
+        g.records["geom"] = (B, H, W, H1, W1, wrap, ngf)
+        return g
+
+    def _inference_plan(self, eng, B, Cin, H, W, wrap, inject, stream) -> Plan:
+        key = (B, Cin, H, W, wrap, inject)
+        hit = self._fwd.get(key)
+        if hit is not None:
+            g, plan = hit
+            g.refresh_weights()
+            if "head_taps" in plan.records:
+                eng.packed_weight(self._convs()[6].weight, "taps", 64, plan.records["head_taps"], stream)
+            return plan
+        tapgemm = self.head_mode == "tapgemm" and self._convs()[0].weight.shape[0] == 64
+        g = self.build_graph(eng, B, H, W, wrap, inject, stream, "g", direct_head=not tapgemm)
+        plan = g.compile_forward()
+        if tapgemm:
+            # head as tap GEMM + gather: z[pixel][tap] = <x[pixel,:], w[tap,:]> over the haloed buffer (each input pixel
+            # read once, no 49x im2col re-read), then out = tanh(b + sum_t z[(y+kh, x+kw), t])
+            head = self._convs()[6]
+            _, _, _, H1, W1, _, ngf = g.records["geom"]
+            x = g.records["head_in"]
+            xz = ActBuf(x.t, B, H1 + 6, W1 + 6, ngf, 0)
+            z = eng.act("g.z", B, H1 + 6, W1 + 6, 64, 0)
+            out = eng.buffers.get("g.head.out", B * H * W, torch.float32)
+            wt = eng.packed_weight(head.weight, "taps", 64, ngf, stream)
+            a = eng.conv_args(xz, wt, z.t, 64, 1, 1, 0, H1 + 6, W1 + 6)
+            plan.keepalive.append(a)
+            plan.add("ng_conv2d", C.byref(a), label="g.head.gemm")
+            plan.add("ng_tap_gather", z.t.data_ptr(), eng.dt_enum, B, H1 + 6, W1 + 6, 64, 7, 7, head.bias.data_ptr(),
+                     L.ACT_TANH, wrap, out.data_ptr(), label="g.head.gather")
+            plan.records["out"] = out
+            plan.records["head_taps"] = ngf
+        else:
+            plan.records["out"] = g.units[-1].out_f32
+        self._fwd[key] = (g, plan)
+        return plan
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, embeds: Optional[torch.Tensor] = None, wrap_pad: int = 0) -> torch.Tensor:
+        require_cuda(x, "generator input")
+        if x.dim() != 4:
+            raise RuntimeError("generator input must be (B, C, H, W)")
+        eng = self.engine(x.device)
+        Btot, Cin, H, W = x.shape
+        inject = embeds is not None
+        chunk = eng.cfg.chunk if eng.cfg.chunk > 0 else Btot
+        out = torch.empty(Btot, 1, H, W, dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        x = x.contiguous().float()
+        if inject:
+            require_cuda(embeds, "embeds")
+            embeds = embeds.contiguous().float()
+        for b0 in range(0, Btot, chunk):
+            B = min(chunk, Btot - b0)
+            plan = self._inference_plan(eng, B, Cin, H, W, wrap_pad, inject, stream)
+            plan.records["src"].view(B, Cin, H, W).copy_(x[b0:b0 + B])
+            if inject:
+                plan.records["emb"].view(B, 256).copy_(embeds[b0:b0 + B])
+            plan.run(stream)
+            o = plan.records["out"].view(B, 1, H, W)
+            if getattr(self.module, "post_correction", False):
+                o = o * self.module.post_correction_param
+            out[b0:b0 + B].copy_(o)
+        self.last_plan = plan
+        return out
+
+    # ---- training -------------------------------------------------------------------------------------
+    def train_context(self, x: torch.Tensor, embeds, wrap_pad: int) -> dict:
+        """Graph + forward/backward plans with dedicated buffers (activations must survive until backward)."""
+        eng = self.engine(x.device)
+        B, Cin, H, W = x.shape
+        inject = embeds is not None
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        key = (B, Cin, H, W, wrap_pad, inject)
+        ctx = self._train.get(key)
+        if ctx is None:
+            g = self.build_graph(eng, B, H, W, wrap_pad, inject, stream, "gt", direct_head=True)
+            fwd = g.compile_forward()
+            dout = eng.buffers.get("gt.dout", B * H * W, torch.float32)
+            bwd = g.compile_backward(dout, self.loss_scale(), need_dw=True, need_dx=False, want_inject_grads=inject)
+            ctx = self._train[key] = {"graph": g, "fwd": fwd, "bwd": bwd, "dout": dout, "geom": (B, Cin, H, W)}
+        else:
+            ctx["graph"].refresh_weights()
+            for u in ctx["graph"].units[1:]:
+                ctx["graph"]._dgrad_weight(u)
+        return ctx
+
+
+# =================================================================================================
+class PatchGANRunner(_RunnerBase):
+    """NLayerDiscriminator (model/networks.py:539-584)."""
+
+    def conv_modules(self) -> List[torch.nn.Module]:
+        return [m for m in self.module.model if isinstance(m, torch.nn.Conv2d)]
+
+    def build_graph(self, eng: Engine, B: int, H: int, W: int, stream: int, tag: str) -> UnitGraph:
+        convs = self.conv_modules()
+        g = UnitGraph(eng, tag, stream)
+        cin = convs[0].weight.shape[1]
+        src = eng.buffers.get(tag + ".in", B * cin * H * W, torch.float32)
+        g.records["src"] = src
+        x = eng.act(tag + ".x0", B, H, W, 16, 0)
+        g.pre_ops.append(("ng_prep_input", (src.data_ptr(), cin, None, 0, B, H, W, 0, 0, L.HALO_ZERO, 16, eng.dt_enum,
+                                            x.t.data_ptr()), tag + ".prep"))
+        c0 = convs[0]
+        Hc, Wc = conv_out(H, 4, 2, 1), conv_out(W, 4, 2, 1)
+        u = g.add(Unit("l0", c0, x, c0.weight.shape[0], 4, 2, 1, Hc, Wc, kind="biasact", act=L.ACT_LRELU, slope=0.2,
+                       halo_mode=L.HALO_ZERO))
+        for i, conv in enumerate(convs[1:-1], start=1):
+            s = conv.stride[0]
+            Hn, Wn = conv_out(u.Hout, 4, s, 1), conv_out(u.Wout, 4, s, 1)
+            u = g.add(Unit(f"l{i}", conv, u.out, conv.weight.shape[0], 4, s, 1, Hn, Wn, act=L.ACT_LRELU, slope=0.2,
+                           out_pad=0, halo_mode=L.HALO_ZERO))
+        cl = convs[-1]
+        Ho, Wo = conv_out(u.Hout, 4, 1, 1), conv_out(u.Wout, 4, 1, 1)
+        g.add(Unit("out", cl, u.out, 16, 4, 1, 1, Ho, Wo, kind="head", act=L.ACT_NONE))
+        g.records["out_hw"] = (Ho, Wo)
+        g.records["cin"] = cin
+        return g
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        require_cuda(x, "discriminator input")
+        eng = self.engine(x.device)
+        B, Cin, H, W = x.shape
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        key = (B, Cin, H, W)
+        hit = self._fwd.get(key)
+        if hit is None:
+            g = self.build_graph(eng, B, H, W, stream, "d")
+            hit = self._fwd[key] = (g, g.compile_forward())
+        else:
+            hit[0].refresh_weights()
+        g, plan = hit
+        plan.records["src"].view(B, Cin, H, W).copy_(x.float())
+        plan.run(stream)
+        Ho, Wo = g.records["out_hw"]
+        self.last_plan = plan
+        return g.units[-1].out_f32.view(B, 1, Ho, Wo).clone()
+
+    def train_context(self, x: torch.Tensor, slot: int, need_dw: bool, need_dx: bool) -> dict:
+        eng = self.engine(x.device)
+        B, Cin, H, W = x.shape
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        key = (B, Cin, H, W, slot, need_dw, need_dx)
+        ctx = self._train.get(key)
+        if ctx is None:
+            tag = f"dt{slot}"
+            g = self.build_graph(eng, B, H, W, stream, tag)
+            fwd = g.compile_forward()
+            Ho, Wo = g.records["out_hw"]
+            dout = eng.buffers.get(tag + ".dout", B * Ho * Wo, torch.float32)
+            bwd = g.compile_backward(dout, self.loss_scale(), need_dw=need_dw, need_dx=need_dx)
+            ctx = self._train[key] = {"graph": g, "fwd": fwd, "bwd": bwd, "dout": dout, "geom": (B, Cin, H, W)}
+        else:
+            ctx["graph"].refresh_weights()
+            for i, u in enumerate(ctx["graph"].units):
+                if i > 0 or need_dx:
+                    ctx["graph"]._dgrad_weight(u)
+        return ctx

@@ -1,0 +1,147 @@
+"""Autograd bridges for the training step (model/pix2pix.py:165-257): the generator and the
+discriminator appear to torch autograd as single differentiable functions of (input, parameters);
+their forward and backward are the compiled C-ABI plans of ``graph.UnitGraph``.
+
+Gradient precision: in the fp16 fast mode activations' gradients are carried in fp16 with a
+power-of-two loss scale S (default 4096, NIRGAN_B200_LOSS_SCALE) that is applied when the fp32 output
+gradient enters the plan and divided out exactly when weight / input gradients are exported as fp32.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+from . import _lib as L
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _export_weight_grads(graph, bwd_plan, S: float, params: List[torch.nn.Parameter]) -> dict:
+    """Packed fp32 weight gradients -> reference-layout fp32 tensors keyed by parameter id."""
+    st = graph.stream
+    out = {}
+    inv = 1.0 / S
+    for i, dwp in bwd_plan.records["dw"].items():
+        u = graph.units[i]
+        w = u.conv.weight
+        gw = torch.empty_like(w, dtype=torch.float32)
+        d0, d1, kh, kw = w.shape
+        if u.pack == "rowmerged":
+            L.call("ng_unpack_weight_grad_rowmerged", dwp.data_ptr(), d0, d1, kh, kw, inv, gw.data_ptr(), st)
+        else:
+            L.call("ng_unpack_weight_grad", dwp.data_ptr(), d0, d1, kh, kw, u.pack, u.cout, u.x.C, inv, gw.data_ptr(), st)
+        out[id(w)] = gw
+        if u.conv.bias is not None:
+            dbb = bwd_plan.records["db"].get(i)
+            if dbb is not None:
+                out[id(u.conv.bias)] = dbb[:u.conv.bias.numel()] * inv
+            else:
+                # bias feeding InstanceNorm: its gradient is identically zero (the reference returns rounding noise)
+                out[id(u.conv.bias)] = torch.zeros_like(u.conv.bias, dtype=torch.float32)
+    return out
+
+
+class GeneratorFunction(torch.autograd.Function):
+    @staticmethod
+    def run(module, runner, x, embeds, wrap_pad):
+        params = [p for p in module.parameters()]
+        return GeneratorFunction.apply(module, runner, wrap_pad, x, embeds, *params)
+
+    @staticmethod
+    def forward(ctx, module, runner, wrap_pad, x, embeds, *params):
+        c = runner.train_context(x, embeds, wrap_pad)
+        B, Cin, H, W = c["geom"]
+        st = _stream(x)
+        fwd = c["fwd"]
+        fwd.records["src"].view(B, Cin, H, W).copy_(x.detach().float())
+        if embeds is not None:
+            fwd.records["emb"].view(B, 256).copy_(embeds.detach().float())
+        fwd.run(st)
+        ctx.c, ctx.module, ctx.runner = c, module, runner
+        ctx.params = params
+        ctx.has_embeds = embeds is not None
+        out = c["graph"].units[-1].out_f32.view(B, 1, H, W)
+        if getattr(module, "post_correction", False):
+            raise NotImplementedError("nirgan_b200: training with post_correction is outside the hot path")
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        c, module, runner = ctx.c, ctx.module, ctx.runner
+        g, bwd = c["graph"], c["bwd"]
+        S = runner.loss_scale()
+        st = _stream(dout)
+        c["dout"].view_as(dout).copy_(dout.float())
+        inj = bwd.records.get("inject")
+        if inj is not None:
+            inj["dscale"].zero_()
+        bwd.run(st)
+        grads = _export_weight_grads(g, bwd, S, ctx.params)
+        if inj is not None:
+            eng = runner._engine
+            B = c["geom"][0]
+            fc = module.fc
+            dW = torch.empty_like(fc.weight, dtype=torch.float32)
+            db = torch.empty_like(fc.bias, dtype=torch.float32)
+            scratch = eng.buffers.get("gt.de128", B * 128 * 128, torch.float32)
+            L.call("ng_inject_bwd", inj["de_map"].data_ptr(), B, inj["H"], inj["W"], 1.0 / S,
+                   c["fwd"].records["emb"].data_ptr(), scratch.data_ptr(), dW.data_ptr(), db.data_ptr(), st)
+            grads[id(fc.weight)], grads[id(fc.bias)] = dW, db
+            if hasattr(module, "scale_param"):
+                grads[id(module.scale_param)] = (inj["dscale"] / S).reshape(module.scale_param.shape)
+        out = []
+        for p in ctx.params:
+            gp = grads.get(id(p))
+            out.append(gp if (gp is not None and p.requires_grad) else None)
+        return (None, None, None, None, None, *out)
+
+
+class DiscriminatorFunction(torch.autograd.Function):
+    @staticmethod
+    def run(module, runner, x):
+        params = [p for p in module.parameters()]
+        return DiscriminatorFunction.apply(module, runner, x, *params)
+
+    @staticmethod
+    def forward(ctx, module, runner, x, *params):
+        need_dw = any(p.requires_grad for p in params)
+        need_dx = x.requires_grad
+        slot = runner._live
+        if slot >= 8:
+            raise RuntimeError("nirgan_b200: 8 discriminator forwards are waiting for their backward; call "
+                               "netD.reset_training_slots() if those graphs were dropped")
+        runner._live += 1
+        c = runner.train_context(x, slot, need_dw, need_dx)
+        B, Cin, H, W = c["geom"]
+        st = _stream(x)
+        c["fwd"].records["src"].view(B, Cin, H, W).copy_(x.detach().float())
+        c["fwd"].run(st)
+        ctx.c, ctx.module, ctx.runner, ctx.params = c, module, runner, params
+        ctx.need_dw, ctx.need_dx = need_dw, need_dx
+        Ho, Wo = c["graph"].records["out_hw"]
+        return c["graph"].units[-1].out_f32.view(B, 1, Ho, Wo).clone()
+
+    @staticmethod
+    def backward(ctx, dout):
+        c, runner = ctx.c, ctx.runner
+        g, bwd = c["graph"], c["bwd"]
+        S = runner.loss_scale()
+        st = _stream(dout)
+        c["dout"].view_as(dout).copy_(dout.float())
+        bwd.run(st)
+        runner._live = max(0, runner._live - 1)
+        grads = _export_weight_grads(g, bwd, S, ctx.params) if ctx.need_dw else {}
+        dx = None
+        if ctx.need_dx:
+            B, Cin, H, W = c["geom"]
+            gx = bwd.records["dx"]
+            dx = torch.empty(B, Cin, H, W, dtype=torch.float32, device=dout.device)
+            L.call("ng_grad_to_nchw", gx.t.data_ptr(), runner._engine.dt_enum, B, H, W, gx.C, Cin, 1.0 / S, dx.data_ptr(), st)
+        out = []
+        for p in ctx.params:
+            gp = grads.get(id(p))
+            out.append(gp if (gp is not None and p.requires_grad) else None)
+        return (None, None, dx, *out)

@@ -228,8 +228,8 @@ def test_stem_rowmerged(impl, dtype, wrap, H, W):
     assert float((got - ref).abs().max()) <= _tol(dtype, ref)
     # weight-gradient unpack is the exact inverse of the row-merged pack
     back = torch.empty_like(w)
-    L.call("ng_unpack_weight_grad_rowmerged", wp.float().contiguous().data_ptr(), 64, 3, 7, 7, back.data_ptr(),
-           Hh.stream())
+    L.call("ng_unpack_weight_grad_rowmerged", wp.float().contiguous().data_ptr(), 64, 3, 7, 7, 1.0,
+           back.data_ptr(), Hh.stream())
     assert torch.equal(back, w)
 
 
@@ -257,4 +257,4 @@ def test_head_tap_gemm_and_gather(impl, dtype, crop, H):
         ref = ref[..., crop:-crop, crop:-crop]
     got = out.view(B, 1, H - 2 * crop, H - 2 * crop)
     assert torch.isfinite(got).all()
-    assert float((got - ref).abs().max()) <= (2e-5 if dtype == L.F32 else (1e-3 if dtype == L.F16 else 6e-3))
+    assert float((got - ref).abs().max()) <= (2e-5 if dtype == L.F32 else (1e-3 if dtype == L.F16 else 1e-2))   # 49 16-bit-rounded partial sums

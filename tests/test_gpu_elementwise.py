@@ -203,7 +203,7 @@ def test_wgrad_matches_autograd(kind):
     L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), db.data_ptr(), Hh.stream())
     dw = torch.empty_like(w)
     n_axis = 1 if form == L.FORM_PHASED else 0
-    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, co_pad, Cin,
+    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, co_pad, Cin, 1.0,
            dw.data_ptr(), Hh.stream())
     rel = float((dw - w.grad).norm() / w.grad.norm())
     assert rel <= 2e-5, rel

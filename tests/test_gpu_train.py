@@ -1,0 +1,219 @@
+"""GPU parity of the training step (model/pix2pix.py:165-257, 485-492) through the drop-in API.
+
+Gradient tolerances: two valid fp32 evaluations of the G step already differ by 5e-4..3e-3 (rel-L2) because
+d|pred-nir|/dpred = sign(.) flips on rounding noise and 23 InstanceNorm backward passes amplify it
+(oracle/pin_against_reference.py) -> fp32 verification mode: rel-L2 <= 1e-2; fp16 tensor-core mode:
+cosine similarity >= 0.99 and rel-L2 <= 0.15.
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, generator=g, device="cuda") * scale
+
+
+@pytest.mark.parametrize("case", ["relu_reflect1", "none_residual", "lrelu_zero", "relu_halo3", "inject_mul", "inject_add",
+                                  "biasact"])
+def test_in_bwd_unit_matches_autograd(case):
+    """ng_in_bwd == autograd of [InstanceNorm -> inject -> act (+res) -> pad] for every unit flavour (fp32)."""
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    B, Cn, H, W = 2, 64, 14, 18
+    dtype = L.F32
+    act, slope, p, mode, use_res, inj_mode, norm = L.ACT_RELU, 0.0, 1, "reflect", False, L.INJECT_NONE, True
+    if case == "none_residual":
+        act, use_res = L.ACT_NONE, True
+    elif case == "lrelu_zero":
+        act, slope, p, mode = L.ACT_LRELU, 0.2, 0, "zero"
+    elif case == "relu_halo3":
+        p = 3
+    elif case == "inject_mul":
+        inj_mode, p, mode, H, W = L.INJECT_MUL_SCALED, 0, "zero", 21, 21
+    elif case == "inject_add":
+        inj_mode, p, mode, H, W = L.INJECT_ADD, 0, "zero", 21, 21
+    elif case == "biasact":
+        act, slope, p, mode, norm = L.ACT_LRELU, 0.2, 0, "zero", False
+    y = (_gen(B, Cn, H, W, seed=1) * 1.5 + 0.3).requires_grad_(True)
+    res = _gen(B, Cn, H, W, seed=2).requires_grad_(True)
+    e = _gen(B, 128 * 128, seed=3).requires_grad_(True)
+    s = torch.tensor(0.6, device="cuda", requires_grad=True)
+    # ---- torch reference ----
+    xh = y
+    if norm:
+        mu = y.mean(dim=(2, 3), keepdim=True)
+        var = y.var(dim=(2, 3), unbiased=False, keepdim=True)
+        xh = (y - mu) / torch.sqrt(var + 1e-5)
+    u = xh
+    if inj_mode != L.INJECT_NONE:
+        em = F.interpolate(e.view(B, 1, 128, 128), size=(H, W), mode="bilinear", align_corners=False)
+        u = xh * (1 + s * em) if inj_mode == L.INJECT_MUL_SCALED else xh + s * em
+    o = F.relu(u) if act == L.ACT_RELU else (F.leaky_relu(u, slope) if act == L.ACT_LRELU else u)
+    if use_res:
+        o = o + res
+    ob = F.pad(o, (p,) * 4, mode="reflect") if (p and mode == "reflect") else o
+    g = _gen(*ob.shape, seed=4)
+    gskip = _gen(B, Cn, H, W, seed=5)
+    (ob * g).sum().backward(retain_graph=True)
+    (o * gskip).sum().backward()
+    # ---- kernel ----
+    yd = y.detach()
+    yb = Hh.to_actbuf(yd if norm else o.detach(), 0, "zero", dtype)    # biasact units keep the activated output
+    mr = None
+    if norm:
+        mr = torch.empty(B * Cn * 2, device="cuda")
+        L.call("ng_in_stats", yb.t.data_ptr(), dtype, B, H * W, Cn, mr.data_ptr(), Hh.stream())
+    gb = g.permute(0, 2, 3, 1).contiguous()
+    gs = gskip.permute(0, 2, 3, 1).contiguous()
+    dy = torch.full((B * H * W * Cn,), float("nan"), device="cuda")
+    do = torch.full((B * H * W * Cn,), float("nan"), device="cuda")
+    sums = torch.empty(B * Cn * 2, device="cuda")
+    dscale = torch.zeros(1, device="cuda")
+    de_map = torch.empty(B * H * W, device="cuda")
+    injected = inj_mode != L.INJECT_NONE
+    L.call("ng_in_bwd", gb.data_ptr(), p, L.HALO_REFLECT if mode == "reflect" else L.HALO_ZERO, gs.data_ptr(),
+           yb.t.data_ptr(), dtype, B, H, W, Cn, mr.data_ptr() if norm else None, act, slope,
+           e.detach().data_ptr() if injected else None, inj_mode, s.detach().data_ptr() if injected else None,
+           sums.data_ptr(), dy.data_ptr(), do.data_ptr(), dscale.data_ptr() if injected else None,
+           de_map.data_ptr() if injected else None, Hh.stream())
+    torch.cuda.synchronize()
+    got = Hh.from_compact(dy, B, H, W, Cn)
+    ref = y.grad
+    assert float((got - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), case
+    if use_res:
+        assert float((Hh.from_compact(do, B, H, W, Cn) - res.grad).abs().max()) <= 1e-5
+    if injected:
+        assert abs(float(dscale) - float(s.grad)) <= 2e-3 * max(1.0, abs(float(s.grad)))
+        dW = torch.empty(128 * 128, 256, device="cuda")
+        db = torch.empty(128 * 128, device="cuda")
+        emb = _gen(B, 256, seed=6)
+        scratch = torch.empty(B * 128 * 128, device="cuda")
+        L.call("ng_inject_bwd", de_map.data_ptr(), B, H, W, 1.0, emb.data_ptr(), scratch.data_ptr(), dW.data_ptr(),
+               db.data_ptr(), Hh.stream())
+        de128 = e.grad.view(B, 128 * 128)
+        assert float((scratch.view(B, -1) - de128).abs().max()) <= 1e-3 * max(1.0, float(de128.abs().max()))
+        assert float((dW - de128.t() @ emb).abs().max()) <= 1e-3 * max(1.0, float((de128.t() @ emb).abs().max()))
+        assert float((db - de128.sum(0)).abs().max()) <= 1e-3 * max(1.0, float(de128.sum(0).abs().max()))
+
+
+def _cfg(lambda_rs=1.0, inject=False):
+    from test_gpu_models import inject_config
+    c = inject_config()
+    c.base_configs.lambda_rs_losses = lambda_rs
+    if not inject:
+        c.satclip.use_satclip = False
+    return c
+
+
+def _load(model, sd_g, sd_d):
+    model.netG.load_state_dict(sd_g)
+    model.netD.load_state_dict(sd_d)
+
+
+def _relerr(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def _cos(a, b):
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-20))
+
+
+@pytest.mark.parametrize("precision,impl", [("fp32", "simt"), ("fp16", "tc")], ids=["fp32-verify", "fp16-tc"])
+def test_training_step_golden(golden_dir, precision, impl):
+    """One D-then-G step on the reference-produced golden: losses, pred, gradients, Adam update."""
+    import nirgan_oracle as O
+    from nirgan_b200.model.pix2pix import Px2Px
+    g = np.load(f"{golden_dir}/train_step_64.npz")
+    sd_g = O.random_state_dict(O.generator_param_shapes(), seed=int(g["sd_g_seed"]))
+    sd_d = O.random_state_dict(O.discriminator_param_shapes(), seed=int(g["sd_d_seed"]))
+    model = Px2Px(_cfg())
+    _load(model, sd_g, sd_d)
+    model = model.cuda().train()
+    model.netG.configure_b200(precision=precision, impl=impl)
+    model.netD.configure_b200(precision=precision, impl=impl)
+    opt_d, opt_g = model.configure_optimizers()
+    batch = {"rgb": torch.from_numpy(g["rgb"]).cuda(), "nir": torch.from_numpy(g["nir"]).cuda()}
+    fp32 = precision == "fp32"
+    # ---- optimizer 0: discriminator ----
+    opt_d.zero_grad()
+    loss_d = model.training_step(batch, 0, 0)
+    loss_d.backward()
+    assert abs(float(loss_d) - float(g["loss_D"])) <= (1e-4 if fp32 else 2e-2) * max(1.0, abs(float(g["loss_D"])))
+    gd = dict(model.netD.named_parameters())
+    for k in ("model.8.weight", "model.0.weight", "model.11.weight", "model.11.bias", "model.0.bias"):
+        ref = torch.from_numpy(g["gD." + k]).cuda()
+        got = gd[k].grad[:8]
+        if fp32:
+            assert _relerr(got, ref) <= 2e-3, (k, _relerr(got, ref))
+        else:
+            assert _cos(got, ref) >= 0.99 and _relerr(got, ref) <= 0.15, (k, _cos(got, ref), _relerr(got, ref))
+    assert all(p.grad is None for p in model.netG.parameters())
+    opt_d.step()
+    if fp32:
+        ref = torch.from_numpy(g["newD.model.11.weight"]).cuda()
+        m = torch.from_numpy(g["gD.model.11.weight"]).cuda().abs()
+        sel = m > 5e-2 * m.max()
+        assert float((gd["model.11.weight"].detach()[:8][sel[:8]] - ref[:8][sel[:8]]).abs().max()) <= 1e-6
+    # ---- optimizer 1: generator ----
+    opt_g.zero_grad()
+    for p in model.netD.parameters():
+        p.grad = None
+    loss_g = model.training_step(batch, 0, 1)
+    loss_g.backward()
+    assert abs(float(loss_g) - float(g["loss_G"])) <= (2e-4 if fp32 else 3e-2) * abs(float(g["loss_G"]))
+    assert all(p.grad is None for p in model.netD.parameters())        # D is frozen in the G pass
+    gg = dict(model.netG.named_parameters())
+    for k in ("model.26.weight", "model.26.bias", "model.10.conv_block.1.weight", "model.19.weight", "model.1.weight",
+              "model.4.weight"):
+        ref = torch.from_numpy(g["gG." + k]).cuda()
+        got = gg[k].grad[:8]
+        if fp32:
+            assert _relerr(got, ref) <= 1e-2, (k, _relerr(got, ref))
+        else:
+            assert _cos(got, ref) >= 0.99 and _relerr(got, ref) <= 0.15, (k, _cos(got, ref), _relerr(got, ref))
+    # every gradient norm against the reference's
+    for k, p in gg.items():
+        if k.endswith("weight"):
+            ref = float(g["gnormG." + k])
+            assert abs(float(p.grad.norm()) - ref) <= (2e-2 if fp32 else 0.15) * ref, k
+    opt_g.step()
+    if fp32:
+        ref = torch.from_numpy(g["newG.model.26.weight"]).cuda()
+        m = torch.from_numpy(g["gG.model.26.weight"]).cuda().abs()
+        sel = m > 5e-2 * m.max()
+        assert float((gg["model.26.weight"].detach()[sel] - ref[sel]).abs().max()) <= 1e-6
+
+
+def test_training_step_inject_vs_oracle_autograd():
+    """SatCLIP-injected generator: fc / scale_param / trunk gradients of the G pass vs torch autograd of the oracle."""
+    import nirgan_oracle as O
+    from nirgan_b200.model.pix2pix import Px2Px
+    sd_g = O.random_state_dict(O.generator_param_shapes(inject=True), seed=31, scale_param=0.5)
+    sd_d = O.random_state_dict(O.discriminator_param_shapes(), seed=32)
+    model = Px2Px(_cfg(inject=True))
+    _load(model, sd_g, sd_d)
+    model = model.cuda().train()
+    model.netG.configure_b200(precision="fp32", impl="simt")
+    model.netD.configure_b200(precision="fp32", impl="simt")
+    gen = torch.Generator().manual_seed(7)
+    rgb = 1.0 + torch.rand(2, 3, 64, 64, generator=gen)
+    nir = torch.rand(2, 1, 64, 64, generator=gen)
+    emb = torch.randn(2, 256, generator=gen)
+    loss = model.training_step({"rgb": rgb.cuda(), "nir": nir.cuda(), "embeds": emb.cuda()}, 0, 1)
+    loss.backward()
+    pg = {k: v.clone().requires_grad_(True) for k, v in sd_g.items()}
+    lo, _ = O.g_loss(pg, sd_d, rgb, nir, emb)
+    lo.backward()
+    assert abs(float(loss) - float(lo)) <= 2e-4 * abs(float(lo))
+    gg = dict(model.netG.named_parameters())
+    for k in ("scale_param", "fc.weight", "fc.bias", "model.1.weight", "model.4.weight", "model.26.weight"):
+        assert _relerr(gg[k].grad.cpu(), pg[k].grad) <= 1e-2, (k, _relerr(gg[k].grad.cpu(), pg[k].grad))
