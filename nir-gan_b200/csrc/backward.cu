@@ -241,6 +241,9 @@ head_bwd_prep_kernel(const float* __restrict__ dout, const float* __restrict__ o
       const size_t o = ((size_t)n * Hc + yc) * Wc + xc;
       v = dout[o] * scale;
       if (act == NG_ACT_TANH) { const float t = out[o]; v *= (1.f - t * t); }
+      // 16-bit gradient storage: saturate instead of overflowing to inf (the NDVI/NDWI/EVI terms are singular where
+      // pred + band crosses zero; an inf here would turn the whole backward pass into NaN)
+      if constexpr (sizeof(T) == 2) v = fminf(fmaxf(v, -3.0e4f), 3.0e4f);
     }
     T* d = dst + i * cpad;
     d[0] = from_f32<T>(v);

@@ -20,6 +20,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <string>
+#include <stdlib.h>
 
 namespace ng {
 
@@ -88,6 +89,27 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask)
+               : "memory");
+}
 __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
@@ -141,6 +163,9 @@ struct TcParams {
   int BH, BW;                 // patch of virtual pixels (BH*BW <= 128)
   int patches_y, patches_x, co_tiles;
   int total_tiles;
+  int group_items;            // G = B * patches_y * patches_x : tiles sharing one (phase, cout-tile) weight slab
+  int groups_per;             // ceil(G / cluster size)
+  int total_groups;           // co_tiles * nphase * groups_per
   int epilogue, act, crop;
   float slope;
   int bf16;
@@ -155,9 +180,9 @@ struct TcCfg {
   static constexpr int A_BYTES = 128 * KC * 2;
   static constexpr int B_BYTES = (BN * KC * 2 + 1023) / 1024 * 1024;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = BN >= 64 ? 128 * BN * 2 : 0;
+  static constexpr int STAGING_BYTES = BN >= 64 ? 128 * 64 * 2 : 0;      // one 64-channel epilogue pass
   static constexpr int RED_BYTES = BN >= 64 ? 2048 : 0;              // cross-group stats combine
-  static constexpr int BUDGET = 200 * 1024;
+  static constexpr int BUDGET = 222 * 1024;
   static constexpr int STAGES_RAW = (BUDGET - STAGING_BYTES - RED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns between the two accumulators
@@ -167,7 +192,10 @@ struct TcCfg {
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
-template <int BN, int KC>
+// CS = thread-block-cluster size.  The CS CTAs of a cluster work on CS different pixel patches that share the same
+// weight slab; each loads 1/CS of every B (weight) stage and multicasts it to all of them, which divides the
+// L2 -> SM weight traffic (the measured limiter of the 128x256 tile) by CS.
+template <int BN, int KC, int CS>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams p) {
@@ -188,9 +216,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CS, num_clusters = gridDim.x / CS;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), CS); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128); }
     fence_barrier_init();
     fence_proxy_async();
@@ -203,33 +234,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();     // peers' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const int chunks = g.Cin / KC;
+  // work item q (one per cluster and round) -> (cout tile, phase, group index); CTA `crank` takes item gi*CS + crank
+  auto decode = [&](int q, int& cot, int& ph, int& n, int& py, int& px, bool& dummy) {
+    int t = q;
+    const int gi = t % p.groups_per; t /= p.groups_per;
+    ph = t % g.nphase;
+    cot = t / g.nphase;
+    int idx = gi * CS + (int)crank;
+    dummy = idx >= p.group_items;             // odd tail: recompute the last patch, write nothing
+    if (dummy) idx = p.group_items - 1;
+    px = idx % p.patches_x; idx /= p.patches_x;
+    py = idx % p.patches_y;
+    n = idx / p.patches_y;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int cot = t % p.co_tiles; t /= p.co_tiles;
-        const int ph = t % g.nphase; t /= g.nphase;
-        const int px = t % p.patches_x; t /= p.patches_x;
-        const int py = t % p.patches_y; t /= p.patches_y;
-        const int n = t;
+      for (int q = cluster_id; q < p.total_groups; q += num_clusters) {
+        int cot, ph, n, py, px; bool dummy;
+        decode(q, cot, ph, n, py, px, dummy);
         const int i0 = py * p.BH, j0 = px * p.BW;
         for (int tp = g.phase_tap0[ph]; tp < g.phase_tap0[ph + 1]; ++tp) {
           const int by = g.S * i0 + g.taps[tp].dy, bx = g.S * j0 + g.taps[tp].dx;
           const int brow = g.taps[tp].wrow + cot * BN;
           for (int c = 0; c < chunks; ++c) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);       // free in every CTA of the cluster
             const uint32_t fb = smem_u32(&full_bar[stage]);
             const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
             mbar_expect_tx(fb, (uint32_t)(p.BH * p.BW * KC * 2 + BN * KC * 2));   // the A box holds BH*BW (<=128) rows
             tma_load_4d(&tmA, fb, sa, c * KC, bx, by, n);
-            tma_load_2d(&tmB, fb, sa + Cfg::A_BYTES, c * KC, brow);
+            if constexpr (CS == 1) {
+              tma_load_2d(&tmB, fb, sa + Cfg::A_BYTES, c * KC, brow);
+            } else {
+              constexpr int ROWS = BN / CS;                          // this CTA's slice of the weight rows
+              tma_load_2d_mc(&tmB, fb, sa + Cfg::A_BYTES + crank * (ROWS * KC * 2), c * KC, brow + (int)crank * ROWS,
+                             MC_MASK);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -244,8 +291,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t SBO = KC == 64 ? 1024 : 256;
       constexpr uint32_t LAYOUT = KC == 64 ? 2 : 6;
       uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int ph = (tile / p.co_tiles) % g.nphase;
+      for (int q = cluster_id; q < p.total_groups; q += num_clusters) {
+        const int ph = (q / p.groups_per) % g.nphase;
         const int kiters = (g.phase_tap0[ph + 1] - g.phase_tap0[ph]) * chunks;
         mbar_wait(smem_u32(&tempty_bar[as]), as_phase ^ 1);
         tc_fence_after();
@@ -259,7 +306,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < KC / 16; ++k)
             umma_f16(tmem_c, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((kit | k) != 0));
-          umma_commit(smem_u32(&empty_bar[stage]));
+          if constexpr (CS == 1) umma_commit(smem_u32(&empty_bar[stage]));
+          else umma_commit_mc(smem_u32(&empty_bar[stage]), MC_MASK);    // release the slot in every CTA of the cluster
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&tfull_bar[as]));
@@ -273,16 +321,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int row = q * 32 + lane;          // accumulator row == TMEM lane
     const int et = threadIdx.x - 64;        // 0..127 epilogue thread index
     uint32_t as = 0, as_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int cot = t % p.co_tiles; t /= p.co_tiles;
-      const int ph = t % g.nphase; t /= g.nphase;
-      const int px = t % p.patches_x; t /= p.patches_x;
-      const int py = t % p.patches_y; t /= p.patches_y;
-      const int n = t;
+    for (int q = cluster_id; q < p.total_groups; q += num_clusters) {
+      int cot, ph, n, py, px; bool dummy;
+      decode(q, cot, ph, n, py, px, dummy);
       const int vi = py * p.BH + row / p.BW, vj = px * p.BW + row % p.BW;
       const int oy = g.OS * vi + g.phase_oy[ph], ox = g.OS * vj + g.phase_ox[ph];
-      const bool valid = row < p.BH * p.BW && oy < g.Hout && ox < g.Wout;
+      const bool valid = !dummy && row < p.BH * p.BW && oy < g.Hout && ox < g.Wout;
       const int n0 = cot * BN;
 
       mbar_wait(smem_u32(&tfull_bar[as]), as_phase);
@@ -305,47 +349,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         rowoff[row] = valid ? ((((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout + n0) : -1ll;
+        // The tile is drained in passes of 64 output channels (16 KB of staging) so that the shared memory saved
+        // goes to one more operand pipeline stage.
+        constexpr int EB = 64, PASSES = BN / EB;
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld32(taddr + ch * 32, r);
-          tmem_ld_wait();
-          uint32_t w[16];
-          if (p.epilogue == NG_EPI_BIAS_ACT) {
+        for (int ps = 0; ps < PASSES; ++ps) {
+#pragma unroll 1
+          for (int ch = 0; ch < EB / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(taddr + ps * EB + ch * 32, r);
+            tmem_ld_wait();
+            uint32_t w[16];
+            if (p.epilogue == NG_EPI_BIAS_ACT) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const float b = p.bias ? p.bias[n0 + ch * 32 + k] : 0.f;
-              r[k] = __float_as_uint(apply_act(__uint_as_float(r[k]) + b, p.act, p.slope));
+              for (int k = 0; k < 32; ++k) {
+                const float b = p.bias ? p.bias[n0 + ps * EB + ch * 32 + k] : 0.f;
+                r[k] = __float_as_uint(apply_act(__uint_as_float(r[k]) + b, p.act, p.slope));
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float a = valid ? __uint_as_float(r[2 * k]) : 0.f, b = valid ? __uint_as_float(r[2 * k + 1]) : 0.f;
+              w[k] = p.bf16 ? pack2<__nv_bfloat16>(a, b) : pack2<__half>(a, b);
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int chunk = (ch * 4 + c4) ^ (row & 7);
+              *reinterpret_cast<uint4*>(staging + (size_t)row * (EB * 2) + chunk * 16) =
+                  make_uint4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
             }
           }
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float a = valid ? __uint_as_float(r[2 * k]) : 0.f, b = valid ? __uint_as_float(r[2 * k + 1]) : 0.f;
-            w[k] = p.bf16 ? pack2<__nv_bfloat16>(a, b) : pack2<__half>(a, b);
+          if (ps == PASSES - 1) {
+            tc_fence_before();
+            mbar_arrive(smem_u32(&tempty_bar[as]));     // accumulator drained: the MMA warp may reuse it
           }
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int chunk = (ch * 4 + c4) ^ (row & 7);
-            *reinterpret_cast<uint4*>(staging + (size_t)row * (BN * 2) + chunk * 16) =
-                make_uint4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(smem_u32(&tempty_bar[as]));     // accumulator drained: the MMA warp may reuse it
-        epi_bar_sync();
+          epi_bar_sync();
 
-        // ---- per-channel partial statistics (deterministic: fixed row order, fixed combine order) ----
-        if (p.epilogue == NG_EPI_RAW && p.stat_partials != nullptr) {
-          constexpr int PAIRS = BN / 2, G = 128 / PAIRS;
-          const int cp = et % PAIRS, rs = et / PAIRS;
-          float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-          for (int r2 = rs; r2 < 128; r2 += G) {
-            const uint32_t word = *reinterpret_cast<const uint32_t*>(staging + (size_t)r2 * (BN * 2) +
-                                                                     (((cp >> 2) ^ (r2 & 7)) * 16) + (cp & 3) * 4);
-            const float2 v = p.bf16 ? unpack2<__nv_bfloat16>(word) : unpack2<__half>(word);
-            s0 += v.x; q0 = fmaf(v.x, v.x, q0); s1 += v.y; q1 = fmaf(v.y, v.y, q1);
-          }
-          if constexpr (G > 1) {
+          // ---- per-channel partial statistics (deterministic: fixed row order, fixed combine order) ----
+          if (p.epilogue == NG_EPI_RAW && p.stat_partials != nullptr) {
+            constexpr int PAIRS = EB / 2, G = 128 / PAIRS;        // 32 channel pairs x 4 row groups
+            const int cp = et % PAIRS, rs = et / PAIRS;
+            float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+            for (int r2 = rs; r2 < 128; r2 += G) {
+              const uint32_t word = *reinterpret_cast<const uint32_t*>(staging + (size_t)r2 * (EB * 2) +
+                                                                       (((cp >> 2) ^ (r2 & 7)) * 16) + (cp & 3) * 4);
+              const float2 v = p.bf16 ? unpack2<__nv_bfloat16>(word) : unpack2<__half>(word);
+              s0 += v.x; q0 = fmaf(v.x, v.x, q0); s1 += v.y; q1 = fmaf(v.y, v.y, q1);
+            }
             if (rs > 0) *reinterpret_cast<float4*>(red + ((rs - 1) * PAIRS + cp) * 4) = make_float4(s0, q0, s1, q1);
             epi_bar_sync();
             if (rs == 0) {
@@ -353,30 +403,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 o = *reinterpret_cast<const float4*>(red + ((k - 1) * PAIRS + cp) * 4);
                 s0 += o.x; q0 += o.y; s1 += o.z; q1 += o.w;
               }
+              if (!dummy) {
+                const int slot = (ph * p.patches_y + py) * p.patches_x + px;
+                float* dst = p.stat_partials + (((size_t)n * p.stat_slots + slot) * g.Cout + n0 + ps * EB + 2 * cp) * 2;
+                *reinterpret_cast<float4*>(dst) = make_float4(s0, q0, s1, q1);
+              }
             }
           }
-          if (rs == 0) {
-            const int slot = (ph * p.patches_y + py) * p.patches_x + px;
-            float* dst = p.stat_partials + (((size_t)n * p.stat_slots + slot) * g.Cout + n0 + 2 * cp) * 2;
-            *reinterpret_cast<float4*>(dst) = make_float4(s0, q0, s1, q1);
-          }
-        }
 
-        // ---- coalesced row stores: BN/8 lanes x 16 B per row ----
-        {
-          constexpr int LPR = BN / 8, RPI = 32 / LPR;     // lanes per row, rows per warp-instruction
-          const int we = warp - 2;
-          const int chunk = lane % LPR;
-          uint8_t* ybase = reinterpret_cast<uint8_t*>(p.y);
-          for (int r2 = we * RPI + lane / LPR; r2 < 128; r2 += 4 * RPI) {
-            const long long off = rowoff[r2];
-            if (off >= 0) {
-              const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)r2 * (BN * 2) + ((chunk ^ (r2 & 7)) * 16));
-              *reinterpret_cast<uint4*>(ybase + off * 2 + chunk * 16) = v;
+          // ---- coalesced row stores: 8 lanes x 16 B per 128-byte row slice, 4 rows per warp instruction ----
+          {
+            constexpr int LPR = EB / 8, RPI = 32 / LPR;
+            const int we = warp - 2;
+            const int chunk = lane % LPR;
+            uint8_t* ybase = reinterpret_cast<uint8_t*>(p.y);
+            for (int r2 = we * RPI + lane / LPR; r2 < 128; r2 += 4 * RPI) {
+              const long long off = rowoff[r2];
+              if (off >= 0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)r2 * (EB * 2) + ((chunk ^ (r2 & 7)) * 16));
+                *reinterpret_cast<uint4*>(ybase + (off + ps * EB) * 2 + chunk * 16) = v;
+              }
             }
           }
+          epi_bar_sync();   // staging (and, after the last pass, rowoff) are reused
         }
-        epi_bar_sync();   // staging / rowoff are reused by the next tile
       }
       if (++as == 2) { as = 0; as_phase ^= 1; }
     }
@@ -384,6 +434,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into it
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
                  : "memory");
@@ -424,7 +475,7 @@ static void choose_patch(int VH, int VW, int S, int& BH, int& BW) {
   }
 }
 
-template <int BN, int KC>
+template <int BN, int KC, int CS>
 static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   using Cfg = TcCfg<BN, KC>;
   int r = get_encode();
@@ -437,8 +488,11 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   p.patches_x = (g.VW + p.BW - 1) / p.BW;
   p.co_tiles = g.Cout / BN;
   const long long tiles = (long long)g.B * p.patches_y * p.patches_x * g.nphase * p.co_tiles;
-  NG_REQUIRE(tiles > 0 && tiles < (1ll << 31), NG_E_SHAPE, "conv_tc: tile count out of range");
+  NG_REQUIRE(tiles > 0 && tiles < (1ll << 30), NG_E_SHAPE, "conv_tc: tile count out of range");
   p.total_tiles = (int)tiles;
+  p.group_items = g.B * p.patches_y * p.patches_x;
+  p.groups_per = (p.group_items + CS - 1) / CS;
+  p.total_groups = p.co_tiles * g.nphase * p.groups_per;
   p.epilogue = a.epilogue; p.act = a.act; p.crop = a.crop; p.slope = a.slope;
   p.bf16 = a.dtype == NG_BF16;
   p.stat_slots = g.nphase * p.patches_y * p.patches_x;
@@ -461,23 +515,55 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
     const int taps_total = a.KH * a.KW;
     cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)taps_total * g.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(BN / CS)};
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = g_encode(&tmB, dt, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "cuTensorMapEncodeTiled(B) failed: %d", (int)cr);
   }
   static bool attr_set = false;   // per instantiation
+  static int max_ctas = 0;
   if (!attr_set) {
-    int e = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int e = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES), "cudaFuncSetAttribute(conv_tc)");
     if (e) return e;
+    max_ctas = num_sms() / CS * CS;
+    if (CS > 1) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(max_ctas); qc.blockDim = dim3(192); qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa; qc.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, conv_tc_kernel<BN, KC, CS>, &qc) == cudaSuccess && ncl > 0 &&
+          ncl * CS < max_ctas)
+        max_ctas = ncl * CS;      // persistent kernel: every cluster must be co-resident
+    }
     attr_set = true;
   }
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  conv_tc_kernel<BN, KC><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  long long want = (long long)p.total_groups * CS;
+  const int grid = (int)(want < max_ctas ? want : max_ctas);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs; cfg.numAttrs = 1;
+  int e = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, CS>, tmA, tmB, p), "conv_tc_kernel launch");
+  if (e) return e;
   NG_LAUNCH_CHECK("conv_tc_kernel");
   return NG_OK;
+}
+
+static int cluster_size_for(int bn, int kc) {
+  static int env = -1;
+  if (env < 0) {
+    const char* v = getenv("NIRGAN_B200_CLUSTER");
+    env = v ? atoi(v) : 1;      // measured on B200: multicast does not shorten the kernel (not L2-bound); kept as a switch
+    if (env != 1 && env != 2 && env != 4) env = 1;
+  }
+  return (bn == 256 && kc == 64) ? env : 1;     // multicast pays on the weight-heavy 256-wide tiles
 }
 
 static int tc_block_n(const ng_conv_args& a) {
@@ -502,13 +588,18 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   const int kc = a.Cin % 64 == 0 ? 64 : (a.Cin == 16 ? 16 : 0);
   NG_REQUIRE(bn != 0 && kc != 0, NG_E_UNSUPPORTED, "conv_tc: Cin %d / Cout %d not tileable", a.Cin, a.Cout);
   NG_REQUIRE(a.epilogue != NG_EPI_HEAD || a.Cout == 16, NG_E_SHAPE, "conv_tc: head epilogue expects Cout stored as 16");
-  if (bn == 16 && kc == 64) return launch_tc<16, 64>(a, g, st);
-  if (bn == 64 && kc == 16) return launch_tc<64, 16>(a, g, st);
-  if (bn == 128 && kc == 16) return launch_tc<128, 16>(a, g, st);
-  if (bn == 256 && kc == 16) return launch_tc<256, 16>(a, g, st);
-  if (bn == 64 && kc == 64) return launch_tc<64, 64>(a, g, st);
-  if (bn == 128 && kc == 64) return launch_tc<128, 64>(a, g, st);
-  if (bn == 256 && kc == 64) return launch_tc<256, 64>(a, g, st);
+  if (bn == 16 && kc == 64) return launch_tc<16, 64, 1>(a, g, st);
+  if (bn == 64 && kc == 16) return launch_tc<64, 16, 1>(a, g, st);
+  if (bn == 128 && kc == 16) return launch_tc<128, 16, 1>(a, g, st);
+  if (bn == 256 && kc == 16) return launch_tc<256, 16, 1>(a, g, st);
+  if (bn == 64 && kc == 64) return launch_tc<64, 64, 1>(a, g, st);
+  if (bn == 128 && kc == 64) return launch_tc<128, 64, 1>(a, g, st);
+  if (bn == 256 && kc == 64) {
+    const int cs = cluster_size_for(bn, kc);
+    if (cs == 4) return launch_tc<256, 64, 4>(a, g, st);
+    if (cs == 2) return launch_tc<256, 64, 2>(a, g, st);
+    return launch_tc<256, 64, 1>(a, g, st);
+  }
   set_error("conv_tc: no kernel for BN %d KC %d", bn, kc);
   return NG_E_UNSUPPORTED;
 }

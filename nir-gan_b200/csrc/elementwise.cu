@@ -105,28 +105,29 @@ in_stats_kernel(const T* __restrict__ y, int HW, int C, float* __restrict__ mr) 
   }
 }
 
-// partials: [B][slots][C][2] (sum, sumsq) -> mean / rstd.  One thread per (n, c) pair of channels walks the
-// slots in fixed order (deterministic); consecutive threads read consecutive 16-byte words.
-__global__ void __launch_bounds__(128)
+// partials: [B][slots][C][2] (sum, sumsq) -> mean / rstd.  One warp per (n, channel pair): lanes stride over the
+// slots, then a fixed-order shuffle tree -> deterministic, and the loads of a warp are independent.
+__global__ void __launch_bounds__(256)
 in_stats_finalize_kernel(const float* __restrict__ part, int B, int slots, int C, float inv_count,
                          float* __restrict__ mr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // index over B * C/2
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int C2 = C >> 1;
-  if (i >= B * C2) return;
-  const int n = i / C2, c2 = i % C2;
+  if (wid >= B * C2) return;
+  const int n = wid / C2, c2 = wid % C2;
   const float4* p = reinterpret_cast<const float4*>(part + ((size_t)n * slots * C + 2 * c2) * 2);
-  double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
   const size_t stride = (size_t)C * 2 / 4;
-#pragma unroll 4
-  for (int k = 0; k < slots; ++k) {
+  float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+  for (int k = lane; k < slots; k += 32) {
     const float4 v = p[(size_t)k * stride];
     s0 += v.x; q0 += v.y; s1 += v.z; q1 += v.w;
   }
-  const double m0 = s0 * inv_count, m1 = s1 * inv_count;
-  double v0 = q0 * inv_count - m0 * m0, v1 = q1 * inv_count - m1 * m1;
-  v0 = v0 < 0.0 ? 0.0 : v0; v1 = v1 < 0.0 ? 0.0 : v1;
-  *reinterpret_cast<float4*>(mr + ((size_t)n * C + 2 * c2) * 2) =
-      make_float4((float)m0, (float)(1.0 / sqrt(v0 + 1e-5)), (float)m1, (float)(1.0 / sqrt(v1 + 1e-5)));
+  s0 = warp_sum(s0); q0 = warp_sum(q0); s1 = warp_sum(s1); q1 = warp_sum(q1);
+  if (lane == 0) {
+    const float m0 = s0 * inv_count, m1 = s1 * inv_count;
+    const float v0 = fmaxf(q0 * inv_count - m0 * m0, 0.f), v1 = fmaxf(q1 * inv_count - m1 * m1, 0.f);
+    *reinterpret_cast<float4*>(mr + ((size_t)n * C + 2 * c2) * 2) =
+        make_float4(m0, rsqrtf(v0 + 1e-5f), m1, rsqrtf(v1 + 1e-5f));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -242,15 +243,48 @@ in_apply_kernel(const T* __restrict__ y, int B, int H, int W, int C, int c8_shif
 __global__ void __launch_bounds__(256)
 linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int B, int K,
               int N, float* __restrict__ y) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N) return;
-  const float* wr = w + (size_t)warp * K;
-  const float bv = bias ? bias[warp] : 0.f;
-  for (int b = 0; b < B; ++b) {
-    float s = 0.f;
-    for (int k = lane; k < K; k += 32) s = fmaf(x[(size_t)b * K + k], wr[k], s);
-    s = warp_sum(s);
-    if (lane == 0) y[(size_t)b * N + warp] = s + bv;
+  // tile: 64 batch rows x 64 outputs, K in chunks of 32; thread = 4 x 4 outputs
+  __shared__ float Xs[32][64 + 4];
+  __shared__ float Ws[32][64 + 4];
+  const int n0 = blockIdx.x * 64, b0 = blockIdx.y * 64;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int lr = t >> 2, lk = (t & 3) * 8;      // loader: 64 rows x 4 threads x 8 k
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + lk + e;
+      Xs[lk + e][lr] = (b0 + lr < B && k < K) ? x[(size_t)(b0 + lr) * K + k] : 0.f;
+      Ws[lk + e][lr] = (n0 + lr < N && k < K) ? w[(size_t)(n0 + lr) * K + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = Xs[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = b0 + ty * 4 + i;
+    if (b >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) y[(size_t)b * N + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+    }
   }
 }
 
@@ -430,27 +464,50 @@ __global__ void unpack_rowmerged_kernel(const float* __restrict__ packed, int O,
 // tap gather: out[n][y][x] = act(bias + sum_t z[n][y+kh][x+kw][t])   (see ng_tap_gather)
 // one warp = 32 consecutive output columns of one row; lanes walk the taps.
 // ---------------------------------------------------------------------------------------------
+// block = 8 x 32 output pixels; the (8+KH-1) x (32+KW-1) input pixels' tap vectors are staged in shared memory with
+// coalesced 128-byte row reads (pixel pitch 33 words -> conflict-free strided reads), then each thread sums its taps.
+constexpr int TG_H = 8, TG_W = 32;
 template <typename T>
 __global__ void __launch_bounds__(256)
 tap_gather_kernel(const T* __restrict__ z, int B, int Hz, int Wz, int zc, int KH, int KW,
-                  const float* __restrict__ bias, int act, int crop, float* __restrict__ out) {
+                  const float* __restrict__ bias, int act, int crop, float* __restrict__ out, int tiles_x, int tiles_y) {
+  extern __shared__ uint32_t tg_sm[];
   const int Ho = Hz - KH + 1 - 2 * crop, Wo = Wz - KW + 1 - 2 * crop;
-  const long long total = (long long)B * Ho * Wo;
-  const float b0 = bias ? bias[0] : 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % Wo);
-    const int y = (int)((i / Wo) % Ho);
-    const int n = (int)(i / ((long long)Wo * Ho));
-    const T* base = z + (((long long)n * Hz + y + crop) * Wz + x + crop) * zc;
-    float s = 0.f;
-    for (int kh = 0; kh < KH; ++kh) {
-      const T* row = base + (long long)kh * Wz * zc + kh * KW;
-#pragma unroll 7
-      for (int kw = 0; kw < KW; ++kw) s += to_f32<T>(row[(long long)kw * zc + kw]);
-    }
-    out[i] = apply_act(s + b0, act, 0.f);
+  const int PH = TG_H + KH - 1, PW = TG_W + KW - 1;
+  const int words = zc / 2;                      // 16-bit path: 2 taps per word; pitch = words + 1
+  const int pitch = (sizeof(T) == 2 ? words : zc) + 1;
+  int tix = blockIdx.x;
+  const int tx0 = (tix % tiles_x) * TG_W; tix /= tiles_x;
+  const int ty0 = (tix % tiles_y) * TG_H;
+  const int n = tix / tiles_y;
+  const int row_words = sizeof(T) == 2 ? words : zc;
+  // stage: every thread copies 4-byte words; consecutive threads -> consecutive words of one pixel
+  for (int i = threadIdx.x; i < PH * PW * row_words; i += 256) {
+    const int wd = i % row_words, pix = i / row_words;
+    const int py = pix / PW, px = pix % PW;
+    const int gy = ty0 + crop + py, gx = tx0 + crop + px;
+    uint32_t v = 0;
+    if (gy < Hz && gx < Wz)
+      v = reinterpret_cast<const uint32_t*>(z + (((size_t)n * Hz + gy) * Wz + gx) * zc)[wd];
+    tg_sm[pix * pitch + wd] = v;
   }
+  __syncthreads();
+  const int lx = threadIdx.x % TG_W, ly = threadIdx.x / TG_W;
+  const int ox = tx0 + lx, oy = ty0 + ly;
+  if (ox >= Wo || oy >= Ho) return;
+  float s = 0.f;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      const int t = kh * KW + kw;
+      const int pix = (ly + kh) * PW + lx + kw;
+      if constexpr (sizeof(T) == 2) {
+        const float2 v = unpack2<T>(tg_sm[pix * pitch + (t >> 1)]);
+        s += (t & 1) ? v.y : v.x;
+      } else {
+        s += __uint_as_float(tg_sm[pix * pitch + t]);
+      }
+    }
+  out[((size_t)n * Ho + oy) * Wo + ox] = apply_act(s + (bias ? bias[0] : 0.f), act, 0.f);
 }
 
 static inline unsigned grid_for(long long work_items, int threads) {
@@ -530,8 +587,8 @@ extern "C" int ng_in_stats_finalize(const float* partials, int32_t B, int32_t sl
   NG_REQUIRE(partials && mean_rstd && B > 0 && slots > 0 && C > 0 && count > 0, NG_E_ARG,
              "in_stats_finalize: bad arguments");
   NG_REQUIRE(C % 2 == 0, NG_E_SHAPE, "in_stats_finalize: C must be even");
-  in_stats_finalize_kernel<<<(B * C / 2 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, B, slots, C,
-                                                                                     1.0f / (float)count, mean_rstd);
+  in_stats_finalize_kernel<<<(B * (C / 2) * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      partials, B, slots, C, 1.0f / (float)count, mean_rstd);
   NG_LAUNCH_CHECK("in_stats_finalize_kernel");
   return NG_OK;
 }
@@ -569,8 +626,8 @@ extern "C" int ng_linear(const float* x, const float* w, const float* bias, int3
                          float* y, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(x && w && y && B > 0 && K > 0 && N > 0, NG_E_ARG, "linear: bad arguments");
-  const int blocks = (N * 32 + 255) / 256;
-  linear_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, w, bias, B, K, N, y);
+  dim3 grid((N + 63) / 64, (B + 63) / 64);
+  linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, B, K, N, y);
   NG_LAUNCH_CHECK("linear_kernel");
   return NG_OK;
 }
@@ -657,9 +714,24 @@ extern "C" int ng_tap_gather(const void* z, int32_t dtype, int32_t B, int32_t Hz
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(z && out && KH * KW <= zc, NG_E_ARG, "tap_gather: need KH*KW <= zc");
   NG_REQUIRE(Hz - KH + 1 - 2 * crop > 0 && Wz - KW + 1 - 2 * crop > 0, NG_E_SHAPE, "tap_gather: empty output");
-  const long long total = (long long)B * (Hz - KH + 1 - 2 * crop) * (Wz - KW + 1 - 2 * crop);
-  DISPATCH_DTYPE(dtype, (tap_gather_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                            (const T*)z, B, Hz, Wz, zc, KH, KW, bias, act, crop, out)));
+  NG_REQUIRE(zc % 2 == 0, NG_E_SHAPE, "tap_gather: zc must be even");
+  const int Ho = Hz - KH + 1 - 2 * crop, Wo = Wz - KW + 1 - 2 * crop;
+  const int tiles_x = (Wo + TG_W - 1) / TG_W, tiles_y = (Ho + TG_H - 1) / TG_H;
+  const int row_words = dtype == NG_F32 ? zc : zc / 2;
+  const size_t smem = (size_t)(TG_H + KH - 1) * (TG_W + KW - 1) * (row_words + 1) * 4;
+  NG_REQUIRE(smem <= 160 * 1024, NG_E_SHAPE, "tap_gather: tile does not fit in shared memory");
+  {
+    cudaError_t e1 = cudaSuccess;
+    switch (dtype) {
+      case NG_F32: e1 = cudaFuncSetAttribute(tap_gather_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case NG_F16: e1 = cudaFuncSetAttribute(tap_gather_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case NG_BF16: e1 = cudaFuncSetAttribute(tap_gather_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+    }
+    int e = check_cuda(e1, "tap_gather smem attribute");
+    if (e) return e;
+  }
+  DISPATCH_DTYPE(dtype, (tap_gather_kernel<T><<<(unsigned)((long long)B * tiles_x * tiles_y), 256, smem, (cudaStream_t)stream>>>(
+                            (const T*)z, B, Hz, Wz, zc, KH, KW, bias, act, crop, out, tiles_x, tiles_y)));
   NG_LAUNCH_CHECK("tap_gather_kernel");
   return NG_OK;
 }

@@ -12,10 +12,20 @@ from . import _lib as L
 class B200Adam(torch.optim.Optimizer):
     def __init__(self, params, lr=2e-4, betas=(0.5, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.skip_nonfinite = True
+        self.skipped_steps = 0
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale: float = 1.0):
         loss = closure() if closure is not None else None
+        # low-precision backward: a non-finite gradient (fp16 overflow despite the loss scale) skips the update,
+        # like torch.cuda.amp.GradScaler does; the flag is read once per step.
+        grads = [p.grad for g in self.param_groups for p in g["params"] if p.grad is not None]
+        if grads and self.skip_nonfinite:
+            bad = torch.stack([(~torch.isfinite(g)).any() for g in grads]).any()
+            if bool(bad):
+                self.skipped_steps += 1
+                return loss
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:

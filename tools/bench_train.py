@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Secondary measurement (BASELINE.json configs[3]): one full Pix2Pix training step (D pass then G pass, LSGAN +
+100*L1 + NDVI/NDWI/EVI, Adam) at batch 32, 256x256 tiles, through nirgan_b200.model.pix2pix.Px2Px.
+Prints one JSON line: samples/s, ms per step, algorithmic TFLOP/s (391.6 GFLOP per sample)."""
+import argparse
+import contextlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--tile", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--precision", default="fp16")
+    ap.add_argument("--conv", default="tc")
+    args = ap.parse_args()
+    import nirgan_b200  # noqa: F401
+    from nirgan_b200.model.pix2pix import Px2Px
+    from test_gpu_train import _cfg
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(sys.stderr):
+        model = Px2Px(_cfg()).to(dev).train()
+    model.netG.configure_b200(precision=args.precision, impl=args.conv)
+    model.netD.configure_b200(precision=args.precision, impl=args.conv)
+    opt_d, opt_g = model.configure_optimizers()
+    g = torch.Generator().manual_seed(1)
+    batch = {"rgb": torch.rand(args.batch, 3, args.tile, args.tile, generator=g).to(dev),
+             "nir": torch.rand(args.batch, 1, args.tile, args.tile, generator=g).to(dev)}
+
+    def step():
+        opt_d.zero_grad(set_to_none=True)
+        ld = model.training_step(batch, 0, 0)
+        ld.backward()
+        opt_d.step()
+        opt_g.zero_grad(set_to_none=True)
+        lg = model.training_step(batch, 0, 1)
+        lg.backward()
+        opt_g.step()
+        return ld, lg
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ld, lg = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    # reference-faithful op count: 2 G forwards per batch (pix2pix.py:177-180 runs G in both optimizer passes)
+    gflop = 505.8 * (args.tile / 256.0) ** 2
+    print(json.dumps({"workload": f"configs[3]: Pix2Pix training step, batch {args.batch}, {args.tile}px, {args.precision}/{args.conv}",
+                      "ms_per_step": ms, "samples_per_s": args.batch / ms * 1e3,
+                      "algorithmic_tflops": args.batch * gflop / ms,
+                      "loss_D": float(ld), "loss_G": float(lg),
+                      "mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                      "skipped_steps": [opt_d.skipped_steps, opt_g.skipped_steps]}))
+
+
+if __name__ == "__main__":
+    main()
