@@ -102,8 +102,14 @@ int ng_conv_stat_slots(const ng_conv_args* a);
 int ng_conv2d(const ng_conv_args* a, void* stream);
 
 /* weight gradient: dw[tap][n][k] (fp32, packed layout) = sum_pixels dy[.., n] * x[.. shifted by tap .., k]
- * with the geometry of the forward op described by `a` (a->x = forward input, a->y = dY compact). */
-int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void* stream);
+ * with the geometry of the forward op described by `a` (a->x = forward input, a->y = dY compact).
+ * impl == NG_IMPL_TC with 16-bit operands, Cin in {64,128,256} and Cout % 64 == 0 runs the tcgen05 split-K kernel
+ * (MN-major operands straight from the NHWC tensors; deterministic two-stage reduction) and needs a caller-provided
+ * workspace of ng_conv2d_wgrad_workspace_bytes(a) bytes; other geometries (and workspace == NULL) use the CUDA-core
+ * kernel.  dbias (optional) = per-channel sum of dy. */
+int64_t ng_conv2d_wgrad_workspace_bytes(const ng_conv_args* a);
+int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void* workspace, int64_t workspace_bytes,
+                    void* stream);
 
 /* pack an fp32 weight (4-D, [d0][d1][KH][KW]) into [tap][n][k]; n_axis selects which of d0/d1 is n.
  * k is zero-padded to k_pad, n to n_pad. */

@@ -38,7 +38,8 @@ _SIGNATURES = {
     "ng_device_check": (c_i32, [c_i32]),
     "ng_conv_stat_slots": (c_i32, [C.POINTER(ConvArgs)]),
     "ng_conv2d": (c_i32, [C.POINTER(ConvArgs), c_vp]),
-    "ng_conv2d_wgrad": (c_i32, [C.POINTER(ConvArgs), c_vp, c_vp, c_vp]),
+    "ng_conv2d_wgrad_workspace_bytes": (c_i64, [C.POINTER(ConvArgs)]),
+    "ng_conv2d_wgrad": (c_i32, [C.POINTER(ConvArgs), c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ng_pack_weight": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_unpack_weight_grad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
     "ng_prep_stem": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),

@@ -3,7 +3,11 @@
 
 namespace ng {
 int conv_simt(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st);
-int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, float* dbias, cudaStream_t st);
+int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, cudaStream_t st);
+int bias_grad(const ng_conv_args& a, const ConvGeom& g, float* dbias, cudaStream_t st);
+int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspace, long long workspace_bytes,
+             cudaStream_t st, bool* handled);
+long long wgrad_tc_workspace_bytes(const ng_conv_args& a, const ConvGeom& g);
 int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st);
 int conv_tc_stat_slots(const ng_conv_args& a, const ConvGeom& g);
 }  // namespace ng
@@ -44,7 +48,17 @@ extern "C" int ng_conv2d(const ng_conv_args* a, void* stream) {
   return NG_E_ARG;
 }
 
-extern "C" int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void* stream) {
+extern "C" int64_t ng_conv2d_wgrad_workspace_bytes(const ng_conv_args* a) {
+  if (!a) return NG_E_ARG;
+  ConvGeom g;
+  int r = build_geometry(*a, g);
+  if (r) return r;
+  if (a->impl != NG_IMPL_TC) return 0;
+  return wgrad_tc_workspace_bytes(*a, g);
+}
+
+extern "C" int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
   int r = require_sm100();
   if (r) return r;
   r = validate(a);
@@ -53,5 +67,15 @@ extern "C" int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* d
   ConvGeom g;
   r = build_geometry(*a, g);
   if (r) return r;
-  return wgrad_simt(*a, g, dw_packed, dbias, (cudaStream_t)stream);
+  bool handled = false;
+  if (a->impl == NG_IMPL_TC) {
+    r = wgrad_tc(*a, g, dw_packed, workspace, workspace_bytes, (cudaStream_t)stream, &handled);
+    if (r) return r;
+  }
+  if (!handled) {
+    r = wgrad_simt(*a, g, dw_packed, (cudaStream_t)stream);
+    if (r) return r;
+  }
+  if (dbias) return bias_grad(*a, g, dbias, (cudaStream_t)stream);
+  return NG_OK;
 }

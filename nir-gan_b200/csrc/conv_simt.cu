@@ -199,7 +199,7 @@ __global__ void colsum_kernel(const T* __restrict__ dy, long long rows, int C, f
 }
 
 template <typename T>
-static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, float* dbias, cudaStream_t st) {
+static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, cudaStream_t st) {
   const int n_tiles = (g.Cout + 63) / 64, k_tiles = (g.Cin + 63) / 64;
   const long long npix = (long long)g.B * g.VH * g.VW;
   long long sp_ = npix / 2048; if (sp_ < 1) sp_ = 1; if (sp_ > 64) sp_ = 64;
@@ -214,23 +214,36 @@ static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, flo
   wgrad_simt_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, n_tiles, k_tiles,
                                                         splits, (int)pps);
   NG_LAUNCH_CHECK("wgrad_simt_kernel");
-  if (dbias) {
-    e = check_cuda(cudaMemsetAsync(dbias, 0, (size_t)g.Cout * sizeof(float), st), "dbias memset");
-    if (e) return e;
-    const long long rows = (long long)g.B * g.Hout * g.Wout;
-    const unsigned cs_blocks = (unsigned)(rows < 1024 ? rows : 1024);
-    const unsigned cs_threads = (unsigned)(g.Cout < 256 ? g.Cout : 256);
-    colsum_kernel<T><<<cs_blocks, cs_threads, 0, st>>>((const T*)a.y, rows, g.Cout, dbias);
-    NG_LAUNCH_CHECK("colsum_kernel");
-  }
   return NG_OK;
 }
 
-int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, float* dbias, cudaStream_t st) {
+template <typename T>
+static int launch_bias_grad(const ng_conv_args& a, const ConvGeom& g, float* dbias, cudaStream_t st) {
+  int e = check_cuda(cudaMemsetAsync(dbias, 0, (size_t)g.Cout * sizeof(float), st), "dbias memset");
+  if (e) return e;
+  const long long rows = (long long)g.B * g.Hout * g.Wout;
+  const unsigned cs_blocks = (unsigned)(rows < 1024 ? rows : 1024);
+  const unsigned cs_threads = (unsigned)(g.Cout < 256 ? g.Cout : 256);
+  colsum_kernel<T><<<cs_blocks, cs_threads, 0, st>>>((const T*)a.y, rows, g.Cout, dbias);
+  NG_LAUNCH_CHECK("colsum_kernel");
+  return NG_OK;
+}
+
+int bias_grad(const ng_conv_args& a, const ConvGeom& g, float* dbias, cudaStream_t st) {
   switch (a.dtype) {
-    case NG_F32:  return launch_wgrad<float>(a, g, dw, dbias, st);
-    case NG_F16:  return launch_wgrad<__half>(a, g, dw, dbias, st);
-    case NG_BF16: return launch_wgrad<__nv_bfloat16>(a, g, dw, dbias, st);
+    case NG_F32:  return launch_bias_grad<float>(a, g, dbias, st);
+    case NG_F16:  return launch_bias_grad<__half>(a, g, dbias, st);
+    case NG_BF16: return launch_bias_grad<__nv_bfloat16>(a, g, dbias, st);
+  }
+  set_error("bias_grad: bad dtype %d", a.dtype);
+  return NG_E_ARG;
+}
+
+int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, cudaStream_t st) {
+  switch (a.dtype) {
+    case NG_F32:  return launch_wgrad<float>(a, g, dw, st);
+    case NG_F16:  return launch_wgrad<__half>(a, g, dw, st);
+    case NG_BF16: return launch_wgrad<__nv_bfloat16>(a, g, dw, st);
   }
   set_error("wgrad_simt: bad dtype %d", a.dtype);
   return NG_E_ARG;

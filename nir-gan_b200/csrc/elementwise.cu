@@ -464,47 +464,49 @@ __global__ void unpack_rowmerged_kernel(const float* __restrict__ packed, int O,
 // tap gather: out[n][y][x] = act(bias + sum_t z[n][y+kh][x+kw][t])   (see ng_tap_gather)
 // one warp = 32 consecutive output columns of one row; lanes walk the taps.
 // ---------------------------------------------------------------------------------------------
-// block = 8 x 32 output pixels; the (8+KH-1) x (32+KW-1) input pixels' tap vectors are staged in shared memory with
-// coalesced 128-byte row reads (pixel pitch 33 words -> conflict-free strided reads), then each thread sums its taps.
+// block = 8 x 32 output pixels; the (8+KH-1) x (32+KW-1) input pixels' tap vectors are staged in shared memory
+// (one warp copies one pixel's 128-byte vector per step -> fully coalesced; pixel pitch ZW+1 words -> the strided
+// reads below are bank-conflict free), then each thread sums its KH*KW taps.  KH, KW, ZC are compile-time.
 constexpr int TG_H = 8, TG_W = 32;
-template <typename T>
+template <typename T, int KH, int KW, int ZC>
 __global__ void __launch_bounds__(256)
-tap_gather_kernel(const T* __restrict__ z, int B, int Hz, int Wz, int zc, int KH, int KW,
-                  const float* __restrict__ bias, int act, int crop, float* __restrict__ out, int tiles_x, int tiles_y) {
+tap_gather_kernel(const T* __restrict__ z, int B, int Hz, int Wz, const float* __restrict__ bias, int act, int crop,
+                  float* __restrict__ out, int tiles_x, int tiles_y) {
   extern __shared__ uint32_t tg_sm[];
+  constexpr int PH = TG_H + KH - 1, PW = TG_W + KW - 1;
+  constexpr int ZW = sizeof(T) == 2 ? ZC / 2 : ZC;        // 32-bit words per pixel
+  constexpr int PITCH = ZW + 1;
   const int Ho = Hz - KH + 1 - 2 * crop, Wo = Wz - KW + 1 - 2 * crop;
-  const int PH = TG_H + KH - 1, PW = TG_W + KW - 1;
-  const int words = zc / 2;                      // 16-bit path: 2 taps per word; pitch = words + 1
-  const int pitch = (sizeof(T) == 2 ? words : zc) + 1;
   int tix = blockIdx.x;
   const int tx0 = (tix % tiles_x) * TG_W; tix /= tiles_x;
   const int ty0 = (tix % tiles_y) * TG_H;
   const int n = tix / tiles_y;
-  const int row_words = sizeof(T) == 2 ? words : zc;
-  // stage: every thread copies 4-byte words; consecutive threads -> consecutive words of one pixel
-  for (int i = threadIdx.x; i < PH * PW * row_words; i += 256) {
-    const int wd = i % row_words, pix = i / row_words;
-    const int py = pix / PW, px = pix % PW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pix = warp; pix < PH * PW; pix += 8) {
+    const int py = pix / PW, px = pix - py * PW;
     const int gy = ty0 + crop + py, gx = tx0 + crop + px;
-    uint32_t v = 0;
-    if (gy < Hz && gx < Wz)
-      v = reinterpret_cast<const uint32_t*>(z + (((size_t)n * Hz + gy) * Wz + gx) * zc)[wd];
-    tg_sm[pix * pitch + wd] = v;
+    const bool ok = gy < Hz && gx < Wz;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(z + (((size_t)n * Hz + (ok ? gy : 0)) * Wz + (ok ? gx : 0)) * ZC);
+#pragma unroll
+    for (int wd = lane; wd < ZW; wd += 32) tg_sm[pix * PITCH + wd] = ok ? src[wd] : 0u;
   }
   __syncthreads();
   const int lx = threadIdx.x % TG_W, ly = threadIdx.x / TG_W;
   const int ox = tx0 + lx, oy = ty0 + ly;
   if (ox >= Wo || oy >= Ho) return;
   float s = 0.f;
+#pragma unroll
   for (int kh = 0; kh < KH; ++kh)
+#pragma unroll
     for (int kw = 0; kw < KW; ++kw) {
+      constexpr int dummy = 0; (void)dummy;
       const int t = kh * KW + kw;
       const int pix = (ly + kh) * PW + lx + kw;
       if constexpr (sizeof(T) == 2) {
-        const float2 v = unpack2<T>(tg_sm[pix * pitch + (t >> 1)]);
+        const float2 v = unpack2<T>(tg_sm[pix * PITCH + (t >> 1)]);
         s += (t & 1) ? v.y : v.x;
       } else {
-        s += __uint_as_float(tg_sm[pix * pitch + t]);
+        s += __uint_as_float(tg_sm[pix * PITCH + t]);
       }
     }
   out[((size_t)n * Ho + oy) * Wo + ox] = apply_act(s + (bias ? bias[0] : 0.f), act, 0.f);
@@ -714,24 +716,23 @@ extern "C" int ng_tap_gather(const void* z, int32_t dtype, int32_t B, int32_t Hz
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(z && out && KH * KW <= zc, NG_E_ARG, "tap_gather: need KH*KW <= zc");
   NG_REQUIRE(Hz - KH + 1 - 2 * crop > 0 && Wz - KW + 1 - 2 * crop > 0, NG_E_SHAPE, "tap_gather: empty output");
-  NG_REQUIRE(zc % 2 == 0, NG_E_SHAPE, "tap_gather: zc must be even");
+  NG_REQUIRE(KH == 7 && KW == 7 && zc == 64, NG_E_UNSUPPORTED, "tap_gather: built for 7x7 taps over 64 stored channels");
   const int Ho = Hz - KH + 1 - 2 * crop, Wo = Wz - KW + 1 - 2 * crop;
   const int tiles_x = (Wo + TG_W - 1) / TG_W, tiles_y = (Ho + TG_H - 1) / TG_H;
   const int row_words = dtype == NG_F32 ? zc : zc / 2;
   const size_t smem = (size_t)(TG_H + KH - 1) * (TG_W + KW - 1) * (row_words + 1) * 4;
-  NG_REQUIRE(smem <= 160 * 1024, NG_E_SHAPE, "tap_gather: tile does not fit in shared memory");
   {
     cudaError_t e1 = cudaSuccess;
     switch (dtype) {
-      case NG_F32: e1 = cudaFuncSetAttribute(tap_gather_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
-      case NG_F16: e1 = cudaFuncSetAttribute(tap_gather_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
-      case NG_BF16: e1 = cudaFuncSetAttribute(tap_gather_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case NG_F32: e1 = cudaFuncSetAttribute(tap_gather_kernel<float, 7, 7, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case NG_F16: e1 = cudaFuncSetAttribute(tap_gather_kernel<__half, 7, 7, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
+      case NG_BF16: e1 = cudaFuncSetAttribute(tap_gather_kernel<__nv_bfloat16, 7, 7, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); break;
     }
     int e = check_cuda(e1, "tap_gather smem attribute");
     if (e) return e;
   }
-  DISPATCH_DTYPE(dtype, (tap_gather_kernel<T><<<(unsigned)((long long)B * tiles_x * tiles_y), 256, smem, (cudaStream_t)stream>>>(
-                            (const T*)z, B, Hz, Wz, zc, KH, KW, bias, act, crop, out, tiles_x, tiles_y)));
+  DISPATCH_DTYPE(dtype, (tap_gather_kernel<T, 7, 7, 64><<<(unsigned)((long long)B * tiles_x * tiles_y), 256, smem, (cudaStream_t)stream>>>(
+                            (const T*)z, B, Hz, Wz, bias, act, crop, out, tiles_x, tiles_y)));
   NG_LAUNCH_CHECK("tap_gather_kernel");
   return NG_OK;
 }

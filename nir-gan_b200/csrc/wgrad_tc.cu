@@ -1,0 +1,344 @@
+// tcgen05 / TMEM / TMA weight-gradient kernel for sm_100a.
+//
+//   dW[tap][n][k] = sum over (image, virtual pixel) of dY[img, OS*v + phase][n] * X[img, S*v + tap offset][k]
+//
+// GEMM view per tap: M = 128 output channels (n), N = BN input channels (k), reduction K = pixels.  Both operands are
+// stored pixel-major with channels contiguous (NHWC), i.e. *MN-major* for the tensor core: a pipeline stage holds 64
+// pixels as [64 rows][64 channels = 128 B] slabs (TMA 128-byte swizzle) -- 2 slabs of dY and BN/64 slabs of X fetched by
+// 4-D TMA boxes at the tap's offset (element stride S / OS for strided and transposed convolutions, out-of-bounds =
+// zero fill = zero padding).  One elected thread issues tcgen05.mma (M=128, N=BN, K=16 pixels, both operands MN-major)
+// into a double-buffered fp32 TMEM accumulator.
+//
+// The pixel range is split across CTAs ("split-K"): work unit = (split, tap, 128-channel n tile); every unit writes its
+// fp32 128 x BN partial to the caller's workspace [split][tap][Cout][Cin] and a second kernel sums the splits in a fixed
+// order, so the result is deterministic (no atomics).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue.
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace ng {
+
+constexpr int WG_PIXELS = 64;                       // pixels (GEMM-K) per pipeline stage
+constexpr int WG_SLAB = WG_PIXELS * 128;            // one 64-channel slab: 8 KB
+
+struct WgParams {
+  ConvGeom g;
+  int BH, BW;                 // virtual-pixel patch, BH*BW == 64
+  int patches_y, patches_x;
+  int P;                      // B * patches_y * patches_x
+  int n_tiles;                // ceil(Cout / 128)
+  int splits, pps;            // pixel-range splits, patches per split
+  int total_units;            // splits * ntaps * n_tiles
+  int bf16;
+  float* partials;            // [splits][ntaps][Cout][Cin]
+};
+
+template <int BN>
+struct WgCfg {
+  static constexpr int A_BYTES = 2 * WG_SLAB;
+  static constexpr int B_BYTES = (BN / 64) * WG_SLAB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN < 64 ? 64 : 2 * BN;      // 128 / 256 / 512
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
+                const __grid_constant__ WgParams p) {
+  using Cfg = WgCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int per_split = g.ntaps * p.n_tiles;
+  auto decode = [&](int u, int& split, int& tap, int& nt, int& pt0, int& pt1) {
+    split = u / per_split;
+    const int r = u - split * per_split;
+    tap = r / p.n_tiles;
+    nt = r - tap * p.n_tiles;
+    pt0 = split * p.pps;
+    pt1 = min(p.P, pt0 + p.pps);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        int split, tap, nt, pt0, pt1;
+        decode(u, split, tap, nt, pt0, pt1);
+        int ph = 0;
+        while (tap >= g.phase_tap0[ph + 1]) ++ph;
+        const int dy = g.taps[tap].dy, dx = g.taps[tap].dx;
+        const int oy0 = g.phase_oy[ph], ox0 = g.phase_ox[ph];
+        const int per_img = p.patches_y * p.patches_x;
+        for (int pt = pt0; pt < pt1; ++pt) {
+          const int n = pt / per_img;
+          const int r = pt - n * per_img;
+          const int py = r / p.patches_x, px = r - py * p.patches_x;
+          const int vi0 = py * p.BH, vj0 = px * p.BW;
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d(&tmY, fb, sa + j * WG_SLAB, nt * 128 + 64 * j, g.OS * vj0 + ox0, g.OS * vi0 + oy0, n);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + j * WG_SLAB, 64 * j, g.S * vj0 + dx, g.S * vi0 + dy, n);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // c = f32, a/b format, both operands MN-major (bits 15, 16), N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bf16 ? 1 : 0) << 7) | ((uint32_t)(p.bf16 ? 1 : 0) << 10) |
+                             (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
+      for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        int split, tap, nt, pt0, pt1;
+        decode(u, split, tap, nt, pt0, pt1);
+        const int kiters = pt1 - pt0;
+        mbar_wait(smem_u32(&tempty_bar[as]), as_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + as * BN;
+        for (int kit = 0; kit < kiters; ++kit) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = make_mnmajor_desc(sa, WG_SLAB, 1024);
+          const uint64_t bdesc = make_mnmajor_desc(sa + Cfg::A_BYTES, WG_SLAB, 1024);
+#pragma unroll
+          for (int k = 0; k < WG_PIXELS / 16; ++k)     // 16 pixel rows = 2048 bytes per K step
+            umma_f16(tmem_c, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
+                     (uint32_t)((kit | k) != 0));
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tfull_bar[as]));
+        if (++as == 2) { as = 0; as_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue (warps 2..5): TMEM -> fp32 partial =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t as = 0, as_phase = 0;
+    for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+      int split, tap, nt, pt0, pt1;
+      decode(u, split, tap, nt, pt0, pt1);
+      const int n = nt * 128 + row;
+      mbar_wait(smem_u32(&tfull_bar[as]), as_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      // packed weight-gradient row of this tap: wrow = (kh*KW + kw) * Cout (phased geometries enumerate taps by phase)
+      float* dst = p.partials + ((size_t)split * g.ntaps * g.Cout + g.taps[tap].wrow + (n < g.Cout ? n : 0)) * (size_t)g.Cin;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (n < g.Cout) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(dst + c * 32 + 4 * k) =
+                make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                            __uint_as_float(r[4 * k + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tempty_bar[as]));
+      if (++as == 2) { as = 0; as_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// dw[i] = sum_s partials[s][i]  (fixed order -> deterministic)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, float4* __restrict__ dw) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = part[i];
+    for (int k = 1; k < splits; ++k) {
+      const float4 v = part[(size_t)k * n4 + i];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    dw[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct WgPlan {
+  int BH, BW, patches_y, patches_x, P, n_tiles, splits, pps, bn;
+};
+
+static bool wgrad_tc_supported(const ng_conv_args& a) {
+  if (a.dtype != NG_F16 && a.dtype != NG_BF16) return false;
+  if (a.Cin != 64 && a.Cin != 128 && a.Cin != 256) return false;
+  if (a.Cout % 64 != 0) return false;
+  return true;
+}
+
+static void wgrad_plan(const ng_conv_args& a, const ConvGeom& g, WgPlan& w) {
+  // patch of exactly 64 virtual pixels (the TMA box may overhang the image: zero fill)
+  long long best = -1;
+  w.BH = 8; w.BW = 8;
+  for (int bw = 64; bw >= 1; bw >>= 1) {
+    const int bh = 64 / bw;
+    if (bw * g.S > 256 || bh * g.S > 256 || bw * g.OS > 256 || bh * g.OS > 256) continue;
+    const long long tiles = (long long)((g.VH + bh - 1) / bh) * ((g.VW + bw - 1) / bw);
+    if (best < 0 || tiles < best) { best = tiles; w.BH = bh; w.BW = bw; }
+  }
+  w.patches_y = (g.VH + w.BH - 1) / w.BH;
+  w.patches_x = (g.VW + w.BW - 1) / w.BW;
+  w.P = g.B * w.patches_y * w.patches_x;
+  w.n_tiles = (g.Cout + 127) / 128;
+  w.bn = g.Cin;
+  const int base = g.ntaps * w.n_tiles, sms = num_sms();
+  int best_s = 1; double best_eff = -1.0;
+  const int max_s = w.P < 64 ? w.P : 64;
+  for (int s = 1; s <= max_s; ++s) {
+    const long long units = (long long)base * s;
+    const long long waves = (units + sms - 1) / sms;
+    const double eff = (double)units / (double)(waves * sms);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
+    if (eff >= 0.9) { best_s = s; break; }
+  }
+  w.pps = (w.P + best_s - 1) / best_s;
+  w.splits = (w.P + w.pps - 1) / w.pps;
+}
+
+long long wgrad_tc_workspace_bytes(const ng_conv_args& a, const ConvGeom& g) {
+  if (!wgrad_tc_supported(a)) return 0;
+  WgPlan w;
+  wgrad_plan(a, g, w);
+  return (long long)w.splits * g.ntaps * g.Cout * g.Cin * (long long)sizeof(float);
+}
+
+template <int BN>
+static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPlan& w, float* dw, void* workspace,
+                           cudaStream_t st) {
+  using Cfg = WgCfg<BN>;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  int r = get_tensor_map_encoder(&encode);
+  if (r) return r;
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.BH = w.BH; p.BW = w.BW; p.patches_y = w.patches_y; p.patches_x = w.patches_x; p.P = w.P;
+  p.n_tiles = w.n_tiles; p.splits = w.splits; p.pps = w.pps;
+  p.total_units = w.splits * g.ntaps * w.n_tiles;
+  p.bf16 = a.dtype == NG_BF16;
+  p.partials = w.splits == 1 ? dw : reinterpret_cast<float*>(workspace);
+
+  CUtensorMap tmY, tmX;
+  const CUtensorMapDataType dt = a.dtype == NG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cout, (cuuint64_t)g.Wout, (cuuint64_t)g.Hout, (cuuint64_t)g.B};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cout * 2, (cuuint64_t)g.Wout * g.Cout * 2,
+                             (cuuint64_t)g.Hout * g.Wout * g.Cout * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(w.BW * g.OS), (cuuint32_t)(w.BH * g.OS), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)g.OS, (cuuint32_t)g.OS, 1};
+    CUresult cr = encode(&tmY, dt, 4, const_cast<void*>(a.y), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "wgrad_tc: cuTensorMapEncodeTiled(dY) failed: %d", (int)cr);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wb, (cuuint64_t)g.Hb, (cuuint64_t)g.B};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Wb * g.Cin * 2, (cuuint64_t)g.Hb * g.Wb * g.Cin * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(w.BW * g.S), (cuuint32_t)(w.BH * g.S), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
+    CUresult cr = encode(&tmX, dt, 4, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "wgrad_tc: cuTensorMapEncodeTiled(X) failed: %d", (int)cr);
+  }
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    int e = check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg::SMEM_BYTES), "cudaFuncSetAttribute(wgrad_tc)");
+    if (e) return e;
+    attr_set = true;
+  }
+  const int sms = num_sms();
+  const int grid = p.total_units < sms ? p.total_units : sms;
+  wgrad_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmY, tmX, p);
+  NG_LAUNCH_CHECK("wgrad_tc_kernel");
+  if (w.splits > 1) {
+    const long long n4 = (long long)g.ntaps * g.Cout * g.Cin / 4;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(workspace), w.splits, n4,
+                                                         reinterpret_cast<float4*>(dw));
+    NG_LAUNCH_CHECK("wgrad_reduce_kernel");
+  }
+  return NG_OK;
+}
+
+// returns NG_E_UNSUPPORTED (without setting an error) when the geometry is not covered: the caller falls back to SIMT
+int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspace, long long workspace_bytes,
+             cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (!wgrad_tc_supported(a) || g.ntaps != a.KH * a.KW) return NG_OK;
+  WgPlan w;
+  wgrad_plan(a, g, w);
+  const long long need = w.splits > 1 ? (long long)w.splits * g.ntaps * g.Cout * g.Cin * (long long)sizeof(float) : 0;
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need)) return NG_OK;     // no workspace: SIMT path
+  NG_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.y & 15) == 0 && ((uintptr_t)dw & 15) == 0 &&
+                 ((uintptr_t)workspace & 15) == 0,
+             NG_E_ALIGN, "wgrad_tc: tensors must be 16-byte aligned");
+  *handled = true;
+  switch (g.Cin) {
+    case 64:  return launch_wgrad_tc<64>(a, g, w, dw, workspace, st);
+    case 128: return launch_wgrad_tc<128>(a, g, w, dw, workspace, st);
+    case 256: return launch_wgrad_tc<256>(a, g, w, dw, workspace, st);
+  }
+  *handled = false;
+  return NG_OK;
+}
+
+}  // namespace ng

@@ -163,6 +163,17 @@ class UnitGraph:
         g_skip = [None] * n         # gradient w.r.t. each unit's output interior from a residual consumer
         dw, db = {}, {}
         dY = None
+        # one split-K workspace shared by every tcgen05 weight-gradient launch of this plan (they run back to back on
+        # one stream), sized for the largest unit
+        ws_bytes = 0
+        if need_dw:
+            for u in units:
+                q = self._args(u, u.x, u.x.t, u.x.t)
+                need = L.load().ng_conv2d_wgrad_workspace_bytes(C.byref(q))
+                if need < 0:
+                    L.check(int(need), "ng_conv2d_wgrad_workspace_bytes")
+                ws_bytes = max(ws_bytes, int(need))
+        ws = eng.buffers.get(tag + ".wgrad_ws", max(ws_bytes // 4, 4), torch.float32)
         for i in range(n - 1, -1, -1):
             u = units[i]
             pre = f"{tag}.{u.name}"
@@ -202,7 +213,8 @@ class UnitGraph:
                 dbb = eng.buffers.get(pre + ".db", u.cout, torch.float32) if has_bias_grad else None
                 a = self._args(u, u.x, dwp, dY.t)         # a.w is unused by wgrad; a.y = dY
                 plan.keepalive.append(a)
-                plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), _ptr(dbb), launches=2, label=pre + ".wgrad")
+                plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), _ptr(dbb), ws.data_ptr(), ws.numel() * 4, launches=2,
+                         label=pre + ".wgrad")
                 dw[i], db[i] = dwp, dbb
             # ---- data gradient ----
             if i == 0 and not need_dx:

@@ -200,7 +200,7 @@ def test_wgrad_matches_autograd(kind):
     a.x, a.w, a.y = xb.t.data_ptr(), xb.t.data_ptr(), dyb.t.data_ptr()
     dwp = torch.empty(K * K * co_pad * Cin, device="cuda")
     db = torch.empty(co_pad, device="cuda")
-    L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), db.data_ptr(), Hh.stream())
+    L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), db.data_ptr(), None, 0, Hh.stream())
     dw = torch.empty_like(w)
     n_axis = 1 if form == L.FORM_PHASED else 0
     L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, co_pad, Cin, 1.0,
@@ -208,3 +208,69 @@ def test_wgrad_matches_autograd(kind):
     rel = float((dw - w.grad).norm() / w.grad.norm())
     assert rel <= 2e-5, rel
     assert float((db[:Cout] - dy.sum(dim=(0, 2, 3))).abs().max()) <= 1e-3
+
+
+# tcgen05 split-K weight gradient (MN-major operands) against torch autograd on the same 16-bit-rounded operands.
+# Geometries: ResnetBlock 3x3 (reflect halo), strided down conv, ConvTranspose (phased), PatchGAN k4 s2 and k4 s1
+# (Cout 512 -> four n tiles), Cout 64 (upper half of the 128-row tile is out-of-bounds zero fill), an image smaller
+# than one 64-pixel patch, and a batch large enough for several pixel splits.
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("kind", ["res", "res69", "down", "down128", "convT", "convT256", "dk4s2", "dk4s1", "tiny"])
+def test_wgrad_tc_matches_autograd(kind, dt):
+    import ctypes as C
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    dtype = L.F16 if dt == "f16" else L.BF16
+    tdt = torch.float16 if dt == "f16" else torch.bfloat16
+    B = 2
+    cfgs = {
+        "res": (256, 256, 3, 1, 1, 16, "reflect", L.FORM_GATHER),
+        "res69": (256, 256, 3, 1, 1, 69, "reflect", L.FORM_GATHER),
+        "down": (64, 128, 3, 2, 1, 36, "zero", L.FORM_GATHER),
+        "down128": (128, 256, 3, 2, 1, 34, "zero", L.FORM_GATHER),
+        "convT": (128, 64, 3, 2, 1, 17, "zero", L.FORM_PHASED),
+        "convT256": (256, 128, 3, 2, 1, 9, "zero", L.FORM_PHASED),
+        "dk4s2": (64, 128, 4, 2, 1, 32, "zero", L.FORM_GATHER),
+        "dk4s1": (256, 512, 4, 1, 1, 8, "zero", L.FORM_GATHER),
+        "tiny": (64, 64, 3, 1, 1, 5, "reflect", L.FORM_GATHER),
+    }
+    Cin, Cout, K, s, p, H, mode, form = cfgs[kind]
+    if kind == "res69":
+        B = 3
+    x = _gen(B, Cin, H, H, seed=11).to(tdt).float()
+    if form == L.FORM_PHASED:
+        w = _gen(Cin, Cout, K, K, seed=12, scale=0.05).requires_grad_(True)
+        out = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=1)
+        Ho = 2 * H
+    else:
+        w = _gen(Cout, Cin, K, K, seed=12, scale=0.05).requires_grad_(True)
+        xr = F.pad(x, (p,) * 4, mode="reflect") if mode == "reflect" else F.pad(x, (p,) * 4)
+        out = F.conv2d(xr, w, stride=s)
+        Ho = out.shape[-1]
+    dy = _gen(*out.shape, seed=13).to(tdt).float()
+    out.backward(dy)
+    xb = Hh.to_actbuf(x, p if mode == "reflect" else 0, mode, dtype)
+    dyb = Hh.to_actbuf(dy, 0, "zero", dtype)
+    a = L.ConvArgs()
+    a.dtype, a.impl, a.form, a.sgn = dtype, L.IMPL_TC, form, 1
+    a.B, a.Hin, a.Win, a.Cin, a.in_pad, a.in_pad_w = B, H, H, Cin, xb.pad, xb.pad
+    a.Cout, a.KH, a.KW, a.stride, a.pad, a.pad_w, a.Hout, a.Wout = Cout, K, K, s, p, p, Ho, Ho
+    a.x, a.w, a.y = xb.t.data_ptr(), xb.t.data_ptr(), dyb.t.data_ptr()
+    need = L.load().ng_conv2d_wgrad_workspace_bytes(C.byref(a))
+    assert need > 0
+    ws = torch.full((need // 4,), float("nan"), device="cuda")
+    dwp = torch.full((K * K * Cout * Cin,), float("nan"), device="cuda")
+    db = torch.empty(Cout, device="cuda")
+    L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), db.data_ptr(), ws.data_ptr(), need, Hh.stream())
+    dw = torch.empty_like(w)
+    n_axis = 1 if form == L.FORM_PHASED else 0
+    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, Cout, Cin, 1.0,
+           dw.data_ptr(), Hh.stream())
+    assert bool(torch.isfinite(dw).all())
+    rel = float((dw - w.grad).norm() / w.grad.norm())
+    assert rel <= 1e-5, rel          # identical 16-bit operands, fp32 accumulation on both sides
+    assert float((db - dy.sum(dim=(0, 2, 3))).abs().max()) <= 1e-3
+    # deterministic: a second run gives bit-identical output
+    dwp2 = torch.empty_like(dwp)
+    L.call("ng_conv2d_wgrad", C.byref(a), dwp2.data_ptr(), None, ws.data_ptr(), need, Hh.stream())
+    assert torch.equal(dwp, dwp2)
