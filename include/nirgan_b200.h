@@ -115,9 +115,11 @@ int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void*
  * k is zero-padded to k_pad, n to n_pad. */
 int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
                    int32_t n_pad, int32_t k_pad, int32_t dtype, void* dst, void* stream);
-/* inverse for gradients: dst[d0][d1][KH][KW] = scale * packed[tap][n_pad][k_pad]  (fp32; scale undoes loss scaling) */
+/* inverse for gradients: dst[d0][d1][KH][KW] = scale * dev_scale[0] * packed[tap][n_pad][k_pad]  (fp32; undoes the
+ * loss scaling: `scale` is the host-known static part, dev_scale (device pointer, may be NULL) the adaptive part
+ * written by ng_grad_scale_pow2) */
 int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
-                          int32_t n_pad, int32_t k_pad, float scale, float* dst, void* stream);
+                          int32_t n_pad, int32_t k_pad, float scale, const float* dev_scale, float* dst, void* stream);
 
 /* Generator stem input in "row-merged" form: NCHW fp32 -> [B][H+2*wrap+2*halo][W+2*wrap][64] `dtype`, where element
  * (kw*8 + c) of output pixel (y, x) is channel c of the reflect-padded image at (y, x + kw)  (kw < KW <= 8, c < cin <= 8,
@@ -131,7 +133,7 @@ int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH,
                              void* stream);
 /* inverse for gradients: fp32 [kh][O][64] -> fp32 [O][I][KH][KW], times scale */
 int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW, float scale,
-                                    float* dst, void* stream);
+                                    const float* dev_scale, float* dst, void* stream);
 
 /* Single-output-channel KHxKW convolution as "tap GEMM + gather": z = [B][Hz][Wz][zc] holds, per input pixel, the
  * dot product of its channels with each of the KH*KW taps (a 1x1 ng_conv2d with Cout = zc >= KH*KW);
@@ -139,6 +141,14 @@ int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, i
  * cropped output.  Replaces Conv2d(64->1, k7) + Tanh (model/networks.py:366-368) without the 49x im2col re-read. */
 int ng_tap_gather(const void* z, int32_t dtype, int32_t B, int32_t Hz, int32_t Wz, int32_t zc, int32_t KH, int32_t KW,
                   const float* bias, int32_t act, int32_t crop, float* out, void* stream);
+
+/* Backward of ng_tap_gather: dz[n][yy][xx][kh*KW+kw] = scale * dev_scale[0] * dout[n][yy-kh-crop][xx-kw-crop] * act'(out)
+ * (zero outside the cropped output window; taps >= KH*KW zero).  With dz, the weight gradient of the single-channel
+ * convolution is a 1x1 ng_conv2d_wgrad (dW[tap][k] = sum_px dz[px][tap] x[px][k]) and its data gradient a 1x1
+ * ng_conv2d over dz -- both on the tensor cores.  Autograd of Conv2d(64->1, k7) + Tanh (model/networks.py:366-368). */
+int ng_tap_scatter(const float* dout, const float* out, int32_t B, int32_t Hz, int32_t Wz, int32_t zc, int32_t KH,
+                   int32_t KW, int32_t act, int32_t crop, float scale, const float* dev_scale, int32_t dtype, void* dz,
+                   void* stream);
 
 /* NCHW fp32 (one or two sources concatenated on C) -> haloed NHWC `dtype` with channels zero-padded to c_pad.
  * wrap_pad: reflect padding applied first (Px2Px_PL.forward, padding_amount); halo: second reflect (or zero) halo. */
@@ -171,17 +181,23 @@ int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* 
               int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd, int32_t act, float slope,
               const float* inject_e, int32_t inject_mode, const float* inject_scale, float* sums_scratch, void* dy,
               void* do_out, float* dscale, float* de_map, void* stream);
-/* dst[B][H][W][c_pad] (dtype): channel 0 = scale * dout * act'(out) inside the crop window, zero elsewhere.
- * dout/out: fp32 [B][H-2*crop][W-2*crop] (the fp32 single-channel head output and its gradient). */
+/* Adaptive power-of-two gradient scale for the 16-bit backward pass: out4[0] = f = 2^floor(log2(target / max|g|))
+ * (1 if g is all zero or not finite), out4[1] = 1/f, out4[2..3] scratch.  The backward plan is linear in the incoming
+ * gradient, so entering with g*f and leaving with (1/f) is exact; it keeps the largest gradient element at `target`
+ * whatever the loss weights, batch size or singular pixels of the spectral-index losses. No host synchronisation. */
+int ng_grad_scale_pow2(const float* g, int64_t n, float target, float* out4, void* stream);
+/* dst[B][H][W][c_pad] (dtype): channel 0 = scale * dev_scale[0] * dout * act'(out) inside the crop window, zero
+ * elsewhere.  dout/out: fp32 [B][H-2*crop][W-2*crop] (the fp32 single-channel head output and its gradient).
+ * dev_scale: device pointer or NULL. */
 int ng_head_bwd_prep(const float* dout, const float* out, int32_t B, int32_t H, int32_t W, int32_t crop, int32_t act,
-                     float scale, int32_t c_pad, int32_t dtype, void* dst, void* stream);
-/* gradient export: NHWC [B][H][W][c_pad] (dtype) -> NCHW fp32 [B][c][H][W], times scale */
+                     float scale, const float* dev_scale, int32_t c_pad, int32_t dtype, void* dst, void* stream);
+/* gradient export: NHWC [B][H][W][c_pad] (dtype) -> NCHW fp32 [B][c][H][W], times scale * dev_scale[0] */
 int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c,
-                    float scale, float* dst, void* stream);
+                    float scale, const float* dev_scale, float* dst, void* stream);
 /* SatCLIP injection backward: adjoint of the bilinear resize (128x128 -> HxW) then of fc:
  * dfc_w[16384][256] = (scale * A^T de_map)^T embeds, dfc_b[16384].  de128_scratch: [B][16384] floats. */
-int ng_inject_bwd(const float* de_map, int32_t B, int32_t H, int32_t W, float scale, const float* embeds,
-                  float* de128_scratch, float* dfc_w, float* dfc_b, void* stream);
+int ng_inject_bwd(const float* de_map, int32_t B, int32_t H, int32_t W, float scale, const float* dev_scale,
+                  const float* embeds, float* de128_scratch, float* dfc_w, float* dfc_b, void* stream);
 
 /* y[b][n] = sum_k x[b][k] * w[n][k] + bias[n]   (fp32) */
 int ng_linear(const float* x, const float* w, const float* bias, int32_t B, int32_t K, int32_t N, float* y,

@@ -41,11 +41,13 @@ _SIGNATURES = {
     "ng_conv2d_wgrad_workspace_bytes": (c_i64, [C.POINTER(ConvArgs)]),
     "ng_conv2d_wgrad": (c_i32, [C.POINTER(ConvArgs), c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ng_pack_weight": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    "ng_unpack_weight_grad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
+    "ng_unpack_weight_grad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
     "ng_prep_stem": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_pack_weight_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    "ng_unpack_weight_grad_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
+    "ng_unpack_weight_grad_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
     "ng_tap_gather": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "ng_tap_scatter": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp,
+                               c_vp]),
     "ng_prep_input": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                               c_vp, c_vp]),
     "ng_in_stats": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
@@ -54,9 +56,10 @@ _SIGNATURES = {
                             c_vp, c_vp, c_i32, c_i32, c_vp]),
     "ng_in_bwd": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp,
                           c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "ng_head_bwd_prep": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_i32, c_vp, c_vp]),
-    "ng_grad_to_nchw": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp]),
-    "ng_inject_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ng_grad_scale_pow2": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_vp]),
+    "ng_head_bwd_prep": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "ng_grad_to_nchw": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ng_inject_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ng_linear": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_lsgan_loss": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_i32, c_vp, c_f32, c_vp]),
     "ng_g_pixel_losses": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),

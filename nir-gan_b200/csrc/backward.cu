@@ -229,8 +229,9 @@ in_bwd_apply_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 head_bwd_prep_kernel(const float* __restrict__ dout, const float* __restrict__ out, int B, int H, int W, int crop,
-                     int act, float scale, int cpad, T* __restrict__ dst) {
+                     int act, float scale, const float* __restrict__ dev_scale, int cpad, T* __restrict__ dst) {
   const long long total = (long long)B * H * W;
+  if (dev_scale) scale *= dev_scale[0];
   const int Hc = H - 2 * crop, Wc = W - 2 * crop;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -251,11 +252,52 @@ head_bwd_prep_kernel(const float* __restrict__ dout, const float* __restrict__ o
   }
 }
 
+// Backward of ng_tap_gather: dz[n][yy][xx][t] = scale * dout[n][yy-kh-crop][xx-kw-crop] * act'(out) for t = kh*KW + kw
+// (zero outside the cropped output window and for t >= KH*KW).  One thread = one pixel x 8 taps (16 B on the 16-bit
+// paths; the 8 threads of a pixel write 128 contiguous bytes).
+template <typename T, int KH, int KW, int ZC>
+__global__ void __launch_bounds__(256)
+tap_scatter_kernel(const float* __restrict__ dout, const float* __restrict__ out, int B, int Hz, int Wz, int act, int crop,
+                   float scale, const float* __restrict__ dev_scale, T* __restrict__ dz) {
+  constexpr int G8 = ZC / 8;
+  const int Hc = Hz - KH + 1 - 2 * crop, Wc = Wz - KW + 1 - 2 * crop;
+  if (dev_scale) scale *= dev_scale[0];
+  const long long total = (long long)B * Hz * Wz * G8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g8 = (int)(i % G8);
+    long long p = i / G8;
+    const int xx = (int)(p % Wz); p /= Wz;
+    const int yy = (int)(p % Hz);
+    const int n = (int)(p / Hz);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = g8 * 8 + k;
+      float v = 0.f;
+      if (t < KH * KW) {
+        const int kh = t / KW, kw = t - kh * KW;
+        const int yc = yy - kh - crop, xc = xx - kw - crop;
+        if (yc >= 0 && yc < Hc && xc >= 0 && xc < Wc) {
+          const size_t o = ((size_t)n * Hc + yc) * Wc + xc;
+          v = dout[o] * scale;
+          if (act == NG_ACT_TANH) { const float tv = out[o]; v *= (1.f - tv * tv); }
+          if constexpr (sizeof(T) == 2) v = fminf(fmaxf(v, -3.0e4f), 3.0e4f);
+        }
+      }
+      f[k] = v;
+    }
+    st8<T>(dz + i * 8, f);
+  }
+}
+
 // NHWC (cpad channels, T, scaled) -> NCHW fp32 (c channels), dst = src * scale
 template <typename T>
 __global__ void __launch_bounds__(256)
-grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, int c, float scale, float* __restrict__ dst) {
+grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, int c, float scale,
+                    const float* __restrict__ dev_scale, float* __restrict__ dst) {
   const long long total = (long long)B * c * H * W;
+  if (dev_scale) scale *= dev_scale[0];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % W), y = (int)((i / W) % H);
@@ -266,8 +308,10 @@ grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, in
 
 // adjoint of F.interpolate(bilinear, align_corners=False) 128x128 -> HxW:  de128 += A^T de_map
 __global__ void __launch_bounds__(256)
-bilerp128_bwd_kernel(const float* __restrict__ de_map, int B, int H, int W, float scale, float* __restrict__ de128) {
+bilerp128_bwd_kernel(const float* __restrict__ de_map, int B, int H, int W, float scale,
+                     const float* __restrict__ dev_scale, float* __restrict__ de128) {
   const long long total = (long long)B * H * W;
+  if (dev_scale) scale *= dev_scale[0];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(i % W), oy = (int)((i / W) % H), n = (int)(i / ((long long)W * H));
@@ -299,6 +343,30 @@ linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int
     for (int b = 0; b < B; ++b) s += dy[(size_t)b * N + n];
     db[n] = s;
   }
+}
+
+// ---- adaptive power-of-two gradient scale ---------------------------------------------------------------
+// out[2] (as uint) <- max |g| bit pattern (non-negative floats order like unsigned integers; inf / NaN sort last)
+__global__ void __launch_bounds__(256)
+grad_amax_kernel(const float* __restrict__ g, long long n, unsigned* __restrict__ amax_bits) {
+  unsigned m = 0u;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(g[i]) & 0x7fffffffu);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(amax_bits, m);
+}
+// out[0] = f = 2^floor(log2(target / amax)) (1 when amax is 0 or not finite), out[1] = 1/f
+__global__ void grad_scale_finalize_kernel(float target, float* __restrict__ out) {
+  const unsigned bits = reinterpret_cast<const unsigned*>(out)[2];
+  float f = 1.f;
+  if (bits != 0u && bits < 0x7f800000u) {
+    int e = (int)floorf(log2f(target / __uint_as_float(bits)));
+    e = max(-60, min(60, e));
+    f = exp2f((float)e);
+  }
+  out[0] = f;
+  out[1] = 1.f / f;
 }
 
 static inline unsigned grid_cap(long long items) {
@@ -362,34 +430,61 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
   return NG_OK;
 }
 
+extern "C" int ng_grad_scale_pow2(const float* g, int64_t n, float target, float* out4, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(g && out4 && n > 0 && target > 0.f, NG_E_ARG, "grad_scale_pow2: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  int e = check_cuda(cudaMemsetAsync(out4 + 2, 0, sizeof(float), st), "grad_scale_pow2 memset");
+  if (e) return e;
+  grad_amax_kernel<<<grid_cap((long long)n), 256, 0, st>>>(g, (long long)n, reinterpret_cast<unsigned*>(out4) + 2);
+  NG_LAUNCH_CHECK("grad_amax_kernel");
+  grad_scale_finalize_kernel<<<1, 1, 0, st>>>(target, out4);
+  NG_LAUNCH_CHECK("grad_scale_finalize_kernel");
+  return NG_OK;
+}
+
 extern "C" int ng_head_bwd_prep(const float* dout, const float* out, int32_t B, int32_t H, int32_t W, int32_t crop,
-                                int32_t act, float scale, int32_t c_pad, int32_t dtype, void* dst, void* stream) {
+                                int32_t act, float scale, const float* dev_scale, int32_t c_pad, int32_t dtype,
+                                void* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(dout && dst && (act != NG_ACT_TANH || out), NG_E_ARG, "head_bwd_prep: null tensor");
   DISPATCH_T(dtype, (head_bwd_prep_kernel<T><<<grid_cap((long long)B * H * W), 256, 0, (cudaStream_t)stream>>>(
-                        dout, out, B, H, W, crop, act, scale, c_pad, (T*)dst)));
+                        dout, out, B, H, W, crop, act, scale, dev_scale, c_pad, (T*)dst)));
   NG_LAUNCH_CHECK("head_bwd_prep_kernel");
   return NG_OK;
 }
 
+extern "C" int ng_tap_scatter(const float* dout, const float* out, int32_t B, int32_t Hz, int32_t Wz, int32_t zc,
+                              int32_t KH, int32_t KW, int32_t act, int32_t crop, float scale, const float* dev_scale,
+                              int32_t dtype, void* dz, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(dout && dz && (act != NG_ACT_TANH || out), NG_E_ARG, "tap_scatter: null tensor");
+  NG_REQUIRE(KH == 7 && KW == 7 && zc == 64, NG_E_UNSUPPORTED, "tap_scatter: built for 7x7 taps over 64 stored channels");
+  NG_REQUIRE(Hz - KH + 1 - 2 * crop > 0 && Wz - KW + 1 - 2 * crop > 0, NG_E_SHAPE, "tap_scatter: empty output");
+  DISPATCH_T(dtype, (tap_scatter_kernel<T, 7, 7, 64><<<grid_cap((long long)B * Hz * Wz * 8), 256, 0, (cudaStream_t)stream>>>(
+                        dout, out, B, Hz, Wz, act, crop, scale, dev_scale, (T*)dz)));
+  NG_LAUNCH_CHECK("tap_scatter_kernel");
+  return NG_OK;
+}
+
 extern "C" int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c,
-                               float scale, float* dst, void* stream) {
+                               float scale, const float* dev_scale, float* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(src && dst && c <= c_pad, NG_E_ARG, "grad_to_nchw: bad arguments");
   DISPATCH_T(dtype, (grad_to_nchw_kernel<T><<<grid_cap((long long)B * c * H * W), 256, 0, (cudaStream_t)stream>>>(
-                        (const T*)src, B, H, W, c_pad, c, scale, dst)));
+                        (const T*)src, B, H, W, c_pad, c, scale, dev_scale, dst)));
   NG_LAUNCH_CHECK("grad_to_nchw_kernel");
   return NG_OK;
 }
 
-extern "C" int ng_inject_bwd(const float* de_map, int32_t B, int32_t H, int32_t W, float scale, const float* embeds,
-                             float* de128_scratch, float* dfc_w, float* dfc_b, void* stream) {
+extern "C" int ng_inject_bwd(const float* de_map, int32_t B, int32_t H, int32_t W, float scale, const float* dev_scale,
+                             const float* embeds, float* de128_scratch, float* dfc_w, float* dfc_b, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(de_map && embeds && de128_scratch && dfc_w, NG_E_ARG, "inject_bwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   int e = check_cuda(cudaMemsetAsync(de128_scratch, 0, (size_t)B * 128 * 128 * sizeof(float), st), "inject_bwd memset");
   if (e) return e;
-  bilerp128_bwd_kernel<<<grid_cap((long long)B * H * W), 256, 0, st>>>(de_map, B, H, W, scale, de128_scratch);
+  bilerp128_bwd_kernel<<<grid_cap((long long)B * H * W), 256, 0, st>>>(de_map, B, H, W, scale, dev_scale, de128_scratch);
   NG_LAUNCH_CHECK("bilerp128_bwd_kernel");
   linear_bwd_kernel<<<128 * 128, 256, 0, st>>>(de128_scratch, embeds, B, 256, 128 * 128, dfc_w, dfc_b);
   NG_LAUNCH_CHECK("linear_bwd_kernel");

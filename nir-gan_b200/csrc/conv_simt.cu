@@ -188,6 +188,45 @@ wgrad_simt_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, c
   }
 }
 
+// Weight gradient of a single-real-output-channel convolution (PatchGAN last layer, stored Cout = 16 with channel 0
+// real): dw[tap][0][k] = sum_px dy[px][0] * x[px + tap][k].  grid = (taps, pixel splits); a thread owns channels
+// k = threadIdx.x + 256*j; the x reads of a warp are contiguous.  Memory-bound (x is re-read per tap from L2).
+template <typename T, int KPT>
+__global__ void __launch_bounds__(256)
+wgrad_cout1_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, const T* __restrict__ dy,
+                   float* __restrict__ dw, int pix_per_split) {
+  const int tp = blockIdx.x, sp = blockIdx.y;
+  int phase = 0;
+  while (tp >= g.phase_tap0[phase + 1]) ++phase;
+  const long long npix = (long long)g.B * g.VH * g.VW;
+  const long long p0 = (long long)sp * pix_per_split, p1 = min(npix, p0 + pix_per_split);
+  float acc[KPT];
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) acc[j] = 0.f;
+  int vj = (int)(p0 % g.VW);
+  long long r = p0 / g.VW;
+  int vi = (int)(r % g.VH), n = (int)(r / g.VH);
+  for (long long p = p0; p < p1; ++p) {
+    const int oy = g.OS * vi + g.phase_oy[phase], ox = g.OS * vj + g.phase_ox[phase];
+    const int by = g.S * vi + g.taps[tp].dy, bx = g.S * vj + g.taps[tp].dx;
+    if (oy < g.Hout && ox < g.Wout && by >= 0 && by < g.Hb && bx >= 0 && bx < g.Wb) {
+      const float d = to_f32<T>(dy[(((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout]);
+      const T* xp = x + (((size_t)n * g.Hb + by) * g.Wb + bx) * g.Cin;
+#pragma unroll
+      for (int j = 0; j < KPT; ++j) {
+        const int k = threadIdx.x + 256 * j;
+        if (k < g.Cin) acc[j] = fmaf(d, to_f32<T>(xp[k]), acc[j]);
+      }
+    }
+    if (++vj == g.VW) { vj = 0; if (++vi == g.VH) { vi = 0; ++n; } }
+  }
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    const int k = threadIdx.x + 256 * j;
+    if (k < g.Cin) atomicAdd(&dw[(size_t)g.taps[tp].wrow * g.Cin + k], acc[j]);
+  }
+}
+
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ dy, long long rows, int C, float* __restrict__ out) {
   // grid.x blocks stride over rows; thread handles channel threadIdx.x (C <= 1024 handled by loop)
@@ -210,6 +249,17 @@ static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, cud
   const size_t wbytes = (size_t)a.KH * a.KW * g.Cout * g.Cin * sizeof(float);
   int e = check_cuda(cudaMemsetAsync(dw, 0, wbytes, st), "wgrad memset");
   if (e) return e;
+  if (g.Cout <= 16 && g.Cin <= 1024 && a.epilogue == NG_EPI_HEAD) {
+    // single real output channel (the caller's dY holds zeros in the padding channels)
+    long long want = npix / 512; if (want < 1) want = 1; if (want > 64) want = 64;
+    const int pps1 = (int)((npix + want - 1) / want);
+    dim3 grid(g.ntaps, (unsigned)((npix + pps1 - 1) / pps1));
+    if (g.Cin <= 256) wgrad_cout1_kernel<T, 1><<<grid, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, pps1);
+    else if (g.Cin <= 512) wgrad_cout1_kernel<T, 2><<<grid, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, pps1);
+    else wgrad_cout1_kernel<T, 4><<<grid, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, pps1);
+    NG_LAUNCH_CHECK("wgrad_cout1_kernel");
+    return NG_OK;
+  }
   const long long blocks = (long long)g.ntaps * n_tiles * k_tiles * splits;
   wgrad_simt_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, n_tiles, k_tiles,
                                                         splits, (int)pps);

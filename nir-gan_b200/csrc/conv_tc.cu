@@ -207,12 +207,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(smem_u32(&tempty_bar[as]));
-        if (valid) {
+        if (valid && p.epilogue == NG_EPI_HEAD) {
           const int hy = oy - p.crop, hx = ox - p.crop, HH = g.Hout - 2 * p.crop, WW = g.Wout - 2 * p.crop;
           if (hy >= 0 && hx >= 0 && hy < HH && hx < WW) {
             const float v = apply_act(__uint_as_float(r[0]) + (p.bias ? p.bias[0] : 0.f), p.act, p.slope);
             reinterpret_cast<float*>(p.y)[((size_t)n * HH + hy) * WW + hx] = v;
           }
+        } else if (valid) {
+          // thin (16 stored channels) NHWC output: data gradient of the PatchGAN input layer
+          uint32_t w[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float a = __uint_as_float(r[2 * k]), b = __uint_as_float(r[2 * k + 1]);
+            if (p.epilogue == NG_EPI_BIAS_ACT) {
+              a = apply_act(a + (p.bias ? p.bias[2 * k] : 0.f), p.act, p.slope);
+              b = apply_act(b + (p.bias ? p.bias[2 * k + 1] : 0.f), p.act, p.slope);
+            }
+            w[k] = p.bf16 ? pack2<__nv_bfloat16>(a, b) : pack2<__half>(a, b);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.y) +
+                                                ((((size_t)n * g.Hout + oy) * g.Wout + ox) * 16) * 2);
+          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
       } else {
         rowoff[row] = valid ? ((((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout + n0) : -1ll;
@@ -438,7 +454,7 @@ static int cluster_size_for(int bn, int kc) {
 }
 
 static int tc_block_n(const ng_conv_args& a) {
-  if (a.epilogue == NG_EPI_HEAD) return 16;
+  if (a.epilogue == NG_EPI_HEAD || a.Cout == 16) return 16;
   if (a.Cout % 256 == 0) return 256;
   if (a.Cout % 128 == 0) return 128;
   if (a.Cout % 64 == 0) return 64;
@@ -459,6 +475,7 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   const int kc = a.Cin % 64 == 0 ? 64 : (a.Cin == 16 ? 16 : 0);
   NG_REQUIRE(bn != 0 && kc != 0, NG_E_UNSUPPORTED, "conv_tc: Cin %d / Cout %d not tileable", a.Cin, a.Cout);
   NG_REQUIRE(a.epilogue != NG_EPI_HEAD || a.Cout == 16, NG_E_SHAPE, "conv_tc: head epilogue expects Cout stored as 16");
+  NG_REQUIRE(bn != 16 || a.stat_partials == nullptr, NG_E_UNSUPPORTED, "conv_tc: no InstanceNorm statistics for 16-channel outputs");
   if (bn == 16 && kc == 64) return launch_tc<16, 64, 1>(a, g, st);
   if (bn == 64 && kc == 16) return launch_tc<64, 16, 1>(a, g, st);
   if (bn == 128 && kc == 16) return launch_tc<128, 16, 1>(a, g, st);

@@ -26,8 +26,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int d0, int d1
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int d0, int d1, int taps, int n_axis,
-                                    int n_pad, int k_pad, float scale, float* __restrict__ dst) {
+                                    int n_pad, int k_pad, float scale, const float* __restrict__ dev_scale,
+                                    float* __restrict__ dst) {
   const long long total = (long long)d0 * d1 * taps;
+  if (dev_scale) scale *= dev_scale[0];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int tp = (int)(i % taps);
@@ -169,15 +171,38 @@ __device__ __forceinline__ float bilerp128(const float* __restrict__ e, int oy, 
   return (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
 }
 
+// Streaming loads / stores: every activation byte is touched exactly once by this kernel, so keep it out of L1.
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y), c = unpack2<T>(u.z), d = unpack2<T>(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// Row-organised apply.  A block owns `rows_per_block` whole output rows (n, yo) (halo rows included); thread t keeps the
+// channel group c8 = t mod C/8 for its whole life (C/8 is a power of two <= 256), so the 8 (mean, rstd) pairs live in
+// registers and the inner loop is: UNROLL independent 16-byte loads (+ residual loads) -> math -> 16-byte stores.
+template <typename T, int UNROLL, bool HAS_RES, bool HAS_INJ>
+__global__ void __launch_bounds__(256, 3)
 in_apply_kernel(const T* __restrict__ y, int B, int H, int W, int C, int c8_shift, const float* __restrict__ mr, int act,
                 float slope, const T* __restrict__ res, int res_pad, const float* __restrict__ inj, int inj_mode,
                 const float* __restrict__ inj_scale, T* __restrict__ out, int op, int halo_mode, int rows_per_block) {
-  // blocks own whole output rows (n, yo): no per-element division by H/W, loads of one row are independent
   const int Ho = H + 2 * op, Wo = W + 2 * op, C8 = C >> 3;
-  const float s = (inj_mode != NG_INJECT_NONE && inj_scale) ? *inj_scale : 1.f;
-  const int row_elems = Wo * C8;
+  const float s = (HAS_INJ && inj_scale) ? *inj_scale : 1.f;
+  const int c8 = threadIdx.x & (C8 - 1);
+  const int xstep = 256 >> c8_shift;                 // output columns covered by the block per iteration
+  const int x_first = threadIdx.x >> c8_shift;
+  const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
+  int n_cached = -1;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mean[k] = 0.f; rstd[k] = 1.f; }
   for (int r = 0; r < rows_per_block; ++r) {
     const long long grow = (long long)blockIdx.x * rows_per_block + r;
     if (grow >= (long long)B * Ho) return;
@@ -185,54 +210,96 @@ in_apply_kernel(const T* __restrict__ y, int B, int H, int W, int C, int c8_shif
     int ys = yo - op;
     const bool row_zero = halo_mode != NG_HALO_REFLECT && (ys < 0 || ys >= H);
     if (halo_mode == NG_HALO_REFLECT) ys = reflect_idx(ys, H);
-    T* orow = out + ((size_t)n * Ho + yo) * Wo * C;
-    const T* yrow = y + ((size_t)n * H + (row_zero ? 0 : ys)) * W * C;
-    const float* mrn = mr ? mr + (size_t)n * C * 2 : nullptr;
-    const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
-    const T* rrow = res ? res + (((size_t)n * Hr + ys + res_pad) * Wr + res_pad) * C : nullptr;
-    const float* injn = inj ? inj + (size_t)n * 128 * 128 : nullptr;
-#pragma unroll 4
-    for (int e = threadIdx.x; e < row_elems; e += 256) {
-      const int xo = e >> c8_shift, c8 = e & (C8 - 1);
-      int xs = xo - op;
-      float f[8];
-      bool zero = row_zero;
-      if (halo_mode == NG_HALO_REFLECT) xs = reflect_idx(xs, W);
-      else zero = zero || xs < 0 || xs >= W;
-      if (zero) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = 0.f;
-        store8<T>(orow + (size_t)e * 8, f);
-        continue;
+    T* orow = out + (((size_t)n * Ho + yo) * Wo) * C + c8 * 8;
+    if (row_zero) {
+      for (int xo = x_first; xo < Wo; xo += xstep) {
+        if constexpr (sizeof(T) == 2) *reinterpret_cast<uint4*>(orow + (size_t)xo * C) = make_uint4(0u, 0u, 0u, 0u);
+        else { float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; store8<T>(orow + (size_t)xo * C, z); }
       }
-      load8<T>(yrow + ((size_t)xs * C8 + c8) * 8, f);
-      if (mrn) {
-        const float4* m4 = reinterpret_cast<const float4*>(mrn + c8 * 16);
+      continue;
+    }
+    if (mr && n != n_cached) {
+      const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float4 m = m4[k];
-          f[2 * k] = (f[2 * k] - m.x) * m.y;
-          f[2 * k + 1] = (f[2 * k + 1] - m.z) * m.w;
+      for (int k = 0; k < 4; ++k) {
+        const float4 m = m4[k];
+        mean[2 * k] = m.x; rstd[2 * k] = m.y; mean[2 * k + 1] = m.z; rstd[2 * k + 1] = m.w;
+      }
+      n_cached = n;
+    }
+    const T* yrow = y + (((size_t)n * H + ys) * W) * C + c8 * 8;
+    const T* rrow = HAS_RES ? res + ((((size_t)n * Hr + ys + res_pad) * Wr + res_pad)) * C + c8 * 8 : nullptr;
+    const float* injn = HAS_INJ ? inj + (size_t)n * 128 * 128 : nullptr;
+    for (int x0 = x_first; x0 < Wo; x0 += xstep * UNROLL) {
+      // phase 1: issue every load of this batch (UNROLL pixels x 16 B, plus the residual) before any use
+      uint4 raw[UNROLL], rres[HAS_RES ? UNROLL : 1];
+      float4 rawf[sizeof(T) == 4 ? UNROLL : 1][2], rresf[(sizeof(T) == 4 && HAS_RES) ? UNROLL : 1][2];
+      int xsrc[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int xo = x0 + u * xstep;
+        int x = xo - op;
+        bool ok = xo < Wo;
+        if (halo_mode == NG_HALO_REFLECT) x = reflect_idx(x, W);
+        else ok = ok && x >= 0 && x < W;
+        xsrc[u] = ok ? x : -1;
+        if (ok) {
+          if constexpr (sizeof(T) == 2) {
+            raw[u] = ldg_stream16(yrow + (size_t)x * C);
+            if constexpr (HAS_RES) rres[u] = ldg_stream16(rrow + (size_t)x * C);
+          } else {
+            rawf[u][0] = *reinterpret_cast<const float4*>(yrow + (size_t)x * C);
+            rawf[u][1] = *reinterpret_cast<const float4*>(yrow + (size_t)x * C + 4);
+            if constexpr (HAS_RES) {
+              rresf[u][0] = *reinterpret_cast<const float4*>(rrow + (size_t)x * C);
+              rresf[u][1] = *reinterpret_cast<const float4*>(rrow + (size_t)x * C + 4);
+            }
+          }
         }
       }
-      if (inj_mode != NG_INJECT_NONE) {
-        const float ev = bilerp128(injn, ys, xs, H, W);
+      // phase 2: one pixel at a time (keeps the live register set small: occupancy is what hides HBM latency)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (inj_mode == NG_INJECT_ADD) f[k] = f[k] + s * ev;
-          else if (inj_mode == NG_INJECT_MUL_SCALED) f[k] = f[k] * (1.f + s * ev);
-          else f[k] = f[k] * ev;
+      for (int u = 0; u < UNROLL; ++u) {
+        const int xo = x0 + u * xstep;
+        if (xo >= Wo) continue;
+        float f[8];
+        if (xsrc[u] < 0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = 0.f;
+        } else {
+          if constexpr (sizeof(T) == 2) unpack8<T>(raw[u], f);
+          else {
+            f[0] = rawf[u][0].x; f[1] = rawf[u][0].y; f[2] = rawf[u][0].z; f[3] = rawf[u][0].w;
+            f[4] = rawf[u][1].x; f[5] = rawf[u][1].y; f[6] = rawf[u][1].z; f[7] = rawf[u][1].w;
+          }
+          if (mr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean[k]) * rstd[k];
+          }
+          if constexpr (HAS_INJ) {
+            const float ev = bilerp128(injn, ys, xsrc[u], H, W);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (inj_mode == NG_INJECT_ADD) f[k] = f[k] + s * ev;
+              else if (inj_mode == NG_INJECT_MUL_SCALED) f[k] = f[k] * (1.f + s * ev);
+              else f[k] = f[k] * ev;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = apply_act(f[k], act, slope);
+          if constexpr (HAS_RES) {
+            float rv[8];
+            if constexpr (sizeof(T) == 2) unpack8<T>(rres[u], rv);
+            else {
+              rv[0] = rresf[u][0].x; rv[1] = rresf[u][0].y; rv[2] = rresf[u][0].z; rv[3] = rresf[u][0].w;
+              rv[4] = rresf[u][1].x; rv[5] = rresf[u][1].y; rv[6] = rresf[u][1].z; rv[7] = rresf[u][1].w;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += rv[k];
+          }
         }
+        store8<T>(orow + (size_t)xo * C, f);
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = apply_act(f[k], act, slope);
-      if (rrow) {
-        float rv[8];
-        load8<T>(rrow + ((size_t)xs * C8 + c8) * 8, rv);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] += rv[k];
-      }
-      store8<T>(orow + (size_t)e * 8, f);
     }
   }
 }
@@ -452,8 +519,9 @@ __global__ void pack_rowmerged_kernel(const float* __restrict__ src, int O, int 
 }
 
 __global__ void unpack_rowmerged_kernel(const float* __restrict__ packed, int O, int I, int KH, int KW, float scale,
-                                        float* __restrict__ dst) {
+                                        const float* __restrict__ dev_scale, float* __restrict__ dst) {
   const int total = O * I * KH * KW;
+  if (dev_scale) scale *= dev_scale[0];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int kw = i % KW, kh = (i / KW) % KH, c = (i / (KW * KH)) % I, o = i / (KW * KH * I);
     dst[i] = scale * packed[((long long)kh * O + o) * 64 + kw * 8 + c];
@@ -546,13 +614,13 @@ extern "C" int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t 
 }
 
 extern "C" int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW,
-                                     int32_t n_axis, int32_t n_pad, int32_t k_pad, float scale, float* dst,
-                                     void* stream) {
+                                     int32_t n_axis, int32_t n_pad, int32_t k_pad, float scale,
+                                     const float* dev_scale, float* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(packed && dst && (n_axis == 0 || n_axis == 1), NG_E_ARG, "unpack_weight_grad: bad arguments");
   const long long total = (long long)d0 * d1 * KH * KW;
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, d0, d1, KH * KW, n_axis, n_pad,
-                                                                             k_pad, scale, dst);
+                                                                             k_pad, scale, dev_scale, dst);
   NG_LAUNCH_CHECK("unpack_wgrad_kernel");
   return NG_OK;
 }
@@ -617,9 +685,16 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   int rpb = 1;                                   // give every block >= ~2048 16-byte items
   while ((long long)rpb * row_elems < 2048 && rpb < 16) rpb *= 2;
   const long long blocks = (rows + rpb - 1) / rpb;
-  DISPATCH_DTYPE(dtype, (in_apply_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-                            (const T*)y, B, H, W, C, c8_shift, mean_rstd, act, slope, (const T*)residual, res_pad,
-                            inject_e, inject_mode, inject_scale, (T*)out, out_pad, halo_mode, rpb)));
+#define NG_APPLY_LAUNCH(RES, INJ)                                                                                  \
+  DISPATCH_DTYPE(dtype, (in_apply_kernel<T, 4, RES, INJ><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(      \
+                            (const T*)y, B, H, W, C, c8_shift, mean_rstd, act, slope, (const T*)residual, res_pad, \
+                            inject_e, inject_mode, inject_scale, (T*)out, out_pad, halo_mode, rpb)))
+  const bool has_inj = inject_mode != NG_INJECT_NONE;
+  if (residual && has_inj) { NG_APPLY_LAUNCH(true, true); }
+  else if (residual) { NG_APPLY_LAUNCH(true, false); }
+  else if (has_inj) { NG_APPLY_LAUNCH(false, true); }
+  else { NG_APPLY_LAUNCH(false, false); }
+#undef NG_APPLY_LAUNCH
   NG_LAUNCH_CHECK("in_apply_kernel");
   return NG_OK;
 }
@@ -702,11 +777,11 @@ extern "C" int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, 
 }
 
 extern "C" int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW,
-                                               float scale, float* dst, void* stream) {
+                                               float scale, const float* dev_scale, float* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(packed && dst && I > 0 && I <= 8 && KW > 0 && KW <= 8, NG_E_ARG, "unpack_weight_grad_rowmerged: bad arguments");
   unpack_rowmerged_kernel<<<grid_for((long long)O * I * KH * KW, 256), 256, 0, (cudaStream_t)stream>>>(packed, O, I, KH,
-                                                                                                      KW, scale, dst);
+                                                                                                      KW, scale, dev_scale, dst);
   NG_LAUNCH_CHECK("unpack_rowmerged_kernel");
   return NG_OK;
 }

@@ -150,6 +150,17 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, uint32_t l
   return d;
 }
 
+// MN-major, 32-byte swizzle: [k rows][16 elements = 32 B], a single MN block; SBO = byte stride between 8-row K groups
+__device__ __forceinline__ uint64_t make_mnmajor_desc_sw32(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                       // SWIZZLE_32B
+  return d;
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
 int get_tensor_map_encoder(PFN_cuTensorMapEncodeTiled_v12000* fn);
 

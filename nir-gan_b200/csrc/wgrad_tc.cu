@@ -37,11 +37,14 @@ struct WgParams {
 template <int BN>
 struct WgCfg {
   static constexpr int A_BYTES = 2 * WG_SLAB;
-  static constexpr int B_BYTES = (BN / 64) * WG_SLAB;
+  // X operand: BN/64 slabs of [64 px][128 B] (128-byte swizzle), or for BN == 16 one slab of [64 px][32 B] (32-byte swizzle)
+  static constexpr int B_BYTES = BN >= 64 ? (BN / 64) * WG_SLAB : WG_PIXELS * 32;
+  static constexpr int B_LOADS = BN >= 64 ? BN / 64 : 1;
+  static constexpr int B_KSTEP = BN >= 64 ? 2048 : 512;            // bytes per 16 pixel rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = 2 * BN < 64 ? 64 : 2 * BN;      // 128 / 256 / 512
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // 32 / 128 / 256 / 512
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
@@ -115,7 +118,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           for (int j = 0; j < 2; ++j)
             tma_load_4d(&tmY, fb, sa + j * WG_SLAB, nt * 128 + 64 * j, g.OS * vj0 + ox0, g.OS * vi0 + oy0, n);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
+          for (int j = 0; j < Cfg::B_LOADS; ++j)
             tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + j * WG_SLAB, 64 * j, g.S * vj0 + dx, g.S * vi0 + dy, n);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -141,10 +144,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = make_mnmajor_desc(sa, WG_SLAB, 1024);
-          const uint64_t bdesc = make_mnmajor_desc(sa + Cfg::A_BYTES, WG_SLAB, 1024);
+          const uint64_t bdesc = BN >= 64 ? make_mnmajor_desc(sa + Cfg::A_BYTES, WG_SLAB, 1024)
+                                          : make_mnmajor_desc_sw32(sa + Cfg::A_BYTES, 256);
 #pragma unroll
-          for (int k = 0; k < WG_PIXELS / 16; ++k)     // 16 pixel rows = 2048 bytes per K step
-            umma_f16(tmem_c, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (2048 >> 4)), idesc,
+          for (int k = 0; k < WG_PIXELS / 16; ++k)     // 16 pixel rows per K step
+            umma_f16(tmem_c, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (Cfg::B_KSTEP >> 4)), idesc,
                      (uint32_t)((kit | k) != 0));
           umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -168,15 +172,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
       // packed weight-gradient row of this tap: wrow = (kh*KW + kw) * Cout (phased geometries enumerate taps by phase)
       float* dst = p.partials + ((size_t)split * g.ntaps * g.Cout + g.taps[tap].wrow + (n < g.Cout ? n : 0)) * (size_t)g.Cin;
+      if constexpr (BN >= 32) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (n < g.Cout) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(dst + c * 32 + 4 * k) =
+                  make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                              __uint_as_float(r[4 * k + 3]));
+          }
+        }
+      } else {
+        uint32_t r[16];
+        tmem_ld16(taddr, r);
         tmem_ld_wait();
         if (n < g.Cout) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(dst + c * 32 + 4 * k) =
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(dst + 4 * k) =
                 make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
                             __uint_as_float(r[4 * k + 3]));
         }
@@ -217,7 +234,7 @@ struct WgPlan {
 
 static bool wgrad_tc_supported(const ng_conv_args& a) {
   if (a.dtype != NG_F16 && a.dtype != NG_BF16) return false;
-  if (a.Cin != 64 && a.Cin != 128 && a.Cin != 256) return false;
+  if (a.Cin != 16 && a.Cin != 64 && a.Cin != 128 && a.Cin != 256) return false;
   if (a.Cout % 64 != 0) return false;
   return true;
 }
@@ -290,10 +307,10 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wb, (cuuint64_t)g.Hb, (cuuint64_t)g.B};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Wb * g.Cin * 2, (cuuint64_t)g.Hb * g.Wb * g.Cin * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(w.BW * g.S), (cuuint32_t)(w.BH * g.S), 1};
+    cuuint32_t box[4] = {(cuuint32_t)(BN >= 64 ? 64 : BN), (cuuint32_t)(w.BW * g.S), (cuuint32_t)(w.BH * g.S), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
     CUresult cr = encode(&tmX, dt, 4, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         BN >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "wgrad_tc: cuTensorMapEncodeTiled(X) failed: %d", (int)cr);
   }
@@ -333,6 +350,7 @@ int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspac
              NG_E_ALIGN, "wgrad_tc: tensors must be 16-byte aligned");
   *handled = true;
   switch (g.Cin) {
+    case 16:  return launch_wgrad_tc<16>(a, g, w, dw, workspace, st);
     case 64:  return launch_wgrad_tc<64>(a, g, w, dw, workspace, st);
     case 128: return launch_wgrad_tc<128>(a, g, w, dw, workspace, st);
     case 256: return launch_wgrad_tc<256>(a, g, w, dw, workspace, st);

@@ -107,6 +107,10 @@ class ActBuf:
         return v.permute(0, 3, 1, 2).float()
 
 
+# when a list, Plan.run records (label, start_event, end_event) per op into it (tools/bench_train.py --profile)
+PROFILE = [None]
+
+
 class Plan:
     """A compiled list of bound C-ABI calls."""
 
@@ -124,10 +128,28 @@ class Plan:
         self.launches += launches
 
     def run(self, stream_ptr: int):
+        if PROFILE[0] is not None:
+            return self._run_profiled(stream_ptr)
         for fn, args, name in self.ops:
             st = fn(*args, stream_ptr)
             if st != 0:
                 L.check(st, name)
+
+
+def _run_profiled(self, stream_ptr: int):
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    for (fn, args, name), label in zip(self.ops, self.labels):
+        st = fn(*args, stream_ptr)
+        if st != 0:
+            L.check(st, name)
+        ev2 = torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        PROFILE[0].append((label, name, ev, ev2))
+        ev = ev2
+
+
+Plan._run_profiled = _run_profiled
 
 
 class Engine:
@@ -146,7 +168,8 @@ class Engine:
     def packed_weight(self, w: torch.Tensor, n_axis: int, n_pad: int, k_pad: int, stream: int) -> torch.Tensor:
         """fp32 master (4-D) -> packed shadow, refreshed when the master changes.
         n_axis 0/1: [tap][n_pad][k_pad];  n_axis 'rowmerged': [kh][O][kw*8+c] (stem);
-        n_axis 'taps': [n = tap (padded to n_pad)][k_pad] for the tap-GEMM form of a 1-output-channel conv."""
+        n_axis 'taps': [n = tap (padded to n_pad)][k_pad] for the tap-GEMM form of a 1-output-channel conv,
+        'taps_T': its transpose [n = channel][k = tap] for the data gradient."""
         key = (w.data_ptr(), n_axis, n_pad, k_pad, self.dt_enum)
         ver = (w._version, WEIGHT_EPOCH[0])
         hit = self._packed.get(key)
@@ -163,6 +186,12 @@ class Engine:
             assert d0 == 1 and kh * kw <= n_pad
             dst = hit[1] if hit is not None else torch.zeros(n_pad * k_pad, dtype=self.dt_torch, device=self.device)
             L.call("ng_pack_weight", src.data_ptr(), d0, d1, kh, kw, 0, 1, k_pad, self.dt_enum, dst.data_ptr(), stream)
+        elif n_axis == "taps_T":
+            # [n = input channel (n_pad)][k = tap (k_pad)]: (1, C, kh, kw) is already a [C][kh*kw] matrix
+            assert d0 == 1 and kh * kw <= k_pad and d1 <= n_pad
+            dst = hit[1] if hit is not None else torch.empty(n_pad * k_pad, dtype=self.dt_torch, device=self.device)
+            L.call("ng_pack_weight", src.data_ptr(), d1, kh * kw, 1, 1, 0, n_pad, k_pad, self.dt_enum, dst.data_ptr(),
+                   stream)
         else:
             dst = hit[1] if hit is not None else torch.empty(kh * kw * n_pad * k_pad, dtype=self.dt_torch,
                                                              device=self.device)

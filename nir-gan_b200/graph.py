@@ -61,6 +61,9 @@ class UnitGraph:
         self.units: List[Unit] = []
         self.pre_ops = []                   # (fn_name, args, label) executed before the units (input prep, fc)
         self.records: dict = {}
+        # single-output-channel 7x7 head as "tap GEMM + gather" (see ng_tap_gather / ng_tap_scatter):
+        # {'conv': module, 'x': ActBuf (haloed head input), 'crop': int, 'B','H','W': output geometry}
+        self.tap_head: Optional[dict] = None
 
     # ---- construction -----------------------------------------------------------------------------
     def weight(self, u: Unit) -> torch.Tensor:
@@ -134,11 +137,37 @@ class UnitGraph:
                      u.slope, _ptr(res.t) if res else None, res.pad if res else 0, _ptr(inj.get("e")),
                      inj.get("mode", L.INJECT_NONE), _ptr(inj.get("scale")), u.out.t.data_ptr(), u.out_pad, u.halo_mode,
                      label=pre + ".apply")
+        if self.tap_head is not None:
+            # z[pixel][tap] = <x[pixel,:], w[tap,:]> over the haloed buffer (each input pixel read once, no 49x im2col
+            # re-read), then out = tanh(b + sum_t z[(y+kh, x+kw), t])
+            th = self.tap_head
+            x, head = th["x"], th["conv"]
+            K = head.weight.shape[-1]
+            Hz, Wz = x.H + 2 * x.pad, x.W + 2 * x.pad
+            xz = ActBuf(x.t, x.B, Hz, Wz, x.C, 0)
+            z = eng.act(self.tag + ".z", x.B, Hz, Wz, 64, 0)
+            out = eng.buffers.get(self.tag + ".head.out", x.B * th["H"] * th["W"], torch.float32)
+            wt = eng.packed_weight(head.weight, "taps", 64, x.C, self.stream)
+            a = eng.conv_args(xz, wt, z.t, 64, 1, 1, 0, Hz, Wz)
+            plan.keepalive.append(a)
+            plan.add("ng_conv2d", C.byref(a), label=self.tag + ".head.gemm")
+            plan.add("ng_tap_gather", z.t.data_ptr(), eng.dt_enum, x.B, Hz, Wz, 64, K, K, head.bias.data_ptr(),
+                     L.ACT_TANH, th["crop"], out.data_ptr(), label=self.tag + ".head.gather")
+            th["out"] = out
+            plan.records["out"] = out
         return plan
 
-    def refresh_weights(self):
-        for u in self.units:
+    def refresh_weights(self, backward: bool = False, need_dx: bool = False):
+        """Re-pack the low-precision weight shadows whose fp32 masters changed (no-op otherwise)."""
+        for i, u in enumerate(self.units):
             self.weight(u)
+            if backward and (i > 0 or need_dx):
+                self._dgrad_weight(u)
+        if self.tap_head is not None:
+            th = self.tap_head
+            self.eng.packed_weight(th["conv"].weight, "taps", 64, th["x"].C, self.stream)
+            if backward:
+                self.eng.packed_weight(th["conv"].weight, "taps_T", th["x"].C, 64, self.stream)
 
     # ---- backward -------------------------------------------------------------------------------------
     def _dgrad_weight(self, u: Unit) -> torch.Tensor:
@@ -151,12 +180,21 @@ class UnitGraph:
 
     def compile_backward(self, dout_f32: torch.Tensor, loss_scale: float, need_dw: bool, need_dx: bool,
                          want_inject_grads: bool = False) -> Plan:
-        """dout_f32: gradient of the fp32 single-channel output of the last (head) unit.  Returns a plan whose
+        """dout_f32: gradient of the fp32 single-channel output of the last (head) unit; loss_scale: 0 = none, else
+        the target max |gradient| of the adaptive power-of-two scaling (fp16 mode).  Returns a plan whose
         records hold 'dw' {unit index: packed fp32 grad}, 'db' {unit index: bias grad}, 'dx' (ActBuf-shaped grad of the
         first unit's input buffer, when need_dx)."""
         eng, tag = self.eng, self.tag
         plan = Plan()
-        S = float(loss_scale)
+        S = 1.0
+        gsc = None
+        if loss_scale:
+            # 16-bit (fp16) gradients: adaptive power-of-two scale f (device scalar) so that max |dout * f| is
+            # `loss_scale`; gradients are exported times 1/f.  No host round trip.
+            gsc = eng.buffers.get(tag + ".gscale", 4, torch.float32)
+            plan.add("ng_grad_scale_pow2", dout_f32.data_ptr(), dout_f32.numel(), float(loss_scale), gsc.data_ptr(),
+                     launches=2, label=tag + ".gscale")
+        plan.records["gscale"] = gsc
         units = self.units
         n = len(units)
         g_halo = [None] * n         # gradient w.r.t. each unit's haloed output buffer (from the next unit's dgrad)
@@ -173,7 +211,37 @@ class UnitGraph:
                 if need < 0:
                     L.check(int(need), "ng_conv2d_wgrad_workspace_bytes")
                 ws_bytes = max(ws_bytes, int(need))
+        th = self.tap_head
+        if th is not None:
+            x = th["x"]
+            Hz, Wz = x.H + 2 * x.pad, x.W + 2 * x.pad
+            th_B = x.B
+            xz = ActBuf(x.t, th_B, Hz, Wz, x.C, 0)
+            dz = eng.act(tag + ".head.dz", th_B, Hz, Wz, 64, 0)
+            if need_dw:
+                q = eng.conv_args(xz, x.t, dz.t, 64, 1, 1, 0, Hz, Wz)
+                ws_bytes = max(ws_bytes, int(L.load().ng_conv2d_wgrad_workspace_bytes(C.byref(q))))
         ws = eng.buffers.get(tag + ".wgrad_ws", max(ws_bytes // 4, 4), torch.float32)
+        if th is not None:
+            head = th["conv"]
+            K = head.weight.shape[-1]
+            plan.add("ng_tap_scatter", dout_f32.data_ptr(), th["out"].data_ptr(), th_B, Hz, Wz, 64, K, K, L.ACT_TANH,
+                     th["crop"], S, _ptr(gsc), eng.dt_enum, dz.t.data_ptr(), label=tag + ".head.dscatter")
+            if need_dw:
+                dwp = eng.buffers.get(tag + ".head.dwp", 64 * x.C, torch.float32)          # [tap (64)][k = channel]
+                dbb = eng.buffers.get(tag + ".head.db", 64, torch.float32)
+                a = eng.conv_args(xz, dwp, dz.t, 64, 1, 1, 0, Hz, Wz)
+                plan.keepalive.append(a)
+                plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), dbb.data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                         launches=3, label=tag + ".head.wgrad")
+                plan.records["tap_head"] = {"conv": head, "dwp": dwp, "db": dbb, "center": (K // 2) * K + K // 2}
+            # data gradient: g[pixel][c] = sum_t dz[pixel][t] * w[t][c]  (1x1 conv over the 64 stored taps)
+            gbuf = eng.act(tag + ".head.dx", x.B, x.H, x.W, x.C, x.pad)
+            wT = eng.packed_weight(head.weight, "taps_T", x.C, 64, self.stream)
+            a = eng.conv_args(ActBuf(dz.t, th_B, Hz, Wz, 64, 0), wT, gbuf.t, x.C, 1, 1, 0, Hz, Wz)
+            plan.keepalive.append(a)
+            plan.add("ng_conv2d", C.byref(a), label=tag + ".head.dgrad")
+            g_halo[n - 1] = gbuf
         for i in range(n - 1, -1, -1):
             u = units[i]
             pre = f"{tag}.{u.name}"
@@ -182,7 +250,7 @@ class UnitGraph:
             if u.kind == "head":
                 dY = eng.act(pre + ".dy", B, u.Hout, u.Wout, u.cout, 0)
                 plan.add("ng_head_bwd_prep", dout_f32.data_ptr(), _ptr(u.out_f32), B, u.Hout, u.Wout, u.crop, u.act, S,
-                         u.cout, eng.dt_enum, dY.t.data_ptr(), label=pre + ".dprep")
+                         _ptr(gsc), u.cout, eng.dt_enum, dY.t.data_ptr(), label=pre + ".dprep")
             else:
                 dY = eng.act(pre + ".dy", B, u.Hout, u.Wout, u.cout, 0)
                 gh, gs = g_halo[i], g_skip[i]
@@ -211,7 +279,8 @@ class UnitGraph:
                 dwp = eng.buffers.get(pre + ".dwp", taps * u.cout * kdim, torch.float32)
                 has_bias_grad = u.kind in ("head", "biasact")
                 dbb = eng.buffers.get(pre + ".db", u.cout, torch.float32) if has_bias_grad else None
-                a = self._args(u, u.x, dwp, dY.t)         # a.w is unused by wgrad; a.y = dY
+                # a.w is unused by wgrad; a.y = dY.  EPI_HEAD marks a single real output channel (dedicated kernel)
+                a = self._args(u, u.x, dwp, dY.t, epilogue=L.EPI_HEAD if u.kind == "head" else L.EPI_RAW)
                 plan.keepalive.append(a)
                 plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), _ptr(dbb), ws.data_ptr(), ws.numel() * 4, launches=2,
                          label=pre + ".wgrad")
@@ -234,8 +303,8 @@ class UnitGraph:
                 # haloed input (in_pad == pad): gradient of the haloed buffer, pad 0;  zero-padded input: pad = pad
                 eff_pad = 0 if xin.pad == u.pad else u.pad
                 a = eng.conv_args(dyb, wd, g.t, xin.C, u.K, 1, eff_pad, Hg, Wg, sgn=-1)
-            if xin.C < 64:
-                a.impl = L.IMPL_SIMT          # thin data gradients (PatchGAN input, 16 stored channels): CUDA-core kernel
+            if xin.C < 64 and xin.C != 16:
+                a.impl = L.IMPL_SIMT          # untileable thin data gradients: CUDA-core kernel
             plan.keepalive.append(a)
             plan.add("ng_conv2d", C.byref(a), label=pre + ".dgrad")
             if i > 0:

@@ -31,8 +31,9 @@ class _RunnerBase:
         return self._engine
 
     def loss_scale(self) -> float:
-        # fp16 gradients are carried with a power-of-two loss scale (exactly undone when exporting gradients)
-        return float(os.environ.get("NIRGAN_B200_LOSS_SCALE", "4096")) if self.cfg.precision == "fp16" else 1.0
+        """Target max |dL/d(output)| of the adaptive power-of-two gradient scaling (ng_grad_scale_pow2) used when
+        gradients are stored as fp16; 0 = no scaling (bf16 / fp32 have the range)."""
+        return float(os.environ.get("NIRGAN_B200_GRAD_AMAX", "8")) if self.cfg.precision == "fp16" else 0.0
 
 
 # =================================================================================================
@@ -108,8 +109,13 @@ class GeneratorRunner(_RunnerBase):
         g.records["head_in"] = u.out
         if direct_head:
             g.add(Unit("head", head, u.out, 16, 7, 1, 3, H1, W1, kind="head", act=L.ACT_TANH, crop=wrap))
+        else:
+            g.tap_head = {"conv": head, "x": u.out, "crop": wrap, "H": H, "W": W}
         g.records["geom"] = (B, H, W, H1, W1, wrap, ngf)
         return g
+
+    def _use_tap_head(self) -> bool:
+        return self.head_mode == "tapgemm" and self._convs()[0].weight.shape[0] == 64
 
     def _inference_plan(self, eng, B, Cin, H, W, wrap, inject, stream) -> Plan:
         key = (B, Cin, H, W, wrap, inject)
@@ -117,30 +123,10 @@ class GeneratorRunner(_RunnerBase):
         if hit is not None:
             g, plan = hit
             g.refresh_weights()
-            if "head_taps" in plan.records:
-                eng.packed_weight(self._convs()[6].weight, "taps", 64, plan.records["head_taps"], stream)
             return plan
-        tapgemm = self.head_mode == "tapgemm" and self._convs()[0].weight.shape[0] == 64
-        g = self.build_graph(eng, B, H, W, wrap, inject, stream, "g", direct_head=not tapgemm)
+        g = self.build_graph(eng, B, H, W, wrap, inject, stream, "g", direct_head=not self._use_tap_head())
         plan = g.compile_forward()
-        if tapgemm:
-            # head as tap GEMM + gather: z[pixel][tap] = <x[pixel,:], w[tap,:]> over the haloed buffer (each input pixel
-            # read once, no 49x im2col re-read), then out = tanh(b + sum_t z[(y+kh, x+kw), t])
-            head = self._convs()[6]
-            _, _, _, H1, W1, _, ngf = g.records["geom"]
-            x = g.records["head_in"]
-            xz = ActBuf(x.t, B, H1 + 6, W1 + 6, ngf, 0)
-            z = eng.act("g.z", B, H1 + 6, W1 + 6, 64, 0)
-            out = eng.buffers.get("g.head.out", B * H * W, torch.float32)
-            wt = eng.packed_weight(head.weight, "taps", 64, ngf, stream)
-            a = eng.conv_args(xz, wt, z.t, 64, 1, 1, 0, H1 + 6, W1 + 6)
-            plan.keepalive.append(a)
-            plan.add("ng_conv2d", C.byref(a), label="g.head.gemm")
-            plan.add("ng_tap_gather", z.t.data_ptr(), eng.dt_enum, B, H1 + 6, W1 + 6, 64, 7, 7, head.bias.data_ptr(),
-                     L.ACT_TANH, wrap, out.data_ptr(), label="g.head.gather")
-            plan.records["out"] = out
-            plan.records["head_taps"] = ngf
-        else:
+        if g.tap_head is None:
             plan.records["out"] = g.units[-1].out_f32
         self._fwd[key] = (g, plan)
         return plan
@@ -184,15 +170,15 @@ class GeneratorRunner(_RunnerBase):
         key = (B, Cin, H, W, wrap_pad, inject)
         ctx = self._train.get(key)
         if ctx is None:
-            g = self.build_graph(eng, B, H, W, wrap_pad, inject, stream, "gt", direct_head=True)
+            g = self.build_graph(eng, B, H, W, wrap_pad, inject, stream, "gt", direct_head=not self._use_tap_head())
             fwd = g.compile_forward()
+            if g.tap_head is None:
+                fwd.records["out"] = g.units[-1].out_f32
             dout = eng.buffers.get("gt.dout", B * H * W, torch.float32)
             bwd = g.compile_backward(dout, self.loss_scale(), need_dw=True, need_dx=False, want_inject_grads=inject)
             ctx = self._train[key] = {"graph": g, "fwd": fwd, "bwd": bwd, "dout": dout, "geom": (B, Cin, H, W)}
         else:
-            ctx["graph"].refresh_weights()
-            for u in ctx["graph"].units[1:]:
-                ctx["graph"]._dgrad_weight(u)
+            ctx["graph"].refresh_weights(backward=True, need_dx=False)
         return ctx
 
 
@@ -263,8 +249,5 @@ class PatchGANRunner(_RunnerBase):
             bwd = g.compile_backward(dout, self.loss_scale(), need_dw=need_dw, need_dx=need_dx)
             ctx = self._train[key] = {"graph": g, "fwd": fwd, "bwd": bwd, "dout": dout, "geom": (B, Cin, H, W)}
         else:
-            ctx["graph"].refresh_weights()
-            for i, u in enumerate(ctx["graph"].units):
-                if i > 0 or need_dx:
-                    ctx["graph"]._dgrad_weight(u)
+            ctx["graph"].refresh_weights(backward=True, need_dx=need_dx)
         return ctx

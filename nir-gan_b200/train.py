@@ -2,9 +2,10 @@
 discriminator appear to torch autograd as single differentiable functions of (input, parameters);
 their forward and backward are the compiled C-ABI plans of ``graph.UnitGraph``.
 
-Gradient precision: in the fp16 fast mode activations' gradients are carried in fp16 with a
-power-of-two loss scale S (default 4096, NIRGAN_B200_LOSS_SCALE) that is applied when the fp32 output
-gradient enters the plan and divided out exactly when weight / input gradients are exported as fp32.
+Gradient precision: in the fp16 fast mode activations' gradients are carried in fp16 with an adaptive
+power-of-two scale f = 2^floor(log2(target / max|dout|)) (target 8, NIRGAN_B200_GRAD_AMAX) computed on
+the device by ng_grad_scale_pow2: it is applied when the fp32 output gradient enters the plan and divided
+out exactly (the plan is linear in dout) when weight / input gradients are exported as fp32.
 """
 from __future__ import annotations
 
@@ -19,28 +20,45 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def _export_weight_grads(graph, bwd_plan, S: float, params: List[torch.nn.Parameter]) -> dict:
-    """Packed fp32 weight gradients -> reference-layout fp32 tensors keyed by parameter id."""
+def _export_weight_grads(graph, bwd_plan, params: List[torch.nn.Parameter]) -> dict:
+    """Packed fp32 weight gradients -> reference-layout fp32 tensors keyed by parameter id (times the inverse of the
+    adaptive gradient scale, read on the device)."""
     st = graph.stream
     out = {}
-    inv = 1.0 / S
+    inv = 1.0
+    gs = bwd_plan.records.get("gscale")
+    dev_inv = gs.data_ptr() + 4 if gs is not None else None
     for i, dwp in bwd_plan.records["dw"].items():
         u = graph.units[i]
         w = u.conv.weight
         gw = torch.empty_like(w, dtype=torch.float32)
         d0, d1, kh, kw = w.shape
         if u.pack == "rowmerged":
-            L.call("ng_unpack_weight_grad_rowmerged", dwp.data_ptr(), d0, d1, kh, kw, inv, gw.data_ptr(), st)
+            L.call("ng_unpack_weight_grad_rowmerged", dwp.data_ptr(), d0, d1, kh, kw, inv, dev_inv, gw.data_ptr(), st)
         else:
-            L.call("ng_unpack_weight_grad", dwp.data_ptr(), d0, d1, kh, kw, u.pack, u.cout, u.x.C, inv, gw.data_ptr(), st)
+            L.call("ng_unpack_weight_grad", dwp.data_ptr(), d0, d1, kh, kw, u.pack, u.cout, u.x.C, inv, dev_inv,
+                   gw.data_ptr(), st)
         out[id(w)] = gw
         if u.conv.bias is not None:
             dbb = bwd_plan.records["db"].get(i)
             if dbb is not None:
-                out[id(u.conv.bias)] = dbb[:u.conv.bias.numel()] * inv
+                db = dbb[:u.conv.bias.numel()]
+                out[id(u.conv.bias)] = db * gs[1] if gs is not None else db.clone()
             else:
                 # bias feeding InstanceNorm: its gradient is identically zero (the reference returns rounding noise)
                 out[id(u.conv.bias)] = torch.zeros_like(u.conv.bias, dtype=torch.float32)
+    th = bwd_plan.records.get("tap_head")
+    if th is not None:
+        # head as tap GEMM: dwp is [tap (64 stored)][channel]; the reference layout (1, C, kh, kw) is [channel][tap]
+        w = th["conv"].weight
+        gw = torch.empty_like(w, dtype=torch.float32)
+        _, cin, kh, kw = w.shape
+        L.call("ng_unpack_weight_grad", th["dwp"].data_ptr(), cin, kh * kw, 1, 1, 1, 64, cin, inv, dev_inv,
+               gw.data_ptr(), st)
+        out[id(w)] = gw
+        # every tap column of dz sums to sum(dy): the centre tap's column sum is the bias gradient
+        db = th["db"][th["center"]:th["center"] + 1]
+        out[id(th["conv"].bias)] = db * gs[1] if gs is not None else db.clone()
     return out
 
 
@@ -63,7 +81,7 @@ class GeneratorFunction(torch.autograd.Function):
         ctx.c, ctx.module, ctx.runner = c, module, runner
         ctx.params = params
         ctx.has_embeds = embeds is not None
-        out = c["graph"].units[-1].out_f32.view(B, 1, H, W)
+        out = fwd.records["out"].view(B, 1, H, W)
         if getattr(module, "post_correction", False):
             raise NotImplementedError("nirgan_b200: training with post_correction is outside the hot path")
         return out.clone()
@@ -72,14 +90,15 @@ class GeneratorFunction(torch.autograd.Function):
     def backward(ctx, dout):
         c, module, runner = ctx.c, ctx.module, ctx.runner
         g, bwd = c["graph"], c["bwd"]
-        S = runner.loss_scale()
         st = _stream(dout)
         c["dout"].view_as(dout).copy_(dout.float())
         inj = bwd.records.get("inject")
         if inj is not None:
             inj["dscale"].zero_()
         bwd.run(st)
-        grads = _export_weight_grads(g, bwd, S, ctx.params)
+        grads = _export_weight_grads(g, bwd, ctx.params)
+        gs = bwd.records.get("gscale")
+        dev_inv = gs.data_ptr() + 4 if gs is not None else None
         if inj is not None:
             eng = runner._engine
             B = c["geom"][0]
@@ -87,11 +106,12 @@ class GeneratorFunction(torch.autograd.Function):
             dW = torch.empty_like(fc.weight, dtype=torch.float32)
             db = torch.empty_like(fc.bias, dtype=torch.float32)
             scratch = eng.buffers.get("gt.de128", B * 128 * 128, torch.float32)
-            L.call("ng_inject_bwd", inj["de_map"].data_ptr(), B, inj["H"], inj["W"], 1.0 / S,
+            L.call("ng_inject_bwd", inj["de_map"].data_ptr(), B, inj["H"], inj["W"], 1.0, dev_inv,
                    c["fwd"].records["emb"].data_ptr(), scratch.data_ptr(), dW.data_ptr(), db.data_ptr(), st)
             grads[id(fc.weight)], grads[id(fc.bias)] = dW, db
             if hasattr(module, "scale_param"):
-                grads[id(module.scale_param)] = (inj["dscale"] / S).reshape(module.scale_param.shape)
+                ds = inj["dscale"] * gs[1] if gs is not None else inj["dscale"].clone()
+                grads[id(module.scale_param)] = ds.reshape(module.scale_param.shape)
         out = []
         for p in ctx.params:
             gp = grads.get(id(p))
@@ -128,18 +148,20 @@ class DiscriminatorFunction(torch.autograd.Function):
     def backward(ctx, dout):
         c, runner = ctx.c, ctx.runner
         g, bwd = c["graph"], c["bwd"]
-        S = runner.loss_scale()
         st = _stream(dout)
         c["dout"].view_as(dout).copy_(dout.float())
         bwd.run(st)
         runner._live = max(0, runner._live - 1)
-        grads = _export_weight_grads(g, bwd, S, ctx.params) if ctx.need_dw else {}
+        grads = _export_weight_grads(g, bwd, ctx.params) if ctx.need_dw else {}
+        gs = bwd.records.get("gscale")
+        dev_inv = gs.data_ptr() + 4 if gs is not None else None
         dx = None
         if ctx.need_dx:
             B, Cin, H, W = c["geom"]
             gx = bwd.records["dx"]
             dx = torch.empty(B, Cin, H, W, dtype=torch.float32, device=dout.device)
-            L.call("ng_grad_to_nchw", gx.t.data_ptr(), runner._engine.dt_enum, B, H, W, gx.C, Cin, 1.0 / S, dx.data_ptr(), st)
+            L.call("ng_grad_to_nchw", gx.t.data_ptr(), runner._engine.dt_enum, B, H, W, gx.C, Cin, 1.0, dev_inv,
+                   dx.data_ptr(), st)
         out = []
         for p in ctx.params:
             gp = grads.get(id(p))

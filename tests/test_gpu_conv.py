@@ -228,7 +228,7 @@ def test_stem_rowmerged(impl, dtype, wrap, H, W):
     assert float((got - ref).abs().max()) <= _tol(dtype, ref)
     # weight-gradient unpack is the exact inverse of the row-merged pack
     back = torch.empty_like(w)
-    L.call("ng_unpack_weight_grad_rowmerged", wp.float().contiguous().data_ptr(), 64, 3, 7, 7, 1.0,
+    L.call("ng_unpack_weight_grad_rowmerged", wp.float().contiguous().data_ptr(), 64, 3, 7, 7, 1.0, None,
            back.data_ptr(), Hh.stream())
     assert torch.equal(back, w)
 

@@ -161,7 +161,7 @@ def test_adam_matches_torch():
         assert float((p - ref_p.detach()).abs().max()) <= 5e-7      # 2 ulp at |p| ~ 2
 
 
-@pytest.mark.parametrize("kind", ["res", "down", "convT", "dk4s2", "head"])
+@pytest.mark.parametrize("kind", ["res", "down", "convT", "dk4s2", "head", "dout"])
 def test_wgrad_matches_autograd(kind):
     import ctypes as C
     from nirgan_b200 import _lib as L
@@ -176,6 +176,8 @@ def test_wgrad_matches_autograd(kind):
         Cin, Cout, K, s, p, H, mode, form = 64, 128, 4, 2, 1, 16, "zero", L.FORM_GATHER
     elif kind == "head":
         Cin, Cout, K, s, p, H, mode, form = 64, 1, 7, 1, 3, 20, "reflect", L.FORM_GATHER
+    elif kind == "dout":
+        Cin, Cout, K, s, p, H, mode, form = 512, 1, 4, 1, 1, 13, "zero", L.FORM_GATHER
     else:
         Cin, Cout, K, s, p, H, mode, form = 128, 64, 3, 2, 1, 9, "zero", L.FORM_PHASED
     x = _gen(B, Cin, H, H, seed=11)
@@ -190,7 +192,7 @@ def test_wgrad_matches_autograd(kind):
         Ho = out.shape[-1]
     dy = _gen(*out.shape, seed=13)
     out.backward(dy)
-    co_pad = 16 if kind == "head" else Cout
+    co_pad = 16 if kind in ("head", "dout") else Cout
     xb = Hh.to_actbuf(x, p if mode == "reflect" else 0, mode, dtype)
     dyb = Hh.to_actbuf(dy, 0, "zero", dtype, c_pad=co_pad)
     a = L.ConvArgs()
@@ -198,12 +200,14 @@ def test_wgrad_matches_autograd(kind):
     a.B, a.Hin, a.Win, a.Cin, a.in_pad, a.in_pad_w = B, H, H, Cin, xb.pad, xb.pad
     a.Cout, a.KH, a.KW, a.stride, a.pad, a.pad_w, a.Hout, a.Wout = co_pad, K, K, s, p, p, Ho, Ho
     a.x, a.w, a.y = xb.t.data_ptr(), xb.t.data_ptr(), dyb.t.data_ptr()
+    if kind in ("head", "dout"):
+        a.epilogue = L.EPI_HEAD        # single real output channel -> dedicated kernel
     dwp = torch.empty(K * K * co_pad * Cin, device="cuda")
     db = torch.empty(co_pad, device="cuda")
     L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), db.data_ptr(), None, 0, Hh.stream())
     dw = torch.empty_like(w)
     n_axis = 1 if form == L.FORM_PHASED else 0
-    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, co_pad, Cin, 1.0,
+    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, co_pad, Cin, 1.0, None,
            dw.data_ptr(), Hh.stream())
     rel = float((dw - w.grad).norm() / w.grad.norm())
     assert rel <= 2e-5, rel
@@ -215,7 +219,7 @@ def test_wgrad_matches_autograd(kind):
 # (Cout 512 -> four n tiles), Cout 64 (upper half of the 128-row tile is out-of-bounds zero fill), an image smaller
 # than one 64-pixel patch, and a batch large enough for several pixel splits.
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
-@pytest.mark.parametrize("kind", ["res", "res69", "down", "down128", "convT", "convT256", "dk4s2", "dk4s1", "tiny"])
+@pytest.mark.parametrize("kind", ["res", "res69", "down", "down128", "convT", "convT256", "dk4s2", "dk4s1", "tiny", "l0"])
 def test_wgrad_tc_matches_autograd(kind, dt):
     import ctypes as C
     from nirgan_b200 import _lib as L
@@ -233,6 +237,7 @@ def test_wgrad_tc_matches_autograd(kind, dt):
         "dk4s2": (64, 128, 4, 2, 1, 32, "zero", L.FORM_GATHER),
         "dk4s1": (256, 512, 4, 1, 1, 8, "zero", L.FORM_GATHER),
         "tiny": (64, 64, 3, 1, 1, 5, "reflect", L.FORM_GATHER),
+        "l0": (16, 64, 4, 2, 1, 40, "zero", L.FORM_GATHER),          # PatchGAN input layer (16 stored channels)
     }
     Cin, Cout, K, s, p, H, mode, form = cfgs[kind]
     if kind == "res69":
@@ -264,7 +269,7 @@ def test_wgrad_tc_matches_autograd(kind, dt):
     L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), db.data_ptr(), ws.data_ptr(), need, Hh.stream())
     dw = torch.empty_like(w)
     n_axis = 1 if form == L.FORM_PHASED else 0
-    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, Cout, Cin, 1.0,
+    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, Cout, Cin, 1.0, None,
            dw.data_ptr(), Hh.stream())
     assert bool(torch.isfinite(dw).all())
     rel = float((dw - w.grad).norm() / w.grad.norm())

@@ -97,7 +97,7 @@ def test_in_bwd_unit_matches_autograd(case):
         db = torch.empty(128 * 128, device="cuda")
         emb = _gen(B, 256, seed=6)
         scratch = torch.empty(B * 128 * 128, device="cuda")
-        L.call("ng_inject_bwd", de_map.data_ptr(), B, H, W, 1.0, emb.data_ptr(), scratch.data_ptr(), dW.data_ptr(),
+        L.call("ng_inject_bwd", de_map.data_ptr(), B, H, W, 1.0, None, emb.data_ptr(), scratch.data_ptr(), dW.data_ptr(),
                db.data_ptr(), Hh.stream())
         de128 = e.grad.view(B, 128 * 128)
         assert float((scratch.view(B, -1) - de128).abs().max()) <= 1e-3 * max(1.0, float(de128.abs().max()))

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--precision", default="fp16")
     ap.add_argument("--conv", default="tc")
+    ap.add_argument("--profile", action="store_true", help="per-op device times of one extra step -> stderr + gpurun_out")
     args = ap.parse_args()
     import nirgan_b200  # noqa: F401
     from nirgan_b200.model.pix2pix import Px2Px
@@ -58,6 +59,35 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    if args.profile:
+        import re
+        from nirgan_b200 import engine
+        engine.PROFILE[0] = []
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        step()
+        e3.record()
+        torch.cuda.synchronize()
+        recs = engine.PROFILE[0]
+        engine.PROFILE[0] = None
+        agg, tot = {}, 0.0
+        for label, name, a, b in recs:
+            t = a.elapsed_time(b)
+            tot += t
+            key = (label.split(".")[0], name, re.sub(r"^[a-z0-9]+\.", "", label))
+            agg[key] = agg.get(key, 0.0) + t
+        rows = sorted(agg.items(), key=lambda kv: -kv[1])
+        print(f"profiled step {e2.elapsed_time(e3):.2f} ms wall, {tot:.2f} ms inside plans", file=sys.stderr)
+        byname = {}
+        for (tag, name, lab), t in rows:
+            byname[name] = byname.get(name, 0.0) + t
+        print("by entry point:", {k: round(v, 3) for k, v in sorted(byname.items(), key=lambda kv: -kv[1])}, file=sys.stderr)
+        for (tag, name, lab), t in rows[:60]:
+            print(f"  {t:8.3f} ms  {tag:5s} {name:24s} {lab}", file=sys.stderr)
+        out_dir = os.path.join(ROOT, "gpurun_out")
+        if os.path.isdir(out_dir):
+            with open(os.path.join(out_dir, "train_op_times.json"), "w") as f:
+                json.dump([{"plan": tag, "op": name, "label": lab, "ms": round(t, 4)} for (tag, name, lab), t in rows], f, indent=0)
     # reference-faithful op count: 2 G forwards per batch (pix2pix.py:177-180 runs G in both optimizer passes)
     gflop = 505.8 * (args.tile / 256.0) ** 2
     print(json.dumps({"workload": f"configs[3]: Pix2Pix training step, batch {args.batch}, {args.tile}px, {args.precision}/{args.conv}",
