@@ -47,180 +47,215 @@ __device__ __forceinline__ float bilerp128_b(const float* __restrict__ e, int oy
 }
 
 struct BwdArgs {
-  int B, H, W, C;
+  int B, H, W, C, c8_shift;
   int act; float slope;
   int gp, halo_mode;           // halo of the incoming gradient buffer
   int inj_mode;
   float inv_hw;
+  int ppb;                     // interior pixels per block
+  unsigned long long w_magic;  // ceil(2^40 / W): p / W == (p * w_magic) >> 40 for p < 2^20
 };
 
-// dL/do for 8 channels of interior pixel (n, y, x): fold the haloed gradient + skip gradient
+__device__ __forceinline__ uint4 ldg16_stream(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 template <typename T>
-__device__ __forceinline__ void gather_do(const BwdArgs& a, const T* __restrict__ g, const T* __restrict__ gskip, int n,
-                                          int y, int x, int c8, float (&d)[8]) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) d[k] = 0.f;
-  if (g) {
-    const int p = a.gp, Hb = a.H + 2 * p, Wb = a.W + 2 * p;
-    int ys[3], xs[3];
-    ys[0] = y + p; xs[0] = x + p;
-    ys[1] = ys[2] = xs[1] = xs[2] = -1;
-    if (a.halo_mode == NG_HALO_REFLECT && p > 0) {
-      if (y >= 1 && y <= p) ys[1] = p - y;
-      if (y >= a.H - 1 - p && y <= a.H - 2) ys[2] = p + 2 * (a.H - 1) - y;
-      if (x >= 1 && x <= p) xs[1] = p - x;
-      if (x >= a.W - 1 - p && x <= a.W - 2) xs[2] = p + 2 * (a.W - 1) - x;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      if (ys[i] < 0) continue;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        if (xs[j] < 0) continue;
-        float f[8];
-        ld8<T>(g + (((size_t)n * Hb + ys[i]) * Wb + xs[j]) * a.C + c8 * 8, f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] += f[k];
-      }
-    }
-  }
-  if (gskip) {
-    float f[8];
-    ld8<T>(gskip + (((size_t)n * a.H + y) * a.W + x) * a.C + c8 * 8, f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) d[k] += f[k];
+__device__ __forceinline__ void up8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack2<T>(u.x), b = unpack2<T>(u.y), c = unpack2<T>(u.z), d = unpack2<T>(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+// raw 8-channel vector: 16 B on the 16-bit paths, 32 B in fp32 verification mode
+template <typename T> struct Raw8 { uint4 lo; };
+template <> struct Raw8<float> { uint4 lo, hi; };
+template <typename T>
+__device__ __forceinline__ Raw8<T> ld_raw8(const T* p) {
+  Raw8<T> r;
+  r.lo = ldg16_stream(p);
+  if constexpr (sizeof(T) == 4) r.hi = ldg16_stream(p + 4);
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void raw_to_f(const Raw8<T>& r, float (&f)[8]) {
+  if constexpr (sizeof(T) == 2) up8<T>(r.lo, f);
+  else {
+    f[0] = __uint_as_float(r.lo.x); f[1] = __uint_as_float(r.lo.y); f[2] = __uint_as_float(r.lo.z); f[3] = __uint_as_float(r.lo.w);
+    f[4] = __uint_as_float(r.hi.x); f[5] = __uint_as_float(r.hi.y); f[6] = __uint_as_float(r.hi.z); f[7] = __uint_as_float(r.hi.w);
   }
 }
 
-// Computes xh, dxh (and du) for 8 channels.  Returns the bilinear embedding value used (0 if none).
+// The reflect halo folds mirrored gradient rows / columns back onto interior pixels next to the border: adds the
+// (rare) extra contributions to d[] for interior pixel (y, x).  ptr = gradient buffer of image n at channel group c8.
 template <typename T>
-__device__ __forceinline__ float unit_backward(const BwdArgs& a, const T* __restrict__ yv, const float* __restrict__ mrn,
-                                               const float* __restrict__ injn, float s, int n, int y, int x, int c8,
-                                               const float (&d_o)[8], float (&xh)[8], float (&du)[8], float (&dxh)[8]) {
-  ld8<T>(yv + (((size_t)n * a.H + y) * a.W + x) * a.C + c8 * 8, xh);
-  if (mrn) {
-    const float4* m4 = reinterpret_cast<const float4*>(mrn + c8 * 16);
+__device__ __forceinline__ void fold_halo_extras(const BwdArgs& a, const T* __restrict__ gn, int y, int x, float (&d)[8]) {
+  const int p = a.gp, Wb = a.W + 2 * p;
+  int ys[3], xs[3];
+  ys[0] = y + p; xs[0] = x + p;
+  ys[1] = (y >= 1 && y <= p) ? p - y : -1;
+  ys[2] = (y >= a.H - 1 - p && y <= a.H - 2) ? p + 2 * (a.H - 1) - y : -1;
+  xs[1] = (x >= 1 && x <= p) ? p - x : -1;
+  xs[2] = (x >= a.W - 1 - p && x <= a.W - 2) ? p + 2 * (a.W - 1) - x : -1;
+  if ((ys[1] & ys[2] & xs[1] & xs[2]) == -1) return;       // all four absent
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (ys[i] < 0) continue;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (xs[j] < 0 || (i == 0 && j == 0)) continue;
+      float f[8];
+      ld8<T>(gn + ((size_t)ys[i] * Wb + xs[j]) * a.C, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] += f[k];
+    }
+  }
+}
+
+// Shared by both passes.  PASS 1: per-(n,c) sums of dxh and dxh*xh (+ injection gradients).  PASS 2: dy = rstd * (dxh -
+// mean(dxh) - xh * mean(dxh*xh)) and the optional export of do for the skip path.  Block (chunk, n) walks `ppb`
+// consecutive interior pixels of image n; thread t owns the channel group c8 = t mod C/8 (statistics in registers) and
+// batches UNROLL pixels of independent 16-byte streaming loads (gradient, skip gradient, forward pre-norm tensor).
+template <typename T, int PASS, int UNROLL, bool HAS_G, bool HAS_SKIP, bool HAS_INJ>
+__global__ void __launch_bounds__(256, 3)
+in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const T* __restrict__ gskip,
+              const T* __restrict__ yv, const float* __restrict__ mr, const float* __restrict__ inj,
+              const float* __restrict__ inj_scale, float* __restrict__ sums, float* __restrict__ dscale,
+              float* __restrict__ de_map, T* __restrict__ dy, T* __restrict__ do_out) {
+  extern __shared__ float sm[];            // PASS 1: [C][2] block accumulators
+  const int n = blockIdx.y, C8 = a.C >> 3;
+  const int c8 = threadIdx.x & (C8 - 1);
+  const int pstep = 256 >> a.c8_shift;
+  const int npix = a.H * a.W;
+  const int p_begin = blockIdx.x * a.ppb, p_end = min(npix, p_begin + a.ppb);
+  if (PASS == 1) {
+    for (int i = threadIdx.x; i < a.C * 2; i += 256) sm[i] = 0.f;
+    __syncthreads();
+  }
+  const float s = (HAS_INJ && inj_scale) ? *inj_scale : 1.f;
+  float mean[8], rstd[8], m1[8], m2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { mean[k] = 0.f; rstd[k] = 1.f; m1[k] = 0.f; m2[k] = 0.f; }
+  if (mr) {
+    const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * a.C + c8 * 8) * 2);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float4 m = m4[k];
-      xh[2 * k] = (xh[2 * k] - m.x) * m.y;
-      xh[2 * k + 1] = (xh[2 * k + 1] - m.z) * m.w;
+      mean[2 * k] = m.x; rstd[2 * k] = m.y; mean[2 * k + 1] = m.z; rstd[2 * k + 1] = m.w;
     }
-  }
-  float ev = 0.f, fac = 1.f, add = 0.f;
-  if (a.inj_mode != NG_INJECT_NONE) {
-    ev = bilerp128_b(injn, y, x, a.H, a.W);
-    if (a.inj_mode == NG_INJECT_ADD) { add = s * ev; }
-    else if (a.inj_mode == NG_INJECT_MUL_SCALED) fac = 1.f + s * ev;
-    else fac = ev;
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float u = xh[k] * fac + add;
-    float dact = 1.f;
-    if (a.act == NG_ACT_RELU) dact = u > 0.f ? 1.f : 0.f;
-    else if (a.act == NG_ACT_LRELU) dact = u > 0.f ? 1.f : a.slope;
-    du[k] = d_o[k] * dact;
-    dxh[k] = du[k] * fac;
-  }
-  return ev;
-}
-
-// ---- pass 1: per-(n,c) sums of dxh and dxh*xh (+ injection gradients) --------------------------------
-// grid = (row chunks, B); block 256 threads; a block walks `rows_per_block` rows of image n.
-template <typename T>
-__global__ void __launch_bounds__(256)
-in_bwd_reduce_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const T* __restrict__ gskip,
-                     const T* __restrict__ yv, const float* __restrict__ mr, const float* __restrict__ inj,
-                     const float* __restrict__ inj_scale, float* __restrict__ sums, float* __restrict__ dscale,
-                     float* __restrict__ de_map, int rows_per_block) {
-  extern __shared__ float sm[];            // [C][2] block accumulators
-  const int n = blockIdx.y, C8 = a.C >> 3;
-  for (int i = threadIdx.x; i < a.C * 2; i += 256) sm[i] = 0.f;
-  __syncthreads();
-  const float s = (a.inj_mode != NG_INJECT_NONE && inj_scale) ? *inj_scale : 1.f;
-  const float* mrn = mr ? mr + (size_t)n * a.C * 2 : nullptr;
-  const float* injn = inj ? inj + (size_t)n * 128 * 128 : nullptr;
-  const int y0 = blockIdx.x * rows_per_block, y1 = min(a.H, y0 + rows_per_block);
-  const int items = (y1 - y0) * a.W * C8;
-  // a thread keeps one channel group (c8) when 256 % C8 == 0, so it can accumulate in registers
-  float acc1[8], acc2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc1[k] = acc2[k] = 0.f;
-  float ds_acc = 0.f;
-  const int c8 = threadIdx.x % C8;         // C8 is a power of two <= 64 -> divides 256
-  for (int e = threadIdx.x; e < items; e += 256) {
-    const int pix = e / C8;
-    const int y = y0 + pix / a.W, x = pix % a.W;
-    float d_o[8], xh[8], du[8], dxh[8];
-    gather_do<T>(a, g, gskip, n, y, x, c8, d_o);
-    const float ev = unit_backward<T>(a, yv, mrn, injn, s, n, y, x, c8, d_o, xh, du, dxh);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { acc1[k] += dxh[k]; acc2[k] = fmaf(dxh[k], xh[k], acc2[k]); }
-    if (a.inj_mode != NG_INJECT_NONE) {
-      float t = 0.f;     // sum over these 8 channels of du * d u / d(s*e)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) t += (a.inj_mode == NG_INJECT_ADD) ? du[k] : du[k] * xh[k];
-      // u = xh*(1+s*e) | xh + s*e | xh*e
-      if (a.inj_mode == NG_INJECT_MUL) { if (de_map) atomicAdd(&de_map[((size_t)n * a.H + y) * a.W + x], t); }
-      else {
-        ds_acc += t * ev;
-        if (de_map) atomicAdd(&de_map[((size_t)n * a.H + y) * a.W + x], t * s);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    atomicAdd(&sm[(c8 * 8 + k) * 2 + 0], acc1[k]);
-    atomicAdd(&sm[(c8 * 8 + k) * 2 + 1], acc2[k]);
-  }
-  if (a.inj_mode != NG_INJECT_NONE && dscale) {
-    ds_acc = warp_sum(ds_acc);
-    if ((threadIdx.x & 31) == 0 && ds_acc != 0.f) atomicAdd(dscale, ds_acc);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < a.C * 2; i += 256) atomicAdd(&sums[(size_t)n * a.C * 2 + i], sm[i]);
-}
-
-// ---- pass 2: dy = rstd * (dxh - mean(dxh) - xh * mean(dxh*xh)); optional do export for the skip path -----
-template <typename T>
-__global__ void __launch_bounds__(256)
-in_bwd_apply_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const T* __restrict__ gskip,
-                    const T* __restrict__ yv, const float* __restrict__ mr, const float* __restrict__ inj,
-                    const float* __restrict__ inj_scale, const float* __restrict__ sums, T* __restrict__ dy,
-                    T* __restrict__ do_out) {
-  const int C8 = a.C >> 3;
-  const long long total = (long long)a.B * a.H * a.W * C8;
-  const float s = (a.inj_mode != NG_INJECT_NONE && inj_scale) ? *inj_scale : 1.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % C8);
-    long long p = i / C8;
-    const int x = (int)(p % a.W); p /= a.W;
-    const int y = (int)(p % a.H);
-    const int n = (int)(p / a.H);
-    const float* mrn = mr ? mr + (size_t)n * a.C * 2 : nullptr;
-    const float* injn = inj ? inj + (size_t)n * 128 * 128 : nullptr;
-    float d_o[8], xh[8], du[8], dxh[8];
-    gather_do<T>(a, g, gskip, n, y, x, c8, d_o);
-    unit_backward<T>(a, yv, mrn, injn, s, n, y, x, c8, d_o, xh, du, dxh);
-    float out[8];
-    if (mrn) {
+    if (PASS == 2) {
       const float4* s4 = reinterpret_cast<const float4*>(sums + ((size_t)n * a.C + c8 * 8) * 2);
-      const float4* m4 = reinterpret_cast<const float4*>(mrn + c8 * 16);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4 sv = s4[k], m = m4[k];
-        out[2 * k] = m.y * (dxh[2 * k] - sv.x * a.inv_hw - xh[2 * k] * sv.y * a.inv_hw);
-        out[2 * k + 1] = m.w * (dxh[2 * k + 1] - sv.z * a.inv_hw - xh[2 * k + 1] * sv.w * a.inv_hw);
+        const float4 sv = s4[k];
+        m1[2 * k] = sv.x * a.inv_hw; m2[2 * k] = sv.y * a.inv_hw;
+        m1[2 * k + 1] = sv.z * a.inv_hw; m2[2 * k + 1] = sv.w * a.inv_hw;
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) out[k] = dxh[k];
     }
-    const size_t off = (((size_t)n * a.H + y) * a.W + x) * a.C + c8 * 8;
-    st8<T>(dy + off, out);
-    if (do_out) st8<T>(do_out + off, d_o);
+  }
+  const int gp = a.gp, Wb = a.W + 2 * gp;
+  const T* gn = HAS_G ? g + (size_t)n * (a.H + 2 * gp) * Wb * a.C + c8 * 8 : nullptr;
+  const T* sn = HAS_SKIP ? gskip + (size_t)n * npix * a.C + c8 * 8 : nullptr;
+  const T* yn = yv + (size_t)n * npix * a.C + c8 * 8;
+  const float* injn = HAS_INJ ? inj + (size_t)n * 128 * 128 : nullptr;
+  const bool fold = HAS_G && a.halo_mode == NG_HALO_REFLECT && gp > 0;
+  float acc1[8], acc2[8], ds_acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc1[k] = acc2[k] = 0.f;
+
+  for (int p0 = p_begin + (threadIdx.x >> a.c8_shift); p0 < p_end; p0 += pstep * UNROLL) {
+    Raw8<T> rg[HAS_G ? UNROLL : 1], rs[HAS_SKIP ? UNROLL : 1], ry[UNROLL];
+    int py[UNROLL], px[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pp = p0 + u * pstep;
+      const int yy = (int)(((unsigned long long)(unsigned)pp * a.w_magic) >> 40);
+      py[u] = yy; px[u] = pp - yy * a.W;
+      if (pp < p_end) {
+        ry[u] = ld_raw8<T>(yn + (size_t)pp * a.C);
+        if constexpr (HAS_G) rg[u] = ld_raw8<T>(gn + ((size_t)(yy + gp) * Wb + px[u] + gp) * a.C);
+        if constexpr (HAS_SKIP) rs[u] = ld_raw8<T>(sn + (size_t)pp * a.C);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pp = p0 + u * pstep;
+      if (pp >= p_end) continue;
+      float d_o[8], xh[8];
+      if constexpr (HAS_G) raw_to_f<T>(rg[u], d_o);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d_o[k] = 0.f;
+      }
+      if (fold) fold_halo_extras<T>(a, gn, py[u], px[u], d_o);
+      if constexpr (HAS_SKIP) {
+        float t[8];
+        raw_to_f<T>(rs[u], t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d_o[k] += t[k];
+      }
+      raw_to_f<T>(ry[u], xh);
+      if (mr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) xh[k] = (xh[k] - mean[k]) * rstd[k];
+      }
+      float ev = 0.f, fac = 1.f, add = 0.f;
+      if constexpr (HAS_INJ) {
+        ev = bilerp128_b(injn, py[u], px[u], a.H, a.W);
+        if (a.inj_mode == NG_INJECT_ADD) add = s * ev;
+        else if (a.inj_mode == NG_INJECT_MUL_SCALED) fac = 1.f + s * ev;
+        else fac = ev;
+      }
+      float du[8], dxh[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float uu = xh[k] * fac + add;
+        float dact = 1.f;
+        if (a.act == NG_ACT_RELU) dact = uu > 0.f ? 1.f : 0.f;
+        else if (a.act == NG_ACT_LRELU) dact = uu > 0.f ? 1.f : a.slope;
+        du[k] = d_o[k] * dact;
+        dxh[k] = du[k] * fac;
+      }
+      if constexpr (PASS == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc1[k] += dxh[k]; acc2[k] = fmaf(dxh[k], xh[k], acc2[k]); }
+        if constexpr (HAS_INJ) {
+          float t = 0.f;     // sum over these 8 channels of du * d u / d(s*e);  u = xh*(1+s*e) | xh + s*e | xh*e
+#pragma unroll
+          for (int k = 0; k < 8; ++k) t += (a.inj_mode == NG_INJECT_ADD) ? du[k] : du[k] * xh[k];
+          if (a.inj_mode == NG_INJECT_MUL) { if (de_map) atomicAdd(&de_map[(size_t)n * npix + pp], t); }
+          else {
+            ds_acc += t * ev;
+            if (de_map) atomicAdd(&de_map[(size_t)n * npix + pp], t * s);
+          }
+        }
+      } else {
+        float o[8];
+        if (mr) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = rstd[k] * (dxh[k] - m1[k] - xh[k] * m2[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = dxh[k];
+        }
+        st8<T>(dy + ((size_t)n * npix + pp) * a.C + c8 * 8, o);
+        if (do_out) st8<T>(do_out + ((size_t)n * npix + pp) * a.C + c8 * 8, d_o);
+      }
+    }
+  }
+  if constexpr (PASS == 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(&sm[(c8 * 8 + k) * 2 + 0], acc1[k]);
+      atomicAdd(&sm[(c8 * 8 + k) * 2 + 1], acc2[k]);
+    }
+    if (HAS_INJ && dscale) {
+      ds_acc = warp_sum(ds_acc);
+      if ((threadIdx.x & 31) == 0 && ds_acc != 0.f) atomicAdd(dscale, ds_acc);
+    }
+    __syncthreads();
+    if (sums)
+      for (int i = threadIdx.x; i < a.C * 2; i += 256) atomicAdd(&sums[(size_t)n * a.C * 2 + i], sm[i]);
   }
 }
 
@@ -387,6 +422,22 @@ using namespace ng;
     default: ng::set_error("bad dtype %d", (int)(dtype)); return NG_E_ARG;  \
   }
 
+template <typename T, int PASS>
+static void launch_in_bwd(const BwdArgs& a, dim3 grid, size_t smem, cudaStream_t st, const void* g, const void* gskip,
+                          const void* y, const float* mr, const float* inj, const float* inj_scale, float* sums,
+                          float* dscale, float* de_map, void* dy, void* do_out) {
+  const bool hg = g != nullptr, hs = gskip != nullptr, hi = a.inj_mode != NG_INJECT_NONE;
+#define NG_BWD(G, S, I)                                                                                              \
+  in_bwd_kernel<T, PASS, 2, G, S, I><<<grid, 256, smem, st>>>(a, (const T*)g, (const T*)gskip, (const T*)y, mr, inj, \
+                                                              inj_scale, sums, dscale, de_map, (T*)dy, (T*)do_out)
+  if (hi) {                       // the injected unit (d1) receives its gradient from one haloed buffer
+    if (hg && hs) NG_BWD(true, true, true); else if (hg) NG_BWD(true, false, true); else NG_BWD(false, true, true);
+  } else {
+    if (hg && hs) NG_BWD(true, true, false); else if (hg) NG_BWD(true, false, false); else NG_BWD(false, true, false);
+  }
+#undef NG_BWD
+}
+
 extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y,
                          int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd, int32_t act,
                          float slope, const float* inject_e, int32_t inject_mode, const float* inject_scale,
@@ -397,36 +448,36 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
   NG_REQUIRE(mean_rstd == nullptr || sums_scratch != nullptr, NG_E_ARG, "in_bwd: normalised unit needs a [B][C][2] scratch");
   NG_REQUIRE(inject_mode == NG_INJECT_NONE || inject_e, NG_E_ARG, "in_bwd: injection without embedding map");
   NG_REQUIRE(halo_mode != NG_HALO_REFLECT || (2 * g_pad + 1 < H && 2 * g_pad + 1 < W), NG_E_SHAPE, "in_bwd: halo too large");
+  NG_REQUIRE((long long)H * W < (1ll << 20) && W < (1 << 12), NG_E_SHAPE, "in_bwd: image %dx%d too large", H, W);
   cudaStream_t st = (cudaStream_t)stream;
   BwdArgs a;
-  a.B = B; a.H = H; a.W = W; a.C = C; a.act = act; a.slope = slope; a.gp = g_pad; a.halo_mode = halo_mode;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.act = act; a.slope = slope; a.gp = g_halo ? g_pad : 0; a.halo_mode = halo_mode;
   a.inj_mode = inject_mode; a.inv_hw = 1.0f / ((float)H * (float)W);
-  if (mean_rstd || inject_mode != NG_INJECT_NONE) {
-    float* sums = sums_scratch;
-    if (sums) {
-      int e = check_cuda(cudaMemsetAsync(sums, 0, (size_t)B * C * 2 * sizeof(float), st), "in_bwd memset");
+  a.c8_shift = 0;
+  while ((1 << a.c8_shift) < C / 8) ++a.c8_shift;
+  a.w_magic = ((1ull << 40) + (unsigned)W - 1) / (unsigned)W;
+  const int pstep = 256 / (C / 8);
+  const bool need_pass1 = mean_rstd != nullptr || (inject_mode != NG_INJECT_NONE && (dscale || de_map));
+  if (need_pass1) {
+    if (sums_scratch) {
+      int e = check_cuda(cudaMemsetAsync(sums_scratch, 0, (size_t)B * C * 2 * sizeof(float), st), "in_bwd memset");
       if (e) return e;
     }
     if (de_map) {
       int e = check_cuda(cudaMemsetAsync(de_map, 0, (size_t)B * H * W * sizeof(float), st), "in_bwd memset de");
       if (e) return e;
     }
-    if (mean_rstd || dscale || de_map) {
-      NG_REQUIRE(sums != nullptr, NG_E_ARG, "in_bwd: scratch required");
-      int rpb = (4096 + W * (C / 8) - 1) / (W * (C / 8));
-      if (rpb < 1) rpb = 1;
-      dim3 grid((H + rpb - 1) / rpb, B);
-      DISPATCH_T(dtype, (in_bwd_reduce_kernel<T><<<grid, 256, C * 2 * sizeof(float), st>>>(
-                            a, (const T*)g_halo, (const T*)g_skip, (const T*)y, mean_rstd, inject_e, inject_scale, sums,
-                            dscale, de_map, rpb)));
-      NG_LAUNCH_CHECK("in_bwd_reduce_kernel");
-    }
+    a.ppb = pstep * 64;            // long blocks: fewer global atomics on the [B][C][2] sums
+    dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)B);
+    DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)C * 2 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
+                                           inject_e, inject_scale, sums_scratch, dscale, de_map, nullptr, nullptr)));
+    NG_LAUNCH_CHECK("in_bwd_kernel<pass 1>");
   }
-  const long long total = (long long)B * H * W * (C / 8);
-  DISPATCH_T(dtype, (in_bwd_apply_kernel<T><<<grid_cap(total), 256, 0, st>>>(
-                        a, (const T*)g_halo, (const T*)g_skip, (const T*)y, mean_rstd, inject_e, inject_scale,
-                        sums_scratch, (T*)dy, (T*)do_out)));
-  NG_LAUNCH_CHECK("in_bwd_apply_kernel");
+  a.ppb = pstep * 16;
+  dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)B);
+  DISPATCH_T(dtype, (launch_in_bwd<T, 2>(a, grid, 0, st, g_halo, g_skip, y, mean_rstd, inject_e, inject_scale,
+                                         sums_scratch, nullptr, nullptr, dy, do_out)));
+  NG_LAUNCH_CHECK("in_bwd_kernel<pass 2>");
   return NG_OK;
 }
 

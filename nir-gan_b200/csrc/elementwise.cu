@@ -185,121 +185,112 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
-// Row-organised apply.  A block owns `rows_per_block` whole output rows (n, yo) (halo rows included); thread t keeps the
-// channel group c8 = t mod C/8 for its whole life (C/8 is a power of two <= 256), so the 8 (mean, rstd) pairs live in
-// registers and the inner loop is: UNROLL independent 16-byte loads (+ residual loads) -> math -> 16-byte stores.
+// Flat apply.  Block (chunk, n) owns `ppb` consecutive pixels of image n's haloed output buffer (row-major over
+// (H+2p) x (W+2p), so its stores are one contiguous span); thread t keeps the channel group c8 = t mod C/8 for its whole
+// life (C/8 is a power of two <= 256), so the 8 (mean, rstd) pairs live in registers.  The inner loop is: UNROLL
+// independent 16-byte streaming loads (+ residual loads) -> math one pixel at a time -> 16-byte stores.  The pixel ->
+// (row, column) split uses a multiply-shift by the precomputed reciprocal of the buffer width.
 template <typename T, int UNROLL, bool HAS_RES, bool HAS_INJ>
 __global__ void __launch_bounds__(256, 3)
-in_apply_kernel(const T* __restrict__ y, int B, int H, int W, int C, int c8_shift, const float* __restrict__ mr, int act,
+in_apply_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, const float* __restrict__ mr, int act,
                 float slope, const T* __restrict__ res, int res_pad, const float* __restrict__ inj, int inj_mode,
-                const float* __restrict__ inj_scale, T* __restrict__ out, int op, int halo_mode, int rows_per_block) {
+                const float* __restrict__ inj_scale, T* __restrict__ out, int op, int halo_mode, int ppb,
+                unsigned long long wo_magic) {
   const int Ho = H + 2 * op, Wo = W + 2 * op, C8 = C >> 3;
+  const int n = blockIdx.y;
+  const int npix = Ho * Wo;
   const float s = (HAS_INJ && inj_scale) ? *inj_scale : 1.f;
   const int c8 = threadIdx.x & (C8 - 1);
-  const int xstep = 256 >> c8_shift;                 // output columns covered by the block per iteration
-  const int x_first = threadIdx.x >> c8_shift;
-  const int Hr = H + 2 * res_pad, Wr = W + 2 * res_pad;
-  int n_cached = -1;
+  const int pstep = 256 >> c8_shift;                 // pixels covered by the block per load
+  const int p_begin = blockIdx.x * ppb, p_end = min(npix, p_begin + ppb);
   float mean[8], rstd[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { mean[k] = 0.f; rstd[k] = 1.f; }
-  for (int r = 0; r < rows_per_block; ++r) {
-    const long long grow = (long long)blockIdx.x * rows_per_block + r;
-    if (grow >= (long long)B * Ho) return;
-    const int yo = (int)(grow % Ho), n = (int)(grow / Ho);
-    int ys = yo - op;
-    const bool row_zero = halo_mode != NG_HALO_REFLECT && (ys < 0 || ys >= H);
-    if (halo_mode == NG_HALO_REFLECT) ys = reflect_idx(ys, H);
-    T* orow = out + (((size_t)n * Ho + yo) * Wo) * C + c8 * 8;
-    if (row_zero) {
-      for (int xo = x_first; xo < Wo; xo += xstep) {
-        if constexpr (sizeof(T) == 2) *reinterpret_cast<uint4*>(orow + (size_t)xo * C) = make_uint4(0u, 0u, 0u, 0u);
-        else { float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; store8<T>(orow + (size_t)xo * C, z); }
-      }
-      continue;
+  if (mr) {
+    const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 m = m4[k];
+      mean[2 * k] = m.x; rstd[2 * k] = m.y; mean[2 * k + 1] = m.z; rstd[2 * k + 1] = m.w;
     }
-    if (mr && n != n_cached) {
-      const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
+  }
+  const int Wr = W + 2 * res_pad;
+  const T* ybase = y + (size_t)n * H * W * C + c8 * 8;
+  const T* rbase = HAS_RES ? res + ((size_t)n * (H + 2 * res_pad) * Wr + (size_t)res_pad * Wr + res_pad) * C + c8 * 8 : nullptr;
+  T* obase = out + (size_t)n * npix * C + c8 * 8;
+  const float* injn = HAS_INJ ? inj + (size_t)n * 128 * 128 : nullptr;
+  for (int p0 = p_begin + (threadIdx.x >> c8_shift); p0 < p_end; p0 += pstep * UNROLL) {
+    // phase 1: issue every load of this batch before any use
+    uint4 raw[UNROLL], rres[HAS_RES ? UNROLL : 1];
+    float4 rawf[sizeof(T) == 4 ? UNROLL : 1][2], rresf[(sizeof(T) == 4 && HAS_RES) ? UNROLL : 1][2];
+    int ysrc[UNROLL], xsrc[UNROLL];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 m = m4[k];
-        mean[2 * k] = m.x; rstd[2 * k] = m.y; mean[2 * k + 1] = m.z; rstd[2 * k + 1] = m.w;
-      }
-      n_cached = n;
-    }
-    const T* yrow = y + (((size_t)n * H + ys) * W) * C + c8 * 8;
-    const T* rrow = HAS_RES ? res + ((((size_t)n * Hr + ys + res_pad) * Wr + res_pad)) * C + c8 * 8 : nullptr;
-    const float* injn = HAS_INJ ? inj + (size_t)n * 128 * 128 : nullptr;
-    for (int x0 = x_first; x0 < Wo; x0 += xstep * UNROLL) {
-      // phase 1: issue every load of this batch (UNROLL pixels x 16 B, plus the residual) before any use
-      uint4 raw[UNROLL], rres[HAS_RES ? UNROLL : 1];
-      float4 rawf[sizeof(T) == 4 ? UNROLL : 1][2], rresf[(sizeof(T) == 4 && HAS_RES) ? UNROLL : 1][2];
-      int xsrc[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int xo = x0 + u * xstep;
-        int x = xo - op;
-        bool ok = xo < Wo;
-        if (halo_mode == NG_HALO_REFLECT) x = reflect_idx(x, W);
-        else ok = ok && x >= 0 && x < W;
-        xsrc[u] = ok ? x : -1;
-        if (ok) {
-          if constexpr (sizeof(T) == 2) {
-            raw[u] = ldg_stream16(yrow + (size_t)x * C);
-            if constexpr (HAS_RES) rres[u] = ldg_stream16(rrow + (size_t)x * C);
-          } else {
-            rawf[u][0] = *reinterpret_cast<const float4*>(yrow + (size_t)x * C);
-            rawf[u][1] = *reinterpret_cast<const float4*>(yrow + (size_t)x * C + 4);
-            if constexpr (HAS_RES) {
-              rresf[u][0] = *reinterpret_cast<const float4*>(rrow + (size_t)x * C);
-              rresf[u][1] = *reinterpret_cast<const float4*>(rrow + (size_t)x * C + 4);
-            }
-          }
-        }
-      }
-      // phase 2: one pixel at a time (keeps the live register set small: occupancy is what hides HBM latency)
-#pragma unroll
-      for (int u = 0; u < UNROLL; ++u) {
-        const int xo = x0 + u * xstep;
-        if (xo >= Wo) continue;
-        float f[8];
-        if (xsrc[u] < 0) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = 0.f;
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pp = p0 + u * pstep;
+      const int yo = (int)(((unsigned long long)(unsigned)pp * wo_magic) >> 40);
+      const int xo = pp - yo * Wo;
+      int ys = yo - op, xs = xo - op;
+      bool ok = pp < p_end;
+      if (halo_mode == NG_HALO_REFLECT) { ys = reflect_idx(ys, H); xs = reflect_idx(xs, W); }
+      else ok = ok && ys >= 0 && ys < H && xs >= 0 && xs < W;
+      ysrc[u] = ys; xsrc[u] = ok ? xs : -1;
+      if (ok) {
+        const size_t off = ((size_t)ys * W + xs) * C;
+        if constexpr (sizeof(T) == 2) {
+          raw[u] = ldg_stream16(ybase + off);
+          if constexpr (HAS_RES) rres[u] = ldg_stream16(rbase + ((size_t)ys * Wr + xs) * C);
         } else {
-          if constexpr (sizeof(T) == 2) unpack8<T>(raw[u], f);
-          else {
-            f[0] = rawf[u][0].x; f[1] = rawf[u][0].y; f[2] = rawf[u][0].z; f[3] = rawf[u][0].w;
-            f[4] = rawf[u][1].x; f[5] = rawf[u][1].y; f[6] = rawf[u][1].z; f[7] = rawf[u][1].w;
-          }
-          if (mr) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean[k]) * rstd[k];
-          }
-          if constexpr (HAS_INJ) {
-            const float ev = bilerp128(injn, ys, xsrc[u], H, W);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (inj_mode == NG_INJECT_ADD) f[k] = f[k] + s * ev;
-              else if (inj_mode == NG_INJECT_MUL_SCALED) f[k] = f[k] * (1.f + s * ev);
-              else f[k] = f[k] * ev;
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) f[k] = apply_act(f[k], act, slope);
+          rawf[u][0] = *reinterpret_cast<const float4*>(ybase + off);
+          rawf[u][1] = *reinterpret_cast<const float4*>(ybase + off + 4);
           if constexpr (HAS_RES) {
-            float rv[8];
-            if constexpr (sizeof(T) == 2) unpack8<T>(rres[u], rv);
-            else {
-              rv[0] = rresf[u][0].x; rv[1] = rresf[u][0].y; rv[2] = rresf[u][0].z; rv[3] = rresf[u][0].w;
-              rv[4] = rresf[u][1].x; rv[5] = rresf[u][1].y; rv[6] = rresf[u][1].z; rv[7] = rresf[u][1].w;
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] += rv[k];
+            rresf[u][0] = *reinterpret_cast<const float4*>(rbase + ((size_t)ys * Wr + xs) * C);
+            rresf[u][1] = *reinterpret_cast<const float4*>(rbase + ((size_t)ys * Wr + xs) * C + 4);
           }
         }
-        store8<T>(orow + (size_t)xo * C, f);
       }
+    }
+    // phase 2: one pixel at a time (small live register set: occupancy is what hides HBM latency)
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int pp = p0 + u * pstep;
+      if (pp >= p_end) continue;
+      float f[8];
+      if (xsrc[u] < 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = 0.f;
+      } else {
+        if constexpr (sizeof(T) == 2) unpack8<T>(raw[u], f);
+        else {
+          f[0] = rawf[u][0].x; f[1] = rawf[u][0].y; f[2] = rawf[u][0].z; f[3] = rawf[u][0].w;
+          f[4] = rawf[u][1].x; f[5] = rawf[u][1].y; f[6] = rawf[u][1].z; f[7] = rawf[u][1].w;
+        }
+        if (mr) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean[k]) * rstd[k];
+        }
+        if constexpr (HAS_INJ) {
+          const float ev = bilerp128(injn, ysrc[u], xsrc[u], H, W);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (inj_mode == NG_INJECT_ADD) f[k] = f[k] + s * ev;
+            else if (inj_mode == NG_INJECT_MUL_SCALED) f[k] = f[k] * (1.f + s * ev);
+            else f[k] = f[k] * ev;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = apply_act(f[k], act, slope);
+        if constexpr (HAS_RES) {
+          float rv[8];
+          if constexpr (sizeof(T) == 2) unpack8<T>(rres[u], rv);
+          else {
+            rv[0] = rresf[u][0].x; rv[1] = rresf[u][0].y; rv[2] = rresf[u][0].z; rv[3] = rresf[u][0].w;
+            rv[4] = rresf[u][1].x; rv[5] = rresf[u][1].y; rv[6] = rresf[u][1].z; rv[7] = rresf[u][1].w;
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] += rv[k];
+        }
+      }
+      store8<T>(obase + (size_t)pp * C, f);
     }
   }
 }
@@ -680,15 +671,16 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   NG_REQUIRE((C8 & (C8 - 1)) == 0, NG_E_SHAPE, "in_apply: C/8 must be a power of two (C = %d)", C);
   int c8_shift = 0;
   while ((1 << c8_shift) < C8) ++c8_shift;
-  const long long rows = (long long)B * (H + 2 * out_pad);
-  const int row_elems = (W + 2 * out_pad) * C8;
-  int rpb = 1;                                   // give every block >= ~2048 16-byte items
-  while ((long long)rpb * row_elems < 2048 && rpb < 16) rpb *= 2;
-  const long long blocks = (rows + rpb - 1) / rpb;
+  const int Ho = H + 2 * out_pad, Wo = W + 2 * out_pad;
+  NG_REQUIRE((long long)Ho * Wo < (1ll << 20) && Wo < (1 << 12), NG_E_SHAPE, "in_apply: image %dx%d too large", Ho, Wo);
+  const unsigned long long wo_magic = ((1ull << 40) + (unsigned)Wo - 1) / (unsigned)Wo;   // exact for p < 2^20
+  const int pstep = 256 / C8;                     // pixels per block per load
+  const int ppb = pstep * 16;                     // 16 sixteen-byte items per thread = 4 batches of UNROLL 4
+  dim3 grid((unsigned)((Ho * Wo + ppb - 1) / ppb), (unsigned)B);
 #define NG_APPLY_LAUNCH(RES, INJ)                                                                                  \
-  DISPATCH_DTYPE(dtype, (in_apply_kernel<T, 4, RES, INJ><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(      \
-                            (const T*)y, B, H, W, C, c8_shift, mean_rstd, act, slope, (const T*)residual, res_pad, \
-                            inject_e, inject_mode, inject_scale, (T*)out, out_pad, halo_mode, rpb)))
+  DISPATCH_DTYPE(dtype, (in_apply_kernel<T, 4, RES, INJ><<<grid, 256, 0, (cudaStream_t)stream>>>(                  \
+                            (const T*)y, H, W, C, c8_shift, mean_rstd, act, slope, (const T*)residual, res_pad,    \
+                            inject_e, inject_mode, inject_scale, (T*)out, out_pad, halo_mode, ppb, wo_magic)))
   const bool has_inj = inject_mode != NG_INJECT_NONE;
   if (residual && has_inj) { NG_APPLY_LAUNCH(true, true); }
   else if (residual) { NG_APPLY_LAUNCH(true, false); }
