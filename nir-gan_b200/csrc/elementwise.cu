@@ -467,25 +467,26 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 prep_stem_kernel(const float* __restrict__ src, int cin, int B, int H, int W, int wrap, int halo, int KW,
                  T* __restrict__ dst) {
+  // block = one output row (n, yb): no per-item division; item = (x, kw) -> 16 bytes; consecutive threads write
+  // consecutive 16-byte groups and read consecutive source columns
   const int H1 = H + 2 * wrap, W1 = W + 2 * wrap, Hb = H1 + 2 * halo;
-  const long long total = (long long)B * Hb * W1 * 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int kw = (int)(i & 7);
-    long long p = i >> 3;
-    const int x = (int)(p % W1); p /= W1;
-    const int yb = (int)(p % Hb);
-    const int n = (int)(p / Hb);
+  const int row = blockIdx.x;
+  const int yb = row % Hb, n = row / Hb;
+  const int y0 = reflect_idx(reflect_idx(yb - halo, H1) - wrap, H);
+  const float* srow = src + ((size_t)n * cin * H + y0) * W;
+  const size_t plane = (size_t)H * W;
+  T* drow = dst + (size_t)row * W1 * 64;
+  for (int i = threadIdx.x; i < W1 * 8; i += 256) {
+    const int kw = i & 7, x = i >> 3;
     float f[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) f[c] = 0.f;
     if (kw < KW) {
       // column x + kw of the (halo-padded) image = column (x + kw - halo) of the wrapper-padded image
-      const int y1 = reflect_idx(yb - halo, H1), x1 = reflect_idx(x + kw - halo, W1);
-      const int y0 = reflect_idx(y1 - wrap, H), x0 = reflect_idx(x1 - wrap, W);
-      for (int c = 0; c < cin; ++c) f[c] = src[(((long long)n * cin + c) * H + y0) * W + x0];
+      const int x0 = reflect_idx(reflect_idx(x + kw - halo, W1) - wrap, W);
+      for (int c = 0; c < cin; ++c) f[c] = srow[c * plane + x0];
     }
-    T* o = dst + i * 8;
+    T* o = drow + (size_t)i * 8;
     if constexpr (sizeof(T) == 2) {
       uint4 u;
       u.x = pack2<T>(f[0], f[1]); u.y = pack2<T>(f[2], f[3]); u.z = pack2<T>(f[4], f[5]); u.w = pack2<T>(f[6], f[7]);
@@ -540,14 +541,32 @@ tap_gather_kernel(const T* __restrict__ z, int B, int Hz, int Wz, const float* _
   const int tx0 = (tix % tiles_x) * TG_W; tix /= tiles_x;
   const int ty0 = (tix % tiles_y) * TG_H;
   const int n = tix / tiles_y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int pix = warp; pix < PH * PW; pix += 8) {
-    const int py = pix / PW, px = pix - py * PW;
-    const int gy = ty0 + crop + py, gx = tx0 + crop + px;
-    const bool ok = gy < Hz && gx < Wz;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(z + (((size_t)n * Hz + (ok ? gy : 0)) * Wz + (ok ? gx : 0)) * ZC);
+  // staging: one thread copies one 16-byte chunk (CH chunks per pixel); 4 independent loads in flight per thread
+  constexpr int CH = (ZC * (int)sizeof(T)) / 16;             // 16-byte chunks per pixel (8 on the 16-bit paths)
+  constexpr int ITEMS = PH * PW * CH;
+  for (int i0 = threadIdx.x; i0 < ITEMS; i0 += 256 * 4) {
+    uint4 v[4];
 #pragma unroll
-    for (int wd = lane; wd < ZW; wd += 32) tg_sm[pix * PITCH + wd] = ok ? src[wd] : 0u;
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < ITEMS) {
+        const int pix = i / CH, c = i - pix * CH;
+        const int py = pix / PW, px = pix - py * PW;
+        const int gy = ty0 + crop + py, gx = tx0 + crop + px;
+        if (gy < Hz && gx < Wz)
+          v[u] = ldg_stream16(reinterpret_cast<const uint8_t*>(z + (((size_t)n * Hz + gy) * Wz + gx) * ZC) + c * 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i < ITEMS) {
+        const int pix = i / CH, c = i - pix * CH;
+        uint32_t* d = tg_sm + pix * PITCH + c * 4;           // odd pitch: four 4-byte stores
+        d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+      }
+    }
   }
   __syncthreads();
   const int lx = threadIdx.x % TG_W, ly = threadIdx.x / TG_W;
@@ -751,8 +770,9 @@ extern "C" int ng_prep_stem(const float* src, int32_t cin, int32_t B, int32_t H,
   NG_REQUIRE(src && dst && cin > 0 && cin <= 8 && KW > 0 && KW <= 8, NG_E_ARG, "prep_stem: cin and KW must be in 1..8");
   NG_REQUIRE(wrap_pad < H && wrap_pad < W && halo < H + 2 * wrap_pad && halo < W + 2 * wrap_pad, NG_E_SHAPE,
              "prep_stem: reflect padding needs a larger tile");
-  const long long total = (long long)B * (H + 2 * wrap_pad + 2 * halo) * (W + 2 * wrap_pad) * 8;
-  DISPATCH_DTYPE(dtype, (prep_stem_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  const long long rows = (long long)B * (H + 2 * wrap_pad + 2 * halo);
+  NG_REQUIRE(rows < (1ll << 31), NG_E_SHAPE, "prep_stem: too many rows");
+  DISPATCH_DTYPE(dtype, (prep_stem_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
                             src, cin, B, H, W, wrap_pad, halo, KW, (T*)dst)));
   NG_LAUNCH_CHECK("prep_stem_kernel");
   return NG_OK;

@@ -41,6 +41,8 @@ class EngineConfig:
     precision: str = "fp16"
     impl: str = "tc"
     chunk: int = 0          # images per pass through the network (0 = whole batch)
+    streams: int = 1        # inference: run this many batch slices concurrently on separate CUDA streams, so the
+                            # HBM-bound apply kernels of one slice overlap the tensor-bound convolutions of another
 
     def __post_init__(self):
         if self.precision not in _PRECISIONS:
@@ -54,7 +56,8 @@ class EngineConfig:
     def from_env() -> "EngineConfig":
         return EngineConfig(os.environ.get("NIRGAN_B200_PRECISION", "fp16"),
                             os.environ.get("NIRGAN_B200_IMPL", "tc"),
-                            int(os.environ.get("NIRGAN_B200_CHUNK", "0")))
+                            int(os.environ.get("NIRGAN_B200_CHUNK", "0")),
+                            int(os.environ.get("NIRGAN_B200_STREAMS", "1")))
 
 
 def require_cuda(t: torch.Tensor, what: str) -> None:

@@ -112,10 +112,11 @@ def _generator_trunk(input_nc, output_nc, ngf, norm_layer, n_blocks):
 class _B200Module(nn.Module):
     """Common plumbing: engine configuration and lazy runner."""
 
-    def configure_b200(self, precision=None, impl=None, chunk=None):
+    def configure_b200(self, precision=None, impl=None, chunk=None, streams=None):
         cfg = self.b200_config
         self.b200_config = EngineConfig(precision or cfg.precision, impl or cfg.impl,
-                                        cfg.chunk if chunk is None else chunk)
+                                        cfg.chunk if chunk is None else chunk,
+                                        cfg.streams if streams is None else streams)
         self._runner = None
         return self
 

@@ -30,6 +30,16 @@ class _RunnerBase:
             self._train.clear()
         return self._engine
 
+    def trim(self, eng: Engine) -> None:
+        """Plans own their buffers for life (static plan, no allocator).  With many distinct input shapes (mixed
+        resolutions, BASELINE config 5) drop every cached plan and buffer once they exceed the budget
+        (NIRGAN_B200_BUFFER_GB, default 90) -- only when no forward is waiting for its backward."""
+        budget = float(os.environ.get("NIRGAN_B200_BUFFER_GB", "90")) * 1e9
+        if eng.buffers.bytes() > budget and self._live == 0:
+            self._fwd.clear()
+            self._train.clear()
+            eng.buffers._b.clear()
+
     def loss_scale(self) -> float:
         """Target max |dL/d(output)| of the adaptive power-of-two gradient scaling (ng_grad_scale_pow2) used when
         gradients are stored as fp16; 0 = no scaling (bf16 / fp32 have the range)."""
@@ -43,6 +53,7 @@ class GeneratorRunner(_RunnerBase):
     def __init__(self, module, cfg=None):
         super().__init__(module, cfg)
         self.head_mode = os.environ.get("NIRGAN_B200_HEAD", "tapgemm")     # inference head: 'tapgemm' | 'direct'
+        self._side_streams: list = []
 
     def _convs(self):
         m = self.module.model
@@ -117,14 +128,16 @@ class GeneratorRunner(_RunnerBase):
     def _use_tap_head(self) -> bool:
         return self.head_mode == "tapgemm" and self._convs()[0].weight.shape[0] == 64
 
-    def _inference_plan(self, eng, B, Cin, H, W, wrap, inject, stream) -> Plan:
-        key = (B, Cin, H, W, wrap, inject)
+    def _inference_plan(self, eng, B, Cin, H, W, wrap, inject, stream, slot: int = 0) -> Plan:
+        key = (B, Cin, H, W, wrap, inject, slot)
         hit = self._fwd.get(key)
         if hit is not None:
             g, plan = hit
             g.refresh_weights()
             return plan
-        g = self.build_graph(eng, B, H, W, wrap, inject, stream, "g", direct_head=not self._use_tap_head())
+        self.trim(eng)
+        g = self.build_graph(eng, B, H, W, wrap, inject, stream, "g" if slot == 0 else f"g{slot}",
+                             direct_head=not self._use_tap_head())
         plan = g.compile_forward()
         if g.tap_head is None:
             plan.records["out"] = g.units[-1].out_f32
@@ -141,22 +154,38 @@ class GeneratorRunner(_RunnerBase):
         inject = embeds is not None
         chunk = eng.cfg.chunk if eng.cfg.chunk > 0 else Btot
         out = torch.empty(Btot, 1, H, W, dtype=torch.float32, device=x.device)
-        stream = torch.cuda.current_stream(x.device).cuda_stream
+        main = torch.cuda.current_stream(x.device)
         x = x.contiguous().float()
         if inject:
             require_cuda(embeds, "embeds")
             embeds = embeds.contiguous().float()
-        for b0 in range(0, Btot, chunk):
+        nstreams = max(1, min(eng.cfg.streams, (Btot + chunk - 1) // chunk if eng.cfg.chunk > 0 else eng.cfg.streams, Btot))
+        if eng.cfg.chunk <= 0 and nstreams > 1:
+            chunk = (Btot + nstreams - 1) // nstreams
+        if nstreams > 1 and len(self._side_streams) < nstreams - 1:
+            self._side_streams += [torch.cuda.Stream(x.device) for _ in range(nstreams - 1 - len(self._side_streams))]
+        streams = [main] + self._side_streams[:nstreams - 1]
+        # build / refresh every plan on the caller's stream first (weight packing), then fork
+        jobs = []
+        for i, b0 in enumerate(range(0, Btot, chunk)):
             B = min(chunk, Btot - b0)
-            plan = self._inference_plan(eng, B, Cin, H, W, wrap_pad, inject, stream)
-            plan.records["src"].view(B, Cin, H, W).copy_(x[b0:b0 + B])
-            if inject:
-                plan.records["emb"].view(B, 256).copy_(embeds[b0:b0 + B])
-            plan.run(stream)
-            o = plan.records["out"].view(B, 1, H, W)
-            if getattr(self.module, "post_correction", False):
-                o = o * self.module.post_correction_param
-            out[b0:b0 + B].copy_(o)
+            slot = i % nstreams
+            jobs.append((b0, B, slot, self._inference_plan(eng, B, Cin, H, W, wrap_pad, inject, main.cuda_stream, slot)))
+        for st in streams[1:]:
+            st.wait_stream(main)
+        for b0, B, slot, plan in jobs:
+            st = streams[slot]
+            with torch.cuda.stream(st):
+                plan.records["src"].view(B, Cin, H, W).copy_(x[b0:b0 + B])
+                if inject:
+                    plan.records["emb"].view(B, 256).copy_(embeds[b0:b0 + B])
+                plan.run(st.cuda_stream)
+                o = plan.records["out"].view(B, 1, H, W)
+                if getattr(self.module, "post_correction", False):
+                    o = o * self.module.post_correction_param
+                out[b0:b0 + B].copy_(o)
+        for st in streams[1:]:
+            main.wait_stream(st)
         self.last_plan = plan
         return out
 
@@ -170,6 +199,7 @@ class GeneratorRunner(_RunnerBase):
         key = (B, Cin, H, W, wrap_pad, inject)
         ctx = self._train.get(key)
         if ctx is None:
+            self.trim(eng)
             g = self.build_graph(eng, B, H, W, wrap_pad, inject, stream, "gt", direct_head=not self._use_tap_head())
             fwd = g.compile_forward()
             if g.tap_head is None:

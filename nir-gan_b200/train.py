@@ -71,6 +71,7 @@ class GeneratorFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, runner, wrap_pad, x, embeds, *params):
         c = runner.train_context(x, embeds, wrap_pad)
+        runner._live += 1               # buffers of this context must survive until its backward (see _RunnerBase.trim)
         B, Cin, H, W = c["geom"]
         st = _stream(x)
         fwd = c["fwd"]
@@ -90,6 +91,7 @@ class GeneratorFunction(torch.autograd.Function):
     def backward(ctx, dout):
         c, module, runner = ctx.c, ctx.module, ctx.runner
         g, bwd = c["graph"], c["bwd"]
+        runner._live = max(0, runner._live - 1)
         st = _stream(dout)
         c["dout"].view_as(dout).copy_(dout.float())
         inj = bwd.records.get("inject")
@@ -129,6 +131,8 @@ class DiscriminatorFunction(torch.autograd.Function):
     def forward(ctx, module, runner, x, *params):
         need_dw = any(p.requires_grad for p in params)
         need_dx = x.requires_grad
+        if runner._live == 0 and runner._engine is not None:
+            runner.trim(runner._engine)
         slot = runner._live
         if slot >= 8:
             raise RuntimeError("nirgan_b200: 8 discriminator forwards are waiting for their backward; call "
