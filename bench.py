@@ -147,7 +147,8 @@ def main():
     ap.add_argument("--conv", default=os.environ.get("NIRGAN_B200_IMPL", "tc"), choices=["tc", "simt"])
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("NIRGAN_B200_CHUNK", "0")))
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("NIRGAN_B200_STREAMS", "1")))
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("NIRGAN_B200_STREAMS", "0")),
+                    help="batch slices run concurrently on separate CUDA streams (0 = engine default: 2 for >= 32 tiles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
@@ -242,6 +243,15 @@ def main():
     ms = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(step_e2e, args.steps, 3)
+    # diagnostic: the host link alone (one H2D of a step's tiles from pinned memory), to read e2e against
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        xd[0].copy_(x_host, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize(dev)
+    h2d_gbs = 3 * x_host.numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9
 
     # ---- per-kernel device times over the same steps (CUDA events on the launching stream) ----
     runner = net._runner
@@ -272,6 +282,19 @@ def main():
     achieved = res_flop / (res_ms * 1e-3) / 1e12
     share = sum(op_ms[i] for i in res_idx) / sum(op_ms.values())
 
+    # HBM-bound companion: the fused InstanceNorm-apply launches; algorithmic bytes from their own arguments
+    # (read y [+ residual], write the haloed output; 16-bit elements) -- DESIGN.md section 3.3
+    esz = 4 if args.precision == "fp32" else 2
+    ap_bytes, ap_ms = 0.0, 0.0
+    for i, (fn, a, name) in enumerate(plan.ops):
+        if name != "ng_in_apply":
+            continue
+        _, _, b_, h_, w_, c_ = a[:6]
+        res_, opad = a[9], a[15]
+        ap_bytes += b_ * c_ * esz * (h_ * w_ * (2 if res_ else 1) + (h_ + 2 * opad) * (w_ + 2 * opad))
+        ap_ms += op_ms[i]
+    hbm_achieved = ap_bytes / (ap_ms * 1e-3) / 1e9 if ap_ms > 0 else 0.0
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -291,18 +314,26 @@ def main():
                                f"{B}x3x{TILE}x{TILE} tiles + {B}x256 random embeddings per GPU, random-init weights",
                    "global_batch": B * world, "tile": TILE, "parallelism": f"tile-sharded x{world}, no collective",
                    "conv_impl": args.conv, "operands": args.precision + " operands, fp32 accumulate (TMEM)",
-                   "chunk": Bc,
+                   "chunk": Bc, "streams": B // Bc if args.chunk <= 0 else args.streams,
                    "l2": "per-step activation working set (~%.1f GB) exceeds the 126 MB L2; no explicit flush" % (
                        runner._engine.buffers.bytes() / 1e9)},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + e_host.numel() * 4,
-                "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
+                "h2d_link_gbs_measured": h2d_gbs,
+                "pipelining": "double-buffered H2D / D2H on copy streams overlap the kernels of neighbouring steps"},
         "gpu_launches": plan.launches * (B // Bc) * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel<256,64> (ResnetBlock 3x3, 256->256)",
                      "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tf_sustained"], "traffic": None,
+                     "frac": achieved / pk["tf_sustained"],
+                     # dram__bytes_read+write of this kernel from profiles/r1c_inference.md (ncu --set full, B=64 launch:
+                     # 144.0 + 100.0 MB; the kernel's traffic is linear in the tiles per launch)
+                     "traffic": 244.0e6 * Bc / 64.0,
                      "ms_per_launch": res_ms, "flop_per_launch": res_flop, "share_of_step": share,
                      "peak_source": pk["src"] + " (sustained bf16; fp16/bf16 share one tcgen05 rate)"},
+        "roofline_hbm": {"bound": "hbm", "kernel": "in_apply_kernel (InstanceNorm + inject + act + residual + halo; all launches of a step)",
+                         "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / pk["hbm_gbs"],
+                         "bytes_per_step_slice": ap_bytes, "ms_per_step_slice": ap_ms, "peak_source": pk["src"]},
         "model_tflops": value * gflop_tile / 1e3,
         "model_frac_of_sustained_peak": value * gflop_tile / 1e3 / pk["tf_sustained"],
         "op_ms": {k: round(sum(v), 4) for k, v in by_name.items()},

@@ -467,7 +467,10 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
       int e = check_cuda(cudaMemsetAsync(de_map, 0, (size_t)B * H * W * sizeof(float), st), "in_bwd memset de");
       if (e) return e;
     }
-    a.ppb = pstep * 64;            // long blocks: fewer global atomics on the [B][C][2] sums
+    // long blocks mean fewer global atomics on the [B][C][2] sums, but the grid must still fill the GPU
+    int mult = 64;
+    while (mult > 8 && (long long)B * ((H * W + pstep * mult - 1) / (pstep * mult)) < 4ll * num_sms()) mult >>= 1;
+    a.ppb = pstep * mult;
     dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)B);
     DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)C * 2 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
                                            inject_e, inject_scale, sums_scratch, dscale, de_map, nullptr, nullptr)));

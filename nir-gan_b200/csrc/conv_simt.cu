@@ -189,42 +189,63 @@ wgrad_simt_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, c
 }
 
 // Weight gradient of a single-real-output-channel convolution (PatchGAN last layer, stored Cout = 16 with channel 0
-// real): dw[tap][0][k] = sum_px dy[px][0] * x[px + tap][k].  grid = (taps, pixel splits); a thread owns channels
-// k = threadIdx.x + 256*j; the x reads of a warp are contiguous.  Memory-bound (x is re-read per tap from L2).
-template <typename T, int KPT>
+// real): dw[tap][0][k] = sum_px dy[px][0] * x[px + tap][k].  grid = (taps, pixel splits).  Thread t owns the 8-channel
+// group cg = t mod Cin/8 (one 16-byte load per pixel) and the pixel lane pl = t / (Cin/8); lanes walk the split's
+// pixels with stride `lanes`, four loads in flight.  Memory-bound (x is re-read per tap from L2).
+template <typename T>
 __global__ void __launch_bounds__(256)
 wgrad_cout1_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, const T* __restrict__ dy,
                    float* __restrict__ dw, int pix_per_split) {
   const int tp = blockIdx.x, sp = blockIdx.y;
   int phase = 0;
   while (tp >= g.phase_tap0[phase + 1]) ++phase;
+  const int C8 = g.Cin >> 3;
+  const int lanes = 256 / C8;                       // C8 divides 256 (checked by the launcher)
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8;
   const long long npix = (long long)g.B * g.VH * g.VW;
   const long long p0 = (long long)sp * pix_per_split, p1 = min(npix, p0 + pix_per_split);
-  float acc[KPT];
+  float acc[8];
 #pragma unroll
-  for (int j = 0; j < KPT; ++j) acc[j] = 0.f;
-  int vj = (int)(p0 % g.VW);
-  long long r = p0 / g.VW;
-  int vi = (int)(r % g.VH), n = (int)(r / g.VH);
-  for (long long p = p0; p < p1; ++p) {
-    const int oy = g.OS * vi + g.phase_oy[phase], ox = g.OS * vj + g.phase_ox[phase];
-    const int by = g.S * vi + g.taps[tp].dy, bx = g.S * vj + g.taps[tp].dx;
-    if (oy < g.Hout && ox < g.Wout && by >= 0 && by < g.Hb && bx >= 0 && bx < g.Wb) {
-      const float d = to_f32<T>(dy[(((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout]);
-      const T* xp = x + (((size_t)n * g.Hb + by) * g.Wb + bx) * g.Cin;
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  constexpr int U = 4;
+  for (long long pb = p0 + pl; pb < p1; pb += (long long)lanes * U) {
+    float d[U];
+    float xv[U][8];
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        const int k = threadIdx.x + 256 * j;
-        if (k < g.Cin) acc[j] = fmaf(d, to_f32<T>(xp[k]), acc[j]);
+    for (int u = 0; u < U; ++u) {
+      const long long p = pb + (long long)u * lanes;
+      d[u] = 0.f;
+      if (p < p1) {
+        const int vj = (int)(p % g.VW);
+        const long long r = p / g.VW;
+        const int vi = (int)(r % g.VH), n = (int)(r / g.VH);
+        const int oy = g.OS * vi + g.phase_oy[phase], ox = g.OS * vj + g.phase_ox[phase];
+        const int by = g.S * vi + g.taps[tp].dy, bx = g.S * vj + g.taps[tp].dx;
+        if (oy < g.Hout && ox < g.Wout && by >= 0 && by < g.Hb && bx >= 0 && bx < g.Wb) {
+          d[u] = to_f32<T>(dy[(((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout]);
+          const T* xp = x + (((size_t)n * g.Hb + by) * g.Wb + bx) * g.Cin + cg * 8;
+          if constexpr (sizeof(T) == 2) {
+            const uint4 v = *reinterpret_cast<const uint4*>(xp);
+            const float2 a0 = unpack2<T>(v.x), a1 = unpack2<T>(v.y), a2 = unpack2<T>(v.z), a3 = unpack2<T>(v.w);
+            xv[u][0] = a0.x; xv[u][1] = a0.y; xv[u][2] = a1.x; xv[u][3] = a1.y;
+            xv[u][4] = a2.x; xv[u][5] = a2.y; xv[u][6] = a3.x; xv[u][7] = a3.y;
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xv[u][k] = xp[k];
+          }
+        }
       }
     }
-    if (++vj == g.VW) { vj = 0; if (++vi == g.VH) { vi = 0; ++n; } }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (d[u] != 0.f) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(d[u], xv[u][k], acc[k]);
+      }
+    }
   }
 #pragma unroll
-  for (int j = 0; j < KPT; ++j) {
-    const int k = threadIdx.x + 256 * j;
-    if (k < g.Cin) atomicAdd(&dw[(size_t)g.taps[tp].wrow * g.Cin + k], acc[j]);
-  }
+  for (int k = 0; k < 8; ++k) atomicAdd(&dw[(size_t)g.taps[tp].wrow * g.Cin + cg * 8 + k], acc[k]);
 }
 
 template <typename T>
@@ -249,14 +270,13 @@ static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, cud
   const size_t wbytes = (size_t)a.KH * a.KW * g.Cout * g.Cin * sizeof(float);
   int e = check_cuda(cudaMemsetAsync(dw, 0, wbytes, st), "wgrad memset");
   if (e) return e;
-  if (g.Cout <= 16 && g.Cin <= 1024 && a.epilogue == NG_EPI_HEAD) {
+  const int c8 = g.Cin / 8;
+  if (g.Cout <= 16 && a.epilogue == NG_EPI_HEAD && g.Cin % 8 == 0 && c8 <= 256 && 256 % c8 == 0) {
     // single real output channel (the caller's dY holds zeros in the padding channels)
-    long long want = npix / 512; if (want < 1) want = 1; if (want > 64) want = 64;
+    long long want = npix / 1024; if (want < 1) want = 1; if (want > 64) want = 64;
     const int pps1 = (int)((npix + want - 1) / want);
     dim3 grid(g.ntaps, (unsigned)((npix + pps1 - 1) / pps1));
-    if (g.Cin <= 256) wgrad_cout1_kernel<T, 1><<<grid, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, pps1);
-    else if (g.Cin <= 512) wgrad_cout1_kernel<T, 2><<<grid, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, pps1);
-    else wgrad_cout1_kernel<T, 4><<<grid, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, pps1);
+    wgrad_cout1_kernel<T><<<grid, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, pps1);
     NG_LAUNCH_CHECK("wgrad_cout1_kernel");
     return NG_OK;
   }

@@ -34,25 +34,36 @@ struct WgParams {
   float* partials;            // [splits][ntaps][Cout][Cin]
 };
 
-template <int BN>
+// NT = taps handled per pipeline stage.  NT == 1: work unit = (split, tap, n tile), two accumulators (epilogue of one
+// unit overlaps the MMAs of the next).  NT == ntaps ("tap-inner", needs NT*BN <= 512 TMEM columns): work unit =
+// (split, n tile); a stage holds the dY tile once plus the X tile of every tap, and each tap accumulates into its own
+// BN-column TMEM slice -- for thin layers (PatchGAN input layer: 16 taps x 16 channels; generator stem: 7 x 64) this cuts
+// the L2 -> shared-memory traffic of the dY operand by NT.
+template <int BN, int NT>
 struct WgCfg {
   static constexpr int A_BYTES = 2 * WG_SLAB;
-  // X operand: BN/64 slabs of [64 px][128 B] (128-byte swizzle), or for BN == 16 one slab of [64 px][32 B] (32-byte swizzle)
-  static constexpr int B_BYTES = BN >= 64 ? (BN / 64) * WG_SLAB : WG_PIXELS * 32;
+  // X operand of one tap: BN/64 slabs of [64 px][128 B] (128-byte swizzle), or for BN == 16 one slab of [64 px][32 B]
+  static constexpr int B_TAP_BYTES = BN >= 64 ? (BN / 64) * WG_SLAB : WG_PIXELS * 32;
+  static constexpr int B_BYTES = NT * B_TAP_BYTES;
   static constexpr int B_LOADS = BN >= 64 ? BN / 64 : 1;
   static constexpr int B_KSTEP = BN >= 64 ? 2048 : 512;            // bytes per 16 pixel rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // 32 / 128 / 256 / 512
+  static constexpr int NACC = NT == 1 ? 2 : 1;
+  static constexpr int ACC_COLS = NACC * NT * BN;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static_assert(ACC_COLS <= 512, "accumulators exceed tensor memory");
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
-template <int BN>
+template <int BN, int NT>
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ WgParams p) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, NT>;
+  constexpr int NACC = Cfg::NACC;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -83,11 +94,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int per_split = g.ntaps * p.n_tiles;
+  const int per_split = (NT == 1 ? g.ntaps : 1) * p.n_tiles;
   auto decode = [&](int u, int& split, int& tap, int& nt, int& pt0, int& pt1) {
     split = u / per_split;
     const int r = u - split * per_split;
-    tap = r / p.n_tiles;
+    tap = r / p.n_tiles;                    // NT > 1: always 0 (the taps are walked inside the unit)
     nt = r - tap * p.n_tiles;
     pt0 = split * p.pps;
     pt1 = min(p.P, pt0 + p.pps);
@@ -117,9 +128,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             tma_load_4d(&tmY, fb, sa + j * WG_SLAB, nt * 128 + 64 * j, g.OS * vj0 + ox0, g.OS * vi0 + oy0, n);
+          if constexpr (NT == 1) {
 #pragma unroll
-          for (int j = 0; j < Cfg::B_LOADS; ++j)
-            tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + j * WG_SLAB, 64 * j, g.S * vj0 + dx, g.S * vi0 + dy, n);
+            for (int j = 0; j < Cfg::B_LOADS; ++j)
+              tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + j * WG_SLAB, 64 * j, g.S * vj0 + dx, g.S * vi0 + dy, n);
+          } else {
+#pragma unroll 1
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+              for (int j = 0; j < Cfg::B_LOADS; ++j)
+                tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES + j * WG_SLAB, 64 * j,
+                            g.S * vj0 + g.taps[t].dx, g.S * vi0 + g.taps[t].dy, n);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -138,23 +158,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         const int kiters = pt1 - pt0;
         mbar_wait(smem_u32(&tempty_bar[as]), as_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_c = tmem_base + as * BN;
+        const uint32_t tmem_c = tmem_base + as * (NT * BN);
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = make_mnmajor_desc(sa, WG_SLAB, 1024);
-          const uint64_t bdesc = BN >= 64 ? make_mnmajor_desc(sa + Cfg::A_BYTES, WG_SLAB, 1024)
-                                          : make_mnmajor_desc_sw32(sa + Cfg::A_BYTES, 256);
+#pragma unroll 1
+          for (int t = 0; t < NT; ++t) {
+            const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES;
+            const uint64_t bdesc = BN >= 64 ? make_mnmajor_desc(sb, WG_SLAB, 1024) : make_mnmajor_desc_sw32(sb, 256);
 #pragma unroll
-          for (int k = 0; k < WG_PIXELS / 16; ++k)     // 16 pixel rows per K step
-            umma_f16(tmem_c, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (Cfg::B_KSTEP >> 4)), idesc,
-                     (uint32_t)((kit | k) != 0));
+            for (int k = 0; k < WG_PIXELS / 16; ++k)     // 16 pixel rows per K step
+              umma_f16(tmem_c + t * BN, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (Cfg::B_KSTEP >> 4)),
+                       idesc, (uint32_t)((kit | k) != 0));
+          }
           umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&tfull_bar[as]));
-        if (++as == 2) { as = 0; as_phase ^= 1; }
+        if (++as == NACC) { as = 0; as_phase ^= 1; }
       }
     }
     __syncwarp();
@@ -169,38 +192,42 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       const int n = nt * 128 + row;
       mbar_wait(smem_u32(&tfull_bar[as]), as_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-      // packed weight-gradient row of this tap: wrow = (kh*KW + kw) * Cout (phased geometries enumerate taps by phase)
-      float* dst = p.partials + ((size_t)split * g.ntaps * g.Cout + g.taps[tap].wrow + (n < g.Cout ? n : 0)) * (size_t)g.Cin;
-      if constexpr (BN >= 32) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c * 32, r);
+      for (int t = 0; t < NT; ++t) {
+        const uint32_t taddr = tmem_base + as * (NT * BN) + t * BN + ((uint32_t)(q * 32) << 16);
+        // packed weight-gradient row of this tap: wrow = (kh*KW + kw) * Cout (phased geometries enumerate taps by phase)
+        const int tp = NT == 1 ? tap : t;
+        float* dst = p.partials + ((size_t)split * g.ntaps * g.Cout + g.taps[tp].wrow + (n < g.Cout ? n : 0)) * (size_t)g.Cin;
+        if constexpr (BN >= 32) {
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c * 32, r);
+            tmem_ld_wait();
+            if (n < g.Cout) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(dst + c * 32 + 4 * k) =
+                    make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
+                                __uint_as_float(r[4 * k + 3]));
+            }
+          }
+        } else {
+          uint32_t r[16];
+          tmem_ld16(taddr, r);
           tmem_ld_wait();
           if (n < g.Cout) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              *reinterpret_cast<float4*>(dst + c * 32 + 4 * k) =
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<float4*>(dst + 4 * k) =
                   make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
                               __uint_as_float(r[4 * k + 3]));
           }
         }
-      } else {
-        uint32_t r[16];
-        tmem_ld16(taddr, r);
-        tmem_ld_wait();
-        if (n < g.Cout) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<float4*>(dst + 4 * k) =
-                make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]),
-                            __uint_as_float(r[4 * k + 3]));
-        }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&tempty_bar[as]));
-      if (++as == 2) { as = 0; as_phase ^= 1; }
+      if (++as == NACC) { as = 0; as_phase ^= 1; }
     }
   }
 
@@ -230,7 +257,16 @@ wgrad_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, f
 // ------------------------------------------------------------------------------------------------
 struct WgPlan {
   int BH, BW, patches_y, patches_x, P, n_tiles, splits, pps, bn;
+  int nt;       // taps per stage: 1, or ntaps for the tap-inner variant
 };
+
+// tap-inner instantiations: (Cin 16, 16 taps) = PatchGAN input layer, (Cin 64, 7 taps) = row-merged generator stem
+static int tap_inner_for(const ConvGeom& g) {
+  if (g.nphase != 1) return 1;
+  if (g.Cin == 16 && g.ntaps == 16) return 16;
+  if (g.Cin == 64 && g.ntaps == 7) return 7;
+  return 1;
+}
 
 static bool wgrad_tc_supported(const ng_conv_args& a) {
   if (a.dtype != NG_F16 && a.dtype != NG_BF16) return false;
@@ -254,9 +290,13 @@ static void wgrad_plan(const ng_conv_args& a, const ConvGeom& g, WgPlan& w) {
   w.P = g.B * w.patches_y * w.patches_x;
   w.n_tiles = (g.Cout + 127) / 128;
   w.bn = g.Cin;
-  const int base = g.ntaps * w.n_tiles, sms = num_sms();
+  w.nt = tap_inner_for(g);
+  const int base = (w.nt == 1 ? g.ntaps : 1) * w.n_tiles, sms = num_sms();
   int best_s = 1; double best_eff = -1.0;
-  const int max_s = w.P < 64 ? w.P : 64;
+  int max_s = 4 * sms / base;                   // enough splits to fill the GPU even for a single-tap, single-tile problem
+  if (max_s < 64) max_s = 64;
+  if (max_s > 256) max_s = 256;
+  if (max_s > w.P) max_s = w.P;
   for (int s = 1; s <= max_s; ++s) {
     const long long units = (long long)base * s;
     const long long waves = (units + sms - 1) / sms;
@@ -275,10 +315,10 @@ long long wgrad_tc_workspace_bytes(const ng_conv_args& a, const ConvGeom& g) {
   return (long long)w.splits * g.ntaps * g.Cout * g.Cin * (long long)sizeof(float);
 }
 
-template <int BN>
+template <int BN, int NT>
 static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPlan& w, float* dw, void* workspace,
                            cudaStream_t st) {
-  using Cfg = WgCfg<BN>;
+  using Cfg = WgCfg<BN, NT>;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   int r = get_tensor_map_encoder(&encode);
   if (r) return r;
@@ -287,7 +327,7 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
   p.g = g;
   p.BH = w.BH; p.BW = w.BW; p.patches_y = w.patches_y; p.patches_x = w.patches_x; p.P = w.P;
   p.n_tiles = w.n_tiles; p.splits = w.splits; p.pps = w.pps;
-  p.total_units = w.splits * g.ntaps * w.n_tiles;
+  p.total_units = w.splits * (NT == 1 ? g.ntaps : 1) * w.n_tiles;
   p.bf16 = a.dtype == NG_BF16;
   p.partials = w.splits == 1 ? dw : reinterpret_cast<float*>(workspace);
 
@@ -316,14 +356,14 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
   }
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    int e = check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int e = check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES), "cudaFuncSetAttribute(wgrad_tc)");
     if (e) return e;
     attr_set = true;
   }
   const int sms = num_sms();
   const int grid = p.total_units < sms ? p.total_units : sms;
-  wgrad_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmY, tmX, p);
+  wgrad_tc_kernel<BN, NT><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmY, tmX, p);
   NG_LAUNCH_CHECK("wgrad_tc_kernel");
   if (w.splits > 1) {
     const long long n4 = (long long)g.ntaps * g.Cout * g.Cin / 4;
@@ -349,11 +389,13 @@ int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspac
                  ((uintptr_t)workspace & 15) == 0,
              NG_E_ALIGN, "wgrad_tc: tensors must be 16-byte aligned");
   *handled = true;
+  if (w.nt == 16 && g.Cin == 16) return launch_wgrad_tc<16, 16>(a, g, w, dw, workspace, st);
+  if (w.nt == 7 && g.Cin == 64) return launch_wgrad_tc<64, 7>(a, g, w, dw, workspace, st);
   switch (g.Cin) {
-    case 16:  return launch_wgrad_tc<16>(a, g, w, dw, workspace, st);
-    case 64:  return launch_wgrad_tc<64>(a, g, w, dw, workspace, st);
-    case 128: return launch_wgrad_tc<128>(a, g, w, dw, workspace, st);
-    case 256: return launch_wgrad_tc<256>(a, g, w, dw, workspace, st);
+    case 16:  return launch_wgrad_tc<16, 1>(a, g, w, dw, workspace, st);
+    case 64:  return launch_wgrad_tc<64, 1>(a, g, w, dw, workspace, st);
+    case 128: return launch_wgrad_tc<128, 1>(a, g, w, dw, workspace, st);
+    case 256: return launch_wgrad_tc<256, 1>(a, g, w, dw, workspace, st);
   }
   *handled = false;
   return NG_OK;

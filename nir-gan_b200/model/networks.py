@@ -125,6 +125,16 @@ class _B200Module(nn.Module):
         if getattr(self, "_runner", None) is not None:
             self._runner._live = 0
 
+    @torch.no_grad()
+    def forward_shared(self, input, embeds=None, wrap_pad: int = 0):
+        """Generator forward WITHOUT an autograd graph that nevertheless keeps its activations: a following
+        grad-enabled forward on the same input tensor with unchanged weights reuses them instead of recomputing
+        (the D pass and the G pass of one training step see the same batch, model/pix2pix.py:177-180)."""
+        require_cuda(input, "generator input")
+        c = self._get_runner(GeneratorRunner).train_forward(input, embeds, wrap_pad)
+        B, _, H, W = c["geom"]
+        return c["fwd"].records["out"].view(B, 1, H, W).clone()
+
     def _get_runner(self, factory):
         if getattr(self, "_runner", None) is None:
             object.__setattr__(self, "_runner", factory(self, self.b200_config))

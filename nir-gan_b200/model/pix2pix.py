@@ -40,6 +40,10 @@ class Px2Px(nn.Module):
                                       o.init_gain)
         self.criterionGAN = networks.GANLoss(o.gan_mode)
         self.inject = self.satclip and style == "inject"
+        # Px2Px_PL.training_step runs G twice per batch (once per optimizer) with identical results;
+        # NIRGAN_B200_REUSE_G=0 restores the reference-faithful double evaluation
+        import os
+        self.reuse_g_forward = os.environ.get("NIRGAN_B200_REUSE_G", "1") != "0"
 
     # pix2pix.py:88-110 -- the pad / crop is fused into the first / last kernel (wrap_pad)
     def forward(self, input, embeds=None, use_padding=True):
@@ -83,7 +87,12 @@ class Px2Px(nn.Module):
         if optimizer_idx == 0:      # discriminator, pix2pix.py:195-212
             self.netD.reset_training_slots()
             with torch.no_grad():    # fake_AB.detach(): G needs no graph in the D pass
-                pred = self.forward(rgb, embeds)
+                if self.reuse_g_forward:
+                    # the G pass of this step evaluates G on the same batch with the same weights: keep the activations
+                    pad = self.config.Data.padding_amount if self.config.Data.padding else 0
+                    pred = self.netG.forward_shared(rgb, embeds if self.inject else None, wrap_pad=pad)
+                else:
+                    pred = self.forward(rgb, embeds)
             pred_fake = self.netD(torch.cat((rgb, pred), 1))
             loss_D_fake = self.criterionGAN(pred_fake, False)
             pred_real = self.netD(torch.cat((rgb, nir), 1))

@@ -26,6 +26,7 @@ class B200Adam(torch.optim.Optimizer):
             if bool(bad):
                 self.skipped_steps += 1
                 return loss
+        from . import engine
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
@@ -40,11 +41,11 @@ class B200Adam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32)
                 st["step"] += 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                p._b200_epoch = engine.WEIGHT_EPOCH[0] + 1      # this parameter's storage changes in this step
                 L.call("ng_adam_step", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(),
                        st["exp_avg_sq"].data_ptr(), p.numel(), float(group["lr"]), float(b1), float(b2),
                        float(group["eps"]), int(st["step"]), float(grad_scale),
                        torch.cuda.current_stream(p.device).cuda_stream)
-        from . import engine
         engine.WEIGHT_EPOCH[0] += 1     # masters changed in place: packed low-precision shadows must be refreshed
         return loss
 

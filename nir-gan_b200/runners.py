@@ -159,7 +159,8 @@ class GeneratorRunner(_RunnerBase):
         if inject:
             require_cuda(embeds, "embeds")
             embeds = embeds.contiguous().float()
-        nstreams = max(1, min(eng.cfg.streams, (Btot + chunk - 1) // chunk if eng.cfg.chunk > 0 else eng.cfg.streams, Btot))
+        want = eng.cfg.streams if eng.cfg.streams > 0 else (2 if Btot >= 32 else 1)
+        nstreams = max(1, min(want, (Btot + chunk - 1) // chunk if eng.cfg.chunk > 0 else want, Btot))
         if eng.cfg.chunk <= 0 and nstreams > 1:
             chunk = (Btot + nstreams - 1) // nstreams
         if nstreams > 1 and len(self._side_streams) < nstreams - 1:
@@ -190,6 +191,27 @@ class GeneratorRunner(_RunnerBase):
         return out
 
     # ---- training -------------------------------------------------------------------------------------
+    def weight_signature(self):
+        ps = list(self.module.parameters())
+        return (max(getattr(p, "_b200_epoch", 0) for p in ps), sum(p._version for p in ps))
+
+    def train_forward(self, x: torch.Tensor, embeds, wrap_pad: int) -> dict:
+        """Run the training forward plan (activations kept for the backward) unless the very same input tensors and
+        weights were the last thing this context computed: Px2Px_PL.training_step evaluates G on the same batch for
+        both optimizers (model/pix2pix.py:177-180) with identical results, so the second evaluation is reused."""
+        c = self.train_context(x, embeds, wrap_pad)
+        key = (x.data_ptr(), x._version, tuple(x.shape),
+               None if embeds is None else (embeds.data_ptr(), embeds._version), self.weight_signature())
+        if c.get("fresh") != key:
+            B, Cin, H, W = c["geom"]
+            fwd = c["fwd"]
+            fwd.records["src"].view(B, Cin, H, W).copy_(x.detach().float())
+            if embeds is not None:
+                fwd.records["emb"].view(B, 256).copy_(embeds.detach().float())
+            fwd.run(torch.cuda.current_stream(x.device).cuda_stream)
+            c["fresh"] = key
+        return c
+
     def train_context(self, x: torch.Tensor, embeds, wrap_pad: int) -> dict:
         """Graph + forward/backward plans with dedicated buffers (activations must survive until backward)."""
         eng = self.engine(x.device)

@@ -70,15 +70,10 @@ class GeneratorFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, runner, wrap_pad, x, embeds, *params):
-        c = runner.train_context(x, embeds, wrap_pad)
+        c = runner.train_forward(x, embeds, wrap_pad)
         runner._live += 1               # buffers of this context must survive until its backward (see _RunnerBase.trim)
         B, Cin, H, W = c["geom"]
-        st = _stream(x)
         fwd = c["fwd"]
-        fwd.records["src"].view(B, Cin, H, W).copy_(x.detach().float())
-        if embeds is not None:
-            fwd.records["emb"].view(B, 256).copy_(embeds.detach().float())
-        fwd.run(st)
         ctx.c, ctx.module, ctx.runner = c, module, runner
         ctx.params = params
         ctx.has_embeds = embeds is not None
@@ -92,6 +87,7 @@ class GeneratorFunction(torch.autograd.Function):
         c, module, runner = ctx.c, ctx.module, ctx.runner
         g, bwd = c["graph"], c["bwd"]
         runner._live = max(0, runner._live - 1)
+        c["fresh"] = None               # a backward may follow only the forward that produced these activations
         st = _stream(dout)
         c["dout"].view_as(dout).copy_(dout.float())
         inj = bwd.records.get("inject")

@@ -255,3 +255,49 @@ def test_data_parallel_gradients_commute_with_batch_sharding():
             if k.endswith("weight"):
                 avg = 0.5 * (a[k] + b[k])
                 assert _relerr(avg, full[k]) <= 2e-3, (opt_idx, k, _relerr(avg, full[k]))
+
+
+def test_g_forward_reuse_matches_double_evaluation():
+    """The G pass reusing the D pass's generator forward (same batch, same weights) gives the same loss and gradients
+    as the reference-faithful double evaluation (model/pix2pix.py:177-180), and the cached activations are dropped
+    as soon as the generator's weights change."""
+    import nirgan_oracle as O
+    from nirgan_b200.model.pix2pix import Px2Px
+    sd_g = O.random_state_dict(O.generator_param_shapes(), seed=51)
+    sd_d = O.random_state_dict(O.discriminator_param_shapes(), seed=52)
+    gen = torch.Generator().manual_seed(9)
+    rgb = (1.0 + torch.rand(2, 3, 64, 64, generator=gen)).cuda()
+    nir = torch.rand(2, 1, 64, 64, generator=gen).cuda()
+    batch = {"rgb": rgb, "nir": nir}
+    model = Px2Px(_cfg())
+    _load(model, sd_g, sd_d)
+    model = model.cuda().train()
+    model.netG.configure_b200(precision="fp16", impl="tc")
+    model.netD.configure_b200(precision="fp16", impl="tc")
+    opt_d, opt_g = model.configure_optimizers()
+    res = {}
+    for reuse in (True, False):          # no optimizer step in between: both see identical weights
+        model.reuse_g_forward = reuse
+        for p in model.parameters():
+            p.grad = None
+        model.training_step(batch, 0, 0).backward()
+        for p in model.netD.parameters():
+            p.grad = None
+        lg = model.training_step(batch, 0, 1)
+        lg.backward()
+        res[reuse] = (lg.detach().clone(), [p.grad.clone() for p in model.netG.parameters() if p.grad is not None])
+    assert torch.equal(res[True][0], res[False][0])                      # identical forward values
+    for x, y in zip(res[True][1], res[False][1]):                        # gradients: up to fp32 atomics ordering
+        if float(y.norm()) > 0:
+            assert _relerr(x, y) <= 2e-3, _relerr(x, y)
+    # weights change -> the next shared forward recomputes and equals the plain inference forward bit for bit
+    model.reuse_g_forward = True
+    before = model.netG.forward_shared(rgb, None, wrap_pad=10)
+    again = model.netG.forward_shared(rgb, None, wrap_pad=10)
+    assert torch.equal(before, again)
+    opt_g.step()
+    after = model.netG.forward_shared(rgb, None, wrap_pad=10)
+    assert not torch.equal(before, after)
+    with torch.no_grad():
+        plain = model.forward(rgb)
+    assert torch.equal(after, plain)

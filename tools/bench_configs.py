@@ -141,7 +141,7 @@ def main():
         if rank == 0:
             timed = seq[args.warmup:]
             samples = B * world * len(timed)
-            gflop = sum(505.8 * (s / 256.0) ** 2 for s in timed) * B * world
+            gflop = sum((391.6 if model.reuse_g_forward else 505.8) * (s / 256.0) ** 2 for s in timed) * B * world
             print(json.dumps({"workload": f"configs[4]: data-parallel Pix2Pix training, batch {B}/GPU, resolutions {timed}, "
                                           "NCCL all-reduce of D and G gradients each step",
                               "metric": "train_samples_per_sec", "value": samples / ms * 1e3, "unit": "samples/s",

@@ -88,11 +88,13 @@ def main():
         if os.path.isdir(out_dir):
             with open(os.path.join(out_dir, "train_op_times.json"), "w") as f:
                 json.dump([{"plan": tag, "op": name, "label": lab, "ms": round(t, 4)} for (tag, name, lab), t in rows], f, indent=0)
-    # reference-faithful op count: 2 G forwards per batch (pix2pix.py:177-180 runs G in both optimizer passes)
-    gflop = 505.8 * (args.tile / 256.0) ** 2
+    # op count per sample: 505.8 GFLOP reference-faithful (2 G forwards per batch, pix2pix.py:177-180) or
+    # 391.6 when the G pass reuses the D pass's forward (the default here; NIRGAN_B200_REUSE_G=0 disables it)
+    gflop = (391.6 if model.reuse_g_forward else 505.8) * (args.tile / 256.0) ** 2
     print(json.dumps({"workload": f"configs[3]: Pix2Pix training step, batch {args.batch}, {args.tile}px, {args.precision}/{args.conv}",
                       "ms_per_step": ms, "samples_per_s": args.batch / ms * 1e3,
-                      "algorithmic_tflops": args.batch * gflop / ms,
+                      "algorithmic_tflops": args.batch * gflop / ms, "gflop_per_sample": gflop,
+                      "g_forward_reused": model.reuse_g_forward,
                       "loss_D": float(ld), "loss_G": float(lg),
                       "mem_gb": torch.cuda.max_memory_allocated() / 1e9,
                       "skipped_steps": [opt_d.skipped_steps, opt_g.skipped_steps]}))

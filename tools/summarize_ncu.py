@@ -68,7 +68,10 @@ WANT = [
 
 
 def rep_table(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(raw)))
     hdr, units = rd[0], rd[1]
     col = {h: i for i, h in enumerate(hdr)}
@@ -104,7 +107,7 @@ def rep_table(path):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--launches")
-    ap.add_argument("--rep")
+    ap.add_argument("--rep", action="append", help=".ncu-rep or its `--page raw --csv` export; may be repeated")
     ap.add_argument("--tag", required=True)
     ap.add_argument("--cmd", default="")
     ap.add_argument("--note", default="")
@@ -118,9 +121,9 @@ def main():
         t, n, tot = launches_table(a.launches)
         md += [f"## Launch list ({n} launches, {tot / 1e3:.2f} ms of kernel time; cold-cache, serialised: compare SHARES)",
                "", f"`ncu --metrics gpu__time_duration.sum --clock-control none` -> `{os.path.basename(a.launches)}`", "", t, ""]
-    if a.rep:
-        md += [f"## `ncu --set full --clock-control none` ({os.path.basename(a.rep)}), mean per launch, grouped by (kernel, grid)",
-               "", rep_table(a.rep), ""]
+    for rep in a.rep or []:
+        md += [f"## `ncu --set full --clock-control none` ({os.path.basename(rep)}), mean per launch, grouped by (kernel, grid)",
+               "", rep_table(rep), ""]
     path = os.path.join(ROOT, "profiles", a.tag + ".md")
     with open(path, "w") as f:
         f.write("\n".join(md))
