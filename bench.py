@@ -134,10 +134,33 @@ def run_reference(args):
                        "note": "CPU oracle port of the reference (pure-Python reference cannot travel); each step is a bounded sample"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = [None]
+
+
+def _quiet_stdout():
+    """stdout must carry exactly one JSON line.  Libraries print there too (NCCL's version banner, the reference's
+    constructor messages), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is written
+    to a saved duplicate of the real stdout."""
+    if _REAL_STDOUT[0] is None:
+        sys.stdout.flush()
+        _REAL_STDOUT[0] = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT[0] is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT[0], data)
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -167,6 +190,10 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        # stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...") off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch
@@ -345,7 +372,7 @@ def main():
     if not args.no_cpu_baseline:
         v, cores, sample = cpu_oracle_tiles_per_sec()
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -113,6 +113,8 @@ class ActBuf:
 
 # when a list, Plan.run records (label, start_event, end_event) per op into it (tools/bench_train.py --profile)
 PROFILE = [None]
+# inference plans are replayed as CUDA graphs (NIRGAN_B200_GRAPH=0 launches every kernel from the host instead)
+GRAPHS = [os.environ.get("NIRGAN_B200_GRAPH", "1") != "0"]
 
 
 class Plan:
@@ -130,6 +132,31 @@ class Plan:
         self.ops.append((fn, args, fn_name))
         self.labels.append(label or fn_name)
         self.launches += launches
+
+    def run_graphed(self, stream: "torch.cuda.Stream"):
+        """Replay the plan as one CUDA graph on `stream` (captured on the second call; the first runs eagerly so that
+        one-off host work -- kernel attributes, TMA descriptor encoder lookup -- happens outside the capture).  All
+        buffers are static and the packed weights are refreshed in place, so the captured graph stays valid."""
+        if PROFILE[0] is not None or not GRAPHS[0]:
+            return self.run(stream.cuda_stream)
+        g = getattr(self, "_graph", None)
+        if g is None:
+            if not getattr(self, "_warm", False):
+                self._warm = True
+                return self.run(stream.cuda_stream)
+            try:
+                g = torch.cuda.CUDAGraph()
+                # captured on torch's private capture stream (the caller's may be the legacy default stream, where
+                # capture is illegal); replay() enqueues the graph on whatever stream is current
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self.run(torch.cuda.current_stream().cuda_stream)
+                self._graph = g
+            except Exception as e:          # capture is an optimisation: fall back to eager launches, loudly, once
+                import warnings
+                warnings.warn(f"nirgan_b200: CUDA graph capture failed ({e}); launching kernels eagerly")
+                GRAPHS[0] = False
+                return self.run(stream.cuda_stream)
+        g.replay()
 
     def run(self, stream_ptr: int):
         if PROFILE[0] is not None:

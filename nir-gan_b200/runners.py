@@ -180,7 +180,7 @@ class GeneratorRunner(_RunnerBase):
                 plan.records["src"].view(B, Cin, H, W).copy_(x[b0:b0 + B])
                 if inject:
                     plan.records["emb"].view(B, 256).copy_(embeds[b0:b0 + B])
-                plan.run(st.cuda_stream)
+                plan.run_graphed(st)
                 o = plan.records["out"].view(B, 1, H, W)
                 if getattr(self.module, "post_correction", False):
                     o = o * self.module.post_correction_param

@@ -40,6 +40,10 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        # stdout carries exactly one JSON line: keep NCCL's banner ("NCCL version ...") off it
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import nirgan_b200  # noqa: F401
