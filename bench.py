@@ -25,6 +25,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# more hardware queues than streams (compute slices + copy streams): no false dependencies between streams
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch  # noqa: E402
 
 TILE = 256

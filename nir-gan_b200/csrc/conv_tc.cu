@@ -42,44 +42,62 @@ struct TcParams {
   float* stat_partials;
 };
 
-template <int BN, int KC>
+// RT ("row taps", generator stem in row-merged form): the taps of a K x 1 stride-1 convolution only shift the patch by
+// whole rows, so the haloed patch (BH + K - 1 rows of RT_BW pixels) is fetched ONCE per tile and every tap's A operand
+// is a descriptor into it (row shifts of RT_BW = 16 pixels are whole 1024-byte swizzle atoms); the K weight slabs stay
+// resident in shared memory for the life of the CTA.  L2 -> SM traffic per tile drops from K x (A + B) to one patch.
+constexpr int RT_BW = 16, RT_BH = 8, RT_KH = 7;
+constexpr int RT_PATCH_ROWS = (RT_BH + RT_KH - 1) * RT_BW;          // 224 pixels
+
+template <int BN, int KC, bool RT = false>
 struct TcCfg {
-  static constexpr int A_BYTES = 128 * KC * 2;
-  static constexpr int B_BYTES = (BN * KC * 2 + 1023) / 1024 * 1024;
+  static constexpr int A_BYTES = RT ? RT_PATCH_ROWS * KC * 2 : 128 * KC * 2;
+  static constexpr int B_BYTES = RT ? 0 : (BN * KC * 2 + 1023) / 1024 * 1024;
+  static constexpr int W_BYTES = RT ? RT_KH * BN * KC * 2 : 0;      // resident weights (RT only)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = BN >= 64 ? 128 * 64 * 2 : 0;      // one 64-channel epilogue pass
-  static constexpr int RED_BYTES = BN >= 64 ? 2048 : 0;              // cross-group stats combine
+  // epilogue: EG groups of four warps drain the accumulator in alternating passes of EB = 32 output channels, each
+  // group with its own 8 KB staging tile, stats scratch and row-offset table (a single warp per scheduler is latency
+  // bound, so two groups nearly halve the drain time of a tile)
+  static constexpr int EG = BN >= 64 ? 2 : 1;
+  static constexpr int EB = 32;
+  static constexpr int THREADS = 64 + 128 * EG;
+  static constexpr int STAGING_BYTES = BN >= 64 ? EG * 128 * EB * 2 : 0;
+  static constexpr int RED_BYTES = BN >= 64 ? EG * 2048 : 0;         // cross-row-group stats combine
+  static constexpr int ROWOFF_BYTES = EG * 1024;
   static constexpr int BUDGET = 222 * 1024;
-  static constexpr int STAGES_RAW = (BUDGET - STAGING_BYTES - RED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (BUDGET - STAGING_BYTES - RED_BYTES - W_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE <= 64 ? 64 : (2 * ACC_STRIDE <= 128 ? 128 : (2 * ACC_STRIDE <= 256 ? 256 : 512));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + RED_BYTES + 1024 /*rowoff*/ + 256 /*barriers*/ +
-                                    1024 /*alignment slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + STAGING_BYTES + RED_BYTES + ROWOFF_BYTES +
+                                    256 /*barriers*/ + 1024 /*alignment slack*/;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
 // CS = thread-block-cluster size.  The CS CTAs of a cluster work on CS different pixel patches that share the same
 // weight slab; each loads 1/CS of every B (weight) stage and multicasts it to all of them, which divides the
 // L2 -> SM weight traffic (the measured limiter of the 128x256 tile) by CS.
-template <int BN, int KC, int CS>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int KC, int CS, bool RT = false>
+__global__ void __launch_bounds__(TcCfg<BN, KC, RT>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams p) {
-  using Cfg = TcCfg<BN, KC>;
+  using Cfg = TcCfg<BN, KC, RT>;
+  static_assert(!RT || (CS == 1 && KC == 64), "row-tap variant: no clusters, 64-channel rows");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* wres = smem + STAGES * Cfg::STAGE_BYTES;            // RT: resident weights [tap][BN][KC]
+  uint8_t* staging = wres + Cfg::W_BYTES;
   float* red = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
   long long* rowoff = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(red) + Cfg::RED_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowoff) + 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowoff) + Cfg::ROWOFF_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* wfull_bar = bars + 2 * STAGES + 4;                  // RT: weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
@@ -89,7 +107,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), CS); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128 * Cfg::EG); }
+    mbar_init(smem_u32(wfull_bar), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -124,10 +143,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      if constexpr (RT) {
+        const uint32_t wb = smem_u32(wfull_bar);
+        mbar_expect_tx(wb, (uint32_t)Cfg::W_BYTES);
+        for (int tp = 0; tp < RT_KH; ++tp)
+          tma_load_2d(&tmB, wb, smem_u32(wres) + tp * (BN * KC * 2), 0, g.taps[tp].wrow);
+      }
       for (int q = cluster_id; q < p.total_groups; q += num_clusters) {
         int cot, ph, n, py, px; bool dummy;
         decode(q, cot, ph, n, py, px, dummy);
         const int i0 = py * p.BH, j0 = px * p.BW;
+        if constexpr (RT) {
+          // one haloed patch per tile: rows i0 + dy0 .. i0 + dy0 + BH + K - 2, columns j0 + dx0 .. + BW - 1
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, (uint32_t)Cfg::A_BYTES);
+          tma_load_4d(&tmA, fb, smem_u32(stage_base + stage * Cfg::STAGE_BYTES), 0, j0 + g.taps[0].dx, i0 + g.taps[0].dy, n);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+        }
         for (int tp = g.phase_tap0[ph]; tp < g.phase_tap0[ph + 1]; ++tp) {
           const int by = g.S * i0 + g.taps[tp].dy, bx = g.S * j0 + g.taps[tp].dx;
           const int brow = g.taps[tp].wrow + cot * BN;
@@ -164,6 +198,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(smem_u32(&tempty_bar[as]), as_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_c = tmem_base + as * Cfg::ACC_STRIDE;
+        if constexpr (RT) {
+          if (q == cluster_id) { mbar_wait(smem_u32(wfull_bar), 0); }      // resident weights (first tile only)
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+#pragma unroll 1
+          for (int tp = 0; tp < RT_KH; ++tp) {
+            // tap tp = the patch shifted down by tp rows of RT_BW pixels (tp * 2048 bytes: whole swizzle atoms)
+            const uint64_t adesc = make_kmajor_desc(sa + tp * (RT_BW * KC * 2), SBO, LAYOUT);
+            const uint64_t bdesc = make_kmajor_desc(smem_u32(wres) + tp * (BN * KC * 2), SBO, LAYOUT);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k)
+              umma_f16(tmem_c, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (uint32_t)((tp | k) != 0));
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(smem_u32(&tfull_bar[as]));
+          if (++as == 2) { as = 0; as_phase ^= 1; }
+          continue;
+        }
         for (int kit = 0; kit < kiters; ++kit) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           tc_fence_after();
@@ -183,10 +237,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5 = group 0, warps 6..9 = group 1) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // accumulator row == TMEM lane
-    const int et = threadIdx.x - 64;        // 0..127 epilogue thread index
+    const int grp = (warp - 2) >> 2;        // epilogue group
+    const int we = (warp - 2) & 3;          // warp within the group
+    const int et = we * 32 + lane;          // 0..127 thread index within the group
     uint32_t as = 0, as_phase = 0;
     for (int q = cluster_id; q < p.total_groups; q += num_clusters) {
       int cot, ph, n, py, px; bool dummy;
@@ -231,22 +287,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
       } else {
-        rowoff[row] = valid ? ((((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout + n0) : -1ll;
-        // The tile is drained in passes of 64 output channels (16 KB of staging) so that the shared memory saved
-        // goes to one more operand pipeline stage.
-        constexpr int EB = 64, PASSES = BN / EB;
+        constexpr int EB = Cfg::EB, EG = Cfg::EG, PASSES = BN / EB;
+        uint8_t* stg = staging + grp * (128 * EB * 2);
+        float* redg = red + grp * 512;
+        long long* rowoffg = rowoff + grp * 128;
+        const uint32_t barid = 1 + grp;
+        rowoffg[row] = valid ? ((((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout + n0) : -1ll;
 #pragma unroll 1
-        for (int ps = 0; ps < PASSES; ++ps) {
-#pragma unroll 1
-          for (int ch = 0; ch < EB / 32; ++ch) {
+        for (int ps = grp; ps < PASSES; ps += EG) {
+          {
             uint32_t r[32];
-            tmem_ld32(taddr + ps * EB + ch * 32, r);
+            tmem_ld32(taddr + ps * EB, r);
             tmem_ld_wait();
+            if (ps + EG >= PASSES) {
+              tc_fence_before();
+              mbar_arrive(smem_u32(&tempty_bar[as]));     // this thread's last read of the accumulator
+            }
             uint32_t w[16];
             if (p.epilogue == NG_EPI_BIAS_ACT) {
 #pragma unroll
               for (int k = 0; k < 32; ++k) {
-                const float b = p.bias ? p.bias[n0 + ps * EB + ch * 32 + k] : 0.f;
+                const float b = p.bias ? p.bias[n0 + ps * EB + k] : 0.f;
                 r[k] = __float_as_uint(apply_act(__uint_as_float(r[k]) + b, p.act, p.slope));
               }
             }
@@ -255,35 +316,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float a = valid ? __uint_as_float(r[2 * k]) : 0.f, b = valid ? __uint_as_float(r[2 * k + 1]) : 0.f;
               w[k] = p.bf16 ? pack2<__nv_bfloat16>(a, b) : pack2<__half>(a, b);
             }
+            // 64-byte staging rows; 16-byte chunk index XOR (row / 2) mod 4 -> conflict-free writes and reads
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-              const int chunk = (ch * 4 + c4) ^ (row & 7);
-              *reinterpret_cast<uint4*>(staging + (size_t)row * (EB * 2) + chunk * 16) =
+              const int chunk = c4 ^ ((row >> 1) & 3);
+              *reinterpret_cast<uint4*>(stg + (size_t)row * (EB * 2) + chunk * 16) =
                   make_uint4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
             }
           }
-          if (ps == PASSES - 1) {
-            tc_fence_before();
-            mbar_arrive(smem_u32(&tempty_bar[as]));     // accumulator drained: the MMA warp may reuse it
-          }
-          epi_bar_sync();
+          bar_sync_id(barid);
 
           // ---- per-channel partial statistics (deterministic: fixed row order, fixed combine order) ----
           if (p.epilogue == NG_EPI_RAW && p.stat_partials != nullptr) {
-            constexpr int PAIRS = EB / 2, G = 128 / PAIRS;        // 32 channel pairs x 4 row groups
+            constexpr int PAIRS = EB / 2, G = 128 / PAIRS;        // 16 channel pairs x 8 row groups
             const int cp = et % PAIRS, rs = et / PAIRS;
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll 4
             for (int r2 = rs; r2 < 128; r2 += G) {
-              const uint32_t word = *reinterpret_cast<const uint32_t*>(staging + (size_t)r2 * (EB * 2) +
-                                                                       (((cp >> 2) ^ (r2 & 7)) * 16) + (cp & 3) * 4);
+              const uint32_t word = *reinterpret_cast<const uint32_t*>(stg + (size_t)r2 * (EB * 2) +
+                                                                       (((cp >> 2) ^ ((r2 >> 1) & 3)) * 16) + (cp & 3) * 4);
               const float2 v = p.bf16 ? unpack2<__nv_bfloat16>(word) : unpack2<__half>(word);
               s0 += v.x; q0 = fmaf(v.x, v.x, q0); s1 += v.y; q1 = fmaf(v.y, v.y, q1);
             }
-            if (rs > 0) *reinterpret_cast<float4*>(red + ((rs - 1) * PAIRS + cp) * 4) = make_float4(s0, q0, s1, q1);
-            epi_bar_sync();
+            if (rs > 0) *reinterpret_cast<float4*>(redg + ((rs - 1) * PAIRS + cp) * 4) = make_float4(s0, q0, s1, q1);
+            bar_sync_id(barid);
             if (rs == 0) {
+#pragma unroll
               for (int k = 1; k < G; ++k) {
-                const float4 o = *reinterpret_cast<const float4*>(red + ((k - 1) * PAIRS + cp) * 4);
+                const float4 o = *reinterpret_cast<const float4*>(redg + ((k - 1) * PAIRS + cp) * 4);
                 s0 += o.x; q0 += o.y; s1 += o.z; q1 += o.w;
               }
               if (!dummy) {
@@ -294,21 +354,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
 
-          // ---- coalesced row stores: 8 lanes x 16 B per 128-byte row slice, 4 rows per warp instruction ----
+          // ---- coalesced row stores: 4 lanes x 16 B per 64-byte row slice, 8 rows per warp instruction ----
           {
             constexpr int LPR = EB / 8, RPI = 32 / LPR;
-            const int we = warp - 2;
             const int chunk = lane % LPR;
             uint8_t* ybase = reinterpret_cast<uint8_t*>(p.y);
+#pragma unroll
             for (int r2 = we * RPI + lane / LPR; r2 < 128; r2 += 4 * RPI) {
-              const long long off = rowoff[r2];
+              const long long off = rowoffg[r2];
               if (off >= 0) {
-                const uint4 v = *reinterpret_cast<const uint4*>(staging + (size_t)r2 * (EB * 2) + ((chunk ^ (r2 & 7)) * 16));
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)r2 * (EB * 2) + ((chunk ^ ((r2 >> 1) & 3)) * 16));
                 *reinterpret_cast<uint4*>(ybase + (off + ps * EB) * 2 + chunk * 16) = v;
               }
             }
           }
-          epi_bar_sync();   // staging (and, after the last pass, rowoff) are reused
+          bar_sync_id(barid);   // staging (and, after the last pass, rowoff) are reused
         }
       }
       if (++as == 2) { as = 0; as_phase ^= 1; }
@@ -362,15 +422,34 @@ static void choose_patch(int VH, int VW, int S, int& BH, int& BW) {
   }
 }
 
-template <int BN, int KC, int CS>
+// Row-tap eligibility: K x 1 stride-1 correlation over 64 stored channels into 64 output channels whose taps are
+// consecutive rows at one column offset (the row-merged generator stem), image at least one patch wide.
+static bool row_tap_ok(const ng_conv_args& a, const ConvGeom& g) {
+  static int env = -1;
+  if (env < 0) { const char* v = getenv("NIRGAN_B200_ROWTAP"); env = v ? atoi(v) : 1; }
+  if (!env) return false;
+  if (a.form != NG_FORM_GATHER || a.sgn != 1 || a.stride != 1 || a.KW != 1 || a.KH != RT_KH) return false;
+  if (a.Cin != 64 || a.Cout != 64 || a.epilogue == NG_EPI_HEAD || g.ntaps != RT_KH) return false;
+  if (g.VW < RT_BW || g.VH < RT_BH) return false;
+  for (int t = 0; t < RT_KH; ++t)
+    if (g.taps[t].dx != g.taps[0].dx || g.taps[t].dy != g.taps[0].dy + t) return false;
+  return true;
+}
+
+static void pick_patch(const ng_conv_args& a, const ConvGeom& g, int& BH, int& BW) {
+  if (row_tap_ok(a, g)) { BH = RT_BH; BW = RT_BW; }
+  else choose_patch(g.VH, g.VW, g.S, BH, BW);
+}
+
+template <int BN, int KC, int CS, bool RT = false>
 static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
-  using Cfg = TcCfg<BN, KC>;
+  using Cfg = TcCfg<BN, KC, RT>;
   int r = get_encode();
   if (r) return r;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.g = g;
-  choose_patch(g.VH, g.VW, g.S, p.BH, p.BW);
+  pick_patch(a, g, p.BH, p.BW);
   p.patches_y = (g.VH + p.BH - 1) / p.BH;
   p.patches_x = (g.VW + p.BW - 1) / p.BW;
   p.co_tiles = g.Cout / BN;
@@ -392,6 +471,7 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
     cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wb, (cuuint64_t)g.Hb, (cuuint64_t)g.B};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Wb * g.Cin * 2, (cuuint64_t)g.Hb * g.Wb * g.Cin * 2};
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(p.BW * g.S), (cuuint32_t)(p.BH * g.S), 1};
+    if (RT) box[2] = (cuuint32_t)(RT_BH + RT_KH - 1);       // the haloed patch: every tap's rows in one box
     cuuint32_t estr[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
     CUresult cr = g_encode(&tmA, dt, 4, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -411,19 +491,19 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   static bool attr_set = false;   // per instantiation
   static int max_ctas = 0;
   if (!attr_set) {
-    int e = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int e = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, CS, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES), "cudaFuncSetAttribute(conv_tc)");
     if (e) return e;
     max_ctas = num_sms() / CS * CS;
     if (CS > 1) {
       cudaLaunchConfig_t qc = {};
-      qc.gridDim = dim3(max_ctas); qc.blockDim = dim3(192); qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      qc.gridDim = dim3(max_ctas); qc.blockDim = dim3(Cfg::THREADS); qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeClusterDimension;
       qa[0].val.clusterDim.x = CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       qc.attrs = qa; qc.numAttrs = 1;
       int ncl = 0;
-      if (cudaOccupancyMaxActiveClusters(&ncl, conv_tc_kernel<BN, KC, CS>, &qc) == cudaSuccess && ncl > 0 &&
+      if (cudaOccupancyMaxActiveClusters(&ncl, conv_tc_kernel<BN, KC, CS, RT>, &qc) == cudaSuccess && ncl > 0 &&
           ncl * CS < max_ctas)
         max_ctas = ncl * CS;      // persistent kernel: every cluster must be co-resident
     }
@@ -432,12 +512,12 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   long long want = (long long)p.total_groups * CS;
   const int grid = (int)(want < max_ctas ? want : max_ctas);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  int e = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, CS>, tmA, tmB, p), "conv_tc_kernel launch");
+  int e = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, CS, RT>, tmA, tmB, p), "conv_tc_kernel launch");
   if (e) return e;
   NG_LAUNCH_CHECK("conv_tc_kernel");
   return NG_OK;
@@ -463,7 +543,7 @@ static int tc_block_n(const ng_conv_args& a) {
 
 int conv_tc_stat_slots(const ng_conv_args& a, const ConvGeom& g) {
   int BH, BW;
-  choose_patch(g.VH, g.VW, g.S, BH, BW);
+  pick_patch(a, g, BH, BW);
   return g.nphase * ((g.VH + BH - 1) / BH) * ((g.VW + BW - 1) / BW);
 }
 
@@ -480,6 +560,7 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   if (bn == 64 && kc == 16) return launch_tc<64, 16, 1>(a, g, st);
   if (bn == 128 && kc == 16) return launch_tc<128, 16, 1>(a, g, st);
   if (bn == 256 && kc == 16) return launch_tc<256, 16, 1>(a, g, st);
+  if (bn == 64 && kc == 64 && row_tap_ok(a, g)) return launch_tc<64, 64, 1, true>(a, g, st);
   if (bn == 64 && kc == 64) return launch_tc<64, 64, 1>(a, g, st);
   if (bn == 128 && kc == 64) return launch_tc<128, 64, 1>(a, g, st);
   if (bn == 256 && kc == 64) {

@@ -124,6 +124,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_id(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SW128, 6 = SW32)

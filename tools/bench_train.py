@@ -11,6 +11,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
+# more hardware queues than streams (compute slices + copy streams): no false dependencies between streams
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import torch  # noqa: E402
 
 
