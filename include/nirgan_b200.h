@@ -50,8 +50,14 @@ enum { NG_IMPL_SIMT = 0,   /* CUDA-core fp32-accumulate implicit GEMM (verificat
        NG_IMPL_TC = 1 };   /* tcgen05 / TMEM / TMA implicit GEMM (f16 or bf16 operands) */
 /* conv forms */
 enum { NG_FORM_GATHER = 0,     /* out[y] = sum_k in[y*stride + sgn*k - sgn*pad] * w[k]   (conv, dgrad of convT / s1 conv) */
-       NG_FORM_PHASED = 1 };   /* out[stride*i + a] = sum_{k == a+pad (mod stride)} in[i + (a+pad-k)/stride] * w[k]
+       NG_FORM_PHASED = 1,     /* out[stride*i + a] = sum_{k == a+pad (mod stride)} in[i + (a+pad-k)/stride] * w[k]
                                   (ConvTranspose2d, dgrad of a strided conv) */
+       NG_FORM_PHASED_MERGED = 2 };
+                               /* the same ConvTranspose2d(k3, s2, p1, op1) with the four output-parity phases merged into
+                                  the GEMM-N dimension: N = 4*Cout virtual channels (phase-major), K = 4 input shifts
+                                  (0/1 rows x 0/1 columns) x Cin; weights packed by ng_pack_weight_phasemerged (zeros
+                                  where a phase does not use a shift).  Each input tile is fetched once per shift instead
+                                  of once per (phase, tap) and every MMA is N >= 256 wide.  TC only. */
 /* epilogues */
 enum { NG_EPI_RAW = 0,        /* store pre-norm output (+ per-tile sum / sum-of-squares partials) */
        NG_EPI_BIAS_ACT = 1,   /* out = act(acc + bias) stored as `dtype` NHWC */
@@ -120,6 +126,10 @@ int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t KH, int32_t
  * written by ng_grad_scale_pow2) */
 int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
                           int32_t n_pad, int32_t k_pad, float scale, const float* dev_scale, float* dst, void* stream);
+
+/* weights for NG_FORM_PHASED_MERGED: ConvTranspose2d weight fp32 [Cin][Cout][3][3] ->
+ * [shift = sy*2+sx][n = phase*Cout + co][Cin], phase = (oy&1)*2 + (ox&1); entry = w[ci][co][pa+1-2sy][pb+1-2sx] or 0 */
+int ng_pack_weight_phasemerged(const float* src, int32_t Cin, int32_t Cout, int32_t dtype, void* dst, void* stream);
 
 /* Generator stem input in "row-merged" form: NCHW fp32 -> [B][H+2*wrap+2*halo][W+2*wrap][64] `dtype`, where element
  * (kw*8 + c) of output pixel (y, x) is channel c of the reflect-padded image at (y, x + kw)  (kw < KW <= 8, c < cin <= 8,

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libnirgan_b200.so")
 # enums of include/nirgan_b200.h
 F32, F16, BF16 = 0, 1, 2
 IMPL_SIMT, IMPL_TC = 0, 1
-FORM_GATHER, FORM_PHASED = 0, 1
+FORM_GATHER, FORM_PHASED, FORM_PHASED_MERGED = 0, 1, 2
 EPI_RAW, EPI_BIAS_ACT, EPI_HEAD = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 HALO_ZERO, HALO_REFLECT = 0, 1
@@ -42,6 +42,7 @@ _SIGNATURES = {
     "ng_conv2d_wgrad": (c_i32, [C.POINTER(ConvArgs), c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ng_pack_weight": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_unpack_weight_grad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ng_pack_weight_phasemerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_prep_stem": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_pack_weight_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_unpack_weight_grad_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),

@@ -42,6 +42,8 @@ extern "C" int ng_conv2d(const ng_conv_args* a, void* stream) {
   ConvGeom g;
   r = build_geometry(*a, g);
   if (r) return r;
+  NG_REQUIRE(!g.merged || (a->impl == NG_IMPL_TC && a->epilogue == NG_EPI_RAW), NG_E_UNSUPPORTED,
+             "conv: the merged-phase form runs on the tcgen05 kernel with the RAW epilogue only");
   if (a->impl == NG_IMPL_SIMT) return conv_simt(*a, g, (cudaStream_t)stream);
   if (a->impl == NG_IMPL_TC) return conv_tc(*a, g, (cudaStream_t)stream);
   set_error("conv: unknown impl %d", a->impl);
@@ -64,6 +66,7 @@ extern "C" int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* d
   r = validate(a);
   if (r) return r;
   NG_REQUIRE(dw_packed != nullptr, NG_E_ARG, "wgrad: null output");
+  NG_REQUIRE(a->form != NG_FORM_PHASED_MERGED, NG_E_UNSUPPORTED, "wgrad: describe the ConvTranspose as NG_FORM_PHASED");
   ConvGeom g;
   r = build_geometry(*a, g);
   if (r) return r;

@@ -48,6 +48,8 @@ struct ConvGeom {
   int phase_tap0[5];
   int phase_oy[4], phase_ox[4];
   int ntaps;
+  int merged;                // NG_FORM_PHASED_MERGED: Cout is the virtual 4*Cout_real, phases live in the channel index
+  int Cout_real;
   ConvTap taps[64];
 };
 

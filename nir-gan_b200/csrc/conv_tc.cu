@@ -292,9 +292,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* redg = red + grp * 512;
         long long* rowoffg = rowoff + grp * 128;
         const uint32_t barid = 1 + grp;
-        rowoffg[row] = valid ? ((((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout + n0) : -1ll;
+        // element offset of this row's output pixel (merged phases: of its 2x2 output block's top-left pixel)
+        rowoffg[row] = valid ? (((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout_real : -1ll;
 #pragma unroll 1
         for (int ps = grp; ps < PASSES; ps += EG) {
+          // where this pass's 32 channels go: plain = channel n0 + ps*EB of the row's pixel; merged phases = channel co0
+          // of the pixel (2i + pa, 2j + pb) with phase = virtual channel / Cout_real
+          int c_first = n0 + ps * EB, phase_id = ph;
+          long long chan_off = c_first;
+          if (g.merged) {
+            phase_id = c_first / g.Cout_real;
+            c_first -= phase_id * g.Cout_real;
+            chan_off = ((long long)(phase_id >> 1) * g.Wout + (phase_id & 1)) * g.Cout_real + c_first;
+          }
           {
             uint32_t r[32];
             tmem_ld32(taddr + ps * EB, r);
@@ -347,8 +357,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 s0 += o.x; q0 += o.y; s1 += o.z; q1 += o.w;
               }
               if (!dummy) {
-                const int slot = (ph * p.patches_y + py) * p.patches_x + px;
-                float* dst = p.stat_partials + (((size_t)n * p.stat_slots + slot) * g.Cout + n0 + ps * EB + 2 * cp) * 2;
+                const int slot = (phase_id * p.patches_y + py) * p.patches_x + px;
+                float* dst = p.stat_partials + (((size_t)n * p.stat_slots + slot) * g.Cout_real + c_first + 2 * cp) * 2;
                 *reinterpret_cast<float4*>(dst) = make_float4(s0, q0, s1, q1);
               }
             }
@@ -364,7 +374,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const long long off = rowoffg[r2];
               if (off >= 0) {
                 const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)r2 * (EB * 2) + ((chunk ^ ((r2 >> 1) & 3)) * 16));
-                *reinterpret_cast<uint4*>(ybase + (off + ps * EB) * 2 + chunk * 16) = v;
+                *reinterpret_cast<uint4*>(ybase + (off + chan_off) * 2 + chunk * 16) = v;
               }
             }
           }
@@ -461,7 +471,7 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   p.total_groups = p.co_tiles * g.nphase * p.groups_per;
   p.epilogue = a.epilogue; p.act = a.act; p.crop = a.crop; p.slope = a.slope;
   p.bf16 = a.dtype == NG_BF16;
-  p.stat_slots = g.nphase * p.patches_y * p.patches_x;
+  p.stat_slots = (g.merged ? 4 : g.nphase) * p.patches_y * p.patches_x;
   p.bias = a.bias; p.y = a.y; p.stat_partials = a.stat_partials;
 
   CUtensorMap tmA, tmB;
@@ -479,7 +489,7 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
                (int)cr, g.Cin, g.Wb, g.Hb, g.B, KC, p.BW * g.S, p.BH * g.S);
   }
   {
-    const int taps_total = a.KH * a.KW;
+    const int taps_total = g.merged ? g.ntaps : a.KH * a.KW;
     cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)taps_total * g.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(BN / CS)};
@@ -533,25 +543,25 @@ static int cluster_size_for(int bn, int kc) {
   return (bn == 256 && kc == 64) ? env : 1;     // multicast pays on the weight-heavy 256-wide tiles
 }
 
-static int tc_block_n(const ng_conv_args& a) {
+static int tc_block_n(const ng_conv_args& a, const ConvGeom& g) {
   if (a.epilogue == NG_EPI_HEAD || a.Cout == 16) return 16;
-  if (a.Cout % 256 == 0) return 256;
-  if (a.Cout % 128 == 0) return 128;
-  if (a.Cout % 64 == 0) return 64;
+  if (g.Cout % 256 == 0) return 256;
+  if (g.Cout % 128 == 0) return 128;
+  if (g.Cout % 64 == 0) return 64;
   return 0;
 }
 
 int conv_tc_stat_slots(const ng_conv_args& a, const ConvGeom& g) {
   int BH, BW;
   pick_patch(a, g, BH, BW);
-  return g.nphase * ((g.VH + BH - 1) / BH) * ((g.VW + BW - 1) / BW);
+  return (g.merged ? 4 : g.nphase) * ((g.VH + BH - 1) / BH) * ((g.VW + BW - 1) / BW);
 }
 
 int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   NG_REQUIRE(a.dtype == NG_F16 || a.dtype == NG_BF16, NG_E_UNSUPPORTED, "conv_tc: operands must be f16 or bf16");
   NG_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0, NG_E_ALIGN,
              "conv_tc: tensors must be 16-byte aligned");
-  const int bn = tc_block_n(a);
+  const int bn = tc_block_n(a, g);
   const int kc = a.Cin % 64 == 0 ? 64 : (a.Cin == 16 ? 16 : 0);
   NG_REQUIRE(bn != 0 && kc != 0, NG_E_UNSUPPORTED, "conv_tc: Cin %d / Cout %d not tileable", a.Cin, a.Cout);
   NG_REQUIRE(a.epilogue != NG_EPI_HEAD || a.Cout == 16, NG_E_SHAPE, "conv_tc: head epilogue expects Cout stored as 16");

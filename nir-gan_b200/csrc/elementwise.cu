@@ -25,6 +25,24 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int d0, int d1
   }
 }
 
+// ConvTranspose2d(k3, s2, p1) weights [Cin][Cout][3][3] -> merged-phase layout [shift][phase*Cout + co][Cin]
+template <typename T>
+__global__ void pack_phasemerged_kernel(const float* __restrict__ src, int Cin, int Cout, T* __restrict__ dst) {
+  const long long total = 4ll * 4 * Cout * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    long long r = i / Cin;
+    const int co = (int)(r % Cout); r /= Cout;
+    const int ph = (int)(r % 4), sh = (int)(r / 4);
+    const int pa = ph >> 1, pb = ph & 1, sy = sh >> 1, sx = sh & 1;
+    const int kh = pa + 1 - 2 * sy, kw = pb + 1 - 2 * sx;
+    float v = 0.f;
+    if (kh >= 0 && kh < 3 && kw >= 0 && kw < 3) v = src[(((long long)ci * Cout + co) * 3 + kh) * 3 + kw];
+    dst[i] = from_f32<T>(v);
+  }
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int d0, int d1, int taps, int n_axis,
                                     int n_pad, int k_pad, float scale, const float* __restrict__ dev_scale,
                                     float* __restrict__ dst) {
@@ -620,6 +638,16 @@ extern "C" int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t 
   DISPATCH_DTYPE(dtype, (pack_weight_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
                             src, d0, d1, KH * KW, n_axis, n_pad, k_pad, (T*)dst)));
   NG_LAUNCH_CHECK("pack_weight_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_pack_weight_phasemerged(const float* src, int32_t Cin, int32_t Cout, int32_t dtype, void* dst,
+                                          void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src && dst && Cin > 0 && Cout > 0, NG_E_ARG, "pack_weight_phasemerged: bad arguments");
+  DISPATCH_DTYPE(dtype, (pack_phasemerged_kernel<T><<<grid_for(16ll * Cout * Cin, 256), 256, 0, (cudaStream_t)stream>>>(
+                            src, Cin, Cout, (T*)dst)));
+  NG_LAUNCH_CHECK("pack_phasemerged_kernel");
   return NG_OK;
 }
 

@@ -124,10 +124,30 @@ int build_geometry(const ng_conv_args& a, ConvGeom& g) {
     // every input pixel contributes to out[s*i - pad + k]: the largest index must fit
     NG_REQUIRE((a.Hin - 1) * s - a.pad + a.KH - 1 <= a.Hout + s - 1 && a.Hout <= (a.Hin - 1) * s - 2 * a.pad + a.KH + s - 1,
                NG_E_SHAPE, "phased conv: Hout %d inconsistent with Hin %d", a.Hout, a.Hin);
+  } else if (a.form == NG_FORM_PHASED_MERGED) {
+    NG_REQUIRE(a.stride == 2 && a.KH == 3 && a.KW == 3 && a.pad == 1 && a.pad_w == 1, NG_E_UNSUPPORTED,
+               "merged-phase conv: built for ConvTranspose2d(k3, s2, p1, op1)");
+    NG_REQUIRE(a.in_pad == a.in_pad_w && a.Hout == 2 * a.Hin && a.Wout == 2 * a.Win, NG_E_SHAPE,
+               "merged-phase conv: output must be 2x the input");
+    g.merged = 1;
+    g.Cout_real = a.Cout;
+    g.Cout = 4 * a.Cout;
+    g.VH = a.Hin; g.VW = a.Win; g.S = 1; g.OS = 2; g.nphase = 1;
+    g.phase_tap0[0] = 0;
+    int t = 0;
+    for (int sy = 0; sy < 2; ++sy)
+      for (int sx = 0; sx < 2; ++sx, ++t) {
+        g.taps[t].dy = (int16_t)(sy + a.in_pad);
+        g.taps[t].dx = (int16_t)(sx + a.in_pad);
+        g.taps[t].wrow = t * g.Cout;
+      }
+    g.ntaps = t;
+    g.phase_tap0[1] = t;
   } else {
     set_error("conv: unknown form %d", a.form);
     return NG_E_ARG;
   }
+  if (!g.merged) g.Cout_real = g.Cout;
   return NG_OK;
 }
 

@@ -213,6 +213,11 @@ class Engine:
         if n_axis == "rowmerged":
             dst = hit[1] if hit is not None else torch.empty(kh * d0 * 64, dtype=self.dt_torch, device=self.device)
             L.call("ng_pack_weight_rowmerged", src.data_ptr(), d0, d1, kh, kw, self.dt_enum, dst.data_ptr(), stream)
+        elif n_axis == "phasemerged":
+            # ConvTranspose2d (Cin, Cout, 3, 3) -> [shift (4)][phase*Cout + co][Cin]  (NG_FORM_PHASED_MERGED)
+            assert kh == 3 and kw == 3 and n_pad == d1 and k_pad == d0
+            dst = hit[1] if hit is not None else torch.empty(16 * d1 * d0, dtype=self.dt_torch, device=self.device)
+            L.call("ng_pack_weight_phasemerged", src.data_ptr(), d0, d1, self.dt_enum, dst.data_ptr(), stream)
         elif n_axis == "taps":
             assert d0 == 1 and kh * kw <= n_pad
             dst = hit[1] if hit is not None else torch.zeros(n_pad * k_pad, dtype=self.dt_torch, device=self.device)

@@ -23,6 +23,11 @@ from . import _lib as L
 from .engine import ActBuf, Engine, Plan, _ptr
 
 
+# NIRGAN_B200_MERGE_PHASES=0 runs ConvTranspose2d as four separate output-phase GEMMs (NG_FORM_PHASED) instead
+import os as _os
+MERGE_PHASES = [_os.environ.get("NIRGAN_B200_MERGE_PHASES", "1") != "0"]
+
+
 @dataclass
 class Unit:
     name: str
@@ -66,8 +71,16 @@ class UnitGraph:
         self.tap_head: Optional[dict] = None
 
     # ---- construction -----------------------------------------------------------------------------
+    def merged_phases(self, u: Unit) -> bool:
+        """ConvTranspose2d(k3, s2, p1, op1) forward on the tcgen05 kernel: merge the four output phases into GEMM-N."""
+        return (u.form == L.FORM_PHASED and self.eng.impl == L.IMPL_TC and u.kind == "norm" and u.K == 3 and u.stride == 2
+                and u.pad == 1 and u.KW is None and u.x.pad == 0 and u.x.C % 64 == 0 and (4 * u.cout) % 64 == 0
+                and u.Hout == 2 * u.x.H and u.Wout == 2 * u.x.W and MERGE_PHASES[0])
+
     def weight(self, u: Unit) -> torch.Tensor:
         cin = u.x.C
+        if self.merged_phases(u):
+            return self.eng.packed_weight(u.conv.weight, "phasemerged", u.cout, cin, self.stream)
         if u.pack == "rowmerged":
             return self.eng.packed_weight(u.conv.weight, "rowmerged", u.cout, 64, self.stream)
         return self.eng.packed_weight(u.conv.weight, u.pack, u.cout, cin, self.stream)
@@ -114,7 +127,7 @@ class UnitGraph:
                 plan.keepalive.append(a)
                 plan.add("ng_conv2d", C.byref(a), label=pre)
                 continue
-            a = self._args(u, u.x, w, u.y.t)
+            a = self._args(u, u.x, w, u.y.t, **({"form": L.FORM_PHASED_MERGED} if self.merged_phases(u) else {}))
             B = u.x.B
             if eng.impl == L.IMPL_TC:
                 slots = L.load().ng_conv_stat_slots(C.byref(a))

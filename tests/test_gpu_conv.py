@@ -104,6 +104,36 @@ def test_conv_transpose_phased(case, impl, dtype):
     assert float((mr[..., 1] / rstd - 1).abs().max()) <= 2e-4
 
 
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("case", CONVT_CASES, ids=[c[0] for c in CONVT_CASES])
+def test_conv_transpose_merged_phases(case, dt):
+    """NG_FORM_PHASED_MERGED (four output phases in GEMM-N, four input shifts in GEMM-K) == ConvTranspose2d, and agrees
+    with the four-phase NG_FORM_PHASED kernel (same products, fp32 accumulation in a different order)."""
+    import ctypes as C
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    dtype = L.F16 if dt == "f16" else L.BF16
+    name, Cin, Cout, H, W, B = case
+    x = Hh.rnd(_gen(B, Cin, H, W, seed=3), dtype)
+    w = Hh.rnd(_gen(Cin, Cout, 3, 3, seed=4, scale=0.05), dtype)
+    xb = Hh.to_actbuf(x, 0, "zero", dtype)
+    wm = torch.empty(16 * Cout * Cin, dtype=Hh.TORCH_DT[dtype], device="cuda")
+    L.call("ng_pack_weight_phasemerged", w.contiguous().data_ptr(), Cin, Cout, dtype, wm.data_ptr(), Hh.stream())
+    y, mr, _ = Hh.conv_call(xb, wm, Cout, 3, 2, 1, 2 * H, 2 * W, dtype, L.IMPL_TC, form=L.FORM_PHASED_MERGED,
+                            want_stats=True)
+    ref = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=1)
+    got = Hh.from_compact(y, B, 2 * H, 2 * W, Cout)
+    assert torch.isfinite(got).all()
+    err = float((got - ref).abs().max())
+    assert err <= _tol(dtype, ref), f"{name}: max-abs {err:.3e}"
+    mu, rstd = Hh.stats_ref(got)
+    assert float((mr[..., 0] - mu).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+    assert float((mr[..., 1] / rstd - 1).abs().max()) <= 2e-4
+    wp = Hh.pack_weight(w, 1, Cout, Cin, dtype)
+    y4, _, _ = Hh.conv_call(xb, wp, Cout, 3, 2, 1, 2 * H, 2 * W, dtype, L.IMPL_TC, form=L.FORM_PHASED)
+    assert float((Hh.from_compact(y4, B, 2 * H, 2 * W, Cout) - got).abs().max()) <= _tol(dtype, ref)
+
+
 @pytest.mark.parametrize("impl,dtype", _impls())
 @pytest.mark.parametrize("crop,H", [(0, 32), (10, 44)])
 def test_head_conv_tanh(impl, dtype, crop, H):
