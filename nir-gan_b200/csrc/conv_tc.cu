@@ -288,12 +288,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
         constexpr int EB = Cfg::EB, EG = Cfg::EG, PASSES = BN / EB;
-        uint8_t* stg = staging + grp * (128 * EB * 2);
-        float* redg = red + grp * 512;
-        long long* rowoffg = rowoff + grp * 128;
+        const uint32_t stg = smem_u32(staging) + grp * (128 * EB * 2);     // shared-space byte addresses
+        const uint32_t redg = smem_u32(red) + grp * 2048;
+        const uint32_t rowoffg = smem_u32(rowoff) + grp * 1024;
         const uint32_t barid = 1 + grp;
         // element offset of this row's output pixel (merged phases: of its 2x2 output block's top-left pixel)
-        rowoffg[row] = valid ? (((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout_real : -1ll;
+        sts64(rowoffg + row * 8, valid ? (((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout_real : -1ll);
 #pragma unroll 1
         for (int ps = grp; ps < PASSES; ps += EG) {
           // where this pass's 32 channels go: plain = channel n0 + ps*EB of the row's pixel; merged phases = channel co0
@@ -330,8 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
               const int chunk = c4 ^ ((row >> 1) & 3);
-              *reinterpret_cast<uint4*>(stg + (size_t)row * (EB * 2) + chunk * 16) =
-                  make_uint4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
+              sts128(stg + row * (EB * 2) + chunk * 16, w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
             }
           }
           bar_sync_id(barid);
@@ -343,17 +342,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll 4
             for (int r2 = rs; r2 < 128; r2 += G) {
-              const uint32_t word = *reinterpret_cast<const uint32_t*>(stg + (size_t)r2 * (EB * 2) +
-                                                                       (((cp >> 2) ^ ((r2 >> 1) & 3)) * 16) + (cp & 3) * 4);
+              const uint32_t word = lds32(stg + r2 * (EB * 2) + (((cp >> 2) ^ ((r2 >> 1) & 3)) * 16) + (cp & 3) * 4);
               const float2 v = p.bf16 ? unpack2<__nv_bfloat16>(word) : unpack2<__half>(word);
               s0 += v.x; q0 = fmaf(v.x, v.x, q0); s1 += v.y; q1 = fmaf(v.y, v.y, q1);
             }
-            if (rs > 0) *reinterpret_cast<float4*>(redg + ((rs - 1) * PAIRS + cp) * 4) = make_float4(s0, q0, s1, q1);
+            if (rs > 0) sts_f4(redg + ((rs - 1) * PAIRS + cp) * 16, make_float4(s0, q0, s1, q1));
             bar_sync_id(barid);
             if (rs == 0) {
 #pragma unroll
               for (int k = 1; k < G; ++k) {
-                const float4 o = *reinterpret_cast<const float4*>(redg + ((k - 1) * PAIRS + cp) * 4);
+                const float4 o = lds_f4(redg + ((k - 1) * PAIRS + cp) * 16);
                 s0 += o.x; q0 += o.y; s1 += o.z; q1 += o.w;
               }
               if (!dummy) {
@@ -371,9 +369,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint8_t* ybase = reinterpret_cast<uint8_t*>(p.y);
 #pragma unroll
             for (int r2 = we * RPI + lane / LPR; r2 < 128; r2 += 4 * RPI) {
-              const long long off = rowoffg[r2];
+              const long long off = lds64(rowoffg + r2 * 8);
               if (off >= 0) {
-                const uint4 v = *reinterpret_cast<const uint4*>(stg + (size_t)r2 * (EB * 2) + ((chunk ^ ((r2 >> 1) & 3)) * 16));
+                const uint4 v = lds128(stg + r2 * (EB * 2) + ((chunk ^ ((r2 >> 1) & 3)) * 16));
                 *reinterpret_cast<uint4*>(ybase + (off + chan_off) * 2 + chunk * 16) = v;
               }
             }
