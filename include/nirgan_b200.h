@@ -227,6 +227,22 @@ int ng_g_pixel_losses(const float* rgb, const float* nir, const float* pred, int
 int ng_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int32_t step, float grad_scale, void* stream);
 
+/* ---- post-processing after the generator (create_synthetic_dataset.py:34-52,111-118) ---------- */
+/* plane resize with F.interpolate semantics: mode 0 'nearest' (the scale_factor=4 upsampling of the Sentinel-2 NIR,
+ * create_synthetic_dataset.py:111), mode 1 'bilinear' align_corners=False (histogram_match, :37).  fp32 planes. */
+int ng_resize_plane(const float* src, int32_t planes, int32_t h, int32_t w, int32_t H, int32_t W, int32_t mode,
+                    float* dst, void* stream);
+/* per-tile histogram matching = skimage.exposure.match_histograms(img, ref, channel_axis=None) for every tile of a
+ * batch (create_synthetic_dataset.py:41-47): image [B][N], reference [B][M] fp32; out [B][N] as NG_F32 or NG_F16 (the
+ * reference stores float16, :116).  Segmented radix sort of both arrays + three binary searches per pixel. */
+int64_t ng_hist_match_workspace_bytes(int32_t B, int32_t N, int32_t M);
+int ng_hist_match(const float* image, const float* reference, int32_t B, int32_t N, int32_t M, int32_t out_dtype,
+                  void* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* the building block on its own: ascending sort of `segs` segments of n floats (-0.0 == +0.0);
+ * workspace >= segs*n*8 + segs*ceil(n/4096)*1024 bytes */
+int ng_sort_segments(const float* src, int32_t segs, int32_t n, float* sorted_out, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,283 @@
+// Post-processing that follows the generator in the reference's inference loop (create_synthetic_dataset.py:34-52,
+// 111-118): nearest / bilinear plane resize and per-tile histogram matching
+// (skimage.exposure.match_histograms, channel_axis=None = _match_cumulative_cdf) on the device, with optional fp16 output
+// (the reference stores float16).
+//
+// Histogram matching of one tile (N source pixels, M reference pixels):
+//   q(v)   = #{source pixels <= v} / N                      (np.unique counts + cumsum)
+//   out(v) = np.interp(q(v), tmpl_quantiles, tmpl_values)   with tmpl_* from np.unique(reference)
+// Both arrays are sorted per tile by a segmented LSD radix sort (8-bit digits, 4 passes, stable scatter built on
+// warp match_any ranks); each pixel then needs three binary searches (its own rank, and the bracket of its quantile among
+// the reference's unique values) -- the sorted arrays of a batch stay in the 126 MB L2.  Integer cross-multiplication
+// replaces the float comparison of quantiles (cnt/N vs e/M), which is exact; the interpolation itself runs in fp64 like
+// np.interp.
+#include "common.cuh"
+
+namespace ng {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_PER_WARP = 512;
+constexpr int RS_TILE = RS_WARPS * RS_PER_WARP;      // 4096 keys per block per pass
+
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+  if (f == 0.f) f = 0.f;                              // -0.0 and +0.0 are one value for np.unique
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+template <bool FROM_FLOAT>
+__device__ __forceinline__ uint32_t load_key(const void* src, size_t i) {
+  if constexpr (FROM_FLOAT) return float_to_key(reinterpret_cast<const float*>(src)[i]);
+  else return reinterpret_cast<const uint32_t*>(src)[i];
+}
+
+// pass kernel 1: per-(tile, segment) digit histogram
+template <bool FROM_FLOAT>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const void* __restrict__ src, int n, int shift, int ntiles, uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t h[256];
+  const int tile = blockIdx.x, seg = blockIdx.y;
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = (size_t)seg * n;
+  const int i0 = tile * RS_TILE, i1 = min(n, i0 + RS_TILE);
+  for (int i = i0 + threadIdx.x; i < i1; i += RS_THREADS)
+    atomicAdd(&h[(load_key<FROM_FLOAT>(src, base + i) >> shift) & 255u], 1u);
+  __syncthreads();
+  ghist[((size_t)seg * ntiles + tile) * 256 + threadIdx.x] = h[threadIdx.x];
+}
+
+// pass kernel 2: per segment, turn the histograms into global destination offsets [tile][digit]
+__global__ void __launch_bounds__(256)
+rs_scan_kernel(uint32_t* __restrict__ ghist, int ntiles) {
+  __shared__ uint32_t tot[256];
+  uint32_t* h = ghist + (size_t)blockIdx.x * ntiles * 256;
+  const int d = threadIdx.x;
+  uint32_t s = 0;
+  for (int t = 0; t < ntiles; ++t) s += h[(size_t)t * 256 + d];
+  tot[d] = s;
+  __syncthreads();
+  if (d == 0) {                                       // 256-entry exclusive scan: negligible
+    uint32_t run = 0;
+    for (int k = 0; k < 256; ++k) { const uint32_t v = tot[k]; tot[k] = run; run += v; }
+  }
+  __syncthreads();
+  uint32_t run = tot[d];
+  for (int t = 0; t < ntiles; ++t) {
+    const uint32_t v = h[(size_t)t * 256 + d];
+    h[(size_t)t * 256 + d] = run;
+    run += v;
+  }
+}
+
+// pass kernel 3: stable scatter.  Warp w owns keys [tile*4096 + w*512, +512) and walks them 32 at a time in order.
+template <bool FROM_FLOAT>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(const void* __restrict__ src, uint32_t* __restrict__ dst, int n, int shift, int ntiles,
+                  const uint32_t* __restrict__ goff) {
+  __shared__ uint32_t wh[RS_WARPS][256];
+  const int tile = blockIdx.x, seg = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wh[0][0])[i] = 0;
+  __syncthreads();
+  const size_t base = (size_t)seg * n;
+  const int w0 = tile * RS_TILE + warp * RS_PER_WARP;
+  // A: per-warp digit counts
+  for (int c = 0; c < RS_PER_WARP; c += 32) {
+    const int i = w0 + c + lane;
+    if (i < n) atomicAdd(&wh[warp][(load_key<FROM_FLOAT>(src, base + i) >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  // B: destination base of (warp, digit) = tile offset of the digit + counts of the lower warps
+  {
+    const int d = threadIdx.x;
+    uint32_t run = goff[((size_t)seg * ntiles + tile) * 256 + d];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) { const uint32_t v = wh[w][d]; wh[w][d] = run; run += v; }
+  }
+  __syncthreads();
+  // C: ordered placement
+  uint32_t* out = dst + base;
+  for (int c = 0; c < RS_PER_WARP; c += 32) {
+    const int i = w0 + c + lane;
+    const bool act = i < n;
+    const uint32_t key = act ? load_key<FROM_FLOAT>(src, base + i) : 0u;
+    const uint32_t d = act ? ((key >> shift) & 255u) : (256u + lane);        // inactive lanes match nobody
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    const int leader = __ffs(peers) - 1;
+    uint32_t b = 0;
+    if (act && lane == leader) { b = wh[warp][d]; wh[warp][d] = b + __popc(peers); }
+    b = __shfl_sync(0xffffffffu, b, leader);
+    if (act) out[b + rank] = key;
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ int count_le(const uint32_t* __restrict__ a, int n, uint32_t key) {   // upper_bound
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+__device__ __forceinline__ int count_lt(const uint32_t* __restrict__ a, int n, uint32_t key) {   // lower_bound
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+template <typename TO>
+__global__ void __launch_bounds__(256)
+hist_match_kernel(const float* __restrict__ img, const uint32_t* __restrict__ ssrc, const uint32_t* __restrict__ sref,
+                  int B, int N, int M, TO* __restrict__ out) {
+  const long long total = (long long)B * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / N);
+    const uint32_t* s = ssrc + (size_t)b * N;
+    const uint32_t* r = sref + (size_t)b * M;
+    const uint32_t key = float_to_key(img[i]);
+    const long long cnt = count_le(s, N, key);                 // source quantile = cnt / N
+    long long i0 = (cnt * M + N - 1) / N - 1;                   // smallest i with (i+1)/M >= cnt/N
+    i0 = i0 < 0 ? 0 : (i0 > M - 1 ? M - 1 : i0);
+    const uint32_t rk = r[i0];
+    const int first = count_lt(r, M, rk);                      // previous unique value ends at first - 1
+    float res = key_to_float(rk);
+    if (first > 0) {
+      const int last1 = count_le(r, M, rk);                    // this unique value's quantile = last1 / M
+      const double q = (double)cnt / (double)N, qk = (double)last1 / (double)M, qp = (double)first / (double)M;
+      const double vk = (double)key_to_float(rk), vp = (double)key_to_float(r[first - 1]);
+      res = (float)(vp + (q - qp) * ((vk - vp) / (qk - qp)));
+    }
+    if constexpr (sizeof(TO) == 2) out[i] = __float2half_rn(res);
+    else out[i] = res;
+  }
+}
+
+// plane resize, PyTorch semantics: mode 0 = 'nearest' (src = floor(dst * in/out)), mode 1 = 'bilinear',
+// align_corners=False (src = (dst + 0.5) * in/out - 0.5, clamped at 0; neighbours clamped to the last index)
+__global__ void __launch_bounds__(256)
+resize_plane_kernel(const float* __restrict__ src, int P, int h, int w, int H, int W, int mode, float* __restrict__ dst) {
+  const long long total = (long long)P * H * W;
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const long long p = i / ((long long)W * H);
+    const float* s = src + p * h * w;
+    if (mode == 0) {
+      const int yy = min((int)floorf(y * sy), h - 1), xx = min((int)floorf(x * sx), w - 1);
+      dst[i] = s[yy * w + xx];
+    } else {
+      const float fy = fmaxf((y + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((x + 0.5f) * sx - 0.5f, 0.f);
+      const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+      const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+      const float ly = fy - y0, lx = fx - x0;
+      dst[i] = (1.f - ly) * ((1.f - lx) * s[y0 * w + x0] + lx * s[y0 * w + x1]) +
+               ly * ((1.f - lx) * s[y1 * w + x0] + lx * s[y1 * w + x1]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+keys_to_float_kernel(const uint32_t* __restrict__ k, long long n, float* __restrict__ o) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    o[i] = key_to_float(k[i]);
+}
+
+static inline int rs_tiles(int n) { return (n + RS_TILE - 1) / RS_TILE; }
+
+// sorts `segs` segments of n floats each into sorted (ordered-uint keys); tmp and ghist are scratch
+static int segmented_sort(const float* src, int segs, int n, uint32_t* sorted, uint32_t* tmp, uint32_t* ghist,
+                          cudaStream_t st) {
+  const int nt = rs_tiles(n);
+  dim3 grid(nt, segs);
+  const void* in = src;
+  uint32_t* bufs[2] = {tmp, sorted};                 // pass 0 -> tmp, 1 -> sorted, 2 -> tmp, 3 -> sorted
+  for (int pass = 0; pass < 4; ++pass) {
+    uint32_t* outb = bufs[pass & 1];
+    if (pass == 0) rs_hist_kernel<true><<<grid, RS_THREADS, 0, st>>>(in, n, 0, nt, ghist);
+    else rs_hist_kernel<false><<<grid, RS_THREADS, 0, st>>>(in, n, 8 * pass, nt, ghist);
+    NG_LAUNCH_CHECK("rs_hist_kernel");
+    rs_scan_kernel<<<segs, 256, 0, st>>>(ghist, nt);
+    NG_LAUNCH_CHECK("rs_scan_kernel");
+    if (pass == 0) rs_scatter_kernel<true><<<grid, RS_THREADS, 0, st>>>(in, outb, n, 0, nt, ghist);
+    else rs_scatter_kernel<false><<<grid, RS_THREADS, 0, st>>>(in, outb, n, 8 * pass, nt, ghist);
+    NG_LAUNCH_CHECK("rs_scatter_kernel");
+    in = outb;
+  }
+  return NG_OK;
+}
+
+}  // namespace ng
+
+using namespace ng;
+
+extern "C" int64_t ng_hist_match_workspace_bytes(int32_t B, int32_t N, int32_t M) {
+  if (B <= 0 || N <= 0 || M <= 0) return NG_E_ARG;
+  const int64_t big = N > M ? N : M;
+  return ((int64_t)B * N + (int64_t)B * M + (int64_t)B * big) * 4 + (int64_t)B * rs_tiles((int)big) * 256 * 4 + 256;
+}
+
+extern "C" int ng_sort_segments(const float* src, int32_t segs, int32_t n, float* sorted_out, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src && sorted_out && workspace && segs > 0 && n > 0, NG_E_ARG, "sort_segments: bad arguments");
+  const int64_t need = (int64_t)segs * n * 8 + (int64_t)segs * rs_tiles(n) * 1024;
+  NG_REQUIRE(workspace_bytes >= need, NG_E_ARG, "sort_segments: workspace of %lld bytes needed", (long long)need);
+  uint32_t* sorted = reinterpret_cast<uint32_t*>(workspace);
+  uint32_t* tmp = sorted + (size_t)segs * n;
+  uint32_t* ghist = tmp + (size_t)segs * n;
+  r = segmented_sort(src, segs, n, sorted, tmp, ghist, (cudaStream_t)stream);
+  if (r) return r;
+  const long long total = (long long)segs * n;
+  long long blocks = (total + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+  keys_to_float_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sorted, total, sorted_out);
+  NG_LAUNCH_CHECK("key_to_float kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_hist_match(const float* image, const float* reference, int32_t B, int32_t N, int32_t M,
+                             int32_t out_dtype, void* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(image && reference && out && workspace && B > 0 && N > 0 && M > 0, NG_E_ARG, "hist_match: bad arguments");
+  NG_REQUIRE(out_dtype == NG_F32 || out_dtype == NG_F16, NG_E_ARG, "hist_match: output must be f32 or f16");
+  NG_REQUIRE(workspace_bytes >= ng_hist_match_workspace_bytes(B, N, M), NG_E_ARG, "hist_match: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* ssrc = reinterpret_cast<uint32_t*>(workspace);
+  uint32_t* sref = ssrc + (size_t)B * N;
+  uint32_t* tmp = sref + (size_t)B * M;
+  const int big = N > M ? N : M;
+  uint32_t* ghist = tmp + (size_t)B * big;
+  r = segmented_sort(image, B, N, ssrc, tmp, ghist, st);
+  if (r) return r;
+  r = segmented_sort(reference, B, M, sref, tmp, ghist, st);
+  if (r) return r;
+  const long long total = (long long)B * N;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (out_dtype == NG_F16)
+    hist_match_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>(image, ssrc, sref, B, N, M, (__half*)out);
+  else
+    hist_match_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(image, ssrc, sref, B, N, M, (float*)out);
+  NG_LAUNCH_CHECK("hist_match_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_resize_plane(const float* src, int32_t planes, int32_t h, int32_t w, int32_t H, int32_t W, int32_t mode,
+                               float* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src && dst && planes > 0 && h > 0 && w > 0 && H > 0 && W > 0 && (mode == 0 || mode == 1), NG_E_ARG,
+             "resize_plane: bad arguments");
+  const long long total = (long long)planes * H * W;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  resize_plane_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, planes, h, w, H, W, mode, dst);
+  NG_LAUNCH_CHECK("resize_plane_kernel");
+  return NG_OK;
+}

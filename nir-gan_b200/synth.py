@@ -6,7 +6,7 @@ Reference: ``dl = DataLoader(SR_dataset(root), batch_size=2, shuffle=False)``; f
 ranks (one process per GPU, no collective on the data path); because InstanceNorm statistics are per sample
 and the kernels' work decomposition is per image, a tile's result is bit-identical whichever rank / batch slot
 computes it, so the union of the shards equals the sequential loop's ``{id: array}`` mapping exactly.
-Histogram matching and the .npz writer that follow the loop are out of scope.
+Histogram matching and the .npz writer that follow the loop live in ``postprocess.py``.
 """
 from __future__ import annotations
 
@@ -39,9 +39,11 @@ def shard(n_items: int, rank: int, world: int, mode: str = "contiguous") -> List
 
 def run_shard(model: Callable[[torch.Tensor], torch.Tensor], tiles: Mapping[str, torch.Tensor], rank: int = 0,
               world: int = 1, batch_size: int = 64, device: Optional[torch.device] = None,
-              mode: str = "contiguous") -> Dict[str, torch.Tensor]:
+              mode: str = "contiguous", s2_nir: Optional[Mapping[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """Run ``model(hr)`` (e.g. ``Px2Px.forward`` in eval mode) over this rank's tiles; returns {id: (1,H,W) fp32 CPU}.
-    Tiles of different sizes are batched by size in list order."""
+    Tiles of different sizes are batched by size in list order.  With ``s2_nir`` ({filename: (1,h,w) Sentinel-2 NIR at a
+    quarter of the tile's resolution}) the prediction is histogram-matched to it on the device and returned as float16,
+    i.e. the loop body of create_synthetic_dataset.py:107-116 (device-side ``postprocess.postprocess``)."""
     names = sorted_tiles(list(tiles.keys()))
     mine = [names[i] for i in shard(len(names), rank, world, mode)]
     out: Dict[str, torch.Tensor] = {}
@@ -55,7 +57,12 @@ def run_shard(model: Callable[[torch.Tensor], torch.Tensor], tiles: Mapping[str,
             hr = torch.stack([tiles[n] for n in mine[i:j]])
             if device is not None:
                 hr = hr.to(device, non_blocking=True)
-            pred = model(hr).float().cpu()
+            pred = model(hr).float()
+            if s2_nir is not None:
+                from .postprocess import postprocess
+                ref = torch.stack([s2_nir[n] for n in mine[i:j]])
+                pred = postprocess(pred, ref.to(pred.device, non_blocking=True))
+            pred = pred.cpu()
             for n, p in zip(mine[i:j], pred):
                 out[tile_id(n)] = p
             i = j

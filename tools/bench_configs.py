@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--precision", default="fp16")
+    ap.add_argument("--postprocess", action="store_true",
+                    help="config 3: also histogram-match every prediction to a synthetic Sentinel-2 NIR band on the device")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -82,9 +84,15 @@ def main():
         mine = synth.shard(n_tiles, rank, world)
         x = torch.rand(len(mine), 3, 512, 512, generator=gen, device=dev)       # this rank's shard, resident in HBM
 
+        s2 = torch.rand(len(mine), 1, 128, 128, generator=gen, device=dev) * 0.35
+
         def step():
             with torch.no_grad():
-                return model.predict_step(x)
+                y = model.predict_step(x)
+                if args.postprocess:
+                    from nirgan_b200.postprocess import postprocess
+                    y = postprocess(y, s2)
+                return y
 
         for _ in range(args.warmup):
             step()
@@ -103,6 +111,7 @@ def main():
                               "metric": "rgb2nir_512px_tiles_per_sec", "value": v, "unit": "tiles/s", "n_gpus": world,
                               "ms_per_step": ms, "equiv_256px_tiles_per_sec": 4 * v,
                               "model_tflops": v * 424.436 / 1e3, "precision": args.precision,
+                              "postprocess": bool(args.postprocess),
                               "ids": [synth.tile_id(names[0]), synth.tile_id(names[-1])],
                               "out_shape": list(y.shape)}), flush=True)
     else:
