@@ -223,6 +223,19 @@ int ng_lsgan_loss(const float* p, int64_t n, float target, float* loss, int32_t 
 int ng_g_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
                       const float* weights4, float* out4, float* dpred, float* scratch, void* stream);
 
+/* Every term of RemoteSensingIndices (utils/remote_sensing_indices.py:84-319) plus the pix2pix L1 term in one pass over
+ * NCHW fp32 planes.  Term order (= the reference's iteration order, :45-52): 0 L1(pred, nir), 1 NDVI, 2 NDWI, 3 GNDVI,
+ * 4 SAVI, 5 MSAVI, 6 EVI; out8[k] = mean criterion of term k for the terms selected by bit k of `mask` (0 otherwise;
+ * out8 has room for 8 floats).  criterion 0 = l1, 1 = l2 (F.mse_loss) for the six indices.  dpred (optional) =
+ * d( sum_k weights7[k] * term_k ) / dpred.  scratch: >= 8*1024 floats. */
+int ng_rs_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
+                       const float* weights7, int32_t criterion, int32_t mask, float* out8, float* dpred,
+                       float* scratch, void* stream);
+/* 'index' mode: the index maps of the target and of the prediction (which = 1..6 as above); loss_eps != 0 keeps the
+ * loss-mode epsilons, 0 gives the index-mode formulas (remote_sensing_indices.py:101,137,304-316) */
+int ng_rs_index(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW, int32_t which,
+                int32_t loss_eps, float* out_target, float* out_pred, void* stream);
+
 /* Adam (torch defaults: eps 1e-8, no weight decay, bias-corrected) on a flat fp32 parameter vector */
 int ng_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int32_t step, float grad_scale, void* stream);

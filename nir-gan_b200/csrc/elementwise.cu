@@ -460,6 +460,120 @@ g_pixel_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ nir
 }
 
 // ---------------------------------------------------------------------------------------------
+// All of RemoteSensingIndices (utils/remote_sensing_indices.py:84-319) + the pix2pix L1 term in one pass.
+// term order: 0 = L1(pred, nir), 1 = NDVI, 2 = NDWI, 3 = GNDVI, 4 = SAVI, 5 = MSAVI, 6 = EVI (the reference's iteration
+// order, :45-52).  `mask` selects the terms to evaluate (the kernel is ALU-bound once all six indices are on);
+// criterion 0 = l1 (F.l1_loss), 1 = l2 (F.mse_loss) for the six indices.  Also writes
+// dpred = d( sum_i w_i * term_i ) / dpred.
+// ---------------------------------------------------------------------------------------------
+struct RsPix {
+  float it, ip, dip;     // index of the target, of the prediction, d(index of the prediction)/dpred
+};
+__device__ __forceinline__ RsPix rs_ndvi(float t, float p, float band, float eps) {
+  const float dp = p + band + eps;
+  return {(t - band) / (t + band + eps), (p - band) / dp, (2.f * band + eps) / (dp * dp)};
+}
+__device__ __forceinline__ RsPix rs_gndvi(float t, float p, float R, float G) {
+  // (n - G) / (ndvi(n) + G) with ndvi(n) = (n - R) / (n + R), no epsilon (remote_sensing_indices.py:169-176)
+  const float ndt = (t - R) / (t + R), ndp = (p - R) / (p + R);
+  const float dnd = 2.f * R / ((p + R) * (p + R));
+  const float den = ndp + G;
+  return {(t - G) / (ndt + G), (p - G) / den, (den - (p - G) * dnd) / (den * den)};
+}
+__device__ __forceinline__ RsPix rs_savi(float t, float p, float R) {
+  const float dp = p + R + 0.5f;
+  return {1.5f * (t - R) / (t + R + 0.5f), 1.5f * (p - R) / dp, 1.5f * (2.f * R + 0.5f) / (dp * dp)};
+}
+__device__ __forceinline__ RsPix rs_msavi(float t, float p, float R) {
+  const float st = sqrtf((2.f * t + 1.f) * (2.f * t + 1.f) - 8.f * (t - R));
+  const float sp = sqrtf((2.f * p + 1.f) * (2.f * p + 1.f) - 8.f * (p - R));
+  return {(2.f * t + 1.f - st) / 2.f, (2.f * p + 1.f - sp) / 2.f, 1.f - (2.f * p - 1.f) / sp};
+}
+__device__ __forceinline__ RsPix rs_evi(float t, float p, float R, float Bl, float eps) {
+  const float k = (R - 7.5f) * (Bl + 1.f);
+  const float dt = (t + 6.f) * k + eps, dp = (p + 6.f) * k + eps;
+  return {2.5f * ((t - R) / dt), 2.5f * ((p - R) / dp), 2.5f * (k * (6.f + R) + eps) / (dp * dp)};
+}
+__device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
+
+struct RsWeights { float w[7]; };
+
+__global__ void __launch_bounds__(256)
+rs_pixel_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ nir, const float* __restrict__ pred,
+                     int B, int HW, RsWeights wt, int criterion, int mask, float inv_n, float* __restrict__ partial,
+                     float* __restrict__ dpred) {
+  float acc[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) acc[k] = 0.f;
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), q = (int)(i % HW);
+    const float R = rgb[((size_t)n * 3 + 0) * HW + q], G = rgb[((size_t)n * 3 + 1) * HW + q],
+                Bl = rgb[((size_t)n * 3 + 2) * HW + q];
+    const float t = nir[i], p = pred[i];
+    float g = 0.f;
+    if (mask & 1) {
+      const float d0 = p - t;
+      acc[0] += fabsf(d0);
+      g += wt.w[0] * sgn(d0);
+    }
+    auto term = [&](int k, const RsPix& x) {
+      const float df = x.it - x.ip;
+      if (criterion == 0) { acc[k] += fabsf(df); g += wt.w[k] * (-sgn(df)) * x.dip; }
+      else { acc[k] = fmaf(df, df, acc[k]); g += wt.w[k] * (-2.f * df) * x.dip; }
+    };
+    if (mask & 2) term(1, rs_ndvi(t, p, R, 1e-6f));
+    if (mask & 4) term(2, rs_ndvi(t, p, G, 1e-6f));
+    if (mask & 8) term(3, rs_gndvi(t, p, R, G));
+    if (mask & 16) term(4, rs_savi(t, p, R));
+    if (mask & 32) term(5, rs_msavi(t, p, R));
+    if (mask & 64) term(6, rs_evi(t, p, R, Bl, 1e-6f));
+    if (dpred) dpred[i] = g * inv_n;
+  }
+  __shared__ float red[7][8];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const float v = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float tsum = 0.f;
+    if (threadIdx.x < 7)
+      for (int i = 0; i < 8; ++i) tsum += red[threadIdx.x][i];
+    partial[(size_t)blockIdx.x * 8 + threadIdx.x] = tsum;
+  }
+}
+
+// 'index' mode of RemoteSensingIndices: the index maps themselves (target, prediction); eps as in the reference
+// (loss_eps != 0 reproduces the loss-mode epsilons, 0 the index-mode formulas)
+__global__ void __launch_bounds__(256)
+rs_index_kernel(const float* __restrict__ rgb, const float* __restrict__ nir, const float* __restrict__ pred, int B,
+                int HW, int which, int loss_eps, float* __restrict__ out_t, float* __restrict__ out_p) {
+  const long long total = (long long)B * HW;
+  const float eps = loss_eps ? 1e-6f : 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), q = (int)(i % HW);
+    const float R = rgb[((size_t)n * 3 + 0) * HW + q], G = rgb[((size_t)n * 3 + 1) * HW + q],
+                Bl = rgb[((size_t)n * 3 + 2) * HW + q];
+    const float t = nir[i], p = pred[i];
+    RsPix x;
+    switch (which) {
+      case 1: x = rs_ndvi(t, p, R, eps); break;
+      case 2: x = rs_ndvi(t, p, G, eps); break;
+      case 3: x = rs_gndvi(t, p, R, G); break;
+      case 4: x = rs_savi(t, p, R); break;
+      case 5: x = rs_msavi(t, p, R); break;
+      default: x = rs_evi(t, p, R, Bl, eps); break;
+    }
+    out_t[i] = x.it;
+    out_p[i] = x.ip;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Adam
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -778,6 +892,35 @@ extern "C" int ng_g_pixel_losses(const float* rgb, const float* nir, const float
   NG_LAUNCH_CHECK("g_pixel_loss_kernel");
   reduce_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, (int)blocks, 4, 1.0f / (float)total, out4, 0);
   NG_LAUNCH_CHECK("reduce_partials_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_rs_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
+                                  const float* weights7, int32_t criterion, int32_t mask, float* out7, float* dpred,
+                                  float* scratch, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(rgb && nir && pred && out7 && scratch && weights7, NG_E_ARG, "rs_pixel_losses: bad arguments");
+  NG_REQUIRE((criterion == 0 || criterion == 1) && mask > 0 && mask < 128, NG_E_ARG, "rs_pixel_losses: bad criterion / mask");
+  const long long total = (long long)B * HW;
+  unsigned blocks = grid_for(total, 256);
+  if (blocks > 1024) blocks = 1024;
+  RsWeights wt;
+  for (int k = 0; k < 7; ++k) wt.w[k] = weights7[k];
+  rs_pixel_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, nir, pred, B, HW, wt, criterion, mask,
+                                                                1.0f / (float)total, scratch, dpred);
+  NG_LAUNCH_CHECK("rs_pixel_loss_kernel");
+  reduce_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, (int)blocks, 8, 1.0f / (float)total, out7, 0);
+  NG_LAUNCH_CHECK("reduce_partials_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_rs_index(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW, int32_t which,
+                           int32_t loss_eps, float* out_target, float* out_pred, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(rgb && nir && pred && out_target && out_pred && which >= 1 && which <= 6, NG_E_ARG, "rs_index: bad arguments");
+  rs_index_kernel<<<grid_for((long long)B * HW, 256), 256, 0, (cudaStream_t)stream>>>(rgb, nir, pred, B, HW, which,
+                                                                                     loss_eps, out_target, out_pred);
+  NG_LAUNCH_CHECK("rs_index_kernel");
   return NG_OK;
 }
 

@@ -78,3 +78,65 @@ def pixel_losses(rgb, nir, pred, weights4):
     for t, n in ((rgb, "rgb"), (nir, "nir"), (pred, "pred")):
         require_cuda(t, n)
     return _PixelLossFn.apply(rgb, nir, pred, tuple(weights4))
+
+
+# term order of ng_rs_pixel_losses = the reference's iteration order (utils/remote_sensing_indices.py:45-52)
+RS_TERMS = ("l1", "ndvi", "ndwi", "gndvi", "savi", "msavi", "evi")
+
+
+class _RsPixelLossFn(torch.autograd.Function):
+    """One pass over (rgb, nir, pred): [L1, NDVI, NDWI, GNDVI, SAVI, MSAVI, EVI] means (criterion l1 / l2 for the six
+    indices) for the terms in `mask`, and d(sum_k w_k * term_k)/dpred for the backward (weights fixed at call time)."""
+
+    @staticmethod
+    def forward(ctx, rgb, nir, pred, weights, criterion, mask):
+        B, _, H, W = pred.shape
+        rgb, nir, p = rgb.contiguous().float(), nir.contiguous().float(), pred.contiguous().float()
+        out = torch.empty(8, dtype=torch.float32, device=p.device)
+        scratch = torch.empty(8 * 1024, dtype=torch.float32, device=p.device)
+        need_grad = pred.requires_grad
+        dpred = torch.empty_like(p) if need_grad else None
+        w = (L.c_f32 * 7)(*[float(v) for v in weights])
+        L.call("ng_rs_pixel_losses", rgb.data_ptr(), nir.data_ptr(), p.data_ptr(), B, H * W, w, int(criterion), int(mask),
+               out.data_ptr(), dpred.data_ptr() if need_grad else None, scratch.data_ptr(), _stream(p))
+        if need_grad:
+            ctx.save_for_backward(dpred)
+        ctx.weights = [float(v) for v in weights]
+        return out[:7]
+
+    @staticmethod
+    def backward(ctx, gout):
+        # term_k enters the total loss as w_k * term_k, so gout == weights up to a common factor c
+        (dpred,) = ctx.saved_tensors
+        c = None
+        for i, w in enumerate(ctx.weights):
+            if w != 0.0:
+                c = gout[i] / w
+                break
+        if c is None:
+            return None, None, torch.zeros_like(dpred), None, None, None
+        return None, None, dpred * c, None, None, None
+
+
+def rs_pixel_losses(rgb, nir, pred, weights7, criterion: str = "l1", mask: int = None):
+    """weights7 = weights the caller will apply to (L1, NDVI, NDWI, GNDVI, SAVI, MSAVI, EVI); terms with a non-zero
+    weight are evaluated (or exactly those in `mask`).  Returns the 7 means (0 for unselected terms)."""
+    for t, n in ((rgb, "rgb"), (nir, "nir"), (pred, "pred")):
+        require_cuda(t, n)
+    if mask is None:
+        mask = sum(1 << k for k, w in enumerate(weights7) if float(w) != 0.0)
+    if mask == 0:
+        return torch.zeros(7, dtype=torch.float32, device=pred.device)
+    return _RsPixelLossFn.apply(rgb, nir, pred, tuple(weights7), 0 if criterion == "l1" else 1, int(mask))
+
+
+def rs_index(rgb, nir, pred, which: str, loss_eps: bool):
+    """Index maps (target, prediction) of one remote-sensing index, shape of `nir`."""
+    for t, n in ((rgb, "rgb"), (nir, "nir"), (pred, "pred")):
+        require_cuda(t, n)
+    B, _, H, W = pred.shape
+    rgb, nir, p = rgb.contiguous().float(), nir.contiguous().float(), pred.contiguous().float()
+    a, b = torch.empty_like(p), torch.empty_like(p)
+    L.call("ng_rs_index", rgb.data_ptr(), nir.data_ptr(), p.data_ptr(), B, H * W, RS_TERMS.index(which), int(loss_eps),
+           a.data_ptr(), b.data_ptr(), _stream(p))
+    return a, b

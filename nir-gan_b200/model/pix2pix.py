@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import networks
 from .generator_inject import define_G_inject
-from ..losses import pixel_losses
+from ..losses import rs_pixel_losses
 
 
 def _get(cfg, name, default=None):
@@ -108,11 +108,14 @@ class Px2Px(nn.Module):
         lam_rs = float(_get(o, "lambda_rs_losses", 0.0))
         w = _get(o, "internal_rs_loss_weights", None)
         wd = dict(w) if isinstance(w, dict) else (vars(w) if w is not None else {})
-        if lam_rs > 0.0 and _get(o, "rs_losses_criterium", "l1") != "l1":
-            raise NotImplementedError("rs_losses_criterium other than 'l1' is outside the hot path")
-        ws = [float(o.lambda_L1)] + [lam_rs * max(float(wd.get(k, 0.0)), 0.0) if lam_rs > 0.0 else 0.0
-                                     for k in ("lambda_ndvi", "lambda_ndwi", "lambda_evi")]
-        parts = pixel_losses(rgb, nir, pred, ws)    # one fused pass: L1 + NDVI + NDWI + EVI (+ d/dpred)
+        crit = _get(o, "rs_losses_criterium", "l1")
+        if crit not in ("l1", "l2"):
+            raise NotImplementedError(f"Criterion '{crit}' not implemented. 'l1' or 'l2' are supported.")
+        # term order of the fused kernel = the reference's iteration order (remote_sensing_indices.py:45-52)
+        keys = ("lambda_ndvi", "lambda_ndwi", "lambda_gndvi", "lambda_savi", "lambda_msavi", "lambda_evi")
+        ws = [float(o.lambda_L1)] + [lam_rs * float(wd.get(k, 0.0)) if (lam_rs > 0.0 and float(wd.get(k, 0.0)) > 0.0)
+                                     else 0.0 for k in keys]
+        parts = rs_pixel_losses(rgb, nir, pred, ws, crit)    # one fused pass: L1 + the weighted indices (+ d/dpred)
         for wi, pi in zip(ws, parts):
             if wi != 0.0:
                 loss_G = loss_G + wi * pi

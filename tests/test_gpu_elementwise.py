@@ -144,6 +144,55 @@ def test_lsgan_and_pixel_losses_match_oracle(golden_dir):
     assert float((dd.grad - 2 * (d_out - 1.0) / d_out.numel()).abs().max()) <= 1e-7
 
 
+@pytest.mark.parametrize("criterion", ["l1", "l2"])
+def test_all_six_indices_and_modes_match_oracle(criterion):
+    """RemoteSensingIndices: every index, both criteria, 'loss' / 'logging_dict' / 'index' modes, and d/dpred of the
+    weighted sum against torch autograd of the oracle (utils/remote_sensing_indices.py:23-319, pinned in
+    tests/golden/PIN_REPORT.txt as rs_all6_rel)."""
+    import nirgan_oracle as O
+    from nirgan_b200.utils.remote_sensing_indices import RemoteSensingIndices
+    g = torch.Generator().manual_seed(21)
+    rgb = (0.05 + 0.6 * torch.rand(3, 3, 40, 56, generator=g)).cuda()      # reflectance-like, denominators away from 0
+    nir = (0.1 + 0.7 * torch.rand(3, 1, 40, 56, generator=g)).cuda()
+    pred = (0.1 + 0.7 * torch.rand(3, 1, 40, 56, generator=g)).cuda()
+    cfg = {"lambda_ndvi": 0.3, "lambda_ndwi": 0.2, "lambda_gndvi": 0.15, "lambda_savi": 0.1, "lambda_msavi": 0.25,
+           "lambda_evi": 0.4}
+    rs = RemoteSensingIndices(mode="loss", criterion=criterion)
+    pc = pred.clone().requires_grad_(True)
+    total = rs.get_and_weight_losses(rgb, nir, pc, cfg)
+    total.backward()
+    po = pred.clone().requires_grad_(True)
+    ref = O.rs_weighted_loss(rgb, nir, po, cfg, criterion)
+    ref.backward()
+    assert abs(float(total) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref)))
+    assert float((pc.grad - po.grad).norm() / po.grad.norm()) <= 2e-5
+    # a zero / negative weight switches the index off, as `if weight > 0.0` does in the reference
+    cfg2 = dict(cfg, lambda_savi=0.0, lambda_msavi=-1.0)
+    assert abs(float(rs.get_and_weight_losses(rgb, nir, pred, cfg2)) -
+               float(O.rs_weighted_loss(rgb, nir, pred, cfg2, criterion))) <= 2e-5
+    # logging_dict and the single-index methods
+    log = rs.get_and_weight_losses(rgb, nir, pred, mode="logging_dict")
+    pairs = {"ndvi": O.ndvi_pair, "ndwi": O.ndwi_pair, "gndvi": O.gndvi_pair, "savi": O.savi_pair, "msavi": O.msavi_pair,
+             "evi": O.evi_pair}
+    for name, fn in pairs.items():
+        a, b = fn(rgb, nir, pred)
+        want = float(O._crit(a, b, criterion))
+        assert abs(float(log[f"indices_loss/{name}_error"]) - want) <= 2e-5 * max(1.0, abs(want)), name
+        assert abs(float(getattr(rs, name + "_calculation")(rgb, nir, pred)) - want) <= 2e-5 * max(1.0, abs(want)), name
+    # index mode: the maps themselves, without the loss-mode epsilons; 3-D inputs are promoted like the reference does
+    ri = RemoteSensingIndices(mode="index", criterion=criterion)
+    for name, fn in pairs.items():
+        kw = {"eps": 0.0} if name in ("ndvi", "ndwi") else ({"loss_mode": False} if name == "evi" else {})
+        a, b = fn(rgb, nir, pred, **kw)
+        ga, gb = getattr(ri, name + "_calculation")(rgb, nir, pred)
+        assert float((ga - a).abs().max()) <= 1e-5 * max(1.0, float(a.abs().max())), name
+        assert float((gb - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max())), name
+    ga, _ = ri.ndvi_calculation(rgb[0], nir[0], pred[0])
+    assert ga.shape == (1, 1, 40, 56)
+    with pytest.raises(NotImplementedError, match="logging_dict"):
+        rs.get_and_weight_losses(rgb, nir, pred, mode="nope")
+
+
 def test_adam_matches_torch():
     from nirgan_b200 import _lib as L
     import helpers as Hh
