@@ -364,7 +364,7 @@ def main():
                          "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / pk["hbm_gbs"],
                          "bytes_per_step_slice": ap_bytes, "ms_per_step_slice": ap_ms, "peak_source": pk["src"]},
         "model_tflops": value * gflop_tile / 1e3,
-        "model_frac_of_sustained_peak": value * gflop_tile / 1e3 / pk["tf_sustained"],
+        "model_frac_of_sustained_peak": value * gflop_tile / 1e3 / (pk["tf_sustained"] * world),
         "op_ms": {k: round(sum(v), 4) for k, v in by_name.items()},
     }
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
