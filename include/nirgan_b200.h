@@ -240,6 +240,17 @@ int ng_rs_index(const float* rgb, const float* nir, const float* pred, int32_t B
 int ng_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int32_t step, float grad_scale, void* stream);
 
+/* Multi-tensor Adam: one launch for every parameter of an optimizer.  params_dev / offsets_dev: device arrays of
+ * `ntensors` parameter pointers and their element offsets into the flat gradient / moment arenas g, m, v (`total`
+ * elements).  step_counter_dev: device int32 holding the number of updates applied so far (advanced here, used for the
+ * bias corrections).  skip_flag (device, optional): a non-zero value makes the whole call a no-op (see
+ * ng_nonfinite_flag) -- torch.cuda.amp-style step skipping without a host round trip. */
+int ng_adam_multi(void* const* params_dev, const int64_t* offsets_dev, int32_t ntensors, const float* g, float* m,
+                  float* v, int64_t total, float lr, float beta1, float beta2, float eps, int32_t* step_counter_dev,
+                  float grad_scale, const int32_t* skip_flag, void* stream);
+/* flag[0] = 1 if any of the n floats is inf or NaN, else 0 */
+int ng_nonfinite_flag(const float* x, int64_t n, int32_t* flag, void* stream);
+
 /* ---- post-processing after the generator (create_synthetic_dataset.py:34-52,111-118) ---------- */
 /* plane resize with F.interpolate semantics: mode 0 'nearest' (the scale_factor=4 upsampling of the Sentinel-2 NIR,
  * create_synthetic_dataset.py:111), mode 1 'bilinear' align_corners=False (histogram_match, :37).  fp32 planes. */

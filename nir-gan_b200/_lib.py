@@ -70,6 +70,9 @@ _SIGNATURES = {
     "ng_g_pixel_losses": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ng_rs_pixel_losses": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "ng_rs_index": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "ng_adam_multi": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_vp, c_f32, c_vp,
+                              c_vp]),
+    "ng_nonfinite_flag": (c_i32, [c_vp, c_i64, c_vp, c_vp]),
     "ng_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -591,6 +591,45 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }
 
 
+// Multi-tensor Adam over a flat gradient / moment arena: parameter tensors stay where the nn.Module keeps them (table of
+// pointers + element offsets into the arena), so one launch updates every parameter of an optimizer.  `skip` (device
+// flag, e.g. "a gradient is not finite") turns the launch into a no-op without a host round trip.
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(float* const* __restrict__ params, const long long* __restrict__ offsets, int ntensors,
+                  const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long total, float lr,
+                  float b1, float b2, float eps, float gscale, const int* __restrict__ step_dev,
+                  const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  // bias corrections from the device-side step counter (already advanced for this step by adam_advance_kernel)
+  const float stepf = (float)(*step_dev);
+  const float bc1 = 1.f - powf(b1, stepf), bc2_sqrt = sqrtf(1.f - powf(b2, stepf));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = ntensors - 1;                       // last tensor whose offset <= i
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (offsets[mid] <= i) lo = mid; else hi = mid - 1; }
+    float* p = params[lo] + (i - offsets[lo]);
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    *p -= (lr / bc1) * (mi / denom);
+  }
+}
+
+__global__ void adam_advance_kernel(int* __restrict__ step_dev, const int* __restrict__ skip) {
+  if (!(skip && *skip)) *step_dev += 1;
+}
+
+// flag[0] = 1 if any element of x is inf / NaN (flag must be zeroed by the caller's memset, done in the entry point)
+__global__ void __launch_bounds__(256)
+nonfinite_flag_kernel(const float* __restrict__ x, long long n, int* __restrict__ flag) {
+  bool bad = false;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    bad |= (__float_as_uint(x[i]) & 0x7f800000u) == 0x7f800000u;
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // generator stem in row-merged form (see ng_prep_stem in the header): one thread = one 16-byte
 // (kw, 8-channel) group of one output pixel.
@@ -932,6 +971,31 @@ extern "C" int ng_adam_step(float* p, const float* g, float* m, float* v, int64_
   adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (long long)n, lr, beta1, beta2, eps, bc1,
                                                                  sqrtf(bc2), grad_scale);
   NG_LAUNCH_CHECK("adam_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_adam_multi(void* const* params_dev, const int64_t* offsets_dev, int32_t ntensors, const float* g,
+                             float* m, float* v, int64_t total, float lr, float beta1, float beta2, float eps,
+                             int32_t* step_counter_dev, float grad_scale, const int32_t* skip_flag, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(params_dev && offsets_dev && g && m && v && step_counter_dev && ntensors > 0 && total > 0, NG_E_ARG,
+             "adam_multi: bad arguments");
+  adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter_dev, skip_flag);
+  NG_LAUNCH_CHECK("adam_advance_kernel");
+  adam_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float* const*>(params_dev), reinterpret_cast<const long long*>(offsets_dev), ntensors, g, m, v,
+      (long long)total, lr, beta1, beta2, eps, grad_scale, step_counter_dev, skip_flag);
+  NG_LAUNCH_CHECK("adam_multi_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_nonfinite_flag(const float* x, int64_t n, int32_t* flag, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(x && flag && n > 0, NG_E_ARG, "nonfinite_flag: bad arguments");
+  int e = check_cuda(cudaMemsetAsync(flag, 0, sizeof(int32_t), (cudaStream_t)stream), "nonfinite_flag memset");
+  if (e) return e;
+  nonfinite_flag_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (long long)n, flag);
+  NG_LAUNCH_CHECK("nonfinite_flag_kernel");
   return NG_OK;
 }
 

@@ -99,7 +99,8 @@ def main():
                       "g_forward_reused": model.reuse_g_forward,
                       "loss_D": float(ld), "loss_G": float(lg),
                       "mem_gb": torch.cuda.max_memory_allocated() / 1e9,
-                      "skipped_steps": [opt_d.skipped_steps, opt_g.skipped_steps]}))
+                      "skipped_steps": [opt_d.skipped_steps, opt_g.skipped_steps],
+                      "adam_arena_steps": [opt_d.fast_steps, opt_g.fast_steps]}))
 
 
 if __name__ == "__main__":
