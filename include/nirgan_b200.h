@@ -267,6 +267,13 @@ int ng_hist_match(const float* image, const float* reference, int32_t B, int32_t
 int ng_sort_segments(const float* src, int32_t segs, int32_t n, float* sorted_out, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
+/* Validation metrics (utils/calculate_metrics.py:6-37): out4 = { F.l1_loss, F.mse_loss, kornia.metrics.psnr(.., max_val),
+ * kornia.metrics.ssim(.., window, max_val).mean() } over `planes` = B*C fp32 planes of HxW.  window odd, <= 11 (5 in
+ * calculate_metrics, 11 in utils/losses.py::ssim_loss).  scratch: ng_image_metrics_scratch_floats() floats. */
+int64_t ng_image_metrics_scratch_floats(int32_t planes, int32_t H, int32_t W);
+int ng_image_metrics(const float* pred, const float* target, int32_t planes, int32_t H, int32_t W, int32_t window,
+                     float max_val, float* out4, float* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

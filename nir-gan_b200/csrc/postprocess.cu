@@ -281,3 +281,117 @@ extern "C" int ng_resize_plane(const float* src, int32_t planes, int32_t h, int3
   NG_LAUNCH_CHECK("resize_plane_kernel");
   return NG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Validation metrics on the device (utils/calculate_metrics.py:6-37): L1, L2, PSNR and the mean
+// SSIM map of kornia.metrics.ssim (kornia==0.7.3, requirements.txt:9): Gaussian window (sigma 1.5), 'same' padding with
+// a reflect border, C1 = (0.01 max)^2, C2 = (0.03 max)^2, eps 1e-12:
+//   num / (den + eps),  num = (2 mu1 mu2 + C1)(2 s12 + C2),  den = (mu1^2 + mu2^2 + C1)(s1 + s2 + C2)
+// One block = a 32 x 8 output tile of one plane; the (32+w-1) x (8+w-1) haloed tiles of both images are staged in shared
+// memory and the five windowed moments are accumulated directly (window 5 or 11).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace ng {
+
+constexpr int MT_W = 32, MT_H = 8, MT_MAXWIN = 11;
+
+__global__ void __launch_bounds__(256)
+image_metrics_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int win, float c1, float c2,
+                     const float* __restrict__ gauss, float* __restrict__ partial, int tiles_x, int tiles_y) {
+  __shared__ float sa[(MT_H + MT_MAXWIN - 1) * (MT_W + MT_MAXWIN - 1)];
+  __shared__ float sb[(MT_H + MT_MAXWIN - 1) * (MT_W + MT_MAXWIN - 1)];
+  __shared__ float gk[MT_MAXWIN];
+  __shared__ float red[3][8];
+  const int half = win / 2, PW = MT_W + win - 1, PH = MT_H + win - 1;
+  int t = blockIdx.x;
+  const int tx0 = (t % tiles_x) * MT_W; t /= tiles_x;
+  const int ty0 = (t % tiles_y) * MT_H;
+  const size_t plane = (size_t)(t / tiles_y) * H * W;
+  if (threadIdx.x < win) gk[threadIdx.x] = gauss[threadIdx.x];
+  for (int i = threadIdx.x; i < PH * PW; i += 256) {
+    const int py = i / PW, px = i - py * PW;
+    const int gy = reflect_idx(min(max(ty0 + py - half, -(H - 1)), 2 * (H - 1)), H);
+    const int gx = reflect_idx(min(max(tx0 + px - half, -(W - 1)), 2 * (W - 1)), W);
+    sa[i] = a[plane + (size_t)gy * W + gx];
+    sb[i] = b[plane + (size_t)gy * W + gx];
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % MT_W, ly = threadIdx.x / MT_W;
+  const int ox = tx0 + lx, oy = ty0 + ly;
+  float l1 = 0.f, l2 = 0.f, ss = 0.f;
+  if (ox < W && oy < H) {
+    float m1 = 0.f, m2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    for (int ky = 0; ky < win; ++ky) {
+      float r1 = 0.f, r2 = 0.f, r11 = 0.f, r22 = 0.f, r12 = 0.f;
+      for (int kx = 0; kx < win; ++kx) {
+        const float x = sa[(ly + ky) * PW + lx + kx], y = sb[(ly + ky) * PW + lx + kx], g = gk[kx];
+        r1 = fmaf(g, x, r1); r2 = fmaf(g, y, r2);
+        r11 = fmaf(g, x * x, r11); r22 = fmaf(g, y * y, r22); r12 = fmaf(g, x * y, r12);
+      }
+      const float g = gk[ky];
+      m1 = fmaf(g, r1, m1); m2 = fmaf(g, r2, m2);
+      e11 = fmaf(g, r11, e11); e22 = fmaf(g, r22, e22); e12 = fmaf(g, r12, e12);
+    }
+    const float s1 = e11 - m1 * m1, s2 = e22 - m2 * m2, s12 = e12 - m1 * m2;
+    const float num = (2.f * m1 * m2 + c1) * (2.f * s12 + c2);
+    const float den = (m1 * m1 + m2 * m2 + c1) * (s1 + s2 + c2);
+    ss = num / (den + 1e-12f);
+    const float d = sa[(ly + half) * PW + lx + half] - sb[(ly + half) * PW + lx + half];
+    l1 = fabsf(d);
+    l2 = d * d;
+  }
+  l1 = warp_sum(l1); l2 = warp_sum(l2); ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = l1; red[1][threadIdx.x >> 5] = l2; red[2][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[threadIdx.x][i];
+    partial[(size_t)blockIdx.x * 4 + threadIdx.x] = s;
+  }
+  if (threadIdx.x == 3) partial[(size_t)blockIdx.x * 4 + 3] = 0.f;
+}
+
+// out[0] = L1, out[1] = L2 (MSE), out[2] = PSNR = 10 log10(max^2 / MSE), out[3] = mean SSIM   (fixed-order sums, fp64)
+__global__ void image_metrics_finalize_kernel(const float* __restrict__ partial, int nblocks, double inv_n, float max_val,
+                                              float* __restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= 3) return;
+  double s = 0.0;
+  for (int i = 0; i < nblocks; ++i) s += partial[(size_t)i * 4 + j];
+  const double mean = s * inv_n;
+  if (j == 0) out[0] = (float)mean;
+  if (j == 1) { out[1] = (float)mean; out[2] = (float)(10.0 * log10((double)max_val * max_val / mean)); }
+  if (j == 2) out[3] = (float)mean;
+}
+
+}  // namespace ng
+
+extern "C" int64_t ng_image_metrics_scratch_floats(int32_t planes, int32_t H, int32_t W) {
+  if (planes <= 0 || H <= 0 || W <= 0) return NG_E_ARG;
+  return (int64_t)planes * ((H + MT_H - 1) / MT_H) * ((W + MT_W - 1) / MT_W) * 4 + MT_MAXWIN;
+}
+
+extern "C" int ng_image_metrics(const float* pred, const float* target, int32_t planes, int32_t H, int32_t W,
+                                int32_t window, float max_val, float* out4, float* scratch, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(pred && target && out4 && scratch && planes > 0 && H > 0 && W > 0, NG_E_ARG, "image_metrics: bad arguments");
+  NG_REQUIRE(window % 2 == 1 && window >= 1 && window <= MT_MAXWIN, NG_E_UNSUPPORTED, "image_metrics: odd window <= 11");
+  NG_REQUIRE(window / 2 < H && window / 2 < W, NG_E_SHAPE, "image_metrics: window larger than the image");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles_x = (W + MT_W - 1) / MT_W, tiles_y = (H + MT_H - 1) / MT_H;
+  const long long blocks = (long long)planes * tiles_x * tiles_y;
+  NG_REQUIRE(blocks < (1ll << 31), NG_E_SHAPE, "image_metrics: too many tiles");
+  // normalised Gaussian window, sigma 1.5 (kornia get_gaussian_kernel1d), computed on the host in fp32 like torch does
+  float g[MT_MAXWIN];
+  float sum = 0.f;
+  for (int i = 0; i < window; ++i) { const float x = (float)(i - window / 2); g[i] = expf(-(x * x) / (2.f * 1.5f * 1.5f)); sum += g[i]; }
+  for (int i = 0; i < window; ++i) g[i] /= sum;
+  float* gdev = scratch + blocks * 4;
+  int e = check_cuda(cudaMemcpyAsync(gdev, g, sizeof(float) * window, cudaMemcpyHostToDevice, st), "image_metrics window");
+  if (e) return e;
+  const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
+  image_metrics_kernel<<<(unsigned)blocks, 256, 0, st>>>(pred, target, H, W, window, c1, c2, gdev, scratch, tiles_x, tiles_y);
+  NG_LAUNCH_CHECK("image_metrics_kernel");
+  image_metrics_finalize_kernel<<<1, 32, 0, st>>>(scratch, (int)blocks, 1.0 / ((double)planes * H * W), max_val, out4);
+  NG_LAUNCH_CHECK("image_metrics_finalize_kernel");
+  return NG_OK;
+}

@@ -56,3 +56,44 @@ def postprocess(pred: torch.Tensor, s2_nir: torch.Tensor) -> torch.Tensor:
     """create_synthetic_dataset.py:111-116: nearest x4 upsampling of the Sentinel-2 NIR, histogram matching, float16."""
     s2_nir_int = F.interpolate(s2_nir, scale_factor=4)
     return histogram_match(pred, s2_nir_int).to(torch.float16)
+
+
+# --------------------------------------------------------------------------------------
+# validation metrics (utils/calculate_metrics.py:6-37) -- kornia==0.7.3 (requirements.txt:9) is not installed here;
+# its published algorithms are restated: kornia.metrics.psnr = 10 log10(max_val^2 / mse), kornia.metrics.ssim =
+# Gaussian window (sigma 1.5, normalised), filter2d_separable with border_type 'reflect' and 'same' padding,
+# C1 = (0.01 max_val)^2, C2 = (0.03 max_val)^2, eps = 1e-12, map = num / (den + eps).  PARITY UNPINNED (no kornia).
+# --------------------------------------------------------------------------------------
+def gaussian_kernel1d(window_size: int, sigma: float = 1.5) -> torch.Tensor:
+    x = torch.arange(window_size, dtype=torch.float32) - window_size // 2
+    g = torch.exp(-(x ** 2) / (2.0 * sigma ** 2))
+    return g / g.sum()
+
+
+def _filter(x: torch.Tensor, k1: torch.Tensor) -> torch.Tensor:
+    p = k1.numel() // 2
+    C = x.shape[1]
+    x = F.pad(x, (p, p, p, p), mode="reflect")
+    kx = k1.view(1, 1, 1, -1).repeat(C, 1, 1, 1)
+    ky = k1.view(1, 1, -1, 1).repeat(C, 1, 1, 1)
+    return F.conv2d(F.conv2d(x, kx, groups=C), ky, groups=C)
+
+
+def ssim_map(img1: torch.Tensor, img2: torch.Tensor, window_size: int, max_val: float = 1.0, eps: float = 1e-12):
+    k = gaussian_kernel1d(window_size)
+    C1, C2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    mu1, mu2 = _filter(img1, k), _filter(img2, k)
+    s1 = _filter(img1 ** 2, k) - mu1 ** 2
+    s2 = _filter(img2 ** 2, k) - mu2 ** 2
+    s12 = _filter(img1 * img2, k) - mu1 * mu2
+    num = (2.0 * mu1 * mu2 + C1) * (2.0 * s12 + C2)
+    den = (mu1 ** 2 + mu2 ** 2 + C1) * (s1 + s2 + C2)
+    return num / (den + eps)
+
+
+def calculate_metrics(pred: torch.Tensor, target: torch.Tensor, phase: str = "train") -> dict:
+    """utils/calculate_metrics.py:6-37."""
+    mse = F.mse_loss(pred, target)
+    return {phase + "/L1": F.l1_loss(pred, target).item(), phase + "/L2": mse.item(),
+            phase + "/PSNR": (10.0 * torch.log10(1.0 / mse)).item(),
+            phase + "/SSIM": ssim_map(pred, target, 5, 1.0).mean().item()}

@@ -54,3 +54,17 @@ def test_reference_loop_shapes_and_dtype():
     assert out.shape == (2, 1, 32, 32) and out.dtype == torch.float16
     for b in range(2):                                  # every output value is between two reference values
         assert float(out[b].min()) >= float(s2[b].min()) - 1e-3 and float(out[b].max()) <= float(s2[b].max()) + 1e-3
+
+
+def test_metrics_oracle_properties():
+    g = torch.Generator().manual_seed(4)
+    a = torch.rand(2, 1, 40, 52, generator=g)
+    m = P.calculate_metrics(a, a, "val")
+    assert m["val/L1"] == 0.0 and m["val/L2"] == 0.0 and m["val/PSNR"] == float("inf")
+    assert abs(m["val/SSIM"] - 1.0) <= 1e-6
+    b = (a + 0.1).clamp(0, 1)
+    m = P.calculate_metrics(a, b, "val")
+    assert abs(m["val/PSNR"] - 10 * np.log10(1.0 / m["val/L2"])) <= 1e-4 and 0.0 < m["val/SSIM"] < 1.0
+    assert abs(float(P.gaussian_kernel1d(5).sum()) - 1.0) <= 1e-6
+    # symmetric in its arguments, and a constant shift of both images leaves the structure term unchanged
+    assert abs(float(P.ssim_map(a, b, 5).mean()) - float(P.ssim_map(b, a, 5).mean())) <= 1e-6

@@ -112,3 +112,24 @@ def test_full_size_properties_512():
     qs = torch.tensor([0.1, 0.5, 0.9], device="cuda")
     assert float((torch.quantile(out.view(8, -1), qs, dim=1) - torch.quantile(ref.view(8, -1), qs, dim=1)).abs().max()) <= 1e-3
     assert torch.equal(PP.histogram_match(img, img), img)
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 64, 64), (3, 1, 37, 53), (1, 3, 256, 256), (4, 1, 8, 40)])
+def test_calculate_metrics_matches_oracle(shape):
+    """utils/calculate_metrics.py:6-37 on the device vs the torch restatement of kornia's psnr / ssim."""
+    import postprocess_oracle as P
+    from nirgan_b200.utils.calculate_metrics import calculate_metrics, image_metrics
+    g = torch.Generator().manual_seed(sum(shape))
+    target = torch.rand(*shape, generator=g)
+    pred = (target + 0.08 * torch.randn(*shape, generator=g)).clamp(0, 1)
+    want = P.calculate_metrics(pred, target, "val")
+    got = calculate_metrics(pred.cuda(), target.cuda(), "val")
+    assert set(got) == set(want) == {"val/L1", "val/L2", "val/PSNR", "val/SSIM"}
+    for k in want:
+        assert abs(got[k] - want[k]) <= 2e-5 * max(1.0, abs(want[k])), (k, got[k], want[k])
+    # window 11 (utils/losses.py::ssim_loss) where the image allows it
+    if min(shape[-2:]) > 5:
+        s11 = float(image_metrics(pred.cuda(), target.cuda(), window_size=11)[3])
+        assert abs(s11 - float(P.ssim_map(pred, target, 11).mean())) <= 2e-5
+    same = calculate_metrics(target.cuda(), target.cuda())
+    assert same["train/L1"] == 0.0 and same["train/PSNR"] == float("inf") and abs(same["train/SSIM"] - 1.0) <= 1e-6
