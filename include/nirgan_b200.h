@@ -96,6 +96,12 @@ typedef struct ng_conv_args {
   const float* bias;    /* [Cout] or NULL */
   void* y;              /* RAW/BIAS_ACT: [B][Hout][Wout][Cout] dtype; HEAD: float [B][Hout-2c][Wout-2c] */
   float* stat_partials; /* RAW + TC: [B][ng_conv_stat_slots][Cout][2] (sum, sumsq) or NULL */
+  /* optional fused InstanceNorm finalisation (TC + RAW + stat_partials): the CTA that completes the last tile of an
+   * image reduces that image's partials in a fixed order and writes (mean, rstd) itself, so no separate
+   * ng_in_stats_finalize launch is needed.  tile_counters: [B] int32, zero before the first launch (the kernel leaves
+   * them zero again); mean_rstd: [B][Cout][2]; both NULL = off. */
+  float* mean_rstd;
+  int32_t* tile_counters;
 } ng_conv_args;
 
 int         ng_version(void);

@@ -29,7 +29,8 @@ class ConvArgs(C.Structure):
         "dtype", "impl", "form", "sgn", "B", "Hin", "Win", "Cin", "in_pad", "in_pad_w", "Cout", "KH", "KW", "stride",
         "pad", "pad_w", "Hout", "Wout", "epilogue", "act")] + [
         ("slope", c_f32), ("crop", c_i32), ("reserved", c_i32),
-        ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("y", c_vp), ("stat_partials", c_vp)]
+        ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("y", c_vp), ("stat_partials", c_vp),
+        ("mean_rstd", c_vp), ("tile_counters", c_vp)]
 
 
 _SIGNATURES = {

@@ -40,6 +40,10 @@ struct TcParams {
   const float* bias;
   void* y;
   float* stat_partials;
+  float* mean_rstd;           // fused finalisation (optional)
+  int* tile_counters;
+  int arrivals_per_image;     // epilogue-group arrivals that complete an image
+  float inv_count;            // 1 / (Hout * Wout)
 };
 
 // RT ("row taps", generator stem in row-merged form): the taps of a K x 1 stride-1 convolution only shift the patch by
@@ -63,7 +67,7 @@ struct TcCfg {
   static constexpr int THREADS = 64 + 128 * EG;
   static constexpr int STAGING_BYTES = BN >= 64 ? EG * 128 * EB * 2 : 0;
   static constexpr int RED_BYTES = BN >= 64 ? EG * 2048 : 0;         // cross-row-group stats combine
-  static constexpr int ROWOFF_BYTES = EG * 1024;
+  static constexpr int ROWOFF_BYTES = EG * 1024 + 64;          // + per-group "this group finalises" flags
   static constexpr int BUDGET = 222 * 1024;
   static constexpr int STAGES_RAW = (BUDGET - STAGING_BYTES - RED_BYTES - W_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -378,6 +382,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           bar_sync_id(barid);   // staging (and, after the last pass, rowoff) are reused
         }
+        // ---- fused InstanceNorm finalisation: the group that completes the image's last tile turns the partials
+        // into (mean, rstd).  Release: every partial of this group is written (barrier above) and fenced before the
+        // arrival; acquire: fence after observing the final count.  Fixed summation order -> deterministic.
+        if (p.mean_rstd != nullptr && p.epilogue == NG_EPI_RAW && p.stat_partials != nullptr && !dummy) {
+          int* flagw = reinterpret_cast<int*>(rowoff) + 512 + grp;      // rowoff table has 2 KB, flags live behind 2 x 1 KB
+          __threadfence();
+          bar_sync_id(barid);
+          if (et == 0) {
+            const int old = atomicAdd(&p.tile_counters[n], 1);
+            const int last = old == p.arrivals_per_image - 1;
+            if (last) p.tile_counters[n] = 0;                            // leave the counters zero for the next launch
+            *flagw = last;
+          }
+          bar_sync_id(barid);
+          if (*flagw) {
+            __threadfence();
+            const int Cr = g.Cout_real;
+            const float2* part = reinterpret_cast<const float2*>(p.stat_partials) + (size_t)n * p.stat_slots * Cr;
+            for (int c = et; c < Cr; c += 128) {
+              float s0 = 0.f, q0 = 0.f;
+              for (int k = 0; k < p.stat_slots; ++k) {
+                const float2 v = __ldcg(part + (size_t)k * Cr + c);
+                s0 += v.x; q0 += v.y;
+              }
+              const float m = s0 * p.inv_count;
+              const float var = fmaxf(q0 * p.inv_count - m * m, 0.f);
+              reinterpret_cast<float2*>(p.mean_rstd)[(size_t)n * Cr + c] = make_float2(m, rsqrtf(var + 1e-5f));
+            }
+          }
+          bar_sync_id(barid);                                            // flag word is reused by the next tile
+        }
       }
       if (++as == 2) { as = 0; as_phase ^= 1; }
     }
@@ -471,6 +506,9 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   p.bf16 = a.dtype == NG_BF16;
   p.stat_slots = (g.merged ? 4 : g.nphase) * p.patches_y * p.patches_x;
   p.bias = a.bias; p.y = a.y; p.stat_partials = a.stat_partials;
+  p.mean_rstd = a.mean_rstd; p.tile_counters = a.tile_counters;
+  p.arrivals_per_image = p.patches_y * p.patches_x * g.nphase * p.co_tiles * Cfg::EG;
+  p.inv_count = 1.0f / ((float)g.Hout * (float)g.Wout);
 
   CUtensorMap tmA, tmB;
   const CUtensorMapDataType dt = a.dtype == NG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -564,6 +602,10 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   NG_REQUIRE(bn != 0 && kc != 0, NG_E_UNSUPPORTED, "conv_tc: Cin %d / Cout %d not tileable", a.Cin, a.Cout);
   NG_REQUIRE(a.epilogue != NG_EPI_HEAD || a.Cout == 16, NG_E_SHAPE, "conv_tc: head epilogue expects Cout stored as 16");
   NG_REQUIRE(bn != 16 || a.stat_partials == nullptr, NG_E_UNSUPPORTED, "conv_tc: no InstanceNorm statistics for 16-channel outputs");
+  NG_REQUIRE((a.mean_rstd == nullptr) == (a.tile_counters == nullptr), NG_E_ARG,
+             "conv_tc: fused finalisation needs both mean_rstd and tile_counters");
+  NG_REQUIRE(a.mean_rstd == nullptr || (a.stat_partials != nullptr && a.epilogue == NG_EPI_RAW), NG_E_ARG,
+             "conv_tc: fused finalisation needs the RAW epilogue with stat_partials");
   if (bn == 16 && kc == 64) return launch_tc<16, 64, 1>(a, g, st);
   if (bn == 64 && kc == 16) return launch_tc<64, 16, 1>(a, g, st);
   if (bn == 128 && kc == 16) return launch_tc<128, 16, 1>(a, g, st);

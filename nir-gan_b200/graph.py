@@ -26,6 +26,10 @@ from .engine import ActBuf, Engine, Plan, _ptr
 # NIRGAN_B200_MERGE_PHASES=0 runs ConvTranspose2d as four separate output-phase GEMMs (NG_FORM_PHASED) instead
 import os as _os
 MERGE_PHASES = [_os.environ.get("NIRGAN_B200_MERGE_PHASES", "1") != "0"]
+# NIRGAN_B200_FUSED_FINALIZE=1 lets the conv kernel's last CTA per image finalise the InstanceNorm statistics instead of
+# launching ng_in_stats_finalize.  Measured on B200: the per-tile __threadfence + counter arrival it needs costs far
+# more than the ~10 us launches it saves (conv time +40 %), so it is OFF by default; kept as a tested switch.
+FUSED_FINALIZE = [_os.environ.get("NIRGAN_B200_FUSED_FINALIZE", "0") == "1"]
 
 
 @dataclass
@@ -136,9 +140,15 @@ class UnitGraph:
                 part = eng.buffers.get(pre + ".part", B * slots * u.cout * 2, torch.float32)
                 a.stat_partials = part.data_ptr()
                 plan.keepalive.append(a)
-                plan.add("ng_conv2d", C.byref(a), label=pre)
-                plan.add("ng_in_stats_finalize", part.data_ptr(), B, slots, u.cout, u.Hout * u.Wout, u.mr.data_ptr(),
-                         label=pre + ".fin")
+                if FUSED_FINALIZE[0]:
+                    # the conv kernel's last CTA per image reduces the partials to (mean, rstd) itself
+                    cnt = eng.buffers.get(pre + ".cnt", B, torch.int32, zero=True)
+                    a.mean_rstd, a.tile_counters = u.mr.data_ptr(), cnt.data_ptr()
+                    plan.add("ng_conv2d", C.byref(a), label=pre)
+                else:
+                    plan.add("ng_conv2d", C.byref(a), label=pre)
+                    plan.add("ng_in_stats_finalize", part.data_ptr(), B, slots, u.cout, u.Hout * u.Wout,
+                             u.mr.data_ptr(), label=pre + ".fin")
             else:
                 plan.keepalive.append(a)
                 plan.add("ng_conv2d", C.byref(a), label=pre)

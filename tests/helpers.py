@@ -70,11 +70,24 @@ def conv_call(x: ActBuf, wp: torch.Tensor, Cout: int, K: int, stride: int, pad: 
         assert slots > 0, L.last_error()
         part = torch.full((x.B * slots * Cout * 2,), float("nan"), dtype=torch.float32, device=dev)
         a.stat_partials = part.data_ptr()
+    fused_mr = cnt = None
+    if want_stats and impl == L.IMPL_TC:
+        # also run the fused finalisation (last CTA per image) and check it against the stand-alone kernel below
+        fused_mr = torch.full((x.B * Cout * 2,), float("nan"), dtype=torch.float32, device=dev)
+        cnt = torch.zeros(x.B, dtype=torch.int32, device=dev)
+        a.mean_rstd, a.tile_counters = fused_mr.data_ptr(), cnt.data_ptr()
     L.call("ng_conv2d", C.byref(a), stream())
     if want_stats:
         mr = torch.empty(x.B * Cout * 2, dtype=torch.float32, device=dev)
         if impl == L.IMPL_TC:
             L.call("ng_in_stats_finalize", part.data_ptr(), x.B, slots, Cout, Hout * Wout, mr.data_ptr(), stream())
+            torch.cuda.synchronize()
+            assert int(cnt.abs().max()) == 0, "tile counters must be left at zero"
+            assert torch.isfinite(fused_mr).all()
+            assert float((fused_mr - mr).abs().max()) <= 1e-5 * max(1.0, float(mr.abs().max())), "fused finalisation"
+            L.call("ng_conv2d", C.byref(a), stream())          # second launch on the same counters
+            torch.cuda.synchronize()
+            assert float((fused_mr - mr).abs().max()) <= 1e-5 * max(1.0, float(mr.abs().max()))
         else:
             L.call("ng_in_stats", y.data_ptr(), dtype, x.B, Hout * Wout, Cout, mr.data_ptr(), stream())
         mr = mr.view(x.B, Cout, 2)
