@@ -15,7 +15,12 @@ pytestmark = pytest.mark.gpu
 
 MODES = [pytest.param("fp32", "simt", 1e-4, 2e-5, id="fp32-verify"),
          pytest.param("fp16", "simt", 2e-2, 2e-3, id="fp16-simt"),
-         pytest.param("fp16", "tc", 2e-2, 2e-3, id="fp16-tc")]
+         pytest.param("fp16", "tc", 2e-2, 2e-3, id="fp16-tc"),
+         # bf16 storage (8-bit mantissa) through 23 InstanceNorm layers measures 6-7e-2 / 1.1e-2 on these fixtures
+         # (profiles/r1d_precision_modes.md): 8x the fp16 error, as the mantissa widths predict.  It cannot meet the
+         # north-star's 2e-2 / 2e-3, which is why fp16 operands (same tcgen05 rate) are the default fast mode; the
+         # bf16 kernels are kept for range-critical use and checked against their own measured envelope.
+         pytest.param("bf16", "tc", 1.2e-1, 2e-2, id="bf16-tc")]
 
 
 def _ns(d):
@@ -93,7 +98,7 @@ def test_generator_config1_256(golden_dir, precision, impl, tmax, tmean):
     ref = torch.from_numpy(g["y"])
     _check(y, ref, tmax, tmean, "G 256 (reference golden)")
     nd = (ndvi_display(y.cpu(), x[:, 0:1]) - ndvi_display(ref, x[:, 0:1])).abs().mean()
-    assert float(nd) <= 5e-3, f"derived NDVI mean-abs {float(nd):.3e}"
+    assert float(nd) <= (5e-3 if precision != "bf16" else 5e-2), f"derived NDVI mean-abs {float(nd):.3e}"
 
 
 @pytest.mark.parametrize("precision,impl,tmax,tmean", MODES)
