@@ -491,8 +491,13 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
     a.n0 = n0;
     if (need_pass1) {
       // long blocks mean fewer global atomics on the [B][C][2] sums, but the grid must still fill the GPU
-      int mult = 64;
-      while (mult > 8 && (long long)nb * ((H * W + pstep * mult - 1) / (pstep * mult)) < 4ll * num_sms()) mult >>= 1;
+      static int mult_cap = -1, fill = -1;
+      if (mult_cap < 0) {
+        const char* v = getenv("NIRGAN_B200_BWD_MULT"); mult_cap = v ? atoi(v) : 64;
+        const char* f = getenv("NIRGAN_B200_BWD_FILL"); fill = f ? atoi(f) : 4;
+      }
+      int mult = mult_cap;
+      while (mult > 4 && (long long)nb * ((H * W + pstep * mult - 1) / (pstep * mult)) < (long long)fill * num_sms()) mult >>= 1;
       a.ppb = pstep * mult;
       dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)nb);
       DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)C * 2 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
