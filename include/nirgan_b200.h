@@ -192,7 +192,9 @@ int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, int32_t W, i
  *   y, mean_rstd : the forward's pre-norm tensor and statistics (mean_rstd NULL = unit without normalisation)
  *   dy     : dL/dy compact [B][H][W][C];  do_out (optional): dL/d(output interior) for the residual path
  *   dscale / de_map (optional): accumulated dL/d(scale_param) (1 float, caller zero-initialised) and
- *   dL/d(bilinear embedding map) [B][H][W] for the injection.   sums_scratch: [B][C][2] floats. */
+ *   dL/d(bilinear embedding map) [B][H][W] for the injection.   sums_scratch: ng_in_bwd_scratch_floats(B,H,W,C)
+ *   floats (per-block partial sums, added in a fixed order by the second pass: no atomics, deterministic). */
+int64_t ng_in_bwd_scratch_floats(int32_t B, int32_t H, int32_t W, int32_t C);
 int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y, int32_t dtype,
               int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd, int32_t act, float slope,
               const float* inject_e, int32_t inject_mode, const float* inject_scale, float* sums_scratch, void* dy,

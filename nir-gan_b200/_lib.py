@@ -56,6 +56,7 @@ _SIGNATURES = {
     "ng_in_stats_finalize": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_in_apply": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp, c_i32, c_vp, c_i32,
                             c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "ng_in_bwd_scratch_floats": (c_i64, [c_i32, c_i32, c_i32, c_i32]),
     "ng_in_bwd": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp,
                           c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ng_grad_scale_pow2": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_vp]),

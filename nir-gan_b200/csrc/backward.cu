@@ -54,7 +54,7 @@ struct BwdArgs {
   int inj_mode;
   float inv_hw;
   int ppb;                     // interior pixels per block
-  int n0;                      // first image of this launch (the batch is processed in L2-sized chunks)
+  int nblk1;                   // pass-1 blocks per image = partial-sum slots per image
   unsigned long long w_magic;  // ceil(2^40 / W): p / W == (p * w_magic) >> 40 for p < 2^20
 };
 
@@ -124,16 +124,12 @@ in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const 
               const T* __restrict__ yv, const float* __restrict__ mr, const float* __restrict__ inj,
               const float* __restrict__ inj_scale, float* __restrict__ sums, float* __restrict__ dscale,
               float* __restrict__ de_map, T* __restrict__ dy, T* __restrict__ do_out) {
-  extern __shared__ float sm[];            // PASS 1: [C][2] block accumulators
-  const int n = a.n0 + blockIdx.y, C8 = a.C >> 3;
+  extern __shared__ float sm[];            // PASS 1: [16 accumulators][256 threads]
+  const int n = blockIdx.y, C8 = a.C >> 3;
   const int c8 = threadIdx.x & (C8 - 1);
   const int pstep = 256 >> a.c8_shift;
   const int npix = a.H * a.W;
   const int p_begin = blockIdx.x * a.ppb, p_end = min(npix, p_begin + a.ppb);
-  if (PASS == 1) {
-    for (int i = threadIdx.x; i < a.C * 2; i += 256) sm[i] = 0.f;
-    __syncthreads();
-  }
   const float s = (HAS_INJ && inj_scale) ? *inj_scale : 1.f;
   float mean[8], rstd[8], m1[8], m2[8];
 #pragma unroll
@@ -146,7 +142,7 @@ in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const 
       mean[2 * k] = m.x; rstd[2 * k] = m.y; mean[2 * k + 1] = m.z; rstd[2 * k + 1] = m.w;
     }
     if (PASS == 2) {
-      const float4* s4 = reinterpret_cast<const float4*>(sums + ((size_t)n * a.C + c8 * 8) * 2);
+      const float4* s4 = reinterpret_cast<const float4*>(sums + ((size_t)n * a.C + c8 * 8) * 2);   // combined sums
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float4 sv = s4[k];
@@ -246,19 +242,43 @@ in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const 
     }
   }
   if constexpr (PASS == 1) {
+    // block reduction without atomics: every thread parks its 16 accumulators, then each output (channel, stat) is the
+    // sum over the 256/C8 threads that own that channel group, in a fixed order; one coalesced write of the block's
+    // [C][2] partial.
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      atomicAdd(&sm[(c8 * 8 + k) * 2 + 0], acc1[k]);
-      atomicAdd(&sm[(c8 * 8 + k) * 2 + 1], acc2[k]);
+      sm[(2 * k) * 256 + threadIdx.x] = acc1[k];
+      sm[(2 * k + 1) * 256 + threadIdx.x] = acc2[k];
     }
     if (HAS_INJ && dscale) {
       ds_acc = warp_sum(ds_acc);
       if ((threadIdx.x & 31) == 0 && ds_acc != 0.f) atomicAdd(dscale, ds_acc);
     }
     __syncthreads();
-    if (sums)
-      for (int i = threadIdx.x; i < a.C * 2; i += 256) atomicAdd(&sums[(size_t)n * a.C * 2 + i], sm[i]);
+    if (sums) {
+      // partial slots live behind the [B][C][2] combined sums
+      float* dst = sums + (size_t)a.B * a.C * 2 + ((size_t)n * a.nblk1 + blockIdx.x) * a.C * 2;
+      const int lanes = 256 >> a.c8_shift;
+      for (int o = threadIdx.x; o < a.C * 2; o += 256) {
+        const int cg = o >> 4, v = o & 15;
+        float t = 0.f;
+        for (int L = 0; L < lanes; ++L) t += sm[v * 256 + (L << a.c8_shift) + cg];
+        dst[o] = t;
+      }
+    }
   }
+}
+
+// combined[n][o] = sum over the image's pass-1 blocks of partial[n][blk][o], in block order (deterministic, no atomics)
+__global__ void __launch_bounds__(256)
+in_bwd_combine_kernel(const float* __restrict__ partial, int total, int per_image, int nblk, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = i / per_image, o = i - n * per_image;
+  const float* p = partial + (size_t)n * nblk * per_image + o;
+  float t = 0.f;
+  for (int k = 0; k < nblk; ++k) t += p[(size_t)k * per_image];
+  out[i] = t;
 }
 
 // ---- gradient plumbing ------------------------------------------------------------------------------
@@ -440,6 +460,19 @@ static void launch_in_bwd(const BwdArgs& a, dim3 grid, size_t smem, cudaStream_t
 #undef NG_BWD
 }
 
+// pass-1 blocks per image: long blocks (fewer partial slots for pass 2 to add up) as long as the grid still fills the GPU
+static int in_bwd_pass1_blocks(int B, int H, int W, int C) {
+  const int pstep = 256 / (C / 8);
+  int mult = 64;
+  while (mult > 4 && (long long)B * ((H * W + pstep * mult - 1) / (pstep * mult)) < 4ll * num_sms()) mult >>= 1;
+  return (H * W + pstep * mult - 1) / (pstep * mult);
+}
+
+extern "C" int64_t ng_in_bwd_scratch_floats(int32_t B, int32_t H, int32_t W, int32_t C) {
+  if (B <= 0 || H <= 0 || W <= 0 || C < 8 || C % 8) return NG_E_ARG;
+  return (int64_t)B * (1 + in_bwd_pass1_blocks(B, H, W, C)) * C * 2;     // combined sums + per-block partials
+}
+
 extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y,
                          int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd, int32_t act,
                          float slope, const float* inject_e, int32_t inject_mode, const float* inject_scale,
@@ -460,56 +493,32 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
   a.w_magic = ((1ull << 40) + (unsigned)W - 1) / (unsigned)W;
   const int pstep = 256 / (C / 8);
   const bool need_pass1 = mean_rstd != nullptr || (inject_mode != NG_INJECT_NONE && (dscale || de_map));
+  a.nblk1 = in_bwd_pass1_blocks(B, H, W, C);
   if (need_pass1) {
-    if (sums_scratch) {
-      int e = check_cuda(cudaMemsetAsync(sums_scratch, 0, (size_t)B * C * 2 * sizeof(float), st), "in_bwd memset");
-      if (e) return e;
-    }
+    NG_REQUIRE(mean_rstd == nullptr || sums_scratch != nullptr, NG_E_ARG, "in_bwd: scratch required");
     if (de_map) {
       int e = check_cuda(cudaMemsetAsync(de_map, 0, (size_t)B * H * W * sizeof(float), st), "in_bwd memset de");
       if (e) return e;
     }
-  }
-  // Both passes read the same tensors (gradient, skip gradient, forward pre-norm).  Optionally (NIRGAN_B200_BWD_L2_MB > 0)
-  // images are processed in chunks whose inputs fit in L2, pass 2 right after pass 1 of the same chunk, so the second
-  // read is served from L2.  Measured on B200 (B = 32, 69x69x256): the smaller grids lose more than the L2 hits gain
-  // (4.9 ms -> 6.6 / 8.6 / 11.5 ms of IN-backward per step for 80 / 48 / 24 MB chunks), so the default is one launch
-  // pair over the whole batch.
-  const size_t esz = dtype == NG_F32 ? 4 : 2;
-  const size_t per_image = ((size_t)(g_halo ? (H + 2 * g_pad) * (W + 2 * g_pad) : 0) + (size_t)H * W * (g_skip ? 2 : 1)) * C * esz;
-  int chunk = B;
-  if (need_pass1) {
-    static long long l2_budget = -1;
-    if (l2_budget < 0) { const char* v = getenv("NIRGAN_B200_BWD_L2_MB"); l2_budget = (v ? atoll(v) : 0) * 1024 * 1024; }
-    chunk = l2_budget > 0 ? (int)(l2_budget / (long long)per_image) : B;
-    if (chunk < 1) chunk = 1;
-    if (chunk > B) chunk = B;
-    if (chunk * 2 > B) chunk = B;                 // fewer than two full chunks: not worth the extra launches
-  }
-  for (int n0 = 0; n0 < B; n0 += chunk) {
-    const int nb = B - n0 < chunk ? B - n0 : chunk;
-    a.n0 = n0;
-    if (need_pass1) {
-      // long blocks mean fewer global atomics on the [B][C][2] sums, but the grid must still fill the GPU
-      static int mult_cap = -1, fill = -1;
-      if (mult_cap < 0) {
-        const char* v = getenv("NIRGAN_B200_BWD_MULT"); mult_cap = v ? atoi(v) : 64;
-        const char* f = getenv("NIRGAN_B200_BWD_FILL"); fill = f ? atoi(f) : 4;
-      }
-      int mult = mult_cap;
-      while (mult > 4 && (long long)nb * ((H * W + pstep * mult - 1) / (pstep * mult)) < (long long)fill * num_sms()) mult >>= 1;
-      a.ppb = pstep * mult;
-      dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)nb);
-      DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)C * 2 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
-                                             inject_e, inject_scale, sums_scratch, dscale, de_map, nullptr, nullptr)));
-      NG_LAUNCH_CHECK("in_bwd_kernel<pass 1>");
+    a.ppb = (H * W + a.nblk1 - 1) / a.nblk1;
+    a.ppb = (a.ppb + pstep - 1) / pstep * pstep;
+    dim3 grid((unsigned)a.nblk1, (unsigned)B);
+    DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)16 * 256 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
+                                           inject_e, inject_scale, mean_rstd ? sums_scratch : nullptr, dscale, de_map,
+                                           nullptr, nullptr)));
+    NG_LAUNCH_CHECK("in_bwd_kernel<pass 1>");
+    if (mean_rstd) {
+      const int total = B * C * 2;
+      in_bwd_combine_kernel<<<(total + 255) / 256, 256, 0, st>>>(sums_scratch + (size_t)total, total, C * 2, a.nblk1,
+                                                                sums_scratch);
+      NG_LAUNCH_CHECK("in_bwd_combine_kernel");
     }
-    a.ppb = pstep * 16;
-    dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)nb);
-    DISPATCH_T(dtype, (launch_in_bwd<T, 2>(a, grid, 0, st, g_halo, g_skip, y, mean_rstd, inject_e, inject_scale,
-                                           sums_scratch, nullptr, nullptr, dy, do_out)));
-    NG_LAUNCH_CHECK("in_bwd_kernel<pass 2>");
   }
+  a.ppb = pstep * 16;
+  dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)B);
+  DISPATCH_T(dtype, (launch_in_bwd<T, 2>(a, grid, 0, st, g_halo, g_skip, y, mean_rstd, inject_e, inject_scale,
+                                         sums_scratch, nullptr, nullptr, dy, do_out)));
+  NG_LAUNCH_CHECK("in_bwd_kernel<pass 2>");
   return NG_OK;
 }
 

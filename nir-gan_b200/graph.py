@@ -283,7 +283,12 @@ class UnitGraph:
                     do_out = eng.act(pre + ".do", B, u.Hout, u.Wout, u.cout, 0)
                     g_skip[u.residual] = do_out
                 inj = u.inject or {}
-                sums = eng.buffers.get(pre + ".bsum", B * u.cout * 2, torch.float32) if u.kind == "norm" else None
+                sums = None
+                if u.kind == "norm":
+                    nf = int(L.load().ng_in_bwd_scratch_floats(B, u.Hout, u.Wout, u.cout))
+                    if nf <= 0:
+                        L.check(nf if nf < 0 else -1, "ng_in_bwd_scratch_floats")
+                    sums = eng.buffers.get(pre + ".bsum", nf, torch.float32)
                 dscale = de_map = None
                 if inj and want_inject_grads:
                     dscale = eng.buffers.get(pre + ".dscale", 1, torch.float32)

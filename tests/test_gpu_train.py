@@ -76,7 +76,7 @@ def test_in_bwd_unit_matches_autograd(case):
     gs = gskip.permute(0, 2, 3, 1).contiguous()
     dy = torch.full((B * H * W * Cn,), float("nan"), device="cuda")
     do = torch.full((B * H * W * Cn,), float("nan"), device="cuda")
-    sums = torch.empty(B * Cn * 2, device="cuda")
+    sums = torch.full((int(L.load().ng_in_bwd_scratch_floats(B, H, W, Cn)),), float("nan"), device="cuda")
     dscale = torch.zeros(1, device="cuda")
     de_map = torch.empty(B * H * W, device="cuda")
     injected = inj_mode != L.INJECT_NONE
