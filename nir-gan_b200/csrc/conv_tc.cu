@@ -8,12 +8,14 @@
 //      landing in shared memory as 128 rows x KC in the canonical K-major swizzled UMMA layout;
 //   B: box (KC, BN) of the packed weight matrix [tap*Cout + n][Cin].
 // One elected thread issues tcgen05.mma (M=128, N=BN, K=16) into a double-buffered TMEM accumulator;
-// four epilogue warps drain TMEM (tcgen05.ld 32x32b), convert to 16-bit, stage the tile in swizzled
-// shared memory, reduce per-channel sum / sum-of-squares for InstanceNorm (deterministic per-tile
-// partials) and write the rows out with 16-byte coalesced stores.
+// EG groups of four epilogue warps drain TMEM in alternating passes of 32 output channels (tcgen05.ld 32x32b), convert
+// to 16-bit, stage the pass in swizzled shared memory, reduce per-channel sum / sum-of-squares for InstanceNorm
+// (deterministic per-tile partials) and write the rows out with 16-byte coalesced stores.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 =
-// epilogue (warp_id % 4 selects the TMEM lane quarter).  Persistent: grid = min(tiles, #SM).
+// Warp roles (64 + 128*EG threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, then EG groups of four
+// epilogue warps (warp_id % 4 selects the TMEM lane quarter).  EG = 2 for the K-deep ResnetBlock convolutions (the
+// drain hides under 36 K iterations and the shared memory goes to a fourth operand stage), EG = 4 for the short-K
+// layers (down / up convolutions), whose tiles are bound by the drain.  Persistent: grid = min(tiles, #SM).
 #include "tc_common.cuh"
 #include <mutex>
 #include <unordered_map>
@@ -53,7 +55,7 @@ struct TcParams {
 constexpr int RT_BW = 16, RT_BH = 8, RT_KH = 7;
 constexpr int RT_PATCH_ROWS = (RT_BH + RT_KH - 1) * RT_BW;          // 224 pixels
 
-template <int BN, int KC, bool RT = false>
+template <int BN, int KC, bool RT = false, int EGW = 2>
 struct TcCfg {
   static constexpr int A_BYTES = RT ? RT_PATCH_ROWS * KC * 2 : 128 * KC * 2;
   static constexpr int B_BYTES = RT ? 0 : (BN * KC * 2 + 1023) / 1024 * 1024;
@@ -62,7 +64,7 @@ struct TcCfg {
   // epilogue: EG groups of four warps drain the accumulator in alternating passes of EB = 32 output channels, each
   // group with its own 8 KB staging tile, stats scratch and row-offset table (a single warp per scheduler is latency
   // bound, so two groups nearly halve the drain time of a tile)
-  static constexpr int EG = BN >= 64 ? 2 : 1;
+  static constexpr int EG = BN >= 64 ? EGW : 1;
   static constexpr int EB = 32;
   static constexpr int THREADS = 64 + 128 * EG;
   static constexpr int STAGING_BYTES = BN >= 64 ? EG * 128 * EB * 2 : 0;
@@ -81,11 +83,11 @@ struct TcCfg {
 // CS = thread-block-cluster size.  The CS CTAs of a cluster work on CS different pixel patches that share the same
 // weight slab; each loads 1/CS of every B (weight) stage and multicasts it to all of them, which divides the
 // L2 -> SM weight traffic (the measured limiter of the 128x256 tile) by CS.
-template <int BN, int KC, int CS, bool RT = false>
-__global__ void __launch_bounds__(TcCfg<BN, KC, RT>::THREADS, 1)
+template <int BN, int KC, int CS, bool RT = false, int EGW = 2>
+__global__ void __launch_bounds__(TcCfg<BN, KC, RT, EGW>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams p) {
-  using Cfg = TcCfg<BN, KC, RT>;
+  using Cfg = TcCfg<BN, KC, RT, EGW>;
   static_assert(!RT || (CS == 1 && KC == 64), "row-tap variant: no clusters, 64-channel rows");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -386,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // into (mean, rstd).  Release: every partial of this group is written (barrier above) and fenced before the
         // arrival; acquire: fence after observing the final count.  Fixed summation order -> deterministic.
         if (p.mean_rstd != nullptr && p.epilogue == NG_EPI_RAW && p.stat_partials != nullptr && !dummy) {
-          int* flagw = reinterpret_cast<int*>(rowoff) + 512 + grp;      // rowoff table has 2 KB, flags live behind 2 x 1 KB
+          int* flagw = reinterpret_cast<int*>(rowoff) + Cfg::EG * 256 + grp;   // flags live behind the EG row-offset tables
           __threadfence();
           bar_sync_id(barid);
           if (et == 0) {
@@ -484,9 +486,9 @@ static void pick_patch(const ng_conv_args& a, const ConvGeom& g, int& BH, int& B
   else choose_patch(g.VH, g.VW, g.S, BH, BW);
 }
 
-template <int BN, int KC, int CS, bool RT = false>
+template <int BN, int KC, int CS, bool RT = false, int EGW = 2>
 static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
-  using Cfg = TcCfg<BN, KC, RT>;
+  using Cfg = TcCfg<BN, KC, RT, EGW>;
   int r = get_encode();
   if (r) return r;
   TcParams p;
@@ -537,7 +539,7 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   static bool attr_set = false;   // per instantiation
   static int max_ctas = 0;
   if (!attr_set) {
-    int e = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, CS, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int e = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, CS, RT, EGW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES), "cudaFuncSetAttribute(conv_tc)");
     if (e) return e;
     max_ctas = num_sms() / CS * CS;
@@ -549,7 +551,7 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
       qa[0].val.clusterDim.x = CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       qc.attrs = qa; qc.numAttrs = 1;
       int ncl = 0;
-      if (cudaOccupancyMaxActiveClusters(&ncl, conv_tc_kernel<BN, KC, CS, RT>, &qc) == cudaSuccess && ncl > 0 &&
+      if (cudaOccupancyMaxActiveClusters(&ncl, conv_tc_kernel<BN, KC, CS, RT, EGW>, &qc) == cudaSuccess && ncl > 0 &&
           ncl * CS < max_ctas)
         max_ctas = ncl * CS;      // persistent kernel: every cluster must be co-resident
     }
@@ -563,7 +565,7 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = CS; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
   cfg.attrs = attrs; cfg.numAttrs = 1;
-  int e = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, CS, RT>, tmA, tmB, p), "conv_tc_kernel launch");
+  int e = check_cuda(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, KC, CS, RT, EGW>, tmA, tmB, p), "conv_tc_kernel launch");
   if (e) return e;
   NG_LAUNCH_CHECK("conv_tc_kernel");
   return NG_OK;
@@ -612,7 +614,20 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   if (bn == 256 && kc == 16) return launch_tc<256, 16, 1>(a, g, st);
   if (bn == 64 && kc == 64 && row_tap_ok(a, g)) return launch_tc<64, 64, 1, true>(a, g, st);
   if (bn == 64 && kc == 64) return launch_tc<64, 64, 1>(a, g, st);
+  // very short K loops on 256-wide tiles (the merged-phase up-convolution to full resolution: 8 operand stages per
+  // tile against 8 drain passes) are bound by the epilogue drain: four epilogue groups.  Measured on B200: 0.222 ->
+  // 0.179 ms for that layer; for 9..18 K iterations (down convs, first up-conv) the fourth operand stage that EG = 4
+  // costs matters more (+7..13 %), so those stay on two groups.
+  int max_kiters = 0;
+  for (int ph = 0; ph < g.nphase; ++ph) {
+    const int it = (g.phase_tap0[ph + 1] - g.phase_tap0[ph]) * (a.Cin / 64);
+    if (it > max_kiters) max_kiters = it;
+  }
+  static int wide_env = -1;
+  if (wide_env < 0) { const char* v = getenv("NIRGAN_B200_EPI4"); wide_env = v ? atoi(v) : 1; }
+  const bool wide = wide_env && kc == 64 && max_kiters <= 8;
   if (bn == 128 && kc == 64) return launch_tc<128, 64, 1>(a, g, st);
+  if (bn == 256 && kc == 64 && wide) return launch_tc<256, 64, 1, false, 4>(a, g, st);
   if (bn == 256 && kc == 64) {
     const int cs = cluster_size_for(bn, kc);
     if (cs == 4) return launch_tc<256, 64, 4>(a, g, st);
