@@ -44,6 +44,7 @@ struct TcParams {
   float* stat_partials;
   float* mean_rstd;           // fused finalisation (optional)
   int* tile_counters;
+  unsigned long long mg_groups_per, mg_patches_x, mg_patches_y;   // ceil(2^42 / d) reciprocals for decode()
   int arrivals_per_image;     // epilogue-group arrivals that complete an image
   float inv_count;            // 1 / (Hout * Wout)
 };
@@ -132,17 +133,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int chunks = g.Cin / KC;
   // work item q (one per cluster and round) -> (cout tile, phase, group index); CTA `crank` takes item gi*CS + crank
+  // divisions by launch constants use precomputed reciprocals: n / d == (n * ceil(2^42 / d)) >> 42, exact while
+  // n * d < 2^42 (checked on the host); the epilogue runs this once per tile in every one of its threads
+  auto fdiv = [](int n, unsigned long long magic) { return (int)(((unsigned long long)(unsigned)n * magic) >> 42); };
   auto decode = [&](int q, int& cot, int& ph, int& n, int& py, int& px, bool& dummy) {
-    int t = q;
-    const int gi = t % p.groups_per; t /= p.groups_per;
-    ph = t % g.nphase;
-    cot = t / g.nphase;
+    const int t = fdiv(q, p.mg_groups_per);
+    const int gi = q - t * p.groups_per;
+    cot = g.nphase == 1 ? t : (t >> 2);       // nphase is 1 or 4
+    ph = g.nphase == 1 ? 0 : (t & 3);
     int idx = gi * CS + (int)crank;
     dummy = idx >= p.group_items;             // odd tail: recompute the last patch, write nothing
     if (dummy) idx = p.group_items - 1;
-    px = idx % p.patches_x; idx /= p.patches_x;
-    py = idx % p.patches_y;
-    n = idx / p.patches_y;
+    const int rowi = fdiv(idx, p.mg_patches_x);
+    px = idx - rowi * p.patches_x;
+    n = fdiv(rowi, p.mg_patches_y);
+    py = rowi - n * p.patches_y;
   };
 
   if (warp == 0) {
@@ -244,23 +249,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else {
     // ===================== epilogue (warps 2..5 = group 0, warps 6..9 = group 1) =====================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;          // accumulator row == TMEM lane
+    const int qtr = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = qtr * 32 + lane;        // accumulator row == TMEM lane
     const int grp = (warp - 2) >> 2;        // epilogue group
     const int we = (warp - 2) & 3;          // warp within the group
     const int et = we * 32 + lane;          // 0..127 thread index within the group
+    const int row_i = row / p.BW, row_j = row - row_i * p.BW;     // this row's pixel inside the patch (tile-invariant)
     uint32_t as = 0, as_phase = 0;
     for (int q = cluster_id; q < p.total_groups; q += num_clusters) {
       int cot, ph, n, py, px; bool dummy;
       decode(q, cot, ph, n, py, px, dummy);
-      const int vi = py * p.BH + row / p.BW, vj = px * p.BW + row % p.BW;
+      const int vi = py * p.BH + row_i, vj = px * p.BW + row_j;
       const int oy = g.OS * vi + g.phase_oy[ph], ox = g.OS * vj + g.phase_ox[ph];
       const bool valid = !dummy && row < p.BH * p.BW && oy < g.Hout && ox < g.Wout;
       const int n0 = cot * BN;
 
       mbar_wait(smem_u32(&tfull_bar[as]), as_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + ((uint32_t)(qtr * 32) << 16);
 
       if constexpr (BN < 64) {
         // ---- single real output channel (generator head, PatchGAN last layer) ----
@@ -346,9 +352,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr int PAIRS = EB / 2, G = 128 / PAIRS;        // 16 channel pairs x 8 row groups
             const int cp = et % PAIRS, rs = et / PAIRS;
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-#pragma unroll 4
-            for (int r2 = rs; r2 < 128; r2 += G) {
-              const uint32_t word = lds32(stg + r2 * (EB * 2) + (((cp >> 2) ^ ((r2 >> 1) & 3)) * 16) + (cp & 3) * 4);
+            // rows rs, rs + 8, ...: the swizzle term ((row >> 1) & 3) is the same for all of them -> one base address
+            const uint32_t a0 = stg + rs * (EB * 2) + (((cp >> 2) ^ ((rs >> 1) & 3)) * 16) + (cp & 3) * 4;
+#pragma unroll
+            for (int k = 0; k < 128 / G; ++k) {
+              const uint32_t word = lds32(a0 + k * (G * EB * 2));
               const float2 v = p.bf16 ? unpack2<__nv_bfloat16>(word) : unpack2<__half>(word);
               s0 += v.x; q0 = fmaf(v.x, v.x, q0); s1 += v.y; q1 = fmaf(v.y, v.y, q1);
             }
@@ -373,11 +381,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr int LPR = EB / 8, RPI = 32 / LPR;
             const int chunk = lane % LPR;
             uint8_t* ybase = reinterpret_cast<uint8_t*>(p.y);
+            // rows r0, r0 + 32, ...: constant swizzle term -> one staging base address per thread
+            const int r0 = we * RPI + lane / LPR;
+            const uint32_t sb = stg + r0 * (EB * 2) + ((chunk ^ ((r0 >> 1) & 3)) * 16);
+            const uint32_t rb = rowoffg + r0 * 8;
 #pragma unroll
-            for (int r2 = we * RPI + lane / LPR; r2 < 128; r2 += 4 * RPI) {
-              const long long off = lds64(rowoffg + r2 * 8);
+            for (int k = 0; k < 128 / (4 * RPI); ++k) {
+              const long long off = lds64(rb + k * (4 * RPI * 8));
               if (off >= 0) {
-                const uint4 v = lds128(stg + r2 * (EB * 2) + ((chunk ^ ((r2 >> 1) & 3)) * 16));
+                const uint4 v = lds128(sb + k * (4 * RPI * EB * 2));
                 *reinterpret_cast<uint4*>(ybase + (off + chan_off) * 2 + chunk * 16) = v;
               }
             }
@@ -504,6 +516,12 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   p.group_items = g.B * p.patches_y * p.patches_x;
   p.groups_per = (p.group_items + CS - 1) / CS;
   p.total_groups = p.co_tiles * g.nphase * p.groups_per;
+  NG_REQUIRE(g.nphase == 1 || g.nphase == 4, NG_E_UNSUPPORTED, "conv_tc: 1 or 4 phases");
+  NG_REQUIRE((long long)p.total_groups * p.groups_per < (1ll << 42) && (long long)p.group_items * p.patches_x < (1ll << 42),
+             NG_E_SHAPE, "conv_tc: problem too large for the reciprocal tile decode");
+  p.mg_groups_per = ((1ull << 42) + (unsigned)p.groups_per - 1) / (unsigned)p.groups_per;
+  p.mg_patches_x = ((1ull << 42) + (unsigned)p.patches_x - 1) / (unsigned)p.patches_x;
+  p.mg_patches_y = ((1ull << 42) + (unsigned)p.patches_y - 1) / (unsigned)p.patches_y;
   p.epilogue = a.epilogue; p.act = a.act; p.crop = a.crop; p.slope = a.slope;
   p.bf16 = a.dtype == NG_BF16;
   p.stat_slots = (g.merged ? 4 : g.nphase) * p.patches_y * p.patches_x;
