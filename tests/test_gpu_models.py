@@ -191,3 +191,33 @@ def test_tile_sharded_inference_matches_sequential_loop(golden_dir):
     for k in seq:
         assert torch.equal(merged[k], seq[k]), k
         _check(seq[k], torch.from_numpy(g["y." + k]), 2e-2, 2e-3, f"synth loop {k}")
+
+
+def test_config2_full_size_properties():
+    """BASELINE.json configs[1] at its full size (64 injected 3x256x256 tiles, the two-stream / CUDA-graph path that
+    bench.py times): size-independent properties -- finite, inside tanh's range, every tile bit-identical to the same
+    tile computed alone, in another slot or with a different slice split (InstanceNorm is per sample) -- and two of the
+    tiles against the CPU oracle within the north-star tolerance."""
+    import nirgan_oracle as O
+    sd = O.random_state_dict(O.generator_param_shapes(inject=True), seed=12, scale_param=1.0)
+    net = make_G(sd, "fp16", "tc", inject=True)
+    g = torch.Generator().manual_seed(64)
+    x = torch.rand(64, 3, 256, 256, generator=g)
+    e = torch.randn(64, 256, generator=g)
+    xc, ec = x.cuda(), e.cuda()
+    with torch.no_grad():
+        y = net(xc, ec)                       # auto: two slices of 32 on two streams
+        y2 = net(xc, ec)                      # second call replays the captured CUDA graphs
+        assert torch.isfinite(y).all() and float(y.abs().max()) <= 1.0
+        assert torch.equal(y, y2)
+        for i in (0, 31, 32, 63):
+            one = net(xc[i:i + 1], ec[i:i + 1])
+            assert torch.equal(one[0], y[i]), i
+        perm = torch.randperm(64, generator=g)
+        yp = net(xc[perm.cuda()], ec[perm.cuda()])
+        assert torch.equal(yp, y[perm.cuda()])
+        net.configure_b200(precision="fp16", impl="tc", streams=1)
+        y1 = net(xc, ec)                      # one slice of 64, one stream
+        assert torch.equal(y1, y)
+        ref = O.resnet_generator_forward(sd, x[[5, 40]], embeds=e[[5, 40]])
+    _check(y[[5, 40]], ref, 2e-2, 2e-3, "config 2, tiles 5 and 40 of 64 vs oracle")

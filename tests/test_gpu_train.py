@@ -301,3 +301,50 @@ def test_g_forward_reuse_matches_double_evaluation():
     with torch.no_grad():
         plain = model.forward(rgb)
     assert torch.equal(after, plain)
+
+
+def test_config4_full_size_step_properties():
+    """BASELINE.json configs[3] at its full size (batch 32, 256x256, rgb / nir ~ U[0,1) so the NDVI / NDWI terms hit their
+    singular pixels): the step runs on the arena optimizer path without skipping, every gradient is finite and non-zero,
+    D stays frozen in the G pass, and the weights move by exactly lr on the first Adam step (|update| = lr for every
+    element with a non-zero gradient, torch.optim.Adam semantics with bias correction at step 1)."""
+    from nirgan_b200.model.pix2pix import Px2Px
+    torch.manual_seed(0)
+    model = Px2Px(_cfg()).cuda().train()
+    model.netG.configure_b200(precision="fp16", impl="tc")
+    model.netD.configure_b200(precision="fp16", impl="tc")
+    opt_d, opt_g = model.configure_optimizers()
+    g = torch.Generator().manual_seed(1)
+    batch = {"rgb": torch.rand(32, 3, 256, 256, generator=g).cuda(), "nir": torch.rand(32, 1, 256, 256, generator=g).cuda()}
+    w_d0 = model.netD.model[8].weight.detach().clone()
+    w_g0 = model.netG.model[10].conv_block[1].weight.detach().clone()
+    opt_d.zero_grad(set_to_none=True)
+    ld = model.training_step(batch, 0, 0)
+    ld.backward()
+    assert all(p.grad is None for p in model.netG.parameters())
+    for n_, p in model.netD.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n_
+        if n_.endswith("weight"):            # biases that feed an InstanceNorm have an identically zero gradient
+            assert float(p.grad.norm()) > 0, n_
+    gd = model.netD.model[8].weight.grad.clone()
+    opt_d.step()
+    opt_g.zero_grad(set_to_none=True)
+    for p in model.netD.parameters():
+        p.grad = None
+    lg = model.training_step(batch, 0, 1)
+    lg.backward()
+    assert all(p.grad is None for p in model.netD.parameters())
+    for n_, p in model.netG.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n_
+        if n_.endswith("weight"):
+            assert float(p.grad.norm()) > 0, n_
+    gg = model.netG.model[10].conv_block[1].weight.grad.clone()
+    opt_g.step()
+    assert torch.isfinite(ld) and torch.isfinite(lg)
+    assert opt_d.skipped_steps == 0 and opt_g.skipped_steps == 0 and opt_d.fast_steps == 1 and opt_g.fast_steps == 1
+    for w0, w1, gr in ((w_d0, model.netD.model[8].weight.detach(), gd), (w_g0, model.netG.model[10].conv_block[1].weight.detach(), gg)):
+        big = gr.abs() > 1e-5            # |g| >> eps = 1e-8, so m / (sqrt(v) + eps) = sign(g) to 1e-3
+        assert int(big.sum()) > 1000
+        step = (w1 - w0)[big]
+        assert float((step.abs() - 2e-4).abs().max()) <= 2e-6
+        assert torch.equal(torch.sign(step), -torch.sign(gr[big]))
