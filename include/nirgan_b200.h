@@ -275,6 +275,14 @@ int ng_hist_match(const float* image, const float* reference, int32_t B, int32_t
 int ng_sort_segments(const float* src, int32_t segs, int32_t n, float* sorted_out, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
+/* SatCLIP location encoder (model/satclip/satclip_wrapper.py:29-34, location_encoder.py:73-151,267-275,
+ * positional_encoding/spherical_harmonics.py:27-42 + spherical_harmonics_closed_form.py:8-40): lonlat [B][2] degrees
+ * (float64) -> L*L real spherical harmonics -> SIREN MLP -> out [B][dim_out] float32; float64 arithmetic like the
+ * reference.  params_t: float64 blob, per hidden layer W^T [in][hidden] then bias [hidden], then W_last^T [hidden][dim_out]
+ * and bias [dim_out] (transposed so the reads coalesce). */
+int ng_satclip_encode(const double* lonlat, int32_t B, int32_t L, const double* params_t, int32_t hidden,
+                      int32_t num_layers, int32_t dim_out, double w0_initial, double w0, float* out, void* stream);
+
 /* Validation metrics (utils/calculate_metrics.py:6-37): out4 = { F.l1_loss, F.mse_loss, kornia.metrics.psnr(.., max_val),
  * kornia.metrics.ssim(.., window, max_val).mean() } over `planes` = B*C fp32 planes of HxW.  window odd, <= 11 (5 in
  * calculate_metrics, 11 in utils/losses.py::ssim_loss).  scratch: ng_image_metrics_scratch_floats() floats. */

@@ -395,3 +395,103 @@ extern "C" int ng_image_metrics(const float* pred, const float* target, int32_t 
   NG_LAUNCH_CHECK("image_metrics_finalize_kernel");
   return NG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// SatCLIP location encoder: the step right before the injected generator,
+// SatClIP_wrapper.predict (model/satclip/satclip_wrapper.py:29-34) = LocationEncoder(posenc, nnet)
+// (model/satclip/location_encoder.py:267-275), float64 like the reference (`x.double()`), float32 result.
+//   posenc: SphericalHarmonics(L) (positional_encoding/spherical_harmonics.py:27-42): phi = deg2rad(lon + 180),
+//           theta = deg2rad(lat + 90), the L*L real harmonics from the closed-form recursion
+//           (positional_encoding/spherical_harmonics_closed_form.py:8-40), order l = 0..L-1, m = -l..l
+//   nnet:   SirenNet (location_encoder.py:73-151), eval mode: hidden layers sin(w0_i * (W x + b)) with w0 = w0_initial
+//           for the first layer and w0 for the others, linear last layer.
+// One block per coordinate pair; thread t evaluates harmonic t, then output j = t (+256 ...) of every layer; activations
+// ping-pong between two shared-memory vectors.  Weights are passed transposed ([in][out]) so a layer's reads coalesce.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace ng {
+
+constexpr int SC_MAXDIM = 1024;
+
+__device__ double sc_assoc_legendre(int l, int m, double x) {
+  double pmm = 1.0;
+  if (m > 0) {
+    const double somx2 = sqrt((1.0 - x) * (1.0 + x));
+    double fact = 1.0;
+    for (int i = 1; i <= m; ++i) { pmm = pmm * (-fact) * somx2; fact += 2.0; }
+  }
+  if (l == m) return pmm;
+  double pmmp1 = x * (2.0 * m + 1.0) * pmm;
+  if (l == m + 1) return pmmp1;
+  double pll = 0.0;
+  for (int ll = m + 2; ll <= l; ++ll) {
+    pll = ((2.0 * ll - 1.0) * x * pmmp1 - (ll + m - 1.0) * pmm) / (double)(ll - m);
+    pmm = pmmp1;
+    pmmp1 = pll;
+  }
+  return pll;
+}
+
+__device__ double sc_renorm(int l, int m) {      // sqrt((2l+1) (l-m)! / (4 pi (l+m)!))
+  double ratio = 1.0;
+  for (int k = l - m + 1; k <= l + m; ++k) ratio /= (double)k;
+  return sqrt((2.0 * l + 1.0) * ratio / (4.0 * 3.14159265358979323846));
+}
+
+__global__ void __launch_bounds__(256)
+satclip_encode_kernel(const double* __restrict__ lonlat, int L, const double* __restrict__ params, int hidden,
+                      int num_layers, int dim_out, double w0_initial, double w0, float* __restrict__ out) {
+  __shared__ double xa[SC_MAXDIM], xb[SC_MAXDIM];
+  const int b = blockIdx.x, dim_in = L * L;
+  const double lon = lonlat[2 * b], lat = lonlat[2 * b + 1];
+  const double deg = 3.14159265358979323846 / 180.0;
+  const double phi = (lon + 180.0) * deg, theta = (lat + 90.0) * deg;
+  const double ct = cos(theta);
+  for (int t = threadIdx.x; t < dim_in; t += 256) {
+    const int l = (int)floor(sqrt((double)t) + 1e-9);
+    const int m = t - l * l - l;
+    double y;
+    if (m == 0) y = sc_renorm(l, 0) * sc_assoc_legendre(l, 0, ct);
+    else if (m > 0) y = 1.4142135623730951 * sc_renorm(l, m) * cos(m * phi) * sc_assoc_legendre(l, m, ct);
+    else y = 1.4142135623730951 * sc_renorm(l, -m) * sin(-m * phi) * sc_assoc_legendre(l, -m, ct);
+    xa[t] = y;
+  }
+  __syncthreads();
+  double* xin = xa;
+  double* xout = xb;
+  const double* w = params;
+  int d = dim_in;
+  for (int layer = 0; layer < num_layers; ++layer) {
+    const double* bias = w + (size_t)d * hidden;
+    const double scale = layer == 0 ? w0_initial : w0;
+    for (int j = threadIdx.x; j < hidden; j += 256) {
+      double acc = bias[j];
+      for (int i = 0; i < d; ++i) acc = fma(w[(size_t)i * hidden + j], xin[i], acc);
+      xout[j] = sin(scale * acc);
+    }
+    __syncthreads();
+    w = bias + hidden;
+    d = hidden;
+    double* tmp = xin; xin = xout; xout = tmp;
+  }
+  const double* bias = w + (size_t)d * dim_out;
+  for (int j = threadIdx.x; j < dim_out; j += 256) {
+    double acc = bias[j];
+    for (int i = 0; i < d; ++i) acc = fma(w[(size_t)i * dim_out + j], xin[i], acc);
+    out[(size_t)b * dim_out + j] = (float)acc;
+  }
+}
+
+}  // namespace ng
+
+extern "C" int ng_satclip_encode(const double* lonlat, int32_t B, int32_t L, const double* params_t, int32_t hidden,
+                                 int32_t num_layers, int32_t dim_out, double w0_initial, double w0, float* out,
+                                 void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(lonlat && params_t && out && B > 0, NG_E_ARG, "satclip_encode: bad arguments");
+  NG_REQUIRE(L >= 1 && L * L <= SC_MAXDIM && hidden >= 1 && hidden <= SC_MAXDIM && dim_out >= 1 && num_layers >= 1,
+             NG_E_SHAPE, "satclip_encode: L*L and hidden must be <= %d", SC_MAXDIM);
+  satclip_encode_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(lonlat, L, params_t, hidden, num_layers, dim_out,
+                                                                      w0_initial, w0, out);
+  NG_LAUNCH_CHECK("satclip_encode_kernel");
+  return NG_OK;
+}

@@ -1,8 +1,9 @@
 """Lightning-free B200 mirror of the hot-path parts of ``model/pix2pix.py::Px2Px_PL``.
 
 Kept: the constructor's network selection (pix2pix.py:18-86), ``forward(input, embeds=None)`` with the
-reflect-pad / crop wrapper (:88-110), ``predict_step`` (:134-163, with precomputed SatCLIP embeddings
-in place of coordinates -- the location encoder is out of scope),
+reflect-pad / crop wrapper (:88-110), ``predict_step(rgb, coords)`` (:134-163) and ``extract_batch`` (:426-482) with the SatCLIP location
+encoder attached through ``attach_satclip`` (one ``ng_satclip_encode`` launch per batch; batches may also carry
+precomputed ``embeds``),
 ``training_step(batch, batch_idx, optimizer_idx)`` loss composition (:165-257) and
 ``configure_optimizers`` (:485-492).  Dropped: Lightning hooks, wandb logging, validation plots.
 """
@@ -40,6 +41,8 @@ class Px2Px(nn.Module):
                                       o.init_gain)
         self.criterionGAN = networks.GANLoss(o.gan_mode)
         self.inject = self.satclip and style == "inject"
+        self.concat = self.satclip and style == "concat"
+        self.satclip_model = None      # pix2pix.py:68-74 builds it from the shipped checkpoint; here it is attached
         # Px2Px_PL.training_step runs G twice per batch (once per optimizer) with identical results;
         # NIRGAN_B200_REUSE_G=0 restores the reference-faithful double evaluation
         import os
@@ -52,15 +55,51 @@ class Px2Px(nn.Module):
             return self.netG(input, embeds, wrap_pad=pad)
         return self.netG(input, wrap_pad=pad)
 
-    @torch.no_grad()
-    def predict_step(self, rgb, embeds=None):
-        assert self.training is False, "Model is in training mode, set to eval mode before predicting"
-        return self.forward(rgb, embeds) if self.inject else self.forward(rgb)
+    def attach_satclip(self, satclip_model):
+        """The reference constructs ``SatClIP_wrapper(device=self.device).eval()`` itself (pix2pix.py:68-74); the
+        checkpoint is not part of the repository, so the encoder (``nirgan_b200.model.satclip.satclip_wrapper``) is
+        handed in."""
+        self.satclip_model = satclip_model
+        return self
 
-    def extract_batch(self, batch):
+    def satclip_get_inject(self, coords):               # pix2pix.py:478-482
+        if self.satclip_model is None:
+            raise RuntimeError("use_satclip is set but no SatCLIP encoder is attached (attach_satclip) and the batch "
+                               "carries no precomputed 'embeds'")
+        return self.satclip_model.predict(coords)
+
+    def satclip_get_concat(self, coords, rgb):          # pix2pix.py:466-476
+        e = self.satclip_get_inject(coords)
+        e = e.view(rgb.shape[0], 1, 1, 256).expand(rgb.shape[0], 1, 256, 256)
+        e = torch.nn.functional.interpolate(e, size=(rgb.shape[-1], rgb.shape[-2]), mode="bicubic")
+        return torch.cat((rgb, e * self.config.satclip.scaling_factor), dim=1)
+
+    @torch.no_grad()
+    def predict_step(self, rgb, coords=None, embeds=None):
+        assert self.training is False, "Model is in training mode, set to eval mode before predicting"
+        if not self.satclip:
+            return self.forward(rgb)
+        batch = {"rgb": rgb, "nir": None, "coords": coords, "embeds": embeds}
+        if self.concat:
+            rgb, _ = self.extract_batch(batch)
+            return self.forward(rgb)
         if self.inject:
-            return batch["rgb"], batch["nir"], batch["embeds"]
-        return batch["rgb"], batch["nir"]
+            rgb, _, embeds = self.extract_batch(batch)
+            return self.forward(rgb, embeds)
+        raise NotImplementedError("SatClip Style not recognized, choose 'concat' or 'inject'")
+
+    def extract_batch(self, batch):                     # pix2pix.py:426-463
+        rgb, nir = batch["rgb"], batch["nir"]
+        if not self.satclip:
+            return rgb, nir
+        if self.concat:
+            return self.satclip_get_concat(batch["coords"], rgb), nir
+        if self.inject:
+            embeds = batch.get("embeds")
+            if embeds is None:
+                embeds = self.satclip_get_inject(batch["coords"])
+            return rgb, nir, embeds
+        raise NotImplementedError("SatClip Style not recognized, choose 'concat' or 'inject'")
 
     def _toggle(self, active: nn.Module, frozen: nn.Module):
         """PL-1.9 ``toggle_optimizer``: parameters of the optimizer that is not stepping do not require grad."""
