@@ -275,6 +275,16 @@ int ng_hist_match(const float* image, const float* reference, int32_t B, int32_t
 int ng_sort_segments(const float* src, int32_t segs, int32_t n, float* sorted_out, void* workspace,
                      int64_t workspace_bytes, void* stream);
 
+/* Optional generator losses (utils/losses.py:10-29 ssim_loss, :64-78 emd_loss -- pix2pix.py:12-13,233-242), forward and
+ * d/dpred (dpred may be NULL).  ssim_loss: out1[0] = 1 - mean(kornia.metrics.ssim(pred, target, window)); planes = B*C;
+ * scratch: ng_ssim_loss_scratch_floats() floats, 16-byte aligned.  emd_loss: per sample softmax over the N = C*H*W
+ * entries, cumulative sums, out1[0] = mean |cdf_pred - cdf_target| over B*N; scratch: B doubles. */
+int64_t ng_ssim_loss_scratch_floats(int32_t planes, int32_t H, int32_t W);
+int ng_ssim_loss(const float* pred, const float* target, int32_t planes, int32_t H, int32_t W, int32_t window,
+                 float max_val, float* out1, float* dpred, float* scratch, void* stream);
+int ng_emd_loss(const float* pred, const float* target, int32_t B, int32_t N, float* out1, float* dpred,
+                double* scratch, void* stream);
+
 /* SatCLIP location encoder (model/satclip/satclip_wrapper.py:29-34, location_encoder.py:73-151,267-275,
  * positional_encoding/spherical_harmonics.py:27-42 + spherical_harmonics_closed_form.py:8-40): lonlat [B][2] degrees
  * (float64) -> L*L real spherical harmonics -> SIREN MLP -> out [B][dim_out] float32; float64 arithmetic like the

@@ -69,6 +69,9 @@ _SIGNATURES = {
     "ng_sort_segments": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "ng_image_metrics_scratch_floats": (c_i64, [c_i32, c_i32, c_i32]),
     "ng_image_metrics": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ng_ssim_loss_scratch_floats": (c_i64, [c_i32, c_i32, c_i32]),
+    "ng_ssim_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "ng_emd_loss": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "ng_satclip_encode": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, C.c_double, C.c_double, c_vp, c_vp]),
     "ng_linear": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_lsgan_loss": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_i32, c_vp, c_f32, c_vp]),

@@ -294,9 +294,13 @@ namespace ng {
 
 constexpr int MT_W = 32, MT_H = 8, MT_MAXWIN = 11;
 
+// GRAD: also writes, per pixel, the partial derivatives of the SSIM map w.r.t. the windowed moments of image a
+// (d/d mu_a with the variance terms chained in, d/d E[a^2], d/d E[ab]) for ssim_bwd_kernel.
+template <bool GRAD>
 __global__ void __launch_bounds__(256)
 image_metrics_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int win, float c1, float c2,
-                     const float* __restrict__ gauss, float* __restrict__ partial, int tiles_x, int tiles_y) {
+                     const float* __restrict__ gauss, float* __restrict__ partial, int tiles_x, int tiles_y,
+                     float4* __restrict__ dmaps) {
   __shared__ float sa[(MT_H + MT_MAXWIN - 1) * (MT_W + MT_MAXWIN - 1)];
   __shared__ float sb[(MT_H + MT_MAXWIN - 1) * (MT_W + MT_MAXWIN - 1)];
   __shared__ float gk[MT_MAXWIN];
@@ -335,6 +339,14 @@ image_metrics_kernel(const float* __restrict__ a, const float* __restrict__ b, i
     const float num = (2.f * m1 * m2 + c1) * (2.f * s12 + c2);
     const float den = (m1 * m1 + m2 * m2 + c1) * (s1 + s2 + c2);
     ss = num / (den + 1e-12f);
+    if (GRAD) {
+      const float A1 = 2.f * m1 * m2 + c1, A2 = 2.f * s12 + c2, B1 = m1 * m1 + m2 * m2 + c1, B2 = s1 + s2 + c2;
+      const float inv = 1.f / (den + 1e-12f);
+      const float d_e11 = -ss * B1 * inv;                         // via s1 in B2
+      const float d_e12 = 2.f * A1 * inv;                         // via s12 in A2
+      const float d_m1 = 2.f * m2 * (A2 - A1) * inv - ss * 2.f * m1 * (B2 - B1) * inv;
+      dmaps[plane + (size_t)oy * W + ox] = make_float4(d_m1, d_e11, d_e12, 0.f);
+    }
     const float d = sa[(ly + half) * PW + lx + half] - sb[(ly + half) * PW + lx + half];
     l1 = fabsf(d);
     l2 = d * d;
@@ -389,10 +401,238 @@ extern "C" int ng_image_metrics(const float* pred, const float* target, int32_t 
   int e = check_cuda(cudaMemcpyAsync(gdev, g, sizeof(float) * window, cudaMemcpyHostToDevice, st), "image_metrics window");
   if (e) return e;
   const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
-  image_metrics_kernel<<<(unsigned)blocks, 256, 0, st>>>(pred, target, H, W, window, c1, c2, gdev, scratch, tiles_x, tiles_y);
+  image_metrics_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(pred, target, H, W, window, c1, c2, gdev, scratch, tiles_x,
+                                                                tiles_y, nullptr);
   NG_LAUNCH_CHECK("image_metrics_kernel");
   image_metrics_finalize_kernel<<<1, 32, 0, st>>>(scratch, (int)blocks, 1.0 / ((double)planes * H * W), max_val, out4);
   NG_LAUNCH_CHECK("image_metrics_finalize_kernel");
+  return NG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Optional generator losses (utils/losses.py:10-29 ssim_loss, :64-78 emd_loss = pix2pix.py's hist_loss; SURVEY.md 8f
+// rank 4), forward and d/dpred.
+//   ssim_loss = 1 - mean(kornia.metrics.ssim(pred, target, 11)).  The forward is image_metrics_kernel<true>; the
+//   backward is the adjoint of the reflect-bordered Gaussian filter applied to the three derivative maps:
+//     d/dx_j = sum_q in fold(j) sum_k g[k] (Dm + 2 x_j De11 + y_j De12)[q - half + k]     (maps zero outside the image)
+//   where fold(j) = {j} plus the out-of-image positions the reflect border maps onto j.
+//   emd_loss = mean |cumsum(softmax(pred_b)) - cumsum(softmax(target_b))| over all B * N entries; with s = sign of the
+//   CDF difference, E_k = sum_{i<k} s_i and A = sum_j p_j E_j:  d/dx_k = p_k (A - E_k) / (B N).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace ng {
+
+__global__ void ssim_loss_finalize_kernel(const float* __restrict__ partial, int nblocks, double inv_n,
+                                          float* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 1024) s += partial[(size_t)i * 4 + 2];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 32; ++i) t += red[i];
+    out[0] = (float)(1.0 - t * inv_n);
+  }
+}
+
+__device__ __forceinline__ int fold_list(int j, int n, int half, int* q) {
+  int c = 0;
+  q[c++] = j;
+  if (j >= 1 && j <= half) q[c++] = -j;
+  if (j <= n - 2 && j >= n - 1 - half) q[c++] = 2 * (n - 1) - j;
+  return c;
+}
+
+__global__ void __launch_bounds__(256)
+ssim_bwd_kernel(const float4* __restrict__ dmaps, const float* __restrict__ x, const float* __restrict__ y, int H, int W,
+                int win, const float* __restrict__ gauss, float scale, long long total, float* __restrict__ dx) {
+  __shared__ float gk[MT_MAXWIN];
+  if (threadIdx.x < win) gk[threadIdx.x] = gauss[threadIdx.x];
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int half = win / 2;
+  const int jx = (int)(idx % W), jy = (int)((idx / W) % H);
+  const size_t plane = (size_t)(idx / ((long long)W * H)) * H * W;
+  const float cx = 2.f * x[idx], cy = y[idx];
+  int qx[3], qy[3];
+  const int nx = fold_list(jx, W, half, qx), ny = fold_list(jy, H, half, qy);
+  float acc = 0.f;
+  for (int a = 0; a < ny; ++a)
+    for (int b = 0; b < nx; ++b) {
+      const int y0 = qy[a] - half, x0 = qx[b] - half;
+      for (int ky = max(0, -y0); ky < win && y0 + ky < H; ++ky) {
+        const float4* row = dmaps + plane + (size_t)(y0 + ky) * W;
+        float r = 0.f;
+        for (int kx = max(0, -x0); kx < win && x0 + kx < W; ++kx) {
+          const float4 d = __ldg(row + x0 + kx);
+          r = fmaf(gk[kx], fmaf(cy, d.z, fmaf(cx, d.y, d.x)), r);
+        }
+        acc = fmaf(gk[ky], r, acc);
+      }
+    }
+  dx[idx] = scale * acc;
+}
+
+constexpr int EMD_T = 1024;
+
+// inclusive scan over the 1024 threads of a block; `total` = the block sum.  ws: 32 entries of shared memory.
+template <typename T>
+__device__ __forceinline__ T emd_block_scan(T v, T* ws, T& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const T n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  __syncthreads();                       // previous use of ws is finished
+  if (lane == 31) ws[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    T w = ws[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      const T n = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += n;
+    }
+    ws[lane] = w;
+  }
+  __syncthreads();
+  total = ws[31];
+  return v + (warp ? ws[warp - 1] : (T)0);
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T emd_block_reduce(T v, T* ws, Op op) {
+  for (int o = 16; o; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T r = ws[0];
+  for (int i = 1; i < 32; ++i) r = op(r, ws[i]);
+  return r;
+}
+
+__global__ void __launch_bounds__(EMD_T)
+emd_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, int N, double* __restrict__ partial,
+                float* __restrict__ grad, float gscale) {
+  __shared__ float wf[32];
+  __shared__ int wi[32];
+  __shared__ double wd[32];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* x = pred + (size_t)b * N;
+  const float* y = target + (size_t)b * N;
+  float mx = -INFINITY, my = -INFINITY;
+  for (int i = t; i < N; i += EMD_T) { mx = fmaxf(mx, x[i]); my = fmaxf(my, y[i]); }
+  auto fmx = [](float a, float c) { return fmaxf(a, c); };
+  auto dsum = [](double a, double c) { return a + c; };
+  mx = emd_block_reduce(mx, wf, fmx);
+  my = emd_block_reduce(my, wf, fmx);
+  double sx = 0.0, sy = 0.0;
+  for (int i = t; i < N; i += EMD_T) { sx += expf(x[i] - mx); sy += expf(y[i] - my); }
+  sx = emd_block_reduce(sx, wd, dsum);
+  sy = emd_block_reduce(sy, wd, dsum);
+  const float inv_sx = (float)(1.0 / sx), inv_sy = (float)(1.0 / sy);
+  double carry = 0.0, loss = 0.0, A = 0.0;
+  long long carry_s = 0;
+  for (int base = 0; base < N; base += EMD_T) {
+    const int i = base + t;
+    const bool valid = i < N;
+    const float p = valid ? expf(x[i] - mx) * inv_sx : 0.f;
+    const float q = valid ? expf(y[i] - my) * inv_sy : 0.f;
+    float tot;
+    const float incl = emd_block_scan(p - q, wf, tot);
+    const float diff = (float)(carry + (double)incl);
+    const int s = valid ? ((diff > 0.f) - (diff < 0.f)) : 0;
+    int stot;
+    const int sincl = emd_block_scan(s, wi, stot);
+    if (valid) {
+      const long long E = carry_s + sincl - s;
+      loss += fabsf(diff);
+      A += (double)p * (double)E;
+      if (grad) grad[(size_t)b * N + i] = (float)E;
+    }
+    carry += (double)tot;
+    carry_s += stot;
+  }
+  loss = emd_block_reduce(loss, wd, dsum);
+  A = emd_block_reduce(A, wd, dsum);
+  if (t == 0) partial[b] = loss;
+  if (grad) {
+    const float Af = (float)A;
+    for (int i = t; i < N; i += EMD_T) {
+      const float p = expf(x[i] - mx) * inv_sx;
+      grad[(size_t)b * N + i] = p * (Af - grad[(size_t)b * N + i]) * gscale;
+    }
+  }
+}
+
+__global__ void emd_finalize_kernel(const double* __restrict__ partial, int B, double inv_n, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < B; ++i) s += partial[i];
+    out[0] = (float)(s * inv_n);
+  }
+}
+
+}  // namespace ng
+
+extern "C" int64_t ng_ssim_loss_scratch_floats(int32_t planes, int32_t H, int32_t W) {
+  if (planes <= 0 || H <= 0 || W <= 0) return NG_E_ARG;
+  // tile partials + window (image_metrics layout, rounded to 16 bytes) + float4 derivative maps
+  const int64_t head = (ng_image_metrics_scratch_floats(planes, H, W) + 3) / 4 * 4;
+  return head + (int64_t)planes * H * W * 4;
+}
+
+extern "C" int ng_ssim_loss(const float* pred, const float* target, int32_t planes, int32_t H, int32_t W, int32_t window,
+                            float max_val, float* out1, float* dpred, float* scratch, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(pred && target && out1 && scratch && planes > 0 && H > 0 && W > 0, NG_E_ARG, "ssim_loss: bad arguments");
+  NG_REQUIRE(window % 2 == 1 && window >= 1 && window <= MT_MAXWIN, NG_E_UNSUPPORTED, "ssim_loss: odd window <= 11");
+  NG_REQUIRE(window / 2 < H && window / 2 < W, NG_E_SHAPE, "ssim_loss: window larger than the image");
+  NG_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, NG_E_ALIGN, "ssim_loss: scratch must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles_x = (W + MT_W - 1) / MT_W, tiles_y = (H + MT_H - 1) / MT_H;
+  const long long blocks = (long long)planes * tiles_x * tiles_y;
+  NG_REQUIRE(blocks < (1ll << 31), NG_E_SHAPE, "ssim_loss: too many tiles");
+  float g[MT_MAXWIN];
+  float sum = 0.f;
+  for (int i = 0; i < window; ++i) { const float x = (float)(i - window / 2); g[i] = expf(-(x * x) / (2.f * 1.5f * 1.5f)); sum += g[i]; }
+  for (int i = 0; i < window; ++i) g[i] /= sum;
+  float* gdev = scratch + blocks * 4;
+  int e = check_cuda(cudaMemcpyAsync(gdev, g, sizeof(float) * window, cudaMemcpyHostToDevice, st), "ssim_loss window");
+  if (e) return e;
+  const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
+  const int64_t head = (ng_image_metrics_scratch_floats(planes, H, W) + 3) / 4 * 4;
+  float4* dmaps = reinterpret_cast<float4*>(scratch + head);
+  const long long total = (long long)planes * H * W;
+  if (dpred)
+    image_metrics_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(pred, target, H, W, window, c1, c2, gdev, scratch, tiles_x,
+                                                                 tiles_y, dmaps);
+  else
+    image_metrics_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(pred, target, H, W, window, c1, c2, gdev, scratch, tiles_x,
+                                                                  tiles_y, nullptr);
+  NG_LAUNCH_CHECK("image_metrics_kernel");
+  ssim_loss_finalize_kernel<<<1, 1024, 0, st>>>(scratch, (int)blocks, 1.0 / (double)total, out1);
+  NG_LAUNCH_CHECK("ssim_loss_finalize_kernel");
+  if (dpred) {
+    ssim_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dmaps, pred, target, H, W, window, gdev,
+                                                                     (float)(-1.0 / (double)total), total, dpred);
+    NG_LAUNCH_CHECK("ssim_bwd_kernel");
+  }
+  return NG_OK;
+}
+
+extern "C" int ng_emd_loss(const float* pred, const float* target, int32_t B, int32_t N, float* out1, float* dpred,
+                           double* scratch, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(pred && target && out1 && scratch && B > 0 && N > 0, NG_E_ARG, "emd_loss: bad arguments");
+  NG_REQUIRE(N < (1 << 24), NG_E_SHAPE, "emd_loss: at most 2^24 - 1 elements per sample");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double inv_n = 1.0 / ((double)B * (double)N);
+  emd_loss_kernel<<<(unsigned)B, EMD_T, 0, st>>>(pred, target, N, scratch, dpred, (float)inv_n);
+  NG_LAUNCH_CHECK("emd_loss_kernel");
+  emd_finalize_kernel<<<1, 32, 0, st>>>(scratch, B, inv_n, out1);
+  NG_LAUNCH_CHECK("emd_finalize_kernel");
   return NG_OK;
 }
 

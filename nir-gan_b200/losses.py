@@ -1,4 +1,4 @@
-"""Fused loss kernels behind autograd (LSGAN, L1 + NDVI/NDWI/EVI)."""
+"""Fused loss kernels behind autograd (LSGAN, L1 + the six remote-sensing indices, SSIM loss, EMD / histogram loss)."""
 from __future__ import annotations
 
 import torch
@@ -140,3 +140,72 @@ def rs_index(rgb, nir, pred, which: str, loss_eps: bool):
     L.call("ng_rs_index", rgb.data_ptr(), nir.data_ptr(), p.data_ptr(), B, H * W, RS_TERMS.index(which), int(loss_eps),
            a.data_ptr(), b.data_ptr(), _stream(p))
     return a, b
+
+
+class _SsimLossFn(torch.autograd.Function):
+    """1 - mean(kornia.metrics.ssim(img1, img2, window)); d/dimg1 from the adjoint-filter kernel (img2 is the target)."""
+
+    @staticmethod
+    def forward(ctx, img1, img2, window):
+        B, Cn, H, W = img1.shape
+        a, b = img1.contiguous().float(), img2.contiguous().float()
+        n = L.load().ng_ssim_loss_scratch_floats(B * Cn, H, W)
+        scratch = torch.empty(int(n), dtype=torch.float32, device=a.device)
+        out = torch.empty(1, dtype=torch.float32, device=a.device)
+        need_grad = img1.requires_grad
+        grad = torch.empty_like(a) if need_grad else None
+        L.call("ng_ssim_loss", a.data_ptr(), b.data_ptr(), B * Cn, H, W, int(window), 1.0, out.data_ptr(),
+               grad.data_ptr() if need_grad else None, scratch.data_ptr(), _stream(a))
+        if need_grad:
+            ctx.save_for_backward(grad)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None, None
+
+
+def ssim_loss(img1, img2, window_size: int = 11):
+    """utils/losses.py:10-29.  Gradient flows to img1 (the prediction) only, as it is used in pix2pix.py:234."""
+    require_cuda(img1, "img1")
+    require_cuda(img2, "img2")
+    if img2.requires_grad:
+        raise NotImplementedError("ssim_loss: gradient w.r.t. the second image is not implemented")
+    return _SsimLossFn.apply(img1, img2, int(window_size))
+
+
+class _EmdLossFn(torch.autograd.Function):
+    """mean |cumsum(softmax(pred_b)) - cumsum(softmax(target_b))|, one block per sample; d/dpred in the same launch."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        B = pred.shape[0]
+        p, t = pred.contiguous().float().view(B, -1), target.contiguous().float().view(B, -1)
+        scratch = torch.empty(B, dtype=torch.float64, device=p.device)
+        out = torch.empty(1, dtype=torch.float32, device=p.device)
+        need_grad = pred.requires_grad
+        grad = torch.empty_like(p) if need_grad else None
+        L.call("ng_emd_loss", p.data_ptr(), t.data_ptr(), B, p.shape[1], out.data_ptr(),
+               grad.data_ptr() if need_grad else None, scratch.data_ptr(), _stream(p))
+        if need_grad:
+            ctx.save_for_backward(grad)
+        ctx.shape = pred.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return (grad * g).view(ctx.shape), None
+
+
+def emd_loss(pred, target):
+    """utils/losses.py:64-78 (imported as hist_loss by pix2pix.py:13).  Inputs must be finite (the reference asserts it on
+    the host; here non-finite values propagate to the loss instead of forcing a device sync)."""
+    require_cuda(pred, "pred")
+    require_cuda(target, "target")
+    if target.requires_grad:
+        raise NotImplementedError("emd_loss: gradient w.r.t. the target is not implemented")
+    if pred.shape != target.shape:
+        raise ValueError(f"emd_loss: shapes differ: {tuple(pred.shape)} vs {tuple(target.shape)}")
+    return _EmdLossFn.apply(pred, target)

@@ -14,7 +14,8 @@ import torch.nn as nn
 
 from . import networks
 from .generator_inject import define_G_inject
-from ..losses import rs_pixel_losses
+from ..losses import emd_loss as hist_loss
+from ..losses import rs_pixel_losses, ssim_loss
 
 
 def _get(cfg, name, default=None):
@@ -142,8 +143,11 @@ class Px2Px(nn.Module):
         pred = self.forward(rgb, embeds)
         pred_fake = self.netD(torch.cat((rgb, pred), 1))
         loss_G = self.criterionGAN(pred_fake, True) * o.lambda_GAN
-        if _get(o, "lambda_ssim", 0.0) > 0.0 or _get(o, "lambda_hist", 0.0) > 0.0:
-            raise NotImplementedError("ssim / hist losses are outside the nirgan_b200 hot path (weight 0 in all configs)")
+        extra = []                                             # pix2pix.py:231-243, added after GAN + L1
+        if _get(o, "lambda_ssim", 0.0) > 0.0:
+            extra.append(ssim_loss(pred, nir) * o.lambda_ssim)
+        if _get(o, "lambda_hist", 0.0) > 0.0:
+            extra.append(hist_loss(pred, nir) * o.lambda_hist)
         lam_rs = float(_get(o, "lambda_rs_losses", 0.0))
         w = _get(o, "internal_rs_loss_weights", None)
         wd = dict(w) if isinstance(w, dict) else (vars(w) if w is not None else {})
@@ -155,7 +159,11 @@ class Px2Px(nn.Module):
         ws = [float(o.lambda_L1)] + [lam_rs * float(wd.get(k, 0.0)) if (lam_rs > 0.0 and float(wd.get(k, 0.0)) > 0.0)
                                      else 0.0 for k in keys]
         parts = rs_pixel_losses(rgb, nir, pred, ws, crit)    # one fused pass: L1 + the weighted indices (+ d/dpred)
-        for wi, pi in zip(ws, parts):
+        if ws[0] != 0.0:
+            loss_G = loss_G + ws[0] * parts[0]
+        for e in extra:
+            loss_G = loss_G + e
+        for wi, pi in zip(ws[1:], parts[1:]):
             if wi != 0.0:
                 loss_G = loss_G + wi * pi
         return loss_G

@@ -97,3 +97,18 @@ def calculate_metrics(pred: torch.Tensor, target: torch.Tensor, phase: str = "tr
     return {phase + "/L1": F.l1_loss(pred, target).item(), phase + "/L2": mse.item(),
             phase + "/PSNR": (10.0 * torch.log10(1.0 / mse)).item(),
             phase + "/SSIM": ssim_map(pred, target, 5, 1.0).mean().item()}
+
+
+def ssim_loss(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11) -> torch.Tensor:
+    """utils/losses.py:10-29: 1 - kornia.metrics.ssim(img1, img2, window_size).mean() (differentiable, torch)."""
+    return 1.0 - ssim_map(img1.float(), img2.float(), window_size).mean()
+
+
+def emd_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """utils/losses.py:64-78 (pix2pix.py's hist_loss): mean |cumsum(softmax) difference| over (B, C*H*W); pinned
+    bit-exact against the reference function by oracle/pin_losses.py."""
+    pred = pred.reshape(pred.shape[0], -1)
+    target = target.reshape(target.shape[0], -1)
+    pred_cdf = torch.cumsum(F.softmax(pred, dim=1), dim=1)
+    target_cdf = torch.cumsum(F.softmax(target, dim=1), dim=1)
+    return torch.mean(torch.abs(pred_cdf - target_cdf))
