@@ -115,6 +115,10 @@ class ActBuf:
 PROFILE = [None]
 # inference plans are replayed as CUDA graphs (NIRGAN_B200_GRAPH=0 launches every kernel from the host instead)
 GRAPHS = [os.environ.get("NIRGAN_B200_GRAPH", "1") != "0"]
+# ops added with side=True (the weight gradients: off the critical path of a backward pass) run on a second stream so
+# that they overlap the HBM-bound norm-backward kernels of the next layer (NIRGAN_B200_SIDE_STREAM=0: single stream)
+SIDE_STREAM = [os.environ.get("NIRGAN_B200_SIDE_STREAM", "1") != "0"]
+_SIDE: Dict[int, "torch.cuda.Stream"] = {}
 
 
 class Plan:
@@ -126,11 +130,14 @@ class Plan:
         self.launches = 0          # kernel launches per run (for bench.py's gpu_launches)
         self.records: dict = {}
         self.labels: List[str] = []
+        self.side: List[bool] = []
+        self._events: list = []
 
-    def add(self, fn_name: str, *args, launches: int = 1, label: str = ""):
+    def add(self, fn_name: str, *args, launches: int = 1, label: str = "", side: bool = False):
         fn = getattr(L.load(), fn_name)
         self.ops.append((fn, args, fn_name))
         self.labels.append(label or fn_name)
+        self.side.append(bool(side))
         self.launches += launches
 
     def run_graphed(self, stream: "torch.cuda.Stream"):
@@ -161,10 +168,57 @@ class Plan:
     def run(self, stream_ptr: int):
         if PROFILE[0] is not None:
             return self._run_profiled(stream_ptr)
+        if SIDE_STREAM[0] and any(self.side):
+            return self._run_two_streams(stream_ptr)
         for fn, args, name in self.ops:
             st = fn(*args, stream_ptr)
             if st != 0:
                 L.check(st, name)
+
+    def _run_two_streams(self, stream_ptr: int):
+        """Side ops depend on everything issued before them on the main stream and on earlier side ops; nothing on the
+        main stream depends on them until the plan ends (they only write their own weight-gradient buffers and a
+        workspace that side ops share, serialised by the side stream).  Each side op is submitted AFTER the next main
+        op, so the main op takes the SMs first and the side op then overlaps what follows it."""
+        dev = torch.cuda.current_device()
+        side = _SIDE.get(dev)
+        if side is None:
+            side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+        main = torch.cuda.ExternalStream(stream_ptr, device=dev) if stream_ptr else torch.cuda.default_stream(dev)
+        n_side = sum(self.side)
+        while len(self._events) < n_side + 1:
+            self._events.append(torch.cuda.Event())
+        side_ptr = side.cuda_stream
+        pending = None
+        k = 0
+        for (fn, args, name), is_side in zip(self.ops, self.side):
+            if is_side:
+                if pending is not None:
+                    self._launch(pending, side_ptr)
+                ev = self._events[k]
+                k += 1
+                ev.record(main)
+                side.wait_event(ev)
+                pending = (fn, args, name)
+                continue
+            st = fn(*args, stream_ptr)
+            if st != 0:
+                L.check(st, name)
+            if pending is not None:
+                self._launch(pending, side_ptr)
+                pending = None
+        if pending is not None:
+            self._launch(pending, side_ptr)
+        ev = self._events[n_side]
+        ev.record(side)
+        main.wait_event(ev)
+
+    @staticmethod
+    def _launch(op, stream_ptr: int):
+        fn, args, name = op
+        st = fn(*args, stream_ptr)
+        if st != 0:
+            L.check(st, name)
 
 
 def _run_profiled(self, stream_ptr: int):

@@ -256,7 +256,7 @@ class UnitGraph:
                 a = eng.conv_args(xz, dwp, dz.t, 64, 1, 1, 0, Hz, Wz)
                 plan.keepalive.append(a)
                 plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), dbb.data_ptr(), ws.data_ptr(), ws.numel() * 4,
-                         launches=3, label=tag + ".head.wgrad")
+                         launches=3, label=tag + ".head.wgrad", side=True)
                 plan.records["tap_head"] = {"conv": head, "dwp": dwp, "db": dbb, "center": (K // 2) * K + K // 2}
             # data gradient: g[pixel][c] = sum_t dz[pixel][t] * w[t][c]  (1x1 conv over the 64 stored taps)
             gbuf = eng.act(tag + ".head.dx", x.B, x.H, x.W, x.C, x.pad)
@@ -311,7 +311,7 @@ class UnitGraph:
                 a = self._args(u, u.x, dwp, dY.t, epilogue=L.EPI_HEAD if u.kind == "head" else L.EPI_RAW)
                 plan.keepalive.append(a)
                 plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), _ptr(dbb), ws.data_ptr(), ws.numel() * 4, launches=2,
-                         label=pre + ".wgrad")
+                         label=pre + ".wgrad", side=True)
                 dw[i], db[i] = dwp, dbb
             # ---- data gradient ----
             if i == 0 and not need_dx:

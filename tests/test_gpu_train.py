@@ -348,3 +348,40 @@ def test_config4_full_size_step_properties():
         step = (w1 - w0)[big]
         assert float((step.abs() - 2e-4).abs().max()) <= 2e-6
         assert torch.equal(torch.sign(step), -torch.sign(gr[big]))
+
+
+def test_side_stream_weight_gradients_equal_single_stream():
+    """The weight gradients run on a second stream (engine.SIDE_STREAM) overlapping the next layer's norm backward; at a
+    size where the overlap is real (batch 16, 256x256) every D and G gradient must equal the single-stream result
+    (same kernels, same deterministic split-K reduction; the atomics of the thin CUDA-core kernels allow 1e-4 relative)."""
+    from nirgan_b200 import engine
+    from nirgan_b200.model.pix2pix import Px2Px
+    torch.manual_seed(0)
+    model = Px2Px(_cfg(inject=True)).cuda().train()
+    model.netG.configure_b200(precision="fp16", impl="tc")
+    model.netD.configure_b200(precision="fp16", impl="tc")
+    g = torch.Generator().manual_seed(3)
+    batch = {"rgb": torch.rand(16, 3, 256, 256, generator=g).cuda(), "nir": torch.rand(16, 1, 256, 256, generator=g).cuda(),
+             "embeds": torch.randn(16, 256, generator=g).cuda()}
+
+    def grads(side):
+        engine.SIDE_STREAM[0] = side
+        out = {}
+        for idx, net in ((0, model.netD), (1, model.netG)):
+            for p in list(model.netD.parameters()) + list(model.netG.parameters()):
+                p.grad = None
+            model.training_step(batch, 0, idx).backward()
+            torch.cuda.synchronize()
+            for n_, p in net.named_parameters():
+                out[(idx, n_)] = p.grad.detach().clone()
+        return out
+
+    keep = engine.SIDE_STREAM[0]
+    try:
+        a, b, c = grads(True), grads(False), grads(True)
+    finally:
+        engine.SIDE_STREAM[0] = keep
+    for k in b:
+        scale = float(b[k].abs().max()) + 1e-30
+        assert float((a[k] - b[k]).abs().max()) <= 1e-4 * scale, k
+        assert float((c[k] - b[k]).abs().max()) <= 1e-4 * scale, k
