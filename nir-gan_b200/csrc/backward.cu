@@ -460,11 +460,33 @@ static void launch_in_bwd(const BwdArgs& a, dim3 grid, size_t smem, cudaStream_t
 #undef NG_BWD
 }
 
-// pass-1 blocks per image: long blocks (fewer partial slots for pass 2 to add up) as long as the grid still fills the GPU
+// Pixels-per-block multiplier (block = pstep * mult consecutive pixels of one image) for a grid of B * ceil(npix / ppb)
+// equal blocks at `resident` blocks per wave: the candidate with the best wave efficiency waves / ceil(waves) (the last,
+// partly filled wave of an HBM-bound kernel runs at a fraction of the bandwidth), longer blocks on ties.
+static int in_bwd_pick_mult(int B, int npix, int pstep, int lo, int hi) {
+  static const bool tune = [] { const char* e = getenv("NIRGAN_B200_BWD_TUNE"); return !(e && e[0] == '0'); }();
+  const double resident = 3.0 * num_sms();
+  int best = lo;
+  double best_eff = -1.0;
+  for (int mult = hi; mult >= lo; --mult) {
+    const long long blocks = (long long)B * ((npix + pstep * mult - 1) / (pstep * mult));
+    const double waves = blocks / resident;
+    if (waves < 1.0 && mult > lo) continue;               // does not fill the GPU once: use shorter blocks
+    const double eff = waves / ceil(waves);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = mult; }
+  }
+  if (!tune) return -1;
+  return best;
+}
+
+// pass-1 blocks per image: long blocks (fewer partial slots to combine) as long as the grid fills whole waves
 static int in_bwd_pass1_blocks(int B, int H, int W, int C) {
   const int pstep = 256 / (C / 8);
-  int mult = 64;
-  while (mult > 4 && (long long)B * ((H * W + pstep * mult - 1) / (pstep * mult)) < 4ll * num_sms()) mult >>= 1;
+  int mult = in_bwd_pick_mult(B, H * W, pstep, 4, 64);
+  if (mult < 0) {
+    mult = 64;
+    while (mult > 4 && (long long)B * ((H * W + pstep * mult - 1) / (pstep * mult)) < 4ll * num_sms()) mult >>= 1;
+  }
   return (H * W + pstep * mult - 1) / (pstep * mult);
 }
 
@@ -514,7 +536,10 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
       NG_LAUNCH_CHECK("in_bwd_combine_kernel");
     }
   }
-  a.ppb = pstep * 16;
+  {
+    const int mult2 = in_bwd_pick_mult(B, H * W, pstep, 4, 32);
+    a.ppb = pstep * (mult2 < 0 ? 16 : mult2);
+  }
   dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)B);
   DISPATCH_T(dtype, (launch_in_bwd<T, 2>(a, grid, 0, st, g_halo, g_skip, y, mean_rstd, inject_e, inject_scale,
                                          sums_scratch, nullptr, nullptr, dy, do_out)));

@@ -191,61 +191,74 @@ wgrad_simt_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, c
 // Weight gradient of a single-real-output-channel convolution (PatchGAN last layer, stored Cout = 16 with channel 0
 // real): dw[tap][0][k] = sum_px dy[px][0] * x[px + tap][k].  grid = (taps, pixel splits).  Thread t owns the 8-channel
 // group cg = t mod Cin/8 (one 16-byte load per pixel) and the pixel lane pl = t / (Cin/8); lanes walk the split's
-// pixels with stride `lanes`, four loads in flight.  Memory-bound (x is re-read per tap from L2).
+// pixels with stride `lanes`, four loads in flight (32-bit index arithmetic), and are summed through shared memory so
+// the block issues one atomic per output.  Latency-bound: many short splits.
 template <typename T>
 __global__ void __launch_bounds__(256)
 wgrad_cout1_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, const T* __restrict__ dy,
                    float* __restrict__ dw, int pix_per_split) {
+  __shared__ float red[256 * 8];
   const int tp = blockIdx.x, sp = blockIdx.y;
   int phase = 0;
   while (tp >= g.phase_tap0[phase + 1]) ++phase;
   const int C8 = g.Cin >> 3;
   const int lanes = 256 / C8;                       // C8 divides 256 (checked by the launcher)
   const int cg = threadIdx.x % C8, pl = threadIdx.x / C8;
-  const long long npix = (long long)g.B * g.VH * g.VW;
-  const long long p0 = (long long)sp * pix_per_split, p1 = min(npix, p0 + pix_per_split);
+  const unsigned npix = (unsigned)g.B * g.VH * g.VW;      // < 2^31 (checked by the launcher)
+  const unsigned p0 = (unsigned)sp * pix_per_split, p1 = min(npix, p0 + pix_per_split);
+  const int tdy = g.taps[tp].dy, tdx = g.taps[tp].dx, poy = g.phase_oy[phase], pox = g.phase_ox[phase];
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   constexpr int U = 4;
-  for (long long pb = p0 + pl; pb < p1; pb += (long long)lanes * U) {
+  for (unsigned pb = p0 + pl; pb < p1; pb += lanes * U) {
     float d[U];
-    float xv[U][8];
+    uint4 raw[U];
+    const T* xp[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long p = pb + (long long)u * lanes;
+      const unsigned p = pb + u * lanes;
       d[u] = 0.f;
+      xp[u] = nullptr;
       if (p < p1) {
-        const int vj = (int)(p % g.VW);
-        const long long r = p / g.VW;
-        const int vi = (int)(r % g.VH), n = (int)(r / g.VH);
-        const int oy = g.OS * vi + g.phase_oy[phase], ox = g.OS * vj + g.phase_ox[phase];
-        const int by = g.S * vi + g.taps[tp].dy, bx = g.S * vj + g.taps[tp].dx;
+        const unsigned r = p / (unsigned)g.VW;
+        const int vj = (int)(p - r * g.VW);
+        const int n = (int)(r / (unsigned)g.VH);
+        const int vi = (int)(r - (unsigned)n * g.VH);
+        const int oy = g.OS * vi + poy, ox = g.OS * vj + pox;
+        const int by = g.S * vi + tdy, bx = g.S * vj + tdx;
         if (oy < g.Hout && ox < g.Wout && by >= 0 && by < g.Hb && bx >= 0 && bx < g.Wb) {
           d[u] = to_f32<T>(dy[(((size_t)n * g.Hout + oy) * g.Wout + ox) * g.Cout]);
-          const T* xp = x + (((size_t)n * g.Hb + by) * g.Wb + bx) * g.Cin + cg * 8;
-          if constexpr (sizeof(T) == 2) {
-            const uint4 v = *reinterpret_cast<const uint4*>(xp);
-            const float2 a0 = unpack2<T>(v.x), a1 = unpack2<T>(v.y), a2 = unpack2<T>(v.z), a3 = unpack2<T>(v.w);
-            xv[u][0] = a0.x; xv[u][1] = a0.y; xv[u][2] = a1.x; xv[u][3] = a1.y;
-            xv[u][4] = a2.x; xv[u][5] = a2.y; xv[u][6] = a3.x; xv[u][7] = a3.y;
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) xv[u][k] = xp[k];
-          }
+          xp[u] = x + (((size_t)n * g.Hb + by) * g.Wb + bx) * g.Cin + cg * 8;
+          if constexpr (sizeof(T) == 2) raw[u] = *reinterpret_cast<const uint4*>(xp[u]);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (d[u] != 0.f) {
+      if (xp[u] == nullptr || d[u] == 0.f) continue;
+      if constexpr (sizeof(T) == 2) {
+        const float2 a0 = unpack2<T>(raw[u].x), a1 = unpack2<T>(raw[u].y), a2 = unpack2<T>(raw[u].z), a3 = unpack2<T>(raw[u].w);
+        acc[0] = fmaf(d[u], a0.x, acc[0]); acc[1] = fmaf(d[u], a0.y, acc[1]);
+        acc[2] = fmaf(d[u], a1.x, acc[2]); acc[3] = fmaf(d[u], a1.y, acc[3]);
+        acc[4] = fmaf(d[u], a2.x, acc[4]); acc[5] = fmaf(d[u], a2.y, acc[5]);
+        acc[6] = fmaf(d[u], a3.x, acc[6]); acc[7] = fmaf(d[u], a3.y, acc[7]);
+      } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(d[u], xv[u][k], acc[k]);
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(d[u], to_f32<T>(xp[u][k]), acc[k]);
       }
     }
   }
+  // sum the pixel lanes of each channel group: red[k][thread], then thread (cg, 0) adds up its `lanes` partners
 #pragma unroll
-  for (int k = 0; k < 8; ++k) atomicAdd(&dw[(size_t)g.taps[tp].wrow * g.Cin + cg * 8 + k], acc[k]);
+  for (int k = 0; k < 8; ++k) red[k * 256 + threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int o = threadIdx.x; o < C8 * 8; o += 256) {
+    const int c = o >> 3, k = o & 7;
+    float t = 0.f;
+    for (int L = 0; L < lanes; ++L) t += red[k * 256 + L * C8 + c];
+    atomicAdd(&dw[(size_t)g.taps[tp].wrow * g.Cin + c * 8 + k], t);
+  }
 }
 
 template <typename T>
@@ -273,7 +286,13 @@ static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, cud
   const int c8 = g.Cin / 8;
   if (g.Cout <= 16 && a.epilogue == NG_EPI_HEAD && g.Cin % 8 == 0 && c8 <= 256 && 256 % c8 == 0) {
     // single real output channel (the caller's dY holds zeros in the padding channels)
-    long long want = npix / 1024; if (want < 1) want = 1; if (want > 64) want = 64;
+    // short splits: ~8 blocks per SM over all taps, at least 4 trips of the 4-deep load batch per lane
+    const int lanes1 = 256 / c8;
+    long long want = (8ll * num_sms() + g.ntaps - 1) / g.ntaps;
+    const long long most = npix / (16ll * lanes1);
+    if (want > most) want = most;
+    if (want < 1) want = 1;
+    if (npix >= (1ll << 31)) { set_error("wgrad: %lld pixels exceed the 32-bit index range", npix); return NG_E_SHAPE; }
     const int pps1 = (int)((npix + want - 1) / want);
     dim3 grid(g.ntaps, (unsigned)((npix + pps1 - 1) / pps1));
     wgrad_cout1_kernel<T><<<grid, 256, 0, st>>>(g, (const T*)a.x, (const T*)a.y, dw, pps1);

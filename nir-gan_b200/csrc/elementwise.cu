@@ -77,6 +77,25 @@ __global__ void prep_input_kernel(const float* __restrict__ sa, int ca, const fl
     if (halo_mode == NG_HALO_REFLECT) { y1 = reflect_idx(y1, H1); x1 = reflect_idx(x1, W1); }
     else zero = y1 < 0 || y1 >= H1 || x1 < 0 || x1 >= W1;
     T* o = dst + p * cpad;
+    if constexpr (sizeof(T) == 2) if ((cpad & 7) == 0) {   // 16-bit paths: one 16-byte store per 8 channels
+      const int y0 = zero ? 0 : reflect_idx(y1 - wrap, H), x0 = zero ? 0 : reflect_idx(x1 - wrap, W);
+      for (int c0 = 0; c0 < cpad; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int c = c0 + k;
+          v[k] = 0.f;
+          if (!zero) {
+            if (c < ca) v[k] = sa[(((long long)n * ca + c) * H + y0) * W + x0];
+            else if (c < ca + cb) v[k] = sb[(((long long)n * cb + (c - ca)) * H + y0) * W + x0];
+          }
+        }
+        uint4 u;
+        u.x = pack2<T>(v[0], v[1]); u.y = pack2<T>(v[2], v[3]); u.z = pack2<T>(v[4], v[5]); u.w = pack2<T>(v[6], v[7]);
+        *reinterpret_cast<uint4*>(o + c0) = u;
+      }
+      continue;
+    }
     if (zero) {
       for (int c = 0; c < cpad; ++c) o[c] = from_f32<T>(0.f);
       continue;
@@ -91,10 +110,6 @@ __global__ void prep_input_kernel(const float* __restrict__ sa, int ca, const fl
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// InstanceNorm statistics
-// ---------------------------------------------------------------------------------------------
-// grid (B, C/32): block of 256 threads = 8 row-groups x 32 channels; two-pass (mean, then centred variance).
 template <typename T>
 __global__ void __launch_bounds__(256)
 in_stats_kernel(const T* __restrict__ y, int HW, int C, float* __restrict__ mr) {
