@@ -114,53 +114,19 @@ __device__ __forceinline__ void fold_halo_extras(const BwdArgs& a, const T* __re
   }
 }
 
-// Shared by both passes.  PASS 1: per-(n,c) sums of dxh and dxh*xh (+ injection gradients).  PASS 2: dy = rstd * (dxh -
+// Shared by all passes.  PHASE 1: per-(n,c) sums of dxh and dxh*xh (+ injection gradients).  PHASE 2: dy = rstd * (dxh -
 // mean(dxh) - xh * mean(dxh*xh)) and the optional export of do for the skip path.  Block (chunk, n) walks `ppb`
 // consecutive interior pixels of image n; thread t owns the channel group c8 = t mod C/8 (statistics in registers) and
 // batches UNROLL pixels of independent 16-byte streaming loads (gradient, skip gradient, forward pre-norm tensor).
 template <typename T, int PASS, int UNROLL, bool HAS_G, bool HAS_SKIP, bool HAS_INJ>
-__global__ void __launch_bounds__(256, 3)
-in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const T* __restrict__ gskip,
-              const T* __restrict__ yv, const float* __restrict__ mr, const float* __restrict__ inj,
-              const float* __restrict__ inj_scale, float* __restrict__ sums, float* __restrict__ dscale,
-              float* __restrict__ de_map, T* __restrict__ dy, T* __restrict__ do_out) {
-  extern __shared__ float sm[];            // PASS 1: [16 accumulators][256 threads]
-  const int n = blockIdx.y, C8 = a.C >> 3;
-  const int c8 = threadIdx.x & (C8 - 1);
-  const int pstep = 256 >> a.c8_shift;
-  const int npix = a.H * a.W;
-  const int p_begin = blockIdx.x * a.ppb, p_end = min(npix, p_begin + a.ppb);
-  const float s = (HAS_INJ && inj_scale) ? *inj_scale : 1.f;
-  float mean[8], rstd[8], m1[8], m2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { mean[k] = 0.f; rstd[k] = 1.f; m1[k] = 0.f; m2[k] = 0.f; }
-  if (mr) {
-    const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * a.C + c8 * 8) * 2);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float4 m = m4[k];
-      mean[2 * k] = m.x; rstd[2 * k] = m.y; mean[2 * k + 1] = m.z; rstd[2 * k + 1] = m.w;
-    }
-    if (PASS == 2) {
-      const float4* s4 = reinterpret_cast<const float4*>(sums + ((size_t)n * a.C + c8 * 8) * 2);   // combined sums
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 sv = s4[k];
-        m1[2 * k] = sv.x * a.inv_hw; m2[2 * k] = sv.y * a.inv_hw;
-        m1[2 * k + 1] = sv.z * a.inv_hw; m2[2 * k + 1] = sv.w * a.inv_hw;
-      }
-    }
-  }
+__device__ __forceinline__ void in_bwd_loop(const BwdArgs& a, const int n, const int c8, const int pstep, const int npix,
+                                            const int p_begin, const int p_end, const float s, const bool mr,
+                                            const float (&mean)[8], const float (&rstd)[8], const float (&m1)[8],
+                                            const float (&m2)[8], const T* __restrict__ gn, const T* __restrict__ sn,
+                                            const T* __restrict__ yn, const float* __restrict__ injn, const bool fold,
+                                            float (&acc1)[8], float (&acc2)[8], float& ds_acc,
+                                            float* __restrict__ de_map, T* __restrict__ dy, T* __restrict__ do_out) {
   const int gp = a.gp, Wb = a.W + 2 * gp;
-  const T* gn = HAS_G ? g + (size_t)n * (a.H + 2 * gp) * Wb * a.C + c8 * 8 : nullptr;
-  const T* sn = HAS_SKIP ? gskip + (size_t)n * npix * a.C + c8 * 8 : nullptr;
-  const T* yn = yv + (size_t)n * npix * a.C + c8 * 8;
-  const float* injn = HAS_INJ ? inj + (size_t)n * 128 * 128 : nullptr;
-  const bool fold = HAS_G && a.halo_mode == NG_HALO_REFLECT && gp > 0;
-  float acc1[8], acc2[8], ds_acc = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) acc1[k] = acc2[k] = 0.f;
-
   for (int p0 = p_begin + (threadIdx.x >> a.c8_shift); p0 < p_end; p0 += pstep * UNROLL) {
     Raw8<T> rg[HAS_G ? UNROLL : 1], rs[HAS_SKIP ? UNROLL : 1], ry[UNROLL];
     int py[UNROLL], px[UNROLL];
@@ -241,31 +207,134 @@ in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const 
       }
     }
   }
-  if constexpr (PASS == 1) {
-    // block reduction without atomics: every thread parks its 16 accumulators, then each output (channel, stat) is the
-    // sum over the 256/C8 threads that own that channel group, in a fixed order; one coalesced write of the block's
-    // [C][2] partial.
+}
+
+// PASS 1 / PASS 2: the two-launch form (pass 2 alone serves the units without a norm).  PASS 3: both phases in one launch
+// for normalised units -- after phase 1 the block publishes its partial sums and takes a ticket on the image's counter;
+// the last block of the image combines the partials (fixed order) and raises the image's flag, the others wait for it,
+// then every block runs phase 2 over the SAME pixels, which it has just read: those reads are served by the L2 instead
+// of HBM.  Blocks are dispatched image-major, so a waiting block only ever waits for blocks dispatched before or right
+// after it; the launcher keeps the blocks of one image (nblk1) well below the number of co-resident blocks.
+template <typename T, int PASS, int UNROLL, bool HAS_G, bool HAS_SKIP, bool HAS_INJ>
+__global__ void __launch_bounds__(256, UNROLL >= 4 ? 2 : 3)
+in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const T* __restrict__ gskip,
+              const T* __restrict__ yv, const float* __restrict__ mr, const float* __restrict__ inj,
+              const float* __restrict__ inj_scale, float* __restrict__ sums, float* __restrict__ dscale,
+              float* __restrict__ de_map, T* __restrict__ dy, T* __restrict__ do_out) {
+  extern __shared__ float sm[];            // PASS 1 / 3: [4 accumulators][256 threads]
+  const int n = blockIdx.y, C8 = a.C >> 3;
+  const int c8 = threadIdx.x & (C8 - 1);
+  const int pstep = 256 >> a.c8_shift;
+  const int npix = a.H * a.W;
+  const int p_begin = blockIdx.x * a.ppb, p_end = min(npix, p_begin + a.ppb);
+  const float s = (HAS_INJ && inj_scale) ? *inj_scale : 1.f;
+  float mean[8], rstd[8], m1[8], m2[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      sm[(2 * k) * 256 + threadIdx.x] = acc1[k];
-      sm[(2 * k + 1) * 256 + threadIdx.x] = acc2[k];
+  for (int k = 0; k < 8; ++k) { mean[k] = 0.f; rstd[k] = 1.f; m1[k] = 0.f; m2[k] = 0.f; }
+  if (mr) {
+    const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * a.C + c8 * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 m = m4[k];
+      mean[2 * k] = m.x; rstd[2 * k] = m.y; mean[2 * k + 1] = m.z; rstd[2 * k + 1] = m.w;
     }
+    if (PASS == 2) {
+      const float4* s4 = reinterpret_cast<const float4*>(sums + ((size_t)n * a.C + c8 * 8) * 2);   // combined sums
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 sv = s4[k];
+        m1[2 * k] = sv.x * a.inv_hw; m2[2 * k] = sv.y * a.inv_hw;
+        m1[2 * k + 1] = sv.z * a.inv_hw; m2[2 * k + 1] = sv.w * a.inv_hw;
+      }
+    }
+  }
+  const int gp = a.gp, Wb = a.W + 2 * gp;
+  const T* gn = HAS_G ? g + (size_t)n * (a.H + 2 * gp) * Wb * a.C + c8 * 8 : nullptr;
+  const T* sn = HAS_SKIP ? gskip + (size_t)n * npix * a.C + c8 * 8 : nullptr;
+  const T* yn = yv + (size_t)n * npix * a.C + c8 * 8;
+  const float* injn = HAS_INJ ? inj + (size_t)n * 128 * 128 : nullptr;
+  const bool fold = HAS_G && a.halo_mode == NG_HALO_REFLECT && gp > 0;
+  float acc1[8], acc2[8], ds_acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc1[k] = acc2[k] = 0.f;
+
+  in_bwd_loop<T, (PASS == 2 ? 2 : 1), UNROLL, HAS_G, HAS_SKIP, HAS_INJ>(a, n, c8, pstep, npix, p_begin, p_end, s,
+                                                                        mr != nullptr, mean, rstd, m1, m2, gn, sn, yn,
+                                                                        injn, fold, acc1, acc2, ds_acc, de_map, dy, do_out);
+  if constexpr (PASS != 2) {
+    // block reduction without atomics, four accumulators at a time (4 KB of shared memory, so that these blocks fit
+    // beside a resident tcgen05 CTA of the weight-gradient stream): every thread parks accumulators 4r..4r+3, then each
+    // output (channel, stat) is the sum over the 256/C8 threads that own that channel group, in a fixed order.
     if (HAS_INJ && dscale) {
       ds_acc = warp_sum(ds_acc);
       if ((threadIdx.x & 31) == 0 && ds_acc != 0.f) atomicAdd(dscale, ds_acc);
     }
-    __syncthreads();
-    if (sums) {
-      // partial slots live behind the [B][C][2] combined sums
-      float* dst = sums + (size_t)a.B * a.C * 2 + ((size_t)n * a.nblk1 + blockIdx.x) * a.C * 2;
-      const int lanes = 256 >> a.c8_shift;
-      for (int o = threadIdx.x; o < a.C * 2; o += 256) {
-        const int cg = o >> 4, v = o & 15;
+    // partial slots live behind the [B][C][2] combined sums
+    float* dst = sums ? sums + (size_t)a.B * a.C * 2 + ((size_t)n * a.nblk1 + blockIdx.x) * a.C * 2 : nullptr;
+    const int lanes = 256 >> a.c8_shift;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      sm[0 * 256 + threadIdx.x] = acc1[2 * r];
+      sm[1 * 256 + threadIdx.x] = acc2[2 * r];
+      sm[2 * 256 + threadIdx.x] = acc1[2 * r + 1];
+      sm[3 * 256 + threadIdx.x] = acc2[2 * r + 1];
+      __syncthreads();
+      if (dst && (int)threadIdx.x < (a.C >> 1)) {
+        const int cg = threadIdx.x >> 2, j = threadIdx.x & 3;
         float t = 0.f;
-        for (int L = 0; L < lanes; ++L) t += sm[v * 256 + (L << a.c8_shift) + cg];
-        dst[o] = t;
+        for (int L = 0; L < lanes; ++L) t += sm[j * 256 + (L << a.c8_shift) + cg];
+        dst[cg * 16 + 4 * r + j] = t;
+      }
+      __syncthreads();
+    }
+  }
+  if constexpr (PASS == 3) {
+    __shared__ int last_flag;
+    int* counter = reinterpret_cast<int*>(sums + (size_t)a.B * a.C * 2 * (1 + a.nblk1));      // [B] tickets, [B] flags
+    int* flag = counter + a.B;
+    float* combined = sums + (size_t)n * a.C * 2;
+    __threadfence();                        // the block's partial slot is visible device-wide
+    __syncthreads();
+    if (threadIdx.x == 0) last_flag = (atomicAdd(&counter[n], 1) == a.nblk1 - 1);
+    __syncthreads();
+    if (last_flag) {
+      __threadfence();
+      const float* part = sums + (size_t)a.B * a.C * 2 + (size_t)n * a.nblk1 * a.C * 2;
+      const int C2 = a.C * 2;
+      for (int o = threadIdx.x; o < C2; o += 256) {
+        float t = 0.f;
+        int k = 0;
+        for (; k + 8 <= a.nblk1; k += 8) {          // eight independent L2 loads in flight, summed in slot order
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __ldcg(part + (size_t)(k + j) * C2 + o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t += v[j];
+        }
+        for (; k < a.nblk1; ++k) t += __ldcg(part + (size_t)k * C2 + o);
+        combined[o] = t;
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicExch(&flag[n], 1);
+    } else {
+      if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile int*>(&flag[n]) == 0) __nanosleep(100);
+        __threadfence();
+      }
+      __syncthreads();
+    }
+    {
+      const float4* s4 = reinterpret_cast<const float4*>(combined + c8 * 16);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 sv = __ldcg(s4 + k);
+        m1[2 * k] = sv.x * a.inv_hw; m2[2 * k] = sv.y * a.inv_hw;
+        m1[2 * k + 1] = sv.z * a.inv_hw; m2[2 * k + 1] = sv.w * a.inv_hw;
       }
     }
+    in_bwd_loop<T, 2, UNROLL, HAS_G, HAS_SKIP, HAS_INJ>(a, n, c8, pstep, npix, p_begin, p_end, s, true, mean, rstd, m1, m2,
+                                                        gn, sn, yn, injn, fold, acc1, acc2, ds_acc, de_map, dy, do_out);
   }
 }
 
@@ -449,9 +518,20 @@ static void launch_in_bwd(const BwdArgs& a, dim3 grid, size_t smem, cudaStream_t
                           const void* y, const float* mr, const float* inj, const float* inj_scale, float* sums,
                           float* dscale, float* de_map, void* dy, void* do_out) {
   const bool hg = g != nullptr, hs = gskip != nullptr, hi = a.inj_mode != NG_INJECT_NONE;
+  // four pixels of loads in flight per thread at 2 blocks / SM (<= 128 registers) beat two at 3 blocks / SM: the kernel is
+  // bound by the bytes in flight, not by occupancy (4.5 -> 4.15 ms per training step); NIRGAN_B200_BWD_UNROLL4=0 restores
+  static const bool deep = [] { const char* e = getenv("NIRGAN_B200_BWD_UNROLL4"); return !(e && e[0] == '0'); }();
 #define NG_BWD(G, S, I)                                                                                              \
-  in_bwd_kernel<T, PASS, 2, G, S, I><<<grid, 256, smem, st>>>(a, (const T*)g, (const T*)gskip, (const T*)y, mr, inj, \
-                                                              inj_scale, sums, dscale, de_map, (T*)dy, (T*)do_out)
+  do {                                                                                                               \
+    if (deep && !(I))                                                                                                \
+      in_bwd_kernel<T, PASS, 4, G, S, I><<<grid, 256, smem, st>>>(a, (const T*)g, (const T*)gskip, (const T*)y, mr,  \
+                                                                  inj, inj_scale, sums, dscale, de_map, (T*)dy,      \
+                                                                  (T*)do_out);                                       \
+    else                                                                                                             \
+      in_bwd_kernel<T, PASS, 2, G, S, I><<<grid, 256, smem, st>>>(a, (const T*)g, (const T*)gskip, (const T*)y, mr,  \
+                                                                  inj, inj_scale, sums, dscale, de_map, (T*)dy,      \
+                                                                  (T*)do_out);                                       \
+  } while (0)
   if (hi) {                       // the injected unit (d1) receives its gradient from one haloed buffer
     if (hg && hs) NG_BWD(true, true, true); else if (hg) NG_BWD(true, false, true); else NG_BWD(false, true, true);
   } else {
@@ -479,9 +559,25 @@ static int in_bwd_pick_mult(int B, int npix, int pstep, int lo, int hi) {
   return best;
 }
 
-// pass-1 blocks per image: long blocks (fewer partial slots to combine) as long as the grid fills whole waves
+static bool in_bwd_fused() {
+  static const bool on = [] { const char* e = getenv("NIRGAN_B200_BWD_FUSED"); return e && e[0] == '1'; }();   // measured slower (blocks idle at the hand-over): off
+  return on;
+}
+
+// pass-1 blocks per image.  Two-launch form: long blocks (fewer partial slots to combine) as long as the grid fills
+// whole waves.  One-launch form (PASS 3): ~45 KB per tensor per block so that what the co-resident blocks read in phase 1
+// (3 blocks x 148 SMs x 2-3 tensors) is still in the L2 for phase 2, but never more blocks per image than half the
+// co-resident capacity (the blocks of an image wait for each other).
 static int in_bwd_pass1_blocks(int B, int H, int W, int C) {
   const int pstep = 256 / (C / 8);
+  if (in_bwd_fused()) {
+    int mult = in_bwd_pick_mult(B, H * W, pstep, 8, 16);
+    if (mult < 0) mult = 11;
+    const int cap = 3 * num_sms() / 2;
+    const int least = (H * W + pstep * cap - 1) / (pstep * cap);
+    if (mult < least) mult = least;
+    return (H * W + pstep * mult - 1) / (pstep * mult);
+  }
   int mult = in_bwd_pick_mult(B, H * W, pstep, 4, 64);
   if (mult < 0) {
     mult = 64;
@@ -492,7 +588,8 @@ static int in_bwd_pass1_blocks(int B, int H, int W, int C) {
 
 extern "C" int64_t ng_in_bwd_scratch_floats(int32_t B, int32_t H, int32_t W, int32_t C) {
   if (B <= 0 || H <= 0 || W <= 0 || C < 8 || C % 8) return NG_E_ARG;
-  return (int64_t)B * (1 + in_bwd_pass1_blocks(B, H, W, C)) * C * 2;     // combined sums + per-block partials
+  // combined sums + per-block partials + per-image ticket counter and flag (one-launch form)
+  return (int64_t)B * (1 + in_bwd_pass1_blocks(B, H, W, C)) * C * 2 + 2 * (int64_t)B;
 }
 
 extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y,
@@ -516,6 +613,23 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
   const int pstep = 256 / (C / 8);
   const bool need_pass1 = mean_rstd != nullptr || (inject_mode != NG_INJECT_NONE && (dscale || de_map));
   a.nblk1 = in_bwd_pass1_blocks(B, H, W, C);
+  if (mean_rstd && in_bwd_fused()) {
+    // one launch: phase 1, per-image hand-over, phase 2 over the same (L2-resident) pixels
+    if (de_map) {
+      int e = check_cuda(cudaMemsetAsync(de_map, 0, (size_t)B * H * W * sizeof(float), st), "in_bwd memset de");
+      if (e) return e;
+    }
+    float* tickets = sums_scratch + (size_t)B * C * 2 * (1 + a.nblk1);
+    int e = check_cuda(cudaMemsetAsync(tickets, 0, 2 * (size_t)B * sizeof(int), st), "in_bwd memset tickets");
+    if (e) return e;
+    a.ppb = (H * W + a.nblk1 - 1) / a.nblk1;
+    a.ppb = (a.ppb + pstep - 1) / pstep * pstep;
+    dim3 grid((unsigned)a.nblk1, (unsigned)B);
+    DISPATCH_T(dtype, (launch_in_bwd<T, 3>(a, grid, (size_t)4 * 256 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
+                                           inject_e, inject_scale, sums_scratch, dscale, de_map, dy, do_out)));
+    NG_LAUNCH_CHECK("in_bwd_kernel<fused>");
+    return NG_OK;
+  }
   if (need_pass1) {
     NG_REQUIRE(mean_rstd == nullptr || sums_scratch != nullptr, NG_E_ARG, "in_bwd: scratch required");
     if (de_map) {
@@ -525,7 +639,7 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
     a.ppb = (H * W + a.nblk1 - 1) / a.nblk1;
     a.ppb = (a.ppb + pstep - 1) / pstep * pstep;
     dim3 grid((unsigned)a.nblk1, (unsigned)B);
-    DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)16 * 256 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
+    DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)4 * 256 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
                                            inject_e, inject_scale, mean_rstd ? sums_scratch : nullptr, dscale, de_map,
                                            nullptr, nullptr)));
     NG_LAUNCH_CHECK("in_bwd_kernel<pass 1>");
