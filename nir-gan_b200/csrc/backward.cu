@@ -388,14 +388,16 @@ tap_scatter_kernel(const float* __restrict__ dout, const float* __restrict__ out
   constexpr int G8 = ZC / 8;
   const int Hc = Hz - KH + 1 - 2 * crop, Wc = Wz - KW + 1 - 2 * crop;
   if (dev_scale) scale *= dev_scale[0];
-  const long long total = (long long)B * Hz * Wz * G8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const unsigned total = (unsigned)B * Hz * Wz * G8;          // < 2^31 (checked by the launcher): 32-bit index arithmetic
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int g8 = (int)(i % G8);
-    long long p = i / G8;
-    const int xx = (int)(p % Wz); p /= Wz;
-    const int yy = (int)(p % Hz);
-    const int n = (int)(p / Hz);
+    unsigned p = i / G8;
+    const unsigned row = p / (unsigned)Wz;
+    const int xx = (int)(p - row * Wz);
+    const int n = (int)(row / (unsigned)Hz);
+    const int yy = (int)(row - (unsigned)n * Hz);
+    const float* dn = dout + (size_t)n * Hc * Wc;
+    const float* on = out + (size_t)n * Hc * Wc;
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -405,15 +407,15 @@ tap_scatter_kernel(const float* __restrict__ dout, const float* __restrict__ out
         const int kh = t / KW, kw = t - kh * KW;
         const int yc = yy - kh - crop, xc = xx - kw - crop;
         if (yc >= 0 && yc < Hc && xc >= 0 && xc < Wc) {
-          const size_t o = ((size_t)n * Hc + yc) * Wc + xc;
-          v = dout[o] * scale;
-          if (act == NG_ACT_TANH) { const float tv = out[o]; v *= (1.f - tv * tv); }
+          const int o = yc * Wc + xc;
+          v = __ldg(dn + o) * scale;
+          if (act == NG_ACT_TANH) { const float tv = __ldg(on + o); v *= (1.f - tv * tv); }
           if constexpr (sizeof(T) == 2) v = fminf(fmaxf(v, -3.0e4f), 3.0e4f);
         }
       }
       f[k] = v;
     }
-    st8<T>(dz + i * 8, f);
+    st8<T>(dz + (size_t)i * 8, f);
   }
 }
 
@@ -545,7 +547,7 @@ static void launch_in_bwd(const BwdArgs& a, dim3 grid, size_t smem, cudaStream_t
 // partly filled wave of an HBM-bound kernel runs at a fraction of the bandwidth), longer blocks on ties.
 static int in_bwd_pick_mult(int B, int npix, int pstep, int lo, int hi) {
   static const bool tune = [] { const char* e = getenv("NIRGAN_B200_BWD_TUNE"); return !(e && e[0] == '0'); }();
-  const double resident = 3.0 * num_sms();
+  const double resident = 2.0 * num_sms();             // 2 blocks / SM of the four-pixel kernels
   int best = lo;
   double best_eff = -1.0;
   for (int mult = hi; mult >= lo; --mult) {
@@ -692,6 +694,7 @@ extern "C" int ng_tap_scatter(const float* dout, const float* out, int32_t B, in
   NG_REQUIRE(dout && dz && (act != NG_ACT_TANH || out), NG_E_ARG, "tap_scatter: null tensor");
   NG_REQUIRE(KH == 7 && KW == 7 && zc == 64, NG_E_UNSUPPORTED, "tap_scatter: built for 7x7 taps over 64 stored channels");
   NG_REQUIRE(Hz - KH + 1 - 2 * crop > 0 && Wz - KW + 1 - 2 * crop > 0, NG_E_SHAPE, "tap_scatter: empty output");
+  NG_REQUIRE((long long)B * Hz * Wz * 8 < (1ll << 31), NG_E_SHAPE, "tap_scatter: batch too large for 32-bit indexing");
   DISPATCH_T(dtype, (tap_scatter_kernel<T, 7, 7, 64><<<grid_cap((long long)B * Hz * Wz * 8), 256, 0, (cudaStream_t)stream>>>(
                         dout, out, B, Hz, Wz, act, crop, scale, dev_scale, (T*)dz)));
   NG_LAUNCH_CHECK("tap_scatter_kernel");

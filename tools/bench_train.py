@@ -5,6 +5,7 @@ Prints one JSON line: samples/s, ms per step, algorithmic TFLOP/s (391.6 GFLOP p
 import argparse
 import contextlib
 import json
+import time
 import os
 import sys
 
@@ -56,8 +57,10 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         ld, lg = step()
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps      # time to ENQUEUE a step (no device sync inside)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
@@ -96,7 +99,7 @@ def main():
     print(json.dumps({"workload": f"configs[3]: Pix2Pix training step, batch {args.batch}, {args.tile}px, {args.precision}/{args.conv}",
                       "ms_per_step": ms, "samples_per_s": args.batch / ms * 1e3,
                       "algorithmic_tflops": args.batch * gflop / ms, "gflop_per_sample": gflop,
-                      "g_forward_reused": model.reuse_g_forward,
+                      "g_forward_reused": model.reuse_g_forward, "host_enqueue_ms_per_step": round(host_ms, 2),
                       "loss_D": float(ld), "loss_G": float(lg),
                       "mem_gb": torch.cuda.max_memory_allocated() / 1e9,
                       "skipped_steps": [opt_d.skipped_steps, opt_g.skipped_steps],
