@@ -67,6 +67,12 @@ struct TcCfg {
   // bound, so two groups nearly halve the drain time of a tile)
   static constexpr int EG = BN >= 64 ? EGW : 1;
   static constexpr int EB = 32;
+  // more groups than a tile has passes (BN = 64: two passes, four groups): the groups split into TG sets that take
+  // alternate tiles, i.e. one accumulator buffer each, so two tiles are drained at the same time
+  static constexpr int PASSES = BN >= 64 ? BN / EB : 1;
+  static constexpr int TG = EG > PASSES ? EG / PASSES : 1;
+  static constexpr int EGT = EG / TG;                         // groups that share one tile
+  static_assert(TG == 1 || TG == 2, "tile-alternating epilogue sets map onto the two accumulator buffers");
   static constexpr int THREADS = 64 + 128 * EG;
   static constexpr int STAGING_BYTES = BN >= 64 ? EG * 128 * EB * 2 : 0;
   static constexpr int RED_BYTES = BN >= 64 ? EG * 2048 : 0;         // cross-row-group stats combine
@@ -114,7 +120,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), CS); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128 * Cfg::EG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128 * Cfg::EGT); }
     mbar_init(smem_u32(wfull_bar), 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -256,7 +262,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int et = we * 32 + lane;          // 0..127 thread index within the group
     const int row_i = row / p.BW, row_j = row - row_i * p.BW;     // this row's pixel inside the patch (tile-invariant)
     uint32_t as = 0, as_phase = 0;
-    for (int q = cluster_id; q < p.total_groups; q += num_clusters) {
+    const int tsel = grp / Cfg::EGT, gt = grp % Cfg::EGT;       // tile set of this group, group index within the tile
+    int it = 0;
+    for (int q = cluster_id; q < p.total_groups; q += num_clusters, ++it) {
+      if (Cfg::TG > 1 && (it % Cfg::TG) != tsel) {              // the other set drains this tile (other accumulator)
+        if (++as == 2) { as = 0; as_phase ^= 1; }
+        continue;
+      }
       int cot, ph, n, py, px; bool dummy;
       decode(q, cot, ph, n, py, px, dummy);
       const int vi = py * p.BH + row_i, vj = px * p.BW + row_j;
@@ -307,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // element offset of this row's output pixel (merged phases: of its 2x2 output block's top-left pixel)
         sts64(rowoffg + row * 8, valid ? (((long long)n * g.Hout + oy) * g.Wout + ox) * (long long)g.Cout_real : -1ll);
 #pragma unroll 1
-        for (int ps = grp; ps < PASSES; ps += EG) {
+        for (int ps = gt; ps < PASSES; ps += Cfg::EGT) {
           // where this pass's 32 channels go: plain = channel n0 + ps*EB of the row's pixel; merged phases = channel co0
           // of the pixel (2i + pa, 2j + pb) with phase = virtual channel / Cout_real
           int c_first = n0 + ps * EB, phase_id = ph;
@@ -321,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t r[32];
             tmem_ld32(taddr + ps * EB, r);
             tmem_ld_wait();
-            if (ps + EG >= PASSES) {
+            if (ps + Cfg::EGT >= PASSES) {
               tc_fence_before();
               mbar_arrive(smem_u32(&tempty_bar[as]));     // this thread's last read of the accumulator
             }
@@ -527,7 +539,7 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   p.stat_slots = (g.merged ? 4 : g.nphase) * p.patches_y * p.patches_x;
   p.bias = a.bias; p.y = a.y; p.stat_partials = a.stat_partials;
   p.mean_rstd = a.mean_rstd; p.tile_counters = a.tile_counters;
-  p.arrivals_per_image = p.patches_y * p.patches_x * g.nphase * p.co_tiles * Cfg::EG;
+  p.arrivals_per_image = p.patches_y * p.patches_x * g.nphase * p.co_tiles * Cfg::EGT;
   p.inv_count = 1.0f / ((float)g.Hout * (float)g.Wout);
 
   CUtensorMap tmA, tmB;
@@ -630,8 +642,12 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   if (bn == 64 && kc == 16) return launch_tc<64, 16, 1>(a, g, st);
   if (bn == 128 && kc == 16) return launch_tc<128, 16, 1>(a, g, st);
   if (bn == 256 && kc == 16) return launch_tc<256, 16, 1>(a, g, st);
-  if (bn == 64 && kc == 64 && row_tap_ok(a, g)) return launch_tc<64, 64, 1, true>(a, g, st);
-  if (bn == 64 && kc == 64) return launch_tc<64, 64, 1>(a, g, st);
+  static int wide_env = -1;
+  if (wide_env < 0) { const char* v = getenv("NIRGAN_B200_EPI4"); wide_env = v ? atoi(v) : 2; }
+  // 64-wide tiles have two drain passes; with four epilogue groups two tiles (both accumulator buffers) drain at once
+  if (bn == 64 && kc == 64 && row_tap_ok(a, g))
+    return wide_env >= 2 ? launch_tc<64, 64, 1, true, 4>(a, g, st) : launch_tc<64, 64, 1, true>(a, g, st);
+  if (bn == 64 && kc == 64) return wide_env >= 2 ? launch_tc<64, 64, 1, false, 4>(a, g, st) : launch_tc<64, 64, 1>(a, g, st);
   // very short K loops on 256-wide tiles (the merged-phase up-convolution to full resolution: 8 operand stages per
   // tile against 8 drain passes) are bound by the epilogue drain: four epilogue groups.  Measured on B200: 0.222 ->
   // 0.179 ms for that layer; for 9..18 K iterations (down convs, first up-conv) the fourth operand stage that EG = 4
@@ -641,10 +657,8 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
     const int it = (g.phase_tap0[ph + 1] - g.phase_tap0[ph]) * (a.Cin / 64);
     if (it > max_kiters) max_kiters = it;
   }
-  static int wide_env = -1;
-  if (wide_env < 0) { const char* v = getenv("NIRGAN_B200_EPI4"); wide_env = v ? atoi(v) : 1; }
   const bool wide = wide_env && kc == 64 && max_kiters <= 8;
-  if (bn == 128 && kc == 64) return launch_tc<128, 64, 1>(a, g, st);
+  if (bn == 128 && kc == 64) return wide_env >= 3 ? launch_tc<128, 64, 1, false, 4>(a, g, st) : launch_tc<128, 64, 1>(a, g, st);
   if (bn == 256 && kc == 64 && wide) return launch_tc<256, 64, 1, false, 4>(a, g, st);
   if (bn == 256 && kc == 64) {
     const int cs = cluster_size_for(bn, kc);
