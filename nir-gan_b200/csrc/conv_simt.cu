@@ -271,6 +271,45 @@ __global__ void colsum_kernel(const T* __restrict__ dy, long long rows, int C, f
   }
 }
 
+// Column sums of a [rows][C] 16-bit matrix, C a multiple of 8 with C/8 dividing 256 (bias gradients of the wide layers:
+// up to 2.5 M rows).  Thread t owns the 8-channel group t mod C/8 (one 16-byte load per row) and the row lane t / (C/8);
+// four rows in flight per thread, lanes summed through shared memory, one atomic per channel and block.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ dy, long long rows, int C, float* __restrict__ out) {
+  __shared__ float red[8 * 256];
+  const int C8 = C >> 3, lanes = 256 / C8;
+  const int cg = threadIdx.x % C8, pl = threadIdx.x / C8;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const long long stride = (long long)gridDim.x * lanes;
+  constexpr int U = 4;
+  for (long long r0 = (long long)blockIdx.x * lanes + pl; r0 < rows; r0 += stride * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * stride;
+      v[u] = r < rows ? __ldg(reinterpret_cast<const uint4*>(dy + r * C + cg * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float2 a0 = unpack2<T>(v[u].x), a1 = unpack2<T>(v[u].y), a2 = unpack2<T>(v[u].z), a3 = unpack2<T>(v[u].w);
+      acc[0] += a0.x; acc[1] += a0.y; acc[2] += a1.x; acc[3] += a1.y;
+      acc[4] += a2.x; acc[5] += a2.y; acc[6] += a3.x; acc[7] += a3.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[k * 256 + threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int o = threadIdx.x; o < C; o += 256) {
+    const int c = o >> 3, k = o & 7;
+    float t = 0.f;
+    for (int L = 0; L < lanes; ++L) t += red[k * 256 + L * C8 + c];
+    atomicAdd(&out[o], t);
+  }
+}
+
 template <typename T>
 static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, cudaStream_t st) {
   const int n_tiles = (g.Cout + 63) / 64, k_tiles = (g.Cin + 63) / 64;
@@ -311,6 +350,17 @@ static int launch_bias_grad(const ng_conv_args& a, const ConvGeom& g, float* dbi
   int e = check_cuda(cudaMemsetAsync(dbias, 0, (size_t)g.Cout * sizeof(float), st), "dbias memset");
   if (e) return e;
   const long long rows = (long long)g.B * g.Hout * g.Wout;
+  if constexpr (sizeof(T) == 2) {
+    const int c8 = g.Cout / 8;
+    if (g.Cout % 8 == 0 && c8 >= 1 && c8 <= 256 && 256 % c8 == 0 && rows >= 4096) {
+      const int lanes = 256 / c8;
+      long long blocks = (rows + 4ll * lanes - 1) / (4ll * lanes);
+      if (blocks > 8ll * num_sms()) blocks = 8ll * num_sms();
+      colsum_vec_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)a.y, rows, g.Cout, dbias);
+      NG_LAUNCH_CHECK("colsum_vec_kernel");
+      return NG_OK;
+    }
+  }
   const unsigned cs_blocks = (unsigned)(rows < 1024 ? rows : 1024);
   const unsigned cs_threads = (unsigned)(g.Cout < 256 ? g.Cout : 256);
   colsum_kernel<T><<<cs_blocks, cs_threads, 0, st>>>((const T*)a.y, rows, g.Cout, dbias);
