@@ -252,6 +252,40 @@ wgrad_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, f
   }
 }
 
+// Same sum for small outputs with many splits (thin layers: 1 k float4 outputs x 134 splits): a thread per output would
+// walk the splits as one chain of dependent-latency loads, so eight threads share an output -- thread (o, ks) adds splits
+// ks, ks + 8, ... four loads at a time, and the eight slices are then added in slice order (fixed order -> deterministic).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_sliced_kernel(const float4* __restrict__ part, int splits, long long n4, float4* __restrict__ dw) {
+  __shared__ float4 red[8][32];
+  const int o = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + o;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    int k = ks;
+    for (; k + 24 < splits; k += 32) {
+      const float4 a = part[(size_t)k * n4 + i], b = part[(size_t)(k + 8) * n4 + i], c = part[(size_t)(k + 16) * n4 + i],
+                   d = part[(size_t)(k + 24) * n4 + i];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+      s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+      s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+    }
+    for (; k < splits; k += 8) {
+      const float4 a = part[(size_t)k * n4 + i];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
+  }
+  red[ks][o] = s;
+  __syncthreads();
+  if (ks == 0 && i < n4) {
+    float4 t = red[0][o];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { const float4 v = red[j][o]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    dw[i] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -369,6 +403,12 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
     const long long n4 = (long long)g.ntaps * g.Cout * g.Cin / 4;
     long long blocks = (n4 + 255) / 256;
     if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    if (w.splits >= 16 && n4 < (long long)sms * 256 * 2) {
+      wgrad_reduce_sliced_kernel<<<(unsigned)((n4 + 31) / 32), 256, 0, st>>>(reinterpret_cast<const float4*>(workspace),
+                                                                           w.splits, n4, reinterpret_cast<float4*>(dw));
+      NG_LAUNCH_CHECK("wgrad_reduce_sliced_kernel");
+      return NG_OK;
+    }
     wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(workspace), w.splits, n4,
                                                          reinterpret_cast<float4*>(dw));
     NG_LAUNCH_CHECK("wgrad_reduce_kernel");
