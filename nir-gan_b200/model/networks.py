@@ -135,6 +135,13 @@ class _B200Module(nn.Module):
         B, _, H, W = c["geom"]
         return c["fwd"].records["out"].view(B, 1, H, W).clone()
 
+    @torch.no_grad()
+    def forward_async(self, input, embeds=None, wrap_pad: int = 0, ready=None):
+        """Streaming inference (no autograd): ``(out, done_events)`` without making the caller's stream wait, so that
+        consecutive calls overlap; see ``GeneratorRunner.forward_async``.  Wait on every event before reading ``out``."""
+        require_cuda(input, "generator input")
+        return self._get_runner(GeneratorRunner).forward_async(input, embeds, wrap_pad, ready)
+
     def _get_runner(self, factory):
         if getattr(self, "_runner", None) is None:
             object.__setattr__(self, "_runner", factory(self, self.b200_config))

@@ -146,6 +146,22 @@ class GeneratorRunner(_RunnerBase):
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, embeds: Optional[torch.Tensor] = None, wrap_pad: int = 0) -> torch.Tensor:
+        """Synchronous-in-stream-order call: the result is valid on the caller's current stream."""
+        out, done = self.forward_async(x, embeds, wrap_pad)
+        main = torch.cuda.current_stream(x.device)
+        for ev in done:
+            main.wait_event(ev)
+        return out
+
+    @torch.no_grad()
+    def forward_async(self, x: torch.Tensor, embeds: Optional[torch.Tensor] = None, wrap_pad: int = 0,
+                      ready: Optional["torch.cuda.Event"] = None):
+        """Streaming form of ``forward``: returns ``(out, done_events)`` without making the caller's stream wait.  The
+        batch is cut into slices that run on the runner's own streams; slice s of this call queues behind slice s of the
+        previous call only, so consecutive calls overlap (the tail of one step runs beside the head of the next) instead
+        of meeting at a barrier on the caller's stream.  ``ready`` = event after which ``x`` / ``embeds`` may be read
+        (default: the caller's stream at call time).  A consumer waits on every event of ``done_events`` (a stream:
+        ``stream.wait_event(e)``) before touching ``out``."""
         require_cuda(x, "generator input")
         if x.dim() != 4:
             raise RuntimeError("generator input must be (B, C, H, W)")
@@ -153,27 +169,41 @@ class GeneratorRunner(_RunnerBase):
         Btot, Cin, H, W = x.shape
         inject = embeds is not None
         chunk = eng.cfg.chunk if eng.cfg.chunk > 0 else Btot
-        out = torch.empty(Btot, 1, H, W, dtype=torch.float32, device=x.device)
         main = torch.cuda.current_stream(x.device)
-        x = x.contiguous().float()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.contiguous().float()
         if inject:
             require_cuda(embeds, "embeds")
-            embeds = embeds.contiguous().float()
+            if embeds.dtype != torch.float32 or not embeds.is_contiguous():
+                embeds = embeds.contiguous().float()
+        out = torch.empty(Btot, 1, H, W, dtype=torch.float32, device=x.device)
         want = eng.cfg.streams if eng.cfg.streams > 0 else (2 if Btot >= 32 else 1)
         nstreams = max(1, min(want, (Btot + chunk - 1) // chunk if eng.cfg.chunk > 0 else want, Btot))
         if eng.cfg.chunk <= 0 and nstreams > 1:
             chunk = (Btot + nstreams - 1) // nstreams
-        if nstreams > 1 and len(self._side_streams) < nstreams - 1:
-            self._side_streams += [torch.cuda.Stream(x.device) for _ in range(nstreams - 1 - len(self._side_streams))]
-        streams = [main] + self._side_streams[:nstreams - 1]
+        if len(self._side_streams) < nstreams:
+            self._side_streams += [torch.cuda.Stream(x.device) for _ in range(nstreams - len(self._side_streams))]
+        streams = self._side_streams[:nstreams]
         # build / refresh every plan on the caller's stream first (weight packing), then fork
         jobs = []
         for i, b0 in enumerate(range(0, Btot, chunk)):
             B = min(chunk, Btot - b0)
             slot = i % nstreams
             jobs.append((b0, B, slot, self._inference_plan(eng, B, Cin, H, W, wrap_pad, inject, main.cuda_stream, slot)))
-        for st in streams[1:]:
-            st.wait_stream(main)
+        if ready is None:
+            ready = torch.cuda.Event()
+            ready.record(main)            # inputs (and refreshed weights) are ready once the caller's stream gets here
+        else:
+            wev = torch.cuda.Event()      # weight packing, if any, was issued on the caller's stream
+            wev.record(main)
+            for st in streams:
+                st.wait_event(wev)
+        for st in streams:
+            st.wait_event(ready)
+            x.record_stream(st)
+            out.record_stream(st)
+            if inject:
+                embeds.record_stream(st)
         for b0, B, slot, plan in jobs:
             st = streams[slot]
             with torch.cuda.stream(st):
@@ -185,10 +215,13 @@ class GeneratorRunner(_RunnerBase):
                 if getattr(self.module, "post_correction", False):
                     o = o * self.module.post_correction_param
                 out[b0:b0 + B].copy_(o)
-        for st in streams[1:]:
-            main.wait_stream(st)
+        done = []
+        for st in streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            done.append(ev)
         self.last_plan = plan
-        return out
+        return out, done
 
     # ---- training -------------------------------------------------------------------------------------
     def weight_signature(self):
