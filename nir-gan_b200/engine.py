@@ -90,6 +90,24 @@ class Buffers:
         return sum(t.numel() * t.element_size() for t in self._b.values())
 
 
+class SliceBuffers:
+    """View of a parent ``Buffers`` for one of ``parts`` equal batch slices: every request must name a buffer the parent
+    already holds at ``parts`` times the size (a [B][...] buffer of the full-batch graph) and gets its slice.  Used to
+    compile half-batch forward plans that write the full-batch graph's activations in place."""
+
+    def __init__(self, parent: Buffers, part: int, parts: int):
+        self.parent, self.part, self.parts, self.device = parent, part, parts, parent.device
+
+    def get(self, name: str, numel: int, dtype: torch.dtype, zero: bool = False) -> torch.Tensor:
+        full = self.parent._b.get((name, numel * self.parts, dtype))
+        if full is None:
+            raise KeyError(f"buffer {name!r} ({numel} x {self.parts}) is not a per-image buffer of the full-batch graph")
+        return full[self.part * numel:(self.part + 1) * numel]
+
+    def bytes(self) -> int:
+        return 0
+
+
 @dataclass
 class ActBuf:
     """Haloed NHWC activation buffer [B][H+2p][W+2p][C]."""

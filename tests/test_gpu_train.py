@@ -385,3 +385,33 @@ def test_side_stream_weight_gradients_equal_single_stream():
         scale = float(b[k].abs().max()) + 1e-30
         assert float((a[k] - b[k]).abs().max()) <= 1e-4 * scale, k
         assert float((c[k] - b[k]).abs().max()) <= 1e-4 * scale, k
+
+
+def test_half_batch_training_forward_equals_full_batch(monkeypatch):
+    """The training forward runs as two half-batch plans on two streams writing the full-batch activations in place
+    (NIRGAN_B200_TRAIN_SLICES); prediction, losses and every gradient equal the single full-batch plan."""
+    from nirgan_b200.model.pix2pix import Px2Px
+    g = torch.Generator().manual_seed(4)
+    batch = {"rgb": torch.rand(16, 3, 128, 128, generator=g).cuda(), "nir": torch.rand(16, 1, 128, 128, generator=g).cuda(),
+             "embeds": torch.randn(16, 256, generator=g).cuda()}
+    res = {}
+    sd = None
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NIRGAN_B200_TRAIN_SLICES", mode)
+        torch.manual_seed(0)
+        model = Px2Px(_cfg(inject=True)).cuda().train()
+        if sd is None:
+            sd = {k: v.clone() for k, v in model.state_dict().items()}
+        model.load_state_dict(sd)
+        model.netG.configure_b200(precision="fp16", impl="tc")
+        model.netD.configure_b200(precision="fp16", impl="tc")
+        loss = model.training_step(batch, 0, 1)
+        loss.backward()
+        torch.cuda.synchronize()
+        ctx = list(model.netG._runner._train.values())[0]
+        assert (ctx["fwd_halves"] is not None) == (mode == "1")
+        res[mode] = (loss.detach().clone(), {n: p.grad.detach().clone() for n, p in model.netG.named_parameters()})
+    assert float((res["0"][0] - res["1"][0]).abs()) <= 1e-6 * float(res["0"][0].abs())
+    for n in res["0"][1]:
+        a, b = res["0"][1][n], res["1"][1][n]
+        assert float((a - b).abs().max()) <= 1e-4 * (float(a.abs().max()) + 1e-30), n
