@@ -286,10 +286,11 @@ class GeneratorRunner(_RunnerBase):
         the batch is odd / small, disabled by NIRGAN_B200_TRAIN_SLICES=0, or a buffer is not per-image)."""
         import os
         from .engine import SliceBuffers
-        # measured on B200 at batch 32: two 16-image halves are SLOWER (21.6 vs 20.9 ms per step; every conv launch pays
-        # its ~25 us pipeline fill twice), whereas 64 -> 2 x 32 is the split that pays in inference: on from batch 64
-        mode = os.environ.get("NIRGAN_B200_TRAIN_SLICES", "auto")
-        if B % 2 or B < 16 or mode == "0" or (mode == "auto" and B < 64):
+        # measured on B200: slower than the single full-batch plan at batch 32 (21.6 vs 20.9 ms per step) and at batch 64
+        # (41.3 vs 39.4 ms) -- every conv launch pays its ~25 us pipeline fill twice and the eager launches of the two
+        # plans do not interleave the way the graph-replayed inference slices do.  Off unless NIRGAN_B200_TRAIN_SLICES=1.
+        mode = os.environ.get("NIRGAN_B200_TRAIN_SLICES", "0")
+        if B % 2 or B < 16 or mode != "1":
             return None
         saved, plans = eng.buffers, []
         try:
