@@ -136,6 +136,7 @@ GRAPHS = [os.environ.get("NIRGAN_B200_GRAPH", "1") != "0"]
 # ops added with side=True (the weight gradients: off the critical path of a backward pass) run on a second stream so
 # that they overlap the HBM-bound norm-backward kernels of the next layer (NIRGAN_B200_SIDE_STREAM=0: single stream)
 SIDE_STREAM = [os.environ.get("NIRGAN_B200_SIDE_STREAM", "1") != "0"]
+TRAIN_GRAPHS = [os.environ.get("NIRGAN_B200_TRAIN_GRAPH", "0") == "1"]
 _SIDE: Dict[int, "torch.cuda.Stream"] = {}
 
 
@@ -182,6 +183,13 @@ class Plan:
                 GRAPHS[0] = False
                 return self.run(stream.cuda_stream)
         g.replay()
+
+    def run_training(self, device):
+        """Training plans: CUDA-graph replay when NIRGAN_B200_TRAIN_GRAPH=1 (off by default), else eager launches."""
+        st = torch.cuda.current_stream(device)
+        if TRAIN_GRAPHS[0]:
+            return self.run_graphed(st)
+        return self.run(st.cuda_stream)
 
     def run(self, stream_ptr: int):
         if PROFILE[0] is not None:

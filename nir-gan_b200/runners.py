@@ -254,7 +254,7 @@ class GeneratorRunner(_RunnerBase):
                 halves[1].run(side.cuda_stream)
                 main.wait_stream(side)
             else:
-                fwd.run(main.cuda_stream)
+                fwd.run_training(x.device)
             c["fresh"] = key
         return c
 

@@ -137,7 +137,7 @@ class GeneratorFunction(torch.autograd.Function):
         inj = bwd.records.get("inject")
         if inj is not None:
             inj["dscale"].zero_()
-        bwd.run(st)
+        bwd.run_training(dout.device)
         grads = _export_weight_grads(g, bwd, ctx.params)
         gs = bwd.records.get("gscale")
         dev_inv = gs.data_ptr() + 4 if gs is not None else None
@@ -182,7 +182,7 @@ class DiscriminatorFunction(torch.autograd.Function):
         B, Cin, H, W = c["geom"]
         st = _stream(x)
         c["fwd"].records["src"].view(B, Cin, H, W).copy_(x.detach().float())
-        c["fwd"].run(st)
+        c["fwd"].run_training(x.device)
         ctx.c, ctx.module, ctx.runner, ctx.params = c, module, runner, params
         ctx.need_dw, ctx.need_dx = need_dw, need_dx
         Ho, Wo = c["graph"].records["out_hw"]
@@ -194,7 +194,7 @@ class DiscriminatorFunction(torch.autograd.Function):
         g, bwd = c["graph"], c["bwd"]
         st = _stream(dout)
         c["dout"].view_as(dout).copy_(dout.float())
-        bwd.run(st)
+        bwd.run_training(dout.device)
         runner._live = max(0, runner._live - 1)
         grads = _export_weight_grads(g, bwd, ctx.params) if ctx.need_dw else {}
         gs = bwd.records.get("gscale")
