@@ -1,0 +1,31 @@
+"""Host logic of the engine that needs no GPU: buffer cache and its batch-slice view."""
+import pytest
+import torch
+
+import nirgan_b200  # noqa: F401
+from nirgan_b200.engine import Buffers, SliceBuffers
+
+
+def test_buffers_are_cached_by_name_size_and_dtype():
+    b = Buffers(torch.device("cpu"))
+    a = b.get("x", 16, torch.float32)
+    assert b.get("x", 16, torch.float32) is a
+    assert b.get("x", 32, torch.float32) is not a
+    assert b.get("x", 16, torch.float16) is not a
+    assert float(b.get("z", 8, torch.float32, zero=True).abs().sum()) == 0.0
+    assert b.bytes() == 16 * 4 + 32 * 4 + 16 * 2 + 8 * 4
+
+
+def test_slice_buffers_return_in_place_views_of_per_image_buffers():
+    full = Buffers(torch.device("cpu"))
+    t = full.get("act", 4 * 6, torch.float32)
+    t.copy_(torch.arange(24, dtype=torch.float32))
+    halves = [SliceBuffers(full, p, 2) for p in range(2)]
+    h0, h1 = halves[0].get("act", 12, torch.float32), halves[1].get("act", 12, torch.float32)
+    assert torch.equal(h0, t[:12]) and torch.equal(h1, t[12:])
+    h1.fill_(-1.0)
+    assert float(t[12:].sum()) == -12.0 and float(t[:12].sum()) == float(sum(range(12)))      # a view, not a copy
+    with pytest.raises(KeyError):
+        halves[0].get("act", 10, torch.float32)          # not half of a full-batch buffer
+    with pytest.raises(KeyError):
+        halves[0].get("scalar", 1, torch.float32)        # buffers that do not scale with the batch are refused
