@@ -170,11 +170,15 @@ class GeneratorRunner(_RunnerBase):
         inject = embeds is not None
         chunk = eng.cfg.chunk if eng.cfg.chunk > 0 else Btot
         main = torch.cuda.current_stream(x.device)
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            x = x.contiguous().float()
         if inject:
             require_cuda(embeds, "embeds")
-            if embeds.dtype != torch.float32 or not embeds.is_contiguous():
+        convert = x.dtype != torch.float32 or not x.is_contiguous() or \
+            (inject and (embeds.dtype != torch.float32 or not embeds.is_contiguous()))
+        if convert:
+            if ready is not None:
+                main.wait_event(ready)      # the layout / dtype conversion below reads the inputs on the caller's stream
+            x = x.contiguous().float()
+            if inject:
                 embeds = embeds.contiguous().float()
         out = torch.empty(Btot, 1, H, W, dtype=torch.float32, device=x.device)
         want = eng.cfg.streams if eng.cfg.streams > 0 else (2 if Btot >= 32 else 1)

@@ -254,3 +254,13 @@ def test_forward_async_matches_forward_over_consecutive_calls():
             for ev in done:
                 main.wait_event(ev)
             assert torch.equal(y, w)
+        # inputs that need a dtype conversion, produced on another stream: the conversion must wait for `ready` too
+        with torch.cuda.stream(side):
+            xh = (xs[0] * 0 + xs[3]).double()
+            ev = torch.cuda.Event()
+            ev.record(side)
+        xh.record_stream(main)
+        y, done = net.forward_async(xh, es[3], ready=ev)
+        for d in done:
+            main.wait_event(d)
+        assert torch.equal(y, want[3])
