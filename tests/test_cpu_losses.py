@@ -38,3 +38,27 @@ def test_ssim_loss_properties():
         for w in (5, 11):
             v = P.ssim_loss(torch.from_numpy(Z[f"{c}.pred"]), torch.from_numpy(Z[f"{c}.target"]), w).item()
             assert abs(v - float(Z[f"{c}.ssim{w}"])) < 1e-6
+
+
+def test_ssim_map_agrees_with_an_independent_scipy_formulation():
+    """kornia is not installed, so the SSIM oracle cannot be pinned against it; as a second opinion the same published
+    formula is evaluated with scipy.ndimage (float64, mode='mirror' = reflect border without repeating the edge) and
+    must agree with the torch restatement to float32 rounding."""
+    from scipy import ndimage
+    g = torch.Generator().manual_seed(9)
+    a = torch.rand(1, 1, 40, 33, generator=g)
+    b = (a + 0.2 * torch.randn(1, 1, 40, 33, generator=g)).clamp(0, 1)
+    for win in (5, 11):
+        k = P.gaussian_kernel1d(win).double().numpy()
+
+        def filt(x):
+            return ndimage.correlate1d(ndimage.correlate1d(x, k, axis=0, mode="mirror"), k, axis=1, mode="mirror")
+
+        x, y = a[0, 0].double().numpy(), b[0, 0].double().numpy()
+        m1, m2 = filt(x), filt(y)
+        s1, s2, s12 = filt(x * x) - m1 * m1, filt(y * y) - m2 * m2, filt(x * y) - m1 * m2
+        c1, c2 = 0.01 ** 2, 0.03 ** 2
+        ref = ((2 * m1 * m2 + c1) * (2 * s12 + c2)) / ((m1 * m1 + m2 * m2 + c1) * (s1 + s2 + c2) + 1e-12)
+        got = P.ssim_map(a, b, win)[0, 0].double().numpy()
+        assert np.abs(got - ref).max() <= 2e-5
+        assert abs((1.0 - ref.mean()) - P.ssim_loss(a, b, win).item()) <= 1e-5
