@@ -76,6 +76,13 @@ class Px2Px(nn.Module):
         return torch.cat((rgb, e * self.config.satclip.scaling_factor), dim=1)
 
     @torch.no_grad()
+    def forward_async(self, input, embeds=None, ready=None):
+        """Streaming form of ``forward`` for inference loops (``synth.run_shard(model_async=...)``): returns
+        ``(pred, done_events)`` without joining the caller's stream; the pad / crop wrapper is applied as in ``forward``."""
+        pad = self.config.Data.padding_amount if self.config.Data.padding else 0
+        return self.netG.forward_async(input, embeds if self.inject else None, pad, ready)
+
+    @torch.no_grad()
     def predict_step(self, rgb, coords=None, embeds=None):
         assert self.training is False, "Model is in training mode, set to eval mode before predicting"
         if not self.satclip:

@@ -191,6 +191,19 @@ def test_tile_sharded_inference_matches_sequential_loop(golden_dir):
     for k in seq:
         assert torch.equal(merged[k], seq[k]), k
         _check(seq[k], torch.from_numpy(g["y." + k]), 2e-2, 2e-3, f"synth loop {k}")
+    # the pipelined loop (pinned staging, H2D / generator / read-back on separate streams) gives the same dictionary
+    piped = synth.run_shard(model, tiles, 0, 1, batch_size=2, device=torch.device("cuda"),
+                            model_async=lambda hr, ready: net.forward_async(hr, None, 10, ready), in_flight=2)
+    assert list(piped.keys()) == list(seq.keys())
+    for k in seq:
+        assert torch.equal(piped[k], seq[k]), k
+    # ... also with the loop body's post-processing (nearest x4 + histogram matching + float16) on the device
+    s2 = {n: torch.rand(1, 8, 8, generator=torch.Generator().manual_seed(7 + int(n[5:11]))) * 0.4 for n in names}
+    a = synth.run_shard(model, tiles, 0, 1, batch_size=2, device=torch.device("cuda"), s2_nir=s2)
+    b = synth.run_shard(model, tiles, 0, 1, batch_size=2, device=torch.device("cuda"), s2_nir=s2,
+                        model_async=lambda hr, ready: net.forward_async(hr, None, 10, ready))
+    for k in a:
+        assert a[k].dtype == torch.float16 and torch.equal(a[k], b[k]), k
 
 
 def test_config2_full_size_properties():
