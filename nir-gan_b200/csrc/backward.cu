@@ -346,7 +346,15 @@ in_bwd_combine_kernel(const float* __restrict__ partial, int total, int per_imag
   const int n = i / per_image, o = i - n * per_image;
   const float* p = partial + (size_t)n * nblk * per_image + o;
   float t = 0.f;
-  for (int k = 0; k < nblk; ++k) t += p[(size_t)k * per_image];
+  int k = 0;
+  for (; k + 8 <= nblk; k += 8) {              // eight independent loads in flight, added in block order
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(k + j) * per_image];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += v[j];
+  }
+  for (; k < nblk; ++k) t += p[(size_t)k * per_image];
   out[i] = t;
 }
 

@@ -244,7 +244,16 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float4* __restrict__ part, int splits, long long n4, float4* __restrict__ dw) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 s = part[i];
-    for (int k = 1; k < splits; ++k) {
+    int k = 1;
+    for (; k + 3 < splits; k += 4) {          // four independent loads in flight, added in split order
+      const float4 a = part[(size_t)k * n4 + i], b = part[(size_t)(k + 1) * n4 + i], c = part[(size_t)(k + 2) * n4 + i],
+                   d = part[(size_t)(k + 3) * n4 + i];
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+      s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
+      s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+      s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+    }
+    for (; k < splits; ++k) {
       const float4 v = part[(size_t)k * n4 + i];
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
