@@ -29,3 +29,25 @@ def test_slice_buffers_return_in_place_views_of_per_image_buffers():
         halves[0].get("act", 10, torch.float32)          # not half of a full-batch buffer
     with pytest.raises(KeyError):
         halves[0].get("scalar", 1, torch.float32)        # buffers that do not scale with the batch are refused
+
+
+def test_plan_records_side_ops_and_launch_counts():
+    """Plan bookkeeping that needs no GPU: ops bound to exported symbols, side flags, launch counts."""
+    from nirgan_b200.engine import Plan
+    p = Plan()
+    p.add("ng_in_stats_finalize", 0, 1, 1, 2, 1, 0, label="a.fin")
+    p.add("ng_conv2d_wgrad", None, 0, 0, 0, 0, launches=3, label="a.wgrad", side=True)
+    p.add("ng_in_apply", label="")
+    assert p.side == [False, True, False] and p.launches == 5
+    assert p.labels == ["a.fin", "a.wgrad", "ng_in_apply"] and [o[2] for o in p.ops][1] == "ng_conv2d_wgrad"
+    with pytest.raises(AttributeError):
+        p.add("ng_no_such_entry_point")
+
+
+def test_tile_batches_group_by_shape_in_list_order():
+    from nirgan_b200.synth import _batches
+    tiles = {f"t{i}": torch.zeros(3, 8 if i not in (3, 4) else 16, 8) for i in range(7)}
+    names = [f"t{i}" for i in range(7)]
+    assert _batches(names, tiles, 2) == [["t0", "t1"], ["t2"], ["t3", "t4"], ["t5", "t6"]]
+    assert _batches(names, tiles, 64) == [["t0", "t1", "t2"], ["t3", "t4"], ["t5", "t6"]]
+    assert _batches([], tiles, 4) == []
