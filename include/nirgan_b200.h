@@ -30,7 +30,24 @@
  *   ng_lsgan_loss      GANLoss('lsgan') model/networks.py:232-233,268-270
  *   ng_g_pixel_losses  L1Loss model/pix2pix.py:60,222 + RemoteSensingIndices NDVI/NDWI/EVI
  *                      utils/remote_sensing_indices.py:84-159,277-319
- *   ng_adam_step       torch.optim.Adam model/pix2pix.py:486-487
+ *   ng_adam_step / ng_adam_multi
+ *                      torch.optim.Adam model/pix2pix.py:486-487 (one launch per optimizer over a flat arena)
+ *   ng_in_bwd          autograd of the InstanceNorm / inject / activation / residual / halo unit above
+ *   ng_prep_stem / ng_tap_gather / ng_tap_scatter / ng_head_bwd_prep
+ *                      ReflectionPad2d(3) + Conv2d(3, 64, 7) input staging and the Conv2d(64, 1, 7) + Tanh head
+ *                      (model/networks.py:341-342,367-368) and their adjoints, incl. the wrapper's pad / crop
+ *   ng_rs_pixel_losses / ng_rs_index
+ *                      all six RemoteSensingIndices, criterion l1 / l2, loss / logging / index modes
+ *                      utils/remote_sensing_indices.py:23-319
+ *   ng_ssim_loss / ng_emd_loss
+ *                      utils/losses.py:10-29,64-78 (ssim_loss; emd_loss = pix2pix.py's hist_loss)
+ *   ng_image_metrics   utils/calculate_metrics.py:6-37 (L1, L2, PSNR, SSIM)
+ *   ng_resize_plane / ng_hist_match / ng_sort_segments
+ *                      F.interpolate + skimage.exposure.match_histograms, create_synthetic_dataset.py:34-52,111-118
+ *   ng_satclip_encode  SatClIP_wrapper.predict model/satclip/satclip_wrapper.py:29-34 (location_encoder.py:73-151,
+ *                      267-275; positional_encoding/spherical_harmonics.py:27-42)
+ *   ng_grad_scale_pow2 / ng_unpack_weight_grad* / ng_grad_to_nchw / ng_inject_bwd / ng_nonfinite_flag
+ *                      plumbing of the training step (fp16 gradient scale, gradient export in the reference layout)
  */
 #ifndef NIRGAN_B200_H_
 #define NIRGAN_B200_H_
