@@ -20,7 +20,7 @@
  *   ng_conv2d          nn.Conv2d / nn.ConvTranspose2d call sites  model/networks.py:342,349,360-363,367,
  *                      405-427 (ResnetBlock), 559-579 (NLayerDiscriminator) and their autograd dgrad
  *   ng_conv2d_wgrad    autograd weight gradient of the same call sites (model/pix2pix.py:165-257)
- *   ng_in_stats / ng_in_stats_finalize / ng_in_apply / ng_in_apply_bwd
+ *   ng_in_stats / ng_in_stats_finalize / ng_in_apply
  *                      nn.InstanceNorm2d + ReLU/LeakyReLU + residual add + ReflectionPad2d
  *                      model/networks.py:29-30,341-344,350-351,405-434,567-576; the SatCLIP
  *                      injection x*(1+s*e) model/generator_inject.py:113-127
