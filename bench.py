@@ -1,13 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- NIR-GAN hot path on B200: 256x256 RGB->NIR tiles/sec.
+"""bench.py -- NIR-GAN hot path on B200: 256x256 RGB->NIR tiles/sec (+ the training step as a sub-record).
 
-Workload (N=1): BASELINE.json configs[1] -- SatCLIP-injected ResnetGenerator inference, 64 synthetic
+Headline workload (N=1): BASELINE.json configs[1] -- SatCLIP-injected ResnetGenerator inference, 64 synthetic
 3x256x256 tiles + 64 random (256,) embeddings per step, random-init weights, through the reference-
 compatible API (`define_G_inject(config)(x, embeds)`).  N>1: the same per-GPU workload on every rank
 (tile-sharded, no collective; scaling = weak).
 
 One JSON line on stdout (rank 0).  `value` = tiles/s with inputs resident in HBM; `e2e` = the same through
-host (pinned) buffers incl. H2D of tiles+embeddings and D2H of the NIR band every step.
+host (pinned) buffers incl. H2D of tiles+embeddings and D2H of the NIR band every step.  Both are the MEDIAN over
+timed windows of exactly --steps steps (barrier + synchronize on both sides of every window, CUDA events, max over
+ranks); windows repeat until there are at least 5 and 2 s of them, p10/p90 are reported.  A clock sampler
+(nvidia-smi) runs beside every timed loop alike.
+`train` sub-record: BASELINE.json configs[3] (full Pix2Pix training step, batch 32, 256x256) and configs[4]
+(data-parallel training, batch 32 per GPU, seeded mixed 128..512 px resolutions, NCCL gradient all-reduce over
+N ranks) through `nirgan_b200.trainer.Trainer`.
 `--impl reference` times the CPU oracle port of the reference on the host cores (the reference is pure
 Python/torch and cannot travel to the GPU box).
 """
@@ -21,9 +27,8 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 # more hardware queues than streams (compute slices + copy streams): no false dependencies between streams
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
@@ -33,6 +38,10 @@ TILE = 256
 BATCH = 64
 METRIC = "rgb2nir_256px_tiles_per_sec"
 UNIT = "tiles/s"
+WORKLOAD = ("configs[1]: SatCLIP-injected ResnetGenerator (9 blocks, ngf 64) inference, 64x3x256x256 tiles + 64x256 "
+            "random embeddings per GPU per step, random-init weights")
+TRAIN_RES = (128, 192, 256, 384, 512)
+GFLOP_PER_SAMPLE_256 = 391.6          # minimal training-step op count (one G forward), 256x256 tile
 
 
 def peaks():
@@ -60,7 +69,7 @@ class ClockSampler:
 
     def stop(self):
         if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.p.terminate()
         try:
             out, _ = self.p.communicate(timeout=5)
@@ -85,14 +94,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def merge_clocks(parts: dict):
+    """One `clocks` object for the line: median of the per-loop medians, union of the reasons, plus the per-loop records."""
+    meds = sorted(c["sm_mhz"] for c in parts.values() if c and c.get("sm_mhz"))
+    out = {"sm_mhz": meds[len(meds) // 2] if meds else None,
+           "sm_max_mhz": max([c["sm_max_mhz"] for c in parts.values() if c and c.get("sm_max_mhz")] or [None]),
+           "reasons": sorted({r for c in parts.values() if c for r in c.get("reasons", [])}),
+           "samples": sum(c.get("samples", 0) for c in parts.values() if c),
+           "per_loop": parts}
+    return out
+
+
 def build_model(dev):
     import nirgan_b200  # noqa: F401
+    from nirgan_b200.config import satclip_inject_config
     from nirgan_b200.model.generator_inject import define_G_inject
-    from test_gpu_models import inject_config
     import contextlib
     torch.manual_seed(0)
     with contextlib.redirect_stdout(sys.stderr):   # the reference prints its scale-param init; stdout is JSON only
-        net = define_G_inject(inject_config())     # random-init, N(0, 0.02) like the reference
+        net = define_G_inject(satclip_inject_config())     # random-init, N(0, 0.02) like the reference
     return net.to(dev).eval()
 
 
@@ -132,8 +152,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": BATCH / v * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: SatCLIP-injected ResnetGenerator inference, 64x3x256x256 tiles + 64x256 embeddings",
-                       "note": "CPU oracle port of the reference (pure-Python reference cannot travel); each step is a bounded sample"},
+            "config": {"workload": WORKLOAD,
+                       "note": "CPU oracle port of the reference (pure-Python reference cannot travel); each step is a "
+                               "bounded sample of the 64-tile step on all host cores"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -161,6 +182,195 @@ def emit(line: dict):
         os.write(_REAL_STDOUT[0], data)
 
 
+def pct(sorted_vals, q):
+    if not sorted_vals:
+        return None
+    i = min(len(sorted_vals) - 1, max(0, int(round(q * (len(sorted_vals) - 1)))))
+    return sorted_vals[i]
+
+
+class Timing:
+    """Window timing shared by every loop of the bench: W warm-up steps (then more, until >= `settle_s` of work has run, so
+    the SM clocks have ramped), then windows of exactly K steps -- barrier + synchronize, event, K steps, join, event,
+    barrier + synchronize; max over ranks -- until >= min_windows windows and >= min_total_s of timed work."""
+
+    def __init__(self, dev, dist, main_stream, extra_streams=()):
+        self.dev, self.dist, self.main, self.extra = dev, dist, main_stream, tuple(extra_streams)
+
+    def barrier(self):
+        torch.cuda.synchronize(self.dev)
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, ms):
+        if self.dist is None:
+            return ms
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def windows(self, fn, steps, warm, join=None, min_windows=5, min_total_s=2.0, max_windows=60, settle_s=1.0):
+        t0 = time.perf_counter()
+        n = 0
+        while n < warm or self.max_over_ranks(time.perf_counter() - t0) < settle_s:
+            fn()
+            n += 1
+            if n % 4 == 0:
+                torch.cuda.synchronize(self.dev)
+        ms_all = []
+        while True:
+            self.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(self.main)
+            for _ in range(steps):
+                fn()
+            if join is not None:
+                join()
+            for st in self.extra:
+                self.main.wait_stream(st)
+            ev1.record(self.main)
+            self.barrier()
+            ms_all.append(self.max_over_ranks(ev0.elapsed_time(ev1)))      # identical on every rank after the reduce
+            if len(ms_all) >= max_windows or (len(ms_all) >= min_windows and sum(ms_all) >= min_total_s * 1e3):
+                break
+        s = sorted(ms_all)
+        return {"ms_p50": pct(s, 0.5), "ms_p10": pct(s, 0.1), "ms_p90": pct(s, 0.9), "n": len(s),
+                "total_s": sum(s) / 1e3, "warm_steps": n, "first_ms": ms_all[0]}
+
+
+# =====================================================================================================================
+# training sub-record (BASELINE.json configs[3] and configs[4])
+# =====================================================================================================================
+def train_record(args, dev, rank, world, dist, tm: Timing, samplers: dict):
+    import contextlib
+    import nirgan_b200  # noqa: F401
+    from nirgan_b200.config import px2px_config
+    from nirgan_b200.model.pix2pix import Px2Px
+    from nirgan_b200.trainer import Trainer
+    torch.manual_seed(0)                       # same initial weights on every rank (DDP)
+    with contextlib.redirect_stdout(sys.stderr):
+        model = Px2Px(px2px_config()).to(dev).train()
+    model.netG.configure_b200(precision=args.precision, impl=args.conv)
+    model.netD.configure_b200(precision=args.precision, impl=args.conv)
+    trainer = Trainer(model, time_exchange=True)
+    B = args.train_batch
+    gen = torch.Generator().manual_seed(200 + rank)
+    # host (pinned) copies of every resolution's batch: the e2e loop feeds the step from them
+    host = {s: {"rgb": torch.rand(B, 3, s, s, generator=gen).pin_memory(),
+                "nir": torch.rand(B, 1, s, s, generator=gen).pin_memory()} for s in TRAIN_RES}
+    data = {s: {k: v.to(dev) for k, v in host[s].items()} for s in TRAIN_RES}
+    losses = torch.zeros(2, device=dev)
+    losses_host = torch.zeros(2).pin_memory()
+    state = {"last": None}
+
+    def step_at(s):
+        ld, lg = trainer.step(data[s])
+        state["last"] = (ld, lg)
+
+    # every resolution once, largest first (plan compilation, pool sizing, graph capture are one-off costs)
+    for s in sorted(TRAIN_RES, reverse=True):
+        for _ in range(2):
+            step_at(s)
+    torch.cuda.synchronize(dev)
+    rec = {}
+
+    # ---- configs[3]: fixed 256x256, batch 32 per GPU ----
+    def flop(s):
+        return GFLOP_PER_SAMPLE_256 * (s / 256.0) ** 2 if model.reuse_g_forward else 505.8 * (s / 256.0) ** 2
+
+    samplers["train"] = ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if rank == 0 else None
+    k4 = max(2, args.train_steps)
+    w = tm.windows(lambda: step_at(256), k4, 3, min_windows=5, min_total_s=1.5, settle_s=0.5)
+    ms4 = w["ms_p50"] / k4
+    torch.cuda.synchronize(dev)
+    ld, lg = state["last"]
+    exposed4 = trainer.exposed_exchange_ms()
+    rec["config4"] = {
+        "workload": f"configs[3]: full Pix2Pix training step (D pass + G pass, LSGAN + 100*L1 + NDVI/NDWI/EVI, Adam), "
+                    f"batch {B} per GPU, 256x256, plain generator behind the pad-10 wrapper",
+        "ms_per_step": ms4, "samples_per_s": B * world / ms4 * 1e3, "steps_per_window": k4, "windows": w,
+        "tflops": B * world * flop(256) / ms4, "gflop_per_sample": flop(256),
+        "frac_of_sustained_peak": B * flop(256) / ms4 / peaks()["tf_sustained"],
+        "allreduce_exposed_ms_per_step": exposed4, "loss_D": float(ld), "loss_G": float(lg)}
+    # the same step fed from pinned host memory (H2D of the batch, D2H of the two losses every step)
+    hstream = torch.cuda.Stream(dev)
+    dbuf = [{k: torch.empty_like(v) for k, v in data[256].items()} for _ in range(2)]
+    hev = [torch.cuda.Event() for _ in range(2)]
+    fev = [None, None]
+    ctr = {"i": 0}
+
+    def step_e2e():
+        i = ctr["i"] & 1
+        ctr["i"] += 1
+        with torch.cuda.stream(hstream):
+            if fev[i] is not None:
+                hstream.wait_event(fev[i])
+            for k in dbuf[i]:
+                dbuf[i][k].copy_(host[256][k], non_blocking=True)
+            hev[i].record(hstream)
+        tm.main.wait_event(hev[i])
+        ld_, lg_ = trainer.step(dbuf[i])
+        fev[i] = torch.cuda.Event()
+        fev[i].record(tm.main)
+        losses[0].copy_(ld_)
+        losses[1].copy_(lg_)
+        losses_host.copy_(losses, non_blocking=True)
+
+    w = tm.windows(step_e2e, k4, 2, min_windows=3, min_total_s=1.0, settle_s=0.2)
+    ms4e = w["ms_p50"] / k4
+    rec["config4"]["e2e"] = {"samples_per_s": B * world / ms4e * 1e3, "ms_per_step": ms4e,
+                             "h2d_bytes_per_step": sum(v.numel() * 4 for v in host[256].values()),
+                             "d2h_bytes_per_step": 8}
+
+    # ---- configs[4]: mixed resolutions, data parallel over `world` ranks ----
+    seq_gen = torch.Generator().manual_seed(1234)
+    k5 = 10
+    seq = [TRAIN_RES[int(torch.randint(0, len(TRAIN_RES), (1,), generator=seq_gen))] for _ in range(k5)]
+    it = {"i": 0}
+
+    def step_mixed():
+        step_at(seq[it["i"] % k5])
+        it["i"] += 1
+
+    def run_cfg5():
+        it["i"] = 0
+        return tm.windows(step_mixed, k5, k5, min_windows=3, min_total_s=1.5, settle_s=0.2)
+
+    w = run_cfg5()
+    ms5 = w["ms_p50"] / k5
+    torch.cuda.synchronize(dev)
+    ld, lg = state["last"]
+    gf5 = sum(flop(s) for s in seq) / k5
+    rec["config5"] = {
+        "workload": f"configs[4]: data-parallel Pix2Pix training, batch {B} per GPU x {world} GPU(s), per-step resolution "
+                    f"from the seeded sequence {seq} (same on every rank), bucketed NCCL all-reduce of the D and G "
+                    "gradients overlapped with the backward pass",
+        "ms_per_step": ms5, "samples_per_s": B * world / ms5 * 1e3, "steps_per_window": k5, "windows": w,
+        "tflops": B * world * gf5 / ms5, "gflop_per_sample_mean": gf5,
+        "frac_of_sustained_peak": B * gf5 / ms5 / peaks()["tf_sustained"],
+        "loss_D": float(ld), "loss_G": float(lg)}
+    if world > 1:
+        # cost of the gradient exchange: the same windows without the collectives (ranks diverge afterwards, measurement
+        # only) and the device-timed wait of the training stream for the last bucket
+        rec["config5"]["allreduce_exposed_ms_per_step_last"] = trainer.exposed_exchange_ms()
+        trainer.exchange = False
+        w0 = run_cfg5()
+        trainer.exchange = True
+        rec["config5"]["ms_per_step_without_allreduce"] = w0["ms_p50"] / k5
+        rec["config5"]["allreduce_exposed_ms_per_step"] = max(0.0, ms5 - w0["ms_p50"] / k5)
+        rec["config5"]["nccl_buckets_per_step"] = {k: r.last_buckets for k, r in trainer.reducers.items()}
+    rec["clocks"] = samplers["train"].stop() if samplers.get("train") else None
+    rec["mem_gb"] = {"max_allocated": torch.cuda.max_memory_allocated(dev) / 1e9,
+                     "generator_pool": model.netG._runner.pool_bytes() / 1e9,
+                     "discriminator_pool": model.netD._runner.pool_bytes() / 1e9}
+    rec["skipped_steps"] = [trainer.opt_d.skipped_steps, trainer.opt_g.skipped_steps]
+    rec["cuda_graphs"] = bool(__import__("nirgan_b200").engine.TRAIN_GRAPHS[0])
+    rec["launches_per_step_256"] = sum(c["fwd"].launches + c["bwd"].launches for r in (model.netG._runner, model.netD._runner)
+                                       for k, c in r._train.items() if c["geom"][2] in (256,))
+    return rec
+
+
 def main():
     _quiet_stdout()
     ap = argparse.ArgumentParser()
@@ -175,6 +385,11 @@ def main():
     ap.add_argument("--streams", type=int, default=int(os.environ.get("NIRGAN_B200_STREAMS", "0")),
                     help="batch slices run concurrently on separate CUDA streams (0 = engine default: 2 for >= 32 tiles)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training sub-record (configs[3] / configs[4])")
+    ap.add_argument("--train-batch", type=int, default=32)
+    ap.add_argument("--train-steps", type=int, default=10, help="steps per timed window of the configs[3] loop")
+    ap.add_argument("--min-windows", type=int, default=5)
+    ap.add_argument("--min-seconds", type=float, default=2.0)
     ap.add_argument("--sync-calls", action="store_true",
                     help="issue steps with net(x, e) (joins the caller's stream every step) instead of forward_async")
     ap.add_argument("--no-graph", action="store_true")
@@ -199,6 +414,9 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
+    if args.no_graph:
+        import nirgan_b200
+        nirgan_b200.engine.GRAPHS[0] = False
 
     B = args.batch
     net = build_model(dev).configure_b200(precision=args.precision, impl=args.conv, chunk=args.chunk,
@@ -210,22 +428,9 @@ def main():
     x = x_host.to(dev)
     e = e_host.to(dev)
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # Both loops use the streaming call of the public API (``forward_async``): a step's slices queue behind the same
     # slices of the previous step on the generator's own streams, so consecutive steps overlap instead of meeting at a
-    # barrier on the caller's stream; the timed region ends when the last step's results are complete.
+    # barrier on the caller's stream; a timed window ends when its last step's results are complete.
     # (--sync-calls: the plain ``net(x, e)`` call, which joins the caller's stream after every step.)
     last_done = {"ev": []}
 
@@ -274,28 +479,25 @@ def main():
                     d2h_stream.wait_event(ev)
                 y_host.copy_(y, non_blocking=True)
 
-    def timed(fn, steps, warm):
-        for _ in range(warm):
-            fn()
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(steps):
-            fn()
+    def join_last():
         for ev in last_done["ev"]:
             main_stream.wait_event(ev)                         # the last step's slices
-        for st in (h2d_stream, d2h_stream):
-            main_stream.wait_stream(st)                        # the timed region ends when the last D2H has landed
-        ev1.record()
-        barrier()
-        return max_over_ranks(ev0.elapsed_time(ev1))
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    ms = timed(step_resident, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else None
-    ms_e2e = timed(step_e2e, args.steps, 3)
+    tm = Timing(dev, dist, main_stream, (h2d_stream, d2h_stream))
+    samplers = {}
+    clock_parts = {}
+    # identical conditions for both loops: a clock sampler beside each, the same warm-up rule, the same window rule
+    samplers["value"] = ClockSampler(local) if rank == 0 else None
+    w_val = tm.windows(step_resident, args.steps, args.warmup, join=join_last, min_windows=args.min_windows,
+                       min_total_s=args.min_seconds)
+    clock_parts["value"] = samplers["value"].stop() if samplers["value"] else None
+    samplers["e2e"] = ClockSampler(local) if rank == 0 else None
+    w_e2e = tm.windows(step_e2e, args.steps, args.warmup, join=join_last, min_windows=args.min_windows,
+                       min_total_s=args.min_seconds)
+    clock_parts["e2e"] = samplers["e2e"].stop() if samplers["e2e"] else None
+    ms, ms_e2e = w_val["ms_p50"], w_e2e["ms_p50"]
     # diagnostic: the host link alone (one H2D of a step's tiles from pinned memory), to read e2e against
-    barrier()
+    tm.barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     c0.record()
     for _ in range(3):
@@ -354,11 +556,13 @@ def main():
     pk = peaks()
     achieved = res_flop / (res_ms * 1e-3) / 1e12
     share = sum(op_ms[i] for i in res_idx) / sum(op_ms.values())
+    small_idx = [i for i in conv_idx if i not in res_idx]
+    small_ms = grouped_ms(small_idx)
 
     # HBM-bound companion: the fused InstanceNorm-apply launches; algorithmic bytes from their own arguments
     # (read y [+ residual], write the haloed output; 16-bit elements) -- DESIGN.md section 3.3
     esz = 4 if args.precision == "fp32" else 2
-    ap_bytes, ap_ms = 0.0, 0.0
+    ap_bytes = 0.0
     for i, (fn, a, name) in enumerate(plan.ops):
         if name != "ng_in_apply":
             continue
@@ -368,50 +572,80 @@ def main():
     ap_idx = [i for i, (fn, a, name) in enumerate(plan.ops) if name == "ng_in_apply"]
     ap_ms = grouped_ms(ap_idx)
     hbm_achieved = ap_bytes / (ap_ms * 1e-3) / 1e9 if ap_ms > 0 else 0.0
+    plan_launches = plan.launches
+
+    # ---- training sub-record ----
+    train = None
+    if not args.no_train:
+        try:
+            train = train_record(args, dev, rank, world, dist, tm, samplers)
+            clock_parts["train"] = train.pop("clocks", None)
+        except Exception as ex:           # the headline must still be printed; the failure is part of the record
+            import traceback
+            traceback.print_exc()
+            train = {"error": f"{type(ex).__name__}: {ex}"}
+            if samplers.get("train"):
+                samplers["train"].stop()
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    tiles = B * world * args.steps
-    value = tiles / (ms * 1e-3)
-    e2e = tiles / (ms_e2e * 1e-3)
+    tiles_per_window = B * world * args.steps
+    value = tiles_per_window / (ms * 1e-3)
+    e2e = tiles_per_window / (ms_e2e * 1e-3)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import nirgan_oracle as O
     gflop_tile = O.g_forward_gflop(TILE, TILE) + 2 * 256 * 16384 / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed `ncu --set full` capture
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_per_launch"] * Bc / tj["tiles_per_launch"]
+        traffic_src = tj["source"]
+    checks = {"value_ge_0p97_e2e": bool(value >= 0.97 * e2e),
+              "value_over_e2e": value / e2e,
+              "value_spread_p90_over_p10": w_val["ms_p90"] / w_val["ms_p10"],
+              "e2e_spread_p90_over_p10": w_e2e["ms_p90"] / w_e2e["ms_p10"]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: SatCLIP-injected ResnetGenerator (9 blocks, ngf 64) inference, "
-                               f"{B}x3x{TILE}x{TILE} tiles + {B}x256 random embeddings per GPU, random-init weights",
+        "config": {"workload": WORKLOAD if B == BATCH else WORKLOAD.replace("64x", f"{B}x"),
                    "global_batch": B * world, "tile": TILE, "parallelism": f"tile-sharded x{world}, no collective",
                    "conv_impl": args.conv, "operands": args.precision + " operands, fp32 accumulate (TMEM)",
                    "chunk": Bc, "streams": B // Bc if args.chunk <= 0 else args.streams,
+                   "timing": "median over windows of exactly `steps` steps (barrier + synchronize around each window, CUDA "
+                             "events on the launching stream, max over ranks); windows repeat until >= 5 and >= 2 s",
                    "l2": "per-step activation working set (~%.1f GB) exceeds the 126 MB L2; no explicit flush" % (
                        runner._engine.buffers.bytes() / 1e9)},
+        "windows": {"value": w_val, "e2e": w_e2e},
+        "checks": checks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 + e_host.numel() * 4,
                 "d2h_bytes_per_step": y_host.numel() * 4, "ms_per_step": ms_e2e / args.steps,
                 "h2d_link_gbs_measured": h2d_gbs,
                 "pipelining": "double-buffered H2D / D2H on copy streams overlap the kernels of neighbouring steps; steps issued with forward_async (slices of consecutive steps overlap)"},
-        "gpu_launches": plan.launches * (B // Bc) * args.steps,
-        "clocks": clocks,
+        "gpu_launches": plan_launches * (B // Bc) * args.steps,
+        "clocks": merge_clocks(clock_parts),
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel<256,64> (ResnetBlock 3x3, 256->256)",
                      "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tf_sustained"],
-                     # dram__bytes_read+write of this kernel from profiles/r1c_inference.md (ncu --set full, B=64 launch:
-                     # 144.0 + 100.0 MB; the kernel's traffic is linear in the tiles per launch)
-                     "traffic": 244.0e6 * Bc / 64.0,
+                     "frac": achieved / pk["tf_sustained"], "frac_of_burst_peak": achieved / pk["tf_burst"],
+                     "traffic": traffic, "traffic_source": traffic_src,
                      "ms_per_launch": res_ms, "flop_per_launch": res_flop, "share_of_step": share,
                      "timing": "the kernel's launches of a step slice replayed as one CUDA graph between one CUDA-event pair, median of repeats",
                      "peak_source": pk["src"] + " (sustained bf16; fp16/bf16 share one tcgen05 rate)"},
         "roofline_hbm": {"bound": "hbm", "kernel": "in_apply_kernel (InstanceNorm + inject + act + residual + halo; all launches of a step)",
                          "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / pk["hbm_gbs"],
                          "bytes_per_step_slice": ap_bytes, "ms_per_step_slice": ap_ms, "peak_source": pk["src"]},
+        "small_convs": {"kernels": "stem, down x2, up x2, head tap-GEMM (the non-ResnetBlock convolutions)",
+                        "ms_per_step_slice": small_ms,
+                        "tflops": (gflop_tile - 18 * 4.832) * Bc / small_ms if small_ms > 0 else None},
         "model_tflops": value * gflop_tile / 1e3,
         "model_frac_of_sustained_peak": value * gflop_tile / 1e3 / (pk["tf_sustained"] * world),
         "op_ms": {k: round(sum(v), 4) for k, v in by_name.items()},
+        "train": train,
     }
     if os.path.isdir(os.path.join(ROOT, "gpurun_out")):
         with open(os.path.join(ROOT, "gpurun_out", "op_times.json"), "w") as f:

@@ -28,8 +28,6 @@
  *                      model/networks.py:341, torch.cat((rgb, pred),1) model/pix2pix.py:197,202,216
  *   ng_linear          self.fc(embeds) model/generator_inject.py:110
  *   ng_lsgan_loss      GANLoss('lsgan') model/networks.py:232-233,268-270
- *   ng_g_pixel_losses  L1Loss model/pix2pix.py:60,222 + RemoteSensingIndices NDVI/NDWI/EVI
- *                      utils/remote_sensing_indices.py:84-159,277-319
  *   ng_adam_step / ng_adam_multi
  *                      torch.optim.Adam model/pix2pix.py:486-487 (one launch per optimizer over a flat arena)
  *   ng_in_bwd          autograd of the InstanceNorm / inject / activation / residual / halo unit above
@@ -37,8 +35,8 @@
  *                      ReflectionPad2d(3) + Conv2d(3, 64, 7) input staging and the Conv2d(64, 1, 7) + Tanh head
  *                      (model/networks.py:341-342,367-368) and their adjoints, incl. the wrapper's pad / crop
  *   ng_rs_pixel_losses / ng_rs_index
- *                      all six RemoteSensingIndices, criterion l1 / l2, loss / logging / index modes
- *                      utils/remote_sensing_indices.py:23-319
+ *                      L1Loss model/pix2pix.py:60,222 + all six RemoteSensingIndices, criterion l1 / l2,
+ *                      loss / logging / index modes utils/remote_sensing_indices.py:23-319 (forward and d/dpred)
  *   ng_ssim_loss / ng_emd_loss
  *                      utils/losses.py:10-29,64-78 (ssim_loss; emd_loss = pix2pix.py's hist_loss)
  *   ng_image_metrics   utils/calculate_metrics.py:6-37 (L1, L2, PSNR, SSIM)
@@ -58,7 +56,7 @@
 extern "C" {
 #endif
 
-#define NG_VERSION 100
+#define NG_VERSION 101
 
 /* element types */
 enum { NG_F32 = 0, NG_F16 = 1, NG_BF16 = 2 };
@@ -144,11 +142,13 @@ int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void*
  * k is zero-padded to k_pad, n to n_pad. */
 int ng_pack_weight(const float* src, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
                    int32_t n_pad, int32_t k_pad, int32_t dtype, void* dst, void* stream);
-/* inverse for gradients: dst[d0][d1][KH][KW] = scale * dev_scale[0] * packed[tap][n_pad][k_pad]  (fp32; undoes the
- * loss scaling: `scale` is the host-known static part, dev_scale (device pointer, may be NULL) the adaptive part
- * written by ng_grad_scale_pow2) */
+/* inverse for gradients: dst[d0][d1][KH][KW] = beta * dst + scale * dev_scale[0] * packed[tap][n_pad][k_pad]  (fp32;
+ * undoes the loss scaling: `scale` is the host-known static part, dev_scale (device pointer, may be NULL) the adaptive
+ * part written by ng_grad_scale_pow2; beta = 0 overwrites -- dst is not read --, beta = 1 accumulates like autograd's
+ * AccumulateGrad when a parameter is reached twice in one backward pass or .grad was not cleared) */
 int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW, int32_t n_axis,
-                          int32_t n_pad, int32_t k_pad, float scale, const float* dev_scale, float* dst, void* stream);
+                          int32_t n_pad, int32_t k_pad, float scale, const float* dev_scale, float beta, float* dst,
+                          void* stream);
 
 /* weights for NG_FORM_PHASED_MERGED: ConvTranspose2d weight fp32 [Cin][Cout][3][3] ->
  * [shift = sy*2+sx][n = phase*Cout + co][Cin], phase = (oy&1)*2 + (ox&1); entry = w[ci][co][pa+1-2sy][pb+1-2sx] or 0 */
@@ -164,9 +164,9 @@ int ng_prep_stem(const float* src, int32_t cin, int32_t B, int32_t H, int32_t W,
 /* weights for the row-merged stem: fp32 [O][I][KH][KW] -> [kh][O][kw*8 + c] (zero padded to 64) */
 int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH, int32_t KW, int32_t dtype, void* dst,
                              void* stream);
-/* inverse for gradients: fp32 [kh][O][64] -> fp32 [O][I][KH][KW], times scale */
+/* inverse for gradients: fp32 [kh][O][64] -> fp32 [O][I][KH][KW], dst = beta * dst + scale * dev_scale[0] * packed */
 int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW, float scale,
-                                    const float* dev_scale, float* dst, void* stream);
+                                    const float* dev_scale, float beta, float* dst, void* stream);
 
 /* Single-output-channel KHxKW convolution as "tap GEMM + gather": z = [B][Hz][Wz][zc] holds, per input pixel, the
  * dot product of its channels with each of the KH*KW taps (a 1x1 ng_conv2d with Cout = zc >= KH*KW);
@@ -226,8 +226,9 @@ int ng_grad_scale_pow2(const float* g, int64_t n, float target, float* out4, voi
  * dev_scale: device pointer or NULL. */
 int ng_head_bwd_prep(const float* dout, const float* out, int32_t B, int32_t H, int32_t W, int32_t crop, int32_t act,
                      float scale, const float* dev_scale, int32_t c_pad, int32_t dtype, void* dst, void* stream);
-/* gradient export: NHWC [B][H][W][c_pad] (dtype) -> NCHW fp32 [B][c][H][W], times scale * dev_scale[0] */
-int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c,
+/* gradient export: channels [c0, c0 + c) of NHWC [B][H][W][c_pad] (dtype) -> NCHW fp32 [B][c][H][W], times
+ * scale * dev_scale[0]  (the G pass needs dL/d(pred) only: channel 3 of the PatchGAN's (rgb, pred) input) */
+int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c0, int32_t c,
                     float scale, const float* dev_scale, float* dst, void* stream);
 /* SatCLIP injection backward: adjoint of the bilinear resize (128x128 -> HxW) then of fc:
  * dfc_w[16384][256] = (scale * A^T de_map)^T embeds, dfc_b[16384].  de128_scratch: [B][16384] floats. */
@@ -243,19 +244,15 @@ int ng_linear(const float* x, const float* w, const float* bias, int32_t B, int3
 int ng_lsgan_loss(const float* p, int64_t n, float target, float* loss, int32_t accumulate, float* grad,
                   float gscale, void* stream);
 
-/* fused generator pixel losses on NCHW fp32 planes: out[0]=L1, out[1]=NDVI, out[2]=NDWI, out[3]=EVI (means);
- * dpred (optional) = d( w[0]*L1 + w[1]*NDVI + w[2]*NDWI + w[3]*EVI ) / dpred.  scratch: >= 4*1024 floats. */
-int ng_g_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
-                      const float* weights4, float* out4, float* dpred, float* scratch, void* stream);
-
 /* Every term of RemoteSensingIndices (utils/remote_sensing_indices.py:84-319) plus the pix2pix L1 term in one pass over
  * NCHW fp32 planes.  Term order (= the reference's iteration order, :45-52): 0 L1(pred, nir), 1 NDVI, 2 NDWI, 3 GNDVI,
  * 4 SAVI, 5 MSAVI, 6 EVI; out8[k] = mean criterion of term k for the terms selected by bit k of `mask` (0 otherwise;
  * out8 has room for 8 floats).  criterion 0 = l1, 1 = l2 (F.mse_loss) for the six indices.  dpred (optional) =
- * d( sum_k weights7[k] * term_k ) / dpred.  scratch: >= 8*1024 floats. */
+ * d( sum_k w[k] * term_k ) / dpred with w = weights7_dev (7 floats on the device: the upstream gradient of every term as
+ * autograd delivers it) when given, else the host array weights7.  scratch: >= 8*1024 floats. */
 int ng_rs_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
-                       const float* weights7, int32_t criterion, int32_t mask, float* out8, float* dpred,
-                       float* scratch, void* stream);
+                       const float* weights7, const float* weights7_dev, int32_t criterion, int32_t mask, float* out8,
+                       float* dpred, float* scratch, void* stream);
 /* 'index' mode: the index maps of the target and of the prediction (which = 1..6 as above); loss_eps != 0 keeps the
  * loss-mode epsilons, 0 gives the index-mode formulas (remote_sensing_indices.py:101,137,304-316) */
 int ng_rs_index(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW, int32_t which,
@@ -265,13 +262,14 @@ int ng_rs_index(const float* rgb, const float* nir, const float* pred, int32_t B
 int ng_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, int32_t step, float grad_scale, void* stream);
 
-/* Multi-tensor Adam: one launch for every parameter of an optimizer.  params_dev / offsets_dev: device arrays of
- * `ntensors` parameter pointers and their element offsets into the flat gradient / moment arenas g, m, v (`total`
- * elements).  step_counter_dev: device int32 holding the number of updates applied so far (advanced here, used for the
+/* Multi-tensor Adam: one launch for every parameter of an optimizer.  params_dev / offsets_dev / numel_dev: device
+ * arrays of `ntensors` parameter pointers, their element offsets into the flat gradient / moment arenas g, m, v (`total`
+ * elements, slots may be padded for alignment) and their element counts (arena elements at or beyond a tensor's count are
+ * padding and are never written through).  step_counter_dev: device int32 holding the number of updates applied so far (advanced here, used for the
  * bias corrections).  skip_flag (device, optional): a non-zero value makes the whole call a no-op (see
  * ng_nonfinite_flag) -- torch.cuda.amp-style step skipping without a host round trip. */
-int ng_adam_multi(void* const* params_dev, const int64_t* offsets_dev, int32_t ntensors, const float* g, float* m,
-                  float* v, int64_t total, float lr, float beta1, float beta2, float eps, int32_t* step_counter_dev,
+int ng_adam_multi(void* const* params_dev, const int64_t* offsets_dev, const int64_t* numel_dev, int32_t ntensors,
+                  const float* g, float* m, float* v, int64_t total, float lr, float beta1, float beta2, float eps, int32_t* step_counter_dev,
                   float grad_scale, const int32_t* skip_flag, void* stream);
 /* flag[0] = 1 if any of the n floats is inf or NaN, else 0 */
 int ng_nonfinite_flag(const float* x, int64_t n, int32_t* flag, void* stream);

@@ -21,6 +21,7 @@ HALO_ZERO, HALO_REFLECT = 0, 1
 INJECT_NONE, INJECT_ADD, INJECT_MUL_SCALED, INJECT_MUL = 0, 1, 2, 3
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+ABI_VERSION = 101          # NG_VERSION of include/nirgan_b200.h this binding was written against
 
 
 class ConvArgs(C.Structure):
@@ -42,11 +43,12 @@ _SIGNATURES = {
     "ng_conv2d_wgrad_workspace_bytes": (c_i64, [C.POINTER(ConvArgs)]),
     "ng_conv2d_wgrad": (c_i32, [C.POINTER(ConvArgs), c_vp, c_vp, c_vp, c_i64, c_vp]),
     "ng_pack_weight": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    "ng_unpack_weight_grad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ng_unpack_weight_grad": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_f32, c_vp,
+                                      c_vp]),
     "ng_pack_weight_phasemerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_prep_stem": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_pack_weight_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    "ng_unpack_weight_grad_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ng_unpack_weight_grad_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_f32, c_vp, c_vp]),
     "ng_tap_gather": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ng_tap_scatter": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp,
                                c_vp]),
@@ -61,7 +63,7 @@ _SIGNATURES = {
                           c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ng_grad_scale_pow2": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_vp]),
     "ng_head_bwd_prep": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_i32, c_vp, c_vp]),
-    "ng_grad_to_nchw": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ng_grad_to_nchw": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
     "ng_inject_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ng_resize_plane": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_hist_match_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),
@@ -75,11 +77,10 @@ _SIGNATURES = {
     "ng_satclip_encode": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, C.c_double, C.c_double, c_vp, c_vp]),
     "ng_linear": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_lsgan_loss": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_i32, c_vp, c_f32, c_vp]),
-    "ng_g_pixel_losses": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "ng_rs_pixel_losses": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ng_rs_pixel_losses": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "ng_rs_index": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
-    "ng_adam_multi": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_vp, c_f32, c_vp,
-                              c_vp]),
+    "ng_adam_multi": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_vp, c_f32,
+                              c_vp, c_vp]),
     "ng_nonfinite_flag": (c_i32, [c_vp, c_i64, c_vp, c_vp]),
     "ng_adam_step": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_vp]),
 }
@@ -102,6 +103,10 @@ def load():
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype, fn.argtypes = res, args
+    got = lib.ng_version()
+    if got != ABI_VERSION:
+        raise RuntimeError(f"nirgan_b200: {LIB_PATH} reports C-ABI version {got}, this binding needs {ABI_VERSION}: "
+                           f"rebuild it (nir-gan_b200/csrc/build.sh)")
     _lib = lib
     return lib
 

@@ -17,18 +17,24 @@ def _needs_grad(module, *tensors) -> bool:
     return any(p.requires_grad for p in module.parameters())
 
 
-def generator_apply(module, runner, x, embeds, wrap_pad):
+def generator_apply(module, runner, x, embeds, wrap_pad, reuse_token=None):
     if _needs_grad(module, x, embeds):
         from .train import GeneratorFunction
-        return GeneratorFunction.run(module, runner, x, embeds, wrap_pad)
+        out = GeneratorFunction.run(module, runner, x, embeds, wrap_pad, reuse_token)
+        if getattr(module, "post_correction", False):
+            # model/generator_inject.py:133-134: a learnable scalar after the tanh head; torch autograd differentiates
+            # this one multiply (d/d(param) = sum(dout * tanh), d/d(tanh) = dout * param) around the compiled plans
+            out = out * module.post_correction_param
+        return out
     return runner.forward(x, embeds, wrap_pad)
 
 
-def discriminator_apply(module, runner, x):
-    if _needs_grad(module, x):
+def discriminator_apply(module, runner, parts):
+    tensors = [t for part in parts for t in part if t is not None]
+    if _needs_grad(module, *tensors):
         from .train import DiscriminatorFunction
-        return DiscriminatorFunction.run(module, runner, x)
-    return runner.forward(x)
+        return DiscriminatorFunction.run(module, runner, parts)
+    return runner.forward(parts)
 
 
 def lsgan_apply(pred, target: float):

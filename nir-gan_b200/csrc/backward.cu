@@ -430,7 +430,7 @@ tap_scatter_kernel(const float* __restrict__ dout, const float* __restrict__ out
 // NHWC (cpad channels, T, scaled) -> NCHW fp32 (c channels), dst = src * scale
 template <typename T>
 __global__ void __launch_bounds__(256)
-grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, int c, float scale,
+grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, int c0, int c, float scale,
                     const float* __restrict__ dev_scale, float* __restrict__ dst) {
   const long long total = (long long)B * c * H * W;
   if (dev_scale) scale *= dev_scale[0];
@@ -438,7 +438,7 @@ grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, in
        i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % W), y = (int)((i / W) % H);
     const int ch = (int)((i / ((long long)W * H)) % c), n = (int)(i / ((long long)W * H * c));
-    dst[i] = to_f32<T>(src[(((size_t)n * H + y) * W + x) * cpad + ch]) * scale;
+    dst[i] = to_f32<T>(src[(((size_t)n * H + y) * W + x) * cpad + c0 + ch]) * scale;
   }
 }
 
@@ -709,12 +709,12 @@ extern "C" int ng_tap_scatter(const float* dout, const float* out, int32_t B, in
   return NG_OK;
 }
 
-extern "C" int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c,
-                               float scale, const float* dev_scale, float* dst, void* stream) {
+extern "C" int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c0,
+                               int32_t c, float scale, const float* dev_scale, float* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
-  NG_REQUIRE(src && dst && c <= c_pad, NG_E_ARG, "grad_to_nchw: bad arguments");
+  NG_REQUIRE(src && dst && c0 >= 0 && c > 0 && c0 + c <= c_pad, NG_E_ARG, "grad_to_nchw: bad arguments");
   DISPATCH_T(dtype, (grad_to_nchw_kernel<T><<<grid_cap((long long)B * c * H * W), 256, 0, (cudaStream_t)stream>>>(
-                        (const T*)src, B, H, W, c_pad, c, scale, dev_scale, dst)));
+                        (const T*)src, B, H, W, c_pad, c0, c, scale, dev_scale, dst)));
   NG_LAUNCH_CHECK("grad_to_nchw_kernel");
   return NG_OK;
 }

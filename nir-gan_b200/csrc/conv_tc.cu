@@ -477,6 +477,61 @@ int get_tensor_map_encoder(PFN_cuTensorMapEncodeTiled_v12000* out) {
 
 static int get_encode() { return get_tensor_map_encoder(nullptr); }
 
+int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
+struct TmapKey {
+  uint64_t base;
+  uint64_t dims[4], strides[3];
+  uint32_t box[4], estr[4];
+  uint32_t dt, rank, sw, promo;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+
+int cached_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle sw,
+                      CUtensorMapL2promotion promo, int* cres) {
+  *cres = 0;
+  int r = get_encode();
+  if (r) return r;
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.base = (uint64_t)(uintptr_t)base;
+  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.estr[i] = estr[i]; }
+  for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
+  k.dt = (uint32_t)dt; k.rank = (uint32_t)rank; k.sw = (uint32_t)sw; k.promo = (uint32_t)promo;
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmaps.find(k);
+    if (it != g_tmaps.end()) { *out = it->second; return NG_OK; }
+  }
+  CUtensorMap tm;
+  CUresult cr = g_encode(&tm, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) { *cres = (int)cr; return NG_E_DRIVER; }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmaps.size() > 16384) g_tmaps.clear();      // bounded: descriptors are cheap to rebuild
+    g_tmaps.emplace(k, tm);
+  }
+  *out = tm;
+  return NG_OK;
+}
+
 static void choose_patch(int VH, int VW, int S, int& BH, int& BW) {
   long long best = -1;
   BH = 1; BW = 1;
@@ -494,8 +549,7 @@ static void choose_patch(int VH, int VW, int S, int& BH, int& BW) {
 // Row-tap eligibility: K x 1 stride-1 correlation over 64 stored channels into 64 output channels whose taps are
 // consecutive rows at one column offset (the row-merged generator stem), image at least one patch wide.
 static bool row_tap_ok(const ng_conv_args& a, const ConvGeom& g) {
-  static int env = -1;
-  if (env < 0) { const char* v = getenv("NIRGAN_B200_ROWTAP"); env = v ? atoi(v) : 1; }
+  static const int env = [] { const char* v = getenv("NIRGAN_B200_ROWTAP"); return v ? atoi(v) : 1; }();   // C++11 magic static: thread-safe
   if (!env) return false;
   if (a.form != NG_FORM_GATHER || a.sgn != 1 || a.stride != 1 || a.KW != 1 || a.KH != RT_KH) return false;
   if (a.Cin != 64 || a.Cout != 64 || a.epilogue == NG_EPI_HEAD || g.ntaps != RT_KH) return false;
@@ -551,10 +605,10 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(p.BW * g.S), (cuuint32_t)(p.BH * g.S), 1};
     if (RT) box[2] = (cuuint32_t)(RT_BH + RT_KH - 1);       // the haloed patch: every tap's rows in one box
     cuuint32_t estr[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
-    CUresult cr = g_encode(&tmA, dt, 4, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "cuTensorMapEncodeTiled(A) failed: %d (dims %d %d %d %d box %d %d %d)",
-               (int)cr, g.Cin, g.Wb, g.Hb, g.B, KC, p.BW * g.S, p.BH * g.S);
+    int cr = 0;
+    const int er = cached_tensor_map(&tmA, dt, 4, a.x, dims, strides, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, &cr);
+    NG_REQUIRE(er == NG_OK, NG_E_DRIVER, "cuTensorMapEncodeTiled(A) failed: %d (dims %d %d %d %d box %d %d %d)",
+               cr, g.Cin, g.Wb, g.Hb, g.B, KC, p.BW * g.S, p.BH * g.S);
   }
   {
     const int taps_total = g.merged ? g.ntaps : a.KH * a.KW;
@@ -562,17 +616,19 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
     cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
     cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(BN / CS)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult cr = g_encode(&tmB, dt, 2, const_cast<void*>(a.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "cuTensorMapEncodeTiled(B) failed: %d", (int)cr);
+    int cr = 0;
+    const int er = cached_tensor_map(&tmB, dt, 2, a.w, dims, strides, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, &cr);
+    NG_REQUIRE(er == NG_OK, NG_E_DRIVER, "cuTensorMapEncodeTiled(B) failed: %d", cr);
   }
-  static bool attr_set = false;   // per instantiation
-  static int max_ctas = 0;
-  if (!attr_set) {
+  // per instantiation AND per device (kernel attributes and the SM count belong to a device); thread-safe
+  static PerDeviceOnce once;
+  static int max_ctas_dev[64];
+  const int dev = current_device();
+  if (once.needed(dev)) {
     int e = check_cuda(cudaFuncSetAttribute(conv_tc_kernel<BN, KC, CS, RT, EGW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES), "cudaFuncSetAttribute(conv_tc)");
     if (e) return e;
-    max_ctas = num_sms() / CS * CS;
+    int max_ctas = num_sms() / CS * CS;
     if (CS > 1) {
       cudaLaunchConfig_t qc = {};
       qc.gridDim = dim3(max_ctas); qc.blockDim = dim3(Cfg::THREADS); qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -585,8 +641,10 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
           ncl * CS < max_ctas)
         max_ctas = ncl * CS;      // persistent kernel: every cluster must be co-resident
     }
-    attr_set = true;
+    __atomic_store_n(&max_ctas_dev[dev & 63], max_ctas, __ATOMIC_RELEASE);
+    once.done(dev);
   }
+  const int max_ctas = __atomic_load_n(&max_ctas_dev[dev & 63], __ATOMIC_ACQUIRE);
   long long want = (long long)p.total_groups * CS;
   const int grid = (int)(want < max_ctas ? want : max_ctas);
   cudaLaunchConfig_t cfg = {};
@@ -602,12 +660,12 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
 }
 
 static int cluster_size_for(int bn, int kc) {
-  static int env = -1;
-  if (env < 0) {
+  // measured on B200: multicast does not shorten the kernel (not L2-bound); kept as a switch
+  static const int env = [] {
     const char* v = getenv("NIRGAN_B200_CLUSTER");
-    env = v ? atoi(v) : 1;      // measured on B200: multicast does not shorten the kernel (not L2-bound); kept as a switch
-    if (env != 1 && env != 2 && env != 4) env = 1;
-  }
+    const int e = v ? atoi(v) : 1;
+    return (e == 2 || e == 4) ? e : 1;
+  }();
   return (bn == 256 && kc == 64) ? env : 1;     // multicast pays on the weight-heavy 256-wide tiles
 }
 
@@ -642,8 +700,7 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   if (bn == 64 && kc == 16) return launch_tc<64, 16, 1>(a, g, st);
   if (bn == 128 && kc == 16) return launch_tc<128, 16, 1>(a, g, st);
   if (bn == 256 && kc == 16) return launch_tc<256, 16, 1>(a, g, st);
-  static int wide_env = -1;
-  if (wide_env < 0) { const char* v = getenv("NIRGAN_B200_EPI4"); wide_env = v ? atoi(v) : 2; }
+  static const int wide_env = [] { const char* v = getenv("NIRGAN_B200_EPI4"); return v ? atoi(v) : 2; }();
   // 64-wide tiles have two drain passes; with four epilogue groups two tiles (both accumulator buffers) drain at once
   if (bn == 64 && kc == 64 && row_tap_ok(a, g))
     return wide_env >= 2 ? launch_tc<64, 64, 1, true, 4>(a, g, st) : launch_tc<64, 64, 1, true>(a, g, st);

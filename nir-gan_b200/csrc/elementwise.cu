@@ -44,7 +44,7 @@ __global__ void pack_phasemerged_kernel(const float* __restrict__ src, int Cin, 
 }
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int d0, int d1, int taps, int n_axis,
-                                    int n_pad, int k_pad, float scale, const float* __restrict__ dev_scale,
+                                    int n_pad, int k_pad, float scale, const float* __restrict__ dev_scale, float beta,
                                     float* __restrict__ dst) {
   const long long total = (long long)d0 * d1 * taps;
   if (dev_scale) scale *= dev_scale[0];
@@ -54,7 +54,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, int d0, in
     const int a1 = (int)((i / taps) % d1);
     const int a0 = (int)(i / ((long long)taps * d1));
     const int n = n_axis == 0 ? a0 : a1, k = n_axis == 0 ? a1 : a0;
-    dst[i] = scale * packed[((long long)tp * n_pad + n) * k_pad + k];
+    const float v = scale * packed[((long long)tp * n_pad + n) * k_pad + k];
+    dst[i] = beta != 0.f ? fmaf(beta, dst[i], v) : v;
   }
 }
 
@@ -413,67 +414,6 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nb
   out[j] = accumulate ? out[j] + v : v;
 }
 
-// fused L1 + NDVI + NDWI + EVI (loss mode, eps 1e-6, criterion l1) forward and d/dpred.
-// utils/remote_sensing_indices.py:104-110,140-148,296-310; model/pix2pix.py:222.
-__global__ void __launch_bounds__(256)
-g_pixel_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ nir, const float* __restrict__ pred,
-                    int B, int HW, float w0, float w1, float w2, float w3, float inv_n, float* __restrict__ partial,
-                    float* __restrict__ dpred) {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  const long long total = (long long)B * HW;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i / HW), q = (int)(i % HW);
-    const float R = rgb[((size_t)n * 3 + 0) * HW + q], G = rgb[((size_t)n * 3 + 1) * HW + q],
-                Bl = rgb[((size_t)n * 3 + 2) * HW + q];
-    const float t = nir[i], p = pred[i];
-    const float eps = 1e-6f;
-    // L1
-    const float d0 = p - t;
-    s0 += fabsf(d0);
-    float g = w0 * (d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f));
-    // NDVI: (n-R)/(n+R+eps); d/dp = (2R+eps)/(p+R+eps)^2
-    {
-      const float it = (t - R) / (t + R + eps), dp = p + R + eps, ip = (p - R) / dp;
-      const float df = it - ip;
-      s1 += fabsf(df);
-      const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
-      g += w1 * (-sg) * ((2.f * R + eps) / (dp * dp));
-    }
-    // NDWI with green
-    {
-      const float it = (t - G) / (t + G + eps), dp = p + G + eps, ip = (p - G) / dp;
-      const float df = it - ip;
-      s2 += fabsf(df);
-      const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
-      g += w2 * (-sg) * ((2.f * G + eps) / (dp * dp));
-    }
-    // EVI: 2.5*(n-R)/((n+6)*(R-7.5)*(B+1)+eps);  with k=(R-7.5)(B+1): d/dp = 2.5*(k*(6+R)+eps)/den^2
-    {
-      const float k = (R - 7.5f) * (Bl + 1.f);
-      const float dt = (t + 6.f) * k + eps, dp = (p + 6.f) * k + eps;
-      const float it = 2.5f * ((t - R) / dt), ip = 2.5f * ((p - R) / dp);
-      const float df = it - ip;
-      s3 += fabsf(df);
-      const float sg = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
-      g += w3 * (-sg) * (2.5f * (k * (6.f + R) + eps) / (dp * dp));
-    }
-    if (dpred) dpred[i] = g * inv_n;
-  }
-  __shared__ float red[4][8];
-  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1;
-    red[2][threadIdx.x >> 5] = s2; red[3][threadIdx.x >> 5] = s3;
-  }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    float tsum = 0.f;
-    for (int i = 0; i < 8; ++i) tsum += red[threadIdx.x][i];
-    partial[(size_t)blockIdx.x * 4 + threadIdx.x] = tsum;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // All of RemoteSensingIndices (utils/remote_sensing_indices.py:84-319) + the pix2pix L1 term in one pass.
 // term order: 0 = L1(pred, nir), 1 = NDVI, 2 = NDWI, 3 = GNDVI, 4 = SAVI, 5 = MSAVI, 6 = EVI (the reference's iteration
@@ -515,8 +455,12 @@ struct RsWeights { float w[7]; };
 
 __global__ void __launch_bounds__(256)
 rs_pixel_loss_kernel(const float* __restrict__ rgb, const float* __restrict__ nir, const float* __restrict__ pred,
-                     int B, int HW, RsWeights wt, int criterion, int mask, float inv_n, float* __restrict__ partial,
-                     float* __restrict__ dpred) {
+                     int B, int HW, RsWeights wt, const float* __restrict__ wdev, int criterion, int mask, float inv_n,
+                     float* __restrict__ partial, float* __restrict__ dpred) {
+  if (wdev) {                 // weights known only on the device (autograd's upstream gradient per term)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) wt.w[k] = wdev[k];
+  }
   float acc[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) acc[k] = 0.f;
@@ -610,8 +554,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // pointers + element offsets into the arena), so one launch updates every parameter of an optimizer.  `skip` (device
 // flag, e.g. "a gradient is not finite") turns the launch into a no-op without a host round trip.
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(float* const* __restrict__ params, const long long* __restrict__ offsets, int ntensors,
-                  const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long total, float lr,
+adam_multi_kernel(float* const* __restrict__ params, const long long* __restrict__ offsets,
+                  const long long* __restrict__ numel, int ntensors, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long total, float lr,
                   float b1, float b2, float eps, float gscale, const int* __restrict__ step_dev,
                   const int* __restrict__ skip) {
   if (skip && *skip) return;
@@ -622,7 +566,9 @@ adam_multi_kernel(float* const* __restrict__ params, const long long* __restrict
        i += (long long)gridDim.x * blockDim.x) {
     int lo = 0, hi = ntensors - 1;                       // last tensor whose offset <= i
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (offsets[mid] <= i) lo = mid; else hi = mid - 1; }
-    float* p = params[lo] + (i - offsets[lo]);
+    const long long j = i - offsets[lo];
+    if (j >= numel[lo]) continue;                        // alignment padding between arena slots: no parameter behind it
+    float* p = params[lo] + j;
     const float gi = g[i] * gscale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
@@ -697,12 +643,13 @@ __global__ void pack_rowmerged_kernel(const float* __restrict__ src, int O, int 
 }
 
 __global__ void unpack_rowmerged_kernel(const float* __restrict__ packed, int O, int I, int KH, int KW, float scale,
-                                        const float* __restrict__ dev_scale, float* __restrict__ dst) {
+                                        const float* __restrict__ dev_scale, float beta, float* __restrict__ dst) {
   const int total = O * I * KH * KW;
   if (dev_scale) scale *= dev_scale[0];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int kw = i % KW, kh = (i / KW) % KH, c = (i / (KW * KH)) % I, o = i / (KW * KH * I);
-    dst[i] = scale * packed[((long long)kh * O + o) * 64 + kw * 8 + c];
+    const float v = scale * packed[((long long)kh * O + o) * 64 + kw * 8 + c];
+    dst[i] = beta != 0.f ? fmaf(beta, dst[i], v) : v;
   }
 }
 
@@ -821,12 +768,12 @@ extern "C" int ng_pack_weight_phasemerged(const float* src, int32_t Cin, int32_t
 
 extern "C" int ng_unpack_weight_grad(const float* packed, int32_t d0, int32_t d1, int32_t KH, int32_t KW,
                                      int32_t n_axis, int32_t n_pad, int32_t k_pad, float scale,
-                                     const float* dev_scale, float* dst, void* stream) {
+                                     const float* dev_scale, float beta, float* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(packed && dst && (n_axis == 0 || n_axis == 1), NG_E_ARG, "unpack_weight_grad: bad arguments");
   const long long total = (long long)d0 * d1 * KH * KW;
   unpack_wgrad_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, d0, d1, KH * KW, n_axis, n_pad,
-                                                                             k_pad, scale, dev_scale, dst);
+                                                                             k_pad, scale, dev_scale, beta, dst);
   NG_LAUNCH_CHECK("unpack_wgrad_kernel");
   return NG_OK;
 }
@@ -916,7 +863,7 @@ extern "C" int ng_linear(const float* x, const float* w, const float* bias, int3
   return NG_OK;
 }
 
-// scratch for the two-stage reductions lives in caller memory for ng_g_pixel_losses; lsgan maps are tiny
+// scratch for the two-stage reductions lives in caller memory for ng_rs_pixel_losses; lsgan maps are tiny
 // (B*30*30) so a single block suffices and needs no scratch.
 extern "C" int ng_lsgan_loss(const float* p, int64_t n, float target, float* loss, int32_t accumulate, float* grad,
                              float gscale, void* stream) {
@@ -933,34 +880,18 @@ extern "C" int ng_lsgan_loss(const float* p, int64_t n, float target, float* los
   return NG_OK;
 }
 
-extern "C" int ng_g_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
-                                 const float* weights4, float* out4, float* dpred, float* scratch, void* stream) {
-  int r = require_sm100(); if (r) return r;
-  NG_REQUIRE(rgb && nir && pred && out4 && scratch && weights4, NG_E_ARG, "g_pixel_losses: bad arguments");
-  const long long total = (long long)B * HW;
-  unsigned blocks = grid_for(total, 256);
-  if (blocks > 1024) blocks = 1024;
-  g_pixel_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, nir, pred, B, HW, weights4[0], weights4[1],
-                                                               weights4[2], weights4[3], 1.0f / (float)total, scratch,
-                                                               dpred);
-  NG_LAUNCH_CHECK("g_pixel_loss_kernel");
-  reduce_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, (int)blocks, 4, 1.0f / (float)total, out4, 0);
-  NG_LAUNCH_CHECK("reduce_partials_kernel");
-  return NG_OK;
-}
-
 extern "C" int ng_rs_pixel_losses(const float* rgb, const float* nir, const float* pred, int32_t B, int32_t HW,
-                                  const float* weights7, int32_t criterion, int32_t mask, float* out7, float* dpred,
-                                  float* scratch, void* stream) {
+                                  const float* weights7, const float* weights7_dev, int32_t criterion, int32_t mask,
+                                  float* out7, float* dpred, float* scratch, void* stream) {
   int r = require_sm100(); if (r) return r;
-  NG_REQUIRE(rgb && nir && pred && out7 && scratch && weights7, NG_E_ARG, "rs_pixel_losses: bad arguments");
+  NG_REQUIRE(rgb && nir && pred && out7 && scratch && (weights7 || weights7_dev), NG_E_ARG, "rs_pixel_losses: bad arguments");
   NG_REQUIRE((criterion == 0 || criterion == 1) && mask > 0 && mask < 128, NG_E_ARG, "rs_pixel_losses: bad criterion / mask");
   const long long total = (long long)B * HW;
   unsigned blocks = grid_for(total, 256);
   if (blocks > 1024) blocks = 1024;
   RsWeights wt;
-  for (int k = 0; k < 7; ++k) wt.w[k] = weights7[k];
-  rs_pixel_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, nir, pred, B, HW, wt, criterion, mask,
+  for (int k = 0; k < 7; ++k) wt.w[k] = weights7 ? weights7[k] : 0.f;
+  rs_pixel_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rgb, nir, pred, B, HW, wt, weights7_dev, criterion, mask,
                                                                 1.0f / (float)total, scratch, dpred);
   NG_LAUNCH_CHECK("rs_pixel_loss_kernel");
   reduce_partials_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, (int)blocks, 8, 1.0f / (float)total, out7, 0);
@@ -989,16 +920,17 @@ extern "C" int ng_adam_step(float* p, const float* g, float* m, float* v, int64_
   return NG_OK;
 }
 
-extern "C" int ng_adam_multi(void* const* params_dev, const int64_t* offsets_dev, int32_t ntensors, const float* g,
-                             float* m, float* v, int64_t total, float lr, float beta1, float beta2, float eps,
+extern "C" int ng_adam_multi(void* const* params_dev, const int64_t* offsets_dev, const int64_t* numel_dev,
+                             int32_t ntensors, const float* g, float* m, float* v, int64_t total, float lr, float beta1, float beta2, float eps,
                              int32_t* step_counter_dev, float grad_scale, const int32_t* skip_flag, void* stream) {
   int r = require_sm100(); if (r) return r;
-  NG_REQUIRE(params_dev && offsets_dev && g && m && v && step_counter_dev && ntensors > 0 && total > 0, NG_E_ARG,
+  NG_REQUIRE(params_dev && offsets_dev && numel_dev && g && m && v && step_counter_dev && ntensors > 0 && total > 0, NG_E_ARG,
              "adam_multi: bad arguments");
   adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter_dev, skip_flag);
   NG_LAUNCH_CHECK("adam_advance_kernel");
   adam_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<float* const*>(params_dev), reinterpret_cast<const long long*>(offsets_dev), ntensors, g, m, v,
+      reinterpret_cast<float* const*>(params_dev), reinterpret_cast<const long long*>(offsets_dev),
+      reinterpret_cast<const long long*>(numel_dev), ntensors, g, m, v,
       (long long)total, lr, beta1, beta2, eps, grad_scale, step_counter_dev, skip_flag);
   NG_LAUNCH_CHECK("adam_multi_kernel");
   return NG_OK;
@@ -1087,11 +1019,12 @@ extern "C" int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, 
 }
 
 extern "C" int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW,
-                                               float scale, const float* dev_scale, float* dst, void* stream) {
+                                               float scale, const float* dev_scale, float beta, float* dst,
+                                               void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(packed && dst && I > 0 && I <= 8 && KW > 0 && KW <= 8, NG_E_ARG, "unpack_weight_grad_rowmerged: bad arguments");
   unpack_rowmerged_kernel<<<grid_for((long long)O * I * KH * KW, 256), 256, 0, (cudaStream_t)stream>>>(packed, O, I, KH,
-                                                                                                      KW, scale, dev_scale, dst);
+                                                                                                      KW, scale, dev_scale, beta, dst);
   NG_LAUNCH_CHECK("unpack_rowmerged_kernel");
   return NG_OK;
 }

@@ -196,4 +196,22 @@ __device__ __forceinline__ uint64_t make_mnmajor_desc_sw32(uint32_t saddr, uint3
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
 int get_tensor_map_encoder(PFN_cuTensorMapEncodeTiled_v12000* fn);
 
+// Tiled tensor map for (pointer, geometry), encoded once and then served from a process-wide cache (mutex-protected;
+// keyed by every encode argument).  The static plans of the host engine call every kernel with the same buffers step
+// after step, so after the first step no launch pays for cuTensorMapEncodeTiled again.  Returns a CUresult-like code
+// (0 = ok) in *cres and NG_OK / NG_E_DRIVER.
+int cached_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle sw,
+                      CUtensorMapL2promotion promo, int* cres);
+
+// One-time, per-device kernel attribute setup (thread-safe): returns true when the calling thread should run the setup
+// for `dev` (first caller) -- the setup itself is idempotent, so a benign race between two first callers is harmless --
+// and marks it done via attr_done().
+struct PerDeviceOnce {
+  unsigned long long mask = 0ull;
+  bool needed(int dev) const { return ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull) == 0ull; }
+  void done(int dev) { __atomic_fetch_or(&mask, 1ull << (dev & 63), __ATOMIC_RELEASE); }
+};
+int current_device();
+
 }  // namespace ng

@@ -362,9 +362,6 @@ template <int BN, int NT>
 static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPlan& w, float* dw, void* workspace,
                            cudaStream_t st) {
   using Cfg = WgCfg<BN, NT>;
-  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-  int r = get_tensor_map_encoder(&encode);
-  if (r) return r;
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.g = g;
@@ -382,27 +379,29 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
                              (cuuint64_t)g.Hout * g.Wout * g.Cout * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(w.BW * g.OS), (cuuint32_t)(w.BH * g.OS), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)g.OS, (cuuint32_t)g.OS, 1};
-    CUresult cr = encode(&tmY, dt, 4, const_cast<void*>(a.y), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "wgrad_tc: cuTensorMapEncodeTiled(dY) failed: %d", (int)cr);
+    int cr = 0;
+    const int er = cached_tensor_map(&tmY, dt, 4, a.y, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, &cr);
+    NG_REQUIRE(er == NG_OK, NG_E_DRIVER, "wgrad_tc: cuTensorMapEncodeTiled(dY) failed: %d", cr);
   }
   {
     cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wb, (cuuint64_t)g.Hb, (cuuint64_t)g.B};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Wb * g.Cin * 2, (cuuint64_t)g.Hb * g.Wb * g.Cin * 2};
     cuuint32_t box[4] = {(cuuint32_t)(BN >= 64 ? 64 : BN), (cuuint32_t)(w.BW * g.S), (cuuint32_t)(w.BH * g.S), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
-    CUresult cr = encode(&tmX, dt, 4, const_cast<void*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         BN >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    NG_REQUIRE(cr == CUDA_SUCCESS, NG_E_DRIVER, "wgrad_tc: cuTensorMapEncodeTiled(X) failed: %d", (int)cr);
+    int cr = 0;
+    const int er = cached_tensor_map(&tmX, dt, 4, a.x, dims, strides, box, estr,
+                                     BN >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, &cr);
+    NG_REQUIRE(er == NG_OK, NG_E_DRIVER, "wgrad_tc: cuTensorMapEncodeTiled(X) failed: %d", cr);
   }
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
+  static PerDeviceOnce once;      // per instantiation and per device; thread-safe
+  const int dev = current_device();
+  if (once.needed(dev)) {
     int e = check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES), "cudaFuncSetAttribute(wgrad_tc)");
     if (e) return e;
-    attr_set = true;
+    once.done(dev);
   }
   const int sms = num_sms();
   const int grid = p.total_units < sms ? p.total_units : sms;

@@ -89,6 +89,110 @@ class Buffers:
     def bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._b.values())
 
+    def drop(self, tags) -> None:
+        """Forget every buffer whose name starts with one of `tags` + '.' (the buffers of an evicted plan)."""
+        tags = tuple(t + "." for t in tags)
+        if not tags:
+            return
+        for k in [k for k in self._b if k[0].startswith(tags)]:
+            del self._b[k]
+
+
+class Pool:
+    """One device allocation that the training contexts of a runner carve their buffers from.  Contexts of different
+    input shapes (mixed resolutions, BASELINE config 5) are never in flight at the same time -- a step's forward and
+    backward complete before the next step's forward starts -- so each context bump-allocates from offset 0 and they all
+    alias the same memory: the footprint is that of the LARGEST shape, not the sum over shapes."""
+
+    def __init__(self, nbytes: int, device):
+        self.capacity = int(nbytes)
+        self.t = torch.empty(self.capacity, dtype=torch.uint8, device=device)
+        self.owner = None          # the context whose activations currently live in the pool
+        self.live = None           # the context whose forward is waiting for its backward
+
+
+class PoolTooSmall(RuntimeError):
+    pass
+
+
+class PoolBuffers:
+    """``Buffers`` interface over a ``Pool``: named buffers of ONE context, 256-byte aligned, allocated in request order.
+    Buffers that must keep their contents between steps of other shapes (zero-initialised counters) live outside."""
+
+    ALIGN = 256
+
+    def __init__(self, pool: Pool, device):
+        self.pool, self.device = pool, device
+        self.off = 0
+        self._b: Dict[Tuple, torch.Tensor] = {}
+        self._own: Dict[Tuple, torch.Tensor] = {}
+
+    def get(self, name: str, numel: int, dtype: torch.dtype, zero: bool = False) -> torch.Tensor:
+        key = (name, numel, dtype)
+        t = self._b.get(key)
+        if t is not None:
+            return t
+        if zero:
+            t = self._own[key] = torch.zeros(numel, dtype=dtype, device=self.device)
+        else:
+            esz = torch.empty(0, dtype=dtype).element_size()
+            nbytes = (numel * esz + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            if self.off + nbytes > self.pool.capacity:
+                raise PoolTooSmall(f"pool of {self.pool.capacity} bytes exhausted at {name!r}")
+            t = self.pool.t[self.off:self.off + numel * esz].view(dtype)
+            self.off += nbytes
+        self._b[key] = t
+        return t
+
+    def bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._own.values())
+
+    def drop(self, tags) -> None:
+        pass
+
+
+class _SizedStub:
+    """Stands in for a device buffer while a context is built only to learn how much memory it needs: plan compilation
+    binds pointers and sizes but never touches buffer contents."""
+
+    def __init__(self, numel: int, dtype: torch.dtype):
+        self._n, self._esz = int(numel), torch.empty(0, dtype=dtype).element_size()
+        self.dtype = dtype
+
+    def data_ptr(self) -> int:
+        return 0x7F0000000000          # non-null, 256-byte aligned, never dereferenced
+
+    def numel(self) -> int:
+        return self._n
+
+    def element_size(self) -> int:
+        return self._esz
+
+
+class CountingBuffers:
+    """``Buffers`` interface that allocates nothing and adds up what a ``PoolBuffers`` would need."""
+
+    def __init__(self, device):
+        self.device = device
+        self._b: Dict[Tuple, _SizedStub] = {}
+        self.total = 0
+
+    def get(self, name: str, numel: int, dtype: torch.dtype, zero: bool = False):
+        key = (name, numel, dtype)
+        t = self._b.get(key)
+        if t is None:
+            t = self._b[key] = _SizedStub(numel, dtype)
+            if not zero:
+                a = PoolBuffers.ALIGN
+                self.total += (numel * t.element_size() + a - 1) // a * a
+        return t
+
+    def bytes(self) -> int:
+        return 0
+
+    def drop(self, tags) -> None:
+        pass
+
 
 class SliceBuffers:
     """View of a parent ``Buffers`` for one of ``parts`` equal batch slices: every request must name a buffer the parent
@@ -136,21 +240,28 @@ GRAPHS = [os.environ.get("NIRGAN_B200_GRAPH", "1") != "0"]
 # ops added with side=True (the weight gradients: off the critical path of a backward pass) run on a second stream so
 # that they overlap the HBM-bound norm-backward kernels of the next layer (NIRGAN_B200_SIDE_STREAM=0: single stream)
 SIDE_STREAM = [os.environ.get("NIRGAN_B200_SIDE_STREAM", "1") != "0"]
-TRAIN_GRAPHS = [os.environ.get("NIRGAN_B200_TRAIN_GRAPH", "0") == "1"]
+# training plans (forward and backward of both networks) are replayed as CUDA graphs too: the step is ~250 launches and
+# the host needs longer to enqueue them one by one than the GPU needs to run them (NIRGAN_B200_TRAIN_GRAPH=0: eager)
+TRAIN_GRAPHS = [os.environ.get("NIRGAN_B200_TRAIN_GRAPH", "1") != "0"]
+# training contexts of all input shapes share one memory pool per runner (NIRGAN_B200_POOL=0: one set of buffers per shape)
+POOL = [os.environ.get("NIRGAN_B200_POOL", "1") != "0"]
 _SIDE: Dict[int, "torch.cuda.Stream"] = {}
 
 
 class Plan:
-    """A compiled list of bound C-ABI calls."""
+    """A compiled list of bound C-ABI calls (plus optional host hooks between them)."""
 
     def __init__(self):
-        self.ops: List[Tuple[Callable, tuple]] = []
+        self.ops: List[Tuple[Callable, tuple, str]] = []
         self.keepalive: list = []
         self.launches = 0          # kernel launches per run (for bench.py's gpu_launches)
         self.records: dict = {}
         self.labels: List[str] = []
         self.side: List[bool] = []
         self._events: list = []
+        self.hook_fn: Optional[Callable] = None     # called as hook_fn(payload, main_stream, side_stream_or_None)
+        self._graphs: Optional[list] = None
+        self._graph_sig = None
 
     def add(self, fn_name: str, *args, launches: int = 1, label: str = "", side: bool = False):
         fn = getattr(L.load(), fn_name)
@@ -159,33 +270,76 @@ class Plan:
         self.side.append(bool(side))
         self.launches += launches
 
+    def add_hook(self, payload, label: str = "hook"):
+        """A host-side call-out at this point of the plan (used by the data-parallel gradient exchange: "everything the
+        plan has exported so far is final").  Side-stream work issued before the hook is flushed first and the hook is
+        handed both streams, so it can order a collective behind either.  Hooks split a graph-replayed plan into one CUDA
+        graph per segment."""
+        self.ops.append((None, payload, "hook"))
+        self.labels.append(label)
+        self.side.append(False)
+
+    def _segments(self):
+        segs, cur = [], []
+        for i, (fn, _, _) in enumerate(self.ops):
+            if fn is None:
+                segs.append(("ops", cur)); segs.append(("hook", i)); cur = []
+            else:
+                cur.append(i)
+        segs.append(("ops", cur))
+        return [s for s in segs if s[0] == "hook" or s[1]]
+
+    def _arg_signature(self):
+        """Values of the mutable ctypes scalars among the bound arguments (accumulate flags of the gradient exports):
+        a captured graph bakes them in, so a change forces eager launches for that run."""
+        sig = []
+        for fn, args, _ in self.ops:
+            if fn is None:
+                continue
+            for a in args:
+                if isinstance(a, C.c_float):
+                    sig.append(a.value)
+        return tuple(sig)
+
     def run_graphed(self, stream: "torch.cuda.Stream"):
-        """Replay the plan as one CUDA graph on `stream` (captured on the second call; the first runs eagerly so that
-        one-off host work -- kernel attributes, TMA descriptor encoder lookup -- happens outside the capture).  All
-        buffers are static and the packed weights are refreshed in place, so the captured graph stays valid."""
+        """Replay the plan as CUDA graphs on `stream` (captured on the second call; the first runs eagerly so that
+        one-off host work -- kernel attributes, TMA descriptor encoding -- happens outside the capture).  All buffers are
+        static and the packed weights are refreshed in place, so the captured graphs stay valid.  Host hooks run between
+        the graphs of the segments they separate."""
         if PROFILE[0] is not None or not GRAPHS[0]:
             return self.run(stream.cuda_stream)
-        g = getattr(self, "_graph", None)
-        if g is None:
+        if self._graphs is None:
             if not getattr(self, "_warm", False):
                 self._warm = True
                 return self.run(stream.cuda_stream)
             try:
-                g = torch.cuda.CUDAGraph()
-                # captured on torch's private capture stream (the caller's may be the legacy default stream, where
-                # capture is illegal); replay() enqueues the graph on whatever stream is current
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self.run(torch.cuda.current_stream().cuda_stream)
-                self._graph = g
+                graphs = []
+                for kind, body in self._segments():
+                    if kind == "hook":
+                        graphs.append(("hook", body))
+                        continue
+                    g = torch.cuda.CUDAGraph()
+                    # captured on torch's private capture stream (the caller's may be the legacy default stream, where
+                    # capture is illegal); replay() enqueues the graph on whatever stream is current
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        self._run_ops(body, torch.cuda.current_stream().cuda_stream)
+                    graphs.append(("graph", g))
+                self._graphs, self._graph_sig = graphs, self._arg_signature()
             except Exception as e:          # capture is an optimisation: fall back to eager launches, loudly, once
                 import warnings
                 warnings.warn(f"nirgan_b200: CUDA graph capture failed ({e}); launching kernels eagerly")
                 GRAPHS[0] = False
                 return self.run(stream.cuda_stream)
-        g.replay()
+        if self._graph_sig != self._arg_signature():
+            return self.run(stream.cuda_stream)
+        for kind, g in self._graphs:
+            if kind == "hook":
+                self._call_hook(g, stream.cuda_stream, None)
+            else:
+                g.replay()
 
     def run_training(self, device):
-        """Training plans: CUDA-graph replay when NIRGAN_B200_TRAIN_GRAPH=1 (off by default), else eager launches."""
+        """Training plans: CUDA-graph replay (NIRGAN_B200_TRAIN_GRAPH=0: eager launches)."""
         st = torch.cuda.current_stream(device)
         if TRAIN_GRAPHS[0]:
             return self.run_graphed(st)
@@ -194,47 +348,74 @@ class Plan:
     def run(self, stream_ptr: int):
         if PROFILE[0] is not None:
             return self._run_profiled(stream_ptr)
-        if SIDE_STREAM[0] and any(self.side):
-            return self._run_two_streams(stream_ptr)
-        for fn, args, name in self.ops:
+        self._run_ops(range(len(self.ops)), stream_ptr)
+
+    def _call_hook(self, i: int, stream_ptr: int, side):
+        if self.hook_fn is not None:
+            dev = torch.cuda.current_device()
+            main = torch.cuda.ExternalStream(stream_ptr, device=dev) if stream_ptr else torch.cuda.default_stream(dev)
+            self.hook_fn(self.ops[i][1], main, side)
+
+    def _run_ops(self, idx, stream_ptr: int):
+        idx = list(idx)
+        if SIDE_STREAM[0] and any(self.side[i] for i in idx):
+            return self._run_two_streams(idx, stream_ptr)
+        for i in idx:
+            fn, args, name = self.ops[i]
+            if fn is None:
+                self._call_hook(i, stream_ptr, None)
+                continue
             st = fn(*args, stream_ptr)
             if st != 0:
                 L.check(st, name)
 
-    def _run_two_streams(self, stream_ptr: int):
+    def _run_two_streams(self, idx, stream_ptr: int):
         """Side ops depend on everything issued before them on the main stream and on earlier side ops; nothing on the
-        main stream depends on them until the plan ends (they only write their own weight-gradient buffers and a
-        workspace that side ops share, serialised by the side stream).  Each side op is submitted AFTER the next main
-        op, so the main op takes the SMs first and the side op then overlaps what follows it."""
+        main stream depends on them until the plan (segment) ends (they only write their own weight-gradient buffers,
+        the gradient arena and a workspace that side ops share, serialised by the side stream).  Each side op is
+        submitted AFTER the next main op, so the main op takes the SMs first and the side op then overlaps what follows."""
         dev = torch.cuda.current_device()
         side = _SIDE.get(dev)
         if side is None:
             side = _SIDE[dev] = torch.cuda.Stream(device=dev)
         main = torch.cuda.ExternalStream(stream_ptr, device=dev) if stream_ptr else torch.cuda.default_stream(dev)
-        n_side = sum(self.side)
+        n_side = sum(1 for i in idx if self.side[i])
         while len(self._events) < n_side + 1:
             self._events.append(torch.cuda.Event())
         side_ptr = side.cuda_stream
-        pending = None
+        pending = []
         k = 0
-        for (fn, args, name), is_side in zip(self.ops, self.side):
-            if is_side:
-                if pending is not None:
-                    self._launch(pending, side_ptr)
-                ev = self._events[k]
-                k += 1
-                ev.record(main)
-                side.wait_event(ev)
-                pending = (fn, args, name)
+        last_side_main = False
+        for i in idx:
+            fn, args, name = self.ops[i]
+            if fn is None:
+                for op in pending:
+                    self._launch(op, side_ptr)
+                pending = []
+                self._call_hook(i, stream_ptr, side)
                 continue
+            if self.side[i]:
+                if not last_side_main:
+                    # a run of consecutive side ops (weight gradient + its exports) shares one fork point
+                    for op in pending:
+                        self._launch(op, side_ptr)
+                    pending = []
+                    ev = self._events[k]
+                    k += 1
+                    ev.record(main)
+                    side.wait_event(ev)
+                pending.append((fn, args, name))
+                last_side_main = True
+                continue
+            last_side_main = False
             st = fn(*args, stream_ptr)
             if st != 0:
                 L.check(st, name)
-            if pending is not None:
-                self._launch(pending, side_ptr)
-                pending = None
-        if pending is not None:
-            self._launch(pending, side_ptr)
+            for op in pending:
+                self._launch(op, side_ptr)
+            pending = []
+        for op in pending:
+            self._launch(op, side_ptr)
         ev = self._events[n_side]
         ev.record(side)
         main.wait_event(ev)
@@ -250,7 +431,10 @@ class Plan:
 def _run_profiled(self, stream_ptr: int):
     ev = torch.cuda.Event(enable_timing=True)
     ev.record()
-    for (fn, args, name), label in zip(self.ops, self.labels):
+    for i, ((fn, args, name), label) in enumerate(zip(self.ops, self.labels)):
+        if fn is None:
+            self._call_hook(i, stream_ptr, None)
+            continue
         st = fn(*args, stream_ptr)
         if st != 0:
             L.check(st, name)

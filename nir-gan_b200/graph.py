@@ -65,14 +65,20 @@ class Unit:
 
 
 class UnitGraph:
-    def __init__(self, eng: Engine, tag: str, stream: int):
-        self.eng, self.tag, self.stream = eng, tag, stream
+    def __init__(self, eng: Engine, tag: str, stream: int = 0):
+        self.eng, self.tag = eng, tag
         self.units: List[Unit] = []
         self.pre_ops = []                   # (fn_name, args, label) executed before the units (input prep, fc)
         self.records: dict = {}
         # single-output-channel 7x7 head as "tap GEMM + gather" (see ng_tap_gather / ng_tap_scatter):
         # {'conv': module, 'x': ActBuf (haloed head input), 'crop': int, 'B','H','W': output geometry}
         self.tap_head: Optional[dict] = None
+
+    @property
+    def stream(self) -> int:
+        """Weight (re-)packing runs on the stream that is current at CALL time: the plan's kernels are launched on the
+        caller's current stream too, so packing is ordered before them whichever stream the module is used from."""
+        return torch.cuda.current_stream(self.eng.device).cuda_stream
 
     # ---- construction -----------------------------------------------------------------------------
     def merged_phases(self, u: Unit) -> bool:
@@ -201,14 +207,30 @@ class UnitGraph:
             return self.eng.packed_weight(w, 0, cin, u.cout, self.stream)
         return self.eng.packed_weight(w, 1, cin, u.cout, self.stream)       # Conv2d (Cout, Cin, k, k): n = Cin
 
+    def _export(self, plan: Plan, exports: list, p: torch.nn.Parameter, fn_name: str, packed_ptr: int, dims: tuple,
+                dev_inv: Optional[int], label: str):
+        """Gradient export as part of the plan (side stream, right behind the weight gradient it unpacks): packed fp32 ->
+        the parameter's slot of the flat gradient arena in the reference layout, times the inverse of the adaptive
+        gradient scale.  The accumulate factor is a mutable ctypes cell set per backward pass (train.py): 0 = overwrite,
+        1 = add (parameter reached twice in one pass, or .grad not cleared)."""
+        slot = p._b200_grad_slot
+        beta = C.c_float(0.0)
+        plan.add(fn_name, packed_ptr, *dims, 1.0, dev_inv, beta, slot.data_ptr(), label=label, side=True)
+        exports.append((p, beta))
+
     def compile_backward(self, dout_f32: torch.Tensor, loss_scale: float, need_dw: bool, need_dx: bool,
-                         want_inject_grads: bool = False) -> Plan:
+                         want_inject_grads: bool = False, hook_units=()) -> Plan:
         """dout_f32: gradient of the fp32 single-channel output of the last (head) unit; loss_scale: 0 = none, else
         the target max |gradient| of the adaptive power-of-two scaling (fp16 mode).  Returns a plan whose
         records hold 'dw' {unit index: packed fp32 grad}, 'db' {unit index: bias grad}, 'dx' (ActBuf-shaped grad of the
-        first unit's input buffer, when need_dx)."""
+        first unit's input buffer, when need_dx), 'exports' [(parameter, accumulate cell)] for the gradients the plan
+        writes into the flat arena itself and 'zero_grads' [parameters whose gradient is identically zero].
+        hook_units: unit indices after whose export a ("grads_ready", arena offset) hook is placed (data-parallel
+        buckets: every gradient at or above that arena offset is final)."""
         eng, tag = self.eng, self.tag
         plan = Plan()
+        exports, zero_grads = [], []
+        plan.records["exports"], plan.records["zero_grads"] = exports, zero_grads
         S = 1.0
         gsc = None
         if loss_scale:
@@ -218,6 +240,7 @@ class UnitGraph:
             plan.add("ng_grad_scale_pow2", dout_f32.data_ptr(), dout_f32.numel(), float(loss_scale), gsc.data_ptr(),
                      launches=2, label=tag + ".gscale")
         plan.records["gscale"] = gsc
+        dev_inv = gsc.data_ptr() + 4 if gsc is not None else None
         units = self.units
         n = len(units)
         g_halo = [None] * n         # gradient w.r.t. each unit's haloed output buffer (from the next unit's dgrad)
@@ -258,6 +281,14 @@ class UnitGraph:
                 plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), dbb.data_ptr(), ws.data_ptr(), ws.numel() * 4,
                          launches=3, label=tag + ".head.wgrad", side=True)
                 plan.records["tap_head"] = {"conv": head, "dwp": dwp, "db": dbb, "center": (K // 2) * K + K // 2}
+                # head as tap GEMM: dwp is [tap (64 stored)][channel]; the reference layout (1, C, kh, kw) is
+                # [channel][tap].  Every tap column of dz sums to sum(dy): the centre tap's column sum is the bias gradient
+                cin_h = head.weight.shape[1]
+                self._export(plan, exports, head.weight, "ng_unpack_weight_grad", dwp.data_ptr(),
+                             (cin_h, K * K, 1, 1, 1, 64, cin_h), dev_inv, tag + ".head.export")
+                center = (K // 2) * K + K // 2
+                self._export(plan, exports, head.bias, "ng_unpack_weight_grad", dbb.data_ptr() + 4 * center,
+                             (1, 1, 1, 1, 0, 1, 1), dev_inv, tag + ".head.export_b")
             # data gradient: g[pixel][c] = sum_t dz[pixel][t] * w[t][c]  (1x1 conv over the 64 stored taps)
             gbuf = eng.act(tag + ".head.dx", x.B, x.H, x.W, x.C, x.pad)
             wT = eng.packed_weight(head.weight, "taps_T", x.C, 64, self.stream)
@@ -313,6 +344,25 @@ class UnitGraph:
                 plan.add("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), _ptr(dbb), ws.data_ptr(), ws.numel() * 4, launches=2,
                          label=pre + ".wgrad", side=True)
                 dw[i], db[i] = dwp, dbb
+                w = u.conv.weight
+                d0, d1, kh, kw = w.shape
+                if u.pack == "rowmerged":
+                    self._export(plan, exports, w, "ng_unpack_weight_grad_rowmerged", dwp.data_ptr(), (d0, d1, kh, kw),
+                                 dev_inv, pre + ".export")
+                else:
+                    self._export(plan, exports, w, "ng_unpack_weight_grad", dwp.data_ptr(),
+                                 (d0, d1, kh, kw, u.pack, u.cout, u.x.C), dev_inv, pre + ".export")
+                if u.conv.bias is not None:
+                    if dbb is not None:
+                        nb = u.conv.bias.numel()
+                        self._export(plan, exports, u.conv.bias, "ng_unpack_weight_grad", dbb.data_ptr(),
+                                     (nb, 1, 1, 1, 0, u.cout, 1), dev_inv, pre + ".export_b")
+                    else:
+                        # bias feeding InstanceNorm: its gradient is identically zero (the reference returns rounding
+                        # noise); its arena slot is never written and stays zero
+                        zero_grads.append(u.conv.bias)
+                if i in hook_units:
+                    plan.add_hook(("grads_ready", w._b200_grad_arena.offset_of(w)), label=pre + ".ddp_hook")
             # ---- data gradient ----
             if i == 0 and not need_dx:
                 continue

@@ -38,46 +38,12 @@ def lsgan(pred: torch.Tensor, target: float) -> torch.Tensor:
     return _LsganFn.apply(pred, target)
 
 
-class _PixelLossFn(torch.autograd.Function):
-    """One pass over (rgb, nir, pred): returns [L1, NDVI, NDWI, EVI] means and keeps
-    d(sum_i w_i * loss_i)/dpred for the backward (weights fixed at call time)."""
-
-    @staticmethod
-    def forward(ctx, rgb, nir, pred, weights):
-        B, _, H, W = pred.shape
-        rgb, nir, p = rgb.contiguous().float(), nir.contiguous().float(), pred.contiguous().float()
-        out = torch.empty(4, dtype=torch.float32, device=p.device)
-        scratch = torch.empty(4 * 1024, dtype=torch.float32, device=p.device)
-        need_grad = pred.requires_grad
-        dpred = torch.empty_like(p) if need_grad else None
-        w = (L.c_f32 * 4)(*[float(v) for v in weights])
-        L.call("ng_g_pixel_losses", rgb.data_ptr(), nir.data_ptr(), p.data_ptr(), B, H * W, w, out.data_ptr(),
-               dpred.data_ptr() if need_grad else None, scratch.data_ptr(), _stream(p))
-        if need_grad:
-            ctx.save_for_backward(dpred)
-        ctx.weights = [float(v) for v in weights]
-        return out
-
-    @staticmethod
-    def backward(ctx, gout):
-        # out_i enters the total loss as w_i * out_i, so gout == weights (up to a common factor c):
-        # dpred was computed for exactly that combination; recover c from the first non-zero weight.
-        (dpred,) = ctx.saved_tensors
-        c = None
-        for i, w in enumerate(ctx.weights):
-            if w != 0.0:
-                c = gout[i] / w
-                break
-        if c is None:
-            return None, None, torch.zeros_like(dpred), None
-        return None, None, dpred * c, None
-
-
 def pixel_losses(rgb, nir, pred, weights4):
-    """weights4 = (w_L1, w_NDVI, w_NDWI, w_EVI) that the caller will apply to the four returned means."""
-    for t, n in ((rgb, "rgb"), (nir, "nir"), (pred, "pred")):
-        require_cuda(t, n)
-    return _PixelLossFn.apply(rgb, nir, pred, tuple(weights4))
+    """(L1, NDVI, NDWI, EVI) means of the shipped configuration; weights4 selects the terms to evaluate (zero weight =
+    term skipped, returned as 0).  The gradient follows whatever the caller does with the four means."""
+    w7 = (weights4[0], weights4[1], weights4[2], 0.0, 0.0, 0.0, weights4[3])
+    t = rs_pixel_losses(rgb, nir, pred, w7)
+    return torch.stack((t[0], t[1], t[2], t[6]))
 
 
 # term order of ng_rs_pixel_losses = the reference's iteration order (utils/remote_sensing_indices.py:45-52)
@@ -86,36 +52,36 @@ RS_TERMS = ("l1", "ndvi", "ndwi", "gndvi", "savi", "msavi", "evi")
 
 class _RsPixelLossFn(torch.autograd.Function):
     """One pass over (rgb, nir, pred): [L1, NDVI, NDWI, GNDVI, SAVI, MSAVI, EVI] means (criterion l1 / l2 for the six
-    indices) for the terms in `mask`, and d(sum_k w_k * term_k)/dpred for the backward (weights fixed at call time)."""
+    indices) for the terms in `mask`.  Backward: a second launch of the same kernel with the per-term upstream gradients
+    as its (device-side) weights writes d(sum_k gout_k * term_k)/dpred -- whatever combination of the returned means the
+    caller builds (model/pix2pix.py:222-247 weights them; 'logging_dict' mode uses them one by one), the gradient is
+    that of the objective actually formed."""
 
     @staticmethod
-    def forward(ctx, rgb, nir, pred, weights, criterion, mask):
+    def forward(ctx, rgb, nir, pred, criterion, mask):
         B, _, H, W = pred.shape
         rgb, nir, p = rgb.contiguous().float(), nir.contiguous().float(), pred.contiguous().float()
         out = torch.empty(8, dtype=torch.float32, device=p.device)
         scratch = torch.empty(8 * 1024, dtype=torch.float32, device=p.device)
-        need_grad = pred.requires_grad
-        dpred = torch.empty_like(p) if need_grad else None
-        w = (L.c_f32 * 7)(*[float(v) for v in weights])
-        L.call("ng_rs_pixel_losses", rgb.data_ptr(), nir.data_ptr(), p.data_ptr(), B, H * W, w, int(criterion), int(mask),
-               out.data_ptr(), dpred.data_ptr() if need_grad else None, scratch.data_ptr(), _stream(p))
-        if need_grad:
-            ctx.save_for_backward(dpred)
-        ctx.weights = [float(v) for v in weights]
+        w = (L.c_f32 * 7)(*([0.0] * 7))
+        L.call("ng_rs_pixel_losses", rgb.data_ptr(), nir.data_ptr(), p.data_ptr(), B, H * W, w, None, int(criterion),
+               int(mask), out.data_ptr(), None, scratch.data_ptr(), _stream(p))
+        if pred.requires_grad:
+            ctx.save_for_backward(rgb, nir, p)
+            ctx.scratch = scratch
+        ctx.criterion, ctx.mask = int(criterion), int(mask)
         return out[:7]
 
     @staticmethod
     def backward(ctx, gout):
-        # term_k enters the total loss as w_k * term_k, so gout == weights up to a common factor c
-        (dpred,) = ctx.saved_tensors
-        c = None
-        for i, w in enumerate(ctx.weights):
-            if w != 0.0:
-                c = gout[i] / w
-                break
-        if c is None:
-            return None, None, torch.zeros_like(dpred), None, None, None
-        return None, None, dpred * c, None, None, None
+        rgb, nir, p = ctx.saved_tensors
+        B, _, H, W = p.shape
+        g = gout.contiguous().float()
+        dpred = torch.empty_like(p)
+        out = torch.empty(8, dtype=torch.float32, device=p.device)
+        L.call("ng_rs_pixel_losses", rgb.data_ptr(), nir.data_ptr(), p.data_ptr(), B, H * W, None, g.data_ptr(),
+               ctx.criterion, ctx.mask, out.data_ptr(), dpred.data_ptr(), ctx.scratch.data_ptr(), _stream(p))
+        return None, None, dpred, None, None
 
 
 def rs_pixel_losses(rgb, nir, pred, weights7, criterion: str = "l1", mask: int = None):
@@ -127,7 +93,7 @@ def rs_pixel_losses(rgb, nir, pred, weights7, criterion: str = "l1", mask: int =
         mask = sum(1 << k for k, w in enumerate(weights7) if float(w) != 0.0)
     if mask == 0:
         return torch.zeros(7, dtype=torch.float32, device=pred.device)
-    return _RsPixelLossFn.apply(rgb, nir, pred, tuple(weights7), 0 if criterion == "l1" else 1, int(mask))
+    return _RsPixelLossFn.apply(rgb, nir, pred, 0 if criterion == "l1" else 1, int(mask))
 
 
 def rs_index(rgb, nir, pred, which: str, loss_eps: bool):

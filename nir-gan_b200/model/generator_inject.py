@@ -48,10 +48,10 @@ class ResnetGenerator_inject(_B200Module):
             self.post_correction_param = nn.Parameter(torch.tensor(self.post_correction_init))
         self.model = nn.Sequential(*layers)
 
-    def forward(self, input, embeds, wrap_pad: int = 0):
+    def forward(self, input, embeds, wrap_pad: int = 0, reuse_token=None):
         require_cuda(input, "ResnetGenerator_inject input")
         from ..autograd import generator_apply
-        return generator_apply(self, self._get_runner(GeneratorRunner), input, embeds, wrap_pad)
+        return generator_apply(self, self._get_runner(GeneratorRunner), input, embeds, wrap_pad, reuse_token)
 
 
 def define_G_inject(config):

@@ -122,18 +122,28 @@ class _B200Module(nn.Module):
 
     def reset_training_slots(self):
         """Forget activations of training forwards whose backward will never run."""
-        if getattr(self, "_runner", None) is not None:
-            self._runner._live = 0
+        r = getattr(self, "_runner", None)
+        if r is not None:
+            r._live = 0
+            for c in r._train.values():
+                if isinstance(c, dict) and "live" in c:
+                    c["live"] = False
 
     @torch.no_grad()
     def forward_shared(self, input, embeds=None, wrap_pad: int = 0):
-        """Generator forward WITHOUT an autograd graph that nevertheless keeps its activations: a following
-        grad-enabled forward on the same input tensor with unchanged weights reuses them instead of recomputing
-        (the D pass and the G pass of one training step see the same batch, model/pix2pix.py:177-180)."""
+        """Generator forward WITHOUT an autograd graph that nevertheless keeps its activations.  Returns
+        ``(pred, token)``: handing ``token`` to the next grad-enabled ``forward(..., reuse_token=token)`` on the SAME
+        batch lets it adopt these activations instead of recomputing them (the D pass and the G pass of one training
+        step evaluate G on the same batch with the same weights, model/pix2pix.py:177-180).  The token dies with any
+        other training forward of this shape and with any change of the generator's weights; the caller vouches for the
+        batch being the same.  ``pred`` is a view of the plan's output buffer (valid until that next forward)."""
         require_cuda(input, "generator input")
-        c = self._get_runner(GeneratorRunner).train_forward(input, embeds, wrap_pad)
+        c = self._get_runner(GeneratorRunner).train_forward(input, embeds, wrap_pad, share=True)
         B, _, H, W = c["geom"]
-        return c["fwd"].records["out"].view(B, 1, H, W).clone()
+        out = c["fwd"].records["out"].view(B, 1, H, W)
+        if getattr(self, "post_correction", False):
+            out = out * self.post_correction_param
+        return out, c["share_token"][0]
 
     @torch.no_grad()
     def forward_async(self, input, embeds=None, wrap_pad: int = 0, ready=None):
@@ -164,12 +174,13 @@ class ResnetGenerator(_B200Module):
         self._runner = None
         self.model = nn.Sequential(*_generator_trunk(input_nc, output_nc, ngf, norm_layer, n_blocks))
 
-    def forward(self, input, wrap_pad: int = 0):
+    def forward(self, input, wrap_pad: int = 0, reuse_token=None):
         """(B, input_nc, H, W) fp32 CUDA -> (B, 1, H, W) fp32.  ``wrap_pad`` fuses Px2Px_PL.forward's
-        reflect-pad / crop (pix2pix.py:91-93,107-108) into the first and last kernels."""
+        reflect-pad / crop (pix2pix.py:91-93,107-108) into the first and last kernels; ``reuse_token``: see
+        ``forward_shared``."""
         require_cuda(input, "ResnetGenerator input")
         from ..autograd import generator_apply
-        return generator_apply(self, self._get_runner(GeneratorRunner), input, None, wrap_pad)
+        return generator_apply(self, self._get_runner(GeneratorRunner), input, None, wrap_pad, reuse_token)
 
 
 def define_G(input_nc, output_nc, ngf, netG, norm="batch", use_dropout=False, init_type="normal", init_gain=0.02,
@@ -212,10 +223,20 @@ class NLayerDiscriminator(_B200Module):
         seq += [nn.Conv2d(ndf * mult, 1, kernel_size=4, stride=1, padding=1)]
         self.model = nn.Sequential(*seq)
 
-    def forward(self, input):
+    def forward(self, input, second=None):
+        """``netD(x)`` as in the reference; ``netD(rgb, pred)`` is ``netD(torch.cat((rgb, pred), 1))`` with the
+        concatenation fused into the input kernel (model/pix2pix.py:197,202,216)."""
         require_cuda(input, "NLayerDiscriminator input")
         from ..autograd import discriminator_apply
-        return discriminator_apply(self, self._get_runner(PatchGANRunner), input)
+        return discriminator_apply(self, self._get_runner(PatchGANRunner), [(input, second)])
+
+    def forward_parts(self, parts):
+        """Several (first, second | None) inputs of equal shape as ONE batch: returns the stacked (len(parts)*B, 1, h, w)
+        patch map.  The D pass feeds its fake and its real batch through the network together this way."""
+        for a, _ in parts:
+            require_cuda(a, "NLayerDiscriminator input")
+        from ..autograd import discriminator_apply
+        return discriminator_apply(self, self._get_runner(PatchGANRunner), list(parts))
 
 
 def define_D(input_nc, ndf, netD, n_layers_D=3, norm="batch", init_type="normal", init_gain=0.02, gpu_ids=[]):

@@ -50,11 +50,11 @@ class Px2Px(nn.Module):
         self.reuse_g_forward = os.environ.get("NIRGAN_B200_REUSE_G", "1") != "0"
 
     # pix2pix.py:88-110 -- the pad / crop is fused into the first / last kernel (wrap_pad)
-    def forward(self, input, embeds=None, use_padding=True):
+    def forward(self, input, embeds=None, use_padding=True, reuse_token=None):
         pad = self.config.Data.padding_amount if self.config.Data.padding else 0
         if self.inject:
-            return self.netG(input, embeds, wrap_pad=pad)
-        return self.netG(input, wrap_pad=pad)
+            return self.netG(input, embeds, wrap_pad=pad, reuse_token=reuse_token)
+        return self.netG(input, wrap_pad=pad, reuse_token=reuse_token)
 
     def attach_satclip(self, satclip_model):
         """The reference constructs ``SatClIP_wrapper(device=self.device).eval()`` itself (pix2pix.py:68-74); the
@@ -131,24 +131,35 @@ class Px2Px(nn.Module):
         else:
             (rgb, nir), embeds = self.extract_batch(batch), None
         o = self.config.base_configs
+        self.netD.reset_training_slots()
+        self.netG.reset_training_slots()
         if optimizer_idx == 0:      # discriminator, pix2pix.py:195-212
-            self.netD.reset_training_slots()
+            self._shared = None
             with torch.no_grad():    # fake_AB.detach(): G needs no graph in the D pass
                 if self.reuse_g_forward:
                     # the G pass of this step evaluates G on the same batch with the same weights: keep the activations
+                    # and hand them over through an explicit token (held together with the batch tensors themselves, so
+                    # neither their memory nor their identity can be recycled in between)
                     pad = self.config.Data.padding_amount if self.config.Data.padding else 0
-                    pred = self.netG.forward_shared(rgb, embeds if self.inject else None, wrap_pad=pad)
+                    pred, token = self.netG.forward_shared(rgb, embeds if self.inject else None, wrap_pad=pad)
+                    self._shared = (token, rgb, rgb._version, embeds, None if embeds is None else embeds._version)
                 else:
                     pred = self.forward(rgb, embeds)
-            pred_fake = self.netD(torch.cat((rgb, pred), 1))
-            loss_D_fake = self.criterionGAN(pred_fake, False)
-            pred_real = self.netD(torch.cat((rgb, nir), 1))
-            loss_D_real = self.criterionGAN(pred_real, True)
+            # torch.cat((rgb, pred), 1) / torch.cat((rgb, nir), 1) are fused into the PatchGAN's input kernel and the fake
+            # and the real batch go through D as one 2B batch (per-sample InstanceNorm: same values as two calls)
+            B = rgb.shape[0]
+            patches = self.netD.forward_parts([(rgb, pred), (rgb, nir)])
+            loss_D_fake = self.criterionGAN(patches[:B], False)
+            loss_D_real = self.criterionGAN(patches[B:], True)
             return loss_D_fake + loss_D_real          # no 0.5 factor (pix2pix.py:206)
         # generator, pix2pix.py:214-257
-        self.netD.reset_training_slots()
-        pred = self.forward(rgb, embeds)
-        pred_fake = self.netD(torch.cat((rgb, pred), 1))
+        token = None
+        sh, self._shared = getattr(self, "_shared", None), None
+        if sh is not None and sh[1] is rgb and sh[2] == rgb._version and sh[3] is embeds and \
+                (embeds is None or sh[4] == embeds._version):
+            token = sh[0]
+        pred = self.forward(rgb, embeds, reuse_token=token)
+        pred_fake = self.netD(rgb, pred)
         loss_G = self.criterionGAN(pred_fake, True) * o.lambda_GAN
         extra = []                                             # pix2pix.py:231-243, added after GAN + L1
         if _get(o, "lambda_ssim", 0.0) > 0.0:

@@ -9,7 +9,8 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib as L
-from .engine import ActBuf, Engine, EngineConfig, Plan, conv_out, require_cuda, _ptr
+from . import engine as _engine
+from .engine import ActBuf, CountingBuffers, Engine, EngineConfig, Plan, Pool, PoolBuffers, conv_out, require_cuda, _ptr
 from .graph import Unit, UnitGraph
 
 
@@ -32,13 +33,98 @@ class _RunnerBase:
 
     def trim(self, eng: Engine) -> None:
         """Plans own their buffers for life (static plan, no allocator).  With many distinct input shapes (mixed
-        resolutions, BASELINE config 5) drop every cached plan and buffer once they exceed the budget
-        (NIRGAN_B200_BUFFER_GB, default 90) -- only when no forward is waiting for its backward."""
+        resolutions, BASELINE config 5) the least-recently-used plans -- and the buffers only they reference -- are
+        dropped once the total exceeds the budget (NIRGAN_B200_BUFFER_GB, default 90), only when no forward is waiting
+        for its backward."""
         budget = float(os.environ.get("NIRGAN_B200_BUFFER_GB", "90")) * 1e9
-        if eng.buffers.bytes() > budget and self._live == 0:
-            self._fwd.clear()
-            self._train.clear()
-            eng.buffers._b.clear()
+        if self._live != 0:
+            return
+        while eng.buffers.bytes() > budget:
+            cands = [(v.get("used", 0) if isinstance(v, dict) else getattr(v[1], "used", 0), d, k)
+                     for d in (self._fwd, self._train) for k, v in d.items()]
+            if len(cands) <= 1:
+                break
+            _, d, k = min(cands, key=lambda c: c[0])
+            v = d[k]
+            tags = set(v.get("tags", ()) if isinstance(v, dict) else getattr(v[1], "tags", ()))
+            if not tags:
+                break
+            # contexts that differ only in what they differentiate share their buffers (same tag): they go together
+            for dd in (self._fwd, self._train):
+                for kk in [kk for kk, vv in dd.items()
+                           if tags & set(vv.get("tags", ()) if isinstance(vv, dict) else getattr(vv[1], "tags", ()))]:
+                    del dd[kk]
+            eng.buffers.drop(tags)
+
+    def pooled_build(self, eng: Engine, key, pool_key, build_fn) -> dict:
+        """Build a training context whose buffers come from the runner's shared pool `pool_key` (engine.Pool): a first,
+        allocation-free pass over the same code measures the context; the pool is (re)allocated when it is too small --
+        contexts bound to the old pool are dropped and rebuild on their next use, so feeding the largest shape first
+        avoids the churn."""
+        if not _engine.POOL[0]:
+            return build_fn()
+        if not hasattr(self, "_pools"):
+            self._pools, self._ctx_bytes = {}, {}
+        saved = eng.buffers
+        need = self._ctx_bytes.get(key)
+        if need is None:
+            counter = CountingBuffers(eng.device)
+            eng.buffers = counter
+            try:
+                build_fn()
+            finally:
+                eng.buffers = saved
+            need = self._ctx_bytes[key] = counter.total
+        pool = self._pools.get(pool_key)
+        if pool is None or pool.capacity < need:
+            if pool is not None:
+                for k in [k for k, v in self._train.items() if v.get("pool") is pool]:
+                    del self._train[k]
+                self._pools.pop(pool_key)
+                del pool
+                torch.cuda.empty_cache()
+            pool = self._pools[pool_key] = Pool(need, eng.device)
+        eng.buffers = PoolBuffers(pool, eng.device)
+        try:
+            ctx = build_fn()
+        finally:
+            eng.buffers = saved
+        ctx["pool"] = pool
+        return ctx
+
+    def pool_bytes(self) -> int:
+        return sum(p.capacity for p in getattr(self, "_pools", {}).values())
+
+    def touch(self, entry) -> None:
+        self._clock = getattr(self, "_clock", 0) + 1
+        if isinstance(entry, dict):
+            entry["used"] = self._clock
+        else:
+            entry[1].used = self._clock          # (graph, plan) pair of an inference plan
+
+    def grad_arena(self):
+        """The flat gradient arena shared with the optimizer of this network (optim.GradArena)."""
+        from .optim import GradArena
+        ar = GradArena.of(list(self.module.parameters()))
+        if ar is None:
+            raise RuntimeError("nirgan_b200: training needs every parameter of the network as a contiguous fp32 CUDA tensor")
+        return ar
+
+    def ddp_hook_units(self, graph: UnitGraph, buckets: int = 3):
+        """Units after whose gradient export the data-parallel exchange may send a bucket: `buckets` - 1 cut points at
+        roughly equal parameter mass, walking the units in backward order.  Empty when no process group with more than
+        one rank is initialised (single-GPU plans stay hook-free)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) or buckets <= 1:
+            return ()
+        sizes = [u.conv.weight.numel() for u in graph.units]
+        total, acc, cuts, target = sum(sizes), 0, [], 1
+        for i in range(len(sizes) - 1, 0, -1):
+            acc += sizes[i]
+            if acc >= total * target / buckets and len(cuts) < buckets - 1:
+                cuts.append(i)
+                target += 1
+        return tuple(cuts)
 
     def loss_scale(self) -> float:
         """Target max |dL/d(output)| of the adaptive power-of-two gradient scaling (ng_grad_scale_pow2) used when
@@ -72,7 +158,7 @@ class GeneratorRunner(_RunnerBase):
         H1, W1 = H + 2 * wrap, W + 2 * wrap
         if H1 % 4 or W1 % 4:
             raise RuntimeError(f"nirgan_b200: padded tile {H1}x{W1} must be divisible by 4 (two stride-2 stages)")
-        g = UnitGraph(eng, tag, stream)
+        g = UnitGraph(eng, tag)
         # input: NCHW fp32 -> row-merged NHWC [B][H1+6][W1][kw*8+c] (wrapper reflect pad + stem reflect halo fused):
         # the 7x7x3 stem becomes a 7x1 conv over 64 "channels" = 7 K-steps of 128-byte rows instead of 49 thin taps
         src = eng.buffers.get(tag + ".in", B * cin * H * W, torch.float32)
@@ -134,14 +220,17 @@ class GeneratorRunner(_RunnerBase):
         if hit is not None:
             g, plan = hit
             g.refresh_weights()
+            self.touch(hit)
             return plan
         self.trim(eng)
-        g = self.build_graph(eng, B, H, W, wrap, inject, stream, "g" if slot == 0 else f"g{slot}",
-                             direct_head=not self._use_tap_head())
+        tag = f"g{slot}_{B}x{Cin}x{H}x{W}p{wrap}{'i' if inject else ''}"      # shape-unique: plans are evicted by tag
+        g = self.build_graph(eng, B, H, W, wrap, inject, stream, tag, direct_head=not self._use_tap_head())
         plan = g.compile_forward()
+        plan.tags = (tag,)
         if g.tap_head is None:
             plan.records["out"] = g.units[-1].out_f32
         self._fwd[key] = (g, plan)
+        self.touch(self._fwd[key])
         return plan
 
     @torch.no_grad()
@@ -188,6 +277,13 @@ class GeneratorRunner(_RunnerBase):
         if len(self._side_streams) < nstreams:
             self._side_streams += [torch.cuda.Stream(x.device) for _ in range(nstreams - len(self._side_streams))]
         streams = self._side_streams[:nstreams]
+        # the packed weight shadows are refreshed IN PLACE on the caller's stream: when the masters changed since the
+        # previous call, slices of that call may still be reading the old shadows on the runner's streams -- wait for them
+        sig = self.weight_signature()
+        if sig != getattr(self, "_async_sig", None):
+            for ev in getattr(self, "_async_done", ()):
+                main.wait_event(ev)
+            self._async_sig = sig
         # build / refresh every plan on the caller's stream first (weight packing), then fork
         jobs = []
         for i, b0 in enumerate(range(0, Btot, chunk)):
@@ -225,6 +321,7 @@ class GeneratorRunner(_RunnerBase):
             ev.record(st)
             done.append(ev)
         self.last_plan = plan
+        self._async_done = done
         return out, done
 
     # ---- training -------------------------------------------------------------------------------------
@@ -232,19 +329,37 @@ class GeneratorRunner(_RunnerBase):
         ps = list(self.module.parameters())
         return (max(getattr(p, "_b200_epoch", 0) for p in ps), sum(p._version for p in ps))
 
-    def train_forward(self, x: torch.Tensor, embeds, wrap_pad: int) -> dict:
-        """Run the training forward plan (activations kept for the backward) unless the very same input tensors and
-        weights were the last thing this context computed: Px2Px_PL.training_step evaluates G on the same batch for
-        both optimizers (model/pix2pix.py:177-180) with identical results, so the second evaluation is reused."""
+    def train_forward(self, x: torch.Tensor, embeds, wrap_pad: int, share: bool = False, reuse_token=None) -> dict:
+        """Run the training forward plan (activations kept for the backward).
+
+        Px2Px_PL.training_step evaluates G on the same batch for both optimizers (model/pix2pix.py:177-180) with
+        identical results, so the second evaluation may be skipped -- but only through an explicit hand-over: the D pass
+        calls with ``share=True`` and receives a token in ``ctx['share_token']``; the G pass passes that token back as
+        ``reuse_token``.  The activations are reused only if the token is the context's current one (no other forward
+        of this shape ran in between) and the generator's weights are unchanged; every other call recomputes."""
         c = self.train_context(x, embeds, wrap_pad)
-        key = (x.data_ptr(), x._version, tuple(x.shape),
-               None if embeds is None else (embeds.data_ptr(), embeds._version), self.weight_signature())
-        if c.get("fresh") != key:
+        if c.get("live"):
+            raise RuntimeError(
+                "nirgan_b200: a grad-enabled generator forward of this shape is still waiting for its backward; a second "
+                "one would overwrite its activations.  Run backward first, or call netG.reset_training_slots() if that "
+                "graph was dropped.")
+        pool = c.get("pool")
+        if pool is not None and pool.live is not None and pool.live is not c and pool.live.get("live"):
+            raise RuntimeError("nirgan_b200: a generator forward of another shape is still waiting for its backward; the "
+                               "training contexts share one memory pool (NIRGAN_B200_POOL=0 gives every shape its own)")
+        sig = self.weight_signature()
+        tok = c.get("share_token")
+        reuse = reuse_token is not None and tok is not None and reuse_token is tok[0] and tok[1] == sig and \
+            (pool is None or pool.owner is c)
+        c["share_token"] = None
+        if pool is not None:
+            pool.owner = c
+        if not reuse:
             B, Cin, H, W = c["geom"]
             fwd = c["fwd"]
-            fwd.records["src"].view(B, Cin, H, W).copy_(x.detach().float())
+            fwd.records["src"].view(B, Cin, H, W).copy_(x.detach())
             if embeds is not None:
-                fwd.records["emb"].view(B, 256).copy_(embeds.detach().float())
+                fwd.records["emb"].view(B, 256).copy_(embeds.detach())
             main = torch.cuda.current_stream(x.device)
             halves = c.get("fwd_halves")
             if halves:
@@ -259,7 +374,8 @@ class GeneratorRunner(_RunnerBase):
                 main.wait_stream(side)
             else:
                 fwd.run_training(x.device)
-            c["fresh"] = key
+        if share:
+            c["share_token"] = (object(), sig)
         return c
 
     def train_context(self, x: torch.Tensor, embeds, wrap_pad: int) -> dict:
@@ -270,22 +386,39 @@ class GeneratorRunner(_RunnerBase):
         stream = torch.cuda.current_stream(x.device).cuda_stream
         key = (B, Cin, H, W, wrap_pad, inject)
         ctx = self._train.get(key)
+        slots = tuple(p._b200_grad_slot.data_ptr() if hasattr(p, "_b200_grad_slot") else 0
+                      for p in self.module.parameters())
+        if ctx is not None and ctx["slots"] != slots:
+            ctx = None                 # the gradient arena moved (a new optimizer adopted the parameters): re-bind
         if ctx is None:
             self.trim(eng)
-            g = self.build_graph(eng, B, H, W, wrap_pad, inject, stream, "gt", direct_head=not self._use_tap_head())
-            fwd = g.compile_forward()
-            if g.tap_head is None:
-                fwd.records["out"] = g.units[-1].out_f32
-            dout = eng.buffers.get("gt.dout", B * H * W, torch.float32)
-            bwd = g.compile_backward(dout, self.loss_scale(), need_dw=True, need_dx=False, want_inject_grads=inject)
-            ctx = self._train[key] = {"graph": g, "fwd": fwd, "bwd": bwd, "dout": dout, "geom": (B, Cin, H, W)}
-            ctx["fwd_halves"] = self._half_batch_plans(eng, B, H, W, wrap_pad, inject, stream)
+            self.grad_arena()
+            slots = tuple(p._b200_grad_slot.data_ptr() for p in self.module.parameters())
+            tag = f"gt_{B}x{Cin}x{H}x{W}p{wrap_pad}{'i' if inject else ''}"
+
+            def build():
+                g = self.build_graph(eng, B, H, W, wrap_pad, inject, stream, tag, direct_head=not self._use_tap_head())
+                fwd = g.compile_forward()
+                if g.tap_head is None:
+                    fwd.records["out"] = g.units[-1].out_f32
+                dout = eng.buffers.get(tag + ".dout", B * H * W, torch.float32)
+                bwd = g.compile_backward(dout, self.loss_scale(), need_dw=True, need_dx=False, want_inject_grads=inject,
+                                         hook_units=self.ddp_hook_units(g))
+                c = {"graph": g, "fwd": fwd, "bwd": bwd, "dout": dout, "geom": (B, Cin, H, W), "tags": (tag,),
+                     "tag": tag, "slots": slots, "live": False}
+                if inject:
+                    c["de128"] = eng.buffers.get(tag + ".de128", B * 128 * 128, torch.float32)
+                c["fwd_halves"] = self._half_batch_plans(eng, B, H, W, wrap_pad, inject, stream, tag)
+                return c
+
+            ctx = self._train[key] = self.pooled_build(eng, key, "g", build)
         else:
             ctx["graph"].refresh_weights(backward=True, need_dx=False)
+        self.touch(ctx)
         return ctx
 
 
-    def _half_batch_plans(self, eng, B, H, W, wrap_pad, inject, stream):
+    def _half_batch_plans(self, eng, B, H, W, wrap_pad, inject, stream, tag):
         """Forward plans for the two halves of the batch that write the full-batch graph's buffers in place (None when
         the batch is odd / small, disabled by NIRGAN_B200_TRAIN_SLICES=0, or a buffer is not per-image)."""
         import os
@@ -294,13 +427,13 @@ class GeneratorRunner(_RunnerBase):
         # (41.3 vs 39.4 ms) -- every conv launch pays its ~25 us pipeline fill twice and the eager launches of the two
         # plans do not interleave the way the graph-replayed inference slices do.  Off unless NIRGAN_B200_TRAIN_SLICES=1.
         mode = os.environ.get("NIRGAN_B200_TRAIN_SLICES", "0")
-        if B % 2 or B < 16 or mode != "1":
+        if B % 2 or B < 16 or mode != "1" or isinstance(eng.buffers, CountingBuffers):
             return None
         saved, plans = eng.buffers, []
         try:
             for part in range(2):
                 eng.buffers = SliceBuffers(saved, part, 2)
-                gh = self.build_graph(eng, B // 2, H, W, wrap_pad, inject, stream, "gt",
+                gh = self.build_graph(eng, B // 2, H, W, wrap_pad, inject, stream, tag,
                                       direct_head=not self._use_tap_head())
                 plans.append(gh.compile_forward())
                 plans[-1].keepalive.append(gh)
@@ -313,20 +446,55 @@ class GeneratorRunner(_RunnerBase):
 
 # =================================================================================================
 class PatchGANRunner(_RunnerBase):
-    """NLayerDiscriminator (model/networks.py:539-584)."""
+    """NLayerDiscriminator (model/networks.py:539-584).
+
+    The input is described as a list of *parts*, each the channel concatenation of one or two NCHW tensors
+    (``torch.cat((rgb, pred), 1)``, model/pix2pix.py:197,202,216), stacked along the batch: the concatenation, the
+    NCHW->NHWC transform, the channel padding and the conversion to the operand type are ONE ``ng_prep_input`` launch per
+    part, and the fake and the real batch of the D pass run as one 2B batch through the network (InstanceNorm is per
+    sample, so every sample's result is the one the reference computes with two separate calls)."""
 
     def conv_modules(self) -> List[torch.nn.Module]:
         return [m for m in self.module.model if isinstance(m, torch.nn.Conv2d)]
 
-    def build_graph(self, eng: Engine, B: int, H: int, W: int, stream: int, tag: str) -> UnitGraph:
+    @staticmethod
+    def describe(parts):
+        """parts [(a, b | None)] -> (unique tensors, ((index of a, index of b | -1), ...), Bp, ca, cb, H, W)."""
+        uniq, struct = [], []
+        Bp, ca, H, W = parts[0][0].shape
+        cb = 0 if parts[0][1] is None else parts[0][1].shape[1]
+
+        def idx(t):
+            for j, u in enumerate(uniq):
+                if u is t:
+                    return j
+            uniq.append(t)
+            return len(uniq) - 1
+
+        for a, b in parts:
+            require_cuda(a, "discriminator input")
+            if tuple(a.shape) != (Bp, ca, H, W) or (b is None) != (cb == 0) or \
+                    (b is not None and tuple(b.shape) != (Bp, cb, H, W)):
+                raise RuntimeError("nirgan_b200: every part of a discriminator batch must have the same shapes")
+            struct.append((idx(a), -1 if b is None else idx(b)))
+        return uniq, tuple(struct), Bp, ca, cb, H, W
+
+    def build_graph(self, eng: Engine, Bp: int, struct, chans, ca: int, cb: int, H: int, W: int, tag: str) -> UnitGraph:
         convs = self.conv_modules()
-        g = UnitGraph(eng, tag, stream)
+        g = UnitGraph(eng, tag)
         cin = convs[0].weight.shape[1]
-        src = eng.buffers.get(tag + ".in", B * cin * H * W, torch.float32)
-        g.records["src"] = src
+        if ca + cb != cin:
+            raise RuntimeError(f"nirgan_b200: discriminator expects {cin} input channels, got {ca} + {cb}")
+        nparts = len(struct)
+        B = nparts * Bp
+        srcs = [eng.buffers.get(f"{tag}.in{j}", Bp * c * H * W, torch.float32) for j, c in enumerate(chans)]
+        g.records["srcs"] = srcs
         x = eng.act(tag + ".x0", B, H, W, 16, 0)
-        g.pre_ops.append(("ng_prep_input", (src.data_ptr(), cin, None, 0, B, H, W, 0, 0, L.HALO_ZERO, 16, eng.dt_enum,
-                                            x.t.data_ptr()), tag + ".prep"))
+        esz = x.t.element_size()
+        for i, (ia, ib) in enumerate(struct):
+            g.pre_ops.append(("ng_prep_input", (srcs[ia].data_ptr(), ca, srcs[ib].data_ptr() if ib >= 0 else None, cb, Bp,
+                                                H, W, 0, 0, L.HALO_ZERO, 16, eng.dt_enum,
+                                                x.t.data_ptr() + i * Bp * H * W * 16 * esz), f"{tag}.prep{i}"))
         c0 = convs[0]
         Hc, Wc = conv_out(H, 4, 2, 1), conv_out(W, 4, 2, 1)
         u = g.add(Unit("l0", c0, x, c0.weight.shape[0], 4, 2, 1, Hc, Wc, kind="biasact", act=L.ACT_LRELU, slope=0.2,
@@ -341,42 +509,67 @@ class PatchGANRunner(_RunnerBase):
         g.add(Unit("out", cl, u.out, 16, 4, 1, 1, Ho, Wo, kind="head", act=L.ACT_NONE))
         g.records["out_hw"] = (Ho, Wo)
         g.records["cin"] = cin
+        g.records["parts"] = (nparts, Bp, ca, cb)
         return g
 
+    @staticmethod
+    def load_inputs(graph: UnitGraph, uniq) -> None:
+        for dst, t in zip(graph.records["srcs"], uniq):
+            dst.view(t.shape).copy_(t.detach())
+
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        require_cuda(x, "discriminator input")
-        eng = self.engine(x.device)
-        B, Cin, H, W = x.shape
-        stream = torch.cuda.current_stream(x.device).cuda_stream
-        key = (B, Cin, H, W)
+    def forward(self, parts) -> torch.Tensor:
+        uniq, struct, Bp, ca, cb, H, W = self.describe(parts)
+        eng = self.engine(uniq[0].device)
+        chans = tuple(t.shape[1] for t in uniq)
+        key = (Bp, struct, chans, H, W)
         hit = self._fwd.get(key)
         if hit is None:
-            g = self.build_graph(eng, B, H, W, stream, "d")
-            hit = self._fwd[key] = (g, g.compile_forward())
+            self.trim(eng)
+            tag = f"d_{len(struct)}x{Bp}x{ca}+{cb}x{H}x{W}s{hash(struct) & 0xffff:x}"
+            g = self.build_graph(eng, Bp, struct, chans, ca, cb, H, W, tag)
+            plan = g.compile_forward()
+            plan.tags = (tag,)
+            hit = self._fwd[key] = (g, plan)
         else:
             hit[0].refresh_weights()
+        self.touch(hit)
         g, plan = hit
-        plan.records["src"].view(B, Cin, H, W).copy_(x.float())
-        plan.run(stream)
+        self.load_inputs(g, uniq)
+        plan.run(torch.cuda.current_stream(uniq[0].device).cuda_stream)
         Ho, Wo = g.records["out_hw"]
         self.last_plan = plan
-        return g.units[-1].out_f32.view(B, 1, Ho, Wo).clone()
+        return g.units[-1].out_f32.view(len(struct) * Bp, 1, Ho, Wo).clone()
 
-    def train_context(self, x: torch.Tensor, slot: int, need_dw: bool, need_dx: bool) -> dict:
-        eng = self.engine(x.device)
-        B, Cin, H, W = x.shape
-        stream = torch.cuda.current_stream(x.device).cuda_stream
-        key = (B, Cin, H, W, slot, need_dw, need_dx)
+    def train_context(self, parts_desc, slot: int, need_dw: bool, need_dx: bool, device) -> dict:
+        struct, chans, Bp, ca, cb, H, W = parts_desc
+        eng = self.engine(device)
+        key = (Bp, struct, chans, H, W, slot, need_dw, need_dx)
         ctx = self._train.get(key)
+        slots = tuple(p._b200_grad_slot.data_ptr() if hasattr(p, "_b200_grad_slot") else 0
+                      for p in self.module.parameters()) if need_dw else ()
+        if ctx is not None and ctx["slots"] != slots:
+            ctx = None
         if ctx is None:
-            tag = f"dt{slot}"
-            g = self.build_graph(eng, B, H, W, stream, tag)
-            fwd = g.compile_forward()
-            Ho, Wo = g.records["out_hw"]
-            dout = eng.buffers.get(tag + ".dout", B * Ho * Wo, torch.float32)
-            bwd = g.compile_backward(dout, self.loss_scale(), need_dw=need_dw, need_dx=need_dx)
-            ctx = self._train[key] = {"graph": g, "fwd": fwd, "bwd": bwd, "dout": dout, "geom": (B, Cin, H, W)}
+            if need_dw:
+                self.grad_arena()
+                slots = tuple(p._b200_grad_slot.data_ptr() for p in self.module.parameters())
+            tag = f"dt{slot}_{len(struct)}x{Bp}x{ca}+{cb}x{H}x{W}s{hash(struct) & 0xffff:x}"
+
+            def build():
+                g = self.build_graph(eng, Bp, struct, chans, ca, cb, H, W, tag)
+                fwd = g.compile_forward()
+                Ho, Wo = g.records["out_hw"]
+                B = len(struct) * Bp
+                dout = eng.buffers.get(tag + ".dout", B * Ho * Wo, torch.float32)
+                bwd = g.compile_backward(dout, self.loss_scale(), need_dw=need_dw, need_dx=need_dx,
+                                         hook_units=self.ddp_hook_units(g, buckets=2) if need_dw else ())
+                return {"graph": g, "fwd": fwd, "bwd": bwd, "dout": dout, "geom": (B, ca + cb, H, W), "tags": (tag,),
+                        "tag": tag, "slots": slots}
+
+            # forwards that wait for their backward at the same time sit in different slots: one pool per slot
+            ctx = self._train[key] = self.pooled_build(eng, key, ("d", slot), build)
         else:
             ctx["graph"].refresh_weights(backward=True, need_dx=need_dx)
+        self.touch(ctx)
         return ctx

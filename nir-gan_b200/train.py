@@ -2,14 +2,19 @@
 discriminator appear to torch autograd as single differentiable functions of (input, parameters);
 their forward and backward are the compiled C-ABI plans of ``graph.UnitGraph``.
 
+Weight gradients never pass through torch arithmetic: the backward plan itself unpacks every packed fp32 weight
+gradient into the parameter's slot of the network's flat gradient arena (``optim.GradArena``; reference layout, adaptive
+gradient scale divided out) and autograd is handed views of those slots, which it adopts as ``.grad`` without a copy.
+When a parameter is reached a second time in one backward pass, or its ``.grad`` still lives in the slot (no
+``zero_grad(set_to_none=True)``), the export kernels accumulate instead (``beta`` = 1) and autograd is told "nothing to
+add" -- exactly AccumulateGrad's semantics.
+
 Gradient precision: in the fp16 fast mode activations' gradients are carried in fp16 with an adaptive
 power-of-two scale f = 2^floor(log2(target / max|dout|)) (target 8, NIRGAN_B200_GRAD_AMAX) computed on
 the device by ng_grad_scale_pow2: it is applied when the fp32 output gradient enters the plan and divided
 out exactly (the plan is linear in dout) when weight / input gradients are exported as fp32.
 """
 from __future__ import annotations
-
-from typing import List
 
 import torch
 
@@ -21,156 +26,128 @@ def _stream(t):
 
 
 # parameters whose arena slot has been handed to autograd during the CURRENT backward pass (cleared by an engine
-# callback when the pass ends): a parameter reached twice in one pass (the PatchGAN sees the fake and the real batch)
-# must not be given the same memory twice -- autograd would sum two aliases of it
+# callback when the pass ends): a parameter reached twice in one pass must not be given the same memory twice --
+# autograd would sum two aliases of it
 _LENT: set = set()
 
 
-def _slot_of(p: torch.nn.Parameter):
-    slot = getattr(p, "_b200_grad_slot", None)
-    return slot if (slot is not None and slot.device == p.device) else None
+def _lend(p: torch.nn.Parameter) -> bool:
+    """Decide how this backward pass delivers the gradient of `p`: True = the export overwrites the slot and autograd
+    adopts a view of it; False = the export accumulates into the slot (already lent in this pass, or .grad lives there)
+    and autograd receives None."""
+    slot = p._b200_grad_slot
+    if id(p) in _LENT or (p.grad is not None and p.grad.data_ptr() == slot.data_ptr()):
+        return False
+    if not _LENT:
+        torch.autograd.Variable._execution_engine.queue_callback(_LENT.clear)
+    _LENT.add(id(p))
+    return True
 
 
-def _grad_dst(p: torch.nn.Parameter) -> torch.Tensor:
-    """Where the fp32 gradient of `p` is written: a fresh view of its slot in the optimizer's flat arena
-    (optim.B200Adam) the first time the parameter is reached in a backward pass and when no .grad is live -- autograd
-    then adopts the view as p.grad without a copy -- else a new tensor (finished by _grad_done)."""
-    slot = _slot_of(p)
-    if slot is not None and p.grad is None and id(p) not in _LENT:
-        if not _LENT:
-            torch.autograd.Variable._execution_engine.queue_callback(_LENT.clear)
-        _LENT.add(id(p))
-        return slot.view_as(slot)
-    return torch.empty_like(p, dtype=torch.float32)
-
-
-def _grad_done(p: torch.nn.Parameter, g: torch.Tensor):
-    """What to return to autograd for `p`: the tensor itself, or None after adding it into the slot that an earlier
-    function of this pass already handed over (None = zero contribution; the sum lives in the arena)."""
-    slot = _slot_of(p)
-    if slot is not None and g.data_ptr() != slot.data_ptr() and p.grad is None and id(p) in _LENT:
-        slot.add_(g)
-        return None
-    return g
-
-
-def _grad_fill(p: torch.nn.Parameter, value) -> torch.Tensor:
-    dst = _grad_dst(p)
-    if value is None:
-        dst.zero_()
-    else:
-        dst.copy_(value.reshape(dst.shape))
-    return _grad_done(p, dst)
-
-
-def _export_weight_grads(graph, bwd_plan, params: List[torch.nn.Parameter]) -> dict:
-    """Packed fp32 weight gradients -> reference-layout fp32 tensors keyed by parameter id (times the inverse of the
-    adaptive gradient scale, read on the device)."""
-    st = graph.stream
+def _deliver(bwd_plan, params) -> dict:
+    """Set the accumulate cells of the plan's gradient exports for this pass; returns {id(p): tensor | None} for the
+    parameters the plan exports plus the identically-zero ones."""
     out = {}
-    inv = 1.0
-    gs = bwd_plan.records.get("gscale")
-    dev_inv = gs.data_ptr() + 4 if gs is not None else None
-    for i, dwp in bwd_plan.records["dw"].items():
-        u = graph.units[i]
-        w = u.conv.weight
-        gw = _grad_dst(w)
-        d0, d1, kh, kw = w.shape
-        if u.pack == "rowmerged":
-            L.call("ng_unpack_weight_grad_rowmerged", dwp.data_ptr(), d0, d1, kh, kw, inv, dev_inv, gw.data_ptr(), st)
-        else:
-            L.call("ng_unpack_weight_grad", dwp.data_ptr(), d0, d1, kh, kw, u.pack, u.cout, u.x.C, inv, dev_inv,
-                   gw.data_ptr(), st)
-        out[id(w)] = _grad_done(w, gw)
-        if u.conv.bias is not None:
-            dbb = bwd_plan.records["db"].get(i)
-            if dbb is not None:
-                db = dbb[:u.conv.bias.numel()]
-                out[id(u.conv.bias)] = _grad_fill(u.conv.bias, db * gs[1] if gs is not None else db)
-            else:
-                # bias feeding InstanceNorm: its gradient is identically zero (the reference returns rounding noise)
-                out[id(u.conv.bias)] = _grad_fill(u.conv.bias, None)
-    th = bwd_plan.records.get("tap_head")
-    if th is not None:
-        # head as tap GEMM: dwp is [tap (64 stored)][channel]; the reference layout (1, C, kh, kw) is [channel][tap]
-        w = th["conv"].weight
-        gw = _grad_dst(w)
-        _, cin, kh, kw = w.shape
-        L.call("ng_unpack_weight_grad", th["dwp"].data_ptr(), cin, kh * kw, 1, 1, 1, 64, cin, inv, dev_inv,
-               gw.data_ptr(), st)
-        out[id(w)] = _grad_done(w, gw)
-        # every tap column of dz sums to sum(dy): the centre tap's column sum is the bias gradient
-        db = th["db"][th["center"]:th["center"] + 1]
-        out[id(th["conv"].bias)] = _grad_fill(th["conv"].bias, db * gs[1] if gs is not None else db)
+    need = {id(p) for p in params if p.requires_grad}
+    for p, beta in bwd_plan.records["exports"]:
+        if id(p) not in need:
+            beta.value = 0.0          # frozen parameter: its slot is scratch
+            continue
+        fresh = _lend(p)
+        beta.value = 0.0 if fresh else 1.0
+        out[id(p)] = p._b200_grad_slot.view_as(p) if fresh else None
+    for p in bwd_plan.records["zero_grads"]:
+        if id(p) in need:
+            out[id(p)] = p._b200_grad_slot.view_as(p) if _lend(p) else None      # the slot is never written: zeros
     return out
 
 
 class GeneratorFunction(torch.autograd.Function):
     @staticmethod
-    def run(module, runner, x, embeds, wrap_pad):
-        params = [p for p in module.parameters()]
-        return GeneratorFunction.apply(module, runner, wrap_pad, x, embeds, *params)
+    def run(module, runner, x, embeds, wrap_pad, reuse_token=None):
+        params = [p for p in module.parameters() if p is not getattr(module, "post_correction_param", None)]
+        return GeneratorFunction.apply(module, runner, wrap_pad, reuse_token, x, embeds, *params)
 
     @staticmethod
-    def forward(ctx, module, runner, wrap_pad, x, embeds, *params):
+    def forward(ctx, module, runner, wrap_pad, reuse_token, x, embeds, *params):
+        if x.requires_grad or (embeds is not None and embeds.requires_grad):
+            raise NotImplementedError("nirgan_b200: gradients w.r.t. the generator's inputs (tiles / embeddings) are not "
+                                      "part of the hot path (the reference trains the networks' parameters only)")
         _LENT.clear()                   # no backward pass is in flight during a forward (belt and braces)
-        c = runner.train_forward(x, embeds, wrap_pad)
-        runner._live += 1               # buffers of this context must survive until its backward (see _RunnerBase.trim)
+        c = runner.train_forward(x, embeds, wrap_pad, reuse_token=reuse_token)
+        c["live"] = True                # buffers of this context must survive until its backward
+        if c.get("pool") is not None:
+            c["pool"].live = c
+        runner._live += 1
         B, Cin, H, W = c["geom"]
-        fwd = c["fwd"]
         ctx.c, ctx.module, ctx.runner = c, module, runner
         ctx.params = params
-        ctx.has_embeds = embeds is not None
-        out = fwd.records["out"].view(B, 1, H, W)
-        if getattr(module, "post_correction", False):
-            raise NotImplementedError("nirgan_b200: training with post_correction is outside the hot path")
-        return out.clone()
+        # a view of the plan's static output buffer: valid until the next training forward of this shape
+        return c["fwd"].records["out"].view(B, 1, H, W)
 
     @staticmethod
     def backward(ctx, dout):
         c, module, runner = ctx.c, ctx.module, ctx.runner
-        g, bwd = c["graph"], c["bwd"]
+        bwd = c["bwd"]
         runner._live = max(0, runner._live - 1)
-        c["fresh"] = None               # a backward may follow only the forward that produced these activations
+        c["live"] = False
+        c["share_token"] = None         # a backward may follow only the forward that produced these activations
         st = _stream(dout)
-        c["dout"].view_as(dout).copy_(dout.float())
+        c["dout"].view_as(dout).copy_(dout)
         inj = bwd.records.get("inject")
         if inj is not None:
             inj["dscale"].zero_()
+        grads = _deliver(bwd, ctx.params)
         bwd.run_training(dout.device)
-        grads = _export_weight_grads(g, bwd, ctx.params)
         gs = bwd.records.get("gscale")
         dev_inv = gs.data_ptr() + 4 if gs is not None else None
         if inj is not None:
-            eng = runner._engine
             B = c["geom"][0]
             fc = module.fc
-            dW, db = _grad_dst(fc.weight), _grad_dst(fc.bias)
-            scratch = eng.buffers.get("gt.de128", B * 128 * 128, torch.float32)
-            L.call("ng_inject_bwd", inj["de_map"].data_ptr(), B, inj["H"], inj["W"], 1.0, dev_inv,
-                   c["fwd"].records["emb"].data_ptr(), scratch.data_ptr(), dW.data_ptr(), db.data_ptr(), st)
-            grads[id(fc.weight)], grads[id(fc.bias)] = _grad_done(fc.weight, dW), _grad_done(fc.bias, db)
-            if hasattr(module, "scale_param"):
-                ds = inj["dscale"] * gs[1] if gs is not None else inj["dscale"]
-                grads[id(module.scale_param)] = _grad_fill(module.scale_param, ds)
+            need = {id(p) for p in ctx.params if p.requires_grad}
+            scratch = c["de128"]
+            if id(fc.weight) in need or id(fc.bias) in need:
+                fw, fb = _lend(fc.weight), _lend(fc.bias)
+                dW = fc.weight._b200_grad_slot if fw else torch.empty_like(fc.weight)
+                db = fc.bias._b200_grad_slot if fb else torch.empty_like(fc.bias)
+                L.call("ng_inject_bwd", inj["de_map"].data_ptr(), B, inj["H"], inj["W"], 1.0, dev_inv,
+                       c["fwd"].records["emb"].data_ptr(), scratch.data_ptr(), dW.data_ptr(), db.data_ptr(), st)
+                if not fw:
+                    fc.weight._b200_grad_slot.add_(dW)       # rare: fc reached twice / .grad not cleared
+                if not fb:
+                    fc.bias._b200_grad_slot.add_(db)
+                grads[id(fc.weight)] = fc.weight._b200_grad_slot.view_as(fc.weight) if fw else None
+                grads[id(fc.bias)] = fc.bias._b200_grad_slot.view_as(fc.bias) if fb else None
+            sp = getattr(module, "scale_param", None)
+            if sp is not None and id(sp) in need:
+                fresh = _lend(sp)
+                L.call("ng_unpack_weight_grad", inj["dscale"].data_ptr(), 1, 1, 1, 1, 0, 1, 1, 1.0, dev_inv,
+                       0.0 if fresh else 1.0, sp._b200_grad_slot.data_ptr(), st)
+                grads[id(sp)] = sp._b200_grad_slot.view_as(sp) if fresh else None
         out = []
         for p in ctx.params:
             gp = grads.get(id(p))
             out.append(gp if (gp is not None and p.requires_grad) else None)
-        return (None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, *out)
 
 
 class DiscriminatorFunction(torch.autograd.Function):
-    @staticmethod
-    def run(module, runner, x):
-        params = [p for p in module.parameters()]
-        return DiscriminatorFunction.apply(module, runner, x, *params)
+    """forward(module, runner, struct, *tensors, *params): `tensors` are the unique input tensors of the parts
+    (PatchGANRunner.describe), `struct` says how they combine."""
 
     @staticmethod
-    def forward(ctx, module, runner, x, *params):
+    def run(module, runner, parts):
+        uniq, struct, Bp, ca, cb, H, W = runner.describe(parts)
+        params = [p for p in module.parameters()]
+        return DiscriminatorFunction.apply(module, runner, (struct, Bp, ca, cb, H, W), len(uniq), *uniq, *params)
+
+    @staticmethod
+    def forward(ctx, module, runner, desc, n_in, *rest):
         _LENT.clear()
+        uniq, params = rest[:n_in], rest[n_in:]
+        struct, Bp, ca, cb, H, W = desc
         need_dw = any(p.requires_grad for p in params)
-        need_dx = x.requires_grad
+        need_dx = any(t.requires_grad for t in uniq)
         if runner._live == 0 and runner._engine is not None:
             runner.trim(runner._engine)
         slot = runner._live
@@ -178,36 +155,47 @@ class DiscriminatorFunction(torch.autograd.Function):
             raise RuntimeError("nirgan_b200: 8 discriminator forwards are waiting for their backward; call "
                                "netD.reset_training_slots() if those graphs were dropped")
         runner._live += 1
-        c = runner.train_context(x, slot, need_dw, need_dx)
-        B, Cin, H, W = c["geom"]
-        st = _stream(x)
-        c["fwd"].records["src"].view(B, Cin, H, W).copy_(x.detach().float())
-        c["fwd"].run_training(x.device)
+        chans = tuple(t.shape[1] for t in uniq)
+        c = runner.train_context((struct, chans, Bp, ca, cb, H, W), slot, need_dw, need_dx, uniq[0].device)
+        runner.load_inputs(c["graph"], uniq)
+        c["fwd"].run_training(uniq[0].device)
         ctx.c, ctx.module, ctx.runner, ctx.params = c, module, runner, params
         ctx.need_dw, ctx.need_dx = need_dw, need_dx
+        ctx.desc, ctx.n_in = desc, n_in
+        ctx.in_needs = tuple(bool(t.requires_grad) for t in uniq)
+        B = len(struct) * Bp
         Ho, Wo = c["graph"].records["out_hw"]
-        return c["graph"].units[-1].out_f32.view(B, 1, Ho, Wo).clone()
+        return c["graph"].units[-1].out_f32.view(B, 1, Ho, Wo)
 
     @staticmethod
     def backward(ctx, dout):
         c, runner = ctx.c, ctx.runner
-        g, bwd = c["graph"], c["bwd"]
+        bwd = c["bwd"]
         st = _stream(dout)
-        c["dout"].view_as(dout).copy_(dout.float())
+        c["dout"].view_as(dout).copy_(dout)
+        grads = _deliver(bwd, ctx.params) if ctx.need_dw else {}
         bwd.run_training(dout.device)
         runner._live = max(0, runner._live - 1)
-        grads = _export_weight_grads(g, bwd, ctx.params) if ctx.need_dw else {}
         gs = bwd.records.get("gscale")
         dev_inv = gs.data_ptr() + 4 if gs is not None else None
-        dx = None
+        dxs = [None] * ctx.n_in
         if ctx.need_dx:
-            B, Cin, H, W = c["geom"]
-            gx = bwd.records["dx"]
-            dx = torch.empty(B, Cin, H, W, dtype=torch.float32, device=dout.device)
-            L.call("ng_grad_to_nchw", gx.t.data_ptr(), runner._engine.dt_enum, B, H, W, gx.C, Cin, 1.0, dev_inv,
-                   dx.data_ptr(), st)
+            struct, Bp, ca, cb, H, W = ctx.desc
+            gx = bwd.records["dx"]                     # [nparts*Bp][H][W][16] gradient of the prepared input
+            esz = gx.t.element_size()
+            for i, (ia, ib) in enumerate(struct):
+                for j, c0, cn in ((ia, 0, ca), (ib, ca, cb)):
+                    if j < 0 or not ctx.in_needs[j]:
+                        continue
+                    if dxs[j] is not None:
+                        raise NotImplementedError("nirgan_b200: one tensor feeding two discriminator parts with "
+                                                  "requires_grad is not supported")
+                    dx = torch.empty(Bp, cn, H, W, dtype=torch.float32, device=dout.device)
+                    L.call("ng_grad_to_nchw", gx.t.data_ptr() + i * Bp * H * W * gx.C * esz, runner._engine.dt_enum, Bp,
+                           H, W, gx.C, c0, cn, 1.0, dev_inv, dx.data_ptr(), st)
+                    dxs[j] = dx
         out = []
         for p in ctx.params:
             gp = grads.get(id(p))
             out.append(gp if (gp is not None and p.requires_grad) else None)
-        return (None, None, dx, *out)
+        return (None, None, None, None, *dxs, *out)

@@ -11,6 +11,8 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (sm_100a) GPU")
+    config.addinivalue_line("markers", "slow: about a minute of host time (full-size CPU oracle evaluation)")
+    config.addinivalue_line("markers", "multigpu: needs at least two GPUs in the box (skipped otherwise)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -68,9 +68,20 @@ def _worker(rank, world, port, q):
     ps[0].grad = torch.full((5, 3), float(rank + 1))
     ps[1].grad = torch.arange(7.0) * (rank + 1)
     allreduce_gradients(ps)          # third parameter has no grad: skipped
+    # bucketed exchange of a flat arena (the training path): buckets go out in reverse order as the backward pass reports
+    # "everything at or above this offset is final"; finish() sends the rest; the result is the SUM over ranks
+    from nirgan_b200.optim import BucketedAllReduce
+    flat = torch.arange(1000.0) * (rank + 1)
+    red = BucketedAllReduce(flat, min_bucket_elems=100)
+    red.ready(950)                   # 50 elements: below the bucket threshold, held back
+    held = red.buckets
+    red.ready(600)                   # [600, 1000) goes out
+    red.ready(580)                   # held back again
+    nb = red.finish()                # [0, 600)
+    bucket_ok = bool(torch.equal(flat, torch.arange(1000.0) * 3)) and held == 0 and nb == 2 and red.last_buckets == 2
     # plain numpy payloads: torch tensors travel through shared-memory handles that die with the worker
     q.put((rank, list(merged.keys()), {k: v.numpy().copy() for k, v in merged.items()}, ps[0].grad.numpy().copy(),
-           ps[1].grad.numpy().copy(), len(local)))
+           ps[1].grad.numpy().copy(), len(local), bucket_ok))
     dist.destroy_process_group()
 
 
@@ -89,7 +100,8 @@ def test_two_ranks_gloo_sharded_inference_and_grad_allreduce():
     tiles = _tiles()
     seq = {synth.tile_id(n): _fake_model(tiles[n][None])[0] for n in sorted(tiles)}
     assert sum(r[5] for r in res) == len(tiles)
-    for rank, keys, merged, g0, g1, _ in res:
+    assert all(r[6] for r in res), "bucketed all-reduce over gloo"
+    for rank, keys, merged, g0, g1, _, _ in res:
         assert keys == list(seq.keys())                       # identical {id -> array} mapping on every rank
         for k in seq:
             assert torch.equal(torch.from_numpy(merged[k]), seq[k])

@@ -12,7 +12,7 @@ from nirgan_b200 import _lib as L
 from nirgan_b200.model import networks
 from nirgan_b200.model.generator_inject import define_G_inject
 
-from test_gpu_models import inject_config
+from nirgan_b200.config import satclip_inject_config as inject_config
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/nirgan_b200.h but not exported"
     assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
-    assert lib.ng_version() == 100
+    assert lib.ng_version() == 101
 
 
 def test_conv_args_struct_layout_matches_header():

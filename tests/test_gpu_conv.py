@@ -258,9 +258,13 @@ def test_stem_rowmerged(impl, dtype, wrap, H, W):
     assert float((got - ref).abs().max()) <= _tol(dtype, ref)
     # weight-gradient unpack is the exact inverse of the row-merged pack
     back = torch.empty_like(w)
-    L.call("ng_unpack_weight_grad_rowmerged", wp.float().contiguous().data_ptr(), 64, 3, 7, 7, 1.0, None,
+    L.call("ng_unpack_weight_grad_rowmerged", wp.float().contiguous().data_ptr(), 64, 3, 7, 7, 1.0, None, 0.0,
            back.data_ptr(), Hh.stream())
     assert torch.equal(back, w)
+    # beta = 1 accumulates (autograd's AccumulateGrad for a parameter reached twice in one pass)
+    L.call("ng_unpack_weight_grad_rowmerged", wp.float().contiguous().data_ptr(), 64, 3, 7, 7, 0.5, None, 1.0,
+           back.data_ptr(), Hh.stream())
+    assert torch.equal(back, w + 0.5 * w)
 
 
 @pytest.mark.parametrize("impl,dtype", _impls())

@@ -256,7 +256,7 @@ def test_wgrad_matches_autograd(kind):
     L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), db.data_ptr(), None, 0, Hh.stream())
     dw = torch.empty_like(w)
     n_axis = 1 if form == L.FORM_PHASED else 0
-    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, co_pad, Cin, 1.0, None,
+    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, co_pad, Cin, 1.0, None, 0.0,
            dw.data_ptr(), Hh.stream())
     rel = float((dw - w.grad).norm() / w.grad.norm())
     assert rel <= 2e-5, rel
@@ -318,9 +318,14 @@ def test_wgrad_tc_matches_autograd(kind, dt):
     L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), db.data_ptr(), ws.data_ptr(), need, Hh.stream())
     dw = torch.empty_like(w)
     n_axis = 1 if form == L.FORM_PHASED else 0
-    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, Cout, Cin, 1.0, None,
+    dw.fill_(float("nan"))           # beta = 0 must not read the destination
+    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, Cout, Cin, 1.0, None, 0.0,
            dw.data_ptr(), Hh.stream())
     assert bool(torch.isfinite(dw).all())
+    dw2 = dw.clone()
+    L.call("ng_unpack_weight_grad", dwp.data_ptr(), w.shape[0], w.shape[1], K, K, n_axis, Cout, Cin, 1.0, None, 1.0,
+           dw2.data_ptr(), Hh.stream())
+    assert torch.equal(dw2, dw + dw)
     rel = float((dw - w.grad).norm() / w.grad.norm())
     assert rel <= 1e-5, rel          # identical 16-bit operands, fp32 accumulation on both sides
     assert float((db - dy.sum(dim=(0, 2, 3))).abs().max()) <= 1e-3

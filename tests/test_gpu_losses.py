@@ -93,7 +93,7 @@ def test_training_step_with_ssim_and_hist_terms(golden_dir):
     """G-pass loss with lambda_ssim / lambda_hist > 0 (model/pix2pix.py:231-243) equals the sum of its parts computed by
     the oracle on the prediction the model produced, and the step runs through backward + Adam."""
     from nirgan_b200.model.pix2pix import Px2Px
-    from test_gpu_train import _cfg
+    from nirgan_b200.config import px2px_config as _cfg
     cfg = _cfg(lambda_rs=0.0)
     cfg.base_configs.lambda_ssim, cfg.base_configs.lambda_hist = 2.0, 50.0
     torch.manual_seed(0)

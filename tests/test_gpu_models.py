@@ -5,8 +5,6 @@ low-precision (tensor-core) mode, <= 1e-4 in the fp32 verification mode; derived
 [-1,1], utils/logging_helpers.py:161-166) mean-abs <= 5e-3.  Checkers: golden fixtures produced by the real
 reference modules (tests/golden, see oracle/pin_against_reference.py) and the CPU oracle on seeded inputs.
 """
-import types
-
 import numpy as np
 import pytest
 import torch
@@ -23,24 +21,7 @@ MODES = [pytest.param("fp32", "simt", 1e-4, 2e-5, id="fp32-verify"),
          pytest.param("bf16", "tc", 1.2e-1, 2e-2, id="bf16-tc")]
 
 
-def _ns(d):
-    return types.SimpleNamespace(**{k: _ns(v) if isinstance(d[k], dict) else v for k, v in d.items()})
-
-
-def inject_config(scale_init=0.01):
-    return _ns({"base_configs": {"input_nc": 3, "output_nc": 1, "ngf": 64, "ndf": 64, "netD": "basic",
-                                 "netG": "resnet_9blocks", "norm": "instance", "no_dropout": True,
-                                 "init_type": "normal", "init_gain": 0.02, "n_layers_D": 3, "gan_mode": "lsgan",
-                                 "lr": 2e-4, "beta1": 0.5, "lambda_GAN": 1.0, "lambda_L1": 100.0,
-                                 "lambda_ssim": 0.0, "lambda_hist": 0.0, "lambda_rs_losses": 1.0,
-                                 "rs_losses_criterium": "l1", "isTrain": True,
-                                 "internal_rs_loss_weights": {"lambda_ndvi": 0.33, "lambda_ndwi": 0.33,
-                                                              "lambda_evi": 0.33, "lambda_savi": 0.0,
-                                                              "lambda_msavi": 0.0, "lambda_gndvi": 0.0}},
-                "satclip": {"use_satclip": True, "satclip_style": "inject", "satclip_inject_style": "multiply",
-                            "post_correction": False, "post_correction_init": 1.0, "scaling_param": True,
-                            "scaling_param_init": scale_init},
-                "Data": {"padding": True, "padding_amount": 10}})
+from nirgan_b200.config import satclip_inject_config as inject_config  # noqa: E402  (the reference's SatCLIP YAML)
 
 
 def make_G(sd, precision, impl, inject=False):

@@ -90,7 +90,7 @@ def test_px2px_predict_step_takes_coordinates():
     """predict_step(rgb, coords) (model/pix2pix.py:134-163, extract_batch :448-459): the attached encoder produces the
     embeddings that are injected; identical to passing the embeddings precomputed; an inject model with neither raises."""
     from nirgan_b200.model.pix2pix import Px2Px
-    from test_gpu_models import inject_config
+    from nirgan_b200.config import satclip_inject_config as inject_config
     torch.manual_seed(0)
     model = Px2Px(inject_config()).cuda().eval()
     sd = S.random_siren_state_dict(100, 256, 256, 2, seed=2)

@@ -5,8 +5,6 @@ d|pred-nir|/dpred = sign(.) flips on rounding noise and 23 InstanceNorm backward
 (oracle/pin_against_reference.py) -> fp32 verification mode: rel-L2 <= 1e-2; fp16 tensor-core mode:
 cosine similarity >= 0.99 and rel-L2 <= 0.15.
 """
-import types
-
 import numpy as np
 import pytest
 import torch
@@ -105,13 +103,9 @@ def test_in_bwd_unit_matches_autograd(case):
         assert float((db - de128.sum(0)).abs().max()) <= 1e-3 * max(1.0, float(de128.sum(0).abs().max()))
 
 
-def _cfg(lambda_rs=1.0, inject=False):
-    from test_gpu_models import inject_config
-    c = inject_config()
-    c.base_configs.lambda_rs_losses = lambda_rs
-    if not inject:
-        c.satclip.use_satclip = False
-    return c
+def _cfg(lambda_rs=1.0, inject=False, **kw):
+    from nirgan_b200.config import px2px_config
+    return px2px_config(lambda_rs=lambda_rs, inject=inject, **kw)
 
 
 def _load(model, sd_g, sd_d):
@@ -292,11 +286,11 @@ def test_g_forward_reuse_matches_double_evaluation():
             assert _relerr(x, y) <= 2e-3, _relerr(x, y)
     # weights change -> the next shared forward recomputes and equals the plain inference forward bit for bit
     model.reuse_g_forward = True
-    before = model.netG.forward_shared(rgb, None, wrap_pad=10)
-    again = model.netG.forward_shared(rgb, None, wrap_pad=10)
+    before = model.netG.forward_shared(rgb, None, wrap_pad=10)[0].clone()
+    again = model.netG.forward_shared(rgb, None, wrap_pad=10)[0].clone()
     assert torch.equal(before, again)
     opt_g.step()
-    after = model.netG.forward_shared(rgb, None, wrap_pad=10)
+    after = model.netG.forward_shared(rgb, None, wrap_pad=10)[0].clone()
     assert not torch.equal(before, after)
     with torch.no_grad():
         plain = model.forward(rgb)
@@ -415,3 +409,281 @@ def test_half_batch_training_forward_equals_full_batch(monkeypatch):
     for n in res["0"][1]:
         a, b = res["0"][1][n], res["1"][1][n]
         assert float((a - b).abs().max()) <= 1e-4 * (float(a.abs().max()) + 1e-30), n
+
+
+# =====================================================================================================================
+# round 2: tighter gradient parity, full-size config 4 against the oracle, the new training-path plumbing
+# =====================================================================================================================
+def _record(name, payload):
+    """Measured parity values are kept (gpurun_out/ on the GPU box; copied to profiles/ by the builder)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, name), "w") as f:
+            json.dump(payload, f, indent=1)
+
+
+def _fresh_model(cfg, sd_g, sd_d, precision, impl):
+    from nirgan_b200.model.pix2pix import Px2Px
+    model = Px2Px(cfg)
+    _load(model, sd_g, sd_d)
+    model = model.cuda().train()
+    model.netG.configure_b200(precision=precision, impl=impl)
+    model.netD.configure_b200(precision=precision, impl=impl)
+    return model
+
+
+def test_fp16_gradients_without_the_l1_sign_effect():
+    """fp16 tensor-core gradients against the fp32 CPU oracle on a SMOOTH objective (lambda_L1 = lambda_rs = 0: the G loss
+    is the LSGAN term alone), which removes the sign(pred - nir) flips that dominate the golden-step comparison and
+    isolates the fp16 dgrad / wgrad / norm-backward kernels.  Gate: cosine >= 0.999 and rel-L2 <= 3e-2 for every weight
+    gradient of G and D (SURVEY 8d asks 0.999 / 1e-2 'to be set relative'; the measured values are recorded)."""
+    import nirgan_oracle as O
+    sd_g = O.random_state_dict(O.generator_param_shapes(), seed=61)
+    sd_d = O.random_state_dict(O.discriminator_param_shapes(), seed=62)
+    gen = torch.Generator().manual_seed(11)
+    rgb = torch.rand(4, 3, 64, 64, generator=gen)
+    nir = torch.rand(4, 1, 64, 64, generator=gen)
+    cfg_o = dict(O.DEFAULT_LOSS_CFG, lambda_L1=0.0, lambda_rs_losses=0.0)
+    tr = O.OracleTrainer(sd_g, sd_d, cfg=cfg_o)
+    ref = tr.step(rgb, nir, apply_update=False)
+    model = _fresh_model(_cfg(lambda_rs=0.0, lambda_l1=0.0), sd_g, sd_d, "fp16", "tc")
+    batch = {"rgb": rgb.cuda(), "nir": nir.cuda()}
+    ld = model.training_step(batch, 0, 0)
+    ld.backward()
+    report = {"D": {}, "G": {}}
+    for k, p in model.netD.named_parameters():
+        if k.endswith("weight"):
+            r = ref["grads_d"][k].cuda()
+            report["D"][k] = (_cos(p.grad, r), _relerr(p.grad, r))
+    for p in model.parameters():
+        p.grad = None
+    lg = model.training_step(batch, 0, 1)
+    lg.backward()
+    for k, p in model.netG.named_parameters():
+        if k.endswith("weight"):
+            r = ref["grads_g"][k].cuda()
+            report["G"][k] = (_cos(p.grad, r), _relerr(p.grad, r))
+    worst = {net: (min(v[0] for v in d.values()), max(v[1] for v in d.values())) for net, d in report.items()}
+    print("fp16 gradient parity, smooth objective (min cos, max rel-L2):", worst)
+    _record("fp16_grad_parity_smooth.json", {"loss_D": [float(ld), float(ref["loss_D"])],
+                                             "loss_G": [float(lg), float(ref["loss_G"])], "worst": worst, "per_tensor": report})
+    assert abs(float(ld) - float(ref["loss_D"])) <= 2e-2 * max(1.0, abs(float(ref["loss_D"])))
+    assert abs(float(lg) - float(ref["loss_G"])) <= 2e-2 * max(1.0, abs(float(ref["loss_G"])))
+    for net in ("D", "G"):
+        for k, (c, r) in report[net].items():
+            assert c >= 0.999 and r <= 3e-2, (net, k, c, r)
+
+
+@pytest.mark.slow
+def test_config4_full_size_step_vs_oracle():
+    """BASELINE.json configs[3] at its full size (batch 32, 256x256, all loss terms) against the CPU oracle: loss_D,
+    loss_G, the prediction and three gradients (~1 min of host time for the oracle)."""
+    import nirgan_oracle as O
+    sd_g = O.random_state_dict(O.generator_param_shapes(), seed=71)
+    sd_d = O.random_state_dict(O.discriminator_param_shapes(), seed=72)
+    gen = torch.Generator().manual_seed(12)
+    rgb = torch.rand(32, 3, 256, 256, generator=gen)
+    nir = torch.rand(32, 1, 256, 256, generator=gen)
+    torch.set_num_threads(max(1, (__import__("os").cpu_count() or 1)))
+    tr = O.OracleTrainer(sd_g, sd_d)
+    ref = tr.step(rgb, nir, apply_update=False)
+    model = _fresh_model(_cfg(), sd_g, sd_d, "fp16", "tc")
+    batch = {"rgb": rgb.cuda(), "nir": nir.cuda()}
+    ld = model.training_step(batch, 0, 0)
+    ld.backward()
+    gd = model.netD.model[8].weight.grad.detach().clone()
+    for p in model.parameters():
+        p.grad = None
+    lg = model.training_step(batch, 0, 1)
+    lg.backward()
+    with torch.no_grad():
+        model.eval()
+        pred = model.forward(batch["rgb"]).cpu()
+        model.train()
+    d = (pred - ref["pred"]).abs()
+    gg = dict(model.netG.named_parameters())
+    rep = {"loss_D": [float(ld), float(ref["loss_D"])], "loss_G": [float(lg), float(ref["loss_G"])],
+           "pred_max_abs": float(d.max()), "pred_mean_abs": float(d.mean()),
+           "gD.model.8.weight": (_cos(gd, ref["grads_d"]["model.8.weight"].cuda()),
+                                 _relerr(gd, ref["grads_d"]["model.8.weight"].cuda()))}
+    for k in ("model.26.weight", "model.10.conv_block.1.weight"):
+        r = ref["grads_g"][k].cuda()
+        rep["gG." + k] = (_cos(gg[k].grad, r), _relerr(gg[k].grad, r))
+    print("config 4 full size vs oracle:", rep)
+    _record("config4_full_size_parity.json", rep)
+    assert abs(rep["loss_D"][0] - rep["loss_D"][1]) <= 2e-2 * max(1.0, abs(rep["loss_D"][1]))
+    assert abs(rep["loss_G"][0] - rep["loss_G"][1]) <= 3e-2 * abs(rep["loss_G"][1])
+    assert rep["pred_max_abs"] <= 2e-2 and rep["pred_mean_abs"] <= 2e-3
+    assert rep["gD.model.8.weight"][0] >= 0.99 and rep["gD.model.8.weight"][1] <= 0.15
+    for k in ("gG.model.26.weight", "gG.model.10.conv_block.1.weight"):
+        assert rep[k][0] >= 0.97 and rep[k][1] <= 0.25, rep
+
+
+def test_discriminator_parts_equal_concatenated_calls():
+    """netD(rgb, x) == netD(torch.cat((rgb, x), 1)) and forward_parts stacks the parts along the batch with every sample's
+    bits unchanged (per-sample InstanceNorm, per-image tiling)."""
+    from nirgan_b200.model import networks
+    torch.manual_seed(3)
+    netD = networks.define_D(4, 64, "basic", 3, "instance", "normal", 0.02).cuda().eval()
+    netD.configure_b200(precision="fp16", impl="tc")
+    g = torch.Generator().manual_seed(5)
+    rgb = torch.rand(3, 3, 64, 64, generator=g).cuda()
+    a = torch.rand(3, 1, 64, 64, generator=g).cuda()
+    b = torch.rand(3, 1, 64, 64, generator=g).cuda()
+    with torch.no_grad():
+        ya = netD(torch.cat((rgb, a), 1))
+        yb = netD(torch.cat((rgb, b), 1))
+        ya2 = netD(rgb, a)
+        both = netD.forward_parts([(rgb, a), (rgb, b)])
+    assert torch.equal(ya, ya2)
+    assert torch.equal(both[:3], ya) and torch.equal(both[3:], yb)
+
+
+def test_post_correction_trains():
+    """Training with the learnable post-correction scalar (model/generator_inject.py:97-100,133-134): with a linear probe
+    loss sum(w * pred), d/d(param) = sum(w * tanh_out) and every other gradient is the plain one times the parameter."""
+    import nirgan_oracle as O
+    from nirgan_b200.config import satclip_inject_config
+    from nirgan_b200.model.generator_inject import define_G_inject
+    sd = O.random_state_dict(O.generator_param_shapes(inject=True), seed=81, scale_param=0.5)
+    gen = torch.Generator().manual_seed(13)
+    x = torch.rand(2, 3, 32, 32, generator=gen).cuda()
+    emb = torch.randn(2, 256, generator=gen).cuda()
+    w = torch.randn(2, 1, 32, 32, generator=gen).cuda()
+    res = {}
+    for pc in (False, True):
+        net = define_G_inject(satclip_inject_config(post_correction=pc, post_correction_init=0.7))
+        net.load_state_dict(sd, strict=False)
+        net = net.cuda().train().configure_b200(precision="fp32", impl="simt")
+        y = net(x, emb, wrap_pad=0)
+        (y * w).sum().backward()
+        res[pc] = (y.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters()})
+    y0, g0 = res[False]
+    y1, g1 = res[True]
+    assert float((y1 - 0.7 * y0).abs().max()) <= 1e-6
+    assert abs(float(g1["post_correction_param"]) - float((w * y0).sum())) <= 1e-3 * abs(float((w * y0).sum()))
+    for k in ("model.1.weight", "model.10.conv_block.1.weight", "fc.weight", "scale_param"):
+        assert _relerr(g1[k], 0.7 * g0[k]) <= 1e-5, k
+
+
+def test_shared_forward_token_rules():
+    """The D pass's generator activations are adopted by the G pass only through the token handed over explicitly: any
+    other forward of that shape, a weight update or a foreign token forces a recompute; two grad-enabled forwards without
+    a backward in between raise instead of silently overwriting each other."""
+    import nirgan_oracle as O
+    from nirgan_b200.model import networks
+    sd = O.random_state_dict(O.generator_param_shapes(), seed=91)
+    net = networks.define_G(3, 1, 64, "resnet_9blocks", "instance", False, "normal", 0.02)
+    net.load_state_dict(sd)
+    net = net.cuda().train().configure_b200(precision="fp16", impl="tc")
+    from nirgan_b200.runners import GeneratorRunner
+    runner = net._get_runner(GeneratorRunner)
+    g = torch.Generator().manual_seed(14)
+    x1 = torch.rand(2, 3, 32, 32, generator=g).cuda()
+    x2 = torch.rand(2, 3, 32, 32, generator=g).cuda()
+    p1, tok = net.forward_shared(x1, None, wrap_pad=0)
+    p1 = p1.clone()
+    # a forward on ANOTHER batch with a stale / missing token recomputes (no silent reuse of x1's activations)
+    y2 = net(x2, wrap_pad=0)
+    with torch.no_grad():
+        net.eval()
+        want2 = net(x2, wrap_pad=0)
+        net.train()
+    assert torch.equal(y2.detach(), want2)
+    y2.sum().backward()
+    # the token died with that forward
+    y1 = net(x1, wrap_pad=0, reuse_token=tok)
+    assert torch.equal(y1.detach(), p1)          # recomputed: same values, and not x2's
+    with pytest.raises(RuntimeError, match="waiting for its backward"):
+        net(x1, wrap_pad=0)
+    net.reset_training_slots()
+    # valid hand-over: the plan is not run again (the input staging buffer still holds the shared call's tiles)
+    _, tok = net.forward_shared(x1, None, wrap_pad=0)
+    ctx = list(runner._train.values())[0]
+    ctx["fwd"].records["src"].fill_(123.0)       # would change the output if the plan ran again
+    y = net(x1, wrap_pad=0, reuse_token=tok)
+    assert torch.equal(y.detach(), p1)
+    y.sum().backward()
+    with pytest.raises(NotImplementedError):
+        net(x1.clone().requires_grad_(True), wrap_pad=0)
+
+
+def test_gradient_accumulation_and_foreign_grads():
+    """AccumulateGrad semantics of the in-plan gradient export: grads adopted from the arena (zero_grad(set_to_none)),
+    accumulated in place when .grad was not cleared, and added into a user-assigned .grad tensor."""
+    import nirgan_oracle as O
+    sd_g = O.random_state_dict(O.generator_param_shapes(), seed=101)
+    sd_d = O.random_state_dict(O.discriminator_param_shapes(), seed=102)
+    model = _fresh_model(_cfg(), sd_g, sd_d, "fp32", "simt")
+    gen = torch.Generator().manual_seed(15)
+    batch = {"rgb": torch.rand(2, 3, 32, 32, generator=gen).cuda(), "nir": torch.rand(2, 1, 32, 32, generator=gen).cuda()}
+    opt_d, opt_g = model.configure_optimizers()
+    w = model.netG.model[10].conv_block[1].weight
+    model.training_step(batch, 0, 1).backward()
+    g1 = w.grad.detach().clone()
+    assert w.grad.data_ptr() == w._b200_grad_slot.data_ptr()          # adopted, not copied
+    model.training_step(batch, 0, 1).backward()                        # .grad not cleared: accumulates in the slot
+    assert _relerr(w.grad, 2 * g1) <= 1e-5
+    for p in model.netG.parameters():
+        p.grad = None
+    w.grad = torch.ones_like(w)                                        # a foreign .grad tensor
+    model.training_step(batch, 0, 1).backward()
+    assert _relerr(w.grad, 1 + g1) <= 1e-5
+    # the discriminator reached twice in one backward pass (reference-style two calls)
+    for p in model.parameters():
+        p.grad = None
+    model.netD.reset_training_slots()
+    rgb, nir = batch["rgb"], batch["nir"]
+    pa = model.netD(torch.cat((rgb, nir), 1))
+    pb = model.netD(torch.cat((rgb, 1 - nir), 1))
+    (model.criterionGAN(pa, True) + model.criterionGAN(pb, False)).backward()
+    two = model.netD.model[8].weight.grad.detach().clone()
+    for p in model.parameters():
+        p.grad = None
+    model.netD.reset_training_slots()
+    both = model.netD.forward_parts([(rgb, nir), (rgb, 1 - nir)])
+    (model.criterionGAN(both[:2], True) + model.criterionGAN(both[2:], False)).backward()
+    assert _relerr(model.netD.model[8].weight.grad, two) <= 1e-4
+
+
+def test_b200adam_state_dict_round_trip_matches_torch_adam():
+    """Checkpoint resume (reference train.py:67-69,126): save / load the optimizer state, keep stepping, stay equal to
+    torch.optim.Adam.  Also the parameter-count edge: tensors whose numel is not a multiple of 4 (arena padding)."""
+    from nirgan_b200.optim import B200Adam
+    torch.manual_seed(0)
+    shapes = [(5, 3), (1,), (7,), (64, 4, 4, 4), ()]
+    ref_p = [torch.nn.Parameter(torch.randn(*s).cuda()) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = torch.optim.Adam(ref_p, lr=2e-4, betas=(0.5, 0.999))
+    ours = B200Adam(our_p, lr=2e-4, betas=(0.5, 0.999))
+
+    def step(opt, ps, seed):
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        for p in ps:
+            gr = torch.randn(p.shape, generator=g, device="cuda")
+            if hasattr(p, "_b200_grad_slot"):
+                p._b200_grad_slot.copy_(gr)
+                p.grad = p._b200_grad_slot
+            else:
+                p.grad = gr
+        opt.step()
+
+    for s in range(3):
+        step(ref, ref_p, s)
+        step(ours, our_p, s)
+    assert ours.fast_steps == 3
+    # neighbours of every small parameter are untouched by the padding lanes of the multi-tensor kernel
+    state = ours.state_dict()
+    fresh_p = [torch.nn.Parameter(p.detach().clone()) for p in our_p]
+    fresh = B200Adam(fresh_p, lr=2e-4, betas=(0.5, 0.999))
+    fresh.load_state_dict(state)
+    for s in range(3, 6):
+        step(ref, ref_p, s)
+        step(fresh, fresh_p, s)
+    assert fresh.fast_steps == 3 and int(fresh._st.step_dev.item()) == 6
+    for a, b in zip(ref_p, fresh_p):
+        assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(a.abs().max()))
+    assert fresh.state[fresh_p[0]]["step"] == 6

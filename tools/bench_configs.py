@@ -7,8 +7,8 @@ tools/bench_configs.py --config 3|5 ...`, or directly for N=1).
             plain generator behind the pad-10 wrapper (532/266/133 pyramid), tiles staged on the device, sharded over
             ranks with NO collective.  value = 512x512 tiles/s over all ranks (also as 256x256-tile equivalents).
 --config 5  data-parallel Pix2Pix training step: batch 32 per GPU, per-step resolution drawn from a seeded sequence over
-            {128,192,256,384,512} (same on all ranks), one NCCL all-reduce (mean) of the D gradients and one of the G
-            gradients per step.  value = samples/s over all ranks.
+            {128,192,256,384,512} (same on all ranks), bucketed NCCL all-reduce of the D and of the G gradients overlapped with
+            the backward pass (nirgan_b200.trainer.Trainer).  value = samples/s over all ranks.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 """
 import argparse
@@ -53,8 +53,7 @@ def main():
     import nirgan_b200  # noqa: F401
     from nirgan_b200.model.pix2pix import Px2Px
     from nirgan_b200 import synth
-    from nirgan_b200.optim import allreduce_gradients
-    from test_gpu_train import _cfg
+    from nirgan_b200.config import px2px_config as _cfg
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -117,7 +116,9 @@ def main():
     else:
         model.train()
         B = args.batch or 32
-        opt_d, opt_g = model.configure_optimizers()
+        from nirgan_b200.trainer import Trainer
+        trainer = Trainer(model)
+        opt_d, opt_g = trainer.opt_d, trainer.opt_g
         sizes = [128, 192, 256, 384, 512]
         seq_gen = torch.Generator().manual_seed(1234)
         total = args.warmup + args.steps
@@ -128,20 +129,9 @@ def main():
                     "nir": torch.rand(B, 1, s, s, generator=gen, device=dev)} for s in sizes}
 
         def step(s):
-            batch = data[s]
-            opt_d.zero_grad(set_to_none=True)
-            ld = model.training_step(batch, 0, 0)
-            ld.backward()
-            allreduce_gradients(model.netD.parameters())
-            opt_d.step()
-            opt_g.zero_grad(set_to_none=True)
-            lg = model.training_step(batch, 0, 1)
-            lg.backward()
-            allreduce_gradients(model.netG.parameters())
-            opt_g.step()
-            return ld, lg
+            return trainer.step(data[s])
 
-        for s in sizes:
+        for s in sorted(sizes, reverse=True):      # largest first: the shared buffer pool is sized once
             step(s)
         for s in seq[:args.warmup]:
             step(s)

@@ -29,28 +29,22 @@ def main():
     args = ap.parse_args()
     import nirgan_b200  # noqa: F401
     from nirgan_b200.model.pix2pix import Px2Px
-    from test_gpu_train import _cfg
+    from nirgan_b200.config import px2px_config as _cfg
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     with contextlib.redirect_stdout(sys.stderr):
         model = Px2Px(_cfg()).to(dev).train()
     model.netG.configure_b200(precision=args.precision, impl=args.conv)
     model.netD.configure_b200(precision=args.precision, impl=args.conv)
-    opt_d, opt_g = model.configure_optimizers()
+    from nirgan_b200.trainer import Trainer
+    trainer = Trainer(model)
+    opt_d, opt_g = trainer.opt_d, trainer.opt_g
     g = torch.Generator().manual_seed(1)
     batch = {"rgb": torch.rand(args.batch, 3, args.tile, args.tile, generator=g).to(dev),
              "nir": torch.rand(args.batch, 1, args.tile, args.tile, generator=g).to(dev)}
 
     def step():
-        opt_d.zero_grad(set_to_none=True)
-        ld = model.training_step(batch, 0, 0)
-        ld.backward()
-        opt_d.step()
-        opt_g.zero_grad(set_to_none=True)
-        lg = model.training_step(batch, 0, 1)
-        lg.backward()
-        opt_g.step()
-        return ld, lg
+        return trainer.step(batch)
 
     for _ in range(args.warmup):
         step()
