@@ -526,8 +526,10 @@ def main():
     for i, (fn, a, name) in enumerate(plan.ops):
         by_name.setdefault(name, []).append(op_ms[i])
     # dominant kernel: the 18 ResnetBlock 3x3 convs (256->256 at H/4): 4.832 GFLOP per tile per launch
-    conv_idx = [i for i, (fn, a, name) in enumerate(plan.ops) if name == "ng_conv2d"]
-    res_idx = conv_idx[3:3 + 18]
+    import re
+    conv_idx = [i for i, (fn, a, name) in enumerate(plan.ops) if name in ("ng_conv2d", "ng_stem_conv")]
+    res_idx = [i for i in conv_idx if re.search(r"\.r\d+[ab]$", plan.labels[i])]
+    assert len(res_idx) == 18, [plan.labels[i] for i in conv_idx]
     Bc = plan.records["src"].numel() // (3 * TILE * TILE)      # tiles per plan run (batch slice)
 
     # average launch duration of one kernel family: its launches of a step back to back between ONE pair of events
@@ -567,7 +569,7 @@ def main():
         if name != "ng_in_apply":
             continue
         _, _, b_, h_, w_, c_ = a[:6]
-        res_, opad = a[9], a[15]
+        res_, opad = a[11], a[17]
         ap_bytes += b_ * c_ * esz * (h_ * w_ * (2 if res_ else 1) + (h_ + 2 * opad) * (w_ + 2 * opad))
     ap_idx = [i for i, (fn, a, name) in enumerate(plan.ops) if name == "ng_in_apply"]
     ap_ms = grouped_ms(ap_idx)

@@ -20,7 +20,7 @@
  *   ng_conv2d          nn.Conv2d / nn.ConvTranspose2d call sites  model/networks.py:342,349,360-363,367,
  *                      405-427 (ResnetBlock), 559-579 (NLayerDiscriminator) and their autograd dgrad
  *   ng_conv2d_wgrad    autograd weight gradient of the same call sites (model/pix2pix.py:165-257)
- *   ng_in_stats / ng_in_stats_finalize / ng_in_apply
+ *   ng_in_stats / ng_in_stats_finalize / ng_in_apply / ng_memset_zero
  *                      nn.InstanceNorm2d + ReLU/LeakyReLU + residual add + ReflectionPad2d
  *                      model/networks.py:29-30,341-344,350-351,405-434,567-576; the SatCLIP
  *                      injection x*(1+s*e) model/generator_inject.py:113-127
@@ -117,7 +117,16 @@ typedef struct ng_conv_args {
    * them zero again); mean_rstd: [B][Cout][2]; both NULL = off. */
   float* mean_rstd;
   int32_t* tile_counters;
+  /* optional fixed-point statistics accumulators (TC + RAW): [B][Cout][2] int64, ZERO before the launch
+   * (ng_memset_zero).  Every tile adds its per-channel sum * 2^NG_STAT_SUM_SHIFT and sum of squares *
+   * 2^NG_STAT_SQ_SHIFT with 64-bit integer atomics -- integer addition is associative, so the totals do not depend
+   * on the order in which tiles finish (deterministic, bit-identical across batch slices and shardings) -- and
+   * ng_in_apply turns them into (mean, rstd) itself: no ng_in_stats_finalize launch, stat_partials may be NULL. */
+  int64_t* stat_acc;
 } ng_conv_args;
+
+#define NG_STAT_SUM_SHIFT 24
+#define NG_STAT_SQ_SHIFT 20
 
 int         ng_version(void);
 const char* ng_last_error(void);
@@ -161,9 +170,20 @@ int ng_pack_weight_phasemerged(const float* src, int32_t Cin, int32_t Cout, int3
  * Conv2d(3->64, k7) (model/networks.py:341-342) and Px2Px_PL.forward's F.pad (model/pix2pix.py:91-93). */
 int ng_prep_stem(const float* src, int32_t cin, int32_t B, int32_t H, int32_t W, int32_t wrap_pad, int32_t halo,
                  int32_t KW, int32_t dtype, void* dst, void* stream);
-/* weights for the row-merged stem: fp32 [O][I][KH][KW] -> [kh][O][kw*8 + c] (zero padded to 64) */
-int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH, int32_t KW, int32_t dtype, void* dst,
-                             void* stream);
+/* weights for the row-merged stem: fp32 [O][I][KH][KW] -> [kh][O][kw*c_slots + c] (c_slots = 8: zero padded to 64
+ * elements, the ng_prep_stem layout; c_slots = 4: 32 elements, the ng_stem_conv layout; I <= c_slots, KW <= 8) */
+int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH, int32_t KW, int32_t c_slots,
+                             int32_t dtype, void* dst, void* stream);
+/* The generator stem -- F.pad(reflect, wrap_pad) + ReflectionPad2d(3) + Conv2d(cin -> 64, k7) (model/pix2pix.py:91-93,
+ * model/networks.py:341-342) -- straight from the caller's NCHW fp32 tiles on the tensor cores: src [B][cin][H][W]
+ * (cin <= 4) -> y [B][H+2*wrap_pad][W+2*wrap_pad][64] pre-norm `dtype` (+ InstanceNorm statistics as for ng_conv2d:
+ * stat_partials [B][ng_stem_conv_stat_slots][64][2] and / or stat_acc [B][64][2], either may be NULL).  The im2col tile
+ * (row-merged, 32 elements per pixel) is assembled in shared memory inside the kernel: no intermediate tensor.
+ * w_packed: ng_pack_weight_rowmerged(..., c_slots = 4, ...) = [7][64][32].  The conv bias is not applied (it cancels in
+ * the InstanceNorm that follows). */
+int ng_stem_conv(const float* src, int32_t cin, int32_t B, int32_t H, int32_t W, int32_t wrap_pad, const void* w_packed,
+                 int32_t dtype, void* y, float* stat_partials, int64_t* stat_acc, void* stream);
+int ng_stem_conv_stat_slots(int32_t H, int32_t W, int32_t wrap_pad);
 /* inverse for gradients: fp32 [kh][O][64] -> fp32 [O][I][KH][KW], dst = beta * dst + scale * dev_scale[0] * packed */
 int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, int32_t KH, int32_t KW, float scale,
                                     const float* dev_scale, float beta, float* dst, void* stream);
@@ -196,11 +216,16 @@ int ng_in_stats_finalize(const float* partials, int32_t B, int32_t slots, int32_
                          float* mean_rstd, void* stream);
 
 /* out = act( inject( (y - mean) * rstd ) ) + residual, written with a halo of out_pad.
- * mean_rstd == NULL skips the normalisation (y is used as is). */
+ * Statistics: mean_rstd ([B][C][2] floats) when given; else stat_acc ([B][C][2] int64 fixed-point sums written by
+ * ng_conv2d, see ng_conv_args.stat_acc) from which every block derives mean = S/(H*W), rstd = rsqrt(Q/(H*W) - mean^2 +
+ * 1e-5) for its channels -- and, when mean_rstd_out is given, the first block of each image also stores them as floats
+ * for the backward pass; both NULL skips the normalisation (y is used as is). */
 int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd,
-                int32_t act, float slope, const void* residual, int32_t res_pad, const float* inject_e,
-                int32_t inject_mode, const float* inject_scale, void* out, int32_t out_pad, int32_t halo_mode,
-                void* stream);
+                const int64_t* stat_acc, float* mean_rstd_out, int32_t act, float slope, const void* residual,
+                int32_t res_pad, const float* inject_e, int32_t inject_mode, const float* inject_scale, void* out,
+                int32_t out_pad, int32_t halo_mode, void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (the statistics accumulators of a whole plan are cleared by one call) */
+int ng_memset_zero(void* ptr, int64_t bytes, void* stream);
 
 /* Backward of the unit computed by ng_in_apply (autograd of InstanceNorm2d / ReLU / LeakyReLU / residual add /
  * ReflectionPad2d / the SatCLIP injection; model/pix2pix.py:165-257 runs it through torch autograd):

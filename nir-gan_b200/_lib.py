@@ -31,7 +31,7 @@ class ConvArgs(C.Structure):
         "pad", "pad_w", "Hout", "Wout", "epilogue", "act")] + [
         ("slope", c_f32), ("crop", c_i32), ("reserved", c_i32),
         ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("y", c_vp), ("stat_partials", c_vp),
-        ("mean_rstd", c_vp), ("tile_counters", c_vp)]
+        ("mean_rstd", c_vp), ("tile_counters", c_vp), ("stat_acc", c_vp)]
 
 
 _SIGNATURES = {
@@ -47,7 +47,9 @@ _SIGNATURES = {
                                       c_vp]),
     "ng_pack_weight_phasemerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_prep_stem": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    "ng_pack_weight_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ng_pack_weight_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ng_stem_conv": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "ng_stem_conv_stat_slots": (c_i32, [c_i32, c_i32, c_i32]),
     "ng_unpack_weight_grad_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_f32, c_vp, c_vp]),
     "ng_tap_gather": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ng_tap_scatter": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp,
@@ -56,8 +58,9 @@ _SIGNATURES = {
                               c_vp, c_vp]),
     "ng_in_stats": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_in_stats_finalize": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    "ng_in_apply": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp, c_i32, c_vp, c_i32,
-                            c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "ng_in_apply": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_f32, c_vp, c_i32, c_vp,
+                            c_i32, c_vp, c_vp, c_i32, c_i32, c_vp]),
+    "ng_memset_zero": (c_i32, [c_vp, c_i64, c_vp]),
     "ng_in_bwd_scratch_floats": (c_i64, [c_i32, c_i32, c_i32, c_i32]),
     "ng_in_bwd": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_f32, c_vp,
                           c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

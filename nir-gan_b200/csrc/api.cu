@@ -10,6 +10,8 @@ int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspac
 long long wgrad_tc_workspace_bytes(const ng_conv_args& a, const ConvGeom& g);
 int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st);
 int conv_tc_stat_slots(const ng_conv_args& a, const ConvGeom& g);
+int conv_tc_stem_direct(const float* src, int cin, int B, int H, int W, int wrap, const void* w_packed, int dtype, void* y,
+                        float* stat_partials, long long* stat_acc, cudaStream_t st);
 }  // namespace ng
 
 using namespace ng;
@@ -81,4 +83,18 @@ extern "C" int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* d
   }
   if (dbias) return bias_grad(*a, g, dbias, (cudaStream_t)stream);
   return NG_OK;
+}
+
+extern "C" int ng_stem_conv(const float* src, int32_t cin, int32_t B, int32_t H, int32_t W, int32_t wrap_pad,
+                            const void* w_packed, int32_t dtype, void* y, float* stat_partials, int64_t* stat_acc,
+                            void* stream) {
+  int r = require_sm100();
+  if (r) return r;
+  return conv_tc_stem_direct(src, cin, B, H, W, wrap_pad, w_packed, dtype, y, stat_partials,
+                             reinterpret_cast<long long*>(stat_acc), (cudaStream_t)stream);
+}
+
+extern "C" int ng_stem_conv_stat_slots(int32_t H, int32_t W, int32_t wrap_pad) {
+  const int H1 = H + 2 * wrap_pad, W1 = W + 2 * wrap_pad;
+  return ((H1 + 7) / 8) * ((W1 + 15) / 16);
 }

@@ -44,6 +44,12 @@ struct TcParams {
   float* stat_partials;
   float* mean_rstd;           // fused finalisation (optional)
   int* tile_counters;
+  unsigned long long* stat_acc;   // fixed-point per-(image, channel) statistics accumulators (optional)
+  int image_minor;            // tile order: consecutive work items walk the images first (spreads the accumulator atomics)
+  unsigned long long mg_B;    // ceil(2^42 / B)
+  // DS ("direct stem"): the A operand is built in shared memory from the caller's NCHW fp32 planes
+  const float* src;           // [B][src_c][src_H][src_W]
+  int src_c, src_H, src_W, src_wrap;
   unsigned long long mg_groups_per, mg_patches_x, mg_patches_y;   // ceil(2^42 / d) reciprocals for decode()
   int arrivals_per_image;     // epilogue-group arrivals that complete an image
   float inv_count;            // 1 / (Hout * Wout)
@@ -56,7 +62,16 @@ struct TcParams {
 constexpr int RT_BW = 16, RT_BH = 8, RT_KH = 7;
 constexpr int RT_PATCH_ROWS = (RT_BH + RT_KH - 1) * RT_BW;          // 224 pixels
 
-template <int BN, int KC, bool RT = false, int EGW = 2>
+// DS ("direct stem", implies RT): the generator stem straight from the NCHW fp32 tiles.  Four producer warps stage the
+// tile's 14 x 22 source window (wrapper reflect pad + stem reflect halo resolved, fp32 -> 16 bit) and write the haloed
+// patch in the row-merged form -- element kw*4 + c of pixel (y, x) = channel c at (y, x + kw), 32 elements = 64 bytes per
+// pixel, 64-byte swizzle -- directly in the canonical K-major UMMA layout.  No intermediate tensor in HBM (ng_prep_stem
+// wrote and the conv re-read 217 + 275 MB per 32 tiles), K = 7 x 32 instead of 7 x 64 (half the MMAs: 3 real channels
+// are padded to 4, not 8).
+constexpr int DS_WIN_W = RT_BW + 8;                                  // 22 source columns + 2 (8-byte row alignment)
+constexpr int DS_SCRATCH_BYTES = (RT_BH + RT_KH - 1) * DS_WIN_W * 8;
+
+template <int BN, int KC, bool RT = false, int EGW = 2, bool DS = false>
 struct TcCfg {
   static constexpr int A_BYTES = RT ? RT_PATCH_ROWS * KC * 2 : 128 * KC * 2;
   static constexpr int B_BYTES = RT ? 0 : (BN * KC * 2 + 1023) / 1024 * 1024;
@@ -73,13 +88,14 @@ struct TcCfg {
   static constexpr int TG = EG > PASSES ? EG / PASSES : 1;
   static constexpr int EGT = EG / TG;                         // groups that share one tile
   static_assert(TG == 1 || TG == 2, "tile-alternating epilogue sets map onto the two accumulator buffers");
-  static constexpr int THREADS = 64 + 128 * EG;
-  static constexpr int STAGING_BYTES = BN >= 64 ? EG * 128 * EB * 2 : 0;
+  static constexpr int THREADS = 64 + 128 * EG + (DS ? 128 : 0);
+  static constexpr int DS_WARP0 = 2 + 4 * EG;                   // first of the four DS producer warps
+  static constexpr int STAGING_BYTES = (BN >= 64 ? EG * 128 * EB * 2 : 0) + (DS ? 2 * DS_SCRATCH_BYTES : 0);
   static constexpr int RED_BYTES = BN >= 64 ? EG * 2048 : 0;         // cross-row-group stats combine
   static constexpr int ROWOFF_BYTES = EG * 1024 + 64;          // + per-group "this group finalises" flags
   static constexpr int BUDGET = 222 * 1024;
   static constexpr int STAGES_RAW = (BUDGET - STAGING_BYTES - RED_BYTES - W_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES = DS ? 4 : (STAGES_RAW > 8 ? 8 : STAGES_RAW);
   static constexpr int ACC_STRIDE = BN < 32 ? 32 : BN;   // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE <= 64 ? 64 : (2 * ACC_STRIDE <= 128 ? 128 : (2 * ACC_STRIDE <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W_BYTES + STAGING_BYTES + RED_BYTES + ROWOFF_BYTES +
@@ -90,18 +106,20 @@ struct TcCfg {
 // CS = thread-block-cluster size.  The CS CTAs of a cluster work on CS different pixel patches that share the same
 // weight slab; each loads 1/CS of every B (weight) stage and multicasts it to all of them, which divides the
 // L2 -> SM weight traffic (the measured limiter of the 128x256 tile) by CS.
-template <int BN, int KC, int CS, bool RT = false, int EGW = 2>
-__global__ void __launch_bounds__(TcCfg<BN, KC, RT, EGW>::THREADS, 1)
+template <int BN, int KC, int CS, bool RT = false, int EGW = 2, bool DS = false>
+__global__ void __launch_bounds__(TcCfg<BN, KC, RT, EGW, DS>::THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams p) {
-  using Cfg = TcCfg<BN, KC, RT, EGW>;
-  static_assert(!RT || (CS == 1 && KC == 64), "row-tap variant: no clusters, 64-channel rows");
+  using Cfg = TcCfg<BN, KC, RT, EGW, DS>;
+  static_assert(!RT || (CS == 1 && (KC == 64 || (DS && KC == 32))), "row-tap variant: no clusters, 64-channel rows");
+  static_assert(!DS || RT, "the direct stem is a row-tap kernel");
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
   uint8_t* wres = smem + STAGES * Cfg::STAGE_BYTES;            // RT: resident weights [tap][BN][KC]
   uint8_t* staging = wres + Cfg::W_BYTES;
+  uint8_t* ds_scratch = staging + (Cfg::STAGING_BYTES - (DS ? 2 * DS_SCRATCH_BYTES : 0));   // DS: two source windows
   float* red = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
   long long* rowoff = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(red) + Cfg::RED_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowoff) + Cfg::ROWOFF_BYTES);
@@ -119,7 +137,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CS) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), 1); mbar_init(smem_u32(&empty_bar[s]), CS); }
+    // DS: a stage is filled by the four producer warps (one arrival each), not by a TMA transaction
+    for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&full_bar[s]), DS ? 4 : 1); mbar_init(smem_u32(&empty_bar[s]), CS); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&tfull_bar[s]), 1); mbar_init(smem_u32(&tempty_bar[s]), 128 * Cfg::EGT); }
     mbar_init(smem_u32(wfull_bar), 1);
     fence_barrier_init();
@@ -150,10 +169,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int idx = gi * CS + (int)crank;
     dummy = idx >= p.group_items;             // odd tail: recompute the last patch, write nothing
     if (dummy) idx = p.group_items - 1;
-    const int rowi = fdiv(idx, p.mg_patches_x);
-    px = idx - rowi * p.patches_x;
-    n = fdiv(rowi, p.mg_patches_y);
-    py = rowi - n * p.patches_y;
+    if (p.image_minor) {                      // idx = patch * B + n
+      const int pt = fdiv(idx, p.mg_B);
+      n = idx - pt * g.B;
+      py = fdiv(pt, p.mg_patches_x);
+      px = pt - py * p.patches_x;
+    } else {                                  // idx = (n * patches_y + py) * patches_x + px
+      const int rowi = fdiv(idx, p.mg_patches_x);
+      px = idx - rowi * p.patches_x;
+      n = fdiv(rowi, p.mg_patches_y);
+      py = rowi - n * p.patches_y;
+    }
   };
 
   if (warp == 0) {
@@ -170,6 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int cot, ph, n, py, px; bool dummy;
         decode(q, cot, ph, n, py, px, dummy);
         const int i0 = py * p.BH, j0 = px * p.BW;
+        if constexpr (DS) break;                                         // the patches come from the DS producer warps
         if constexpr (RT) {
           // one haloed patch per tile: rows i0 + dy0 .. i0 + dy0 + BH + K - 2, columns j0 + dx0 .. + BW - 1
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
@@ -206,8 +233,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bf16 ? 1 : 0) << 7) | ((uint32_t)(p.bf16 ? 1 : 0) << 10) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      constexpr uint32_t SBO = KC == 64 ? 1024 : 256;
-      constexpr uint32_t LAYOUT = KC == 64 ? 2 : 6;
+      constexpr uint32_t SBO = KC == 64 ? 1024 : (KC == 32 ? 512 : 256);      // 8 rows of KC 16-bit elements
+      constexpr uint32_t LAYOUT = KC == 64 ? 2 : (KC == 32 ? 4 : 6);          // SWIZZLE_128B / 64B / 32B
       uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
       for (int q = cluster_id; q < p.total_groups; q += num_clusters) {
         const int ph = (q / p.groups_per) % g.nphase;
@@ -253,6 +280,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
+  } else if (DS && warp >= Cfg::DS_WARP0) {
+    // ===================== direct-stem patch producers (4 warps) =====================
+    if constexpr (DS) {
+      const int pt = threadIdx.x - Cfg::DS_WARP0 * 32;                   // 0..127
+      constexpr int PR = RT_BH + RT_KH - 1;                              // 14 patch rows
+      constexpr int WC = RT_BW + RT_KH - 1;                              // 22 source columns
+      const int H1 = g.Hout, W1 = g.Wout, halo = RT_KH / 2;
+      const size_t plane = (size_t)p.src_H * p.src_W;
+      // channel 3 (and the two alignment columns) of both windows stay zero: 3 real channels are stored as 4
+      for (int i = pt; i < 2 * DS_SCRATCH_BYTES / 4; i += 128) reinterpret_cast<uint32_t*>(ds_scratch)[i] = 0u;
+      asm volatile("bar.sync 6, 128;" ::: "memory");
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int q = cluster_id; q < p.total_groups; q += num_clusters, ++it) {
+        int cot, ph, n, py, px; bool dummy;
+        decode(q, cot, ph, n, py, px, dummy);
+        const int i0 = py * p.BH, j0 = px * p.BW;
+        uint16_t* win = reinterpret_cast<uint16_t*>(ds_scratch + (it & 1) * DS_SCRATCH_BYTES);
+        // ---- source window: rows i0 - 3 .. i0 + 10, columns j0 - 3 .. j0 + 18 of the (wrapper-padded) image, both
+        // reflections resolved; consecutive threads read consecutive columns of one (channel, row)
+        const float* sn = p.src + (size_t)n * p.src_c * plane;
+        for (int e = pt; e < p.src_c * PR * WC; e += 128) {
+          const int c = e % WC, rr = e / WC;
+          const int r = rr % PR, ch = rr / PR;
+          const int y1 = min(i0 + r - halo, H1 - 1 + halo), x1 = min(j0 + c - halo, W1 - 1 + halo);
+          const int y0 = reflect_idx(reflect_idx(y1, H1) - p.src_wrap, p.src_H);
+          const int x0 = reflect_idx(reflect_idx(x1, W1) - p.src_wrap, p.src_W);
+          const float v = sn[ch * plane + (size_t)y0 * p.src_W + x0];
+          uint16_t hv;
+          if (p.bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(v); hv = *reinterpret_cast<const uint16_t*>(&t); }
+          else { const __half t = __float2half_rn(v); hv = *reinterpret_cast<const uint16_t*>(&t); }
+          win[(r * DS_WIN_W + c) * 4 + ch] = hv;
+        }
+        asm volatile("bar.sync 6, 128;" ::: "memory");
+        // ---- patch rows: pixel (r, x) -> 32 elements (kw*4 + c) = source columns x .. x + 7 (kw = 7 meets zero weights)
+        if (pt < 32) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        asm volatile("bar.sync 6, 128;" ::: "memory");
+        const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+        const uint32_t wsrc = smem_u32(win);
+#pragma unroll
+        for (int k = 0; k < (RT_PATCH_ROWS * 4) / 128; ++k) {
+          const int id = pt + k * 128;
+          const int pix = id >> 2, qc = id & 3;
+          const int r = pix >> 4, x = pix & 15;
+          const uint32_t a0 = wsrc + ((r * DS_WIN_W + x + 2 * qc) << 3);
+          const long long lo = lds64(a0), hi = lds64(a0 + 8);
+          sts128(sa + pix * 64 + ((qc ^ ((pix >> 1) & 3)) << 4), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi,
+                 (uint32_t)(hi >> 32));
+        }
+        fence_proxy_async();                 // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
   } else {
     // ===================== epilogue (warps 2..5 = group 0, warps 6..9 = group 1) =====================
     const int qtr = warp & 3;               // TMEM lane quarter this warp may access
@@ -360,7 +442,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bar_sync_id(barid);
 
           // ---- per-channel partial statistics (deterministic: fixed row order, fixed combine order) ----
-          if (p.epilogue == NG_EPI_RAW && p.stat_partials != nullptr) {
+          if (p.epilogue == NG_EPI_RAW && (p.stat_partials != nullptr || p.stat_acc != nullptr)) {
             constexpr int PAIRS = EB / 2, G = 128 / PAIRS;        // 16 channel pairs x 8 row groups
             const int cp = et % PAIRS, rs = et / PAIRS;
             float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
@@ -380,7 +462,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 o = lds_f4(redg + ((k - 1) * PAIRS + cp) * 16);
                 s0 += o.x; q0 += o.y; s1 += o.z; q1 += o.w;
               }
-              if (!dummy) {
+              if (!dummy && p.stat_acc != nullptr) {
+                // fixed point: integer adds commute, so the per-image totals are independent of tile completion order
+                unsigned long long* acc = p.stat_acc + ((size_t)n * g.Cout_real + c_first + 2 * cp) * 2;
+                constexpr float SS = (float)(1 << NG_STAT_SUM_SHIFT), SQ = (float)(1 << NG_STAT_SQ_SHIFT);
+                atomicAdd(acc + 0, (unsigned long long)__float2ll_rn(s0 * SS));
+                atomicAdd(acc + 1, (unsigned long long)__float2ll_rn(q0 * SQ));
+                atomicAdd(acc + 2, (unsigned long long)__float2ll_rn(s1 * SS));
+                atomicAdd(acc + 3, (unsigned long long)__float2ll_rn(q1 * SQ));
+              }
+              if (!dummy && p.stat_partials != nullptr) {
                 const int slot = (phase_id * p.patches_y + py) * p.patches_x + px;
                 float* dst = p.stat_partials + (((size_t)n * p.stat_slots + slot) * g.Cout_real + c_first + 2 * cp) * 2;
                 *reinterpret_cast<float4*>(dst) = make_float4(s0, q0, s1, q1);
@@ -593,6 +684,9 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   p.stat_slots = (g.merged ? 4 : g.nphase) * p.patches_y * p.patches_x;
   p.bias = a.bias; p.y = a.y; p.stat_partials = a.stat_partials;
   p.mean_rstd = a.mean_rstd; p.tile_counters = a.tile_counters;
+  p.stat_acc = reinterpret_cast<unsigned long long*>(a.stat_acc);
+  p.image_minor = (a.stat_acc != nullptr && g.B > 1) ? 1 : 0;
+  p.mg_B = ((1ull << 42) + (unsigned)g.B - 1) / (unsigned)g.B;
   p.arrivals_per_image = p.patches_y * p.patches_x * g.nphase * p.co_tiles * Cfg::EGT;
   p.inv_count = 1.0f / ((float)g.Hout * (float)g.Wout);
 
@@ -659,6 +753,74 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   return NG_OK;
 }
 
+// Generator stem straight from the NCHW fp32 tiles (see the DS notes above).  y: [B][H1][W1][64] pre-norm, 16-bit;
+// w_packed: [7][64][32] (ng_pack_weight_rowmerged with 4 channel slots).
+int conv_tc_stem_direct(const float* src, int cin, int B, int H, int W, int wrap, const void* w_packed, int dtype, void* y,
+                        float* stat_partials, long long* stat_acc, cudaStream_t st) {
+  constexpr int BN = 64, KC = 32;
+  using Cfg = TcCfg<BN, KC, true, 4, true>;
+  NG_REQUIRE(dtype == NG_F16 || dtype == NG_BF16, NG_E_UNSUPPORTED, "stem_direct: operands must be f16 or bf16");
+  NG_REQUIRE(src && w_packed && y && cin >= 1 && cin <= 4 && B > 0, NG_E_ARG, "stem_direct: bad arguments (cin <= 4)");
+  NG_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)stat_acc & 15) == 0, NG_E_ALIGN,
+             "stem_direct: tensors must be 16-byte aligned");
+  const int H1 = H + 2 * wrap, W1 = W + 2 * wrap;
+  NG_REQUIRE(wrap >= 0 && wrap < H && wrap < W && H1 > 3 && W1 > 3, NG_E_SHAPE, "stem_direct: reflect padding needs a larger tile");
+  NG_REQUIRE(H1 >= RT_BH && W1 >= RT_BW, NG_E_SHAPE, "stem_direct: tile smaller than one 8 x 16 patch");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  ConvGeom& g = p.g;
+  g.B = B; g.Hb = H1 + 6; g.Wb = W1; g.Cin = KC; g.Cout = BN; g.Cout_real = BN;
+  g.VH = H1; g.VW = W1; g.S = 1; g.OS = 1; g.Hout = H1; g.Wout = W1; g.nphase = 1; g.ntaps = RT_KH;
+  g.phase_tap0[0] = 0; g.phase_tap0[1] = RT_KH;
+  for (int t = 0; t < RT_KH; ++t) { g.taps[t].dy = (int16_t)t; g.taps[t].dx = 0; g.taps[t].wrow = t * BN; }
+  p.BH = RT_BH; p.BW = RT_BW;
+  p.patches_y = (H1 + RT_BH - 1) / RT_BH;
+  p.patches_x = (W1 + RT_BW - 1) / RT_BW;
+  p.co_tiles = 1;
+  const long long tiles = (long long)B * p.patches_y * p.patches_x;
+  NG_REQUIRE(tiles > 0 && tiles < (1ll << 30), NG_E_SHAPE, "stem_direct: tile count out of range");
+  p.total_tiles = (int)tiles; p.group_items = (int)tiles; p.groups_per = (int)tiles; p.total_groups = (int)tiles;
+  p.mg_groups_per = ((1ull << 42) + (unsigned)p.groups_per - 1) / (unsigned)p.groups_per;
+  p.mg_patches_x = ((1ull << 42) + (unsigned)p.patches_x - 1) / (unsigned)p.patches_x;
+  p.mg_patches_y = ((1ull << 42) + (unsigned)p.patches_y - 1) / (unsigned)p.patches_y;
+  p.mg_B = ((1ull << 42) + (unsigned)B - 1) / (unsigned)B;
+  p.epilogue = NG_EPI_RAW; p.act = NG_ACT_NONE;
+  p.bf16 = dtype == NG_BF16;
+  p.stat_slots = p.patches_y * p.patches_x;
+  p.y = y; p.stat_partials = stat_partials;
+  p.stat_acc = reinterpret_cast<unsigned long long*>(stat_acc);
+  p.image_minor = (stat_acc != nullptr && B > 1) ? 1 : 0;
+  p.inv_count = 1.0f / ((float)H1 * (float)W1);
+  p.src = src; p.src_c = cin; p.src_H = H; p.src_W = W; p.src_wrap = wrap;
+
+  CUtensorMap tmB;
+  {
+    const CUtensorMapDataType dt = dtype == NG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t dims[2] = {(cuuint64_t)KC, (cuuint64_t)RT_KH * BN};
+    cuuint64_t strides[1] = {(cuuint64_t)KC * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    int cr = 0;
+    const int er = cached_tensor_map(&tmB, dt, 2, w_packed, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_64B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, &cr);
+    NG_REQUIRE(er == NG_OK, NG_E_DRIVER, "stem_direct: cuTensorMapEncodeTiled(W) failed: %d", cr);
+  }
+  auto kern = conv_tc_kernel<BN, KC, 1, true, 4, true>;
+  static PerDeviceOnce once;
+  const int dev = current_device();
+  if (once.needed(dev)) {
+    int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES),
+                       "cudaFuncSetAttribute(stem_direct)");
+    if (e) return e;
+    once.done(dev);
+  }
+  const int sms = num_sms();
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmB, tmB, p);
+  NG_LAUNCH_CHECK("conv_tc_kernel<direct stem>");
+  return NG_OK;
+}
+
 static int cluster_size_for(int bn, int kc) {
   // measured on B200: multicast does not shorten the kernel (not L2-bound); kept as a switch
   static const int env = [] {
@@ -691,7 +853,12 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   const int kc = a.Cin % 64 == 0 ? 64 : (a.Cin == 16 ? 16 : 0);
   NG_REQUIRE(bn != 0 && kc != 0, NG_E_UNSUPPORTED, "conv_tc: Cin %d / Cout %d not tileable", a.Cin, a.Cout);
   NG_REQUIRE(a.epilogue != NG_EPI_HEAD || a.Cout == 16, NG_E_SHAPE, "conv_tc: head epilogue expects Cout stored as 16");
-  NG_REQUIRE(bn != 16 || a.stat_partials == nullptr, NG_E_UNSUPPORTED, "conv_tc: no InstanceNorm statistics for 16-channel outputs");
+  NG_REQUIRE(bn != 16 || (a.stat_partials == nullptr && a.stat_acc == nullptr), NG_E_UNSUPPORTED,
+             "conv_tc: no InstanceNorm statistics for 16-channel outputs");
+  NG_REQUIRE(a.stat_acc == nullptr || (a.epilogue == NG_EPI_RAW && ((uintptr_t)a.stat_acc & 15) == 0), NG_E_ARG,
+             "conv_tc: stat_acc needs the RAW epilogue and 16-byte alignment");
+  NG_REQUIRE(a.stat_acc == nullptr || a.mean_rstd == nullptr, NG_E_ARG,
+             "conv_tc: fused finalisation works on stat_partials, not on stat_acc");
   NG_REQUIRE((a.mean_rstd == nullptr) == (a.tile_counters == nullptr), NG_E_ARG,
              "conv_tc: fused finalisation needs both mean_rstd and tile_counters");
   NG_REQUIRE(a.mean_rstd == nullptr || (a.stat_partials != nullptr && a.epilogue == NG_EPI_RAW), NG_E_ARG,

@@ -226,7 +226,8 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // (row, column) split uses a multiply-shift by the precomputed reciprocal of the buffer width.
 template <typename T, int UNROLL, bool HAS_RES, bool HAS_INJ>
 __global__ void __launch_bounds__(256, 3)
-in_apply_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, const float* __restrict__ mr, int act,
+in_apply_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, const float* __restrict__ mr,
+                const long long* __restrict__ acc, float* __restrict__ mr_out, int act,
                 float slope, const T* __restrict__ res, int res_pad, const float* __restrict__ inj, int inj_mode,
                 const float* __restrict__ inj_scale, T* __restrict__ out, int op, int halo_mode, int ppb,
                 unsigned long long wo_magic) {
@@ -247,7 +248,26 @@ in_apply_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, cons
       const float4 m = m4[k];
       mean[2 * k] = m.x; rstd[2 * k] = m.y; mean[2 * k + 1] = m.z; rstd[2 * k + 1] = m.w;
     }
+  } else if (acc) {
+    // fixed-point (sum, sum of squares) accumulated by the conv epilogue's integer atomics: exact totals -> mean / rstd
+    const longlong2* a2 = reinterpret_cast<const longlong2*>(acc + ((size_t)n * C + c8 * 8) * 2);
+    const double inv_n = 1.0 / ((double)H * (double)W);
+    const double ks = inv_n / (double)(1 << NG_STAT_SUM_SHIFT), kq = inv_n / (double)(1 << NG_STAT_SQ_SHIFT);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const longlong2 v = a2[k];
+      const double m = (double)v.x * ks;
+      const double var = fmax((double)v.y * kq - m * m, 0.0);
+      mean[k] = (float)m;
+      rstd[k] = rsqrtf((float)var + 1e-5f);
+    }
+    if (mr_out != nullptr && blockIdx.x == 0 && (threadIdx.x >> c8_shift) == 0) {
+      float4* o4 = reinterpret_cast<float4*>(mr_out + ((size_t)n * C + c8 * 8) * 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o4[k] = make_float4(mean[2 * k], rstd[2 * k], mean[2 * k + 1], rstd[2 * k + 1]);
+    }
   }
+  const bool norm = mr != nullptr || acc != nullptr;
   const int Wr = W + 2 * res_pad;
   const T* ybase = y + (size_t)n * H * W * C + c8 * 8;
   const T* rbase = HAS_RES ? res + ((size_t)n * (H + 2 * res_pad) * Wr + (size_t)res_pad * Wr + res_pad) * C + c8 * 8 : nullptr;
@@ -298,7 +318,7 @@ in_apply_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, cons
           f[0] = rawf[u][0].x; f[1] = rawf[u][0].y; f[2] = rawf[u][0].z; f[3] = rawf[u][0].w;
           f[4] = rawf[u][1].x; f[5] = rawf[u][1].y; f[6] = rawf[u][1].z; f[7] = rawf[u][1].w;
         }
-        if (mr) {
+        if (norm) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean[k]) * rstd[k];
         }
@@ -631,11 +651,13 @@ prep_stem_kernel(const float* __restrict__ src, int cin, int B, int H, int W, in
 }
 
 template <typename T>
-__global__ void pack_rowmerged_kernel(const float* __restrict__ src, int O, int I, int KH, int KW, T* __restrict__ dst) {
-  const int total = KH * O * 64;
+__global__ void pack_rowmerged_kernel(const float* __restrict__ src, int O, int I, int KH, int KW, int cs,
+                                      T* __restrict__ dst) {
+  const int RW = 8 * cs;                               // row width: 64 (c_slots 8) or 32 (c_slots 4)
+  const int total = KH * O * RW;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i & 63, o = (i >> 6) % O, kh = (i >> 6) / O;
-    const int kw = e >> 3, c = e & 7;
+    const int e = i % RW, o = (i / RW) % O, kh = (i / RW) / O;
+    const int kw = e / cs, c = e % cs;
     float v = 0.f;
     if (kw < KW && c < I) v = src[(((long long)o * I + c) * KH + kh) * KW + kw];
     dst[i] = from_f32<T>(v);
@@ -816,12 +838,22 @@ extern "C" int ng_in_stats_finalize(const float* partials, int32_t B, int32_t sl
   return NG_OK;
 }
 
+extern "C" int ng_memset_zero(void* ptr, int64_t bytes, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(ptr && bytes >= 0, NG_E_ARG, "memset_zero: bad arguments");
+  return check_cuda(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream), "memset_zero");
+}
+
 extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C,
-                           const float* mean_rstd, int32_t act, float slope, const void* residual, int32_t res_pad,
+                           const float* mean_rstd, const int64_t* stat_acc, float* mean_rstd_out, int32_t act,
+                           float slope, const void* residual, int32_t res_pad,
                            const float* inject_e, int32_t inject_mode, const float* inject_scale, void* out,
                            int32_t out_pad, int32_t halo_mode, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(y && out, NG_E_ARG, "in_apply: null tensor");
+  NG_REQUIRE(!(mean_rstd && stat_acc), NG_E_ARG, "in_apply: give mean_rstd or stat_acc, not both");
+  NG_REQUIRE(((uintptr_t)stat_acc & 15) == 0 && ((uintptr_t)mean_rstd_out & 15) == 0, NG_E_ALIGN,
+             "in_apply: statistics must be 16-byte aligned");
   NG_REQUIRE(C % 8 == 0, NG_E_SHAPE, "in_apply: C %d must be a multiple of 8", C);
   NG_REQUIRE(inject_mode == NG_INJECT_NONE || inject_e, NG_E_ARG, "in_apply: injection without embedding map");
   NG_REQUIRE(inject_mode == NG_INJECT_NONE || inject_mode == NG_INJECT_MUL || inject_scale, NG_E_ARG,
@@ -841,7 +873,8 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   dim3 grid((unsigned)((Ho * Wo + ppb - 1) / ppb), (unsigned)B);
 #define NG_APPLY_LAUNCH(RES, INJ)                                                                                  \
   DISPATCH_DTYPE(dtype, (in_apply_kernel<T, 4, RES, INJ><<<grid, 256, 0, (cudaStream_t)stream>>>(                  \
-                            (const T*)y, H, W, C, c8_shift, mean_rstd, act, slope, (const T*)residual, res_pad,    \
+                            (const T*)y, H, W, C, c8_shift, mean_rstd, (const long long*)stat_acc, mean_rstd_out, act,    \
+                            slope, (const T*)residual, res_pad,                                                     \
                             inject_e, inject_mode, inject_scale, (T*)out, out_pad, halo_mode, ppb, wo_magic)))
   const bool has_inj = inject_mode != NG_INJECT_NONE;
   if (residual && has_inj) { NG_APPLY_LAUNCH(true, true); }
@@ -1008,12 +1041,13 @@ extern "C" int ng_prep_stem(const float* src, int32_t cin, int32_t B, int32_t H,
   return NG_OK;
 }
 
-extern "C" int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH, int32_t KW, int32_t dtype,
-                                        void* dst, void* stream) {
+extern "C" int ng_pack_weight_rowmerged(const float* src, int32_t O, int32_t I, int32_t KH, int32_t KW, int32_t c_slots,
+                                        int32_t dtype, void* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
-  NG_REQUIRE(src && dst && I > 0 && I <= 8 && KW > 0 && KW <= 8, NG_E_ARG, "pack_weight_rowmerged: I and KW must be in 1..8");
-  DISPATCH_DTYPE(dtype, (pack_rowmerged_kernel<T><<<grid_for((long long)KH * O * 64, 256), 256, 0, (cudaStream_t)stream>>>(
-                            src, O, I, KH, KW, (T*)dst)));
+  NG_REQUIRE(src && dst && (c_slots == 8 || c_slots == 4) && I > 0 && I <= c_slots && KW > 0 && KW <= 8, NG_E_ARG,
+             "pack_weight_rowmerged: c_slots 4 or 8, I <= c_slots, KW in 1..8");
+  DISPATCH_DTYPE(dtype, (pack_rowmerged_kernel<T><<<grid_for((long long)KH * O * 8 * c_slots, 256), 256, 0, (cudaStream_t)stream>>>(
+                            src, O, I, KH, KW, c_slots, (T*)dst)));
   NG_LAUNCH_CHECK("pack_rowmerged_kernel");
   return NG_OK;
 }

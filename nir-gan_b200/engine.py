@@ -474,9 +474,11 @@ class Engine:
         src = w.detach()
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.float().contiguous()
-        if n_axis == "rowmerged":
-            dst = hit[1] if hit is not None else torch.empty(kh * d0 * 64, dtype=self.dt_torch, device=self.device)
-            L.call("ng_pack_weight_rowmerged", src.data_ptr(), d0, d1, kh, kw, self.dt_enum, dst.data_ptr(), stream)
+        if n_axis in ("rowmerged", "rowmerged4"):
+            # [kh][O][kw*cs + c]: cs = 8 (64-wide rows, the ng_prep_stem layout) or 4 (32-wide, ng_stem_conv)
+            cs = 8 if n_axis == "rowmerged" else 4
+            dst = hit[1] if hit is not None else torch.empty(kh * d0 * 8 * cs, dtype=self.dt_torch, device=self.device)
+            L.call("ng_pack_weight_rowmerged", src.data_ptr(), d0, d1, kh, kw, cs, self.dt_enum, dst.data_ptr(), stream)
         elif n_axis == "phasemerged":
             # ConvTranspose2d (Cin, Cout, 3, 3) -> [shift (4)][phase*Cout + co][Cin]  (NG_FORM_PHASED_MERGED)
             assert kh == 3 and kw == 3 and n_pad == d1 and k_pad == d0
@@ -522,39 +524,6 @@ class Engine:
         a.x, a.w, a.bias, a.y = x.t.data_ptr(), w.data_ptr(), _ptr(bias), y.data_ptr()
         a.stat_partials = _ptr(partials)
         return a
-
-    def add_conv_norm(self, plan: Plan, name: str, x: ActBuf, w_packed: torch.Tensor, Cout: int, K: int, stride: int,
-                      pad: int, Hout: int, Wout: int, form=L.FORM_GATHER, sgn=1, **geom):
-        """conv -> compact pre-norm Y + (mean, rstd).  Returns (Y ActBuf, mean_rstd tensor)."""
-        y = self.act(name + ".y", x.B, Hout, Wout, Cout, 0)
-        mr = self.buffers.get(name + ".mr", x.B * Cout * 2, torch.float32)
-        a = self.conv_args(x, w_packed, y.t, Cout, K, stride, pad, Hout, Wout, form, sgn, **geom)
-        if self.impl == L.IMPL_TC:
-            slots = L.load().ng_conv_stat_slots(C.byref(a))
-            if slots <= 0:
-                L.check(slots if slots < 0 else -1, "ng_conv_stat_slots")
-            part = self.buffers.get(name + ".part", x.B * slots * Cout * 2, torch.float32)
-            a.stat_partials = part.data_ptr()
-            plan.keepalive.append(a)
-            plan.add("ng_conv2d", C.byref(a), label=name)
-            plan.add("ng_in_stats_finalize", part.data_ptr(), x.B, slots, Cout, Hout * Wout, mr.data_ptr(),
-                     label=name + ".fin")
-        else:
-            plan.keepalive.append(a)
-            plan.add("ng_conv2d", C.byref(a), label=name)
-            plan.add("ng_in_stats", y.t.data_ptr(), self.dt_enum, x.B, Hout * Wout, Cout, mr.data_ptr(),
-                     label=name + ".stats")
-        return y, mr
-
-    def add_apply(self, plan: Plan, name: str, y: ActBuf, mr: Optional[torch.Tensor], act: int, out_pad: int,
-                  halo_mode=L.HALO_REFLECT, slope=0.0, residual: Optional[ActBuf] = None,
-                  inject_e: Optional[torch.Tensor] = None, inject_mode=L.INJECT_NONE,
-                  inject_scale: Optional[torch.Tensor] = None) -> ActBuf:
-        out = self.act(name, y.B, y.H, y.W, y.C, out_pad)
-        plan.add("ng_in_apply", y.t.data_ptr(), self.dt_enum, y.B, y.H, y.W, y.C, _ptr(mr), act, slope,
-                 _ptr(residual.t) if residual else None, residual.pad if residual else 0, _ptr(inject_e),
-                 inject_mode, _ptr(inject_scale), out.t.data_ptr(), out_pad, halo_mode, label=name)
-        return out
 
 
 def conv_out(h: int, k: int, s: int, p: int) -> int:

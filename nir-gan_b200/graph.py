@@ -30,6 +30,11 @@ MERGE_PHASES = [_os.environ.get("NIRGAN_B200_MERGE_PHASES", "1") != "0"]
 # launching ng_in_stats_finalize.  Measured on B200: the per-tile __threadfence + counter arrival it needs costs far
 # more than the ~10 us launches it saves (conv time +40 %), so it is OFF by default; kept as a tested switch.
 FUSED_FINALIZE = [_os.environ.get("NIRGAN_B200_FUSED_FINALIZE", "0") == "1"]
+# InstanceNorm statistics of the tcgen05 path: the conv epilogue adds every tile's per-channel (sum, sum of squares) to
+# 64-bit fixed-point accumulators with integer atomics and the apply kernel derives (mean, rstd) from them itself, so a
+# normalised unit is two launches (conv, apply) and the plan starts with ONE memset of all its accumulators.
+# NIRGAN_B200_STAT_ACC=0: per-tile fp32 partials + an ng_in_stats_finalize launch per unit (round-1 form).
+STAT_ACC = [_os.environ.get("NIRGAN_B200_STAT_ACC", "1") != "0"]
 
 
 @dataclass
@@ -56,6 +61,9 @@ class Unit:
     residual: Optional[int] = None        # index of the unit whose output buffer is added
     inject: Optional[dict] = None         # {'e': tensor, 'mode': int, 'scale': tensor}
     crop: int = 0
+    # generator stem straight from the NCHW fp32 tiles (ng_stem_conv): {'src': tensor, 'cin', 'H', 'W', 'wrap'}; x is then a
+    # shape-only description (no row-merged buffer exists)
+    direct: Optional[dict] = None
     # filled by the builder
     y: Optional[ActBuf] = None
     mr: Optional[torch.Tensor] = None
@@ -93,6 +101,8 @@ class UnitGraph:
             return self.eng.packed_weight(u.conv.weight, "phasemerged", u.cout, cin, self.stream)
         if u.pack == "rowmerged":
             return self.eng.packed_weight(u.conv.weight, "rowmerged", u.cout, 64, self.stream)
+        if u.pack == "rowmerged4":
+            return self.eng.packed_weight(u.conv.weight, "rowmerged4", u.cout, 32, self.stream)
         return self.eng.packed_weight(u.conv.weight, u.pack, u.cout, cin, self.stream)
 
     def add(self, u: Unit) -> Unit:
@@ -121,9 +131,20 @@ class UnitGraph:
         plan = Plan()
         plan.records.update(self.records)
         plan.records["weights"] = [u for u in self.units]
+        use_acc = eng.impl == L.IMPL_TC and STAT_ACC[0] and not FUSED_FINALIZE[0]
+        acc_off, acc_all = {}, None
+        if use_acc:
+            total = 0
+            for i, u in enumerate(self.units):
+                if u.kind == "norm":
+                    acc_off[i] = total
+                    total += u.x.B * u.cout * 2
+            if total:
+                acc_all = eng.buffers.get(self.tag + ".statacc", total, torch.int64)
+                plan.add("ng_memset_zero", acc_all.data_ptr(), total * 8, label=self.tag + ".statacc.zero")
         for name, args, label in self.pre_ops:
             plan.add(name, *args, label=label)
-        for u in self.units:
+        for ui, u in enumerate(self.units):
             w = self.weight(u)
             pre = f"{self.tag}.{u.name}"
             if u.kind == "head":
@@ -137,9 +158,32 @@ class UnitGraph:
                 plan.keepalive.append(a)
                 plan.add("ng_conv2d", C.byref(a), label=pre)
                 continue
-            a = self._args(u, u.x, w, u.y.t, **({"form": L.FORM_PHASED_MERGED} if self.merged_phases(u) else {}))
             B = u.x.B
-            if eng.impl == L.IMPL_TC:
+            acc_ptr = None
+            if u.direct is not None:
+                # the stem straight from the fp32 tiles: im2col tile assembled in shared memory inside the conv
+                d = u.direct
+                part = None
+                if use_acc:
+                    acc_ptr = acc_all.data_ptr() + 8 * acc_off[ui]
+                else:
+                    slots = int(L.load().ng_stem_conv_stat_slots(d["H"], d["W"], d["wrap"]))
+                    part = eng.buffers.get(pre + ".part", B * slots * u.cout * 2, torch.float32)
+                plan.add("ng_stem_conv", d["src"].data_ptr(), d["cin"], B, d["H"], d["W"], d["wrap"], w.data_ptr(),
+                         eng.dt_enum, u.y.t.data_ptr(), _ptr(part), acc_ptr, label=pre)
+                if not use_acc:
+                    plan.add("ng_in_stats_finalize", part.data_ptr(), B, slots, u.cout, u.Hout * u.Wout,
+                             u.mr.data_ptr(), label=pre + ".fin")
+            else:
+                a = self._args(u, u.x, w, u.y.t, **({"form": L.FORM_PHASED_MERGED} if self.merged_phases(u) else {}))
+            if u.direct is not None:
+                pass
+            elif use_acc:
+                acc_ptr = acc_all.data_ptr() + 8 * acc_off[ui]
+                a.stat_acc = acc_ptr
+                plan.keepalive.append(a)
+                plan.add("ng_conv2d", C.byref(a), label=pre)
+            elif eng.impl == L.IMPL_TC:
                 slots = L.load().ng_conv_stat_slots(C.byref(a))
                 if slots <= 0:
                     L.check(slots if slots < 0 else -1, "ng_conv_stat_slots")
@@ -162,7 +206,8 @@ class UnitGraph:
                          label=pre + ".stats")
             res = self.units[u.residual].out if u.residual is not None else None
             inj = u.inject or {}
-            plan.add("ng_in_apply", u.y.t.data_ptr(), eng.dt_enum, B, u.Hout, u.Wout, u.cout, u.mr.data_ptr(), u.act,
+            plan.add("ng_in_apply", u.y.t.data_ptr(), eng.dt_enum, B, u.Hout, u.Wout, u.cout,
+                     None if use_acc else u.mr.data_ptr(), acc_ptr, u.mr.data_ptr() if use_acc else None, u.act,
                      u.slope, _ptr(res.t) if res else None, res.pad if res else 0, _ptr(inj.get("e")),
                      inj.get("mode", L.INJECT_NONE), _ptr(inj.get("scale")), u.out.t.data_ptr(), u.out_pad, u.halo_mode,
                      label=pre + ".apply")

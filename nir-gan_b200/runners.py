@@ -147,7 +147,7 @@ class GeneratorRunner(_RunnerBase):
         return m[1], m[4], m[7], [m[10 + b] for b in range(nb)], m[10 + nb], m[13 + nb], m[17 + nb]
 
     def build_graph(self, eng: Engine, B: int, H: int, W: int, wrap: int, inject: bool, stream: int, tag: str,
-                    direct_head: bool) -> UnitGraph:
+                    direct_head: bool, direct_stem: bool = False) -> UnitGraph:
         mod = self.module
         stem, d1, d2, blocks, u1, u2, head = self._convs()
         ngf, cin = stem.weight.shape[0], stem.weight.shape[1]
@@ -163,14 +163,23 @@ class GeneratorRunner(_RunnerBase):
         # the 7x7x3 stem becomes a 7x1 conv over 64 "channels" = 7 K-steps of 128-byte rows instead of 49 thin taps
         src = eng.buffers.get(tag + ".in", B * cin * H * W, torch.float32)
         g.records["src"] = src
-        x0 = ActBuf(eng.buffers.get(tag + ".x0", B * (H1 + 6) * W1 * 64, eng.dt_torch), B, H1, W1, 64, 3)
-        g.pre_ops.append(("ng_prep_stem", (src.data_ptr(), cin, B, H, W, wrap, 3, 7, eng.dt_enum, x0.t.data_ptr()),
-                          tag + ".prep"))
         C2, C4 = 2 * ngf, 4 * ngf
         H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
         H3, W3 = conv_out(H2, 3, 2, 1), conv_out(W2, 3, 2, 1)
-        u = g.add(Unit("stem", stem, x0, ngf, 7, 1, 3, H1, W1, pack="rowmerged", KW=1, pad_w=0, in_pad_w=0,
-                       act=L.ACT_RELU, out_pad=0))
+        direct_stem = direct_stem and eng.impl == L.IMPL_TC and cin <= 4 and ngf == 64 and H1 >= 8 and W1 >= 16
+        if direct_stem:
+            # forward-only plans: ng_stem_conv builds the im2col tile in shared memory from the fp32 tiles (no row-merged
+            # tensor in HBM; training plans keep it because the stem's weight gradient reads it)
+            xd = ActBuf(src, B, H1, W1, 32, 3)            # shape-only description of the virtual row-merged input
+            u = g.add(Unit("stem", stem, xd, ngf, 7, 1, 3, H1, W1, pack="rowmerged4", KW=1, pad_w=0, in_pad_w=0,
+                           act=L.ACT_RELU, out_pad=0,
+                           direct={"src": src, "cin": cin, "H": H, "W": W, "wrap": wrap}))
+        else:
+            x0 = ActBuf(eng.buffers.get(tag + ".x0", B * (H1 + 6) * W1 * 64, eng.dt_torch), B, H1, W1, 64, 3)
+            g.pre_ops.append(("ng_prep_stem", (src.data_ptr(), cin, B, H, W, wrap, 3, 7, eng.dt_enum, x0.t.data_ptr()),
+                              tag + ".prep"))
+            u = g.add(Unit("stem", stem, x0, ngf, 7, 1, 3, H1, W1, pack="rowmerged", KW=1, pad_w=0, in_pad_w=0,
+                           act=L.ACT_RELU, out_pad=0))
         inj = None
         if inject:
             if H2 != W2:
@@ -224,7 +233,8 @@ class GeneratorRunner(_RunnerBase):
             return plan
         self.trim(eng)
         tag = f"g{slot}_{B}x{Cin}x{H}x{W}p{wrap}{'i' if inject else ''}"      # shape-unique: plans are evicted by tag
-        g = self.build_graph(eng, B, H, W, wrap, inject, stream, tag, direct_head=not self._use_tap_head())
+        g = self.build_graph(eng, B, H, W, wrap, inject, stream, tag, direct_head=not self._use_tap_head(),
+                             direct_stem=os.environ.get("NIRGAN_B200_STEM_DIRECT", "1") != "0")
         plan = g.compile_forward()
         plan.tags = (tag,)
         if g.tap_head is None:

@@ -25,6 +25,36 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 IN_EPS = 1e-5  # nn.InstanceNorm2d default, model/networks.py:29-30
 
+# Optional emulation of the B200 path's STORAGE precision (test infrastructure for the gradient-parity tests): when set
+# to torch.float16 / torch.bfloat16, inputs, weights, every convolution output and every unit output are rounded to that
+# type where the kernels store them -- all arithmetic stays fp32 and the rounding is straight-through for autograd.  The
+# fp32 autograd of THIS function has the same ReLU / LeakyReLU masks as the low-precision forward, so comparing gradients
+# against it isolates the backward kernels' own arithmetic from the (large, unavoidable) effect of mask flips.
+# None (default) = the reference's exact fp32 arithmetic; the pinning scripts and golden fixtures never set it.
+STORAGE_DTYPE = [None]
+
+
+class storage_rounding:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        self.prev = STORAGE_DTYPE[0]
+        STORAGE_DTYPE[0] = self.dtype
+        return self
+
+    def __exit__(self, *exc):
+        STORAGE_DTYPE[0] = self.prev
+        return False
+
+
+def _st(x: Tensor) -> Tensor:
+    """Round to the emulated storage type (straight-through gradient); identity by default."""
+    d = STORAGE_DTYPE[0]
+    if d is None:
+        return x
+    return x + (x.detach().to(d).float() - x.detach())
+
 
 # --------------------------------------------------------------------------------------
 # building blocks
@@ -63,11 +93,11 @@ def resnet_generator_forward(sd: Dict[str, Tensor], x: Tensor, n_blocks: int = 9
     model[:6] (i.e. after InstanceNorm of down-1, before its ReLU)."""
     L = generator_layout(n_blocks)
     g = lambda k: sd[prefix + k]
-    w = lambda i: (g(f"model.{i}.weight"), g(f"model.{i}.bias"))
+    w = lambda i: (_st(g(f"model.{i}.weight")), g(f"model.{i}.bias"))
 
-    h = F.conv2d(_rpad(x, 3), *w(L["stem"]))                       # :341-342
-    h = F.relu(_inorm(h))                                          # :343-344
-    h = _inorm(F.conv2d(h, *w(L["down1"]), stride=2, padding=1))   # :349-350
+    h = _st(F.conv2d(_rpad(_st(x), 3), *w(L["stem"])))             # :341-342
+    h = _st(F.relu(_inorm(h)))                                     # :343-344
+    h = _inorm(_st(F.conv2d(h, *w(L["down1"]), stride=2, padding=1)))   # :349-350
     if embeds is not None:                                         # generator_inject.py:110-127
         e = F.linear(embeds, g("fc.weight"), g("fc.bias")).view(-1, 1, 128, 128)
         # NOTE the reference passes size=(W, H) (generator_inject.py:116): square tiles only.
@@ -80,17 +110,17 @@ def resnet_generator_forward(sd: Dict[str, Tensor], x: Tensor, n_blocks: int = 9
             h = h * (1 + s * e)
         elif inject_style == "multiply":
             h = h * e
-    h = F.relu(h)                                                  # :351
-    h = F.relu(_inorm(F.conv2d(h, *w(L["down2"]), stride=2, padding=1)))
+    h = _st(F.relu(h))                                             # :351
+    h = _st(F.relu(_inorm(_st(F.conv2d(h, *w(L["down2"]), stride=2, padding=1)))))
     for b in range(n_blocks):                                      # :354-356, :405-434
         i = L["block0"] + b
-        r = F.conv2d(_rpad(h, 1), g(f"model.{i}.conv_block.1.weight"), g(f"model.{i}.conv_block.1.bias"))
-        r = F.relu(_inorm(r))
-        r = F.conv2d(_rpad(r, 1), g(f"model.{i}.conv_block.5.weight"), g(f"model.{i}.conv_block.5.bias"))
-        h = h + _inorm(r)                                          # no ReLU after the add, :433
+        r = _st(F.conv2d(_rpad(h, 1), _st(g(f"model.{i}.conv_block.1.weight")), g(f"model.{i}.conv_block.1.bias")))
+        r = _st(F.relu(_inorm(r)))
+        r = _st(F.conv2d(_rpad(r, 1), _st(g(f"model.{i}.conv_block.5.weight")), g(f"model.{i}.conv_block.5.bias")))
+        h = _st(h + _inorm(r))                                     # no ReLU after the add, :433
     for key in ("up1", "up2"):                                     # :358-365
-        h = F.conv_transpose2d(h, *w(L[key]), stride=2, padding=1, output_padding=1)
-        h = F.relu(_inorm(h))
+        h = _st(F.conv_transpose2d(h, *w(L[key]), stride=2, padding=1, output_padding=1))
+        h = _st(F.relu(_inorm(h)))
     h = torch.tanh(F.conv2d(_rpad(h, 3), *w(L["head"])))           # :366-368
     if post_correction:                                            # generator_inject.py:133-134
         h = h * g("post_correction_param")
@@ -102,16 +132,16 @@ def patchgan_forward(sd: Dict[str, Tensor], x: Tensor, n_layers: int = 3, prefix
     (n_layers-1) x [Conv4x4 s2 + IN + LReLU]; Conv4x4 s1 + IN + LReLU; Conv4x4 s1 -> 1 channel.
     All zero-pad 1, bias everywhere (norm = instance)."""
     g = lambda k: sd[prefix + k]
-    h = F.leaky_relu(F.conv2d(x, g("model.0.weight"), g("model.0.bias"), stride=2, padding=1), 0.2)
+    h = _st(F.leaky_relu(F.conv2d(_st(x), _st(g("model.0.weight")), g("model.0.bias"), stride=2, padding=1), 0.2))
     idx = 2
     for _ in range(1, n_layers):
-        h = F.conv2d(h, g(f"model.{idx}.weight"), g(f"model.{idx}.bias"), stride=2, padding=1)
-        h = F.leaky_relu(_inorm(h), 0.2)
+        h = _st(F.conv2d(h, _st(g(f"model.{idx}.weight")), g(f"model.{idx}.bias"), stride=2, padding=1))
+        h = _st(F.leaky_relu(_inorm(h), 0.2))
         idx += 3
-    h = F.conv2d(h, g(f"model.{idx}.weight"), g(f"model.{idx}.bias"), stride=1, padding=1)
-    h = F.leaky_relu(_inorm(h), 0.2)
+    h = _st(F.conv2d(h, _st(g(f"model.{idx}.weight")), g(f"model.{idx}.bias"), stride=1, padding=1))
+    h = _st(F.leaky_relu(_inorm(h), 0.2))
     idx += 3
-    return F.conv2d(h, g(f"model.{idx}.weight"), g(f"model.{idx}.bias"), stride=1, padding=1)
+    return F.conv2d(h, _st(g(f"model.{idx}.weight")), g(f"model.{idx}.bias"), stride=1, padding=1)
 
 
 def lsgan_loss(pred: Tensor, target_is_real: bool) -> Tensor:

@@ -81,6 +81,32 @@ def conv_call(x: ActBuf, wp: torch.Tensor, Cout: int, K: int, stride: int, pad: 
         mr = torch.empty(x.B * Cout * 2, dtype=torch.float32, device=dev)
         if impl == L.IMPL_TC:
             L.call("ng_in_stats_finalize", part.data_ptr(), x.B, slots, Cout, Hout * Wout, mr.data_ptr(), stream())
+            # the product path: fixed-point accumulators filled by integer atomics, turned into (mean, rstd) by the apply
+            # kernel itself (mean_rstd_out); must agree with the per-tile partials + finalize form, and be bit-identical
+            # from launch to launch whatever order the tiles finish in
+            accs = []
+            for _ in range(2):
+                b = L.ConvArgs()
+                C.memmove(C.byref(b), C.byref(a), C.sizeof(L.ConvArgs))
+                b.stat_partials, b.mean_rstd, b.tile_counters = None, None, None
+                acc = torch.full((x.B * Cout * 2,), 7, dtype=torch.int64, device=dev)
+                L.call("ng_memset_zero", acc.data_ptr(), acc.numel() * 8, stream())
+                b.stat_acc = acc.data_ptr()
+                y2 = torch.empty_like(y)
+                b.y = y2.data_ptr()
+                L.call("ng_conv2d", C.byref(b), stream())
+                accs.append(acc)
+            torch.cuda.synchronize()
+            assert torch.equal(accs[0], accs[1]), "fixed-point statistics must not depend on tile completion order"
+            assert torch.equal(y2, y), "image-minor tile order must not change the convolution output"
+            mr2 = torch.full((x.B * Cout * 2,), float("nan"), dtype=torch.float32, device=dev)
+            o2 = torch.empty(x.B * Hout * Wout * Cout, dtype=TORCH_DT[dtype], device=dev)
+            L.call("ng_in_apply", y.data_ptr(), dtype, x.B, Hout, Wout, Cout, None, accs[0].data_ptr(), mr2.data_ptr(),
+                   L.ACT_NONE, 0.0, None, 0, None, L.INJECT_NONE, None, o2.data_ptr(), 0, L.HALO_ZERO, stream())
+            torch.cuda.synchronize()
+            m1, m2 = mr.view(-1, 2), mr2.view(-1, 2)
+            assert float((m1[:, 0] - m2[:, 0]).abs().max()) <= 1e-5 * max(1.0, float(m1[:, 0].abs().max())), "acc mean"
+            assert float((m1[:, 1] / m2[:, 1] - 1).abs().max()) <= 1e-4, "acc rstd"
             torch.cuda.synchronize()
             assert int(cnt.abs().max()) == 0, "tile counters must be left at zero"
             assert torch.isfinite(fused_mr).all()

@@ -30,8 +30,8 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 
 def test_conv_args_struct_layout_matches_header():
-    # 20 int32 + float + 2 int32 = 92 bytes, pointers 8-aligned from offset 96
-    assert L.ConvArgs.x.offset == 96 and ctypes.sizeof(L.ConvArgs) == 152
+    # 20 int32 + float + 2 int32 = 92 bytes, pointers 8-aligned from offset 96; 8 pointers
+    assert L.ConvArgs.x.offset == 96 and ctypes.sizeof(L.ConvArgs) == 160 and L.ConvArgs.stat_acc.offset == 152
     assert L.ConvArgs.slope.offset == 80 and L.ConvArgs.crop.offset == 84
 
 

@@ -222,7 +222,7 @@ def test_argument_errors_are_reported():
     assert "conv" in L.last_error()
     assert L.load().ng_conv2d(None, None) < 0
     with pytest.raises(RuntimeError):
-        L.call("ng_in_apply", None, L.F16, 1, 4, 4, 8, None, 0, 0.0, None, 0, None, 0, None, None, 0, 0, None)
+        L.call("ng_in_apply", None, L.F16, 1, 4, 4, 8, None, None, None, 0, 0.0, None, 0, None, 0, None, None, 0, 0, None)
 
 
 @pytest.mark.parametrize("impl,dtype", _impls())
@@ -241,7 +241,7 @@ def test_stem_rowmerged(impl, dtype, wrap, H, W):
     x0 = torch.empty(B * (H1 + 6) * W1 * 64, dtype=Hh.TORCH_DT[dtype], device="cuda")
     L.call("ng_prep_stem", x.data_ptr(), 3, B, H, W, wrap, 3, 7, dtype, x0.data_ptr(), Hh.stream())
     wp = torch.empty(7 * 64 * 64, dtype=Hh.TORCH_DT[dtype], device="cuda")
-    L.call("ng_pack_weight_rowmerged", w.data_ptr(), 64, 3, 7, 7, dtype, wp.data_ptr(), Hh.stream())
+    L.call("ng_pack_weight_rowmerged", w.data_ptr(), 64, 3, 7, 7, 8, dtype, wp.data_ptr(), Hh.stream())
     y = torch.full((B * H1 * W1 * 64,), float("nan"), device="cuda").to(Hh.TORCH_DT[dtype])
     a = L.ConvArgs()
     a.dtype, a.impl, a.form, a.sgn = dtype, impl, L.FORM_GATHER, 1
@@ -292,3 +292,52 @@ def test_head_tap_gemm_and_gather(impl, dtype, crop, H):
     got = out.view(B, 1, H - 2 * crop, H - 2 * crop)
     assert torch.isfinite(got).all()
     assert float((got - ref).abs().max()) <= (2e-5 if dtype == L.F32 else (1e-3 if dtype == L.F16 else 1e-2))   # 49 16-bit-rounded partial sums
+
+
+
+@pytest.mark.parametrize("dtype_name", ["f16", "bf16"])
+@pytest.mark.parametrize("cin,wrap,H,W,B", [(3, 0, 32, 32, 2), (3, 10, 24, 36, 2), (3, 0, 50, 70, 3), (4, 10, 44, 44, 1),
+                                            (3, 10, 256, 256, 2)])
+def test_stem_direct_from_fp32_tiles(dtype_name, cin, wrap, H, W, B):
+    """ng_stem_conv (im2col tile assembled in shared memory from the NCHW fp32 tiles, K = 7 x 32, 64-byte swizzle) ==
+    F.pad(reflect, wrap) + ReflectionPad2d(3) + Conv2d(cin -> 64, k7), incl. partially covered 8 x 16 patches at the right /
+    bottom border, both statistics forms, and launch-to-launch bit-exactness."""
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    dtype = L.F16 if dtype_name == "f16" else L.BF16
+    x = _gen(B, cin, H, W, seed=31)
+    w = Hh.rnd(_gen(64, cin, 7, 7, seed=32, scale=0.05), dtype)
+    H1, W1 = H + 2 * wrap, W + 2 * wrap
+    wp = torch.empty(7 * 64 * 32, dtype=Hh.TORCH_DT[dtype], device="cuda")
+    L.call("ng_pack_weight_rowmerged", w.data_ptr(), 64, cin, 7, 7, 4, dtype, wp.data_ptr(), Hh.stream())
+    slots = int(L.load().ng_stem_conv_stat_slots(H, W, wrap))
+    outs = []
+    for rep in range(2):
+        y = torch.full((B * H1 * W1 * 64,), float("nan"), device="cuda").to(Hh.TORCH_DT[dtype])
+        part = torch.full((B * slots * 64 * 2,), float("nan"), device="cuda")
+        acc = torch.zeros(B * 64 * 2, dtype=torch.int64, device="cuda")
+        L.call("ng_stem_conv", x.data_ptr(), cin, B, H, W, wrap, wp.data_ptr(), dtype, y.data_ptr(), part.data_ptr(),
+               acc.data_ptr(), Hh.stream())
+        torch.cuda.synchronize()
+        outs.append((y, part, acc))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])
+    y, part, acc = outs[0]
+    xr = Hh.rnd(x, dtype)
+    if wrap:
+        xr = F.pad(xr, (wrap,) * 4, mode="reflect")
+    ref = F.conv2d(F.pad(xr, (3,) * 4, mode="reflect"), w)
+    got = Hh.from_compact(y, B, H1, W1, 64)
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= _tol(dtype, ref)
+    # statistics of the STORED (rounded) output: per-tile partials -> finalize, and the fixed-point accumulators
+    mr = torch.empty(B * 64 * 2, device="cuda")
+    L.call("ng_in_stats_finalize", part.data_ptr(), B, slots, 64, H1 * W1, mr.data_ptr(), Hh.stream())
+    mu, rstd = Hh.stats_ref(got)
+    m = mr.view(B, 64, 2)
+    assert float((m[..., 0] - mu).abs().max()) <= 1e-4 * max(1.0, float(mu.abs().max()))
+    assert float((m[..., 1] / rstd - 1).abs().max()) <= 1e-3
+    a = acc.view(B, 64, 2).double()
+    mean_acc = a[..., 0] / 2 ** 24 / (H1 * W1)
+    var_acc = a[..., 1] / 2 ** 20 / (H1 * W1) - mean_acc ** 2
+    assert float((mean_acc - mu.double()).abs().max()) <= 1e-4 * max(1.0, float(mu.abs().max()))
+    assert float((torch.rsqrt(var_acc + 1e-5) / rstd.double() - 1).abs().max()) <= 1e-3

@@ -61,7 +61,7 @@ def test_in_stats_and_apply(dtype):
                                           (L.ACT_NONE, 0.0, 0, "zero", True), (L.ACT_LRELU, 0.2, 2, "zero", False)]:
         rb = Hh.to_actbuf(res, 1, "reflect", dtype) if use_res else None
         out = torch.empty(B * (H + 2 * op) * (W + 2 * op) * Cn, dtype=Hh.TORCH_DT[dtype], device="cuda")
-        L.call("ng_in_apply", yb.t.data_ptr(), dtype, B, H, W, Cn, mr.data_ptr(), act, slope,
+        L.call("ng_in_apply", yb.t.data_ptr(), dtype, B, H, W, Cn, mr.data_ptr(), None, None, act, slope,
                rb.t.data_ptr() if rb else None, 1, None, L.INJECT_NONE, None, out.data_ptr(), op,
                L.HALO_REFLECT if mode == "reflect" else L.HALO_ZERO, Hh.stream())
         ref = (y - mu[..., None, None]) * rstd[..., None, None]
@@ -90,7 +90,7 @@ def test_apply_with_satclip_injection(Hm, style):
     L.call("ng_in_stats", yb.t.data_ptr(), dtype, B, Hm * Hm, Cn, mr.data_ptr(), Hh.stream())
     out = torch.empty(B * Hm * Hm * Cn, dtype=torch.float32, device="cuda")
     mode = {"multiply": L.INJECT_MUL_SCALED, "add": L.INJECT_ADD, "multiply_raw": L.INJECT_MUL}[style]
-    L.call("ng_in_apply", yb.t.data_ptr(), dtype, B, Hm, Hm, Cn, mr.data_ptr(), L.ACT_RELU, 0.0, None, 0,
+    L.call("ng_in_apply", yb.t.data_ptr(), dtype, B, Hm, Hm, Cn, mr.data_ptr(), None, None, L.ACT_RELU, 0.0, None, 0,
            e.data_ptr(), mode, s.data_ptr(), out.data_ptr(), 0, L.HALO_ZERO, Hh.stream())
     mu, rstd = Hh.stats_ref(y)
     xh = (y - mu[..., None, None]) * rstd[..., None, None]
