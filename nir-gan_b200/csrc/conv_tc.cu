@@ -291,29 +291,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // channel 3 (and the two alignment columns) of both windows stay zero: 3 real channels are stored as 4
       for (int i = pt; i < 2 * DS_SCRATCH_BYTES / 4; i += 128) reinterpret_cast<uint32_t*>(ds_scratch)[i] = 0u;
       asm volatile("bar.sync 6, 128;" ::: "memory");
-      uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (int q = cluster_id; q < p.total_groups; q += num_clusters, ++it) {
+      // Each thread owns up to DS_EPT fixed (channel, row, column) positions of the 14 x 22 x cin source window.  The
+      // loads of tile i + 1 are issued (all independent, in registers) before tile i's patch is built, so their latency
+      // hides behind the build and the wait for a free stage instead of being paid once per element.
+      constexpr int DS_EPT = 10;                                         // ceil(4 * 14 * 22 / 128)
+      const int n_el = p.src_c * PR * WC;
+      int el[DS_EPT];                                                    // row | column << 4 | channel << 9, -1 = none
+#pragma unroll
+      for (int k = 0; k < DS_EPT; ++k) {
+        const int e = pt + k * 128;
+        const int c = e % WC, rr = e / WC;
+        el[k] = e < n_el ? ((rr % PR) | (c << 4) | ((rr / PR) << 9)) : -1;
+      }
+      float v[DS_EPT];
+      auto issue_loads = [&](int q) {
         int cot, ph, n, py, px; bool dummy;
         decode(q, cot, ph, n, py, px, dummy);
         const int i0 = py * p.BH, j0 = px * p.BW;
-        uint16_t* win = reinterpret_cast<uint16_t*>(ds_scratch + (it & 1) * DS_SCRATCH_BYTES);
-        // ---- source window: rows i0 - 3 .. i0 + 10, columns j0 - 3 .. j0 + 18 of the (wrapper-padded) image, both
-        // reflections resolved; consecutive threads read consecutive columns of one (channel, row)
         const float* sn = p.src + (size_t)n * p.src_c * plane;
-        for (int e = pt; e < p.src_c * PR * WC; e += 128) {
-          const int c = e % WC, rr = e / WC;
-          const int r = rr % PR, ch = rr / PR;
-          const int y1 = min(i0 + r - halo, H1 - 1 + halo), x1 = min(j0 + c - halo, W1 - 1 + halo);
-          const int y0 = reflect_idx(reflect_idx(y1, H1) - p.src_wrap, p.src_H);
-          const int x0 = reflect_idx(reflect_idx(x1, W1) - p.src_wrap, p.src_W);
-          const float v = sn[ch * plane + (size_t)y0 * p.src_W + x0];
-          uint16_t hv;
-          if (p.bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(v); hv = *reinterpret_cast<const uint16_t*>(&t); }
-          else { const __half t = __float2half_rn(v); hv = *reinterpret_cast<const uint16_t*>(&t); }
-          win[(r * DS_WIN_W + c) * 4 + ch] = hv;
+#pragma unroll
+        for (int k = 0; k < DS_EPT; ++k) {
+          v[k] = 0.f;
+          if (el[k] >= 0) {
+            // rows i0 - 3 .. i0 + 10, columns j0 - 3 .. j0 + 18 of the (wrapper-padded) image, both reflections resolved
+            const int er = el[k] & 15, ec = (el[k] >> 4) & 31, ech = el[k] >> 9;
+            const int y1 = min(i0 + er - halo, H1 - 1 + halo), x1 = min(j0 + ec - halo, W1 - 1 + halo);
+            const int y0 = reflect_idx(reflect_idx(y1, H1) - p.src_wrap, p.src_H);
+            const int x0 = reflect_idx(reflect_idx(x1, W1) - p.src_wrap, p.src_W);
+            v[k] = __ldg(sn + ech * plane + (size_t)y0 * p.src_W + x0);
+          }
+        }
+      };
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      if (cluster_id < p.total_groups) issue_loads(cluster_id);
+      for (int q = cluster_id; q < p.total_groups; q += num_clusters, ++it) {
+        uint16_t* win = reinterpret_cast<uint16_t*>(ds_scratch + (it & 1) * DS_SCRATCH_BYTES);
+        // ---- this tile's source window: registers -> shared (16 bit)
+#pragma unroll
+        for (int k = 0; k < DS_EPT; ++k) {
+          if (el[k] >= 0) {
+            uint16_t hv;
+            if (p.bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(v[k]); hv = *reinterpret_cast<const uint16_t*>(&t); }
+            else { const __half t = __float2half_rn(v[k]); hv = *reinterpret_cast<const uint16_t*>(&t); }
+            win[((el[k] & 15) * DS_WIN_W + ((el[k] >> 4) & 31)) * 4 + (el[k] >> 9)] = hv;
+          }
         }
         asm volatile("bar.sync 6, 128;" ::: "memory");
+        if (q + num_clusters < p.total_groups) issue_loads(q + num_clusters);      // next tile's loads fly during the build
         // ---- patch rows: pixel (r, x) -> 32 elements (kw*4 + c) = source columns x .. x + 7 (kw = 7 meets zero weights)
         if (pt < 32) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         asm volatile("bar.sync 6, 128;" ::: "memory");

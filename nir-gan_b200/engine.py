@@ -155,12 +155,15 @@ class _SizedStub:
     """Stands in for a device buffer while a context is built only to learn how much memory it needs: plan compilation
     binds pointers and sizes but never touches buffer contents."""
 
-    def __init__(self, numel: int, dtype: torch.dtype):
+    FAKE_BASE = 0x7F0000000000         # non-null, 256-byte aligned, never dereferenced
+
+    def __init__(self, numel: int, dtype: torch.dtype, fake_off: int = 0):
         self._n, self._esz = int(numel), torch.empty(0, dtype=dtype).element_size()
         self.dtype = dtype
+        self._addr = self.FAKE_BASE + fake_off
 
     def data_ptr(self) -> int:
-        return 0x7F0000000000          # non-null, 256-byte aligned, never dereferenced
+        return self._addr
 
     def numel(self) -> int:
         return self._n
@@ -176,19 +179,103 @@ class CountingBuffers:
         self.device = device
         self._b: Dict[Tuple, _SizedStub] = {}
         self.total = 0
+        self.ranges: list = []             # (fake offset, bytes, key, zero-initialised)
 
     def get(self, name: str, numel: int, dtype: torch.dtype, zero: bool = False):
         key = (name, numel, dtype)
         t = self._b.get(key)
         if t is None:
-            t = self._b[key] = _SizedStub(numel, dtype)
-            if not zero:
-                a = PoolBuffers.ALIGN
-                self.total += (numel * t.element_size() + a - 1) // a * a
+            # every stub gets its own range of a fake address space, so that plan_memory() can tell from the pointers
+            # bound into a plan which buffers each op touches
+            t = self._b[key] = _SizedStub(numel, dtype, self.total)
+            a = PoolBuffers.ALIGN
+            nbytes = (numel * t.element_size() + a - 1) // a * a
+            self.ranges.append((self.total, nbytes, key, bool(zero)))
+            self.total += nbytes
         return t
 
     def bytes(self) -> int:
         return 0
+
+    def drop(self, tags) -> None:
+        pass
+
+
+def plan_memory(plans, counting: "CountingBuffers", pinned=()):
+    """Liveness-based layout of the buffers of forward-only plan(s) built over `counting`: a buffer is live from the first
+    to the last op that is bound to a pointer inside it (`pinned` stubs -- inputs written before the plan runs, results
+    read after it -- are live throughout), and buffers whose live ranges do not overlap share memory.  Greedy by size,
+    lowest fitting offset.  Returns ({buffer key: byte offset}, total bytes)."""
+    import bisect
+    starts = [r[0] for r in counting.ranges]
+    base = _SizedStub.FAKE_BASE
+    first, last = {}, {}
+
+    def touch(ptr, i):
+        if not isinstance(ptr, int) or ptr < base or ptr >= base + counting.total:
+            return
+        k = bisect.bisect_right(starts, ptr - base) - 1
+        first.setdefault(k, i)
+        last[k] = i
+
+    i = 0
+    for plan in plans:
+        for fn, args, _ in plan.ops:
+            for a in (args if fn is not None else ()):
+                obj = getattr(a, "_obj", None)
+                if isinstance(obj, L.ConvArgs):
+                    for f in ("x", "w", "bias", "y", "stat_partials", "mean_rstd", "tile_counters", "stat_acc"):
+                        touch(getattr(obj, f), i)
+                else:
+                    touch(a, i)
+            i += 1
+    n_ops = i
+    pinned_ids = set()
+    for t in pinned:
+        if isinstance(t, _SizedStub):
+            pinned_ids.add(bisect.bisect_right(starts, t.data_ptr() - base) - 1)
+    items = []
+    for k, (off, nbytes, key, zero) in enumerate(counting.ranges):
+        if k in pinned_ids or zero or k not in first:
+            lo, hi = -1, n_ops            # external, persistent or never seen in an op: keep it alive throughout
+        else:
+            lo, hi = first[k], last[k]
+        items.append((nbytes, lo, hi, key))
+    placed, offsets, total = [], {}, 0
+    for nbytes, lo, hi, key in sorted(items, key=lambda t: -t[0]):
+        busy = sorted((o, o + n) for (o, n, l2, h2) in placed if not (h2 < lo or hi < l2))
+        off = 0
+        for o, e in busy:
+            if off + nbytes <= o:
+                break
+            off = max(off, e)
+        placed.append((off, nbytes, lo, hi))
+        offsets[key] = off
+        total = max(total, off + nbytes)
+    return offsets, total
+
+
+class PlannedBuffers:
+    """``Buffers`` interface over one allocation with the byte offsets computed by ``plan_memory``."""
+
+    def __init__(self, offsets: dict, total: int, device):
+        self.device, self.offsets, self.total = device, offsets, total
+        self.t = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+        self._b: Dict[Tuple, torch.Tensor] = {}
+
+    def get(self, name: str, numel: int, dtype: torch.dtype, zero: bool = False) -> torch.Tensor:
+        key = (name, numel, dtype)
+        t = self._b.get(key)
+        if t is None:
+            off = self.offsets[key]
+            esz = torch.empty(0, dtype=dtype).element_size()
+            t = self._b[key] = self.t[off:off + numel * esz].view(dtype)
+            if zero:
+                t.zero_()
+        return t
+
+    def bytes(self) -> int:
+        return self.total
 
     def drop(self, tags) -> None:
         pass

@@ -32,27 +32,34 @@ class _RunnerBase:
         return self._engine
 
     def trim(self, eng: Engine) -> None:
-        """Plans own their buffers for life (static plan, no allocator).  With many distinct input shapes (mixed
-        resolutions, BASELINE config 5) the least-recently-used plans -- and the buffers only they reference -- are
-        dropped once the total exceeds the budget (NIRGAN_B200_BUFFER_GB, default 90), only when no forward is waiting
-        for its backward."""
+        """Plans own their memory for life (static plans, no allocator).  With many distinct input shapes the
+        least-recently-used plans are dropped once the total exceeds the budget (NIRGAN_B200_BUFFER_GB, default 90) --
+        only when no forward is waiting for its backward.  Training contexts share one pool per runner (its size is that
+        of the largest shape), so evicting them frees nothing unless pooling is off."""
         budget = float(os.environ.get("NIRGAN_B200_BUFFER_GB", "90")) * 1e9
         if self._live != 0:
             return
-        while eng.buffers.bytes() > budget:
+
+        def held():
+            planned = sum(getattr(v[1], "planned_bytes", 0) for v in self._fwd.values())
+            return eng.buffers.bytes() + planned + self.pool_bytes()
+
+        def tags_of(v):
+            return set(v.get("tags", ()) if isinstance(v, dict) else getattr(v[1], "tags", ()))
+
+        while held() > budget:
             cands = [(v.get("used", 0) if isinstance(v, dict) else getattr(v[1], "used", 0), d, k)
-                     for d in (self._fwd, self._train) for k, v in d.items()]
+                     for d in (self._fwd, self._train) for k, v in d.items()
+                     if not (isinstance(v, dict) and v.get("pool") is not None)]
             if len(cands) <= 1:
                 break
             _, d, k = min(cands, key=lambda c: c[0])
-            v = d[k]
-            tags = set(v.get("tags", ()) if isinstance(v, dict) else getattr(v[1], "tags", ()))
+            tags = tags_of(d[k])
             if not tags:
                 break
             # contexts that differ only in what they differentiate share their buffers (same tag): they go together
             for dd in (self._fwd, self._train):
-                for kk in [kk for kk, vv in dd.items()
-                           if tags & set(vv.get("tags", ()) if isinstance(vv, dict) else getattr(vv[1], "tags", ()))]:
+                for kk in [kk for kk, vv in dd.items() if tags & tags_of(vv)]:
                     del dd[kk]
             eng.buffers.drop(tags)
 
@@ -233,15 +240,44 @@ class GeneratorRunner(_RunnerBase):
             return plan
         self.trim(eng)
         tag = f"g{slot}_{B}x{Cin}x{H}x{W}p{wrap}{'i' if inject else ''}"      # shape-unique: plans are evicted by tag
-        g = self.build_graph(eng, B, H, W, wrap, inject, stream, tag, direct_head=not self._use_tap_head(),
-                             direct_stem=os.environ.get("NIRGAN_B200_STEM_DIRECT", "1") != "0")
-        plan = g.compile_forward()
-        plan.tags = (tag,)
-        if g.tap_head is None:
-            plan.records["out"] = g.units[-1].out_f32
+
+        def build():
+            g = self.build_graph(eng, B, H, W, wrap, inject, stream, tag, direct_head=not self._use_tap_head(),
+                                 direct_stem=os.environ.get("NIRGAN_B200_STEM_DIRECT", "1") != "0")
+            plan = g.compile_forward()
+            plan.tags = (tag,)
+            if g.tap_head is None:
+                plan.records["out"] = g.units[-1].out_f32
+            return g, plan
+
+        if os.environ.get("NIRGAN_B200_MEMPLAN", "1") != "0":
+            # forward-only plan: a buffer is dead after its last reader, so the ~70 per-layer buffers are laid out by
+            # liveness in ONE allocation (engine.plan_memory): peak = the two or three tensors alive at the widest layer
+            # instead of the sum over layers (B = 64 at 256x256: ~1.2 GB instead of 9.8 GB).  First pass: sizes and
+            # pointer uses only (no allocation); second pass: the real plan over the planned layout.
+            saved = eng.buffers
+            counter = CountingBuffers(eng.device)
+            eng.buffers = counter
+            try:
+                g0, p0 = build()
+                pinned = [p0.records[k] for k in ("src", "emb", "out") if k in p0.records]
+                offsets, total = _engine.plan_memory([p0], counter, pinned)
+                eng.buffers = _engine.PlannedBuffers(offsets, total, eng.device)
+                g, plan = build()
+                plan.keepalive.append(eng.buffers)
+                plan.planned_bytes = total
+            finally:
+                eng.buffers = saved
+        else:
+            g, plan = build()
         self._fwd[key] = (g, plan)
         self.touch(self._fwd[key])
         return plan
+
+    def inference_bytes(self) -> int:
+        """Device memory held by the cached inference plans (planned layouts + per-layer buffers)."""
+        eng = self._engine
+        return sum(getattr(p, "planned_bytes", 0) for _, p in self._fwd.values()) + (eng.buffers.bytes() if eng else 0)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, embeds: Optional[torch.Tensor] = None, wrap_pad: int = 0) -> torch.Tensor:

@@ -51,3 +51,42 @@ def test_tile_batches_group_by_shape_in_list_order():
     assert _batches(names, tiles, 2) == [["t0", "t1"], ["t2"], ["t3", "t4"], ["t5", "t6"]]
     assert _batches(names, tiles, 64) == [["t0", "t1", "t2"], ["t3", "t4"], ["t5", "t6"]]
     assert _batches([], tiles, 4) == []
+
+
+def test_plan_memory_never_overlaps_live_buffers():
+    """engine.plan_memory: buffers whose live ranges (first..last op that is bound to a pointer inside them) intersect
+    never share bytes; pinned buffers stay alive throughout; the total is well below the sum for a chain of layers."""
+    import torch
+    from nirgan_b200.engine import CountingBuffers, Plan, plan_memory
+    cb = CountingBuffers("cpu")
+    src = cb.get("in", 1000, torch.float32)
+    bufs = [cb.get(f"l{i}", 5000 + 100 * (i % 3), torch.float16) for i in range(12)]
+    out = cb.get("out", 300, torch.float32)
+    p = Plan()
+    prev = src
+    for i, b in enumerate(bufs):                      # layer i reads layer i-1 (and i-3 as a residual), writes i
+        res = bufs[i - 3].data_ptr() + 64 if i >= 3 else None
+        p.add("ng_in_apply", prev.data_ptr(), res, b.data_ptr(), label=f"l{i}")
+        prev = b
+    p.add("ng_tap_gather", prev.data_ptr(), out.data_ptr(), label="head")
+    offsets, total = plan_memory([p], cb, pinned=[src, out])
+    live = {}
+    for i, (fn, args, _) in enumerate(p.ops):
+        for a in args:
+            if a is None:
+                continue
+            for off, nbytes, key, _z in cb.ranges:
+                if off <= a - 0x7F0000000000 < off + nbytes:
+                    lo, hi = live.get(key, (i, i))
+                    live[key] = (min(lo, i), max(hi, i))
+    live[("in", 1000, torch.float32)] = (-1, len(p.ops))
+    live[("out", 300, torch.float32)] = (-1, len(p.ops))
+    size = {key: nbytes for _, nbytes, key, _z in cb.ranges}
+    keys = list(size)
+    for i, a in enumerate(keys):
+        for b in keys[i + 1:]:
+            la, lb = live[a], live[b]
+            if not (la[1] < lb[0] or lb[1] < la[0]):          # alive at the same time -> disjoint memory
+                assert offsets[a] + size[a] <= offsets[b] or offsets[b] + size[b] <= offsets[a], (a, b)
+    assert total <= 0.6 * sum(size.values())
+    assert total >= max(size.values())
