@@ -209,10 +209,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tp = g.phase_tap0[ph]; tp < g.phase_tap0[ph + 1]; ++tp) {
           const int by = g.S * i0 + g.taps[tp].dy, bx = g.S * j0 + g.taps[tp].dx;
           const int brow = g.taps[tp].wrow + cot * BN;
+          // merged phases: tap tp is the input shift (sy, sx) = (tp >> 1, tp & 1); output phase (pa, pb) uses it iff
+          // pa >= sy and pb >= sx -- 9 of the 16 (shift, phase) weight slabs are non-zero.  Only those are fetched (and
+          // multiplied, see the MMA issuer); a shift that none of this tile's phases uses is skipped altogether.
+          uint32_t used = 0;
+          const int Cr = g.Cout_real, nph = g.merged ? BN / Cr : 0, ph_lo = g.merged ? (cot * BN) / Cr : 0;
+          for (int l = 0; l < nph; ++l) {
+            const int phs = ph_lo + l;
+            if ((phs >> 1) >= (tp >> 1) && (phs & 1) >= (tp & 1)) used |= 1u << l;
+          }
+          if (g.merged && used == 0) continue;
           for (int c = 0; c < chunks; ++c) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);       // free in every CTA of the cluster
             const uint32_t fb = smem_u32(&full_bar[stage]);
             const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+            if (g.merged) {
+              mbar_expect_tx(fb, (uint32_t)(p.BH * p.BW * KC * 2 + __popc(used) * Cr * KC * 2));
+              tma_load_4d(&tmA, fb, sa, c * KC, bx, by, n);
+              for (int l = 0; l < nph; ++l)          // tmB's box is one phase slab (Cout_real rows) for merged launches
+                if (used & (1u << l)) tma_load_2d(&tmB, fb, sa + Cfg::A_BYTES + l * (Cr * KC * 2), c * KC, brow + l * Cr);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_expect_tx(fb, (uint32_t)(p.BH * p.BW * KC * 2 + BN * KC * 2));   // the A box holds BH*BW (<=128) rows
             tma_load_4d(&tmA, fb, sa, c * KC, bx, by, n);
             if constexpr (CS == 1) {
@@ -258,6 +276,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(smem_u32(&tfull_bar[as]));
+          if (++as == 2) { as = 0; as_phase ^= 1; }
+          continue;
+        }
+        if (g.merged) {
+          // sparse merged phases (see the producer): one N = Cout_real MMA chain per (shift, phase) slab that is not
+          // identically zero, each phase accumulating in its own TMEM column block
+          const int Cr = g.Cout_real, nph = BN / Cr;
+          const int cot = (q / p.groups_per) / g.nphase, ph_lo = (cot * BN) / Cr;
+          const uint32_t idesc_s = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(Cr >> 3) << 17);
+          int kit = 0;
+          for (int tp = 0; tp < g.ntaps; ++tp) {
+            uint32_t used = 0;
+            for (int l = 0; l < nph; ++l) {
+              const int phs = ph_lo + l;
+              if ((phs >> 1) >= (tp >> 1) && (phs & 1) >= (tp & 1)) used |= 1u << l;
+            }
+            if (used == 0) continue;
+            for (int c = 0; c < chunks; ++c, ++kit) {
+              mbar_wait(smem_u32(&full_bar[stage]), phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+              const uint64_t adesc = make_kmajor_desc(sa, SBO, LAYOUT);
+              for (int l = 0; l < nph; ++l) {
+                if (!(used & (1u << l))) continue;
+                const uint64_t bdesc = make_kmajor_desc(sa + Cfg::A_BYTES + l * (Cr * KC * 2), SBO, LAYOUT);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)       // every phase uses shift 0: its first MMA is at kit == 0
+                  umma_f16(tmem_c + l * Cr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_s,
+                           (uint32_t)((kit | k) != 0));
+              }
+              umma_commit(smem_u32(&empty_bar[stage]));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
           umma_commit(smem_u32(&tfull_bar[as]));
           if (++as == 2) { as = 0; as_phase ^= 1; }
           continue;
@@ -733,7 +786,8 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
     const int taps_total = g.merged ? g.ntaps : a.KH * a.KW;
     cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)taps_total * g.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
-    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(BN / CS)};
+    // merged phases: one box = one (shift, phase) slab of Cout_real rows (only the non-zero slabs are fetched)
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(g.merged ? g.Cout_real : BN / CS)};
     cuuint32_t estr[2] = {1, 1};
     int cr = 0;
     const int er = cached_tensor_map(&tmB, dt, 2, a.w, dims, strides, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, &cr);
@@ -910,7 +964,7 @@ int conv_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) {
   if (bn == 128 && kc == 64) return wide_env >= 3 ? launch_tc<128, 64, 1, false, 4>(a, g, st) : launch_tc<128, 64, 1>(a, g, st);
   if (bn == 256 && kc == 64 && wide) return launch_tc<256, 64, 1, false, 4>(a, g, st);
   if (bn == 256 && kc == 64) {
-    const int cs = cluster_size_for(bn, kc);
+    const int cs = g.merged ? 1 : cluster_size_for(bn, kc);
     if (cs == 4) return launch_tc<256, 64, 4>(a, g, st);
     if (cs == 2) return launch_tc<256, 64, 2>(a, g, st);
     return launch_tc<256, 64, 1>(a, g, st);

@@ -29,16 +29,21 @@ struct WgParams {
   int P;                      // B * patches_y * patches_x
   int n_tiles;                // ceil(Cout / 128)
   int splits, pps;            // pixel-range splits, patches per split
-  int total_units;            // splits * ntaps * n_tiles
+  int total_units;            // splits * ngroups * n_tiles
   int bf16;
   float* partials;            // [splits][ntaps][Cout][Cin]
+  // tap groups: a work unit walks grp_cnt[k] (<= NT) consecutive taps of ONE output phase starting at grp_first[k]; the
+  // dY tile of a pipeline stage is loaded once per group instead of once per tap
+  int ngroups;
+  unsigned char grp_first[64], grp_cnt[64];
 };
 
-// NT = taps handled per pipeline stage.  NT == 1: work unit = (split, tap, n tile), two accumulators (epilogue of one
-// unit overlaps the MMAs of the next).  NT == ntaps ("tap-inner", needs NT*BN <= 512 TMEM columns): work unit =
-// (split, n tile); a stage holds the dY tile once plus the X tile of every tap, and each tap accumulates into its own
-// BN-column TMEM slice -- for thin layers (PatchGAN input layer: 16 taps x 16 channels; generator stem: 7 x 64) this cuts
-// the L2 -> shared-memory traffic of the dY operand by NT.
+// NT = taps handled per pipeline stage ("tap group", NT*BN <= 512 TMEM columns): work unit = (split, tap group, n tile); a
+// stage holds the dY tile once plus the X tile of every tap of the group, and each tap accumulates into its own BN-column
+// TMEM slice.  For the thin layers (few input channels, many taps) the dY operand dominates the L2 -> shared-memory
+// traffic and is fetched once per GROUP instead of once per tap: PatchGAN input layer 16 taps x 16 channels and the
+// generator stem 7 x 64 in one group; 64-channel layers in groups of 3-4, 128-channel layers in pairs.  Two accumulator
+// sets (the epilogue of one unit overlaps the MMAs of the next) whenever 2*NT*BN columns fit.
 template <int BN, int NT>
 struct WgCfg {
   static constexpr int A_BYTES = 2 * WG_SLAB;
@@ -50,7 +55,7 @@ struct WgCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES_RAW = (216 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int NACC = NT == 1 ? 2 : 1;
+  static constexpr int NACC = 2 * NT * BN <= 512 ? 2 : 1;
   static constexpr int ACC_COLS = NACC * NT * BN;
   static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : (ACC_COLS <= 64 ? 64 : (ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
@@ -94,12 +99,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int per_split = (NT == 1 ? g.ntaps : 1) * p.n_tiles;
-  auto decode = [&](int u, int& split, int& tap, int& nt, int& pt0, int& pt1) {
+  const int per_split = p.ngroups * p.n_tiles;
+  auto decode = [&](int u, int& split, int& tap, int& cnt, int& nt, int& pt0, int& pt1) {
     split = u / per_split;
     const int r = u - split * per_split;
-    tap = r / p.n_tiles;                    // NT > 1: always 0 (the taps are walked inside the unit)
-    nt = r - tap * p.n_tiles;
+    const int grp = r / p.n_tiles;
+    tap = p.grp_first[grp];                 // first tap of the group
+    cnt = p.grp_cnt[grp];                   // taps walked inside the unit (<= NT)
+    nt = r - grp * p.n_tiles;
     pt0 = split * p.pps;
     pt1 = min(p.P, pt0 + p.pps);
   };
@@ -109,12 +116,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-        int split, tap, nt, pt0, pt1;
-        decode(u, split, tap, nt, pt0, pt1);
+        int split, tap, cnt, nt, pt0, pt1;
+        decode(u, split, tap, cnt, nt, pt0, pt1);
         int ph = 0;
         while (tap >= g.phase_tap0[ph + 1]) ++ph;
-        const int dy = g.taps[tap].dy, dx = g.taps[tap].dx;
         const int oy0 = g.phase_oy[ph], ox0 = g.phase_ox[ph];
+        const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + cnt * Cfg::B_TAP_BYTES);
         const int per_img = p.patches_y * p.patches_x;
         for (int pt = pt0; pt < pt1; ++pt) {
           const int n = pt / per_img;
@@ -124,22 +131,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          mbar_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
+          mbar_expect_tx(fb, stage_tx);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             tma_load_4d(&tmY, fb, sa + j * WG_SLAB, nt * 128 + 64 * j, g.OS * vj0 + ox0, g.OS * vi0 + oy0, n);
-          if constexpr (NT == 1) {
+#pragma unroll 1
+          for (int t = 0; t < cnt; ++t)
 #pragma unroll
             for (int j = 0; j < Cfg::B_LOADS; ++j)
-              tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + j * WG_SLAB, 64 * j, g.S * vj0 + dx, g.S * vi0 + dy, n);
-          } else {
-#pragma unroll 1
-            for (int t = 0; t < NT; ++t)
-#pragma unroll
-              for (int j = 0; j < Cfg::B_LOADS; ++j)
-                tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES + j * WG_SLAB, 64 * j,
-                            g.S * vj0 + g.taps[t].dx, g.S * vi0 + g.taps[t].dy, n);
-          }
+              tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES + j * WG_SLAB, 64 * j,
+                          g.S * vj0 + g.taps[tap + t].dx, g.S * vi0 + g.taps[tap + t].dy, n);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -153,8 +154,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
                              (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-        int split, tap, nt, pt0, pt1;
-        decode(u, split, tap, nt, pt0, pt1);
+        int split, tap, cnt, nt, pt0, pt1;
+        decode(u, split, tap, cnt, nt, pt0, pt1);
         const int kiters = pt1 - pt0;
         mbar_wait(smem_u32(&tempty_bar[as]), as_phase ^ 1);
         tc_fence_after();
@@ -165,7 +166,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t adesc = make_mnmajor_desc(sa, WG_SLAB, 1024);
 #pragma unroll 1
-          for (int t = 0; t < NT; ++t) {
+          for (int t = 0; t < cnt; ++t) {
             const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES;
             const uint64_t bdesc = BN >= 64 ? make_mnmajor_desc(sb, WG_SLAB, 1024) : make_mnmajor_desc_sw32(sb, 256);
 #pragma unroll
@@ -187,16 +188,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     const int row = q * 32 + lane;
     uint32_t as = 0, as_phase = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-      int split, tap, nt, pt0, pt1;
-      decode(u, split, tap, nt, pt0, pt1);
+      int split, tap, cnt, nt, pt0, pt1;
+      decode(u, split, tap, cnt, nt, pt0, pt1);
       const int n = nt * 128 + row;
       mbar_wait(smem_u32(&tfull_bar[as]), as_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int t = 0; t < NT; ++t) {
+      for (int t = 0; t < cnt; ++t) {
         const uint32_t taddr = tmem_base + as * (NT * BN) + t * BN + ((uint32_t)(q * 32) << 16);
         // packed weight-gradient row of this tap: wrow = (kh*KW + kw) * Cout (phased geometries enumerate taps by phase)
-        const int tp = NT == 1 ? tap : t;
+        const int tp = tap + t;
         float* dst = p.partials + ((size_t)split * g.ntaps * g.Cout + g.taps[tp].wrow + (n < g.Cout ? n : 0)) * (size_t)g.Cin;
         if constexpr (BN >= 32) {
 #pragma unroll 1
@@ -300,14 +301,22 @@ wgrad_reduce_sliced_kernel(const float4* __restrict__ part, int splits, long lon
 // ------------------------------------------------------------------------------------------------
 struct WgPlan {
   int BH, BW, patches_y, patches_x, P, n_tiles, splits, pps, bn;
-  int nt;       // taps per stage: 1, or ntaps for the tap-inner variant
+  int nt;       // taps per stage (compile-time group capacity)
+  int ngroups;
+  unsigned char grp_first[64], grp_cnt[64];
 };
 
-// tap-inner instantiations: (Cin 16, 16 taps) = PatchGAN input layer, (Cin 64, 7 taps) = row-merged generator stem
-static int tap_inner_for(const ConvGeom& g) {
-  if (g.nphase != 1) return 1;
-  if (g.Cin == 16 && g.ntaps == 16) return 16;
-  if (g.Cin == 64 && g.ntaps == 7) return 7;
+// taps per group by input-channel count (NT * Cin <= 512 TMEM columns; instantiated pairs only):
+// (16, 16) PatchGAN input layer; (64, 7) row-merged generator stem; (64, 3) / (64, 4) 3x3 / 4x4 layers with 64 input
+// channels; (128, 2) layers with 128 input channels.  NIRGAN_B200_WGRAD_GROUPS=0: one tap per unit except the two
+// round-1 tap-inner cases.
+static int taps_per_group(const ConvGeom& g) {
+  static const bool on = [] { const char* e = getenv("NIRGAN_B200_WGRAD_GROUPS"); return !(e && e[0] == '0'); }();
+  if (g.Cin == 16 && g.ntaps == 16 && g.nphase == 1) return 16;
+  if (g.Cin == 64 && g.ntaps == 7 && g.nphase == 1) return 7;
+  if (!on) return 1;
+  if (g.Cin == 64 && g.ntaps > 1) return g.ntaps % 4 == 0 && g.nphase == 1 ? 4 : 3;
+  if (g.Cin == 128 && g.ntaps > 1) return 2;
   return 1;
 }
 
@@ -333,8 +342,17 @@ static void wgrad_plan(const ng_conv_args& a, const ConvGeom& g, WgPlan& w) {
   w.P = g.B * w.patches_y * w.patches_x;
   w.n_tiles = (g.Cout + 127) / 128;
   w.bn = g.Cin;
-  w.nt = tap_inner_for(g);
-  const int base = (w.nt == 1 ? g.ntaps : 1) * w.n_tiles, sms = num_sms();
+  w.nt = taps_per_group(g);
+  // groups of up to nt consecutive taps that share an output phase (the dY box position depends on the phase)
+  w.ngroups = 0;
+  for (int ph = 0; ph < g.nphase; ++ph)
+    for (int t = g.phase_tap0[ph]; t < g.phase_tap0[ph + 1]; t += w.nt) {
+      const int left = g.phase_tap0[ph + 1] - t;
+      w.grp_first[w.ngroups] = (unsigned char)t;
+      w.grp_cnt[w.ngroups] = (unsigned char)(left < w.nt ? left : w.nt);
+      ++w.ngroups;
+    }
+  const int base = w.ngroups * w.n_tiles, sms = num_sms();
   int best_s = 1; double best_eff = -1.0;
   int max_s = 4 * sms / base;                   // enough splits to fill the GPU even for a single-tap, single-tile problem
   if (max_s < 64) max_s = 64;
@@ -367,7 +385,10 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
   p.g = g;
   p.BH = w.BH; p.BW = w.BW; p.patches_y = w.patches_y; p.patches_x = w.patches_x; p.P = w.P;
   p.n_tiles = w.n_tiles; p.splits = w.splits; p.pps = w.pps;
-  p.total_units = w.splits * (NT == 1 ? g.ntaps : 1) * w.n_tiles;
+  p.ngroups = w.ngroups;
+  memcpy(p.grp_first, w.grp_first, sizeof(p.grp_first));
+  memcpy(p.grp_cnt, w.grp_cnt, sizeof(p.grp_cnt));
+  p.total_units = w.splits * w.ngroups * w.n_tiles;
   p.bf16 = a.dtype == NG_BF16;
   p.partials = w.splits == 1 ? dw : reinterpret_cast<float*>(workspace);
 
@@ -439,6 +460,10 @@ int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspac
   *handled = true;
   if (w.nt == 16 && g.Cin == 16) return launch_wgrad_tc<16, 16>(a, g, w, dw, workspace, st);
   if (w.nt == 7 && g.Cin == 64) return launch_wgrad_tc<64, 7>(a, g, w, dw, workspace, st);
+  if (w.nt == 4 && g.Cin == 64) return launch_wgrad_tc<64, 4>(a, g, w, dw, workspace, st);
+  if (w.nt == 3 && g.Cin == 64) return launch_wgrad_tc<64, 3>(a, g, w, dw, workspace, st);
+  if (w.nt == 2 && g.Cin == 128) return launch_wgrad_tc<128, 2>(a, g, w, dw, workspace, st);
+  NG_REQUIRE(w.nt == 1, NG_E_UNSUPPORTED, "wgrad_tc: no kernel for %d taps per group at Cin %d", w.nt, g.Cin);
   switch (g.Cin) {
     case 16:  return launch_wgrad_tc<16, 1>(a, g, w, dw, workspace, st);
     case 64:  return launch_wgrad_tc<64, 1>(a, g, w, dw, workspace, st);
