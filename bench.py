@@ -117,25 +117,45 @@ def build_model(dev):
 
 
 def cpu_oracle_tiles_per_sec(budget_s=12.0, batch=4):
-    """Reference CPU path (oracle port) on the host cores: bounded sample of the same workload."""
+    """The reference's CPU path on the host cores: a bounded sample of the same workload.  Runs the reference's OWN modules
+    (oracle/_ref: unmodified model/networks.py + model/generator_inject.py placed there by oracle/make_ref.py, kind
+    "reference") when that tree travelled with the snapshot, else the oracle port (kind "port").
+    Returns (tiles/s, cores, sample description, kind)."""
+    import contextlib
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import nirgan_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = O.random_state_dict(O.generator_param_shapes(inject=True), seed=0)
     g = torch.Generator().manual_seed(1)
     x = torch.rand(batch, 3, TILE, TILE, generator=g)
     e = torch.randn(batch, 256, generator=g)
+    fwd, kind = None, "port"
+    try:
+        import make_ref
+        mods = make_ref.load()
+        if mods is not None:
+            from nirgan_b200.config import satclip_inject_config      # attribute-style mirror of config_px2px_SatCLIP.yaml
+            torch.manual_seed(0)
+            with contextlib.redirect_stdout(sys.stderr):
+                net = mods[1].define_G_inject(satclip_inject_config()).eval()
+            fwd, kind = (lambda xb, eb: net(xb, eb)), "reference"
+    except Exception as ex:                    # the reference tree is optional: say why the port is used instead
+        print(f"bench.py: oracle/_ref not usable ({type(ex).__name__}: {ex}); timing the oracle port", file=sys.stderr)
+    if fwd is None:
+        import nirgan_oracle as O
+        sd = O.random_state_dict(O.generator_param_shapes(inject=True), seed=0)
+        fwd = lambda xb, eb: O.resnet_generator_forward(sd, xb, embeds=eb)
     with torch.no_grad():
-        O.resnet_generator_forward(sd, x[:1], embeds=e[:1])          # warm-up
+        fwd(x[:1], e[:1])                                             # warm-up
         n, t0 = 0, time.perf_counter()
         while True:
-            O.resnet_generator_forward(sd, x, embeds=e)
+            fwd(x, e)
             n += batch
             el = time.perf_counter() - t0
             if el >= budget_s or n >= 64:
                 break
-    return n / el, cores, f"{n} tiles ({n // batch} batches of {batch}) of the 64-tile step, fp32, torch {torch.__version__} CPU, {el:.1f} s"
+    what = "the reference's own nn.Modules (oracle/_ref)" if kind == "reference" else "oracle port"
+    return n / el, cores, (f"{n} tiles ({n // batch} batches of {batch}) of the 64-tile step, {what}, fp32, "
+                           f"torch {torch.__version__} CPU, {el:.1f} s"), kind
 
 
 def run_reference(args):
@@ -144,8 +164,9 @@ def run_reference(args):
         return
     vals = []
     sample = ""
+    kind = "port"
     for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_oracle_tiles_per_sec(budget_s=6.0, batch=4)
+        v, cores, sample, kind = cpu_oracle_tiles_per_sec(budget_s=6.0, batch=4)
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
@@ -153,9 +174,10 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": BATCH / v * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD,
-                       "note": "CPU oracle port of the reference (pure-Python reference cannot travel); each step is a "
-                               "bounded sample of the 64-tile step on all host cores"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                       "note": "the reference's CPU implementation of the path (its own modules from oracle/_ref when "
+                               "present, else the oracle port); each step is a bounded sample of the 64-tile step on all "
+                               "host cores"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -390,6 +412,8 @@ def main():
     ap.add_argument("--train-steps", type=int, default=10, help="steps per timed window of the configs[3] loop")
     ap.add_argument("--min-windows", type=int, default=5)
     ap.add_argument("--min-seconds", type=float, default=2.0)
+    ap.add_argument("--settle", type=float, default=1.0,
+                    help="seconds of untimed work before the first window of a loop (clock ramp); 0 under a profiler")
     ap.add_argument("--sync-calls", action="store_true",
                     help="issue steps with net(x, e) (joins the caller's stream every step) instead of forward_async")
     ap.add_argument("--no-graph", action="store_true")
@@ -489,11 +513,11 @@ def main():
     # identical conditions for both loops: a clock sampler beside each, the same warm-up rule, the same window rule
     samplers["value"] = ClockSampler(local) if rank == 0 else None
     w_val = tm.windows(step_resident, args.steps, args.warmup, join=join_last, min_windows=args.min_windows,
-                       min_total_s=args.min_seconds)
+                       min_total_s=args.min_seconds, settle_s=args.settle)
     clock_parts["value"] = samplers["value"].stop() if samplers["value"] else None
     samplers["e2e"] = ClockSampler(local) if rank == 0 else None
     w_e2e = tm.windows(step_e2e, args.steps, args.warmup, join=join_last, min_windows=args.min_windows,
-                       min_total_s=args.min_seconds)
+                       min_total_s=args.min_seconds, settle_s=args.settle)
     clock_parts["e2e"] = samplers["e2e"].stop() if samplers["e2e"] else None
     ms, ms_e2e = w_val["ms_p50"], w_e2e["ms_p50"]
     # diagnostic: the host link alone (one H2D of a step's tiles from pinned memory), to read e2e against
@@ -654,8 +678,8 @@ def main():
             json.dump([{"op": name, "label": plan.labels[i], "ms": round(op_ms[i], 5)}
                        for i, (fn, a, name) in enumerate(plan.ops)], f, indent=0)
     if not args.no_cpu_baseline:
-        v, cores, sample = cpu_oracle_tiles_per_sec()
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        v, cores, sample, kind = cpu_oracle_tiles_per_sec()
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -45,6 +45,7 @@ struct TcParams {
   float* mean_rstd;           // fused finalisation (optional)
   int* tile_counters;
   unsigned long long* stat_acc;   // fixed-point per-(image, channel) statistics accumulators (optional)
+  int sparse_merged;          // merged phases: skip the identically-zero (shift, phase) weight slabs (off by default)
   int image_minor;            // tile order: consecutive work items walk the images first (spreads the accumulator atomics)
   unsigned long long mg_B;    // ceil(2^42 / B)
   // DS ("direct stem"): the A operand is built in shared memory from the caller's NCHW fp32 planes
@@ -213,17 +214,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // pa >= sy and pb >= sx -- 9 of the 16 (shift, phase) weight slabs are non-zero.  Only those are fetched (and
           // multiplied, see the MMA issuer); a shift that none of this tile's phases uses is skipped altogether.
           uint32_t used = 0;
-          const int Cr = g.Cout_real, nph = g.merged ? BN / Cr : 0, ph_lo = g.merged ? (cot * BN) / Cr : 0;
+          const bool sparse = g.merged && p.sparse_merged;
+          const int Cr = g.Cout_real, nph = sparse ? BN / Cr : 0, ph_lo = sparse ? (cot * BN) / Cr : 0;
           for (int l = 0; l < nph; ++l) {
             const int phs = ph_lo + l;
             if ((phs >> 1) >= (tp >> 1) && (phs & 1) >= (tp & 1)) used |= 1u << l;
           }
-          if (g.merged && used == 0) continue;
+          if (sparse && used == 0) continue;
           for (int c = 0; c < chunks; ++c) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);       // free in every CTA of the cluster
             const uint32_t fb = smem_u32(&full_bar[stage]);
             const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
-            if (g.merged) {
+            if (sparse) {
               mbar_expect_tx(fb, (uint32_t)(p.BH * p.BW * KC * 2 + __popc(used) * Cr * KC * 2));
               tma_load_4d(&tmA, fb, sa, c * KC, bx, by, n);
               for (int l = 0; l < nph; ++l)          // tmB's box is one phase slab (Cout_real rows) for merged launches
@@ -280,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++as == 2) { as = 0; as_phase ^= 1; }
           continue;
         }
-        if (g.merged) {
+        if (g.merged && p.sparse_merged) {
           // sparse merged phases (see the producer): one N = Cout_real MMA chain per (shift, phase) slab that is not
           // identically zero, each phase accumulating in its own TMEM column block
           const int Cr = g.Cout_real, nph = BN / Cr;
@@ -765,6 +767,12 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   p.stat_acc = reinterpret_cast<unsigned long long*>(a.stat_acc);
   p.image_minor = (a.stat_acc != nullptr && g.B > 1) ? 1 : 0;
   p.mg_B = ((1ull << 42) + (unsigned)g.B - 1) / (unsigned)g.B;
+  // Measured on B200 (profiles/r2c): fetching / multiplying only the 9 non-zero (shift, phase) slabs of a merged-phase
+  // ConvTranspose is SLOWER than the dense N = 256 form (u2 0.142 -> 0.203 ms, u1 0.110 -> 0.121 ms per 32 tiles): an
+  // N = 64 tcgen05.mma re-reads the whole 128-row A tile from shared memory for a quarter of the columns, so the 72
+  // narrow MMAs cost more than the 32 wide ones they replace.  Kept as a tested switch.
+  static const int sparse_env = [] { const char* v = getenv("NIRGAN_B200_SPARSE_MERGED"); return v ? atoi(v) : 0; }();
+  p.sparse_merged = (g.merged && sparse_env && CS == 1) ? 1 : 0;
   p.arrivals_per_image = p.patches_y * p.patches_x * g.nphase * p.co_tiles * Cfg::EGT;
   p.inv_count = 1.0f / ((float)g.Hout * (float)g.Wout);
 
@@ -787,7 +795,7 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
     cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)taps_total * g.Cout};
     cuuint64_t strides[1] = {(cuuint64_t)g.Cin * 2};
     // merged phases: one box = one (shift, phase) slab of Cout_real rows (only the non-zero slabs are fetched)
-    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(g.merged ? g.Cout_real : BN / CS)};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)(p.sparse_merged ? g.Cout_real : BN / CS)};
     cuuint32_t estr[2] = {1, 1};
     int cr = 0;
     const int er = cached_tensor_map(&tmB, dt, 2, a.w, dims, strides, box, estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, &cr);
