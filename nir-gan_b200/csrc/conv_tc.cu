@@ -340,40 +340,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if constexpr (DS) {
       const int pt = threadIdx.x - Cfg::DS_WARP0 * 32;                   // 0..127
       constexpr int PR = RT_BH + RT_KH - 1;                              // 14 patch rows
-      constexpr int WC = RT_BW + RT_KH - 1;                              // 22 source columns
       const int H1 = g.Hout, W1 = g.Wout, halo = RT_KH / 2;
       const size_t plane = (size_t)p.src_H * p.src_W;
-      // channel 3 (and the two alignment columns) of both windows stay zero: 3 real channels are stored as 4
-      for (int i = pt; i < 2 * DS_SCRATCH_BYTES / 4; i += 128) reinterpret_cast<uint32_t*>(ds_scratch)[i] = 0u;
-      asm volatile("bar.sync 6, 128;" ::: "memory");
-      // Each thread owns up to DS_EPT fixed (channel, row, column) positions of the 14 x 22 x cin source window.  The
-      // loads of tile i + 1 are issued (all independent, in registers) before tile i's patch is built, so their latency
-      // hides behind the build and the wait for a free stage instead of being paid once per element.
-      constexpr int DS_EPT = 10;                                         // ceil(4 * 14 * 22 / 128)
-      const int n_el = p.src_c * PR * WC;
-      int el[DS_EPT];                                                    // row | column << 4 | channel << 9, -1 = none
+      // Source window of a tile: 14 rows x 24 columns (padded-image columns j0 - 4 .. j0 + 19: the 22 the taps need plus one
+      // on either side so that the window starts on an even source column) x up to 4 channels, kept in shared memory as
+      // [row][column][4 channels] 16-bit (8 bytes per pixel).  Work item = (row, column PAIR): per channel one 8-byte load
+      // of two neighbouring source pixels (a scalar pair with the reflections resolved where the pair touches the image
+      // border, or when the geometry rules out aligned pairs), then ONE 16-byte shared store of the two converted pixels.
+      // 168 items over 128 threads; the loads of tile i + 1 are issued into registers before tile i's patch is built, so
+      // their latency hides behind the build and the wait for a free stage.
+      constexpr int CPAIRS = DS_WIN_W / 2;                               // 12 column pairs per row
+      constexpr int N_ITEMS = PR * CPAIRS;                               // 168
+      constexpr int IPT = (N_ITEMS + 127) / 128;                         // items per thread: 2
+      const bool vec_ok = ((p.src_W | p.src_wrap) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.src) & 7) == 0 &&
+                          (plane & 1) == 0;
+      float2 v[IPT][4];
 #pragma unroll
-      for (int k = 0; k < DS_EPT; ++k) {
-        const int e = pt + k * 128;
-        const int c = e % WC, rr = e / WC;
-        el[k] = e < n_el ? ((rr % PR) | (c << 4) | ((rr / PR) << 9)) : -1;
-      }
-      float v[DS_EPT];
+      for (int k = 0; k < IPT; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[k][c] = make_float2(0.f, 0.f);
       auto issue_loads = [&](int q) {
         int cot, ph, n, py, px; bool dummy;
         decode(q, cot, ph, n, py, px, dummy);
         const int i0 = py * p.BH, j0 = px * p.BW;
         const float* sn = p.src + (size_t)n * p.src_c * plane;
 #pragma unroll
-        for (int k = 0; k < DS_EPT; ++k) {
-          v[k] = 0.f;
-          if (el[k] >= 0) {
-            // rows i0 - 3 .. i0 + 10, columns j0 - 3 .. j0 + 18 of the (wrapper-padded) image, both reflections resolved
-            const int er = el[k] & 15, ec = (el[k] >> 4) & 31, ech = el[k] >> 9;
-            const int y1 = min(i0 + er - halo, H1 - 1 + halo), x1 = min(j0 + ec - halo, W1 - 1 + halo);
-            const int y0 = reflect_idx(reflect_idx(y1, H1) - p.src_wrap, p.src_H);
-            const int x0 = reflect_idx(reflect_idx(x1, W1) - p.src_wrap, p.src_W);
-            v[k] = __ldg(sn + ech * plane + (size_t)y0 * p.src_W + x0);
+        for (int k = 0; k < IPT; ++k) {
+          const int item = pt + k * 128;
+          if (item >= N_ITEMS) continue;
+          const int r = item / CPAIRS, cp = item - r * CPAIRS;
+          // row: padded-image row i0 + r - 3 -> both reflections resolved (rows are independent of one another)
+          const int y1 = min(i0 + r - halo, H1 - 1 + halo);
+          const int y0 = reflect_idx(reflect_idx(y1, H1) - p.src_wrap, p.src_H);
+          const float* row = sn + (size_t)y0 * p.src_W;
+          const int xp = j0 - 4 + 2 * cp;                                // padded-image column of the pair's first pixel
+          const int xs = xp - p.src_wrap;                                // source column, if no reflection is involved
+          if (vec_ok && xp >= 0 && xp + 1 < W1 && xs >= 0 && xs + 1 < p.src_W) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < p.src_c) v[k][c] = __ldg(reinterpret_cast<const float2*>(row + c * plane + xs));
+          } else {
+            const int xa = min(max(xp, -halo), W1 - 1 + halo), xb = min(max(xp + 1, -halo), W1 - 1 + halo);
+            const int x0 = reflect_idx(reflect_idx(xa, W1) - p.src_wrap, p.src_W);
+            const int x1 = reflect_idx(reflect_idx(xb, W1) - p.src_wrap, p.src_W);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < p.src_c) v[k][c] = make_float2(__ldg(row + c * plane + x0), __ldg(row + c * plane + x1));
           }
         }
       };
@@ -381,30 +393,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int it = 0;
       if (cluster_id < p.total_groups) issue_loads(cluster_id);
       for (int q = cluster_id; q < p.total_groups; q += num_clusters, ++it) {
-        uint16_t* win = reinterpret_cast<uint16_t*>(ds_scratch + (it & 1) * DS_SCRATCH_BYTES);
-        // ---- this tile's source window: registers -> shared (16 bit)
+        const uint32_t wsrc = smem_u32(ds_scratch + (it & 1) * DS_SCRATCH_BYTES);
+        // ---- this tile's source window: registers -> shared, two pixels x 4 channels (16 bit) per store
 #pragma unroll
-        for (int k = 0; k < DS_EPT; ++k) {
-          if (el[k] >= 0) {
-            uint16_t hv;
-            if (p.bf16) { const __nv_bfloat16 t = __float2bfloat16_rn(v[k]); hv = *reinterpret_cast<const uint16_t*>(&t); }
-            else { const __half t = __float2half_rn(v[k]); hv = *reinterpret_cast<const uint16_t*>(&t); }
-            win[((el[k] & 15) * DS_WIN_W + ((el[k] >> 4) & 31)) * 4 + (el[k] >> 9)] = hv;
+        for (int k = 0; k < IPT; ++k) {
+          const int item = pt + k * 128;
+          if (item >= N_ITEMS) continue;
+          uint32_t w0, w1, w2, w3;
+          if (p.bf16) {
+            w0 = pack2<__nv_bfloat16>(v[k][0].x, v[k][1].x); w1 = pack2<__nv_bfloat16>(v[k][2].x, v[k][3].x);
+            w2 = pack2<__nv_bfloat16>(v[k][0].y, v[k][1].y); w3 = pack2<__nv_bfloat16>(v[k][2].y, v[k][3].y);
+          } else {
+            w0 = pack2<__half>(v[k][0].x, v[k][1].x); w1 = pack2<__half>(v[k][2].x, v[k][3].x);
+            w2 = pack2<__half>(v[k][0].y, v[k][1].y); w3 = pack2<__half>(v[k][2].y, v[k][3].y);
           }
+          sts128(wsrc + item * 16, w0, w1, w2, w3);                      // item = row * 12 + pair -> (row * 24 + 2 * pair) * 8
         }
         asm volatile("bar.sync 6, 128;" ::: "memory");
         if (q + num_clusters < p.total_groups) issue_loads(q + num_clusters);      // next tile's loads fly during the build
-        // ---- patch rows: pixel (r, x) -> 32 elements (kw*4 + c) = source columns x .. x + 7 (kw = 7 meets zero weights)
+        // ---- patch rows: pixel (r, x) -> 32 elements (kw*4 + c) = window columns x + 1 .. x + 8 (kw = 7 meets zero weights)
         if (pt < 32) mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         asm volatile("bar.sync 6, 128;" ::: "memory");
         const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
-        const uint32_t wsrc = smem_u32(win);
 #pragma unroll
         for (int k = 0; k < (RT_PATCH_ROWS * 4) / 128; ++k) {
           const int id = pt + k * 128;
           const int pix = id >> 2, qc = id & 3;
           const int r = pix >> 4, x = pix & 15;
-          const uint32_t a0 = wsrc + ((r * DS_WIN_W + x + 2 * qc) << 3);
+          const uint32_t a0 = wsrc + ((r * DS_WIN_W + x + 2 * qc + 1) << 3);
           const long long lo = lds64(a0), hi = lds64(a0 + 8);
           sts128(sa + pix * 64 + ((qc ^ ((pix >> 1) & 3)) << 4), (uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi,
                  (uint32_t)(hi >> 32));

@@ -44,12 +44,18 @@ struct WgParams {
 // traffic and is fetched once per GROUP instead of once per tap: PatchGAN input layer 16 taps x 16 channels and the
 // generator stem 7 x 64 in one group; 64-channel layers in groups of 3-4, 128-channel layers in pairs.  Two accumulator
 // sets (the epilogue of one unit overlaps the MMAs of the next) whenever 2*NT*BN columns fit.
-template <int BN, int NT>
+// RP ("row patch", the row-merged generator stem: NT taps that are pure row shifts of an 8 x 8 pixel patch over 64 stored
+// channels): the X operand of a stage is ONE haloed patch of (8 + NT - 1) rows x 8 pixels and tap t's operand is the
+// 64-pixel window that starts t rows (t x 1024 bytes = whole swizzle atoms) into it -- 14 KB per stage instead of
+// NT x 8 KB, which is what bounded this layer (L2 -> shared-memory traffic).
+constexpr int RP_BW = 8, RP_BH = 8;
+
+template <int BN, int NT, bool RP = false>
 struct WgCfg {
   static constexpr int A_BYTES = 2 * WG_SLAB;
   // X operand of one tap: BN/64 slabs of [64 px][128 B] (128-byte swizzle), or for BN == 16 one slab of [64 px][32 B]
   static constexpr int B_TAP_BYTES = BN >= 64 ? (BN / 64) * WG_SLAB : WG_PIXELS * 32;
-  static constexpr int B_BYTES = NT * B_TAP_BYTES;
+  static constexpr int B_BYTES = RP ? (RP_BH + NT - 1) * RP_BW * 128 : NT * B_TAP_BYTES;
   static constexpr int B_LOADS = BN >= 64 ? BN / 64 : 1;
   static constexpr int B_KSTEP = BN >= 64 ? 2048 : 512;            // bytes per 16 pixel rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -63,11 +69,12 @@ struct WgCfg {
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
-template <int BN, int NT>
+template <int BN, int NT, bool RP = false>
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ WgParams p) {
-  using Cfg = WgCfg<BN, NT>;
+  using Cfg = WgCfg<BN, NT, RP>;
+  static_assert(!RP || BN == 64, "row-patch variant: 64 stored input channels");
   constexpr int NACC = Cfg::NACC;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -121,7 +128,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
         int ph = 0;
         while (tap >= g.phase_tap0[ph + 1]) ++ph;
         const int oy0 = g.phase_oy[ph], ox0 = g.phase_ox[ph];
-        const uint32_t stage_tx = (uint32_t)(Cfg::A_BYTES + cnt * Cfg::B_TAP_BYTES);
+        const uint32_t stage_tx = RP ? (uint32_t)Cfg::STAGE_BYTES : (uint32_t)(Cfg::A_BYTES + cnt * Cfg::B_TAP_BYTES);
         const int per_img = p.patches_y * p.patches_x;
         for (int pt = pt0; pt < pt1; ++pt) {
           const int n = pt / per_img;
@@ -135,12 +142,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             tma_load_4d(&tmY, fb, sa + j * WG_SLAB, nt * 128 + 64 * j, g.OS * vj0 + ox0, g.OS * vi0 + oy0, n);
+          if constexpr (RP) {
+            // one haloed patch: rows vi0 + dy0 .. vi0 + dy0 + 8 + NT - 2 (tmX's box is that tall), 8 pixels wide
+            tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES, 0, vj0 + g.taps[tap].dx, vi0 + g.taps[tap].dy, n);
+          } else {
 #pragma unroll 1
-          for (int t = 0; t < cnt; ++t)
+            for (int t = 0; t < cnt; ++t)
 #pragma unroll
-            for (int j = 0; j < Cfg::B_LOADS; ++j)
-              tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES + j * WG_SLAB, 64 * j,
-                          g.S * vj0 + g.taps[tap + t].dx, g.S * vi0 + g.taps[tap + t].dy, n);
+              for (int j = 0; j < Cfg::B_LOADS; ++j)
+                tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES + j * WG_SLAB, 64 * j,
+                            g.S * vj0 + g.taps[tap + t].dx, g.S * vi0 + g.taps[tap + t].dy, n);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -167,7 +179,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           const uint64_t adesc = make_mnmajor_desc(sa, WG_SLAB, 1024);
 #pragma unroll 1
           for (int t = 0; t < cnt; ++t) {
-            const uint32_t sb = sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES;
+            // RP: tap t = the patch t rows (t * 8 pixels * 128 B = t swizzle atoms) further down
+            const uint32_t sb = sa + Cfg::A_BYTES + t * (RP ? RP_BW * 128 : Cfg::B_TAP_BYTES);
             const uint64_t bdesc = BN >= 64 ? make_mnmajor_desc(sb, WG_SLAB, 1024) : make_mnmajor_desc_sw32(sb, 256);
 #pragma unroll
             for (int k = 0; k < WG_PIXELS / 16; ++k)     // 16 pixel rows per K step
@@ -299,6 +312,14 @@ wgrad_reduce_sliced_kernel(const float4* __restrict__ part, int splits, long lon
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static bool row_patch_ok(const ConvGeom& g) {
+  static const bool on = [] { const char* e = getenv("NIRGAN_B200_WGRAD_ROWPATCH"); return !(e && e[0] == '0'); }();
+  if (!on || g.nphase != 1 || g.Cin != 64 || g.ntaps != 7 || g.S != 1 || g.OS != 1) return false;
+  for (int t = 0; t < g.ntaps; ++t)
+    if (g.taps[t].dx != g.taps[0].dx || g.taps[t].dy != g.taps[0].dy + t) return false;
+  return g.VW >= RP_BW && g.VH >= RP_BH;
+}
+
 struct WgPlan {
   int BH, BW, patches_y, patches_x, P, n_tiles, splits, pps, bn;
   int nt;       // taps per stage (compile-time group capacity)
@@ -337,6 +358,7 @@ static void wgrad_plan(const ng_conv_args& a, const ConvGeom& g, WgPlan& w) {
     const long long tiles = (long long)((g.VH + bh - 1) / bh) * ((g.VW + bw - 1) / bw);
     if (best < 0 || tiles < best) { best = tiles; w.BH = bh; w.BW = bw; }
   }
+  if (row_patch_ok(g)) { w.BH = RP_BH; w.BW = RP_BW; }
   w.patches_y = (g.VH + w.BH - 1) / w.BH;
   w.patches_x = (g.VW + w.BW - 1) / w.BW;
   w.P = g.B * w.patches_y * w.patches_x;
@@ -376,10 +398,10 @@ long long wgrad_tc_workspace_bytes(const ng_conv_args& a, const ConvGeom& g) {
   return (long long)w.splits * g.ntaps * g.Cout * g.Cin * (long long)sizeof(float);
 }
 
-template <int BN, int NT>
+template <int BN, int NT, bool RP = false>
 static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPlan& w, float* dw, void* workspace,
                            cudaStream_t st) {
-  using Cfg = WgCfg<BN, NT>;
+  using Cfg = WgCfg<BN, NT, RP>;
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.g = g;
@@ -409,6 +431,7 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
     cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.Wb, (cuuint64_t)g.Hb, (cuuint64_t)g.B};
     cuuint64_t strides[3] = {(cuuint64_t)g.Cin * 2, (cuuint64_t)g.Wb * g.Cin * 2, (cuuint64_t)g.Hb * g.Wb * g.Cin * 2};
     cuuint32_t box[4] = {(cuuint32_t)(BN >= 64 ? 64 : BN), (cuuint32_t)(w.BW * g.S), (cuuint32_t)(w.BH * g.S), 1};
+    if (RP) box[2] = (cuuint32_t)(RP_BH + NT - 1);          // the haloed patch: every row tap in one box
     cuuint32_t estr[4] = {1, (cuuint32_t)g.S, (cuuint32_t)g.S, 1};
     int cr = 0;
     const int er = cached_tensor_map(&tmX, dt, 4, a.x, dims, strides, box, estr,
@@ -419,14 +442,14 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
   static PerDeviceOnce once;      // per instantiation and per device; thread-safe
   const int dev = current_device();
   if (once.needed(dev)) {
-    int e = check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<BN, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    int e = check_cuda(cudaFuncSetAttribute(wgrad_tc_kernel<BN, NT, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             Cfg::SMEM_BYTES), "cudaFuncSetAttribute(wgrad_tc)");
     if (e) return e;
     once.done(dev);
   }
   const int sms = num_sms();
   const int grid = p.total_units < sms ? p.total_units : sms;
-  wgrad_tc_kernel<BN, NT><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmY, tmX, p);
+  wgrad_tc_kernel<BN, NT, RP><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tmY, tmX, p);
   NG_LAUNCH_CHECK("wgrad_tc_kernel");
   if (w.splits > 1) {
     const long long n4 = (long long)g.ntaps * g.Cout * g.Cin / 4;
@@ -459,6 +482,8 @@ int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspac
              NG_E_ALIGN, "wgrad_tc: tensors must be 16-byte aligned");
   *handled = true;
   if (w.nt == 16 && g.Cin == 16) return launch_wgrad_tc<16, 16>(a, g, w, dw, workspace, st);
+  if (w.nt == 7 && g.Cin == 64 && row_patch_ok(g) && w.BW == RP_BW && w.BH == RP_BH)
+    return launch_wgrad_tc<64, 7, true>(a, g, w, dw, workspace, st);
   if (w.nt == 7 && g.Cin == 64) return launch_wgrad_tc<64, 7>(a, g, w, dw, workspace, st);
   if (w.nt == 4 && g.Cin == 64) return launch_wgrad_tc<64, 4>(a, g, w, dw, workspace, st);
   if (w.nt == 3 && g.Cin == 64) return launch_wgrad_tc<64, 3>(a, g, w, dw, workspace, st);

@@ -333,3 +333,38 @@ def test_wgrad_tc_matches_autograd(kind, dt):
     dwp2 = torch.empty_like(dwp)
     L.call("ng_conv2d_wgrad", C.byref(a), dwp2.data_ptr(), None, ws.data_ptr(), need, Hh.stream())
     assert torch.equal(dwp, dwp2)
+
+
+@pytest.mark.parametrize("H,W,B", [(24, 40, 2), (69, 69, 3), (8, 16, 1)])
+def test_wgrad_tc_row_patch_stem(H, W, B):
+    """Weight gradient of the row-merged generator stem (7 x 1 taps over 64 stored channels, Cout 64): the tcgen05 kernel's
+    row-patch form (one haloed 14 x 8 pixel X patch per stage, every tap a window into it) against torch autograd of the
+    same 7 x 1 convolution, incl. partially covered patches at the right / bottom border."""
+    import ctypes as C
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    dtype, tdt = L.F16, torch.float16
+    x = _gen(B, 64, H, W, seed=41).to(tdt).float()
+    w = _gen(64, 64, 7, 1, seed=42, scale=0.05).requires_grad_(True)
+    xr = F.pad(x, (0, 0, 3, 3))                                   # rows only: the column taps are merged into channels
+    out = F.conv2d(xr, w)
+    dy = _gen(*out.shape, seed=43).to(tdt).float()
+    out.backward(dy)
+    xb_t = xr.permute(0, 2, 3, 1).contiguous().to(tdt).reshape(-1)   # [B][H+6][W][64]: halo rows materialised
+    dyb = Hh.to_actbuf(dy, 0, "zero", dtype)
+    a = L.ConvArgs()
+    a.dtype, a.impl, a.form, a.sgn = dtype, L.IMPL_TC, L.FORM_GATHER, 1
+    a.B, a.Hin, a.Win, a.Cin, a.in_pad, a.in_pad_w = B, H, W, 64, 3, 0
+    a.Cout, a.KH, a.KW, a.stride, a.pad, a.pad_w, a.Hout, a.Wout = 64, 7, 1, 1, 3, 0, H, W
+    a.x, a.w, a.y = xb_t.data_ptr(), xb_t.data_ptr(), dyb.t.data_ptr()
+    need = L.load().ng_conv2d_wgrad_workspace_bytes(C.byref(a))
+    assert need > 0
+    ws = torch.full((need // 4,), float("nan"), device="cuda")
+    dwp = torch.full((7 * 64 * 64,), float("nan"), device="cuda")
+    L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), None, ws.data_ptr(), need, Hh.stream())
+    dw = torch.empty_like(w)
+    L.call("ng_unpack_weight_grad", dwp.data_ptr(), 64, 64, 7, 1, 0, 64, 64, 1.0, None, 0.0, dw.data_ptr(), Hh.stream())
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(dw).all())
+    rel = float((dw - w.grad).norm() / w.grad.norm())
+    assert rel <= 1e-5, rel
