@@ -61,6 +61,11 @@ def _worker(rank, world, port, precision, impl, size, out_dir):
     grads["d"] = {k: (p.grad / world).cpu() for k, p in model.netD.named_parameters()}
     lg = tr._pass(batch, 1, model.netG, tr.opt_g, "g")
     grads["g"] = {k: (p.grad / world).cpu() for k, p in model.netG.named_parameters()}
+    # configs[4] mixes resolutions from step to step: two more steps at other tile sizes (each shape has its own plans,
+    # all of them carved from the shared buffer pool) through the public step()
+    for s2 in (96, size):
+        rgb2, nir2 = _batches(2 * world, s2)
+        tr.step({"rgb": rgb2[sl].cuda(), "nir": nir2[sl].cuda()})
     torch.cuda.synchronize()
     weights = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     torch.save({"grads": grads, "weights": weights, "loss": (float(ld), float(lg)),
@@ -97,7 +102,7 @@ def test_two_rank_nccl_step_equals_single_rank_on_concatenated_batch(precision, 
     for net in ("d", "g"):
         for k in ranks[0]["grads"][net]:
             assert torch.equal(ranks[0]["grads"][net][k], ranks[1]["grads"][net][k]), (net, k)
-    for k in ranks[0]["weights"]:
+    for k in ranks[0]["weights"]:       # after three steps at mixed resolutions (64, 96, 64 px)
         assert torch.equal(ranks[0]["weights"][k], ranks[1]["weights"][k]), k
     # ... and they are the single-rank gradients of the concatenated batch.  (D pass exactly so; in the G pass each rank's D
     # has already taken its -- identical -- optimizer step, as in the single-rank run.)

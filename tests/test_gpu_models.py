@@ -258,3 +258,36 @@ def test_forward_async_matches_forward_over_consecutive_calls():
         for d in done:
             main.wait_event(d)
         assert torch.equal(y, want[3])
+
+
+def test_config3_full_size_512px_tiles():
+    """BASELINE.json configs[2] at its full size: create_synthetic_dataset-style inference of 3x512x512 tiles behind the
+    pad-10 wrapper (532 / 266 / 133 pyramid, plain generator).  Tile-sharded over 3 emulated ranks == the sequential loop
+    bit for bit with ids in sorted order; a tile computed alone or in a batch of 6 has the same bits; two tiles against the
+    CPU oracle within the north-star tolerance (NIR max-abs 2e-2 / mean-abs 2e-3, derived NDVI mean-abs 5e-3)."""
+    import nirgan_oracle as O
+    from nirgan_b200 import synth
+    sd = O.random_state_dict(O.generator_param_shapes(), seed=33)
+    net = make_G(sd, "fp16", "tc")
+    names = [f"tile_{i:06d}.tif" for i in (4, 1, 5, 0, 3, 2)]
+    tiles = {n: torch.rand(3, 512, 512, generator=torch.Generator().manual_seed(500 + int(n[5:11]))) for n in names}
+    model = lambda hr: net(hr, wrap_pad=10)
+    dev = torch.device("cuda")
+    seq = synth.run_shard(model, tiles, 0, 1, batch_size=2, device=dev)
+    assert list(seq.keys()) == [f"tile_{i:06d}" for i in range(6)]
+    merged = {}
+    for r in range(3):
+        merged.update(synth.run_shard(model, tiles, r, 3, batch_size=2, device=dev))
+    big = synth.run_shard(model, tiles, 0, 1, batch_size=6, device=dev)
+    for k in seq:
+        assert seq[k].shape == (1, 512, 512) and torch.isfinite(seq[k]).all()
+        assert torch.equal(merged[k], seq[k]) and torch.equal(big[k], seq[k]), k
+    torch.set_num_threads(max(1, (__import__("os").cpu_count() or 1)))
+    for n in names[:2]:
+        k = synth.tile_id(n)
+        with torch.no_grad():
+            ref = O.px2px_forward(sd, tiles[n][None], 10, True)[0]
+        _check(seq[k], ref, 2e-2, 2e-3, f"config 3 {k}")
+        red = tiles[n][0:1]
+        d = (ndvi_display(seq[k].float().cpu(), red) - ndvi_display(ref, red)).abs().mean()
+        assert float(d) <= 5e-3, float(d)
