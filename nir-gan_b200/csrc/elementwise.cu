@@ -3,6 +3,8 @@
 // pixel losses and Adam.  All are vectorised (16-byte accesses on the 16-bit paths) and sized in
 // multiples of the SM count.
 #include "common.cuh"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace ng {
 
@@ -345,6 +347,126 @@ in_apply_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, cons
         }
       }
       store8<T>(obase + (size_t)pp * C, f);
+    }
+  }
+}
+
+// Lean form of the flat apply for the common case -- 16-bit storage, normalised unit, ReLU or no activation, optional
+// residual, no injection -- written for INSTRUCTION count: the generic kernel above executes ~70 warp instructions per
+// 16-byte item (ncu r2h: 45 % integer / address arithmetic, IPC 2.0, 51 % of DRAM peak) and is bound by issue slots and
+// SM clock (it loses 24 % under the power cap), not by HBM.  Here: (y - mean) * rstd is one FFMA with precomputed
+// (rstd, -mean * rstd); ReLU runs on the packed 16-bit result (max with 0 commutes with rounding: same bits); the
+// (row, column) of a pixel is advanced incrementally instead of by a 64-bit multiply-shift per pixel; offsets are 32-bit
+// element indices added to per-image base pointers.
+__device__ __forceinline__ uint32_t relu_packed(uint32_t w, bool bf16) {
+  if (bf16) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&w);
+    v = __hmax2(v, __floats2bfloat162_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __half2 v = *reinterpret_cast<__half2*>(&w);
+  v = __hmax2(v, __floats2half2_rn(0.f, 0.f));
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <typename T, int UNROLL, bool HAS_RES, bool RELU>
+__global__ void __launch_bounds__(256, 3)
+in_apply_fast_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, const float* __restrict__ mr,
+                     const long long* __restrict__ acc, float* __restrict__ mr_out, const T* __restrict__ res,
+                     int res_pad, T* __restrict__ out, int op, int reflect, int ppb) {
+  static_assert(sizeof(T) == 2, "16-bit storage only");
+  constexpr bool BF = std::is_same<T, __nv_bfloat16>::value;
+  const int Ho = H + 2 * op, Wo = W + 2 * op, C8 = C >> 3;
+  const int n = blockIdx.y;
+  const int npix = Ho * Wo;
+  const int c8 = threadIdx.x & (C8 - 1);
+  const int pstep = 256 >> c8_shift;                 // pixels covered by the block per load
+  const int p_begin = blockIdx.x * ppb, p_end = min(npix, p_begin + ppb);
+  float sa[8], sb[8];                                // xh = y * sa + sb
+  if (mr) {
+    const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 m = m4[k];
+      sa[2 * k] = m.y; sb[2 * k] = -m.x * m.y; sa[2 * k + 1] = m.w; sb[2 * k + 1] = -m.z * m.w;
+    }
+  } else {
+    const longlong2* a2 = reinterpret_cast<const longlong2*>(acc + ((size_t)n * C + c8 * 8) * 2);
+    const double inv_n = 1.0 / ((double)H * (double)W);
+    const double ks = inv_n / (double)(1 << NG_STAT_SUM_SHIFT), kq = inv_n / (double)(1 << NG_STAT_SQ_SHIFT);
+    float mean[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const longlong2 v = a2[k];
+      const double m = (double)v.x * ks;
+      const double var = fmax((double)v.y * kq - m * m, 0.0);
+      mean[k] = (float)m;
+      sa[k] = rsqrtf((float)var + 1e-5f);
+      sb[k] = -mean[k] * sa[k];
+    }
+    if (mr_out != nullptr && blockIdx.x == 0 && (threadIdx.x >> c8_shift) == 0) {
+      float4* o4 = reinterpret_cast<float4*>(mr_out + ((size_t)n * C + c8 * 8) * 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o4[k] = make_float4(mean[2 * k], sa[2 * k], mean[2 * k + 1], sa[2 * k + 1]);
+    }
+  }
+  const int Wr = W + 2 * res_pad;
+  const T* ybase = y + (size_t)n * H * W * C + c8 * 8;
+  const T* rbase = HAS_RES ? res + ((size_t)n * (H + 2 * res_pad) * Wr + (size_t)res_pad * Wr + res_pad) * C + c8 * 8 : nullptr;
+  T* obase = out + (size_t)n * npix * C + c8 * 8;
+  // this thread's first pixel -> (row, column) once; afterwards advanced by pstep per unrolled item
+  int pp = p_begin + (threadIdx.x >> c8_shift);
+  int yo = pp / Wo, xo = pp - yo * Wo;
+  const int adv_y = pstep / Wo, adv_x = pstep - adv_y * Wo;      // pstep pixels = adv_y rows + adv_x columns
+  while (pp < p_end) {
+    uint4 raw[UNROLL], rres[HAS_RES ? UNROLL : 1];
+    int ok[UNROLL];
+    int ooff[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      int ys = yo - op, xs = xo - op;
+      bool inside = pp < p_end;
+      if (reflect) {
+        ys = ys < 0 ? -ys : (ys >= H ? 2 * (H - 1) - ys : ys);
+        xs = xs < 0 ? -xs : (xs >= W ? 2 * (W - 1) - xs : xs);
+      } else {
+        inside = inside && (unsigned)ys < (unsigned)H && (unsigned)xs < (unsigned)W;
+      }
+      ok[u] = pp < p_end ? (inside ? 1 : 2) : 0;                 // 1 = compute, 2 = zero halo, 0 = past the block
+      ooff[u] = pp * C;
+      if (inside) {
+        raw[u] = ldg_stream16(ybase + (ys * W + xs) * C);
+        if constexpr (HAS_RES) rres[u] = ldg_stream16(rbase + (ys * Wr + xs) * C);
+      }
+      pp += pstep; yo += adv_y; xo += adv_x;
+      if (xo >= Wo) { xo -= Wo; ++yo; }
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (ok[u] == 0) continue;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[u] == 1) {
+        float f[8];
+        unpack8<T>(raw[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sa[k], sb[k]);
+        if constexpr (HAS_RES) {
+          float rv[8];
+          unpack8<T>(rres[u], rv);
+          if constexpr (RELU) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.f) + rv[k];
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += rv[k];
+          }
+        }
+        o.x = pack2<T>(f[0], f[1]); o.y = pack2<T>(f[2], f[3]); o.z = pack2<T>(f[4], f[5]); o.w = pack2<T>(f[6], f[7]);
+        if constexpr (RELU && !HAS_RES) {
+          o.x = relu_packed(o.x, BF); o.y = relu_packed(o.y, BF); o.z = relu_packed(o.z, BF); o.w = relu_packed(o.w, BF);
+        }
+      }
+      *reinterpret_cast<uint4*>(obase + ooff[u]) = o;
     }
   }
 }
@@ -871,6 +993,28 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   const int pstep = 256 / C8;                     // pixels per block per load
   const int ppb = pstep * 16;                     // 16 sixteen-byte items per thread = 4 batches of UNROLL 4
   dim3 grid((unsigned)((Ho * Wo + ppb - 1) / ppb), (unsigned)B);
+  // lean kernel for the common case (see in_apply_fast_kernel); NIRGAN_B200_APPLY_FAST=0 keeps the generic one
+  static const bool fast_on = [] { const char* e = getenv("NIRGAN_B200_APPLY_FAST"); return !(e && e[0] == '0'); }();
+  const bool has_inj0 = inject_mode != NG_INJECT_NONE;
+  if (fast_on && dtype != NG_F32 && !has_inj0 && (mean_rstd || stat_acc) && (act == NG_ACT_RELU || act == NG_ACT_NONE) &&
+      (long long)(H + 2 * (residual ? res_pad : 0)) * (W + 2 * (residual ? res_pad : 0)) * C < (1ll << 31) &&
+      (long long)Ho * Wo * C < (1ll << 31)) {              // 32-bit element offsets inside one image
+    const int reflect = halo_mode == NG_HALO_REFLECT ? 1 : 0;
+#define NG_FAST(TT, RES, RL)                                                                                         \
+    in_apply_fast_kernel<TT, 4, RES, RL><<<grid, 256, 0, (cudaStream_t)stream>>>(                                      \
+        (const TT*)y, H, W, C, c8_shift, mean_rstd, (const long long*)stat_acc, mean_rstd_out, (const TT*)residual,    \
+        res_pad, (TT*)out, out_pad, reflect, ppb)
+#define NG_FAST_T(TT)                                                                                                \
+    do {                                                                                                             \
+      if (residual) { if (act == NG_ACT_RELU) NG_FAST(TT, true, true); else NG_FAST(TT, true, false); }             \
+      else { if (act == NG_ACT_RELU) NG_FAST(TT, false, true); else NG_FAST(TT, false, false); }                    \
+    } while (0)
+    if (dtype == NG_F16) NG_FAST_T(__half); else NG_FAST_T(__nv_bfloat16);
+#undef NG_FAST_T
+#undef NG_FAST
+    NG_LAUNCH_CHECK("in_apply_fast_kernel");
+    return NG_OK;
+  }
 #define NG_APPLY_LAUNCH(RES, INJ)                                                                                  \
   DISPATCH_DTYPE(dtype, (in_apply_kernel<T, 4, RES, INJ><<<grid, 256, 0, (cudaStream_t)stream>>>(                  \
                             (const T*)y, H, W, C, c8_shift, mean_rstd, (const long long*)stat_acc, mean_rstd_out, act,    \
