@@ -338,6 +338,132 @@ in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const 
   }
 }
 
+// Lean form of the two norm-backward passes for the common case -- 16-bit storage, normalised unit, no injection, the
+// activation a compile-time constant -- written for instruction count (ncu r2h: the generic kernel executes ~85 warp
+// instructions per 16-byte load, a third of them address arithmetic, at IPC 1.6 and 34-36 % of the HBM peak): xh is one
+// FFMA per element, the mask a select, dy two FFMAs with per-channel constants, the (row, column) of a pixel is advanced
+// incrementally, offsets are 32-bit.  Same block -> pixel mapping, partial-sum slots and combine kernel as the generic
+// form, so either can serve either pass.
+template <typename T, int PASS, int UNROLL, bool HAS_G, bool HAS_SKIP, int ACT>
+__global__ void __launch_bounds__(256, 2)
+in_bwd_fast_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const T* __restrict__ gskip,
+                   const T* __restrict__ yv, const float* __restrict__ mr, float* __restrict__ sums, T* __restrict__ dy,
+                   T* __restrict__ do_out) {
+  static_assert(sizeof(T) == 2, "16-bit storage only");
+  extern __shared__ float sm[];            // PASS 1: [4 accumulators][256 threads]
+  const int n = blockIdx.y, C8 = a.C >> 3, C = a.C;
+  const int c8 = threadIdx.x & (C8 - 1);
+  const int pstep = 256 >> a.c8_shift;
+  const int npix = a.H * a.W;
+  const int p_begin = blockIdx.x * a.ppb, p_end = min(npix, p_begin + a.ppb);
+  float sa[8], sb[8], k1[8], k2[8];        // xh = y * sa + sb ; dy = dxh * sa + xh * k2 + k1
+  {
+    const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 m = m4[k];
+      sa[2 * k] = m.y; sb[2 * k] = -m.x * m.y; sa[2 * k + 1] = m.w; sb[2 * k + 1] = -m.z * m.w;
+    }
+    if (PASS == 2) {
+      const float4* s4 = reinterpret_cast<const float4*>(sums + ((size_t)n * C + c8 * 8) * 2);   // combined sums
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 sv = s4[k];
+        k1[2 * k] = -sa[2 * k] * (sv.x * a.inv_hw); k2[2 * k] = -sa[2 * k] * (sv.y * a.inv_hw);
+        k1[2 * k + 1] = -sa[2 * k + 1] * (sv.z * a.inv_hw); k2[2 * k + 1] = -sa[2 * k + 1] * (sv.w * a.inv_hw);
+      }
+    }
+  }
+  const int gp = a.gp, Wb = a.W + 2 * gp;
+  const T* gn = HAS_G ? g + (size_t)n * (a.H + 2 * gp) * Wb * C + c8 * 8 : nullptr;
+  const T* sn = HAS_SKIP ? gskip + (size_t)n * npix * C + c8 * 8 : nullptr;
+  const T* yn = yv + (size_t)n * npix * C + c8 * 8;
+  T* dyn = PASS == 2 ? dy + (size_t)n * npix * C + c8 * 8 : nullptr;
+  T* don = (PASS == 2 && do_out) ? do_out + (size_t)n * npix * C + c8 * 8 : nullptr;
+  const bool fold = HAS_G && a.halo_mode == NG_HALO_REFLECT && gp > 0;
+  float acc1[8], acc2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc1[k] = acc2[k] = 0.f;
+  int pp = p_begin + (threadIdx.x >> a.c8_shift);
+  int py = pp / a.W, px = pp - py * a.W;
+  const int adv_y = pstep / a.W, adv_x = pstep - adv_y * a.W;
+  while (pp < p_end) {
+    Raw8<T> rg[HAS_G ? UNROLL : 1], rs[HAS_SKIP ? UNROLL : 1], ry[UNROLL];
+    int ypos[UNROLL], xpos[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      ypos[u] = py; xpos[u] = pp < p_end ? px : -1;
+      if (pp < p_end) {
+        ry[u] = ld_raw8<T>(yn + pp * C);
+        if constexpr (HAS_G) rg[u] = ld_raw8<T>(gn + ((py + gp) * Wb + px + gp) * C);
+        if constexpr (HAS_SKIP) rs[u] = ld_raw8<T>(sn + pp * C);
+      }
+      pp += pstep; py += adv_y; px += adv_x;
+      if (px >= a.W) { px -= a.W; ++py; }
+    }
+    int pq = pp - UNROLL * pstep;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u, pq += pstep) {
+      if (xpos[u] < 0) continue;
+      float d_o[8], xh[8];
+      if constexpr (HAS_G) raw_to_f<T>(rg[u], d_o);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d_o[k] = 0.f;
+      }
+      // mirrored halo rows / columns fold back onto interior pixels within gp of the border only
+      if (fold && ((unsigned)(ypos[u] - 1) >= (unsigned)(a.H - 2) || (unsigned)(xpos[u] - 1) >= (unsigned)(a.W - 2) ||
+                   ypos[u] <= gp || xpos[u] <= gp || ypos[u] >= a.H - 1 - gp || xpos[u] >= a.W - 1 - gp))
+        fold_halo_extras<T>(a, gn, ypos[u], xpos[u], d_o);
+      if constexpr (HAS_SKIP) {
+        float t[8];
+        raw_to_f<T>(rs[u], t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d_o[k] += t[k];
+      }
+      raw_to_f<T>(ry[u], xh);
+      float dxh[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        xh[k] = fmaf(xh[k], sa[k], sb[k]);
+        if (ACT == NG_ACT_RELU) dxh[k] = xh[k] > 0.f ? d_o[k] : 0.f;
+        else if (ACT == NG_ACT_LRELU) dxh[k] = xh[k] > 0.f ? d_o[k] : d_o[k] * a.slope;
+        else dxh[k] = d_o[k];
+      }
+      if constexpr (PASS == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc1[k] += dxh[k]; acc2[k] = fmaf(dxh[k], xh[k], acc2[k]); }
+      } else {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(dxh[k], sa[k], fmaf(xh[k], k2[k], k1[k]));
+        st8<T>(dyn + pq * C, o);
+        if (don) st8<T>(don + pq * C, d_o);
+      }
+    }
+  }
+  if constexpr (PASS == 1) {
+    // identical block reduction and slot layout as the generic kernel
+    float* dst = sums + (size_t)a.B * C * 2 + ((size_t)n * a.nblk1 + blockIdx.x) * C * 2;
+    const int lanes = 256 >> a.c8_shift;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      sm[0 * 256 + threadIdx.x] = acc1[2 * r];
+      sm[1 * 256 + threadIdx.x] = acc2[2 * r];
+      sm[2 * 256 + threadIdx.x] = acc1[2 * r + 1];
+      sm[3 * 256 + threadIdx.x] = acc2[2 * r + 1];
+      __syncthreads();
+      if ((int)threadIdx.x < (C >> 1)) {
+        const int cg = threadIdx.x >> 2, j = threadIdx.x & 3;
+        float t = 0.f;
+        for (int L2 = 0; L2 < lanes; ++L2) t += sm[j * 256 + (L2 << a.c8_shift) + cg];
+        dst[cg * 16 + 4 * r + j] = t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // combined[n][o] = sum over the image's pass-1 blocks of partial[n][blk][o], in block order (deterministic, no atomics)
 __global__ void __launch_bounds__(256)
 in_bwd_combine_kernel(const float* __restrict__ partial, int total, int per_image, int nblk, float* __restrict__ out) {
@@ -528,6 +654,27 @@ static void launch_in_bwd(const BwdArgs& a, dim3 grid, size_t smem, cudaStream_t
                           const void* y, const float* mr, const float* inj, const float* inj_scale, float* sums,
                           float* dscale, float* de_map, void* dy, void* do_out) {
   const bool hg = g != nullptr, hs = gskip != nullptr, hi = a.inj_mode != NG_INJECT_NONE;
+  // lean kernels for the common case (16-bit, normalised, no injection); NIRGAN_B200_BWD_FAST=0 keeps the generic ones
+  static const bool fast_on = [] { const char* e = getenv("NIRGAN_B200_BWD_FAST"); return !(e && e[0] == '0'); }();
+  if constexpr (sizeof(T) == 2 && (PASS == 1 || PASS == 2)) {
+    const long long big = (long long)(a.H + 2 * a.gp) * (a.W + 2 * a.gp) * a.C;
+    if (fast_on && !hi && mr != nullptr && dscale == nullptr && de_map == nullptr && big < (1ll << 31) && (256 >> a.c8_shift) < a.W &&
+        (a.act == NG_ACT_RELU || a.act == NG_ACT_NONE || a.act == NG_ACT_LRELU)) {
+#define NG_BWDF(G, S, ACT)                                                                                          \
+      in_bwd_fast_kernel<T, PASS, 4, G, S, ACT><<<grid, 256, smem, st>>>(a, (const T*)g, (const T*)gskip, (const T*)y, \
+                                                                        mr, sums, (T*)dy, (T*)do_out)
+#define NG_BWDF_ACT(ACT)                                                                                            \
+      do {                                                                                                           \
+        if (hg && hs) NG_BWDF(true, true, ACT); else if (hg) NG_BWDF(true, false, ACT); else NG_BWDF(false, true, ACT); \
+      } while (0)
+      if (a.act == NG_ACT_RELU) NG_BWDF_ACT(NG_ACT_RELU);
+      else if (a.act == NG_ACT_LRELU) NG_BWDF_ACT(NG_ACT_LRELU);
+      else NG_BWDF_ACT(NG_ACT_NONE);
+#undef NG_BWDF_ACT
+#undef NG_BWDF
+      return;
+    }
+  }
   // four pixels of loads in flight per thread at 2 blocks / SM (<= 128 registers) beat two at 3 blocks / SM: the kernel is
   // bound by the bytes in flight, not by occupancy (4.5 -> 4.15 ms per training step); NIRGAN_B200_BWD_UNROLL4=0 restores
   static const bool deep = [] { const char* e = getenv("NIRGAN_B200_BWD_UNROLL4"); return !(e && e[0] == '0'); }();
