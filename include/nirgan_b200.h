@@ -24,7 +24,8 @@
  *                      nn.InstanceNorm2d + ReLU/LeakyReLU + residual add + ReflectionPad2d
  *                      model/networks.py:29-30,341-344,350-351,405-434,567-576; the SatCLIP
  *                      injection x*(1+s*e) model/generator_inject.py:113-127
- *   ng_prep_input      F.pad(..., mode='reflect') model/pix2pix.py:91-93, ReflectionPad2d(3)
+ *   ng_prep_input / ng_prep_input_s2d
+ *                      F.pad(..., mode='reflect') model/pix2pix.py:91-93, ReflectionPad2d(3)
  *                      model/networks.py:341, torch.cat((rgb, pred),1) model/pix2pix.py:197,202,216
  *   ng_linear          self.fc(embeds) model/generator_inject.py:110
  *   ng_lsgan_loss      GANLoss('lsgan') model/networks.py:232-233,268-270
@@ -209,6 +210,18 @@ int ng_prep_input(const float* src_a, int32_t ca, const float* src_b, int32_t cb
                   int32_t wrap_pad, int32_t halo, int32_t halo_mode, int32_t c_pad, int32_t dtype, void* dst,
                   void* stream);
 
+/* Space-to-depth form of the PatchGAN input layer Conv2d(4 -> 64, k4, s2, p1) (model/networks.py:559): the zero-padded
+ * (pad 1) channel concatenation of src_a / src_b is written as [B][(H+2)/2][(W+2)/2][(py*2+px)*16 + c] `dtype` (H, W even,
+ * ca + cb <= 16, 16-bit), on which the layer is a 2x2 STRIDE-1 convolution over 64 stored channels -- kernel position
+ * (kh, kw) = (2*dy + py, 2*dx + px), a bijection -- i.e. an ordinary ng_conv2d / ng_conv2d_wgrad with KH = KW = 2, pad 0.
+ * ng_pack_weight_s2d packs the fp32 [O][I][4][4] master as [tap = dy*2+dx][O][64] (transpose 0) or [tap][64][O]
+ * (transpose 1: the data gradient's operand); ng_unpack_weight_grad_s2d is the inverse for the weight gradient. */
+int ng_prep_input_s2d(const float* src_a, int32_t ca, const float* src_b, int32_t cb, int32_t B, int32_t H, int32_t W,
+                      int32_t dtype, void* dst, void* stream);
+int ng_pack_weight_s2d(const float* src, int32_t O, int32_t I, int32_t transpose, int32_t dtype, void* dst, void* stream);
+int ng_unpack_weight_grad_s2d(const float* packed, int32_t O, int32_t I, float scale, const float* dev_scale, float beta,
+                              float* dst, void* stream);
+
 /* per-(n,c) mean / rstd (eps 1e-5, biased variance) of a compact NHWC tensor */
 int ng_in_stats(const void* y, int32_t dtype, int32_t B, int32_t HW, int32_t C, float* mean_rstd, void* stream);
 /* same from the conv epilogue partial sums */
@@ -252,9 +265,10 @@ int ng_grad_scale_pow2(const float* g, int64_t n, float target, float* out4, voi
 int ng_head_bwd_prep(const float* dout, const float* out, int32_t B, int32_t H, int32_t W, int32_t crop, int32_t act,
                      float scale, const float* dev_scale, int32_t c_pad, int32_t dtype, void* dst, void* stream);
 /* gradient export: channels [c0, c0 + c) of NHWC [B][H][W][c_pad] (dtype) -> NCHW fp32 [B][c][H][W], times
- * scale * dev_scale[0]  (the G pass needs dL/d(pred) only: channel 3 of the PatchGAN's (rgb, pred) input) */
+ * scale * dev_scale[0]  (the G pass needs dL/d(pred) only: channel 3 of the PatchGAN's (rgb, pred) input).
+ * s2d != 0: the source is in the space-to-depth layout of ng_prep_input_s2d (c_pad = channel slots per parity). */
 int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c0, int32_t c,
-                    float scale, const float* dev_scale, float* dst, void* stream);
+                    int32_t s2d, float scale, const float* dev_scale, float* dst, void* stream);
 /* SatCLIP injection backward: adjoint of the bilinear resize (128x128 -> HxW) then of fc:
  * dfc_w[16384][256] = (scale * A^T de_map)^T embeds, dfc_b[16384].  de128_scratch: [B][16384] floats. */
 int ng_inject_bwd(const float* de_map, int32_t B, int32_t H, int32_t W, float scale, const float* dev_scale,

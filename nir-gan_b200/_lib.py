@@ -66,7 +66,10 @@ _SIGNATURES = {
                           c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ng_grad_scale_pow2": (c_i32, [c_vp, c_i64, c_f32, c_vp, c_vp]),
     "ng_head_bwd_prep": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_i32, c_vp, c_vp]),
-    "ng_grad_to_nchw": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ng_grad_to_nchw": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    "ng_prep_input_s2d": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ng_pack_weight_s2d": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "ng_unpack_weight_grad_s2d": (c_i32, [c_vp, c_i32, c_i32, c_f32, c_vp, c_f32, c_vp, c_vp]),
     "ng_inject_bwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ng_resize_plane": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "ng_hist_match_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32]),

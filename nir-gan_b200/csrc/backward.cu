@@ -556,7 +556,7 @@ tap_scatter_kernel(const float* __restrict__ dout, const float* __restrict__ out
 // NHWC (cpad channels, T, scaled) -> NCHW fp32 (c channels), dst = src * scale
 template <typename T>
 __global__ void __launch_bounds__(256)
-grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, int c0, int c, float scale,
+grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, int c0, int c, int s2d, float scale,
                     const float* __restrict__ dev_scale, float* __restrict__ dst) {
   const long long total = (long long)B * c * H * W;
   if (dev_scale) scale *= dev_scale[0];
@@ -564,7 +564,14 @@ grad_to_nchw_kernel(const T* __restrict__ src, int B, int H, int W, int cpad, in
        i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % W), y = (int)((i / W) % H);
     const int ch = (int)((i / ((long long)W * H)) % c), n = (int)(i / ((long long)W * H * c));
-    dst[i] = to_f32<T>(src[(((size_t)n * H + y) * W + x) * cpad + c0 + ch]) * scale;
+    if (s2d) {
+      // source in the space-to-depth layout of the zero-padded image (ng_prep_input_s2d): [(H+2)/2][(W+2)/2][parity*cpad + ch]
+      const int yp = y + 1, xp = x + 1, Ws = (W + 2) >> 1, Hs = (H + 2) >> 1;
+      const size_t pix = ((size_t)n * Hs + (yp >> 1)) * Ws + (xp >> 1);
+      dst[i] = to_f32<T>(src[pix * (4 * cpad) + ((yp & 1) * 2 + (xp & 1)) * cpad + c0 + ch]) * scale;
+    } else {
+      dst[i] = to_f32<T>(src[(((size_t)n * H + y) * W + x) * cpad + c0 + ch]) * scale;
+    }
   }
 }
 
@@ -857,11 +864,11 @@ extern "C" int ng_tap_scatter(const float* dout, const float* out, int32_t B, in
 }
 
 extern "C" int ng_grad_to_nchw(const void* src, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t c_pad, int32_t c0,
-                               int32_t c, float scale, const float* dev_scale, float* dst, void* stream) {
+                               int32_t c, int32_t s2d, float scale, const float* dev_scale, float* dst, void* stream) {
   int r = require_sm100(); if (r) return r;
   NG_REQUIRE(src && dst && c0 >= 0 && c > 0 && c0 + c <= c_pad, NG_E_ARG, "grad_to_nchw: bad arguments");
   DISPATCH_T(dtype, (grad_to_nchw_kernel<T><<<grid_cap((long long)B * c * H * W), 256, 0, (cudaStream_t)stream>>>(
-                        (const T*)src, B, H, W, c_pad, c0, c, scale, dev_scale, dst)));
+                        (const T*)src, B, H, W, c_pad, c0, c, s2d, scale, dev_scale, dst)));
   NG_LAUNCH_CHECK("grad_to_nchw_kernel");
   return NG_OK;
 }

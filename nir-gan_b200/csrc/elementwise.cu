@@ -113,6 +113,74 @@ __global__ void prep_input_kernel(const float* __restrict__ sa, int ca, const fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// space-to-depth form of the PatchGAN input layer (Conv2d(4 -> 64, k4, s2, p1), model/networks.py:559):
+// the zero-padded (pad 1) image is stored as [B][(H+2)/2][(W+2)/2][(py*2+px)*cs + c] (cs = 16 channel slots per parity),
+// on which the 4x4 stride-2 convolution is a 2x2 STRIDE-1 convolution over 64 channels with kernel position
+// (kh, kw) = (2*dy + py, 2*dx + px): a bijection, no padded taps.  The thin 16-channel strided form moved 32-byte TMA
+// elements through a 16-stage-per-tile pipeline (0.37 ms per 64 images of 256x256 for a 45 us HBM floor); this one is an
+// ordinary 64-channel convolution for forward, weight gradient and data gradient alike.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+prep_input_s2d_kernel(const float* __restrict__ sa, int ca, const float* __restrict__ sb, int cb, int B, int H, int W,
+                      T* __restrict__ dst) {
+  // one thread = one (output pixel, parity) = 16 channel slots = 32 bytes (two 16-byte stores)
+  const int Hs = (H + 2) >> 1, Ws = (W + 2) >> 1;
+  const long long total = (long long)B * Hs * Ws * 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int par = (int)(i & 3);
+    long long r = i >> 2;
+    const int xs = (int)(r % Ws); r /= Ws;
+    const int ys = (int)(r % Hs);
+    const int n = (int)(r / Hs);
+    const int y0 = 2 * ys + (par >> 1) - 1, x0 = 2 * xs + (par & 1) - 1;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = 0.f;
+    if (y0 >= 0 && y0 < H && x0 >= 0 && x0 < W) {
+      for (int c = 0; c < ca; ++c) v[c] = sa[(((long long)n * ca + c) * H + y0) * W + x0];
+      for (int c = 0; c < cb; ++c) v[ca + c] = sb[(((long long)n * cb + c) * H + y0) * W + x0];
+    }
+    uint4 u0, u1;
+    u0.x = pack2<T>(v[0], v[1]); u0.y = pack2<T>(v[2], v[3]); u0.z = pack2<T>(v[4], v[5]); u0.w = pack2<T>(v[6], v[7]);
+    u1.x = pack2<T>(v[8], v[9]); u1.y = pack2<T>(v[10], v[11]); u1.z = pack2<T>(v[12], v[13]); u1.w = pack2<T>(v[14], v[15]);
+    uint4* o = reinterpret_cast<uint4*>(dst + i * 16);
+    o[0] = u0; o[1] = u1;
+  }
+}
+
+// weights of the space-to-depth form.  src fp32 [O][I][4][4]; tap = dy*2 + dx, element (py*2+px)*16 + c <-> w[o][c][2dy+py][2dx+px].
+// transpose == 0: dst [tap][O][64] (forward);  transpose == 1: dst [tap][64][O] (data gradient: n = input slot, k = O)
+template <typename T>
+__global__ void pack_weight_s2d_kernel(const float* __restrict__ src, int O, int I, int transpose, T* __restrict__ dst) {
+  const int total = 4 * O * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int e, o, tap;
+    if (!transpose) { e = i & 63; o = (i >> 6) % O; tap = (i >> 6) / O; }
+    else { o = i % O; e = (i / O) & 63; tap = (i / O) >> 6; }
+    const int par = e >> 4, c = e & 15;
+    const int kh = 2 * (tap >> 1) + (par >> 1), kw = 2 * (tap & 1) + (par & 1);
+    float v = 0.f;
+    if (c < I) v = src[(((long long)o * I + c) * 4 + kh) * 4 + kw];
+    dst[i] = from_f32<T>(v);
+  }
+}
+
+// inverse for gradients: packed fp32 [tap][O][64] -> dst fp32 [O][I][4][4] (dst = beta * dst + scale * dev_scale[0] * packed)
+__global__ void unpack_wgrad_s2d_kernel(const float* __restrict__ packed, int O, int I, float scale,
+                                        const float* __restrict__ dev_scale, float beta, float* __restrict__ dst) {
+  const int total = O * I * 16;
+  if (dev_scale) scale *= dev_scale[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kw = i & 3, kh = (i >> 2) & 3, c = (i >> 4) % I, o = (i >> 4) / I;
+    const int tap = (kh >> 1) * 2 + (kw >> 1), par = (kh & 1) * 2 + (kw & 1);
+    const float v = scale * packed[((long long)tap * O + o) * 64 + par * 16 + c];
+    dst[i] = beta != 0.f ? fmaf(beta, dst[i], v) : v;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 in_stats_kernel(const T* __restrict__ y, int HW, int C, float* __restrict__ mr) {
@@ -935,6 +1003,44 @@ extern "C" int ng_prep_input(const float* src_a, int32_t ca, const float* src_b,
   DISPATCH_DTYPE(dtype, (prep_input_kernel<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
                             src_a, ca, src_b, cb, B, H, W, wrap_pad, halo, halo_mode, c_pad, (T*)dst)));
   NG_LAUNCH_CHECK("prep_input_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_prep_input_s2d(const float* src_a, int32_t ca, const float* src_b, int32_t cb, int32_t B, int32_t H,
+                                 int32_t W, int32_t dtype, void* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src_a && dst && ca > 0 && cb >= 0 && (cb == 0 || src_b) && ca + cb <= 16, NG_E_ARG,
+             "prep_input_s2d: bad arguments (at most 16 channels)");
+  NG_REQUIRE(H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && dtype != NG_F32, NG_E_SHAPE,
+             "prep_input_s2d: even H, W and 16-bit storage");
+  const long long total = (long long)B * ((H + 2) / 2) * ((W + 2) / 2) * 4;
+  if (dtype == NG_F16)
+    prep_input_s2d_kernel<__half><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src_a, ca, src_b, cb, B, H, W, (__half*)dst);
+  else
+    prep_input_s2d_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src_a, ca, src_b, cb, B, H, W,
+                                                                                               (__nv_bfloat16*)dst);
+  NG_LAUNCH_CHECK("prep_input_s2d_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_pack_weight_s2d(const float* src, int32_t O, int32_t I, int32_t transpose, int32_t dtype, void* dst,
+                                  void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(src && dst && O > 0 && I > 0 && I <= 16 && (transpose == 0 || transpose == 1), NG_E_ARG,
+             "pack_weight_s2d: bad arguments");
+  DISPATCH_DTYPE(dtype, (pack_weight_s2d_kernel<T><<<grid_for(4ll * O * 64, 256), 256, 0, (cudaStream_t)stream>>>(
+                            src, O, I, transpose, (T*)dst)));
+  NG_LAUNCH_CHECK("pack_weight_s2d_kernel");
+  return NG_OK;
+}
+
+extern "C" int ng_unpack_weight_grad_s2d(const float* packed, int32_t O, int32_t I, float scale, const float* dev_scale,
+                                         float beta, float* dst, void* stream) {
+  int r = require_sm100(); if (r) return r;
+  NG_REQUIRE(packed && dst && O > 0 && I > 0 && I <= 16, NG_E_ARG, "unpack_weight_grad_s2d: bad arguments");
+  unpack_wgrad_s2d_kernel<<<grid_for((long long)O * I * 16, 256), 256, 0, (cudaStream_t)stream>>>(packed, O, I, scale,
+                                                                                                   dev_scale, beta, dst);
+  NG_LAUNCH_CHECK("unpack_wgrad_s2d_kernel");
   return NG_OK;
 }
 

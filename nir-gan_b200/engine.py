@@ -566,6 +566,12 @@ class Engine:
             cs = 8 if n_axis == "rowmerged" else 4
             dst = hit[1] if hit is not None else torch.empty(kh * d0 * 8 * cs, dtype=self.dt_torch, device=self.device)
             L.call("ng_pack_weight_rowmerged", src.data_ptr(), d0, d1, kh, kw, cs, self.dt_enum, dst.data_ptr(), stream)
+        elif n_axis in ("s2d", "s2d_T"):
+            # PatchGAN input layer in space-to-depth form: (O, I, 4, 4) -> [tap (4)][O][64] / transposed [tap][64][O]
+            assert kh == 4 and kw == 4 and d1 <= 16
+            dst = hit[1] if hit is not None else torch.empty(4 * d0 * 64, dtype=self.dt_torch, device=self.device)
+            L.call("ng_pack_weight_s2d", src.data_ptr(), d0, d1, 1 if n_axis == "s2d_T" else 0, self.dt_enum,
+                   dst.data_ptr(), stream)
         elif n_axis == "phasemerged":
             # ConvTranspose2d (Cin, Cout, 3, 3) -> [shift (4)][phase*Cout + co][Cin]  (NG_FORM_PHASED_MERGED)
             assert kh == 3 and kw == 3 and n_pad == d1 and k_pad == d0

@@ -103,6 +103,8 @@ class UnitGraph:
             return self.eng.packed_weight(u.conv.weight, "rowmerged", u.cout, 64, self.stream)
         if u.pack == "rowmerged4":
             return self.eng.packed_weight(u.conv.weight, "rowmerged4", u.cout, 32, self.stream)
+        if u.pack == "s2d":
+            return self.eng.packed_weight(u.conv.weight, "s2d", u.cout, 64, self.stream)
         return self.eng.packed_weight(u.conv.weight, u.pack, u.cout, cin, self.stream)
 
     def add(self, u: Unit) -> Unit:
@@ -248,6 +250,8 @@ class UnitGraph:
         """Weights re-packed for the data gradient: roles of Cin / Cout swapped."""
         w = u.conv.weight
         cin = u.x.C
+        if u.pack == "s2d":                         # space-to-depth input layer: n = the 64 input slots, k = Cout
+            return self.eng.packed_weight(w, "s2d_T", cin, u.cout, self.stream)
         if u.form == L.FORM_PHASED:                 # ConvTranspose2d (Cin, Cout, k, k): n = Cin, k = Cout
             return self.eng.packed_weight(w, 0, cin, u.cout, self.stream)
         return self.eng.packed_weight(w, 1, cin, u.cout, self.stream)       # Conv2d (Cout, Cin, k, k): n = Cin
@@ -394,6 +398,9 @@ class UnitGraph:
                 if u.pack == "rowmerged":
                     self._export(plan, exports, w, "ng_unpack_weight_grad_rowmerged", dwp.data_ptr(), (d0, d1, kh, kw),
                                  dev_inv, pre + ".export")
+                elif u.pack == "s2d":
+                    self._export(plan, exports, w, "ng_unpack_weight_grad_s2d", dwp.data_ptr(), (d0, d1), dev_inv,
+                                 pre + ".export")
                 else:
                     self._export(plan, exports, w, "ng_unpack_weight_grad", dwp.data_ptr(),
                                  (d0, d1, kh, kw, u.pack, u.cout, u.x.C), dev_inv, pre + ".export")

@@ -535,16 +535,33 @@ class PatchGANRunner(_RunnerBase):
         B = nparts * Bp
         srcs = [eng.buffers.get(f"{tag}.in{j}", Bp * c * H * W, torch.float32) for j, c in enumerate(chans)]
         g.records["srcs"] = srcs
-        x = eng.act(tag + ".x0", B, H, W, 16, 0)
-        esz = x.t.element_size()
-        for i, (ia, ib) in enumerate(struct):
-            g.pre_ops.append(("ng_prep_input", (srcs[ia].data_ptr(), ca, srcs[ib].data_ptr() if ib >= 0 else None, cb, Bp,
-                                                H, W, 0, 0, L.HALO_ZERO, 16, eng.dt_enum,
-                                                x.t.data_ptr() + i * Bp * H * W * 16 * esz), f"{tag}.prep{i}"))
         c0 = convs[0]
         Hc, Wc = conv_out(H, 4, 2, 1), conv_out(W, 4, 2, 1)
-        u = g.add(Unit("l0", c0, x, c0.weight.shape[0], 4, 2, 1, Hc, Wc, kind="biasact", act=L.ACT_LRELU, slope=0.2,
-                       halo_mode=L.HALO_ZERO))
+        s2d = (eng.impl == L.IMPL_TC and eng.dt_enum != L.F32 and H % 2 == 0 and W % 2 == 0 and cin <= 16 and
+               tuple(c0.kernel_size) == (4, 4) and tuple(c0.stride) == (2, 2) and tuple(c0.padding) == (1, 1) and
+               c0.weight.shape[0] % 64 == 0 and os.environ.get("NIRGAN_B200_D_S2D", "1") != "0")
+        g.records["s2d"] = s2d
+        if s2d:
+            # input layer in space-to-depth form: [B][(H+2)/2][(W+2)/2][4 parities x 16 slots] of the zero-padded image,
+            # on which Conv2d(k4, s2, p1) is a 2x2 stride-1 convolution over 64 stored channels (ng_prep_input_s2d)
+            Hs, Ws = (H + 2) // 2, (W + 2) // 2
+            x = eng.act(tag + ".x0", B, Hs, Ws, 64, 0)
+            esz = x.t.element_size()
+            for i, (ia, ib) in enumerate(struct):
+                g.pre_ops.append(("ng_prep_input_s2d", (srcs[ia].data_ptr(), ca, srcs[ib].data_ptr() if ib >= 0 else None, cb,
+                                                        Bp, H, W, eng.dt_enum, x.t.data_ptr() + i * Bp * Hs * Ws * 64 * esz),
+                                  f"{tag}.prep{i}"))
+            u = g.add(Unit("l0", c0, x, c0.weight.shape[0], 2, 1, 0, Hc, Wc, kind="biasact", act=L.ACT_LRELU, slope=0.2,
+                           halo_mode=L.HALO_ZERO, pack="s2d"))
+        else:
+            x = eng.act(tag + ".x0", B, H, W, 16, 0)
+            esz = x.t.element_size()
+            for i, (ia, ib) in enumerate(struct):
+                g.pre_ops.append(("ng_prep_input", (srcs[ia].data_ptr(), ca, srcs[ib].data_ptr() if ib >= 0 else None, cb, Bp,
+                                                    H, W, 0, 0, L.HALO_ZERO, 16, eng.dt_enum,
+                                                    x.t.data_ptr() + i * Bp * H * W * 16 * esz), f"{tag}.prep{i}"))
+            u = g.add(Unit("l0", c0, x, c0.weight.shape[0], 4, 2, 1, Hc, Wc, kind="biasact", act=L.ACT_LRELU, slope=0.2,
+                           halo_mode=L.HALO_ZERO))
         for i, conv in enumerate(convs[1:-1], start=1):
             s = conv.stride[0]
             Hn, Wn = conv_out(u.Hout, 4, s, 1), conv_out(u.Wout, 4, s, 1)

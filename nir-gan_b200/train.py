@@ -181,8 +181,10 @@ class DiscriminatorFunction(torch.autograd.Function):
         dxs = [None] * ctx.n_in
         if ctx.need_dx:
             struct, Bp, ca, cb, H, W = ctx.desc
-            gx = bwd.records["dx"]                     # [nparts*Bp][H][W][16] gradient of the prepared input
-            esz = gx.t.element_size()
+            gx = bwd.records["dx"]                     # gradient of the prepared input: [nparts*Bp][H][W][16], or its
+            esz = gx.t.element_size()                  # space-to-depth form [nparts*Bp][(H+2)/2][(W+2)/2][4 x 16]
+            s2d = bool(c["graph"].records.get("s2d"))
+            img = ((H + 2) // 2) * ((W + 2) // 2) * 64 if s2d else H * W * gx.C
             for i, (ia, ib) in enumerate(struct):
                 for j, c0, cn in ((ia, 0, ca), (ib, ca, cb)):
                     if j < 0 or not ctx.in_needs[j]:
@@ -191,8 +193,8 @@ class DiscriminatorFunction(torch.autograd.Function):
                         raise NotImplementedError("nirgan_b200: one tensor feeding two discriminator parts with "
                                                   "requires_grad is not supported")
                     dx = torch.empty(Bp, cn, H, W, dtype=torch.float32, device=dout.device)
-                    L.call("ng_grad_to_nchw", gx.t.data_ptr() + i * Bp * H * W * gx.C * esz, runner._engine.dt_enum, Bp,
-                           H, W, gx.C, c0, cn, 1.0, dev_inv, dx.data_ptr(), st)
+                    L.call("ng_grad_to_nchw", gx.t.data_ptr() + i * Bp * img * esz, runner._engine.dt_enum, Bp,
+                           H, W, 16 if s2d else gx.C, c0, cn, 1 if s2d else 0, 1.0, dev_inv, dx.data_ptr(), st)
                     dxs[j] = dx
         out = []
         for p in ctx.params:
