@@ -55,6 +55,7 @@ struct BwdArgs {
   float inv_hw;
   int ppb;                     // interior pixels per block
   int nblk1;                   // pass-1 blocks per image = partial-sum slots per image
+  int n0;                      // first image of this launch (image-chunked launches: grid.y = images in the chunk)
   unsigned long long w_magic;  // ceil(2^40 / W): p / W == (p * w_magic) >> 40 for p < 2^20
 };
 
@@ -222,7 +223,7 @@ in_bwd_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, const 
               const float* __restrict__ inj_scale, float* __restrict__ sums, float* __restrict__ dscale,
               float* __restrict__ de_map, T* __restrict__ dy, T* __restrict__ do_out) {
   extern __shared__ float sm[];            // PASS 1 / 3: [4 accumulators][256 threads]
-  const int n = blockIdx.y, C8 = a.C >> 3;
+  const int n = blockIdx.y + a.n0, C8 = a.C >> 3;
   const int c8 = threadIdx.x & (C8 - 1);
   const int pstep = 256 >> a.c8_shift;
   const int npix = a.H * a.W;
@@ -351,7 +352,7 @@ in_bwd_fast_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, c
                    T* __restrict__ do_out) {
   static_assert(sizeof(T) == 2, "16-bit storage only");
   extern __shared__ float sm[];            // PASS 1: [4 accumulators][256 threads]
-  const int n = blockIdx.y, C8 = a.C >> 3, C = a.C;
+  const int n = blockIdx.y + a.n0, C8 = a.C >> 3, C = a.C;
   const int c8 = threadIdx.x & (C8 - 1);
   const int pstep = 256 >> a.c8_shift;
   const int npix = a.H * a.W;
@@ -466,8 +467,9 @@ in_bwd_fast_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, c
 
 // combined[n][o] = sum over the image's pass-1 blocks of partial[n][blk][o], in block order (deterministic, no atomics)
 __global__ void __launch_bounds__(256)
-in_bwd_combine_kernel(const float* __restrict__ partial, int total, int per_image, int nblk, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+in_bwd_combine_kernel(const float* __restrict__ partial, int first, int total, int per_image, int nblk,
+                      float* __restrict__ out) {
+  const int i = first + blockIdx.x * blockDim.x + threadIdx.x;      // [first, total): the images of this chunk
   if (i >= total) return;
   const int n = i / per_image, o = i - n * per_image;
   const float* p = partial + (size_t)n * nblk * per_image + o;
@@ -774,6 +776,7 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
   a.c8_shift = 0;
   while ((1 << a.c8_shift) < C / 8) ++a.c8_shift;
   a.w_magic = ((1ull << 40) + (unsigned)W - 1) / (unsigned)W;
+  a.n0 = 0;
   const int pstep = 256 / (C / 8);
   const bool need_pass1 = mean_rstd != nullptr || (inject_mode != NG_INJECT_NONE && (dscale || de_map));
   a.nblk1 = in_bwd_pass1_blocks(B, H, W, C);
@@ -794,34 +797,54 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
     NG_LAUNCH_CHECK("in_bwd_kernel<fused>");
     return NG_OK;
   }
-  if (need_pass1) {
-    NG_REQUIRE(mean_rstd == nullptr || sums_scratch != nullptr, NG_E_ARG, "in_bwd: scratch required");
-    if (de_map) {
-      int e = check_cuda(cudaMemsetAsync(de_map, 0, (size_t)B * H * W * sizeof(float), st), "in_bwd memset de");
-      if (e) return e;
-    }
-    a.ppb = (H * W + a.nblk1 - 1) / a.nblk1;
-    a.ppb = (a.ppb + pstep - 1) / pstep * pstep;
-    dim3 grid((unsigned)a.nblk1, (unsigned)B);
-    DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)4 * 256 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
-                                           inject_e, inject_scale, mean_rstd ? sums_scratch : nullptr, dscale, de_map,
-                                           nullptr, nullptr)));
-    NG_LAUNCH_CHECK("in_bwd_kernel<pass 1>");
-    if (mean_rstd) {
-      const int total = B * C * 2;
-      in_bwd_combine_kernel<<<(total + 255) / 256, 256, 0, st>>>(sums_scratch + (size_t)total, total, C * 2, a.nblk1,
-                                                                sums_scratch);
-      NG_LAUNCH_CHECK("in_bwd_combine_kernel");
-    }
+  // Image-chunked schedule for normalised units: pass 1 and pass 2 of a chunk of images run back to back, with the chunk
+  // sized so that what pass 1 streamed (g + y [+ skip]) is still in the 126 MB L2 when pass 2 re-reads it -- the second
+  // read of every unit then comes from L2 instead of HBM.  NIRGAN_B200_BWD_CHUNK_MB=0: whole batch per launch.
+  static const long long chunk_bytes = [] {
+    const char* e = getenv("NIRGAN_B200_BWD_CHUNK_MB");
+    return (long long)(e ? atoi(e) : 40) << 20;
+  }();
+  const int esz = dtype == NG_F32 ? 4 : 2;
+  const long long per_image = ((long long)(H + 2 * a.gp) * (W + 2 * a.gp) * (g_halo ? 1 : 0) + (long long)H * W * (g_skip ? 2 : 1)) *
+                              C * esz;
+  int chunk = B;
+  if (need_pass1 && mean_rstd && chunk_bytes > 0 && de_map == nullptr) {
+    chunk = (int)(chunk_bytes / (per_image > 0 ? per_image : 1));
+    if (chunk < (B + 7) / 8) chunk = (B + 7) / 8;             // at most 8 chunks per unit (launch overhead)
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
   }
-  {
-    const int mult2 = in_bwd_pick_mult(B, H * W, pstep, 4, 32);
-    a.ppb = pstep * (mult2 < 0 ? 16 : mult2);
+  const int mult2 = in_bwd_pick_mult(chunk, H * W, pstep, 4, 32);
+  const int ppb2 = pstep * (mult2 < 0 ? 16 : mult2);
+  int ppb1 = (H * W + a.nblk1 - 1) / a.nblk1;
+  ppb1 = (ppb1 + pstep - 1) / pstep * pstep;
+  if (need_pass1 && de_map) {
+    int e = check_cuda(cudaMemsetAsync(de_map, 0, (size_t)B * H * W * sizeof(float), st), "in_bwd memset de");
+    if (e) return e;
   }
-  dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)B);
-  DISPATCH_T(dtype, (launch_in_bwd<T, 2>(a, grid, 0, st, g_halo, g_skip, y, mean_rstd, inject_e, inject_scale,
-                                         sums_scratch, nullptr, nullptr, dy, do_out)));
-  NG_LAUNCH_CHECK("in_bwd_kernel<pass 2>");
+  for (int n0 = 0; n0 < B; n0 += chunk) {
+    const int nb = B - n0 < chunk ? B - n0 : chunk;
+    a.n0 = n0;
+    if (need_pass1) {
+      a.ppb = ppb1;
+      dim3 grid((unsigned)a.nblk1, (unsigned)nb);
+      DISPATCH_T(dtype, (launch_in_bwd<T, 1>(a, grid, (size_t)4 * 256 * sizeof(float), st, g_halo, g_skip, y, mean_rstd,
+                                             inject_e, inject_scale, mean_rstd ? sums_scratch : nullptr, dscale, de_map,
+                                             nullptr, nullptr)));
+      NG_LAUNCH_CHECK("in_bwd_kernel<pass 1>");
+      if (mean_rstd) {
+        const int total = B * C * 2, first = n0 * C * 2, count = nb * C * 2;
+        in_bwd_combine_kernel<<<(count + 255) / 256, 256, 0, st>>>(sums_scratch + (size_t)total, first, first + count, C * 2,
+                                                                  a.nblk1, sums_scratch);
+        NG_LAUNCH_CHECK("in_bwd_combine_kernel");
+      }
+    }
+    a.ppb = ppb2;
+    dim3 grid((unsigned)((H * W + a.ppb - 1) / a.ppb), (unsigned)nb);
+    DISPATCH_T(dtype, (launch_in_bwd<T, 2>(a, grid, 0, st, g_halo, g_skip, y, mean_rstd, inject_e, inject_scale,
+                                           sums_scratch, nullptr, nullptr, dy, do_out)));
+    NG_LAUNCH_CHECK("in_bwd_kernel<pass 2>");
+  }
   return NG_OK;
 }
 
