@@ -242,7 +242,10 @@ int ng_memset_zero(void* ptr, int64_t bytes, void* stream);
 
 /* Backward of the unit computed by ng_in_apply (autograd of InstanceNorm2d / ReLU / LeakyReLU / residual add /
  * ReflectionPad2d / the SatCLIP injection; model/pix2pix.py:165-257 runs it through torch autograd):
- *   g_halo : dL/d(haloed output buffer) [B][H+2*g_pad][W+2*g_pad][C] or NULL (halo folded back per halo_mode)
+ *   g_halo : dL/d(haloed output buffer) [B][H+2*g_pad][W+2*g_pad][C] or NULL (halo folded back per halo_mode).
+ *            CONSUMED: with 16-bit storage and a reflect halo the fold is done in place (the halo contributions are added
+ *            into the interior pixels next to the border before the two passes stream the interior), so the buffer
+ *            must not be handed to a second ng_in_bwd call without being produced again.
  *   g_skip : dL/d(output interior) from a skip connection, compact [B][H][W][C], or NULL
  *   y, mean_rstd : the forward's pre-norm tensor and statistics (mean_rstd NULL = unit without normalisation)
  *   dy     : dL/dy compact [B][H][W][C];  do_out (optional): dL/d(output interior) for the residual path
@@ -250,7 +253,7 @@ int ng_memset_zero(void* ptr, int64_t bytes, void* stream);
  *   dL/d(bilinear embedding map) [B][H][W] for the injection.   sums_scratch: ng_in_bwd_scratch_floats(B,H,W,C)
  *   floats (per-block partial sums, added in a fixed order by the second pass: no atomics, deterministic). */
 int64_t ng_in_bwd_scratch_floats(int32_t B, int32_t H, int32_t W, int32_t C);
-int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y, int32_t dtype,
+int ng_in_bwd(void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y, int32_t dtype,
               int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd, int32_t act, float slope,
               const float* inject_e, int32_t inject_mode, const float* inject_scale, float* sums_scratch, void* dy,
               void* do_out, float* dscale, float* de_map, void* stream);

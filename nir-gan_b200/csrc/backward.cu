@@ -10,7 +10,7 @@
 //   dy  = rstd * (dxh - mean_hw(dxh) - xh * mean_hw(dxh * xh))          (InstanceNorm backward)
 // Pass 1 (ng_in_bwd_reduce) accumulates the two per-(n,c) means (+ injection gradients), pass 2
 // (ng_in_bwd_apply) recomputes dxh and writes dy (and, for residual blocks, do for the skip path).
-#include "common.cuh"
+#include "tc_common.cuh"
 #include <stdlib.h>
 
 namespace ng {
@@ -56,6 +56,7 @@ struct BwdArgs {
   int ppb;                     // interior pixels per block
   int nblk1;                   // pass-1 blocks per image = partial-sum slots per image
   int n0;                      // first image of this launch (image-chunked launches: grid.y = images in the chunk)
+  int pf_ahead;                // lean kernels: loop iterations of operands kept prefetched into L2 ahead of the loads (0 = off)
   unsigned long long w_magic;  // ceil(2^40 / W): p / W == (p * w_magic) >> 40 for p < 2^20
 };
 
@@ -64,6 +65,10 @@ __device__ __forceinline__ uint4 ldg16_stream(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
+}
+// DRAM -> L2 bulk prefetch (no destination in the SM): the later ld.global of the same bytes hits the L2
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 template <typename T>
 __device__ __forceinline__ void up8(const uint4& u, float (&f)[8]) {
@@ -388,7 +393,29 @@ in_bwd_fast_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, c
   int pp = p_begin + (threadIdx.x >> a.c8_shift);
   int py = pp / a.W, px = pp - py * a.W;
   const int adv_y = pstep / a.W, adv_x = pstep - adv_y * a.W;
+  // The loads of an iteration cover pstep * UNROLL consecutive pixels of every operand.  One thread keeps the next
+  // `pf_ahead` iterations' bytes on their way from DRAM into the L2 (bulk prefetch: no registers, no shared memory), so
+  // the register-staged loads see L2 latency and the bytes a block can keep in flight stop being the bound -- without
+  // the shared-memory ring that would evict the co-resident tcgen05 CTA of the weight-gradient stream.
+  const int chunk_px = pstep * UNROLL;
+  auto prefetch_chunk = [&](int p0) {
+    if (p0 >= p_end) return;
+    const int p1 = min(p0 + chunk_px, p_end) - 1;
+    const uint32_t bytes = (uint32_t)(p1 - p0 + 1) * C * 2;
+    l2_prefetch(yv + ((size_t)n * npix + p0) * C, bytes);
+    if constexpr (HAS_SKIP) l2_prefetch(gskip + ((size_t)n * npix + p0) * C, bytes);
+    if constexpr (HAS_G) {
+      const int y0 = p0 / a.W, y1 = p1 / a.W;
+      const size_t a0 = (size_t)(y0 + gp) * Wb + (p0 - y0 * a.W) + gp, a1 = (size_t)(y1 + gp) * Wb + (p1 - y1 * a.W) + gp;
+      l2_prefetch(g + ((size_t)n * (a.H + 2 * gp) * Wb + a0) * C, (uint32_t)(a1 - a0 + 1) * C * 2);
+    }
+  };
+  int pf_next = p_begin;
+  if (a.pf_ahead > 0 && threadIdx.x == 0) {
+    for (int i = 0; i < a.pf_ahead; ++i, pf_next += chunk_px) prefetch_chunk(pf_next);
+  }
   while (pp < p_end) {
+    if (a.pf_ahead > 0 && threadIdx.x == 0) { prefetch_chunk(pf_next); pf_next += chunk_px; }
     Raw8<T> rg[HAS_G ? UNROLL : 1], rs[HAS_SKIP ? UNROLL : 1], ry[UNROLL];
     int ypos[UNROLL], xpos[UNROLL];
 #pragma unroll
@@ -463,6 +490,298 @@ in_bwd_fast_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, c
       __syncthreads();
     }
   }
+}
+
+// ---- TMA-staged form of the two norm-backward passes ----------------------------------------------------
+// The register-staged kernels above are bound by the bytes they keep in flight (ncu r2h: 34-36 % of the HBM peak with
+// the load batches of a warp draining while it computes).  Here one producer thread streams the operands with bulk
+// asynchronous copies (cp.async.bulk, completion on an mbarrier) into a ring of shared-memory stages -- ~190 KB in
+// flight per SM regardless of what the 16 consumer warps are doing -- and the consumers read 16-byte vectors from
+// shared memory.  One persistent CTA per SM owns a contiguous range of `stage items` (a row segment, or a few whole
+// rows, of one image) of the whole batch; pass 1 leaves one partial-sum slot per (CTA, image it touched), pass 2 sums
+// the slots of its image in CTA order (deterministic) while its first stages are already in flight: no combine launch.
+// A reflect halo of g folds back onto the interior pixels within gp of the border.  The staged kernels read plain row
+// segments, so this pre-pass adds the halo contributions into those interior pixels IN PLACE, once (the register-staged
+// kernels redo the fold in both passes).  Reads touch halo positions only, writes interior positions only: no ordering
+// between threads is needed.  One thread = one border pixel x 8 channels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_halo_kernel(const __grid_constant__ BwdArgs a, T* __restrict__ g) {
+  const int p = a.gp, H = a.H, W = a.W, C8 = a.C >> 3, Wb = W + 2 * p, Hb = H + 2 * p;
+  const int nrow_px = 2 * p * W, per_image = nrow_px + (H - 2 * p) * 2 * p;
+  const long long total = (long long)a.B * per_image * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const long long t = i / C8;
+    const int n = (int)(t / per_image);
+    int j = (int)(t - (long long)n * per_image), y, x;
+    if (j < nrow_px) {                      // rows 1..p and H-1-p..H-2, every column
+      const int ri = j / W;
+      x = j - ri * W;
+      y = ri < p ? 1 + ri : H - 1 - p + (ri - p);
+    } else {                                // the other rows (0, p+1..H-2-p, H-1): columns 1..p and W-1-p..W-2
+      j -= nrow_px;
+      const int yi = j / (2 * p), ci = j - yi * 2 * p;
+      y = yi == 0 ? 0 : (yi == H - 2 * p - 1 ? H - 1 : p + yi);
+      x = ci < p ? 1 + ci : W - 1 - p + (ci - p);
+    }
+    T* gn = g + (size_t)n * Hb * Wb * a.C + c8 * 8;
+    float d[8], own[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = 0.f;
+    fold_halo_extras<T>(a, gn, y, x, d);
+    T* o = gn + ((size_t)(y + p) * Wb + x + p) * a.C;
+    ld8<T>(o, own);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) own[k] += d[k];
+    st8<T>(o, own);
+  }
+}
+
+struct BwdStream {
+  int segw, rows, split, ipi;     // stage item = rows x segw pixels of one image; items per image
+  int total, G, kmax;             // items in the batch, CTAs, partial slots per CTA
+  int nstages, tensor_bytes;      // shared-memory ring: nstages x tensors x tensor_bytes
+};
+constexpr int kBwdConsumers = 512;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <typename T, int PASS, bool HAS_G, bool HAS_SKIP, int ACT>
+__global__ void __launch_bounds__(kBwdConsumers + 32, 1)
+in_bwd_stream_kernel(const __grid_constant__ BwdArgs a, const __grid_constant__ BwdStream q, const T* __restrict__ g,
+                     const T* __restrict__ gskip, const T* __restrict__ yv, const float* __restrict__ mr,
+                     float* __restrict__ sums, T* __restrict__ dy, T* __restrict__ do_out) {
+  static_assert(sizeof(T) == 2, "16-bit storage only");
+  constexpr int NTEN = (HAS_G ? 1 : 0) + (HAS_SKIP ? 1 : 0) + 1;
+  extern __shared__ __align__(128) uint8_t ring_raw[];
+  __shared__ __align__(8) uint64_t bars[16];          // full[8], empty[8]
+  const uint32_t ring = smem_u32(ring_raw);
+  float* red = reinterpret_cast<float*>(ring_raw + (size_t)q.nstages * NTEN * q.tensor_bytes);    // [4][512]
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
+  const int tid = threadIdx.x, C = a.C, npix = a.H * a.W;
+  if (tid == 0) {
+    for (int s = 0; s < q.nstages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kBwdConsumers / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const long long it0 = (long long)blockIdx.x * q.total / q.G, it1 = (long long)(blockIdx.x + 1) * q.total / q.G;
+  const int gp = a.gp, Wb = a.W + 2 * gp, Hb = a.H + 2 * gp;
+  const uint32_t seg_bytes = (uint32_t)q.segw * C * 2;
+
+  if (tid >= kBwdConsumers) {
+    // ---- producer: one thread keeps the ring full ----
+    if (tid != kBwdConsumers) return;
+    int k = 0;
+    for (long long it = it0; it < it1; ++it, ++k) {
+      const int s = k % q.nstages;
+      mbar_wait(empty0 + 8 * s, ((k / q.nstages) & 1) ^ 1);
+      const int n = (int)(it / q.ipi), r = (int)(it - (long long)n * q.ipi);
+      const int yb = r / q.split, xs = r - yb * q.split;
+      const int y0 = yb * q.rows, x0 = xs * q.segw, nr = min(q.rows, a.H - y0);
+      const uint32_t bytes = seg_bytes * nr;
+      const uint32_t bar = full0 + 8 * s;
+      mbar_expect_tx(bar, bytes * NTEN);
+      uint32_t dst = ring + (uint32_t)s * NTEN * q.tensor_bytes;
+      if constexpr (HAS_G) {
+        for (int rr = 0; rr < nr; ++rr)
+          bulk_g2s(dst + rr * seg_bytes, g + (((size_t)n * Hb + y0 + rr + gp) * Wb + x0 + gp) * C, seg_bytes, bar);
+        dst += q.tensor_bytes;
+      }
+      // the un-haloed tensors are contiguous over the rows of a stage (split == 1 whenever rows > 1)
+      bulk_g2s(dst, yv + ((size_t)n * npix + (size_t)y0 * a.W + x0) * C, bytes, bar);
+      if constexpr (HAS_SKIP) bulk_g2s(dst + q.tensor_bytes, gskip + ((size_t)n * npix + (size_t)y0 * a.W + x0) * C, bytes, bar);
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int C8 = C >> 3, c8 = tid & (C8 - 1), lane_px = tid >> a.c8_shift, lanes = kBwdConsumers >> a.c8_shift;
+  float sa[8], sb[8], k1[8], k2[8], acc1[8], acc2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { acc1[k] = acc2[k] = 0.f; k1[k] = k2[k] = 0.f; sa[k] = 1.f; sb[k] = 0.f; }
+  float* part = sums + (size_t)a.B * C * 2;
+  const int n_first = (int)(it0 / q.ipi);
+  int cur_n = -1;
+
+  auto flush = [&](int n) {          // PASS 1: block reduction in a fixed order into the slot of (this CTA, image n)
+    float* dst = part + ((size_t)blockIdx.x * q.kmax + (n - n_first)) * C * 2;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      red[0 * kBwdConsumers + tid] = acc1[2 * r];
+      red[1 * kBwdConsumers + tid] = acc2[2 * r];
+      red[2 * kBwdConsumers + tid] = acc1[2 * r + 1];
+      red[3 * kBwdConsumers + tid] = acc2[2 * r + 1];
+      consumers_sync();
+      if (tid < (C >> 1)) {
+        const int cg = tid >> 2, j = tid & 3;
+        float t = 0.f;
+        for (int L = 0; L < lanes; ++L) t += red[j * kBwdConsumers + (L << a.c8_shift) + cg];
+        dst[cg * 16 + 4 * r + j] = t;
+      }
+      consumers_sync();
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc1[k] = acc2[k] = 0.f;
+  };
+
+  int k = 0;
+  for (long long it = it0; it < it1; ++it, ++k) {
+    const int s = k % q.nstages;
+    const int n = (int)(it / q.ipi), r = (int)(it - (long long)n * q.ipi);
+    const int yb = r / q.split, xs = r - yb * q.split;
+    const int y0 = yb * q.rows, x0 = xs * q.segw, nr = min(q.rows, a.H - y0);
+    if (n != cur_n) {
+      if (PASS == 1 && cur_n >= 0) flush(cur_n);
+      cur_n = n;
+      const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 m = m4[j];
+        sa[2 * j] = m.y; sb[2 * j] = -m.x * m.y; sa[2 * j + 1] = m.w; sb[2 * j + 1] = -m.z * m.w;
+      }
+      if constexpr (PASS == 2) {
+        // the image's sums: slots of the CTAs whose ranges meet the image, added in CTA order
+        const long long i_lo = (long long)n * q.ipi, i_hi = i_lo + q.ipi - 1;
+        const int c_lo = (int)(((i_lo + 1) * q.G - 1) / q.total), c_hi = (int)(((i_hi + 1) * q.G - 1) / q.total);
+        float s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+        for (int cc = c_lo; cc <= c_hi; ++cc) {
+          const int nf = (int)(((long long)cc * q.total / q.G) / q.ipi);
+          const float4* p4 = reinterpret_cast<const float4*>(part + (((size_t)cc * q.kmax + (n - nf)) * C + c8 * 8) * 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 v = __ldcg(p4 + j);
+            s1[2 * j] += v.x; s2[2 * j] += v.y; s1[2 * j + 1] += v.z; s2[2 * j + 1] += v.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { k1[j] = -sa[j] * (s1[j] * a.inv_hw); k2[j] = -sa[j] * (s2[j] * a.inv_hw); }
+      }
+    }
+    const int npx = nr * q.segw;
+    const size_t pix0 = (size_t)n * npix + (size_t)y0 * a.W + x0;       // stage pixels are consecutive interior pixels
+    T* dyn = PASS == 2 ? dy + pix0 * C + c8 * 8 : nullptr;
+    T* don = (PASS == 2 && do_out) ? do_out + pix0 * C + c8 * 8 : nullptr;
+    const uint32_t sbase = ring + (uint32_t)s * NTEN * q.tensor_bytes + c8 * 16;
+    const uint32_t off_y = HAS_G ? q.tensor_bytes : 0, off_s = off_y + q.tensor_bytes;
+    mbar_wait(full0 + 8 * s, (k / q.nstages) & 1);
+#pragma unroll 2
+    for (int qx = lane_px; qx < npx; qx += lanes) {
+      const uint32_t so = sbase + (uint32_t)qx * C * 2;
+      float d_o[8], xh[8];
+      if constexpr (HAS_G) up8<T>(lds128(so), d_o);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d_o[j] = 0.f;
+      }
+      if constexpr (HAS_SKIP) {
+        float t[8];
+        up8<T>(lds128(so + off_s), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d_o[j] += t[j];
+      }
+      up8<T>(lds128(so + off_y), xh);
+      float dxh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[j] = fmaf(xh[j], sa[j], sb[j]);
+        if (ACT == NG_ACT_RELU) dxh[j] = xh[j] > 0.f ? d_o[j] : 0.f;
+        else if (ACT == NG_ACT_LRELU) dxh[j] = xh[j] > 0.f ? d_o[j] : d_o[j] * a.slope;
+        else dxh[j] = d_o[j];
+      }
+      if constexpr (PASS == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc1[j] += dxh[j]; acc2[j] = fmaf(dxh[j], xh[j], acc2[j]); }
+      } else {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(dxh[j], sa[j], fmaf(xh[j], k2[j], k1[j]));
+        st8<T>(dyn + (size_t)qx * C, o);
+        if (don) st8<T>(don + (size_t)qx * C, d_o);
+      }
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(empty0 + 8 * s);
+  }
+  if (PASS == 1 && cur_n >= 0) flush(cur_n);
+}
+
+// Geometry of the staged form; false when the shape does not fit it (the register-staged kernels serve those).
+static bool in_bwd_stream_geometry(int B, int H, int W, int C, int ntensors, BwdStream* out, bool sizing_only = false) {
+  // opt-in (NIRGAN_B200_BWD_STREAM=1, read per call so that tests can switch it): in isolation the staged kernels reach
+  // 52-75 % of the HBM copy peak against 34-36 % (profiles/r2q_in_bwd_stream.md), but their ~200 KB shared-memory ring
+  // cannot sit beside a tcgen05 CTA of the weight-gradient stream, and the training step loses more from that lost
+  // overlap than the kernels gain (20.6 vs 19.4 ms per step, r2q).
+  const char* env = getenv("NIRGAN_B200_BWD_STREAM");
+  const bool on = sizing_only || (env && env[0] == '1');
+  if (!on || C > 512 || C < 8) return false;
+  const long long rowbytes = (long long)W * C * 2;
+  BwdStream q;
+  q.rows = 1; q.split = 0;
+  for (int budget = 16384; budget <= 32768 && !q.split; budget *= 2) {
+    if (rowbytes <= budget) {
+      q.split = 1;
+      q.rows = (int)(16384 / rowbytes);
+      if (q.rows < 1) q.rows = 1;
+      if (q.rows > H) q.rows = H;
+      if (q.rows > 16) q.rows = 16;
+    } else {
+      for (int sp = 2; sp <= W; ++sp)        // whole divisors of the row only, and never segments below half the budget
+        if (W % sp == 0 && rowbytes / sp <= budget) {
+          if (rowbytes / sp >= budget / 2) q.split = sp;
+          break;
+        }
+    }
+  }
+  if (!q.split) return false;
+  q.segw = W / q.split;
+  q.ipi = ((H + q.rows - 1) / q.rows) * q.split;
+  const long long total = (long long)B * q.ipi;
+  if (total >= (1ll << 31) / 1024) return false;
+  q.total = (int)total;
+  q.G = num_sms() < q.total ? num_sms() : q.total;
+  const int per = (q.total + q.G - 1) / q.G;
+  q.kmax = (per + q.ipi - 1) / q.ipi + 1;
+  q.tensor_bytes = (q.rows * q.segw * C * 2 + 127) / 128 * 128;
+  const int avail = 232448 - 4 * kBwdConsumers * (int)sizeof(float) - 1024;
+  q.nstages = avail / (ntensors * q.tensor_bytes);
+  if (q.nstages > 8) q.nstages = 8;
+  if (q.nstages < 2) return false;
+  *out = q;
+  return true;
+}
+
+template <typename T, int PASS>
+static int launch_in_bwd_stream(const BwdArgs& a, const BwdStream& q, cudaStream_t st, const void* g, const void* gskip,
+                                const void* y, const float* mr, float* sums, void* dy, void* do_out) {
+  const bool hg = g != nullptr, hs = gskip != nullptr;
+  const int nten = (hg ? 1 : 0) + (hs ? 1 : 0) + 1;
+  const size_t smem = (size_t)q.nstages * nten * q.tensor_bytes + 4 * kBwdConsumers * sizeof(float);
+#define NG_BWDS(HG, HS, ACT)                                                                                            \
+  do {                                                                                                                  \
+    auto kern = in_bwd_stream_kernel<T, PASS, HG, HS, ACT>;                                                             \
+    int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024),          \
+                       "in_bwd_stream smem attribute");                                                                 \
+    if (e) return e;                                                                                                    \
+    kern<<<q.G, kBwdConsumers + 32, smem, st>>>(a, q, (const T*)g, (const T*)gskip, (const T*)y, mr, sums, (T*)dy,      \
+                                                (T*)do_out);                                                            \
+  } while (0)
+#define NG_BWDS_ACT(ACT)                                                                                                \
+  do {                                                                                                                  \
+    if (hg && hs) NG_BWDS(true, true, ACT); else if (hg) NG_BWDS(true, false, ACT); else NG_BWDS(false, true, ACT);    \
+  } while (0)
+  if (a.act == NG_ACT_RELU) NG_BWDS_ACT(NG_ACT_RELU);
+  else if (a.act == NG_ACT_LRELU) NG_BWDS_ACT(NG_ACT_LRELU);
+  else NG_BWDS_ACT(NG_ACT_NONE);
+#undef NG_BWDS_ACT
+#undef NG_BWDS
+  return NG_OK;
 }
 
 // combined[n][o] = sum over the image's pass-1 blocks of partial[n][blk][o], in block order (deterministic, no atomics)
@@ -658,6 +977,13 @@ using namespace ng;
     default: ng::set_error("bad dtype %d", (int)(dtype)); return NG_E_ARG;  \
   }
 
+#define DISPATCH_T16(dtype, CALL)                                           \
+  switch (dtype) {                                                          \
+    case NG_F16: { using T = __half; CALL; break; }                         \
+    case NG_BF16: { using T = __nv_bfloat16; CALL; break; }                 \
+    default: ng::set_error("bad dtype %d", (int)(dtype)); return NG_E_ARG;  \
+  }
+
 template <typename T, int PASS>
 static void launch_in_bwd(const BwdArgs& a, dim3 grid, size_t smem, cudaStream_t st, const void* g, const void* gskip,
                           const void* y, const float* mr, const float* inj, const float* inj_scale, float* sums,
@@ -754,11 +1080,18 @@ static int in_bwd_pass1_blocks(int B, int H, int W, int C) {
 
 extern "C" int64_t ng_in_bwd_scratch_floats(int32_t B, int32_t H, int32_t W, int32_t C) {
   if (B <= 0 || H <= 0 || W <= 0 || C < 8 || C % 8) return NG_E_ARG;
-  // combined sums + per-block partials + per-image ticket counter and flag (one-launch form)
-  return (int64_t)B * (1 + in_bwd_pass1_blocks(B, H, W, C)) * C * 2 + 2 * (int64_t)B;
+  // combined sums + per-block partials + per-image ticket counter and flag (one-launch form); the staged form keeps one
+  // partial slot per (CTA, image it touches) behind the combined sums
+  int64_t need = (int64_t)B * (1 + in_bwd_pass1_blocks(B, H, W, C)) * C * 2 + 2 * (int64_t)B;
+  BwdStream q;
+  if (in_bwd_stream_geometry(B, H, W, C, 3, &q, true)) {
+    const int64_t staged = (int64_t)B * C * 2 + (int64_t)q.G * q.kmax * C * 2;
+    if (staged > need) need = staged;
+  }
+  return need;
 }
 
-extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y,
+extern "C" int ng_in_bwd(void* g_halo, int32_t g_pad, int32_t halo_mode, const void* g_skip, const void* y,
                          int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, const float* mean_rstd, int32_t act,
                          float slope, const float* inject_e, int32_t inject_mode, const float* inject_scale,
                          float* sums_scratch, void* dy, void* do_out, float* dscale, float* de_map, void* stream) {
@@ -777,6 +1110,8 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
   while ((1 << a.c8_shift) < C / 8) ++a.c8_shift;
   a.w_magic = ((1ull << 40) + (unsigned)W - 1) / (unsigned)W;
   a.n0 = 0;
+  static const int pf_ahead = [] { const char* e = getenv("NIRGAN_B200_BWD_PREFETCH"); return e ? atoi(e) : 3; }();
+  a.pf_ahead = pf_ahead;
   const int pstep = 256 / (C / 8);
   const bool need_pass1 = mean_rstd != nullptr || (inject_mode != NG_INJECT_NONE && (dscale || de_map));
   a.nblk1 = in_bwd_pass1_blocks(B, H, W, C);
@@ -797,12 +1132,36 @@ extern "C" int ng_in_bwd(const void* g_halo, int32_t g_pad, int32_t halo_mode, c
     NG_LAUNCH_CHECK("in_bwd_kernel<fused>");
     return NG_OK;
   }
+  // Staged form (16-bit storage, normalised unit, no injection): two launches, no combine.  The partial-slot geometry
+  // depends on the shape only (not on which tensors are present), so both passes and the scratch query agree.
+  if (dtype != NG_F32 && mean_rstd && inject_mode == NG_INJECT_NONE && dscale == nullptr && de_map == nullptr &&
+      (act == NG_ACT_RELU || act == NG_ACT_NONE || act == NG_ACT_LRELU)) {
+    BwdStream q, q3;
+    const int nten = (g_halo ? 1 : 0) + (g_skip ? 1 : 0) + 1;
+    if (in_bwd_stream_geometry(B, H, W, C, nten, &q) && in_bwd_stream_geometry(B, H, W, C, 3, &q3)) {
+      if (g_halo && halo_mode == NG_HALO_REFLECT && a.gp > 0) {
+        const long long items = (long long)B * (2 * a.gp * W + (H - 2 * a.gp) * 2 * a.gp) * (C / 8);
+        DISPATCH_T16(dtype, (fold_halo_kernel<T><<<grid_cap(items), 256, 0, st>>>(a, (T*)g_halo)));
+        NG_LAUNCH_CHECK("fold_halo_kernel");
+        a.halo_mode = NG_HALO_ZERO;          // folded: the passes read the interior only
+      }
+      DISPATCH_T16(dtype, (r = launch_in_bwd_stream<T, 1>(a, q, st, g_halo, g_skip, y, mean_rstd, sums_scratch, nullptr, nullptr)));
+      if (r) return r;
+      NG_LAUNCH_CHECK("in_bwd_stream_kernel<pass 1>");
+      DISPATCH_T16(dtype, (r = launch_in_bwd_stream<T, 2>(a, q, st, g_halo, g_skip, y, mean_rstd, sums_scratch, dy, do_out)));
+      if (r) return r;
+      NG_LAUNCH_CHECK("in_bwd_stream_kernel<pass 2>");
+      return NG_OK;
+    }
+  }
   // Image-chunked schedule for normalised units: pass 1 and pass 2 of a chunk of images run back to back, with the chunk
   // sized so that what pass 1 streamed (g + y [+ skip]) is still in the 126 MB L2 when pass 2 re-reads it -- the second
-  // read of every unit then comes from L2 instead of HBM.  NIRGAN_B200_BWD_CHUNK_MB=0: whole batch per launch.
+  // read of every unit then comes from L2 instead of HBM.  Measured SLOWER at every chunk size (r2o: 19.30 ms per training
+  // step unchunked, 19.90 / 20.81 / 21.59 ms with 80 / 40 / 20 MB chunks -- the extra launches and their partly filled
+  // waves cost more than the L2 hits return), so the default NIRGAN_B200_BWD_CHUNK_MB=0 keeps the whole batch per launch.
   static const long long chunk_bytes = [] {
     const char* e = getenv("NIRGAN_B200_BWD_CHUNK_MB");
-    return (long long)(e ? atoi(e) : 40) << 20;
+    return (long long)(e ? atoi(e) : 0) << 20;
   }();
   const int esz = dtype == NG_F32 ? 4 : 2;
   const long long per_image = ((long long)(H + 2 * a.gp) * (W + 2 * a.gp) * (g_halo ? 1 : 0) + (long long)H * W * (g_skip ? 2 : 1)) *

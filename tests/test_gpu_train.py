@@ -107,6 +107,70 @@ def test_in_bwd_unit_matches_autograd(case, dt):
         assert float((db - de128.sum(0)).abs().max()) <= 1e-3 * max(1.0, float(de128.sum(0).abs().max()))
 
 
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("shape", [
+    # B, C, H, W, act, halo, mode, skip gradient, haloed gradient
+    (3, 256, 64, 64, "relu", 1, "reflect", True, True),      # ResnetBlock unit: half-row stages, CTA ranges straddle images
+    (2, 512, 31, 31, "lrelu", 0, "zero", False, True),       # PatchGAN l3: odd width, 31 KB row stages
+    (5, 128, 12, 20, "none", 1, "reflect", True, True),      # several rows per stage, ragged last stage of an image
+    (2, 64, 256, 256, "relu", 3, "reflect", False, True),    # stem unit of a 256 px tile, 7x7 halo
+    (300, 64, 8, 8, "relu", 1, "reflect", False, True),      # more images than CTAs: several partial slots per CTA
+    (4, 128, 32, 32, "lrelu", 0, "zero", True, False),       # skip gradient only
+], ids=["res64", "d_l3", "rows", "stem256", "manyimg", "skiponly"])
+@pytest.mark.parametrize("form", ["staged", "lean"])
+def test_in_bwd_staged_form_matches_autograd(shape, dt, form, monkeypatch):
+    """The TMA-staged norm backward (16-bit storage, normalised units; opt-in) and the default lean register-staged form
+    with its L2 prefetch, against autograd on the same rounded inputs, over the stage geometries the staged form has: row
+    segments, whole rows, several rows, ragged tails, CTA ranges that straddle images."""
+    monkeypatch.setenv("NIRGAN_B200_BWD_STREAM", "1" if form == "staged" else "0")
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    B, Cn, H, W, actn, p, mode, has_skip, has_g = shape
+    dtype = L.F16 if dt == "f16" else L.BF16
+    act = {"relu": L.ACT_RELU, "lrelu": L.ACT_LRELU, "none": L.ACT_NONE}[actn]
+    slope = 0.2
+    tdt = Hh.TORCH_DT[dtype]
+    y = Hh.rnd(_gen(B, Cn, H, W, seed=11) * 1.5 + 0.3, dtype).requires_grad_(True)
+    mu = y.mean(dim=(2, 3), keepdim=True)
+    var = y.var(dim=(2, 3), unbiased=False, keepdim=True)
+    xh = (y - mu) / torch.sqrt(var + 1e-5)
+    o = F.relu(xh) if act == L.ACT_RELU else (F.leaky_relu(xh, slope) if act == L.ACT_LRELU else xh)
+    o.retain_grad()
+    ob = F.pad(o, (p,) * 4, mode="reflect") if (p and mode == "reflect") else o
+    g = Hh.rnd(_gen(*ob.shape, seed=12), dtype)
+    gskip = Hh.rnd(_gen(B, Cn, H, W, seed=13), dtype)
+    loss = 0
+    if has_g:
+        loss = loss + (ob * g).sum()
+    if has_skip:
+        loss = loss + (o * gskip).sum()
+    loss.backward()
+    yb = Hh.to_actbuf(y.detach(), 0, "zero", dtype)
+    mr = torch.empty(B * Cn * 2, device="cuda")
+    L.call("ng_in_stats", yb.t.data_ptr(), dtype, B, H * W, Cn, mr.data_ptr(), Hh.stream())
+    gb = g.permute(0, 2, 3, 1).contiguous().to(tdt)
+    gs = gskip.permute(0, 2, 3, 1).contiguous().to(tdt)
+    dy = torch.full((B * H * W * Cn,), float("nan"), device="cuda").to(tdt)
+    do = torch.full((B * H * W * Cn,), float("nan"), device="cuda").to(tdt)
+    sums = torch.full((int(L.load().ng_in_bwd_scratch_floats(B, H, W, Cn)),), float("nan"), device="cuda")
+    L.call("ng_in_bwd", gb.data_ptr() if has_g else None, p, L.HALO_REFLECT if mode == "reflect" else L.HALO_ZERO,
+           gs.data_ptr() if has_skip else None, yb.t.data_ptr(), dtype, B, H, W, Cn, mr.data_ptr(), act, slope,
+           None, L.INJECT_NONE, None, sums.data_ptr(), dy.data_ptr(), do.data_ptr() if has_skip else None, None, None,
+           Hh.stream())
+    torch.cuda.synchronize()
+    got = Hh.from_compact(dy, B, H, W, Cn)
+    ref = y.grad
+    assert bool(torch.isfinite(got).all())
+    eps = 2.0 ** -11 if dtype == L.F16 else 2.0 ** -8          # one output rounding on top of the fp32 arithmetic
+    # a pixel whose rounded y EQUALS the channel mean (bf16 on tiny images: one in ~10^4) has xh == 0 exactly in torch and
+    # +-1e-8 here (one FFMA with the rounded -mean * rstd, the same expression as the forward's mask): its mask may differ
+    bad = (got - ref).abs() > 2.5 * eps * max(1.0, float(ref.abs().max()))
+    assert float(bad.float().mean()) <= (0.0 if dtype == L.F16 else 2e-4), shape
+    assert _relerr(got, ref) <= (eps if dtype == L.F16 else 2 * eps)
+    if has_skip:
+        assert float((Hh.from_compact(do, B, H, W, Cn) - o.grad).abs().max()) <= 4 * eps * max(1.0, float(o.grad.abs().max()))
+
+
 def _cfg(lambda_rs=1.0, inject=False, **kw):
     from nirgan_b200.config import px2px_config
     return px2px_config(lambda_rs=lambda_rs, inject=inject, **kw)
