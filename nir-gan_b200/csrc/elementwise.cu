@@ -294,13 +294,34 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 // life (C/8 is a power of two <= 256), so the 8 (mean, rstd) pairs live in registers.  The inner loop is: UNROLL
 // independent 16-byte streaming loads (+ residual loads) -> math one pixel at a time -> 16-byte stores.  The pixel ->
 // (row, column) split uses a multiply-shift by the precomputed reciprocal of the buffer width.
+// DRAM -> L2 bulk prefetch of the source rows a block is about to read (y and, if present, the haloed residual): the
+// block's 16-byte loads then see L2 latency, and the bytes a block keeps in flight stop bounding the kernel.  One thread
+// per block; rows are over-approximated at the reflect borders (a neighbouring block needs them anyway).
+__device__ __forceinline__ void apply_prefetch_rows(const void* y, const void* res, int n, int H, int W, int C, int esz,
+                                                    int op, bool reflect, int res_pad, int Wo, int p_begin, int p_end) {
+  const int yo0 = p_begin / Wo, yo1 = (p_end - 1) / Wo;
+  int lo = min(max(yo0 - op, 0), H - 1), hi = min(max(yo1 - op, 0), H - 1);
+  if (reflect) {
+    if (yo0 < op) hi = max(hi, min(op, H - 1));
+    if (yo1 >= H + op) lo = min(lo, max(H - 1 - op, 0));
+  }
+  const size_t row = (size_t)W * C * esz;
+  const char* yp = reinterpret_cast<const char*>(y) + ((size_t)n * H + lo) * row;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(yp), "r"((uint32_t)((hi - lo + 1) * row)) : "memory");
+  if (res) {
+    const size_t rrow = (size_t)(W + 2 * res_pad) * C * esz;
+    const char* rp = reinterpret_cast<const char*>(res) + ((size_t)n * (H + 2 * res_pad) + lo + res_pad) * rrow;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rp), "r"((uint32_t)((hi - lo + 1) * rrow)) : "memory");
+  }
+}
+
 template <typename T, int UNROLL, bool HAS_RES, bool HAS_INJ>
 __global__ void __launch_bounds__(256, 3)
 in_apply_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, const float* __restrict__ mr,
                 const long long* __restrict__ acc, float* __restrict__ mr_out, int act,
                 float slope, const T* __restrict__ res, int res_pad, const float* __restrict__ inj, int inj_mode,
                 const float* __restrict__ inj_scale, T* __restrict__ out, int op, int halo_mode, int ppb,
-                unsigned long long wo_magic) {
+                unsigned long long wo_magic, int pf) {
   const int Ho = H + 2 * op, Wo = W + 2 * op, C8 = C >> 3;
   const int n = blockIdx.y;
   const int npix = Ho * Wo;
@@ -308,6 +329,9 @@ in_apply_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, cons
   const int c8 = threadIdx.x & (C8 - 1);
   const int pstep = 256 >> c8_shift;                 // pixels covered by the block per load
   const int p_begin = blockIdx.x * ppb, p_end = min(npix, p_begin + ppb);
+  if (pf && threadIdx.x == 0 && p_begin < p_end)
+    apply_prefetch_rows(y, HAS_RES ? res : nullptr, n, H, W, C, (int)sizeof(T), op, halo_mode == NG_HALO_REFLECT, res_pad, Wo,
+                        p_begin, p_end);
   float mean[8], rstd[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) { mean[k] = 0.f; rstd[k] = 1.f; }
@@ -441,7 +465,7 @@ template <typename T, int UNROLL, bool HAS_RES, bool RELU>
 __global__ void __launch_bounds__(256, 3)
 in_apply_fast_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, const float* __restrict__ mr,
                      const long long* __restrict__ acc, float* __restrict__ mr_out, const T* __restrict__ res,
-                     int res_pad, T* __restrict__ out, int op, int reflect, int ppb) {
+                     int res_pad, T* __restrict__ out, int op, int reflect, int ppb, int pf) {
   static_assert(sizeof(T) == 2, "16-bit storage only");
   constexpr bool BF = std::is_same<T, __nv_bfloat16>::value;
   const int Ho = H + 2 * op, Wo = W + 2 * op, C8 = C >> 3;
@@ -450,6 +474,8 @@ in_apply_fast_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift,
   const int c8 = threadIdx.x & (C8 - 1);
   const int pstep = 256 >> c8_shift;                 // pixels covered by the block per load
   const int p_begin = blockIdx.x * ppb, p_end = min(npix, p_begin + ppb);
+  if (pf && threadIdx.x == 0 && p_begin < p_end)
+    apply_prefetch_rows(y, HAS_RES ? res : nullptr, n, H, W, C, 2, op, reflect != 0, res_pad, Wo, p_begin, p_end);
   float sa[8], sb[8];                                // xh = y * sa + sb
   if (mr) {
     const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
@@ -1099,6 +1125,7 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   const int pstep = 256 / C8;                     // pixels per block per load
   const int ppb = pstep * 16;                     // 16 sixteen-byte items per thread = 4 batches of UNROLL 4
   dim3 grid((unsigned)((Ho * Wo + ppb - 1) / ppb), (unsigned)B);
+  static const int apply_pf = [] { const char* e = getenv("NIRGAN_B200_APPLY_PREFETCH"); return e ? atoi(e) : 1; }();
   // lean kernel for the common case (see in_apply_fast_kernel); NIRGAN_B200_APPLY_FAST=0 keeps the generic one
   static const bool fast_on = [] { const char* e = getenv("NIRGAN_B200_APPLY_FAST"); return !(e && e[0] == '0'); }();
   const bool has_inj0 = inject_mode != NG_INJECT_NONE;
@@ -1109,7 +1136,7 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
 #define NG_FAST(TT, RES, RL)                                                                                         \
     in_apply_fast_kernel<TT, 4, RES, RL><<<grid, 256, 0, (cudaStream_t)stream>>>(                                      \
         (const TT*)y, H, W, C, c8_shift, mean_rstd, (const long long*)stat_acc, mean_rstd_out, (const TT*)residual,    \
-        res_pad, (TT*)out, out_pad, reflect, ppb)
+        res_pad, (TT*)out, out_pad, reflect, ppb, apply_pf)
 #define NG_FAST_T(TT)                                                                                                \
     do {                                                                                                             \
       if (residual) { if (act == NG_ACT_RELU) NG_FAST(TT, true, true); else NG_FAST(TT, true, false); }             \
@@ -1125,7 +1152,7 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   DISPATCH_DTYPE(dtype, (in_apply_kernel<T, 4, RES, INJ><<<grid, 256, 0, (cudaStream_t)stream>>>(                  \
                             (const T*)y, H, W, C, c8_shift, mean_rstd, (const long long*)stat_acc, mean_rstd_out, act,    \
                             slope, (const T*)residual, res_pad,                                                     \
-                            inject_e, inject_mode, inject_scale, (T*)out, out_pad, halo_mode, ppb, wo_magic)))
+                            inject_e, inject_mode, inject_scale, (T*)out, out_pad, halo_mode, ppb, wo_magic, apply_pf)))
   const bool has_inj = inject_mode != NG_INJECT_NONE;
   if (residual && has_inj) { NG_APPLY_LAUNCH(true, true); }
   else if (residual) { NG_APPLY_LAUNCH(true, false); }
