@@ -57,7 +57,7 @@
 extern "C" {
 #endif
 
-#define NG_VERSION 101
+#define NG_VERSION 102
 
 /* element types */
 enum { NG_F32 = 0, NG_F16 = 1, NG_BF16 = 2 };
@@ -195,6 +195,14 @@ int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, i
  * cropped output.  Replaces Conv2d(64->1, k7) + Tanh (model/networks.py:366-368) without the 49x im2col re-read. */
 int ng_tap_gather(const void* z, int32_t dtype, int32_t B, int32_t Hz, int32_t Wz, int32_t zc, int32_t KH, int32_t KW,
                   const float* bias, int32_t act, int32_t crop, float* out, void* stream);
+
+/* Conv2d(64 -> 1, k7) + Tanh head in ONE kernel (model/networks.py:366-368; 16-bit storage): per 8 x 16 output patch
+ * the haloed 14 x 22 x 64 input patch is fetched once by TMA, the tap GEMM of the whole patch runs on tcgen05 into TMEM,
+ * and the 49 shifted taps are summed from a shared-memory z tile -- z never goes to HBM (the ng_conv2d tap GEMM +
+ * ng_tap_gather pair writes and re-reads it).  x_haloed: [B][H+6][W+6][64] (halo 3 already filled by ng_in_apply),
+ * w_taps: [64 taps (49 used)][64 channels] as packed by ng_pack_weight for the tap GEMM, out: fp32 [B][H-2*crop][W-2*crop]. */
+int ng_head_conv(const void* x_haloed, int32_t dtype, int32_t B, int32_t H, int32_t W, const void* w_taps,
+                 const float* bias, int32_t act, int32_t crop, float* out, void* stream);
 
 /* Backward of ng_tap_gather: dz[n][yy][xx][kh*KW+kw] = scale * dev_scale[0] * dout[n][yy-kh-crop][xx-kw-crop] * act'(out)
  * (zero outside the cropped output window; taps >= KH*KW zero).  With dz, the weight gradient of the single-channel

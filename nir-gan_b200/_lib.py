@@ -21,7 +21,7 @@ HALO_ZERO, HALO_REFLECT = 0, 1
 INJECT_NONE, INJECT_ADD, INJECT_MUL_SCALED, INJECT_MUL = 0, 1, 2, 3
 
 c_i32, c_i64, c_f32, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
-ABI_VERSION = 101          # NG_VERSION of include/nirgan_b200.h this binding was written against
+ABI_VERSION = 102          # NG_VERSION of include/nirgan_b200.h this binding was written against
 
 
 class ConvArgs(C.Structure):
@@ -51,6 +51,7 @@ _SIGNATURES = {
     "ng_stem_conv": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "ng_stem_conv_stat_slots": (c_i32, [c_i32, c_i32, c_i32]),
     "ng_unpack_weight_grad_rowmerged": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_f32, c_vp, c_vp]),
+    "ng_head_conv": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ng_tap_gather": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "ng_tap_scatter": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_vp, c_i32, c_vp,
                                c_vp]),

@@ -34,6 +34,8 @@ FUSED_FINALIZE = [_os.environ.get("NIRGAN_B200_FUSED_FINALIZE", "0") == "1"]
 # 64-bit fixed-point accumulators with integer atomics and the apply kernel derives (mean, rstd) from them itself, so a
 # normalised unit is two launches (conv, apply) and the plan starts with ONE memset of all its accumulators.
 # NIRGAN_B200_STAT_ACC=0: per-tile fp32 partials + an ng_in_stats_finalize launch per unit (round-1 form).
+# Conv2d(64 -> 1, k7) + Tanh head as one kernel (ng_head_conv); NIRGAN_B200_HEAD_FUSED=0 keeps the tap GEMM + gather pair
+HEAD_FUSED = [_os.environ.get("NIRGAN_B200_HEAD_FUSED", "1") != "0"]
 STAT_ACC = [_os.environ.get("NIRGAN_B200_STAT_ACC", "1") != "0"]
 
 
@@ -220,15 +222,20 @@ class UnitGraph:
             x, head = th["x"], th["conv"]
             K = head.weight.shape[-1]
             Hz, Wz = x.H + 2 * x.pad, x.W + 2 * x.pad
-            xz = ActBuf(x.t, x.B, Hz, Wz, x.C, 0)
-            z = eng.act(self.tag + ".z", x.B, Hz, Wz, 64, 0)
             out = eng.buffers.get(self.tag + ".head.out", x.B * th["H"] * th["W"], torch.float32)
             wt = eng.packed_weight(head.weight, "taps", 64, x.C, self.stream)
-            a = eng.conv_args(xz, wt, z.t, 64, 1, 1, 0, Hz, Wz)
-            plan.keepalive.append(a)
-            plan.add("ng_conv2d", C.byref(a), label=self.tag + ".head.gemm")
-            plan.add("ng_tap_gather", z.t.data_ptr(), eng.dt_enum, x.B, Hz, Wz, 64, K, K, head.bias.data_ptr(),
-                     L.ACT_TANH, th["crop"], out.data_ptr(), label=self.tag + ".head.gather")
+            if HEAD_FUSED[0] and eng.impl == L.IMPL_TC and eng.dt_enum != L.F32 and K == 7 and x.C == 64 and x.pad == 3:
+                # one kernel: the z tile of an 8 x 16 output patch stays in TMEM / shared memory (ng_head_conv)
+                plan.add("ng_head_conv", x.t.data_ptr(), eng.dt_enum, x.B, x.H, x.W, wt.data_ptr(), head.bias.data_ptr(),
+                         L.ACT_TANH, th["crop"], out.data_ptr(), label=self.tag + ".head")
+            else:
+                xz = ActBuf(x.t, x.B, Hz, Wz, x.C, 0)
+                z = eng.act(self.tag + ".z", x.B, Hz, Wz, 64, 0)
+                a = eng.conv_args(xz, wt, z.t, 64, 1, 1, 0, Hz, Wz)
+                plan.keepalive.append(a)
+                plan.add("ng_conv2d", C.byref(a), label=self.tag + ".head.gemm")
+                plan.add("ng_tap_gather", z.t.data_ptr(), eng.dt_enum, x.B, Hz, Wz, 64, K, K, head.bias.data_ptr(),
+                         L.ACT_TANH, th["crop"], out.data_ptr(), label=self.tag + ".head.gather")
             th["out"] = out
             plan.records["out"] = out
         return plan

@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/nirgan_b200.h but not exported"
     assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
-    assert lib.ng_version() == 101
+    assert lib.ng_version() == 102
 
 
 def test_conv_args_struct_layout_matches_header():

@@ -296,6 +296,41 @@ def test_head_tap_gemm_and_gather(impl, dtype, crop, H):
 
 
 @pytest.mark.parametrize("dtype_name", ["f16", "bf16"])
+@pytest.mark.parametrize("crop,H,W,B", [(0, 32, 32, 2), (10, 44, 44, 2), (10, 37, 61, 3), (0, 8, 16, 1), (10, 276, 276, 2),
+                                        (3, 150, 40, 5)])
+def test_head_fused_kernel(dtype_name, crop, H, W, B):
+    """ng_head_conv (haloed patch by TMA, tap GEMM of the whole patch on tcgen05, 49-tap gather from the shared z tile) ==
+    ReflectionPad2d(3) + Conv2d(64 -> 1, k7) + Tanh with the wrapper's crop, incl. partially covered 8 x 16 patches, more
+    tiles than CTAs (both epilogue groups, both accumulators, stage reuse), and launch-to-launch bit-exactness."""
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    dtype = L.F16 if dtype_name == "f16" else L.BF16
+    Cin = 64
+    x = Hh.rnd(_gen(B, Cin, H, W, seed=5), dtype)
+    w = Hh.rnd(_gen(1, Cin, 7, 7, seed=6, scale=0.02), dtype)
+    bias = _gen(1, seed=7, scale=0.1)
+    xb = Hh.to_actbuf(x, 3, "reflect", dtype)
+    wt = torch.zeros(64 * 64, dtype=Hh.TORCH_DT[dtype], device="cuda")
+    L.call("ng_pack_weight", w.data_ptr(), 1, Cin, 7, 7, 0, 1, 64, dtype, wt.data_ptr(), Hh.stream())
+    Hc, Wc = H - 2 * crop, W - 2 * crop
+    outs = []
+    for _ in range(2):
+        out = torch.full((B * Hc * Wc,), float("nan"), device="cuda")
+        L.call("ng_head_conv", xb.t.data_ptr(), dtype, B, H, W, wt.data_ptr(), bias.data_ptr(), L.ACT_TANH, crop,
+               out.data_ptr(), Hh.stream())
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    ref = torch.tanh(F.conv2d(F.pad(x, (3,) * 4, mode="reflect"), w, bias))
+    if crop:
+        ref = ref[..., crop:-crop, crop:-crop]
+    got = outs[0].view(B, 1, Hc, Wc)
+    assert torch.isfinite(got).all()
+    # 49 partial sums of magnitude ~0.2 rounded to 16 bits before the fp32 sum (as in the tap GEMM + gather pair)
+    assert float((got - ref).abs().max()) <= (1.5e-3 if dtype == L.F16 else 1.2e-2)
+
+
+@pytest.mark.parametrize("dtype_name", ["f16", "bf16"])
 @pytest.mark.parametrize("cin,wrap,H,W,B", [(3, 0, 32, 32, 2), (3, 10, 24, 36, 2), (3, 0, 50, 70, 3), (4, 10, 44, 44, 1),
                                             (3, 10, 256, 256, 2)])
 def test_stem_direct_from_fp32_tiles(dtype_name, cin, wrap, H, W, B):
