@@ -22,10 +22,13 @@ constexpr int HD_ROWS = HD_PH * HD_PW;                                   // 308 
 constexpr int HD_CHUNKS = (HD_ROWS + 127) / 128;                         // 3 row chunks of 128
 constexpr int HD_C = 64;                                                 // input channels = K of the GEMM
 constexpr int HD_TAPS = 64;                                              // 49 taps stored as 64
-constexpr int HD_A_BYTES = HD_CHUNKS * 128 * HD_C * 2;                   // 49152 per stage (rows >= 308 never read back)
+// A stage holds the 308 patch rows (39 KB, whole 1024-byte swizzle atoms).  The third row chunk's MMA reads 76 rows past
+// them -- into the next stage / the weights, readable shared memory whose products land in TMEM lanes nobody drains --
+// which is what lets a third stage fit: with two, the kernel was bound by the TMA round trip per pair of tiles.
+constexpr int HD_A_BYTES = (HD_ROWS * HD_C * 2 + 1023) / 1024 * 1024;    // 39936 per stage
 constexpr int HD_BOX_BYTES = HD_ROWS * HD_C * 2;                         // 39424 arrive per tile
 constexpr int HD_W_BYTES = HD_TAPS * HD_C * 2;                           // 8192
-constexpr int HD_STAGES = 2;
+constexpr int HD_STAGES = 3;
 constexpr int HD_ZPITCH = 132;                                           // bytes per z row: 33 words, odd -> conflict-free
 constexpr int HD_Z_BYTES = (HD_ROWS * HD_ZPITCH + 127) / 128 * 128;
 constexpr int HD_GROUPS = 2;
