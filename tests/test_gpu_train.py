@@ -584,7 +584,7 @@ def test_fp16_gradients_without_the_l1_sign_effect():
 @pytest.mark.slow
 def test_config4_full_size_step_vs_oracle():
     """BASELINE.json configs[3] at its full size (batch 32, 256x256, all loss terms) against the CPU oracle: loss_D,
-    loss_G, the prediction and three gradients (~1 min of host time for the oracle).  rgb ~ U[0.7,1): with rgb ~ U[0,1)
+    loss_G, the prediction and three gradients (~1 min of host time for the oracle).  rgb ~ 1 + U[0,1): with rgb ~ U[0,1)
     and a random-init generator (pred ~ tanh of small numbers, either sign) the NDVI / NDWI denominators pred + band + eps
     cross zero at thousands of pixels, loss_G and its gradient are dominated by those poles and even two fp32 evaluations
     disagree (measured: loss_G 78.8 vs 76.8, gradient cosine -0.33 with identical loss_D / pred / D gradients); that input
@@ -593,7 +593,7 @@ def test_config4_full_size_step_vs_oracle():
     sd_g = O.random_state_dict(O.generator_param_shapes(), seed=71)
     sd_d = O.random_state_dict(O.discriminator_param_shapes(), seed=72)
     gen = torch.Generator().manual_seed(12)
-    rgb = 0.7 + 0.3 * torch.rand(32, 3, 256, 256, generator=gen)
+    rgb = 1.0 + torch.rand(32, 3, 256, 256, generator=gen)
     nir = torch.rand(32, 1, 256, 256, generator=gen)
     torch.set_num_threads(max(1, (__import__("os").cpu_count() or 1)))
     tr = O.OracleTrainer(sd_g, sd_d)
@@ -624,7 +624,10 @@ def test_config4_full_size_step_vs_oracle():
     _record("config4_full_size_parity.json", rep)
     assert abs(rep["loss_D"][0] - rep["loss_D"][1]) <= 2e-2 * max(1.0, abs(rep["loss_D"][1]))
     assert abs(rep["loss_G"][0] - rep["loss_G"][1]) <= 3e-2 * abs(rep["loss_G"][1])
-    assert rep["pred_max_abs"] <= 2e-2 and rep["pred_mean_abs"] <= 2e-3
+    # inputs at 3x the nominal [0, 1) scale on purpose (see above; U[0.7, 1) still crosses the poles: loss_G 85.3 vs 77.3):
+    # the prediction tolerance scales with them.  The nominal-domain bound (2e-2 / 2e-3) is asserted on U[0, 1) tiles at
+    # full size by test_config3_full_size_512px_tiles (tests/test_gpu_models.py).
+    assert rep["pred_max_abs"] <= 4e-2 and rep["pred_mean_abs"] <= 4e-3
     assert rep["gD.model.8.weight"][0] >= 0.99 and rep["gD.model.8.weight"][1] <= 0.15
     for k in ("gG.model.26.weight", "gG.model.10.conv_block.1.weight"):
         assert rep[k][0] >= 0.97 and rep[k][1] <= 0.25, rep
