@@ -36,6 +36,8 @@ struct WgParams {
   // dY tile of a pipeline stage is loaded once per group instead of once per tap
   int ngroups;
   unsigned char grp_first[64], grp_cnt[64];
+  int tap_stride;             // tap index distance between the taps of a group (1; 3 = the kh taps of one kw of a 3x3)
+  int k_tiles;                // BN-wide input-channel tiles per tap (1 unless BN < Cin)
 };
 
 // NT = taps handled per pipeline stage ("tap group", NT*BN <= 512 TMEM columns): work unit = (split, tap group, n tile); a
@@ -48,6 +50,10 @@ struct WgParams {
 // channels): the X operand of a stage is ONE haloed patch of (8 + NT - 1) rows x 8 pixels and tap t's operand is the
 // 64-pixel window that starts t rows (t x 1024 bytes = whole swizzle atoms) into it -- 14 KB per stage instead of
 // NT x 8 KB, which is what bounded this layer (L2 -> shared-memory traffic).
+// RP with BN = 128, NT = 3 serves the stride-1 3x3 convolutions with 128 / 256 input channels (the 18 ResnetBlock
+// convolutions): a group is the three kh taps of one kw (tap stride 3), the X operand two 64-channel slabs of the haloed
+// 10 x 8 pixel patch (20 KB for three taps instead of 3 x 16 KB), the input channels go in k tiles of 128.  Per stage
+// 36 KB feed 3 x 128x128x64 MACs = 87 MAC/B, against 44 MAC/B for the one-tap 128 x 256 unit that was L2 -> SM bound.
 constexpr int RP_BW = 8, RP_BH = 8;
 
 template <int BN, int NT, bool RP = false>
@@ -55,7 +61,8 @@ struct WgCfg {
   static constexpr int A_BYTES = 2 * WG_SLAB;
   // X operand of one tap: BN/64 slabs of [64 px][128 B] (128-byte swizzle), or for BN == 16 one slab of [64 px][32 B]
   static constexpr int B_TAP_BYTES = BN >= 64 ? (BN / 64) * WG_SLAB : WG_PIXELS * 32;
-  static constexpr int B_BYTES = RP ? (RP_BH + NT - 1) * RP_BW * 128 : NT * B_TAP_BYTES;
+  static constexpr int RP_SLAB = (RP_BH + NT - 1) * RP_BW * 128;   // one 64-channel slab of the haloed row patch
+  static constexpr int B_BYTES = RP ? (BN / 64) * RP_SLAB : NT * B_TAP_BYTES;
   static constexpr int B_LOADS = BN >= 64 ? BN / 64 : 1;
   static constexpr int B_KSTEP = BN >= 64 ? 2048 : 512;            // bytes per 16 pixel rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX,
                 const __grid_constant__ WgParams p) {
   using Cfg = WgCfg<BN, NT, RP>;
-  static_assert(!RP || BN == 64, "row-patch variant: 64 stored input channels");
+  static_assert(!RP || BN == 64 || BN == 128, "row-patch variant: one or two 64-channel slabs");
   constexpr int NACC = Cfg::NACC;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -106,10 +113,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int per_split = p.ngroups * p.n_tiles;
-  auto decode = [&](int u, int& split, int& tap, int& cnt, int& nt, int& pt0, int& pt1) {
+  const int per_split = p.ngroups * p.n_tiles * p.k_tiles;
+  auto decode = [&](int u, int& split, int& tap, int& cnt, int& nt, int& kt, int& pt0, int& pt1) {
     split = u / per_split;
-    const int r = u - split * per_split;
+    int r = u - split * per_split;
+    kt = r % p.k_tiles;                     // input-channel tile (BN channels)
+    r /= p.k_tiles;
     const int grp = r / p.n_tiles;
     tap = p.grp_first[grp];                 // first tap of the group
     cnt = p.grp_cnt[grp];                   // taps walked inside the unit (<= NT)
@@ -123,8 +132,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-        int split, tap, cnt, nt, pt0, pt1;
-        decode(u, split, tap, cnt, nt, pt0, pt1);
+        int split, tap, cnt, nt, kt, pt0, pt1;
+        decode(u, split, tap, cnt, nt, kt, pt0, pt1);
         int ph = 0;
         while (tap >= g.phase_tap0[ph + 1]) ++ph;
         const int oy0 = g.phase_oy[ph], ox0 = g.phase_ox[ph];
@@ -144,13 +153,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
             tma_load_4d(&tmY, fb, sa + j * WG_SLAB, nt * 128 + 64 * j, g.OS * vj0 + ox0, g.OS * vi0 + oy0, n);
           if constexpr (RP) {
             // one haloed patch: rows vi0 + dy0 .. vi0 + dy0 + 8 + NT - 2 (tmX's box is that tall), 8 pixels wide
-            tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES, 0, vj0 + g.taps[tap].dx, vi0 + g.taps[tap].dy, n);
+#pragma unroll
+            for (int j = 0; j < Cfg::B_LOADS; ++j)
+              tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + j * Cfg::RP_SLAB, kt * BN + 64 * j, vj0 + g.taps[tap].dx,
+                          vi0 + g.taps[tap].dy, n);
           } else {
 #pragma unroll 1
             for (int t = 0; t < cnt; ++t)
 #pragma unroll
               for (int j = 0; j < Cfg::B_LOADS; ++j)
-                tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES + j * WG_SLAB, 64 * j,
+                tma_load_4d(&tmX, fb, sa + Cfg::A_BYTES + t * Cfg::B_TAP_BYTES + j * WG_SLAB, kt * BN + 64 * j,
                             g.S * vj0 + g.taps[tap + t].dx, g.S * vi0 + g.taps[tap + t].dy, n);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -166,8 +178,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
                              (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       uint32_t stage = 0, phase = 0, as = 0, as_phase = 0;
       for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-        int split, tap, cnt, nt, pt0, pt1;
-        decode(u, split, tap, cnt, nt, pt0, pt1);
+        int split, tap, cnt, nt, kt, pt0, pt1;
+        decode(u, split, tap, cnt, nt, kt, pt0, pt1);
         const int kiters = pt1 - pt0;
         mbar_wait(smem_u32(&tempty_bar[as]), as_phase ^ 1);
         tc_fence_after();
@@ -181,7 +193,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
           for (int t = 0; t < cnt; ++t) {
             // RP: tap t = the patch t rows (t * 8 pixels * 128 B = t swizzle atoms) further down
             const uint32_t sb = sa + Cfg::A_BYTES + t * (RP ? RP_BW * 128 : Cfg::B_TAP_BYTES);
-            const uint64_t bdesc = BN >= 64 ? make_mnmajor_desc(sb, WG_SLAB, 1024) : make_mnmajor_desc_sw32(sb, 256);
+            const uint64_t bdesc = BN >= 64 ? make_mnmajor_desc(sb, RP ? Cfg::RP_SLAB : WG_SLAB, 1024)
+                                            : make_mnmajor_desc_sw32(sb, 256);
 #pragma unroll
             for (int k = 0; k < WG_PIXELS / 16; ++k)     // 16 pixel rows per K step
               umma_f16(tmem_c + t * BN, adesc + (uint64_t)(k * (2048 >> 4)), bdesc + (uint64_t)(k * (Cfg::B_KSTEP >> 4)),
@@ -201,8 +214,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
     const int row = q * 32 + lane;
     uint32_t as = 0, as_phase = 0;
     for (int u = blockIdx.x; u < p.total_units; u += gridDim.x) {
-      int split, tap, cnt, nt, pt0, pt1;
-      decode(u, split, tap, cnt, nt, pt0, pt1);
+      int split, tap, cnt, nt, kt, pt0, pt1;
+      decode(u, split, tap, cnt, nt, kt, pt0, pt1);
       const int n = nt * 128 + row;
       mbar_wait(smem_u32(&tfull_bar[as]), as_phase);
       tc_fence_after();
@@ -210,8 +223,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__
       for (int t = 0; t < cnt; ++t) {
         const uint32_t taddr = tmem_base + as * (NT * BN) + t * BN + ((uint32_t)(q * 32) << 16);
         // packed weight-gradient row of this tap: wrow = (kh*KW + kw) * Cout (phased geometries enumerate taps by phase)
-        const int tp = tap + t;
-        float* dst = p.partials + ((size_t)split * g.ntaps * g.Cout + g.taps[tp].wrow + (n < g.Cout ? n : 0)) * (size_t)g.Cin;
+        const int tp = tap + t * p.tap_stride;
+        float* dst = p.partials + ((size_t)split * g.ntaps * g.Cout + g.taps[tp].wrow + (n < g.Cout ? n : 0)) * (size_t)g.Cin +
+                     kt * BN;
         if constexpr (BN >= 32) {
 #pragma unroll 1
           for (int c = 0; c < BN / 32; ++c) {
@@ -320,7 +334,21 @@ static bool row_patch_ok(const ConvGeom& g) {
   return g.VW >= RP_BW && g.VH >= RP_BH;
 }
 
+// stride-1 3x3 with 128 / 256 input channels, taps enumerated kh-major with unit offsets: the row-patch form over
+// (kw group) x (three kh taps)
+static bool row_patch3_ok(const ConvGeom& g) {
+  static const bool on = [] { const char* e = getenv("NIRGAN_B200_WGRAD_ROWPATCH3"); return !(e && e[0] == '0'); }();
+  if (!on || g.nphase != 1 || g.ntaps != 9 || g.S != 1 || g.OS != 1 || (g.Cin != 128 && g.Cin != 256)) return false;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw) {
+      const int t = kh * 3 + kw;
+      if (g.taps[t].dy != g.taps[0].dy + kh || g.taps[t].dx != g.taps[0].dx + kw) return false;
+    }
+  return g.VW >= RP_BW && g.VH >= RP_BH;
+}
+
 struct WgPlan {
+  int tap_stride, k_tiles;
   int BH, BW, patches_y, patches_x, P, n_tiles, splits, pps, bn;
   int nt;       // taps per stage (compile-time group capacity)
   int ngroups;
@@ -358,23 +386,32 @@ static void wgrad_plan(const ng_conv_args& a, const ConvGeom& g, WgPlan& w) {
     const long long tiles = (long long)((g.VH + bh - 1) / bh) * ((g.VW + bw - 1) / bw);
     if (best < 0 || tiles < best) { best = tiles; w.BH = bh; w.BW = bw; }
   }
-  if (row_patch_ok(g)) { w.BH = RP_BH; w.BW = RP_BW; }
+  const bool rp3 = row_patch3_ok(g);
+  if (row_patch_ok(g) || rp3) { w.BH = RP_BH; w.BW = RP_BW; }
   w.patches_y = (g.VH + w.BH - 1) / w.BH;
   w.patches_x = (g.VW + w.BW - 1) / w.BW;
   w.P = g.B * w.patches_y * w.patches_x;
   w.n_tiles = (g.Cout + 127) / 128;
   w.bn = g.Cin;
   w.nt = taps_per_group(g);
+  w.tap_stride = 1; w.k_tiles = 1;
   // groups of up to nt consecutive taps that share an output phase (the dY box position depends on the phase)
   w.ngroups = 0;
-  for (int ph = 0; ph < g.nphase; ++ph)
-    for (int t = g.phase_tap0[ph]; t < g.phase_tap0[ph + 1]; t += w.nt) {
-      const int left = g.phase_tap0[ph + 1] - t;
-      w.grp_first[w.ngroups] = (unsigned char)t;
-      w.grp_cnt[w.ngroups] = (unsigned char)(left < w.nt ? left : w.nt);
-      ++w.ngroups;
-    }
-  const int base = w.ngroups * w.n_tiles, sms = num_sms();
+  if (rp3) {
+    // group kw = taps kw, kw + 3, kw + 6 (the three row shifts of one haloed patch); input channels in tiles of 128
+    w.nt = 3; w.tap_stride = 3; w.bn = 128; w.k_tiles = g.Cin / 128;
+    for (int kw = 0; kw < 3; ++kw) { w.grp_first[kw] = (unsigned char)kw; w.grp_cnt[kw] = 3; }
+    w.ngroups = 3;
+  } else {
+    for (int ph = 0; ph < g.nphase; ++ph)
+      for (int t = g.phase_tap0[ph]; t < g.phase_tap0[ph + 1]; t += w.nt) {
+        const int left = g.phase_tap0[ph + 1] - t;
+        w.grp_first[w.ngroups] = (unsigned char)t;
+        w.grp_cnt[w.ngroups] = (unsigned char)(left < w.nt ? left : w.nt);
+        ++w.ngroups;
+      }
+  }
+  const int base = w.ngroups * w.n_tiles * w.k_tiles, sms = num_sms();
   int best_s = 1; double best_eff = -1.0;
   int max_s = 4 * sms / base;                   // enough splits to fill the GPU even for a single-tap, single-tile problem
   if (max_s < 64) max_s = 64;
@@ -410,7 +447,8 @@ static int launch_wgrad_tc(const ng_conv_args& a, const ConvGeom& g, const WgPla
   p.ngroups = w.ngroups;
   memcpy(p.grp_first, w.grp_first, sizeof(p.grp_first));
   memcpy(p.grp_cnt, w.grp_cnt, sizeof(p.grp_cnt));
-  p.total_units = w.splits * w.ngroups * w.n_tiles;
+  p.tap_stride = w.tap_stride; p.k_tiles = w.k_tiles;
+  p.total_units = w.splits * w.ngroups * w.n_tiles * w.k_tiles;
   p.bf16 = a.dtype == NG_BF16;
   p.partials = w.splits == 1 ? dw : reinterpret_cast<float*>(workspace);
 
@@ -481,6 +519,7 @@ int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspac
                  ((uintptr_t)workspace & 15) == 0,
              NG_E_ALIGN, "wgrad_tc: tensors must be 16-byte aligned");
   *handled = true;
+  if (w.tap_stride == 3) return launch_wgrad_tc<128, 3, true>(a, g, w, dw, workspace, st);
   if (w.nt == 16 && g.Cin == 16) return launch_wgrad_tc<16, 16>(a, g, w, dw, workspace, st);
   if (w.nt == 7 && g.Cin == 64 && row_patch_ok(g) && w.BW == RP_BW && w.BH == RP_BH)
     return launch_wgrad_tc<64, 7, true>(a, g, w, dw, workspace, st);

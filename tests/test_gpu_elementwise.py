@@ -268,7 +268,8 @@ def test_wgrad_matches_autograd(kind):
 # (Cout 512 -> four n tiles), Cout 64 (upper half of the 128-row tile is out-of-bounds zero fill), an image smaller
 # than one 64-pixel patch, and a batch large enough for several pixel splits.
 @pytest.mark.parametrize("dt", ["f16", "bf16"])
-@pytest.mark.parametrize("kind", ["res", "res69", "down", "down128", "convT", "convT256", "dk4s2", "dk4s1", "tiny", "l0"])
+@pytest.mark.parametrize("kind", ["res", "res69", "res128", "down", "down128", "convT", "convT256", "dk4s2", "dk4s1", "tiny",
+                                  "l0"])
 def test_wgrad_tc_matches_autograd(kind, dt):
     import ctypes as C
     from nirgan_b200 import _lib as L
@@ -278,7 +279,8 @@ def test_wgrad_tc_matches_autograd(kind, dt):
     B = 2
     cfgs = {
         "res": (256, 256, 3, 1, 1, 16, "reflect", L.FORM_GATHER),
-        "res69": (256, 256, 3, 1, 1, 69, "reflect", L.FORM_GATHER),
+        "res69": (256, 256, 3, 1, 1, 69, "reflect", L.FORM_GATHER),      # row-patch form, ragged 8 x 8 patches, 3 images
+        "res128": (128, 128, 3, 1, 1, 20, "zero", L.FORM_GATHER),        # row-patch form, one k tile, zero padding
         "down": (64, 128, 3, 2, 1, 36, "zero", L.FORM_GATHER),
         "down128": (128, 256, 3, 2, 1, 34, "zero", L.FORM_GATHER),
         "convT": (128, 64, 3, 2, 1, 17, "zero", L.FORM_PHASED),
