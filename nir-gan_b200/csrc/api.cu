@@ -3,7 +3,9 @@
 
 namespace ng {
 int conv_simt(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st);
-int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, cudaStream_t st);
+int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspace, long long workspace_bytes,
+               cudaStream_t st);
+long long wgrad_simt_workspace_bytes(const ng_conv_args& a, const ConvGeom& g);
 int bias_grad(const ng_conv_args& a, const ConvGeom& g, float* dbias, cudaStream_t st);
 int wgrad_tc(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspace, long long workspace_bytes,
              cudaStream_t st, bool* handled);
@@ -57,8 +59,10 @@ extern "C" int64_t ng_conv2d_wgrad_workspace_bytes(const ng_conv_args* a) {
   ConvGeom g;
   int r = build_geometry(*a, g);
   if (r) return r;
-  if (a->impl != NG_IMPL_TC) return 0;
-  return wgrad_tc_workspace_bytes(*a, g);
+  const long long simt = wgrad_simt_workspace_bytes(*a, g);      // single-output-channel layers (either impl)
+  if (a->impl != NG_IMPL_TC) return simt;
+  const long long tc = wgrad_tc_workspace_bytes(*a, g);
+  return tc > simt ? tc : simt;
 }
 
 extern "C" int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* dbias, void* workspace,
@@ -78,7 +82,7 @@ extern "C" int ng_conv2d_wgrad(const ng_conv_args* a, float* dw_packed, float* d
     if (r) return r;
   }
   if (!handled) {
-    r = wgrad_simt(*a, g, dw_packed, (cudaStream_t)stream);
+    r = wgrad_simt(*a, g, dw_packed, workspace, workspace_bytes, (cudaStream_t)stream);
     if (r) return r;
   }
   if (dbias) return bias_grad(*a, g, dbias, (cudaStream_t)stream);

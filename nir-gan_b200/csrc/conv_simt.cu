@@ -310,8 +310,146 @@ colsum_vec_kernel(const T* __restrict__ dy, long long rows, int C, float* __rest
   }
 }
 
+// Same gradient with every input pixel read ONCE (the kernel above walks the 71 MB activation once per tap: 16 times
+// for the 4x4 PatchGAN layer, 0.34 ms).  Stride-1 geometries: the block walks a contiguous range of positions of the
+// haloed input buffer; thread (cg, pl) keeps all ntaps x 8 accumulators of its channel group in registers and, per input
+// position, multiplies its 8 channels by the <= 16 output gradients that reach it (dy[n][by - dy_t][bx - dx_t], an L1 hit
+// shared by the 64 channel groups).  Per-block partials go to the workspace and a second kernel adds them in block order:
+// deterministic, no atomics.
+constexpr int WG1_TAPS = 16, WG1_TPT = 8;            // taps supported / taps per thread (two thread halves share a position)
 template <typename T>
-static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, cudaStream_t st) {
+__global__ void __launch_bounds__(512, 1)
+wgrad_cout1_once_kernel(const __grid_constant__ ConvGeom g, const T* __restrict__ x, const T* __restrict__ dy,
+                        float* __restrict__ partial, int pos_per_block) {
+  static_assert(sizeof(T) == 2, "16-bit storage only");
+  __shared__ float red[512 * 8];
+  const int C8 = g.Cin >> 3, lanes = 256 / C8;
+  const int half = threadIdx.x >> 8, tl = threadIdx.x & 255;         // taps [8 * half, 8 * half + 8)
+  const int cg = tl % C8, pl = tl / C8;
+  const unsigned npos = (unsigned)g.B * g.Hb * g.Wb;
+  const unsigned q0 = blockIdx.x * (unsigned)pos_per_block, q1 = min(npos, q0 + (unsigned)pos_per_block);
+  float acc[WG1_TPT][8];
+  int tdy[WG1_TPT], tdx[WG1_TPT];
+#pragma unroll
+  for (int t = 0; t < WG1_TPT; ++t) {
+    const int tp = half * WG1_TPT + t;
+    // a tap beyond ntaps gets an offset no position can satisfy
+    tdy[t] = tp < g.ntaps ? g.taps[tp].dy : (1 << 20);
+    tdx[t] = tp < g.ntaps ? g.taps[tp].dx : (1 << 20);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[t][k] = 0.f;
+  }
+  const unsigned per_img = (unsigned)g.Hb * g.Wb;
+  unsigned q = q0 + pl;
+  uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+  if (q < q1) raw = *reinterpret_cast<const uint4*>(x + (size_t)q * g.Cin + cg * 8);
+  while (q < q1) {
+    const unsigned qn = q + lanes;
+    uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (qn < q1) nxt = *reinterpret_cast<const uint4*>(x + (size_t)qn * g.Cin + cg * 8);     // next position's load in flight
+    const int n = (int)(q / per_img);
+    const unsigned r = q - (unsigned)n * per_img;
+    const int by = (int)(r / (unsigned)g.Wb), bx = (int)(r - (unsigned)by * g.Wb);
+    const T* dyn = dy + (size_t)n * g.Hout * g.Wout * g.Cout;
+    float d[WG1_TPT];
+#pragma unroll
+    for (int t = 0; t < WG1_TPT; ++t) {                    // the gradients that reach this position: loads first
+      const int vi = by - tdy[t], vj = bx - tdx[t];
+      d[t] = 0.f;
+      if ((unsigned)vi < (unsigned)g.Hout && (unsigned)vj < (unsigned)g.Wout)
+        d[t] = to_f32<T>(dyn[((size_t)vi * g.Wout + vj) * g.Cout]);
+    }
+    const float2 a0 = unpack2<T>(raw.x), a1 = unpack2<T>(raw.y), a2 = unpack2<T>(raw.z), a3 = unpack2<T>(raw.w);
+#pragma unroll
+    for (int t = 0; t < WG1_TPT; ++t) {
+      acc[t][0] = fmaf(d[t], a0.x, acc[t][0]); acc[t][1] = fmaf(d[t], a0.y, acc[t][1]);
+      acc[t][2] = fmaf(d[t], a1.x, acc[t][2]); acc[t][3] = fmaf(d[t], a1.y, acc[t][3]);
+      acc[t][4] = fmaf(d[t], a2.x, acc[t][4]); acc[t][5] = fmaf(d[t], a2.y, acc[t][5]);
+      acc[t][6] = fmaf(d[t], a3.x, acc[t][6]); acc[t][7] = fmaf(d[t], a3.y, acc[t][7]);
+    }
+    raw = nxt;
+    q = qn;
+  }
+  // per tap: sum the pixel lanes of each channel group in lane order, one partial row [tap][Cin] per block
+  float* dst = partial + (size_t)blockIdx.x * g.ntaps * g.Cin;
+#pragma unroll
+  for (int t = 0; t < WG1_TPT; ++t) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[k * 512 + threadIdx.x] = acc[t][k];
+    __syncthreads();
+    const int tp = half * WG1_TPT + t;
+    if (tp < g.ntaps) {
+      for (int o = tl; o < C8 * 8; o += 256) {
+        const int c = o >> 3, k = o & 7;
+        float v = 0.f;
+        for (int L = 0; L < lanes; ++L) v += red[k * 512 + half * 256 + L * C8 + c];
+        dst[(size_t)tp * g.Cin + o] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dw[taps[t].wrow][c] = sum over blocks (in block order) of partial[b][t][c]
+__global__ void __launch_bounds__(256)
+wgrad_cout1_reduce_kernel(const __grid_constant__ ConvGeom g, const float* __restrict__ partial, int blocks,
+                          float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.ntaps * g.Cin) return;
+  const int t = i / g.Cin, c = i - t * g.Cin;
+  const size_t stride = (size_t)g.ntaps * g.Cin;
+  float v = 0.f;
+  int b = 0;
+  for (; b + 4 <= blocks; b += 4) {
+    const float p0 = partial[(size_t)b * stride + i], p1 = partial[(size_t)(b + 1) * stride + i],
+                p2 = partial[(size_t)(b + 2) * stride + i], p3 = partial[(size_t)(b + 3) * stride + i];
+    v += p0; v += p1; v += p2; v += p3;
+  }
+  for (; b < blocks; ++b) v += partial[(size_t)b * stride + i];
+  dw[(size_t)g.taps[t].wrow * g.Cin + c] = v;
+}
+
+static bool wgrad_cout1_once_ok(const ng_conv_args& a, const ConvGeom& g, int* blocks, int* pos_per_block) {
+  static const bool on = [] { const char* e = getenv("NIRGAN_B200_WGRAD_COUT1_ONCE"); return !(e && e[0] == '0'); }();
+  const int c8 = g.Cin / 8;
+  if (!on || (a.dtype != NG_F16 && a.dtype != NG_BF16) || g.Cout > 16 || g.nphase != 1 || g.S != 1 || g.OS != 1 ||
+      g.ntaps > WG1_TAPS || g.Cin % 8 != 0 || c8 > 256 || 256 % c8 != 0)
+    return false;
+  const long long npos = (long long)g.B * g.Hb * g.Wb;
+  if (npos >= (1ll << 31)) return false;
+  const int lanes = 256 / c8;
+  long long nb = num_sms();
+  if (nb * lanes * 4 > npos) nb = (npos + lanes * 4 - 1) / (lanes * 4);     // at least four positions per lane
+  if (nb < 1) nb = 1;
+  const long long ppb = ((npos + nb - 1) / nb + lanes - 1) / lanes * lanes;
+  *pos_per_block = (int)ppb;
+  *blocks = (int)((npos + ppb - 1) / ppb);
+  return true;
+}
+
+long long wgrad_simt_workspace_bytes(const ng_conv_args& a, const ConvGeom& g) {
+  int blocks = 0, ppb = 0;
+  if (!wgrad_cout1_once_ok(a, g, &blocks, &ppb)) return 0;
+  return (long long)blocks * g.ntaps * g.Cin * (long long)sizeof(float);
+}
+
+template <typename T>
+static int launch_wgrad(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspace, long long workspace_bytes,
+                        cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    int blocks = 0, ppb = 0;
+    if (a.epilogue == NG_EPI_HEAD && wgrad_cout1_once_ok(a, g, &blocks, &ppb) && workspace != nullptr &&
+        workspace_bytes >= (long long)blocks * g.ntaps * g.Cin * (long long)sizeof(float)) {
+      // the packed gradient has stored Cout (16) rows per tap; only row 0 is real: clear, then write row 0 of every tap
+      int e = check_cuda(cudaMemsetAsync(dw, 0, (size_t)a.KH * a.KW * g.Cout * g.Cin * sizeof(float), st), "wgrad memset");
+      if (e) return e;
+      wgrad_cout1_once_kernel<T><<<blocks, 512, 0, st>>>(g, (const T*)a.x, (const T*)a.y, (float*)workspace, ppb);
+      NG_LAUNCH_CHECK("wgrad_cout1_once_kernel");
+      wgrad_cout1_reduce_kernel<<<(g.ntaps * g.Cin + 255) / 256, 256, 0, st>>>(g, (const float*)workspace, blocks, dw);
+      NG_LAUNCH_CHECK("wgrad_cout1_reduce_kernel");
+      return NG_OK;
+    }
+  }
   const int n_tiles = (g.Cout + 63) / 64, k_tiles = (g.Cin + 63) / 64;
   const long long npix = (long long)g.B * g.VH * g.VW;
   long long sp_ = npix / 2048; if (sp_ < 1) sp_ = 1; if (sp_ > 64) sp_ = 64;
@@ -378,11 +516,12 @@ int bias_grad(const ng_conv_args& a, const ConvGeom& g, float* dbias, cudaStream
   return NG_E_ARG;
 }
 
-int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, cudaStream_t st) {
+int wgrad_simt(const ng_conv_args& a, const ConvGeom& g, float* dw, void* workspace, long long workspace_bytes,
+               cudaStream_t st) {
   switch (a.dtype) {
-    case NG_F32:  return launch_wgrad<float>(a, g, dw, st);
-    case NG_F16:  return launch_wgrad<__half>(a, g, dw, st);
-    case NG_BF16: return launch_wgrad<__nv_bfloat16>(a, g, dw, st);
+    case NG_F32:  return launch_wgrad<float>(a, g, dw, workspace, workspace_bytes, st);
+    case NG_F16:  return launch_wgrad<__half>(a, g, dw, workspace, workspace_bytes, st);
+    case NG_BF16: return launch_wgrad<__nv_bfloat16>(a, g, dw, workspace, workspace_bytes, st);
   }
   set_error("wgrad_simt: bad dtype %d", a.dtype);
   return NG_E_ARG;

@@ -1123,7 +1123,11 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   NG_REQUIRE((long long)Ho * Wo < (1ll << 20) && Wo < (1 << 12), NG_E_SHAPE, "in_apply: image %dx%d too large", Ho, Wo);
   const unsigned long long wo_magic = ((1ull << 40) + (unsigned)Wo - 1) / (unsigned)Wo;   // exact for p < 2^20
   const int pstep = 256 / C8;                     // pixels per block per load
-  const int ppb = pstep * 16;                     // 16 sixteen-byte items per thread = 4 batches of UNROLL 4
+  // 16 sixteen-byte items per thread = 4 batches of UNROLL 4.  Tuning the multiplier for the wave efficiency of the grid
+  // (B = 32 ResnetBlock units: 1120 blocks = 2.52 waves at 3 blocks / SM -> 832 blocks = 1.87 waves) measured SLOWER
+  // end to end (r2z: 7639 vs 7813 tiles/s): these kernels run beside the other slice's persistent convolution, not alone.
+  const int mult = 16;
+  const int ppb = pstep * mult;
   dim3 grid((unsigned)((Ho * Wo + ppb - 1) / ppb), (unsigned)B);
   static const int apply_pf = [] { const char* e = getenv("NIRGAN_B200_APPLY_PREFETCH"); return e ? atoi(e) : 1; }();
   // lean kernel for the common case (see in_apply_fast_kernel); NIRGAN_B200_APPLY_FAST=0 keeps the generic one

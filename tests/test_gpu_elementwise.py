@@ -263,6 +263,50 @@ def test_wgrad_matches_autograd(kind):
     assert float((db[:Cout] - dy.sum(dim=(0, 2, 3))).abs().max()) <= 1e-3
 
 
+@pytest.mark.parametrize("dt", ["f16", "bf16"])
+@pytest.mark.parametrize("Cin,K,H,B", [(512, 4, 13, 2), (512, 4, 31, 5), (64, 3, 20, 3), (256, 4, 9, 1)])
+def test_wgrad_single_output_channel_reads_input_once(Cin, K, H, B, dt):
+    """Weight gradient of a stride-1 convolution with ONE real output channel (PatchGAN last layer: 512 -> 1, k4, p1) in
+    the single-read form -- every position of the haloed input buffer visited once, all taps accumulated in registers,
+    per-block partials reduced in block order -- against autograd on the same 16-bit-rounded operands; bit-identical
+    from launch to launch (no atomics)."""
+    import ctypes as C
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    dtype = L.F16 if dt == "f16" else L.BF16
+    tdt = torch.float16 if dt == "f16" else torch.bfloat16
+    p = 1
+    x = _gen(B, Cin, H, H, seed=11).to(tdt).float()
+    w = _gen(1, Cin, K, K, seed=12, scale=0.05).requires_grad_(True)
+    out = F.conv2d(F.pad(x, (p,) * 4), w)
+    Ho = out.shape[-1]
+    dy = _gen(*out.shape, seed=13).to(tdt).float()
+    out.backward(dy)
+    xb = Hh.to_actbuf(x, p, "zero", dtype)                       # halo materialised (zeros), as the PatchGAN buffers are
+    dyb = Hh.to_actbuf(dy, 0, "zero", dtype, c_pad=16)
+    a = L.ConvArgs()
+    a.dtype, a.impl, a.form, a.sgn = dtype, L.IMPL_TC, L.FORM_GATHER, 1
+    a.B, a.Hin, a.Win, a.Cin, a.in_pad, a.in_pad_w = B, H, H, Cin, xb.pad, xb.pad
+    a.Cout, a.KH, a.KW, a.stride, a.pad, a.pad_w, a.Hout, a.Wout = 16, K, K, 1, p, p, Ho, Ho
+    a.x, a.w, a.y = xb.t.data_ptr(), xb.t.data_ptr(), dyb.t.data_ptr()
+    a.epilogue = L.EPI_HEAD
+    need = int(L.load().ng_conv2d_wgrad_workspace_bytes(C.byref(a)))
+    assert need > 0                                              # the single-read form asks for its partial slots
+    ws = torch.full((need // 4,), float("nan"), device="cuda")
+    outs = []
+    for _ in range(2):
+        dwp = torch.full((K * K * 16 * Cin,), float("nan"), device="cuda")
+        L.call("ng_conv2d_wgrad", C.byref(a), dwp.data_ptr(), None, ws.data_ptr(), need, Hh.stream())
+        torch.cuda.synchronize()
+        outs.append(dwp)
+    assert torch.equal(outs[0], outs[1])
+    dw = torch.empty_like(w)
+    L.call("ng_unpack_weight_grad", outs[0].data_ptr(), 1, Cin, K, K, 0, 16, Cin, 1.0, None, 0.0, dw.data_ptr(), Hh.stream())
+    rel = float((dw - w.grad).norm() / w.grad.norm())
+    assert rel <= 1e-5, rel
+    assert float(outs[0].view(K * K, 16, Cin)[:, 1:].abs().max()) == 0.0       # padding rows of the packed gradient
+
+
 # tcgen05 split-K weight gradient (MN-major operands) against torch autograd on the same 16-bit-rounded operands.
 # Geometries: ResnetBlock 3x3 (reflect halo), strided down conv, ConvTranspose (phased), PatchGAN k4 s2 and k4 s1
 # (Cout 512 -> four n tiles), Cout 64 (upper half of the 128-row tile is out-of-bounds zero fill), an image smaller
