@@ -101,9 +101,9 @@ class UnitGraph:
         cin = u.x.C
         if self.merged_phases(u):
             return self.eng.packed_weight(u.conv.weight, "phasemerged", u.cout, cin, self.stream)
-        if u.pack == "rowmerged":
+        if u.pack == "rowmerged" and u.direct is None:
             return self.eng.packed_weight(u.conv.weight, "rowmerged", u.cout, 64, self.stream)
-        if u.pack == "rowmerged4":
+        if u.pack == "rowmerged4" or u.direct is not None:        # ng_stem_conv reads the 32-wide row-merged weights
             return self.eng.packed_weight(u.conv.weight, "rowmerged4", u.cout, 32, self.stream)
         if u.pack == "s2d":
             return self.eng.packed_weight(u.conv.weight, "s2d", u.cout, 64, self.stream)

@@ -154,7 +154,7 @@ class GeneratorRunner(_RunnerBase):
         return m[1], m[4], m[7], [m[10 + b] for b in range(nb)], m[10 + nb], m[13 + nb], m[17 + nb]
 
     def build_graph(self, eng: Engine, B: int, H: int, W: int, wrap: int, inject: bool, stream: int, tag: str,
-                    direct_head: bool, direct_stem: bool = False) -> UnitGraph:
+                    direct_head: bool, direct_stem: bool = False, keep_rowmerged: bool = False) -> UnitGraph:
         mod = self.module
         stem, d1, d2, blocks, u1, u2, head = self._convs()
         ngf, cin = stem.weight.shape[0], stem.weight.shape[1]
@@ -174,7 +174,16 @@ class GeneratorRunner(_RunnerBase):
         H2, W2 = conv_out(H1, 3, 2, 1), conv_out(W1, 3, 2, 1)
         H3, W3 = conv_out(H2, 3, 2, 1), conv_out(W2, 3, 2, 1)
         direct_stem = direct_stem and eng.impl == L.IMPL_TC and cin <= 4 and ngf == 64 and H1 >= 8 and W1 >= 16
-        if direct_stem:
+        if direct_stem and keep_rowmerged:
+            # training plans: the forward runs ng_stem_conv from the fp32 tiles as well (0.27 -> 0.18 ms per 32 tiles); the
+            # row-merged tensor is still written by ng_prep_stem because the stem's weight gradient contracts over it
+            x0 = ActBuf(eng.buffers.get(tag + ".x0", B * (H1 + 6) * W1 * 64, eng.dt_torch), B, H1, W1, 64, 3)
+            g.pre_ops.append(("ng_prep_stem", (src.data_ptr(), cin, B, H, W, wrap, 3, 7, eng.dt_enum, x0.t.data_ptr()),
+                              tag + ".prep"))
+            u = g.add(Unit("stem", stem, x0, ngf, 7, 1, 3, H1, W1, pack="rowmerged", KW=1, pad_w=0, in_pad_w=0,
+                           act=L.ACT_RELU, out_pad=0,
+                           direct={"src": src, "cin": cin, "H": H, "W": W, "wrap": wrap}))
+        elif direct_stem:
             # forward-only plans: ng_stem_conv builds the im2col tile in shared memory from the fp32 tiles (no row-merged
             # tensor in HBM; training plans keep it because the stem's weight gradient reads it)
             xd = ActBuf(src, B, H1, W1, 32, 3)            # shape-only description of the virtual row-merged input
@@ -443,7 +452,8 @@ class GeneratorRunner(_RunnerBase):
             tag = f"gt_{B}x{Cin}x{H}x{W}p{wrap_pad}{'i' if inject else ''}"
 
             def build():
-                g = self.build_graph(eng, B, H, W, wrap_pad, inject, stream, tag, direct_head=not self._use_tap_head())
+                g = self.build_graph(eng, B, H, W, wrap_pad, inject, stream, tag, direct_head=not self._use_tap_head(),
+                                     direct_stem=os.environ.get("NIRGAN_B200_STEM_DIRECT", "1") != "0", keep_rowmerged=True)
                 fwd = g.compile_forward()
                 if g.tap_head is None:
                     fwd.records["out"] = g.units[-1].out_f32
@@ -480,7 +490,8 @@ class GeneratorRunner(_RunnerBase):
             for part in range(2):
                 eng.buffers = SliceBuffers(saved, part, 2)
                 gh = self.build_graph(eng, B // 2, H, W, wrap_pad, inject, stream, tag,
-                                      direct_head=not self._use_tap_head())
+                                      direct_head=not self._use_tap_head(),
+                                      direct_stem=os.environ.get("NIRGAN_B200_STEM_DIRECT", "1") != "0", keep_rowmerged=True)
                 plans.append(gh.compile_forward())
                 plans[-1].keepalive.append(gh)
         except KeyError:
