@@ -551,7 +551,7 @@ def main():
         by_name.setdefault(name, []).append(op_ms[i])
     # dominant kernel: the 18 ResnetBlock 3x3 convs (256->256 at H/4): 4.832 GFLOP per tile per launch
     import re
-    conv_idx = [i for i, (fn, a, name) in enumerate(plan.ops) if name in ("ng_conv2d", "ng_stem_conv")]
+    conv_idx = [i for i, (fn, a, name) in enumerate(plan.ops) if name in ("ng_conv2d", "ng_stem_conv", "ng_head_conv")]
     res_idx = [i for i in conv_idx if re.search(r"\.r\d+[ab]$", plan.labels[i])]
     assert len(res_idx) == 18, [plan.labels[i] for i in conv_idx]
     Bc = plan.records["src"].numel() // (3 * TILE * TILE)      # tiles per plan run (batch slice)
@@ -665,7 +665,7 @@ def main():
         "roofline_hbm": {"bound": "hbm", "kernel": "in_apply_kernel (InstanceNorm + inject + act + residual + halo; all launches of a step)",
                          "achieved": hbm_achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_achieved / pk["hbm_gbs"],
                          "bytes_per_step_slice": ap_bytes, "ms_per_step_slice": ap_ms, "peak_source": pk["src"]},
-        "small_convs": {"kernels": "stem, down x2, up x2, head tap-GEMM (the non-ResnetBlock convolutions)",
+        "small_convs": {"kernels": "stem, down x2, up x2, fused head (the non-ResnetBlock convolutions)",
                         "ms_per_step_slice": small_ms,
                         "tflops": (gflop_tile - 18 * 4.832) * Bc / small_ms if small_ms > 0 else None},
         "model_tflops": value * gflop_tile / 1e3,

@@ -57,6 +57,7 @@ struct BwdArgs {
   int nblk1;                   // pass-1 blocks per image = partial-sum slots per image
   int n0;                      // first image of this launch (image-chunked launches: grid.y = images in the chunk)
   int pf_ahead;                // lean kernels: loop iterations of operands kept prefetched into L2 ahead of the loads (0 = off)
+  int reverse2;                // lean pass 2 walks images / pixel blocks in the reverse of pass 1's order (L2 reuse)
   unsigned long long w_magic;  // ceil(2^40 / W): p / W == (p * w_magic) >> 40 for p < 2^20
 };
 
@@ -357,11 +358,15 @@ in_bwd_fast_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, c
                    T* __restrict__ do_out) {
   static_assert(sizeof(T) == 2, "16-bit storage only");
   extern __shared__ float sm[];            // PASS 1: [4 accumulators][256 threads]
-  const int n = blockIdx.y + a.n0, C8 = a.C >> 3, C = a.C;
+  // pass 2 in the reverse of pass 1's dispatch order: what pass 1 read LAST (the final images of the batch) is what the L2
+  // still holds when pass 2 starts, so its first blocks re-read from the L2 instead of HBM
+  const bool rev = PASS == 2 && a.reverse2;
+  const int bx = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+  const int n = (rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y) + a.n0, C8 = a.C >> 3, C = a.C;
   const int c8 = threadIdx.x & (C8 - 1);
   const int pstep = 256 >> a.c8_shift;
   const int npix = a.H * a.W;
-  const int p_begin = blockIdx.x * a.ppb, p_end = min(npix, p_begin + a.ppb);
+  const int p_begin = bx * a.ppb, p_end = min(npix, p_begin + a.ppb);
   float sa[8], sb[8], k1[8], k2[8];        // xh = y * sa + sb ; dy = dxh * sa + xh * k2 + k1
   {
     const float4* m4 = reinterpret_cast<const float4*>(mr + ((size_t)n * C + c8 * 8) * 2);
@@ -1112,6 +1117,8 @@ extern "C" int ng_in_bwd(void* g_halo, int32_t g_pad, int32_t halo_mode, const v
   a.n0 = 0;
   static const int pf_ahead = [] { const char* e = getenv("NIRGAN_B200_BWD_PREFETCH"); return e ? atoi(e) : 3; }();
   a.pf_ahead = pf_ahead;
+  static const int reverse2 = [] { const char* e = getenv("NIRGAN_B200_BWD_REVERSE"); return e ? atoi(e) : 1; }();
+  a.reverse2 = reverse2;
   const int pstep = 256 / (C / 8);
   const bool need_pass1 = mean_rstd != nullptr || (inject_mode != NG_INJECT_NONE && (dscale || de_map));
   a.nblk1 = in_bwd_pass1_blocks(B, H, W, C);
