@@ -398,10 +398,10 @@ in_bwd_fast_kernel(const __grid_constant__ BwdArgs a, const T* __restrict__ g, c
   int pp = p_begin + (threadIdx.x >> a.c8_shift);
   int py = pp / a.W, px = pp - py * a.W;
   const int adv_y = pstep / a.W, adv_x = pstep - adv_y * a.W;
-  // The loads of an iteration cover pstep * UNROLL consecutive pixels of every operand.  One thread keeps the next
-  // `pf_ahead` iterations' bytes on their way from DRAM into the L2 (bulk prefetch: no registers, no shared memory), so
-  // the register-staged loads see L2 latency and the bytes a block can keep in flight stop being the bound -- without
-  // the shared-memory ring that would evict the co-resident tcgen05 CTA of the weight-gradient stream.
+  // The loads of an iteration cover pstep * UNROLL consecutive pixels of every operand.  Optionally (pf_ahead > 0) one
+  // thread keeps the next iterations' bytes on their way from DRAM into the L2 (bulk prefetch: no registers, no shared
+  // memory).  Measured: no gain here -- these kernels are bound by DRAM efficiency over ~600 concurrent streams, not by
+  // the latency of the individual loads (see the launcher).
   const int chunk_px = pstep * UNROLL;
   auto prefetch_chunk = [&](int p0) {
     if (p0 >= p_end) return;
@@ -720,9 +720,9 @@ in_bwd_stream_kernel(const __grid_constant__ BwdArgs a, const __grid_constant__ 
 // Geometry of the staged form; false when the shape does not fit it (the register-staged kernels serve those).
 static bool in_bwd_stream_geometry(int B, int H, int W, int C, int ntensors, BwdStream* out, bool sizing_only = false) {
   // opt-in (NIRGAN_B200_BWD_STREAM=1, read per call so that tests can switch it): in isolation the staged kernels reach
-  // 52-75 % of the HBM copy peak against 34-36 % (profiles/r2q_in_bwd_stream.md), but their ~200 KB shared-memory ring
-  // cannot sit beside a tcgen05 CTA of the weight-gradient stream, and the training step loses more from that lost
-  // overlap than the kernels gain (20.6 vs 19.4 ms per step, r2q).
+  // 52-77 % of the HBM copy peak (profiles/r2q_in_bwd_stream.md; the lean ones 47-79 % on the same units, r3g), but their
+  // ~200 KB shared-memory ring cannot sit beside a tcgen05 CTA of the weight-gradient stream, and the training step
+  // loses more from that lost overlap than the kernels gain (20.6 vs 19.4 ms per step, r2q).
   const char* env = getenv("NIRGAN_B200_BWD_STREAM");
   const bool on = sizing_only || (env && env[0] == '1');
   if (!on || C > 512 || C < 8) return false;
@@ -1041,18 +1041,21 @@ static void launch_in_bwd(const BwdArgs& a, dim3 grid, size_t smem, cudaStream_t
 // equal blocks at `resident` blocks per wave: the candidate with the best wave efficiency waves / ceil(waves) (the last,
 // partly filled wave of an HBM-bound kernel runs at a fraction of the bandwidth), longer blocks on ties.
 static int in_bwd_pick_mult(int B, int npix, int pstep, int lo, int hi) {
-  static const bool tune = [] { const char* e = getenv("NIRGAN_B200_BWD_TUNE"); return !(e && e[0] == '0'); }();
+  // NIRGAN_B200_BWD_TUNE: 0 = fixed block length, 1 (default) = whole waves only, 2 = a single, nearly full wave counts as
+  // filled too (blocks 4-5x longer, the per-block prologue / reduction paid once per SM slot): measured no difference
+  // (r3h: 4.17 vs 4.15 ms of norm backward per step)
+  static const int tune = [] { const char* e = getenv("NIRGAN_B200_BWD_TUNE"); return e ? atoi(e) : 1; }();
   const double resident = 2.0 * num_sms();             // 2 blocks / SM of the four-pixel kernels
   int best = lo;
   double best_eff = -1.0;
   for (int mult = hi; mult >= lo; --mult) {
     const long long blocks = (long long)B * ((npix + pstep * mult - 1) / (pstep * mult));
     const double waves = blocks / resident;
-    if (waves < 1.0 && mult > lo) continue;               // does not fill the GPU once: use shorter blocks
-    const double eff = waves / ceil(waves);
+    if (waves < (tune >= 2 ? 0.9 : 1.0) && mult > lo) continue;   // does not fill the GPU once: use shorter blocks
+    const double eff = waves <= 1.0 ? waves : waves / ceil(waves);
     if (eff > best_eff + 0.02) { best_eff = eff; best = mult; }
   }
-  if (!tune) return -1;
+  if (tune <= 0) return -1;
   return best;
 }
 
@@ -1115,7 +1118,9 @@ extern "C" int ng_in_bwd(void* g_halo, int32_t g_pad, int32_t halo_mode, const v
   while ((1 << a.c8_shift) < C / 8) ++a.c8_shift;
   a.w_magic = ((1ull << 40) + (unsigned)W - 1) / (unsigned)W;
   a.n0 = 0;
-  static const int pf_ahead = [] { const char* e = getenv("NIRGAN_B200_BWD_PREFETCH"); return e ? atoi(e) : 3; }();
+  // off by default: measured no effect on these kernels (r3f: 4.11 ms of norm backward per step without, 3.92-4.18 ms
+  // with 1-12 iterations ahead) while the DRAM reads grow by ~20 % (r3g); the apply kernels do gain from theirs
+  static const int pf_ahead = [] { const char* e = getenv("NIRGAN_B200_BWD_PREFETCH"); return e ? atoi(e) : 0; }();
   a.pf_ahead = pf_ahead;
   static const int reverse2 = [] { const char* e = getenv("NIRGAN_B200_BWD_REVERSE"); return e ? atoi(e) : 1; }();
   a.reverse2 = reverse2;
@@ -1180,7 +1185,7 @@ extern "C" int ng_in_bwd(void* g_halo, int32_t g_pad, int32_t halo_mode, const v
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
   }
-  const int mult2 = in_bwd_pick_mult(chunk, H * W, pstep, 4, 32);
+  const int mult2 = in_bwd_pick_mult(chunk, H * W, pstep, 4, 64);
   const int ppb2 = pstep * (mult2 < 0 ? 16 : mult2);
   int ppb1 = (H * W + a.nblk1 - 1) / a.nblk1;
   ppb1 = (ppb1 + pstep - 1) / pstep * pstep;
