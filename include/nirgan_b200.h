@@ -196,13 +196,19 @@ int ng_unpack_weight_grad_rowmerged(const float* packed, int32_t O, int32_t I, i
 int ng_tap_gather(const void* z, int32_t dtype, int32_t B, int32_t Hz, int32_t Wz, int32_t zc, int32_t KH, int32_t KW,
                   const float* bias, int32_t act, int32_t crop, float* out, void* stream);
 
-/* Conv2d(64 -> 1, k7) + Tanh head in ONE kernel (model/networks.py:366-368; 16-bit storage): per 8 x 16 output patch
- * the haloed 14 x 22 x 64 input patch is fetched once by TMA, the tap GEMM of the whole patch runs on tcgen05 into TMEM,
- * and the 49 shifted taps are summed from a shared-memory z tile -- z never goes to HBM (the ng_conv2d tap GEMM +
- * ng_tap_gather pair writes and re-reads it).  x_haloed: [B][H+6][W+6][64] (halo 3 already filled by ng_in_apply),
- * w_taps: [64 taps (49 used)][64 channels] as packed by ng_pack_weight for the tap GEMM, out: fp32 [B][H-2*crop][W-2*crop]. */
-int ng_head_conv(const void* x_haloed, int32_t dtype, int32_t B, int32_t H, int32_t W, const void* w_taps,
-                 const float* bias, int32_t act, int32_t crop, float* out, void* stream);
+/* Single-output-channel convolution in ONE kernel (16-bit storage): the generator head Conv2d(64 -> 1, k7) + Tanh
+ * (model/networks.py:366-368; C = 64, K = 7) and the PatchGAN's last layer Conv2d(512 -> 1, k4, p1)
+ * (model/networks.py:574-576; C = 512, K = 4).  Per 8 x 16 output patch the haloed (8+K-1) x (16+K-1) x C input patch is
+ * fetched once by TMA (64 channels per pipeline stage), the tap GEMM z[pixel][tap] of the whole patch runs on tcgen05 into
+ * TMEM, and the K*K shifted taps are summed from a shared-memory z tile -- z never goes to HBM (the ng_conv2d tap GEMM +
+ * ng_tap_gather pair writes and re-reads it; the im2col form re-reads the input once per tap).
+ * H x W: the convolution's output; pad: its padding (3 / 1); halo (<= pad): the part of the padding that is materialised
+ * in the buffer, x_haloed = [B][H+K-1-2*(pad-halo)][W+K-1-2*(pad-halo)][C] (the head's reflect halo of 3 is written by
+ * ng_in_apply; the PatchGAN buffers carry none: the rest of the padding is zeros by TMA out-of-bounds fill),
+ * w_taps: [taps stored (64 for K = 7, 16 for K = 4)][C] as packed by ng_pack_weight for the tap GEMM,
+ * out: fp32 [B][H-2*crop][W-2*crop] = act(bias + conv). */
+int ng_head_conv(const void* x_haloed, int32_t dtype, int32_t B, int32_t H, int32_t W, int32_t C, int32_t K, int32_t pad,
+                 int32_t halo, const void* w_taps, const float* bias, int32_t act, int32_t crop, float* out, void* stream);
 
 /* Backward of ng_tap_gather: dz[n][yy][xx][kh*KW+kw] = scale * dev_scale[0] * dout[n][yy-kh-crop][xx-kw-crop] * act'(out)
  * (zero outside the cropped output window; taps >= KH*KW zero).  With dz, the weight gradient of the single-channel

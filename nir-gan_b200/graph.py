@@ -97,8 +97,16 @@ class UnitGraph:
                 and u.pad == 1 and u.KW is None and u.x.pad == 0 and u.x.C % 64 == 0 and (4 * u.cout) % 64 == 0
                 and u.Hout == 2 * u.x.H and u.Wout == 2 * u.x.W and MERGE_PHASES[0])
 
+    def tap_conv(self, u: Unit) -> bool:
+        """PatchGAN last layer (512 -> 1, k4, p1; zero padding by TMA fill) through the one-kernel tap form (ng_head_conv)."""
+        return (HEAD_FUSED[0] and u.kind == "head" and self.eng.impl == L.IMPL_TC and self.eng.dt_enum != L.F32
+                and u.K == 4 and u.KW in (0, 4, None) and u.stride == 1 and u.pad == 1 and u.x.C == 512 and u.x.pad in (0, 1)
+                and u.crop == 0 and u.act == L.ACT_NONE)
+
     def weight(self, u: Unit) -> torch.Tensor:
         cin = u.x.C
+        if self.tap_conv(u):
+            return self.eng.packed_weight(u.conv.weight, "taps", 16, cin, self.stream)
         if self.merged_phases(u):
             return self.eng.packed_weight(u.conv.weight, "phasemerged", u.cout, cin, self.stream)
         if u.pack == "rowmerged" and u.direct is None:
@@ -151,6 +159,11 @@ class UnitGraph:
         for ui, u in enumerate(self.units):
             w = self.weight(u)
             pre = f"{self.tag}.{u.name}"
+            if u.kind == "head" and self.tap_conv(u):
+                plan.add("ng_head_conv", u.x.t.data_ptr(), eng.dt_enum, u.x.B, u.Hout, u.Wout, u.x.C, u.K, u.pad, u.x.pad,
+                         w.data_ptr(),
+                         u.conv.bias.data_ptr(), u.act, 0, u.out_f32.data_ptr(), label=pre)
+                continue
             if u.kind == "head":
                 a = self._args(u, u.x, w, u.out_f32, epilogue=L.EPI_HEAD, act=u.act, crop=u.crop, bias=u.conv.bias.data)
                 plan.keepalive.append(a)
@@ -226,8 +239,8 @@ class UnitGraph:
             wt = eng.packed_weight(head.weight, "taps", 64, x.C, self.stream)
             if HEAD_FUSED[0] and eng.impl == L.IMPL_TC and eng.dt_enum != L.F32 and K == 7 and x.C == 64 and x.pad == 3:
                 # one kernel: the z tile of an 8 x 16 output patch stays in TMEM / shared memory (ng_head_conv)
-                plan.add("ng_head_conv", x.t.data_ptr(), eng.dt_enum, x.B, x.H, x.W, wt.data_ptr(), head.bias.data_ptr(),
-                         L.ACT_TANH, th["crop"], out.data_ptr(), label=self.tag + ".head")
+                plan.add("ng_head_conv", x.t.data_ptr(), eng.dt_enum, x.B, x.H, x.W, 64, 7, 3, 3, wt.data_ptr(),
+                         head.bias.data_ptr(), L.ACT_TANH, th["crop"], out.data_ptr(), label=self.tag + ".head")
             else:
                 xz = ActBuf(x.t, x.B, Hz, Wz, x.C, 0)
                 z = eng.act(self.tag + ".z", x.B, Hz, Wz, 64, 0)

@@ -316,7 +316,7 @@ def test_head_fused_kernel(dtype_name, crop, H, W, B):
     outs = []
     for _ in range(2):
         out = torch.full((B * Hc * Wc,), float("nan"), device="cuda")
-        L.call("ng_head_conv", xb.t.data_ptr(), dtype, B, H, W, wt.data_ptr(), bias.data_ptr(), L.ACT_TANH, crop,
+        L.call("ng_head_conv", xb.t.data_ptr(), dtype, B, H, W, 64, 7, 3, 3, wt.data_ptr(), bias.data_ptr(), L.ACT_TANH, crop,
                out.data_ptr(), Hh.stream())
         torch.cuda.synchronize()
         outs.append(out)
@@ -328,6 +328,39 @@ def test_head_fused_kernel(dtype_name, crop, H, W, B):
     assert torch.isfinite(got).all()
     # 49 partial sums of magnitude ~0.2 rounded to 16 bits before the fp32 sum (as in the tap GEMM + gather pair)
     assert float((got - ref).abs().max()) <= (1.5e-3 if dtype == L.F16 else 1.2e-2)
+
+
+@pytest.mark.parametrize("dtype_name", ["f16", "bf16"])
+@pytest.mark.parametrize("halo", [0, 1])
+@pytest.mark.parametrize("H,W,B", [(30, 30, 3), (31, 31, 64), (8, 16, 1), (13, 45, 2), (62, 62, 20)])
+def test_patchgan_last_layer_fused_kernel(dtype_name, H, W, B, halo):
+    """ng_head_conv in its 512 -> 1, k4, p1 form (eight 64-channel K chunks accumulated in TMEM, 16 taps, zero halo) ==
+    Conv2d(512, 1, 4, 1, 1) over the same 16-bit-rounded operands; ragged patches, more tiles than CTAs, bit-exact
+    from launch to launch."""
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    dtype = L.F16 if dtype_name == "f16" else L.BF16
+    Cin, K = 512, 4
+    Hi, Wi = H + 1, W + 1                                       # input size whose k4 p1 s1 output is H x W
+    x = Hh.rnd(_gen(B, Cin, Hi, Wi, seed=5), dtype)
+    w = Hh.rnd(_gen(1, Cin, K, K, seed=6, scale=0.02), dtype)
+    bias = _gen(1, seed=7, scale=0.1)
+    xb = Hh.to_actbuf(x, halo, "zero", dtype)                   # halo 1: padding materialised; 0: all of it by TMA zero fill
+    wt = torch.zeros(16 * Cin, dtype=Hh.TORCH_DT[dtype], device="cuda")
+    L.call("ng_pack_weight", w.data_ptr(), 1, Cin, K, K, 0, 1, Cin, dtype, wt.data_ptr(), Hh.stream())
+    outs = []
+    for _ in range(2):
+        out = torch.full((B * H * W,), float("nan"), device="cuda")
+        L.call("ng_head_conv", xb.t.data_ptr(), dtype, B, H, W, Cin, K, 1, halo, wt.data_ptr(), bias.data_ptr(), L.ACT_NONE, 0,
+               out.data_ptr(), Hh.stream())
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    ref = F.conv2d(x, w, bias, padding=1)
+    assert ref.shape[-2:] == (H, W)
+    got = outs[0].view(B, 1, H, W)
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= 2e-4               # identical 16-bit operands, fp32 all the way (fp32 z tile)
 
 
 @pytest.mark.parametrize("dtype_name", ["f16", "bf16"])
