@@ -839,43 +839,50 @@ head_bwd_prep_kernel(const float* __restrict__ dout, const float* __restrict__ o
 }
 
 // Backward of ng_tap_gather: dz[n][yy][xx][t] = scale * dout[n][yy-kh-crop][xx-kw-crop] * act'(out) for t = kh*KW + kw
-// (zero outside the cropped output window and for t >= KH*KW).  One thread = one pixel x 8 taps (16 B on the 16-bit
-// paths; the 8 threads of a pixel write 128 contiguous bytes).
+// (zero outside the cropped output window and for t >= KH*KW).  A block owns a TH x TW tile of z pixels: it first builds
+// the (TH + KH - 1) x (TW + KW - 1) window of gm = scale * dout * act'(out) in shared memory (each output pixel's product
+// computed once instead of once per tap), then one thread per z pixel writes that pixel's ZC taps -- 128 contiguous bytes
+// on the 16-bit paths, the tap -> (kh, kw) mapping resolved at compile time.  (The first form, a thread per pixel and 8
+// taps with the index arithmetic per tap, ran at 0.31 ms for the 326 MB it writes; bound by instruction issue.)
 template <typename T, int KH, int KW, int ZC>
 __global__ void __launch_bounds__(256)
 tap_scatter_kernel(const float* __restrict__ dout, const float* __restrict__ out, int B, int Hz, int Wz, int act, int crop,
                    float scale, const float* __restrict__ dev_scale, T* __restrict__ dz) {
-  constexpr int G8 = ZC / 8;
+  constexpr int TH = 8, TW = 32, GH = TH + KH - 1, GW = TW + KW - 1;
+  __shared__ float gm[GH][GW + 1];
   const int Hc = Hz - KH + 1 - 2 * crop, Wc = Wz - KW + 1 - 2 * crop;
   if (dev_scale) scale *= dev_scale[0];
-  const unsigned total = (unsigned)B * Hz * Wz * G8;          // < 2^31 (checked by the launcher): 32-bit index arithmetic
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int g8 = (int)(i % G8);
-    unsigned p = i / G8;
-    const unsigned row = p / (unsigned)Wz;
-    const int xx = (int)(p - row * Wz);
-    const int n = (int)(row / (unsigned)Hz);
-    const int yy = (int)(row - (unsigned)n * Hz);
-    const float* dn = dout + (size_t)n * Hc * Wc;
-    const float* on = out + (size_t)n * Hc * Wc;
+  const int n = blockIdx.z, ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+  const float* dn = dout + (size_t)n * Hc * Wc;
+  const float* on = out + (size_t)n * Hc * Wc;
+  for (int i = threadIdx.x; i < GH * GW; i += 256) {
+    const int ly = i / GW, lx = i - ly * GW;
+    const int yc = ty0 - (KH - 1) - crop + ly, xc = tx0 - (KW - 1) - crop + lx;
+    float v = 0.f;
+    if ((unsigned)yc < (unsigned)Hc && (unsigned)xc < (unsigned)Wc) {
+      const int o = yc * Wc + xc;
+      v = __ldg(dn + o) * scale;
+      if (act == NG_ACT_TANH) { const float tv = __ldg(on + o); v *= (1.f - tv * tv); }
+      // 16-bit gradient storage: saturate instead of overflowing to inf
+      if constexpr (sizeof(T) == 2) v = fminf(fmaxf(v, -3.0e4f), 3.0e4f);
+    }
+    gm[ly][lx] = v;
+  }
+  __syncthreads();
+  const int py = threadIdx.x / TW, px = threadIdx.x - py * TW;
+  const int yy = ty0 + py, xx = tx0 + px;
+  if (yy >= Hz || xx >= Wz) return;
+  T* d = dz + (((size_t)n * Hz + yy) * Wz + xx) * ZC;
+#pragma unroll
+  for (int g8 = 0; g8 < ZC / 8; ++g8) {
     float f[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int t = g8 * 8 + k;
-      float v = 0.f;
-      if (t < KH * KW) {
-        const int kh = t / KW, kw = t - kh * KW;
-        const int yc = yy - kh - crop, xc = xx - kw - crop;
-        if (yc >= 0 && yc < Hc && xc >= 0 && xc < Wc) {
-          const int o = yc * Wc + xc;
-          v = __ldg(dn + o) * scale;
-          if (act == NG_ACT_TANH) { const float tv = __ldg(on + o); v *= (1.f - tv * tv); }
-          if constexpr (sizeof(T) == 2) v = fminf(fmaxf(v, -3.0e4f), 3.0e4f);
-        }
-      }
-      f[k] = v;
+      constexpr int dummy = 0; (void)dummy;
+      const int t = g8 * 8 + k;                       // compile-time after unrolling
+      f[k] = t < KH * KW ? gm[py + (KH - 1) - t / KW][px + (KW - 1) - t % KW] : 0.f;
     }
-    st8<T>(dz + (size_t)i * 8, f);
+    st8<T>(d + g8 * 8, f);
   }
 }
 
@@ -1251,7 +1258,9 @@ extern "C" int ng_tap_scatter(const float* dout, const float* out, int32_t B, in
   NG_REQUIRE(KH == 7 && KW == 7 && zc == 64, NG_E_UNSUPPORTED, "tap_scatter: built for 7x7 taps over 64 stored channels");
   NG_REQUIRE(Hz - KH + 1 - 2 * crop > 0 && Wz - KW + 1 - 2 * crop > 0, NG_E_SHAPE, "tap_scatter: empty output");
   NG_REQUIRE((long long)B * Hz * Wz * 8 < (1ll << 31), NG_E_SHAPE, "tap_scatter: batch too large for 32-bit indexing");
-  DISPATCH_T(dtype, (tap_scatter_kernel<T, 7, 7, 64><<<grid_cap((long long)B * Hz * Wz * 8), 256, 0, (cudaStream_t)stream>>>(
+  NG_REQUIRE(B <= 65535, NG_E_SHAPE, "tap_scatter: batch %d exceeds the grid's z extent", B);
+  const dim3 grid((unsigned)((Wz + 31) / 32), (unsigned)((Hz + 7) / 8), (unsigned)B);
+  DISPATCH_T(dtype, (tap_scatter_kernel<T, 7, 7, 64><<<grid, 256, 0, (cudaStream_t)stream>>>(
                         dout, out, B, Hz, Wz, act, crop, scale, dev_scale, (T*)dz)));
   NG_LAUNCH_CHECK("tap_scatter_kernel");
   return NG_OK;

@@ -330,6 +330,34 @@ def test_head_fused_kernel(dtype_name, crop, H, W, B):
     assert float((got - ref).abs().max()) <= (1.5e-3 if dtype == L.F16 else 1.2e-2)
 
 
+@pytest.mark.parametrize("dtype_name", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("crop,H,W,B", [(0, 32, 32, 2), (10, 44, 44, 2), (3, 37, 61, 3), (0, 8, 8, 1)])
+def test_tap_scatter_matches_definition(dtype_name, crop, H, W, B):
+    """ng_tap_scatter (adjoint of the head's tap gather, tiled through shared memory):
+    dz[n][yy][xx][kh*7+kw] = scale * dout[n][yy-kh-crop][xx-kw-crop] * (1 - out^2), zero outside the cropped window and
+    for the 15 padding taps; H x W = the head conv's output before the crop."""
+    from nirgan_b200 import _lib as L
+    import helpers as Hh
+    dtype = {"f32": L.F32, "f16": L.F16, "bf16": L.BF16}[dtype_name]
+    Hz, Wz, Hc, Wc = H + 6, W + 6, H - 2 * crop, W - 2 * crop
+    dout = _gen(B, Hc, Wc, seed=3)
+    out = torch.tanh(_gen(B, Hc, Wc, seed=4))
+    dev_scale = torch.tensor([0.5], device="cuda")
+    dz = torch.full((B * Hz * Wz * 64,), float("nan"), device="cuda").to(Hh.TORCH_DT[dtype])
+    L.call("ng_tap_scatter", dout.data_ptr(), out.data_ptr(), B, Hz, Wz, 64, 7, 7, L.ACT_TANH, crop, 3.0, dev_scale.data_ptr(),
+           dtype, dz.data_ptr(), Hh.stream())
+    torch.cuda.synchronize()
+    gm = 1.5 * dout * (1 - out * out)
+    ref = torch.zeros(B, Hz, Wz, 64, device="cuda")
+    for kh in range(7):
+        for kw in range(7):
+            ref[:, kh + crop:kh + crop + Hc, kw + crop:kw + crop + Wc, kh * 7 + kw] = gm
+    got = dz.view(B, Hz, Wz, 64).float()
+    assert bool(torch.isfinite(got).all())
+    tol = 1e-6 if dtype == L.F32 else (2.0 ** -10 if dtype == L.F16 else 2.0 ** -7)
+    assert float((got - ref).abs().max()) <= tol * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("dtype_name", ["f16", "bf16"])
 @pytest.mark.parametrize("halo", [0, 1])
 @pytest.mark.parametrize("H,W,B", [(30, 30, 3), (31, 31, 64), (8, 16, 1), (13, 45, 2), (62, 62, 20)])
