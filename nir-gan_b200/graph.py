@@ -35,6 +35,8 @@ FUSED_FINALIZE = [_os.environ.get("NIRGAN_B200_FUSED_FINALIZE", "0") == "1"]
 # normalised unit is two launches (conv, apply) and the plan starts with ONE memset of all its accumulators.
 # NIRGAN_B200_STAT_ACC=0: per-tile fp32 partials + an ng_in_stats_finalize launch per unit (round-1 form).
 # Conv2d(64 -> 1, k7) + Tanh head as one kernel (ng_head_conv); NIRGAN_B200_HEAD_FUSED=0 keeps the tap GEMM + gather pair
+# data gradient of the 64-input-channel stride-2 convolution in merged-phase form; NIRGAN_B200_DGRAD_MERGED=0: phased form
+DGRAD_MERGED = [_os.environ.get("NIRGAN_B200_DGRAD_MERGED", "1") != "0"]
 HEAD_FUSED = [_os.environ.get("NIRGAN_B200_HEAD_FUSED", "1") != "0"]
 STAT_ACC = [_os.environ.get("NIRGAN_B200_STAT_ACC", "1") != "0"]
 
@@ -266,10 +268,22 @@ class UnitGraph:
                 self.eng.packed_weight(th["conv"].weight, "taps_T", th["x"].C, 64, self.stream)
 
     # ---- backward -------------------------------------------------------------------------------------
+    def dgrad_merged(self, u: Unit) -> bool:
+        """Data gradient of Conv2d(k3, s2, p1) = ConvTranspose2d(k3, s2, p1, op1) of dY with the SAME weight tensor read as
+        (in = Cout, out = Cin, 3, 3): the merged-phase form of the forward up-convolutions applies (the four output
+        parities as GEMM-N = 4 * Cin instead of four launches-in-one of N = Cin MMAs).  Taken where it is wider than the
+        plain phased form: Cin = 64 (d1: N = 64 -> 256, 0.30 -> 0.2 ms); at Cin >= 128 the phased form is already N >= 128."""
+        return (DGRAD_MERGED[0] and MERGE_PHASES[0] and u.form != L.FORM_PHASED and self.eng.impl == L.IMPL_TC
+                and self.eng.dt_enum != L.F32 and u.kind == "norm" and u.K == 3 and u.stride == 2 and u.pad == 1
+                and u.KW is None and u.x.pad == 0 and u.x.C == 64 and u.cout % 64 == 0
+                and u.x.H == 2 * u.Hout and u.x.W == 2 * u.Wout)
+
     def _dgrad_weight(self, u: Unit) -> torch.Tensor:
         """Weights re-packed for the data gradient: roles of Cin / Cout swapped."""
         w = u.conv.weight
         cin = u.x.C
+        if self.dgrad_merged(u):
+            return self.eng.packed_weight(w, "phasemerged", cin, u.cout, self.stream)
         if u.pack == "s2d":                         # space-to-depth input layer: n = the 64 input slots, k = Cout
             return self.eng.packed_weight(w, "s2d_T", cin, u.cout, self.stream)
         if u.form == L.FORM_PHASED:                 # ConvTranspose2d (Cin, Cout, k, k): n = Cin, k = Cout
@@ -448,7 +462,8 @@ class UnitGraph:
             if u.form == L.FORM_PHASED:            # ConvTranspose -> stride-2 conv of dY
                 a = eng.conv_args(dyb, wd, g.t, xin.C, u.K, 2, u.pad, Hg, Wg)
             elif u.stride == 2:                     # strided conv -> phased transposed conv
-                a = eng.conv_args(dyb, wd, g.t, xin.C, u.K, 2, u.pad, Hg, Wg, form=L.FORM_PHASED)
+                a = eng.conv_args(dyb, wd, g.t, xin.C, u.K, 2, u.pad, Hg, Wg,
+                                  form=L.FORM_PHASED_MERGED if self.dgrad_merged(u) else L.FORM_PHASED)
             else:                                   # stride-1 conv -> flipped full correlation
                 # haloed input (in_pad == pad): gradient of the haloed buffer, pad 0;  zero-padded input: pad = pad
                 eff_pad = 0 if xin.pad == u.pad else u.pad
