@@ -32,9 +32,14 @@
  *   ng_adam_step / ng_adam_multi
  *                      torch.optim.Adam model/pix2pix.py:486-487 (one launch per optimizer over a flat arena)
  *   ng_in_bwd          autograd of the InstanceNorm / inject / activation / residual / halo unit above
- *   ng_prep_stem / ng_tap_gather / ng_tap_scatter / ng_head_bwd_prep
- *                      ReflectionPad2d(3) + Conv2d(3, 64, 7) input staging and the Conv2d(64, 1, 7) + Tanh head
- *                      (model/networks.py:341-342,367-368) and their adjoints, incl. the wrapper's pad / crop
+ *   ng_stem_conv / ng_prep_stem
+ *                      F.pad(reflect) + ReflectionPad2d(3) + Conv2d(3, 64, 7) straight from the fp32 tiles
+ *                      (model/pix2pix.py:91-93, model/networks.py:341-342); ng_prep_stem: the row-merged tensor the
+ *                      stem's weight gradient contracts over
+ *   ng_head_conv / ng_tap_gather / ng_tap_scatter / ng_head_bwd_prep
+ *                      the single-output-channel layers: Conv2d(64, 1, 7) + Tanh head (model/networks.py:366-368) and the
+ *                      PatchGAN logit Conv2d(512, 1, 4, 1, 1) (model/networks.py:574-576) in one kernel; the two-kernel
+ *                      form of the head and the adjoints, incl. the wrapper's crop
  *   ng_rs_pixel_losses / ng_rs_index
  *                      L1Loss model/pix2pix.py:60,222 + all six RemoteSensingIndices, criterion l1 / l2,
  *                      loss / logging / index modes utils/remote_sensing_indices.py:23-319 (forward and d/dpred)
