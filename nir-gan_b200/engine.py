@@ -464,7 +464,8 @@ class Plan:
         dev = torch.cuda.current_device()
         side = _SIDE.get(dev)
         if side is None:
-            side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+            # NIRGAN_B200_SIDE_PRIORITY=-1: high-priority side stream (experiment; default: same priority as the caller's)
+            side = _SIDE[dev] = torch.cuda.Stream(device=dev, priority=int(os.environ.get("NIRGAN_B200_SIDE_PRIORITY", "0")))
         main = torch.cuda.ExternalStream(stream_ptr, device=dev) if stream_ptr else torch.cuda.default_stream(dev)
         n_side = sum(1 for i in idx if self.side[i])
         while len(self._events) < n_side + 1:

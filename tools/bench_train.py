@@ -43,6 +43,14 @@ def main():
     batch = {"rgb": torch.rand(args.batch, 3, args.tile, args.tile, generator=g).to(dev),
              "nir": torch.rand(args.batch, 1, args.tile, args.tile, generator=g).to(dev)}
 
+    # NIRGAN_B200_HP_STREAM=1: run the step on a high-priority stream (the weight-gradient side stream keeps the default
+    # priority), so that the main-stream kernels are dispatched first when both streams have work
+    import os
+    hp = torch.cuda.Stream(dev, priority=-1) if os.environ.get("NIRGAN_B200_HP_STREAM", "0") == "1" else None
+    if hp is not None:
+        hp.wait_stream(torch.cuda.current_stream(dev))
+        torch.cuda.set_stream(hp)
+
     def step():
         return trainer.step(batch)
 
