@@ -1173,6 +1173,20 @@ extern "C" int ng_in_bwd(void* g_halo, int32_t g_pad, int32_t halo_mode, const v
       return NG_OK;
     }
   }
+  // Lean form: optionally fold the reflect halo once, in place, before the two passes (the pre-pass of the staged form) so
+  // that neither pass carries the per-pixel border test and the extra loads.  NIRGAN_B200_BWD_PREFOLD (default 1).
+  {
+    static const bool prefold = [] { const char* e = getenv("NIRGAN_B200_BWD_PREFOLD"); return !(e && e[0] == '0'); }();
+    const long long big = (long long)(H + 2 * a.gp) * (W + 2 * a.gp) * C;
+    if (prefold && dtype != NG_F32 && mean_rstd && inject_mode == NG_INJECT_NONE && dscale == nullptr && de_map == nullptr &&
+        g_halo && halo_mode == NG_HALO_REFLECT && a.gp > 0 && big < (1ll << 31) && (256 >> a.c8_shift) < W &&
+        (act == NG_ACT_RELU || act == NG_ACT_NONE || act == NG_ACT_LRELU)) {
+      const long long items = (long long)B * (2 * a.gp * W + (H - 2 * a.gp) * 2 * a.gp) * (C / 8);
+      DISPATCH_T16(dtype, (fold_halo_kernel<T><<<grid_cap(items), 256, 0, st>>>(a, (T*)g_halo)));
+      NG_LAUNCH_CHECK("fold_halo_kernel");
+      a.halo_mode = NG_HALO_ZERO;
+    }
+  }
   // Image-chunked schedule for normalised units: pass 1 and pass 2 of a chunk of images run back to back, with the chunk
   // sized so that what pass 1 streamed (g + y [+ skip]) is still in the 126 MB L2 when pass 2 re-reads it -- the second
   // read of every unit then comes from L2 instead of HBM.  Measured SLOWER at every chunk size (r2o: 19.30 ms per training
