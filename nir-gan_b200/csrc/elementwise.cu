@@ -461,8 +461,8 @@ __device__ __forceinline__ uint32_t relu_packed(uint32_t w, bool bf16) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <typename T, int UNROLL, bool HAS_RES, bool RELU>
-__global__ void __launch_bounds__(256, 3)
+template <typename T, int UNROLL, bool HAS_RES, bool RELU, int MINB = 3>
+__global__ void __launch_bounds__(256, MINB)
 in_apply_fast_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, const float* __restrict__ mr,
                      const long long* __restrict__ acc, float* __restrict__ mr_out, const T* __restrict__ res,
                      int res_pad, T* __restrict__ out, int op, int reflect, int ppb, int pf) {
@@ -1137,10 +1137,19 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
       (long long)(H + 2 * (residual ? res_pad : 0)) * (W + 2 * (residual ? res_pad : 0)) * C < (1ll << 31) &&
       (long long)Ho * Wo * C < (1ll << 31)) {              // 32-bit element offsets inside one image
     const int reflect = halo_mode == NG_HALO_REFLECT ? 1 : 0;
-#define NG_FAST(TT, RES, RL)                                                                                         \
-    in_apply_fast_kernel<TT, 4, RES, RL><<<grid, 256, 0, (cudaStream_t)stream>>>(                                      \
+    // NIRGAN_B200_APPLY_VARIANT: 0 = four 16-byte items in flight per thread at 3 blocks / SM (default), 1 = eight at 2,
+    // 2 = four at 4 (<= 64 registers), 3 = two at 4
+    static const int variant = [] { const char* e = getenv("NIRGAN_B200_APPLY_VARIANT"); return e ? atoi(e) : 0; }();
+#define NG_FAST_ARGS(TT)                                                                                             \
         (const TT*)y, H, W, C, c8_shift, mean_rstd, (const long long*)stat_acc, mean_rstd_out, (const TT*)residual,    \
-        res_pad, (TT*)out, out_pad, reflect, ppb, apply_pf)
+        res_pad, (TT*)out, out_pad, reflect, ppb, apply_pf
+#define NG_FAST(TT, RES, RL)                                                                                         \
+    do {                                                                                                             \
+      if (variant == 1) in_apply_fast_kernel<TT, 8, RES, RL, 2><<<grid, 256, 0, (cudaStream_t)stream>>>(NG_FAST_ARGS(TT));      \
+      else if (variant == 2) in_apply_fast_kernel<TT, 4, RES, RL, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(NG_FAST_ARGS(TT)); \
+      else if (variant == 3) in_apply_fast_kernel<TT, 2, RES, RL, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(NG_FAST_ARGS(TT)); \
+      else in_apply_fast_kernel<TT, 4, RES, RL, 3><<<grid, 256, 0, (cudaStream_t)stream>>>(NG_FAST_ARGS(TT));                   \
+    } while (0)
 #define NG_FAST_T(TT)                                                                                                \
     do {                                                                                                             \
       if (residual) { if (act == NG_ACT_RELU) NG_FAST(TT, true, true); else NG_FAST(TT, true, false); }             \
@@ -1149,6 +1158,7 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
     if (dtype == NG_F16) NG_FAST_T(__half); else NG_FAST_T(__nv_bfloat16);
 #undef NG_FAST_T
 #undef NG_FAST
+#undef NG_FAST_ARGS
     NG_LAUNCH_CHECK("in_apply_fast_kernel");
     return NG_OK;
   }
