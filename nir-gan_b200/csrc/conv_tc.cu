@@ -72,6 +72,23 @@ constexpr int RT_PATCH_ROWS = (RT_BH + RT_KH - 1) * RT_BW;          // 224 pixel
 constexpr int DS_WIN_W = RT_BW + 8;                                  // 22 source columns + 2 (8-byte row alignment)
 constexpr int DS_SCRATCH_BYTES = (RT_BH + RT_KH - 1) * DS_WIN_W * 8;
 
+// Merged phases: virtual channel block ("slot") s of the 4 * Cout_real outputs holds output parity
+// (pa, pb) = (s >> 1, (s & 1) ^ (s >> 1)) -- Gray order (0,0), (0,1), (1,1), (1,0) -- so that the slots an input shift
+// (sy, sx) contributes to (pa >= sy and pb >= sx) are always CONTIGUOUS: shift (0,0) -> slots 0..3, (0,1) -> 1..2,
+// (1,0) -> 2..3, (1,1) -> 2.  The banded form multiplies each shift by exactly that band: one N = band x Cout_real MMA
+// chain per K chunk instead of N = 4 x Cout_real with 7 of 16 slabs structurally zero.
+__host__ __device__ __forceinline__ bool merged_slot_uses_shift(int slot, int tp) {
+  const int pa = slot >> 1, pb = (slot & 1) ^ (slot >> 1);
+  return pa >= (tp >> 1) && pb >= (tp & 1);
+}
+// band of used slots inside [ph_lo, ph_lo + nph) for shift tp: l in [lo, hi) relative to ph_lo (lo == hi: none)
+__device__ __forceinline__ void merged_band(int tp, int ph_lo, int nph, int& lo, int& hi) {
+  lo = nph; hi = 0;
+  for (int l = 0; l < nph; ++l)
+    if (merged_slot_uses_shift(ph_lo + l, tp)) { if (l < lo) lo = l; hi = l + 1; }
+  if (hi == 0) lo = 0;
+}
+
 template <int BN, int KC, bool RT = false, int EGW = 2, bool DS = false>
 struct TcCfg {
   static constexpr int A_BYTES = RT ? RT_PATCH_ROWS * KC * 2 : 128 * KC * 2;
@@ -216,10 +233,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t used = 0;
           const bool sparse = g.merged && p.sparse_merged;
           const int Cr = g.Cout_real, nph = sparse ? BN / Cr : 0, ph_lo = sparse ? (cot * BN) / Cr : 0;
-          for (int l = 0; l < nph; ++l) {
-            const int phs = ph_lo + l;
-            if ((phs >> 1) >= (tp >> 1) && (phs & 1) >= (tp & 1)) used |= 1u << l;
-          }
+          for (int l = 0; l < nph; ++l)
+            if (merged_slot_uses_shift(ph_lo + l, tp)) used |= 1u << l;
           if (sparse && used == 0) continue;
           for (int c = 0; c < chunks; ++c) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);       // free in every CTA of the cluster
@@ -282,6 +297,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++as == 2) { as = 0; as_phase ^= 1; }
           continue;
         }
+        if (g.merged && p.sparse_merged == 2) {
+          // banded merged phases: per shift ONE MMA chain over the contiguous band of slots that use it
+          const int Cr = g.Cout_real, nph = BN / Cr;
+          const int cot = (q / p.groups_per) / g.nphase, ph_lo = (cot * BN) / Cr;
+          int kit = 0;
+          for (int tp = 0; tp < g.ntaps; ++tp) {
+            int lo, hi;
+            merged_band(tp, ph_lo, nph, lo, hi);
+            if (hi == lo) continue;
+            const uint32_t idesc_b = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(((hi - lo) * Cr) >> 3) << 17);
+            for (int c = 0; c < chunks; ++c, ++kit) {
+              mbar_wait(smem_u32(&full_bar[stage]), phase);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
+              const uint64_t adesc = make_kmajor_desc(sa, SBO, LAYOUT);
+              const uint64_t bdesc = make_kmajor_desc(sa + Cfg::A_BYTES + lo * (Cr * KC * 2), SBO, LAYOUT);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)       // shift 0 covers every slot of the tile: first MMA at kit == 0
+                umma_f16(tmem_c + lo * Cr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc_b,
+                         (uint32_t)((kit | k) != 0));
+              umma_commit(smem_u32(&empty_bar[stage]));
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          umma_commit(smem_u32(&tfull_bar[as]));
+          if (++as == 2) { as = 0; as_phase ^= 1; }
+          continue;
+        }
         if (g.merged && p.sparse_merged) {
           // sparse merged phases (see the producer): one N = Cout_real MMA chain per (shift, phase) slab that is not
           // identically zero, each phase accumulating in its own TMEM column block
@@ -291,10 +334,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           int kit = 0;
           for (int tp = 0; tp < g.ntaps; ++tp) {
             uint32_t used = 0;
-            for (int l = 0; l < nph; ++l) {
-              const int phs = ph_lo + l;
-              if ((phs >> 1) >= (tp >> 1) && (phs & 1) >= (tp & 1)) used |= 1u << l;
-            }
+            for (int l = 0; l < nph; ++l)
+              if (merged_slot_uses_shift(ph_lo + l, tp)) used |= 1u << l;
             if (used == 0) continue;
             for (int c = 0; c < chunks; ++c, ++kit) {
               mbar_wait(smem_u32(&full_bar[stage]), phase);
@@ -505,7 +546,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (g.merged) {
             phase_id = c_first / g.Cout_real;
             c_first -= phase_id * g.Cout_real;
-            chan_off = ((long long)(phase_id >> 1) * g.Wout + (phase_id & 1)) * g.Cout_real + c_first;
+            chan_off = ((long long)(phase_id >> 1) * g.Wout + ((phase_id & 1) ^ (phase_id >> 1))) * g.Cout_real + c_first;
           }
           {
             uint32_t r[32];
@@ -787,8 +828,13 @@ static int launch_tc(const ng_conv_args& a, const ConvGeom& g, cudaStream_t st) 
   // ConvTranspose is SLOWER than the dense N = 256 form (u2 0.142 -> 0.203 ms, u1 0.110 -> 0.121 ms per 32 tiles): an
   // N = 64 tcgen05.mma re-reads the whole 128-row A tile from shared memory for a quarter of the columns, so the 72
   // narrow MMAs cost more than the 32 wide ones they replace.  Kept as a tested switch.
+  // NIRGAN_B200_SPARSE_MERGED: 0 (default) = dense N = 4 * Cout_real, 1 = one N = Cout_real chain per non-zero slab (the
+  // slower form above), 2 = banded: with the slots in Gray order every shift's slots are contiguous, so each shift is ONE
+  // chain of N = 256 / 128 / 128 / 64 (Cout_real = 64) instead of four times N = 256 -- a third fewer tensor-pipe cycles,
+  // but no faster (r3u: u2 0.163-0.185 vs 0.153 ms, u1 0.107-0.116 vs 0.114 ms): these short-K tiles are bound by the
+  // accumulator drain and the 268 MB of output, not by the MMAs.
   static const int sparse_env = [] { const char* v = getenv("NIRGAN_B200_SPARSE_MERGED"); return v ? atoi(v) : 0; }();
-  p.sparse_merged = (g.merged && sparse_env && CS == 1) ? 1 : 0;
+  p.sparse_merged = (g.merged && sparse_env && CS == 1) ? sparse_env : 0;
   p.arrivals_per_image = p.patches_y * p.patches_x * g.nphase * p.co_tiles * Cfg::EGT;
   p.inv_count = 1.0f / ((float)g.Hout * (float)g.Wout);
 

@@ -37,7 +37,8 @@ __global__ void pack_phasemerged_kernel(const float* __restrict__ src, int Cin, 
     long long r = i / Cin;
     const int co = (int)(r % Cout); r /= Cout;
     const int ph = (int)(r % 4), sh = (int)(r / 4);
-    const int pa = ph >> 1, pb = ph & 1, sy = sh >> 1, sx = sh & 1;
+    // slot ph of the virtual channels = output parity in Gray order (0,0), (0,1), (1,1), (1,0): see conv_tc.cu
+    const int pa = ph >> 1, pb = (ph & 1) ^ (ph >> 1), sy = sh >> 1, sx = sh & 1;
     const int kh = pa + 1 - 2 * sy, kw = pb + 1 - 2 * sx;
     float v = 0.f;
     if (kh >= 0 && kh < 3 && kw >= 0 && kw < 3) v = src[(((long long)ci * Cout + co) * 3 + kh) * 3 + kw];
