@@ -462,11 +462,12 @@ __device__ __forceinline__ uint32_t relu_packed(uint32_t w, bool bf16) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <typename T, int UNROLL, bool HAS_RES, bool RELU, int MINB = 3>
+template <typename T, int UNROLL, bool HAS_RES, bool RELU, int MINB = 3, bool INJ = false>
 __global__ void __launch_bounds__(256, MINB)
 in_apply_fast_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift, const float* __restrict__ mr,
                      const long long* __restrict__ acc, float* __restrict__ mr_out, const T* __restrict__ res,
-                     int res_pad, T* __restrict__ out, int op, int reflect, int ppb, int pf) {
+                     int res_pad, T* __restrict__ out, int op, int reflect, int ppb, int pf,
+                     const float* __restrict__ inj = nullptr, int inj_mode = 0, const float* __restrict__ inj_scale = nullptr) {
   static_assert(sizeof(T) == 2, "16-bit storage only");
   constexpr bool BF = std::is_same<T, __nv_bfloat16>::value;
   const int Ho = H + 2 * op, Wo = W + 2 * op, C8 = C >> 3;
@@ -513,10 +514,15 @@ in_apply_fast_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift,
   int pp = p_begin + (threadIdx.x >> c8_shift);
   int yo = pp / Wo, xo = pp - yo * Wo;
   const int adv_y = pstep / Wo, adv_x = pstep - adv_y * Wo;      // pstep pixels = adv_y rows + adv_x columns
+  // SatCLIP injection (the d1 unit): u = xh * (1 + s * e) | xh + s * e | xh * e with e the bilinear sample of the
+  // 128 x 128 embedding map at the SOURCE pixel (generator_inject.py:113-127)
+  const float* injn = INJ ? inj + (size_t)n * 128 * 128 : nullptr;
+  const float inj_s = (INJ && inj_scale) ? *inj_scale : 1.f;
   while (pp < p_end) {
     uint4 raw[UNROLL], rres[HAS_RES ? UNROLL : 1];
     int ok[UNROLL];
     int ooff[UNROLL];
+    int ysrc[INJ ? UNROLL : 1], xsrc[INJ ? UNROLL : 1];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       int ys = yo - op, xs = xo - op;
@@ -529,6 +535,7 @@ in_apply_fast_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift,
       }
       ok[u] = pp < p_end ? (inside ? 1 : 2) : 0;                 // 1 = compute, 2 = zero halo, 0 = past the block
       ooff[u] = pp * C;
+      if constexpr (INJ) { ysrc[u] = ys; xsrc[u] = xs; }
       if (inside) {
         raw[u] = ldg_stream16(ybase + (ys * W + xs) * C);
         if constexpr (HAS_RES) rres[u] = ldg_stream16(rbase + (ys * Wr + xs) * C);
@@ -545,6 +552,13 @@ in_apply_fast_kernel(const T* __restrict__ y, int H, int W, int C, int c8_shift,
         unpack8<T>(raw[u], f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], sa[k], sb[k]);
+        if constexpr (INJ) {
+          const float ev = bilerp128(injn, ysrc[u], xsrc[u], H, W);
+          const float fac = inj_mode == NG_INJECT_MUL_SCALED ? 1.f + inj_s * ev : (inj_mode == NG_INJECT_MUL ? ev : 1.f);
+          const float add = inj_mode == NG_INJECT_ADD ? inj_s * ev : 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = fmaf(f[k], fac, add);
+        }
         if constexpr (HAS_RES) {
           float rv[8];
           unpack8<T>(rres[u], rv);
@@ -1134,7 +1148,8 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
   // lean kernel for the common case (see in_apply_fast_kernel); NIRGAN_B200_APPLY_FAST=0 keeps the generic one
   static const bool fast_on = [] { const char* e = getenv("NIRGAN_B200_APPLY_FAST"); return !(e && e[0] == '0'); }();
   const bool has_inj0 = inject_mode != NG_INJECT_NONE;
-  if (fast_on && dtype != NG_F32 && !has_inj0 && (mean_rstd || stat_acc) && (act == NG_ACT_RELU || act == NG_ACT_NONE) &&
+  if (fast_on && dtype != NG_F32 && (!has_inj0 || residual == nullptr) && (mean_rstd || stat_acc) &&
+      (act == NG_ACT_RELU || act == NG_ACT_NONE) &&
       (long long)(H + 2 * (residual ? res_pad : 0)) * (W + 2 * (residual ? res_pad : 0)) * C < (1ll << 31) &&
       (long long)Ho * Wo * C < (1ll << 31)) {              // 32-bit element offsets inside one image
     const int reflect = halo_mode == NG_HALO_REFLECT ? 1 : 0;
@@ -1151,13 +1166,18 @@ extern "C" int ng_in_apply(const void* y, int32_t dtype, int32_t B, int32_t H, i
       else if (variant == 3) in_apply_fast_kernel<TT, 2, RES, RL, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(NG_FAST_ARGS(TT)); \
       else in_apply_fast_kernel<TT, 4, RES, RL, 3><<<grid, 256, 0, (cudaStream_t)stream>>>(NG_FAST_ARGS(TT));                   \
     } while (0)
+#define NG_FAST_INJ(TT, RL)                                                                                          \
+    in_apply_fast_kernel<TT, 4, false, RL, 3, true><<<grid, 256, 0, (cudaStream_t)stream>>>(NG_FAST_ARGS(TT), inject_e,    \
+                                                                                           inject_mode, inject_scale)
 #define NG_FAST_T(TT)                                                                                                \
     do {                                                                                                             \
-      if (residual) { if (act == NG_ACT_RELU) NG_FAST(TT, true, true); else NG_FAST(TT, true, false); }             \
+      if (has_inj0) { if (act == NG_ACT_RELU) NG_FAST_INJ(TT, true); else NG_FAST_INJ(TT, false); }                 \
+      else if (residual) { if (act == NG_ACT_RELU) NG_FAST(TT, true, true); else NG_FAST(TT, true, false); }        \
       else { if (act == NG_ACT_RELU) NG_FAST(TT, false, true); else NG_FAST(TT, false, false); }                    \
     } while (0)
     if (dtype == NG_F16) NG_FAST_T(__half); else NG_FAST_T(__nv_bfloat16);
 #undef NG_FAST_T
+#undef NG_FAST_INJ
 #undef NG_FAST
 #undef NG_FAST_ARGS
     NG_LAUNCH_CHECK("in_apply_fast_kernel");
